@@ -1,0 +1,54 @@
+"""Regenerate tests/golden/*.npz from the IMPORTED reference (build container only).
+
+TEST INFRASTRUCTURE.  Run:  python -m oracle.gen_golden
+The reference's own code (captioning/models/hf_wrapper.py at /root/reference) is executed on
+CPU with seeded synthetic clips and the seeded 'trained-like' weights of
+oracle.caption_model.build_effb2_trm; only ``efficientnet_pytorch`` is substituted by the
+restatement in oracle/efficientnet_b2.py (the package is absent from the image).  The outputs
+are the golden vectors the oracle restatement AND the CUDA path are checked against.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import caption_model as cm
+from . import ref_import
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def effb2_trm(seed=1, batch=8, n=160000):
+    hf = ref_import.load("captioning.models.hf_wrapper")
+    orc = cm.build_effb2_trm(seed)
+    ref = hf.Effb2TrmCaptioningModel(hf.Effb2TrmConfig()).eval()
+    ref.load_state_dict(orc.state_dict(), strict=True)
+    wav, lens = cm.synth_wav(batch, n, seed=7, ragged=True, varied=True)
+    base = {"wav": wav, "wav_len": lens, "specaug": False, "mode": "inference", "temp": 1.0, "max_length": 20}
+    with torch.no_grad():
+        enc = ref.model.model.encoder
+        lms = enc.db_transform(enc.melspec_extractor(wav))
+        g = ref.model(dict(base, sample_method="greedy"))
+        b3 = ref(wav, lens, sample_method="beam", beam_size=3)
+        b2 = ref(wav, lens, sample_method="beam", beam_size=2, max_length=12)
+    steps = int((g["seq"] != 2).any(0).nonzero().max().item()) + 1 if (g["seq"] != 2).any() else 1
+    np.savez_compressed(
+        os.path.join(OUT, "effb2_trm.npz"),
+        seed=seed, batch=batch, n_samples=n, wav_seed=7,
+        bn_stats=cm.bn_stats_vector(orc.encoder).numpy(),
+        wav_len=lens.numpy(),
+        lms_stride=np.array([1, 7]),                       # lms[:, ::1, ::7] keeps the file small
+        lms=lms[:, :, ::7].numpy(),
+        lms_max=lms.max().item(),
+        attn_emb=g["attn_emb"][:3].numpy(),   # first 3 clips only (file size)
+         attn_emb_len=g["attn_emb_len"].numpy(), fc_emb=g["fc_emb"].numpy(),
+        greedy_seq=g["seq"].numpy(), greedy_logit0=g["logit"][:, :2].numpy(),
+        greedy_logprob=g["sampled_logprob"].numpy(), greedy_embed0=g["embed"][:, :2].numpy(),
+        beam3_seq=b3.numpy(), beam2_len12_seq=b2.numpy(),
+    )
+    print("effb2_trm greedy\n", g["seq"], "\nbeam3\n", b3, "\nbeam2/12\n", b2)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    effb2_trm()
