@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI declared in include/audiocaption_b200.h.
+
+There is NO CPU fallback: if the shared library is missing or a call fails this raises."""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+c_f32p = C.c_void_p
+c_i64p = C.c_void_p
+
+_SIGS = {
+    "ac_version": (C.c_int, []),
+    "ac_last_error": (C.c_char_p, []),
+    "ac_launch_count": (C.c_int64, []),
+    "ac_frontend_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "ac_frontend_destroy": (None, [C.c_void_p]),
+    "ac_frontend_num_frames": (C.c_int, [C.c_void_p, C.c_int]),
+    "ac_logmel_fwd": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
+    "ac_db_clamp": (C.c_int, [c_f32p, C.c_int64, c_f32p, C.c_float, C.c_void_p]),
+    "ac_effb2_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ac_effb2_destroy": (None, [C.c_void_p]),
+    "ac_effb2_num_tensors": (C.c_int, []),
+    "ac_effb2_out_frames": (C.c_int, [C.c_int]),
+    "ac_effb2_out_dim": (C.c_int, []),
+    "ac_effb2_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ac_effb2_fwd": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_float, C.c_int, C.c_int, C.c_int, c_f32p,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_effb2_block_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "ac_masked_mean": (C.c_int, [c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    "ac_trm_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ac_trm_destroy": (None, [C.c_void_p]),
+    "ac_trm_num_tensors": (C.c_int, [C.c_int]),
+    "ac_trm_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ac_trm_greedy": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                c_i64p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_trm_beam": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                              C.c_int, C.c_int, C.c_int, c_i64p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+class AudioCaptionB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AudioCaptionB200Error(
+                f"CUDA library {LIB_PATH} is missing -- run `python -m audiocaption_b200.build` "
+                "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise AudioCaptionB200Error(f"{what} failed ({rc}): {lib().ac_last_error().decode()}")
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def tensor_table(tensors):
+    n = len(tensors)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    numels = (C.c_int64 * n)(*[t.numel() for t in tensors])
+    return ptrs, numels, n
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,259 @@
+"""Mirror of the reference's waveform encoders (captioning/models/cnn_encoder.py).
+
+``EfficientNetB2`` -- cnn_encoder.py:769-839 / hf_wrapper.py:260-315: 16 kHz log-mel front-end
+(n_fft 512, hop 160, 64 HTK mels, top_db 120) + EfficientNet-B2 backbone + mean over
+frequency.  The modules below only HOLD parameters under the reference's state_dict names
+(``melspec_extractor.spectrogram.window``, ``melspec_extractor.mel_scale.fb``,
+``backbone.eff_net._blocks.N._expand_conv.weight`` ...); the arithmetic runs in
+csrc/logmel.cu and csrc/effb2.cu through the C ABI.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ._native import Workspace, params_signature, require_cuda
+
+
+# ----------------------------------------------------------------------------- parameter holders
+class _Conv(nn.Module):
+    def __init__(self, cin, cout, k, groups=1, bias=False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin // groups, k, k))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if bias:
+            bound = 1.0 / math.sqrt(cin // groups * k * k)
+            self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+        self.out_channels = cout
+
+
+class _BN(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class _MBConv(nn.Module):
+    def __init__(self, cin, cout, expand, k, nsq):
+        super().__init__()
+        ce = cin * expand
+        if expand != 1:
+            self._expand_conv = _Conv(cin, ce, 1)
+            self._bn0 = _BN(ce)
+        self._depthwise_conv = _Conv(ce, ce, k, groups=ce)
+        self._bn1 = _BN(ce)
+        self._se_reduce = _Conv(ce, nsq, 1, bias=True)
+        self._se_expand = _Conv(nsq, ce, 1, bias=True)
+        self._project_conv = _Conv(ce, cout, 1)
+        self._bn2 = _BN(cout)
+
+
+def _block_plan():
+    l = _lib.lib()
+    info = (ctypes.c_int * 9)()
+    n = l.ac_effb2_block_info(0, info)
+    plan = []
+    for i in range(n):
+        l.ac_effb2_block_info(i, info)
+        plan.append(tuple(info))
+    return plan
+
+
+class _EffNetHolder(nn.Module):
+    """state_dict-compatible with efficientnet_pytorch.EfficientNet('efficientnet-b2', include_top=False)
+    after ``_change_in_channels(1)`` (hf_wrapper.py:235-241)."""
+
+    def __init__(self):
+        super().__init__()
+        plan = _block_plan()
+        self._conv_stem = _Conv(1, 32, 3)
+        self._bn0 = _BN(32)
+        self._blocks = nn.ModuleList([_MBConv(p[0], p[1], p[2], p[3], p[7]) for p in plan])
+        self._conv_head = _Conv(plan[-1][1], _lib.lib().ac_effb2_out_dim(), 1)
+        self._bn1 = _BN(self._conv_head.out_channels)
+
+
+class _EffiNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.eff_net = _EffNetHolder()
+
+
+class _Spectrogram(nn.Module):
+    def __init__(self, n_fft):
+        super().__init__()
+        self.register_buffer("window", torch.hann_window(n_fft, periodic=True))
+
+
+class _MelScale(nn.Module):
+    def __init__(self, fb):
+        super().__init__()
+        self.register_buffer("fb", fb)
+
+
+def _melscale_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate, norm, mel_scale):
+    """Same construction as torchaudio.functional.melscale_fbanks (the reference gets its `fb`
+    buffer from torchaudio.transforms.MelScale); used only to initialise the buffer -- a loaded
+    state_dict overrides it."""
+    import torchaudio
+    return torchaudio.functional.melscale_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate, norm, mel_scale)
+
+
+class MelSpectrogram(nn.Module):
+    """Parameter holder + launcher for the fused log-mel kernel (csrc/logmel.cu)."""
+
+    def __init__(self, sample_rate, n_fft, hop_length, f_min, f_max, n_mels, norm=None, mel_scale="htk"):
+        super().__init__()
+        self.n_fft, self.hop_length, self.n_mels = n_fft, hop_length, n_mels
+        self.spectrogram = _Spectrogram(n_fft)
+        self.mel_scale = _MelScale(_melscale_fbanks(n_fft // 2 + 1, float(f_min), float(f_max), n_mels,
+                                                    sample_rate, norm, mel_scale))
+        self._handle = None
+        self._sig = None
+
+    def _frontend(self):
+        bufs = [self.spectrogram.window, self.mel_scale.fb]
+        sig = params_signature(bufs)
+        if self._handle is None or sig != self._sig:
+            self.release()
+            win = self.spectrogram.window.detach().float().cpu().contiguous()
+            fb = self.mel_scale.fb.detach().float().cpu().contiguous()
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().ac_frontend_create(_lib.ptr(win), self.n_fft, self.hop_length, _lib.ptr(fb),
+                                                     fb.shape[0], fb.shape[1], ctypes.byref(h)), "ac_frontend_create")
+            self._handle, self._sig = h, sig
+        return self._handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib().ac_frontend_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def forward(self, wav: torch.Tensor, want_max: bool = False):
+        """wav [B, N] fp32 cuda -> (lms [B, n_mels, T] in dB (un-clamped), gmax [1] or None)"""
+        require_cuda(wav, "MelSpectrogram")
+        wav = wav.float().contiguous()
+        B, N = wav.shape
+        T = 1 + N // self.hop_length
+        out = torch.empty(B, self.n_mels, T, device=wav.device, dtype=torch.float32)
+        gmax = torch.empty(1, device=wav.device, dtype=torch.float32) if want_max else None
+        with torch.cuda.device(wav.device):
+            _lib.check(_lib.lib().ac_logmel_fwd(self._frontend(), _lib.ptr(wav), B, N, _lib.ptr(out), _lib.ptr(gmax),
+                                                _lib.current_stream()), "ac_logmel_fwd")
+        return out, gmax
+
+
+class AmplitudeToDB(nn.Module):
+    """AmplitudeToDB(stype="power", top_db) on an already-dB tensor produced by the fused kernel:
+    only the batch-global top_db clamp is left to do."""
+
+    def __init__(self, top_db=None):
+        super().__init__()
+        self.top_db = top_db
+
+    def forward(self, lms, gmax):
+        if self.top_db is not None:
+            _lib.check(_lib.lib().ac_db_clamp(_lib.ptr(lms), lms.numel(), _lib.ptr(gmax), float(self.top_db),
+                                              _lib.current_stream()), "ac_db_clamp")
+        return lms
+
+
+class EfficientNetB2(nn.Module):
+    """Drop-in for captioning.models.cnn_encoder.EfficientNetB2 (cnn_encoder.py:769-839,
+    hf_wrapper.py:260-315).  Inference only (eval-mode BatchNorm, no SpecAugment)."""
+
+    def __init__(self, n_mels: int = 64, win_length: int = 32, hop_length: int = 10, f_min: int = 0,
+                 pretrained: bool = False, prune_ratio: float = 0.0, prune_se: bool = True,
+                 prune_start_layer: int = 0, freeze: bool = False):
+        super().__init__()
+        if prune_ratio > 0 or pretrained:
+            raise NotImplementedError("pruned / downloaded EfficientNet-B2 variants are out of scope")
+        sample_rate = 16000
+        n_fft = win_length * sample_rate // 1000
+        self.melspec_extractor = MelSpectrogram(sample_rate, n_fft, hop_length * sample_rate // 1000,
+                                                f_min, sample_rate // 2, n_mels)
+        self.hop_length = 10 * sample_rate // 1000
+        self.db_transform = AmplitudeToDB(top_db=120)
+        self.backbone = _EffiNet()
+        self.fc_emb_size = self.backbone.eff_net._conv_head.out_channels
+        self.downsample_ratio = 32
+        self._ws = Workspace()
+        self._handle = None
+        self._sig = None
+        if freeze:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    # -- weight pack (re-done whenever a parameter changed)
+    def _backbone_tensors(self):
+        return [v for k, v in self.backbone.eff_net.state_dict(keep_vars=True).items()
+                if not k.endswith("num_batches_tracked")]
+
+    def _net(self):
+        tensors = self._backbone_tensors()
+        sig = params_signature(tensors)
+        if self._handle is None or sig != self._sig:
+            self.release()
+            ts = [t.detach().float().contiguous() for t in tensors]
+            for t in ts:
+                require_cuda(t, "EfficientNetB2 parameters")
+            ptrs, numels, n = _lib.tensor_table(ts)
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().ac_effb2_create(ptrs, numels, n, _lib.current_stream(), ctypes.byref(h)),
+                       "ac_effb2_create")
+            self._handle, self._sig = h, sig
+        return self._handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib().ac_effb2_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def log_mel(self, wav):
+        """The reference's `db_transform(melspec_extractor(wav))` (clamped), for inspection."""
+        lms, gmax = self.melspec_extractor(wav, want_max=True)
+        return self.db_transform(lms, gmax)
+
+    def forward(self, input_dict):
+        wav = input_dict["wav"]
+        wav_len = input_dict["wav_len"]
+        if self.training and input_dict.get("specaug", False):
+            raise NotImplementedError("SpecAugment (training) is out of scope of the B200 inference path")
+        require_cuda(wav, "EfficientNetB2.forward")
+        l = _lib.lib()
+        with torch.cuda.device(wav.device):
+            lms, gmax = self.melspec_extractor(wav, want_max=True)   # clamp is fused into the stem conv
+            B, F, T = lms.shape
+            Tp = l.ac_effb2_out_frames(T)
+            attn_emb = torch.empty(B, Tp, self.fc_emb_size, device=wav.device, dtype=torch.float32)
+            nbytes = l.ac_effb2_workspace_bytes(B, F, T)
+            ws = self._ws.get(nbytes, wav.device)
+            _lib.check(l.ac_effb2_fwd(self._net(), _lib.ptr(lms), _lib.ptr(gmax), float(self.db_transform.top_db),
+                                      B, F, T, _lib.ptr(attn_emb), _lib.ptr(ws), nbytes, _lib.current_stream()),
+                       "ac_effb2_fwd")
+            wave_length = torch.as_tensor(wav_len)
+            feat_length = torch.div(wave_length, self.hop_length, rounding_mode="floor") + 1
+            feat_length = torch.div(feat_length, self.downsample_ratio, rounding_mode="floor")
+            len_dev = feat_length.to(device=wav.device, dtype=torch.int64)
+            fc_emb = torch.empty(B, self.fc_emb_size, device=wav.device, dtype=torch.float32)
+            _lib.check(l.ac_masked_mean(_lib.ptr(attn_emb), _lib.ptr(len_dev), B, Tp, self.fc_emb_size,
+                                        _lib.ptr(fc_emb), _lib.current_stream()), "ac_masked_mean")
+        return {"fc_emb": fc_emb, "attn_emb": attn_emb, "attn_emb_len": feat_length.cpu()}

@@ -1,0 +1,77 @@
+// Shared helpers for the audiocaption_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/audiocaption_b200.h"
+
+namespace ac {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+inline int check_cuda(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return AC_ERR_CUDA;
+    }
+    return AC_OK;
+}
+
+#define AC_CUDA(call)                                               \
+    do {                                                            \
+        int _rc = ::ac::check_cuda((call), #call);                  \
+        if (_rc != AC_OK) return _rc;                               \
+    } while (0)
+
+// call after every kernel launch
+#define AC_LAUNCHED(name)                                           \
+    do {                                                            \
+        ::ac::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+        int _rc = ::ac::check_cuda(cudaGetLastError(), name);       \
+        if (_rc != AC_OK) return _rc;                               \
+    } while (0)
+
+#define AC_REQUIRE(cond, ...)                                       \
+    do {                                                            \
+        if (!(cond)) {                                              \
+            ::ac::set_error(__VA_ARGS__);                           \
+            return AC_ERR_ARG;                                      \
+        }                                                           \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// float atomic max valid for any sign (buffer initialised to -inf)
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.0f)
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+#endif
+
+}  // namespace ac

@@ -1,0 +1,560 @@
+// EfficientNet-B2 feature extractor (eval mode), fp32, NHWC.
+//
+// Replaces `_EffiNet.forward` of the reference (captioning/models/hf_wrapper.py:218-241:
+// efficientnet_pytorch 0.7.1 `extract_features` on a [B,1,F,T] log-mel + mean over F).
+// The block plan (23 MBConv blocks, "static same" padding computed for a 260x260 image and
+// applied to the 64 x T spectrogram) is rebuilt here from the B2 coefficients exactly as the
+// package does; tests compare it with the oracle's plan through ac_effb2_block_info.
+//
+// Data layout in HBM: activations [B, H(freq), W(time), C] fp32 (channels innermost), so a
+// 1x1 convolution is the TN GEMM of gemm.cu and the depthwise convolution vectorises over
+// channels.  BatchNorm is folded to a per-channel scale/bias at pack time and applied in the
+// producing kernel's epilogue, together with swish, the SE gate (applied while the projection
+// GEMM loads its A operand) and the residual add.  The top_db clamp of AmplitudeToDB is
+// applied while the stem convolution loads the spectrogram.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace ac {
+
+struct BlockPlan {
+    int cin, cout, expand, k, s, pad_lo, pad_hi, nsq, skip;
+    int cexp() const { return cin * expand; }
+};
+
+static int round_filters(int f) {
+    double x = f * 1.1;
+    int nf = std::max(8, (int)(x + 4.0) / 8 * 8);
+    if (nf < 0.9 * x) nf += 8;
+    return nf;
+}
+static int round_repeats(int r) { return (int)ceil(1.2 * r); }
+
+struct Plan {
+    int stem_out, stem_pad_lo, stem_pad_hi, head_in, head_out;
+    std::vector<BlockPlan> blocks;
+    Plan() {
+        static const int base[7][6] = {  // repeats, k, s, expand, in, out   (efficientnet-b0 stages)
+            {1, 3, 1, 1, 32, 16},  {2, 3, 2, 6, 16, 24},  {2, 5, 2, 6, 24, 40}, {3, 3, 2, 6, 40, 80},
+            {3, 5, 1, 6, 80, 112}, {4, 5, 2, 6, 112, 192}, {1, 3, 1, 6, 192, 320}};
+        auto same_pad = [](int img, int k, int s, int& lo, int& hi) {
+            int o = (img + s - 1) / s;
+            int p = std::max((o - 1) * s + (k - 1) + 1 - img, 0);
+            lo = p / 2; hi = p - p / 2;
+        };
+        int img = 260;
+        stem_out = round_filters(32);
+        same_pad(img, 3, 2, stem_pad_lo, stem_pad_hi);
+        img = (img + 1) / 2;
+        for (auto& st : base) {
+            int cin = round_filters(st[4]), cout = round_filters(st[5]), rep = round_repeats(st[0]);
+            for (int r = 0; r < rep; ++r) {
+                BlockPlan b;
+                b.cin = r == 0 ? cin : cout; b.cout = cout; b.expand = st[3]; b.k = st[1];
+                b.s = r == 0 ? st[2] : 1;
+                same_pad(img, b.k, b.s, b.pad_lo, b.pad_hi);
+                b.nsq = std::max(1, (int)(b.cin * 0.25));
+                b.skip = (r > 0 && b.cin == b.cout) ? 1 : 0;   // first block of a stage never skips
+                blocks.push_back(b);
+                img = (img + b.s - 1) / b.s;
+            }
+            head_in = cout;
+        }
+        head_out = round_filters(1280);
+    }
+};
+
+static const Plan& plan() { static Plan p; return p; }
+
+// ----------------------------------------------------------------------------- pack kernels
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ bias, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float s = gamma[i] / sqrtf(var[i] + eps);
+        scale[i] = s;
+        bias[i] = beta[i] - mean[i] * s;
+    }
+}
+// [C][KK] -> [KK][C]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) {
+        int r = i / cols, c = i % cols;
+        out[(size_t)c * rows + r] = in[i];
+    }
+}
+
+// ----------------------------------------------------------------------------- stem
+// lms [B, H, W] -> out [B, Ho, Wo, 32]; 3x3 stride 2, BN + swish.  8 threads per output pixel.
+__global__ void __launch_bounds__(256)
+stem_kernel(const float* __restrict__ lms, const float* __restrict__ gmax, float top_db,
+            const float* __restrict__ w /*[9][C]*/, const float* __restrict__ scale,
+            const float* __restrict__ bias, float* __restrict__ out, int H, int W, int Ho, int Wo,
+            int C, int pad_lo, int64_t total /* B*Ho*Wo*C/4 */) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c4n = C / 4;
+    int c4 = (int)(idx % c4n);
+    int64_t p = idx / c4n;
+    int wo = (int)(p % Wo); p /= Wo;
+    int ho = (int)(p % Ho);
+    int b = (int)(p / Ho);
+    const float floor_v = gmax ? (*gmax - top_db) : -INFINITY;
+    const float* x = lms + (size_t)b * H * W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        int ih = ho * 2 + kh - pad_lo;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            int iw = wo * 2 + kw - pad_lo;
+            if (iw < 0 || iw >= W) continue;
+            float v = fmaxf(__ldg(x + (size_t)ih * W + iw), floor_v);
+            float4 ww = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C) + c4);
+            acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
+            acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+        }
+    }
+    float4 s = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+    float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    float4 o = make_float4(swishf(fmaf(acc.x, s.x, bb.x)), swishf(fmaf(acc.y, s.y, bb.y)),
+                           swishf(fmaf(acc.z, s.z, bb.z)), swishf(fmaf(acc.w, s.w, bb.w)));
+    reinterpret_cast<float4*>(out)[idx] = o;
+}
+
+// ----------------------------------------------------------------------------- depthwise
+// in [B,Hi,Wi,C] -> out [B,Ho,Wo,C], k x k stride s, BN + swish, plus the per-strip channel sums
+// that feed squeeze-and-excitation: partial[b][strip][c] (deterministic two-level reduction).
+// One CTA = one strip of `pw` output pixels of one output row; thread = (pixel group g, channel
+// quad c4) and walks pixels g, g+G, ...  Consecutive threads hold consecutive channel quads, so
+// every global access is a coalesced 128-bit load/store.
+constexpr int kDwStrip = 32;
+
+template <int K>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w /*[K*K][C]*/,
+              const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ out,
+              float* __restrict__ partial, int Hi, int Wi, int Ho, int Wo, int C, int stride, int pad_lo,
+              int per /*channel quads per pass*/, int G, int strips_w) {
+    extern __shared__ __align__(16) float4 s_part[];   // [G][per]
+    const int c4n = C / 4;
+    const int strip = blockIdx.x;              // ho * strips_w + ws
+    const int ho = strip / strips_w, ws = strip % strips_w;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int g = tid / per, cl = tid % per;
+    const bool active = g < G;
+    const int wo0 = ws * kDwStrip;
+    const int npx = min(kDwStrip, Wo - wo0);
+    const float4* in4 = reinterpret_cast<const float4*>(in) + (size_t)b * Hi * Wi * c4n;
+    float4* out4 = reinterpret_cast<float4*>(out) + ((size_t)(b * Ho + ho) * Wo) * c4n;
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+
+    for (int cbase = 0; cbase < c4n; cbase += per) {
+        const int c4 = cbase + cl;
+        const bool on = active && c4 < c4n;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+            const float4 bi = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+            for (int p = g; p < npx; p += G) {
+                const int wo = wo0 + p;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh) {
+                    const int ih = ho * stride + kh - pad_lo;
+                    if (ih < 0 || ih >= Hi) continue;
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) {
+                        const int iw = wo * stride + kw - pad_lo;
+                        if (iw < 0 || iw >= Wi) continue;
+                        const float4 v = __ldg(in4 + ((size_t)ih * Wi + iw) * c4n + c4);
+                        const float4 ww = __ldg(w4 + (kh * K + kw) * c4n + c4);
+                        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+                        acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+                    }
+                }
+                float4 o = make_float4(swishf(fmaf(acc.x, sc.x, bi.x)), swishf(fmaf(acc.y, sc.y, bi.y)),
+                                       swishf(fmaf(acc.z, sc.z, bi.z)), swishf(fmaf(acc.w, sc.w, bi.w)));
+                out4[(size_t)wo * c4n + c4] = o;
+                sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+            }
+        }
+        // reduce the G pixel groups (fixed order -> deterministic)
+        if (active) s_part[g * per + cl] = sum;
+        __syncthreads();
+        if (g == 0 && c4 < c4n) {
+            float4 t = s_part[cl];
+            for (int q = 1; q < G; ++q) {
+                float4 u = s_part[q * per + cl];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            reinterpret_cast<float4*>(partial)[((size_t)b * gridDim.x + strip) * c4n + c4] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------- squeeze-excite
+// partial [B][strips][C] -> gate [B][C] = sigmoid(We * swish(Wr * mean + br) + be).  One CTA per clip.
+__global__ void __launch_bounds__(256)
+se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const float* __restrict__ wr /*[nsq][C]*/,
+          const float* __restrict__ br, const float* __restrict__ we /*[C][nsq]*/, const float* __restrict__ be,
+          float* __restrict__ gate, int C, int nsq) {
+    extern __shared__ float s_se[];   // mean[C] + r[nsq]
+    float* s_mean = s_se;
+    float* s_r = s_se + C;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* p = partial + (size_t)b * strips * C;
+    for (int c = tid; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < strips; ++q) s += p[(size_t)q * C + c];
+        s_mean[c] = s * inv_hw;
+    }
+    __syncthreads();
+    for (int j = warp; j < nsq; j += blockDim.x / 32) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + (size_t)j * C + c), s_mean[c], s);
+        s = warp_sum(s);
+        if (lane == 0) s_r[j] = swishf(s + br[j]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int j = 0; j < nsq; ++j) s = fmaf(__ldg(we + (size_t)c * nsq + j), s_r[j], s);
+        gate[(size_t)b * C + c] = sigmoidf_(s + be[c]);
+    }
+}
+
+// ----------------------------------------------------------------------------- head tail
+// y [B, H, W, C] -> out [B, W, C] = mean over H  ('b c f t -> b t c', 'mean')
+__global__ void freq_mean_kernel(const float* __restrict__ y, float* __restrict__ out, int H, int W, int C,
+                                 int64_t total /* B*W*C/4 */) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c4n = C / 4;
+    int c4 = (int)(idx % c4n);
+    int64_t p = idx / c4n;
+    int w = (int)(p % W);
+    int b = (int)(p / W);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int h = 0; h < H; ++h) {
+        float4 v = __ldg(y4 + (((size_t)b * H + h) * W + w) * c4n + c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float inv = 1.0f / (float)H;
+    reinterpret_cast<float4*>(out)[idx] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+}
+
+// x [B,T,D], lens [B] -> out [B,D] = sum_{t<len} x / len
+__global__ void masked_mean_kernel(const float* __restrict__ x, const int64_t* __restrict__ lens, int T, int D,
+                                   float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const int64_t len = lens[b];
+    const int n = (int)min((int64_t)T, max((int64_t)0, len));
+    float s = 0.f;
+    for (int t = 0; t < n; ++t) s += x[((size_t)b * T + t) * D + d];
+    out[(size_t)b * D + d] = s / (float)len;
+}
+
+struct ConvBN { float* w; float* scale; float* bias; };
+struct BlockW {
+    ConvBN expand, dw, project;
+    float *se_wr, *se_br, *se_we, *se_be;
+};
+
+static int out_size(int in, int k, int s, int lo, int hi) { return (in + lo + hi - k) / s + 1; }
+
+}  // namespace ac
+
+struct ac_effb2 {
+    float* blob = nullptr;
+    ac::ConvBN stem, head;
+    std::vector<ac::BlockW> blocks;
+};
+
+namespace ac {
+
+struct Dims { int H, W; };
+
+// walks the plan and reports per-layer spatial sizes
+static void walk(int n_mels, int n_frames, Dims& stem, std::vector<Dims>& in_dims, std::vector<Dims>& out_dims) {
+    const Plan& P = plan();
+    stem.H = out_size(n_mels, 3, 2, P.stem_pad_lo, P.stem_pad_hi);
+    stem.W = out_size(n_frames, 3, 2, P.stem_pad_lo, P.stem_pad_hi);
+    Dims d = stem;
+    for (auto& b : P.blocks) {
+        in_dims.push_back(d);
+        d.H = out_size(d.H, b.k, b.s, b.pad_lo, b.pad_hi);
+        d.W = out_size(d.W, b.k, b.s, b.pad_lo, b.pad_hi);
+        out_dims.push_back(d);
+    }
+}
+
+struct WsLayout { size_t x_elems, e_elems, d_elems, part_elems, gate_elems, head_elems; };
+
+static WsLayout ws_layout(int batch, int n_mels, int n_frames) {
+    const Plan& P = plan();
+    Dims stem; std::vector<Dims> din, dout;
+    walk(n_mels, n_frames, stem, din, dout);
+    WsLayout L{};
+    L.x_elems = (size_t)stem.H * stem.W * P.stem_out;
+    for (size_t i = 0; i < P.blocks.size(); ++i) {
+        auto& b = P.blocks[i];
+        size_t pin = (size_t)din[i].H * din[i].W, pout = (size_t)dout[i].H * dout[i].W;
+        L.x_elems = std::max(L.x_elems, pout * b.cout);
+        if (b.expand != 1) L.e_elems = std::max(L.e_elems, pin * b.cexp());
+        L.d_elems = std::max(L.d_elems, pout * b.cexp());
+        size_t strips = (size_t)dout[i].H * cdiv(dout[i].W, kDwStrip);
+        L.part_elems = std::max(L.part_elems, strips * b.cexp());
+        L.gate_elems = std::max(L.gate_elems, (size_t)b.cexp());
+    }
+    L.head_elems = (size_t)dout.back().H * dout.back().W * P.head_out;
+    L.x_elems *= batch; L.e_elems *= batch; L.d_elems *= batch; L.part_elems *= batch;
+    L.gate_elems *= batch; L.head_elems *= batch;
+    return L;
+}
+
+static int launch_dw(const float* in, const ConvBN& cw, float* out, float* partial, int B, Dims di, Dims dd,
+                     int C, const BlockPlan& bp, cudaStream_t st) {
+    const int c4n = C / 4;
+    const int chunks = cdiv(c4n, 256);
+    const int per = cdiv(c4n, chunks);
+    const int G = std::max(1, 256 / per);
+    const int threads = (per * G + 31) / 32 * 32;
+    const int strips_w = cdiv(dd.W, kDwStrip);
+    dim3 grid(dd.H * strips_w, B);
+    size_t sm = (size_t)G * per * sizeof(float4);
+    if (bp.k == 3)
+        dwconv_kernel<3><<<grid, threads, sm, st>>>(in, cw.w, cw.scale, cw.bias, out, partial, di.H, di.W, dd.H,
+                                                    dd.W, C, bp.s, bp.pad_lo, per, G, strips_w);
+    else
+        dwconv_kernel<5><<<grid, threads, sm, st>>>(in, cw.w, cw.scale, cw.bias, out, partial, di.H, di.W, dd.H,
+                                                    dd.W, C, bp.s, bp.pad_lo, per, G, strips_w);
+    AC_LAUNCHED("dwconv_kernel");
+    return AC_OK;
+}
+
+}  // namespace ac
+
+extern "C" {
+
+int ac_effb2_num_tensors(void) {
+    const ac::Plan& P = ac::plan();
+    int n = 1 + 4;   // stem conv + bn
+    for (auto& b : P.blocks) n += (b.expand != 1 ? 5 : 0) + 5 + 4 + 5;
+    return n + 5;    // head conv + bn
+}
+int ac_effb2_out_dim(void) { return ac::plan().head_out; }
+int ac_effb2_out_frames(int n_frames) {
+    ac::Dims stem; std::vector<ac::Dims> a, b;
+    ac::walk(64, n_frames, stem, a, b);
+    return b.back().W;
+}
+int ac_effb2_block_info(int block, int* o) {
+    const ac::Plan& P = ac::plan();
+    if (block < 0 || block >= (int)P.blocks.size()) return (int)P.blocks.size();
+    auto& b = P.blocks[block];
+    o[0] = b.cin; o[1] = b.cout; o[2] = b.expand; o[3] = b.k; o[4] = b.s; o[5] = b.pad_lo; o[6] = b.pad_hi;
+    o[7] = b.nsq; o[8] = b.skip;
+    return (int)P.blocks.size();
+}
+
+size_t ac_effb2_workspace_bytes(int batch, int n_mels, int n_frames) {
+    ac::WsLayout L = ac::ws_layout(batch, n_mels, n_frames);
+    size_t fl = 2 * ac::align_up(L.x_elems, 64) + ac::align_up(L.e_elems, 64) + ac::align_up(L.d_elems, 64) +
+                ac::align_up(L.part_elems, 64) + ac::align_up(L.gate_elems, 64) + ac::align_up(L.head_elems, 64);
+    return fl * sizeof(float);
+}
+
+int ac_effb2_create(const float* const* t, const int64_t* numels, int n_tensors, void* stream, ac_effb2_t** out) {
+    using namespace ac;
+    AC_REQUIRE(t && numels && out, "ac_effb2_create: null argument");
+    AC_REQUIRE(n_tensors == ac_effb2_num_tensors(), "ac_effb2_create: expected %d tensors, got %d",
+               ac_effb2_num_tensors(), n_tensors);
+    const Plan& P = plan();
+    cudaStream_t st = (cudaStream_t)stream;
+    const float eps = 1e-3f;
+    // ---- size the packed blob
+    size_t total = 0;
+    auto take = [&](size_t n) { size_t o = total; total += align_up(n, 64); return o; };
+    struct Off { size_t w, s, b; };
+    auto take_cb = [&](size_t wn, size_t c) { Off o; o.w = take(wn); o.s = take(c); o.b = take(c); return o; };
+    Off stem_o = take_cb(9 * P.stem_out, P.stem_out);
+    struct BOff { Off e, d, p; size_t wr, br, we, be; };
+    std::vector<BOff> bo;
+    for (auto& b : P.blocks) {
+        BOff o{};
+        int ce = b.cexp();
+        if (b.expand != 1) o.e = take_cb((size_t)ce * b.cin, ce);
+        o.d = take_cb((size_t)b.k * b.k * ce, ce);
+        o.wr = take((size_t)b.nsq * ce); o.br = take(b.nsq); o.we = take((size_t)ce * b.nsq); o.be = take(ce);
+        o.p = take_cb((size_t)b.cout * ce, b.cout);
+        bo.push_back(o);
+    }
+    Off head_o = take_cb((size_t)P.head_out * P.head_in, P.head_out);
+    ac_effb2_t* net = new ac_effb2_t();
+    AC_CUDA(cudaMalloc(&net->blob, total * sizeof(float)));
+    float* B0 = net->blob;
+    int ti = 0;
+    int rc = AC_OK;
+    auto expect = [&](int64_t n, const char* what) {
+        if (rc == AC_OK && numels[ti] != n) {
+            set_error("ac_effb2_create: tensor %d (%s) has %lld elements, expected %lld", ti, what,
+                      (long long)numels[ti], (long long)n);
+            rc = AC_ERR_ARG;
+        }
+    };
+    auto copy = [&](size_t off, int64_t n, const char* what) {
+        expect(n, what);
+        if (rc == AC_OK) rc = check_cuda(cudaMemcpyAsync(B0 + off, t[ti], n * sizeof(float), cudaMemcpyDeviceToDevice, st), what);
+        ++ti;
+    };
+    auto transposed = [&](size_t off, int rows, int cols, const char* what) {   // [rows][cols] -> [cols][rows]
+        expect((int64_t)rows * cols, what);
+        if (rc == AC_OK) {
+            transpose_kernel<<<cdiv(rows * cols, 256), 256, 0, st>>>(t[ti], B0 + off, rows, cols);
+            g_launches++;
+        }
+        ++ti;
+    };
+    auto bn = [&](const Off& o, int c, const char* what) {   // weight, bias, running_mean, running_var
+        for (int q = 0; q < 4; ++q)
+            if (rc == AC_OK && numels[ti + q] != c) {
+                set_error("ac_effb2_create: tensor %d (%s) has %lld elements, expected %d", ti + q, what,
+                          (long long)numels[ti + q], c);
+                rc = AC_ERR_ARG;
+            }
+        if (rc == AC_OK) {
+            bn_fold_kernel<<<cdiv(c, 256), 256, 0, st>>>(t[ti], t[ti + 1], t[ti + 2], t[ti + 3], eps, B0 + o.s, B0 + o.b, c);
+            g_launches++;
+        }
+        ti += 4;
+    };
+    transposed(stem_o.w, P.stem_out, 9, "_conv_stem.weight");
+    bn(stem_o, P.stem_out, "_bn0");
+    net->stem = {B0 + stem_o.w, B0 + stem_o.s, B0 + stem_o.b};
+    for (size_t i = 0; i < P.blocks.size(); ++i) {
+        auto& b = P.blocks[i]; auto& o = bo[i];
+        int ce = b.cexp();
+        BlockW w{};
+        if (b.expand != 1) {
+            copy(o.e.w, (int64_t)ce * b.cin, "_expand_conv.weight");
+            bn(o.e, ce, "_bn0");
+            w.expand = {B0 + o.e.w, B0 + o.e.s, B0 + o.e.b};
+        }
+        transposed(o.d.w, ce, b.k * b.k, "_depthwise_conv.weight");
+        bn(o.d, ce, "_bn1");
+        w.dw = {B0 + o.d.w, B0 + o.d.s, B0 + o.d.b};
+        copy(o.wr, (int64_t)b.nsq * ce, "_se_reduce.weight"); copy(o.br, b.nsq, "_se_reduce.bias");
+        copy(o.we, (int64_t)ce * b.nsq, "_se_expand.weight"); copy(o.be, ce, "_se_expand.bias");
+        w.se_wr = B0 + o.wr; w.se_br = B0 + o.br; w.se_we = B0 + o.we; w.se_be = B0 + o.be;
+        copy(o.p.w, (int64_t)b.cout * ce, "_project_conv.weight");
+        bn(o.p, b.cout, "_bn2");
+        w.project = {B0 + o.p.w, B0 + o.p.s, B0 + o.p.b};
+        net->blocks.push_back(w);
+    }
+    copy(head_o.w, (int64_t)P.head_out * P.head_in, "_conv_head.weight");
+    bn(head_o, P.head_out, "_bn1");
+    net->head = {B0 + head_o.w, B0 + head_o.s, B0 + head_o.b};
+    if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_effb2_create pack kernels");
+    if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_effb2_create sync");
+    if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
+    cudaFuncSetAttribute(dwconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(dwconv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    *out = net;
+    return AC_OK;
+}
+
+void ac_effb2_destroy(ac_effb2_t* net) {
+    if (!net) return;
+    cudaFree(net->blob);
+    delete net;
+}
+
+int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, float top_db, int B, int n_mels,
+                 int n_frames, float* attn_emb, void* workspace, size_t ws_bytes, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(net && lms && attn_emb, "ac_effb2_fwd: null argument");
+    AC_REQUIRE(B >= 0 && B <= 65535, "ac_effb2_fwd: batch %d out of range", B);
+    AC_REQUIRE(n_mels >= 8 && n_frames >= 32, "ac_effb2_fwd: input %dx%d too small", n_mels, n_frames);
+    if (B == 0) return AC_OK;
+    AC_REQUIRE(workspace && ws_bytes >= ac_effb2_workspace_bytes(B, n_mels, n_frames),
+               "ac_effb2_fwd: workspace too small (%zu < %zu)", ws_bytes, ac_effb2_workspace_bytes(B, n_mels, n_frames));
+    const Plan& P = plan();
+    cudaStream_t st = (cudaStream_t)stream;
+    WsLayout L = ws_layout(B, n_mels, n_frames);
+    float* p = (float*)workspace;
+    float* X0 = p; p += align_up(L.x_elems, 64);
+    float* X1 = p; p += align_up(L.x_elems, 64);
+    float* E = p; p += align_up(L.e_elems, 64);
+    float* D = p; p += align_up(L.d_elems, 64);
+    float* PART = p; p += align_up(L.part_elems, 64);
+    float* GATE = p; p += align_up(L.gate_elems, 64);
+    float* HEAD = p;
+
+    Dims stem; std::vector<Dims> din, dout;
+    walk(n_mels, n_frames, stem, din, dout);
+    {
+        int64_t total = (int64_t)B * stem.H * stem.W * P.stem_out / 4;
+        stem_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(lms, gmax, top_db, net->stem.w, net->stem.scale,
+                                                                  net->stem.bias, X0, n_mels, n_frames, stem.H,
+                                                                  stem.W, P.stem_out, P.stem_pad_lo, total);
+        AC_LAUNCHED("stem_kernel");
+    }
+    float* cur = X0; float* nxt = X1;
+    for (size_t i = 0; i < P.blocks.size(); ++i) {
+        const BlockPlan& b = P.blocks[i];
+        const BlockW& w = net->blocks[i];
+        const int ce = b.cexp();
+        const int pin = din[i].H * din[i].W, pout = dout[i].H * dout[i].W;
+        const float* dw_in = cur;
+        if (b.expand != 1) {
+            GemmArgs g; g.A = cur; g.W = w.expand.w; g.C = E; g.M = B * pin; g.N = ce; g.K = b.cin;
+            g.cscale = w.expand.scale; g.cbias = w.expand.bias; g.act = ACT_SWISH;
+            int rc = gemm_tn(g, st); if (rc) return rc;
+            dw_in = E;
+        }
+        int rc = launch_dw(dw_in, w.dw, D, PART, B, din[i], dout[i], ce, b, st); if (rc) return rc;
+        const int strips = dout[i].H * cdiv(dout[i].W, kDwStrip);
+        se_kernel<<<B, 256, (ce + b.nsq) * sizeof(float), st>>>(PART, strips, 1.0f / (float)pout, w.se_wr, w.se_br,
+                                                                w.se_we, w.se_be, GATE, ce, b.nsq);
+        AC_LAUNCHED("se_kernel");
+        GemmArgs g; g.A = D; g.W = w.project.w; g.C = nxt; g.M = B * pout; g.N = b.cout; g.K = ce;
+        g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
+        g.act = ACT_NONE; g.R = b.skip ? cur : nullptr;
+        rc = gemm_tn(g, st); if (rc) return rc;
+        std::swap(cur, nxt);
+    }
+    const Dims last = dout.back();
+    {
+        GemmArgs g; g.A = cur; g.W = net->head.w; g.C = HEAD; g.M = B * last.H * last.W; g.N = P.head_out;
+        g.K = P.head_in; g.cscale = net->head.scale; g.cbias = net->head.bias; g.act = ACT_SWISH;
+        int rc = gemm_tn(g, st); if (rc) return rc;
+        int64_t total = (int64_t)B * last.W * P.head_out / 4;
+        freq_mean_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(HEAD, attn_emb, last.H, last.W, P.head_out, total);
+        AC_LAUNCHED("freq_mean_kernel");
+    }
+    return AC_OK;
+}
+
+int ac_masked_mean(const float* x, const int64_t* lens, int batch, int T, int D, float* out, void* stream) {
+    AC_REQUIRE(x && lens && out, "ac_masked_mean: null argument");
+    if (batch == 0 || D == 0) return AC_OK;
+    dim3 grid(ac::cdiv(D, 128), batch);
+    ac::masked_mean_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, lens, T, D, out);
+    AC_LAUNCHED("masked_mean_kernel");
+    return AC_OK;
+}
+
+}  // extern "C"

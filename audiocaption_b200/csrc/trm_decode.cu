@@ -1,0 +1,666 @@
+// Transformer caption decoder: KV-cached greedy and beam-search decoding, fp32.
+//
+// Replaces the reference's `TransformerDecoder.forward` (captioning/models/transformer_decoder.py:80-103,
+// HF copy captioning/models/hf_wrapper.py:1045-1068) driven by `CaptionModel.stepwise_forward`
+// (captioning/models/base.py:152-218) and `CaptionModel.beam_search` (:254-361) with the
+// Transformer glue of captioning/models/transformer_model.py:34-86.
+//
+// The reference re-evaluates the whole prefix (and re-projects the audio memory) at every step.
+// In eval mode that is mathematically identical to:
+//   once per call : P = LayerNorm(ReLU(attn_emb W0^T + b0));  K_l, V_l = P Wkv_l^T + bkv_l   (GEMMs)
+//   per step      : one token per row through the 2 post-norm layers with cached self-attention
+//                   K/V, cross-attention against K_l/V_l, FFN, classifier.
+// Clips are independent, so ONE CTA owns one clip for the whole decode (all `max_len` steps,
+// `R` = 1 row for greedy, `R` = beam rows for beam search): no grid-wide synchronisation, no
+// host round trip per token, a single launch.  Weights are stored transposed ([K][N]) at pack
+// time so that thread n streams column n with coalesced loads while the R activations are
+// broadcast from shared memory.
+//
+// Masks: causal by construction (only positions <= t are cached); `tgt_key_padding_mask`
+// = (prefix token == <pad>) and `memory_key_padding_mask` = (frame >= attn_emb_len) are applied
+// as -inf before the softmax exactly as nn.MultiheadAttention merges them.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace ac {
+
+constexpr int D = 256;          // d_model
+constexpr int NH = 4;           // heads
+constexpr int HD = 64;          // head dim
+constexpr int kMaxKeys = 128;   // max(t_mem, max_len)
+constexpr int kMaxLen = 64;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct LayerW {
+    const float *sa_in_wt, *sa_in_b, *sa_out_wt, *sa_out_b;   // [D][3D], [3D], [D][D], [D]
+    const float *ca_q_wt, *ca_q_b, *ca_out_wt, *ca_out_b;     // [D][D] ...
+    const float *ff1_wt, *ff1_b, *ff2_wt, *ff2_b;             // [D][F], [F], [F][D], [D]
+    const float *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
+    const float *ca_kv_w, *ca_kv_b;                            // [2D][D] (original layout, for the GEMM), [2D]
+};
+
+constexpr int kMaxLayers = 4;
+
+struct DecW {
+    const float* emb;     // [V][D]
+    const float* pe;      // [pe_len][D]
+    const float* cls_wt;  // [D][V]
+    const float *proj_w, *proj_b, *proj_ln_g, *proj_ln_b;   // attn_proj: [D][attn_emb_dim] original layout
+    LayerW layer[kMaxLayers];
+    int nlayers, dff, vocab, attn_emb_dim, pe_len;
+};
+
+// ------------------------------------------------------------------------------------ helpers
+// out[r][n] = act(bias[n] + sum_k xin[r][k] * Wt[k][n]); xin/out in shared memory.
+template <int R>
+__device__ __forceinline__ void matvec_t(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                         const float* xin, int ldx, float* out, int ldo, int N, int K, bool relu) {
+    for (int n = threadIdx.x; n < N; n += kThreads) {
+        float acc[R];
+        const float b0 = bias ? __ldg(bias + n) : 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = b0;
+        const float* w = Wt + n;
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) {
+            const float wv = __ldg(w + (size_t)k * N);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fmaf(wv, xin[r * ldx + k], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r * ldo + n] = relu ? fmaxf(acc[r], 0.0f) : acc[r];
+    }
+}
+
+// x[r][:] = LayerNorm(x[r][:] + add[r][:]) * g + b   (eps 1e-5, biased variance), one warp per row
+template <int R>
+__device__ __forceinline__ void add_layernorm(float* x, const float* add, const float* __restrict__ g,
+                                              const float* __restrict__ b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < R; r += kWarps) {
+        float v[D / 32];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) {
+            v[i] = x[r * D + lane + 32 * i] + add[r * D + lane + 32 * i];
+            s += v[i];
+        }
+        const float mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) {
+            const int c = lane + 32 * i;
+            x[r * D + c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+        }
+    }
+}
+
+// softmax over n keys for every (row, head); sc layout [R][NH][kMaxKeys]
+template <int R>
+__device__ __forceinline__ void softmax_rows(float* sc, int n) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < R * NH; i += kWarps) {
+        float* p = sc + i * kMaxKeys;
+        float m = -INFINITY;
+        for (int j = lane; j < n; j += 32) m = fmaxf(m, p[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < n; j += 32) { float e = expf(p[j] - m); p[j] = e; s += e; }
+        s = warp_sum(s);
+        const float inv = 1.0f / s;
+        for (int j = lane; j < n; j += 32) p[j] *= inv;
+    }
+}
+
+struct DecodeArgs {
+    DecW w;
+    const float* kv_mem;        // [nlayers][clips][t_mem][2D]  (K | V per frame)
+    int n_clips;
+    const int64_t* mem_len;     // [clips]
+    float* kv_cache;            // [clips][nlayers][2][max_len][R][D]
+    float* logits_ws;           // [clips][R][V] scratch (beam) ...
+    int t_mem, max_len, start_idx, end_idx, pad_idx;
+    // greedy outputs
+    int64_t* seq;               // [clips][max_len]
+    float* logprob;             // nullable [clips][max_len]
+    float* logit_out;           // nullable [clips][max_len][V]
+    float* embed_out;           // nullable [clips][max_len][D]
+    // beam
+    int beam; float temp;
+};
+
+// One decoder step for the R rows of this clip: token ids `words[r]` at position t.
+// anc[r][j] = cache slot holding row r's ancestor at position j (greedy: always r).
+// On return s_x holds the final hidden states [R][D]; logits are written to `logits` ([R][V], global).
+template <int R>
+__device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* words, const int (*anc)[kMaxLen],
+                             const unsigned char (*padflag)[8], float* s_x, float* s_q, float* s_att, float* s_h,
+                             float* s_sc, float* logits) {
+    const DecW& W = a.w;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_mem = min((int)min((int64_t)a.t_mem, a.mem_len[clip]), a.t_mem);
+    // embedding * sqrt(d) + positional encoding
+    for (int r = 0; r < R; ++r)
+        s_x[r * D + tid] = __ldg(W.emb + (size_t)words[r] * D + tid) * 16.0f + __ldg(W.pe + (size_t)t * D + tid);
+    __syncthreads();
+
+    for (int l = 0; l < W.nlayers; ++l) {
+        const LayerW& L = W.layer[l];
+        float* kc = a.kv_cache + ((((size_t)clip * W.nlayers + l) * 2 + 0) * a.max_len) * R * D;
+        float* vc = a.kv_cache + ((((size_t)clip * W.nlayers + l) * 2 + 1) * a.max_len) * R * D;
+        // ---- self attention
+        matvec_t<R>(L.sa_in_wt, L.sa_in_b, s_x, D, s_h, 3 * D, 3 * D, D, false);
+        __syncthreads();
+        for (int r = 0; r < R; ++r) {
+            s_q[r * D + tid] = s_h[r * 3 * D + tid] * 0.125f;
+            kc[((size_t)t * R + r) * D + tid] = s_h[r * 3 * D + D + tid];
+            vc[((size_t)t * R + r) * D + tid] = s_h[r * 3 * D + 2 * D + tid];
+        }
+        __syncthreads();   // also orders the cache writes before the reads below (same CTA)
+        const int nk = t + 1;
+        for (int it = warp; it < R * NH * nk; it += kWarps) {
+            const int j = it % nk, hh = (it / nk) % NH, r = it / (nk * NH);
+            const float* kp = kc + ((size_t)j * R + anc[r][j]) * D + hh * HD;
+            const float* qp = s_q + r * D + hh * HD;
+            float s = qp[lane] * kp[lane] + qp[lane + 32] * kp[lane + 32];
+            s = warp_sum(s);
+            if (lane == 0) s_sc[(r * NH + hh) * kMaxKeys + j] = padflag[j][anc[r][j]] ? -INFINITY : s;
+        }
+        __syncthreads();
+        softmax_rows<R>(s_sc, nk);
+        __syncthreads();
+        for (int r = 0; r < R; ++r) {
+            const float* p = s_sc + (r * NH + tid / HD) * kMaxKeys;
+            float o = 0.f;
+            for (int j = 0; j < nk; ++j) o = fmaf(p[j], vc[((size_t)j * R + anc[r][j]) * D + tid], o);
+            s_att[r * D + tid] = o;
+        }
+        __syncthreads();
+        matvec_t<R>(L.sa_out_wt, L.sa_out_b, s_att, D, s_q, D, D, D, false);
+        __syncthreads();
+        add_layernorm<R>(s_x, s_q, L.n1_g, L.n1_b);
+        __syncthreads();
+        // ---- cross attention over the projected audio memory
+        matvec_t<R>(L.ca_q_wt, L.ca_q_b, s_x, D, s_q, D, D, D, false);
+        __syncthreads();
+        const float* km = a.kv_mem + (((size_t)l * a.n_clips + clip) * a.t_mem) * 2 * D;
+        for (int it = warp; it < R * NH * a.t_mem; it += kWarps) {
+            const int j = it % a.t_mem, hh = (it / a.t_mem) % NH, r = it / (a.t_mem * NH);
+            const float* kp = km + (size_t)j * 2 * D + hh * HD;
+            const float* qp = s_q + r * D + hh * HD;
+            float s = qp[lane] * __ldg(kp + lane) + qp[lane + 32] * __ldg(kp + lane + 32);
+            s = warp_sum(s) * 0.125f;
+            if (lane == 0) s_sc[(r * NH + hh) * kMaxKeys + j] = j < n_mem ? s : -INFINITY;
+        }
+        __syncthreads();
+        softmax_rows<R>(s_sc, a.t_mem);
+        __syncthreads();
+        for (int r = 0; r < R; ++r) {
+            const float* p = s_sc + (r * NH + tid / HD) * kMaxKeys;
+            float o = 0.f;
+            for (int j = 0; j < n_mem; ++j) o = fmaf(p[j], __ldg(km + (size_t)j * 2 * D + D + tid), o);
+            s_att[r * D + tid] = o;
+        }
+        __syncthreads();
+        matvec_t<R>(L.ca_out_wt, L.ca_out_b, s_att, D, s_q, D, D, D, false);
+        __syncthreads();
+        add_layernorm<R>(s_x, s_q, L.n2_g, L.n2_b);
+        __syncthreads();
+        // ---- feed forward
+        matvec_t<R>(L.ff1_wt, L.ff1_b, s_x, D, s_h, W.dff, W.dff, D, true);
+        __syncthreads();
+        matvec_t<R>(L.ff2_wt, L.ff2_b, s_h, W.dff, s_q, D, D, W.dff, false);
+        __syncthreads();
+        add_layernorm<R>(s_x, s_q, L.n3_g, L.n3_b);
+        __syncthreads();
+    }
+    // ---- classifier (no bias)
+    const int V = W.vocab;
+    for (int n = tid; n < V; n += kThreads) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        const float* w = W.cls_wt + n;
+#pragma unroll 8
+        for (int k = 0; k < D; ++k) {
+            const float wv = __ldg(w + (size_t)k * V);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fmaf(wv, s_x[r * D + k], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) logits[(size_t)r * V + n] = acc[r];
+    }
+    __syncthreads();
+}
+
+// block-wide (max value, lowest index) reduction
+__device__ __forceinline__ void block_argmax(float& v, int& idx, float* s_v, int* s_i) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if (lane == 0) { s_v[warp] = v; s_i[warp] = idx; }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < kWarps ? s_v[lane] : -INFINITY;
+        idx = lane < kWarps ? s_i[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (lane == 0) { s_v[0] = v; s_i[0] = idx; }
+    }
+    __syncthreads();
+    v = s_v[0]; idx = s_i[0];
+    __syncthreads();
+}
+
+__device__ __forceinline__ float block_sum(float v, float* s_v) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) s_v[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) t += s_v[i];   // fixed order: deterministic
+    __syncthreads();
+    return t;
+}
+
+constexpr size_t dec_smem_floats(int R) { return (size_t)R * (D + D + D + 1024 + NH * kMaxKeys); }
+
+// ------------------------------------------------------------------------------------ greedy
+__global__ void __launch_bounds__(kThreads)
+greedy_kernel(DecodeArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_x = smem; float* s_q = s_x + D; float* s_att = s_q + D; float* s_h = s_att + D;
+    float* s_sc = s_h + 1024;
+    __shared__ int s_anc[1][kMaxLen];
+    __shared__ unsigned char s_pad[kMaxLen][8];
+    __shared__ float s_rv[kWarps];
+    __shared__ int s_ri[kWarps];
+    __shared__ int s_word;
+    const int clip = blockIdx.x, tid = threadIdx.x;
+    const int V = a.w.vocab;
+    for (int j = tid; j < kMaxLen; j += kThreads) s_anc[0][j] = 0;
+    float* logits_ws = a.logits_ws + (size_t)clip * V;
+    int word = a.start_idx;
+    bool finished = false;
+    __syncthreads();
+    for (int t = 0; t < a.max_len; ++t) {
+        if (finished) {   // rows that emitted <end> keep <end> (base.py:161-168)
+            if (tid == 0) a.seq[(size_t)clip * a.max_len + t] = a.end_idx;
+            continue;
+        }
+        if (tid == 0) { s_pad[t][0] = (word == a.pad_idx); s_word = word; }
+        __syncthreads();
+        float* logits = a.logit_out ? a.logit_out + ((size_t)clip * a.max_len + t) * V : logits_ws;
+        decoder_step<1>(a, clip, t, &s_word, s_anc, s_pad, s_x, s_q, s_att, s_h, s_sc, logits);
+        if (a.embed_out) a.embed_out[((size_t)clip * a.max_len + t) * D + tid] = s_x[tid];
+        // log-softmax + argmax (first maximum wins, as torch.max on CPU)
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int n = tid; n < V; n += kThreads) {
+            float v = logits[n];
+            if (v > best) { best = v; bi = n; }
+        }
+        block_argmax(best, bi, s_rv, s_ri);
+        float se = 0.f;
+        for (int n = tid; n < V; n += kThreads) se += expf(logits[n] - best);
+        se = block_sum(se, s_rv);
+        word = bi;
+        if (tid == 0) {
+            a.seq[(size_t)clip * a.max_len + t] = word;
+            if (a.logprob) a.logprob[(size_t)clip * a.max_len + t] = -logf(se);
+        }
+        finished = (word == a.end_idx);
+    }
+}
+
+// ------------------------------------------------------------------------------------ beam search
+template <int R>
+__global__ void __launch_bounds__(kThreads)
+beam_kernel(DecodeArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_x = smem; float* s_q = s_x + R * D; float* s_att = s_q + R * D; float* s_h = s_att + R * D;
+    float* s_sc = s_h + R * 1024;
+    __shared__ int s_anc[2][R][kMaxLen];
+    __shared__ unsigned char s_pad[kMaxLen][8];
+    __shared__ int s_seq[2][R][kMaxLen];
+    __shared__ int s_words[R];
+    __shared__ float s_score[R];
+    __shared__ float s_newscore[R];
+    __shared__ int s_newidx[R];
+    __shared__ float s_rv[kWarps];
+    __shared__ int s_ri[kWarps];
+    __shared__ int s_best_seq[kMaxLen];
+    __shared__ int s_best_len, s_ndone, s_stop;
+    __shared__ float s_best_score;
+    const int clip = blockIdx.x, tid = threadIdx.x;
+    const int V = a.w.vocab;
+    float* lp = a.logits_ws + (size_t)clip * R * V;
+    if (tid < R) { s_words[tid] = a.start_idx; s_score[tid] = 0.f; }
+    if (tid == 0) { s_ndone = 0; s_stop = 0; s_best_len = 0; s_best_score = -INFINITY; }
+    for (int i = tid; i < R * kMaxLen; i += kThreads) { s_anc[0][i / kMaxLen][i % kMaxLen] = i / kMaxLen; }
+    __syncthreads();
+    int cur = 0;
+    for (int t = 0; t < a.max_len; ++t) {
+        if (tid < R) s_pad[t][tid] = (s_words[tid] == a.pad_idx);
+        if (tid < R) s_anc[cur][tid][t] = tid;
+        __syncthreads();
+        decoder_step<R>(a, clip, t, s_words, s_anc[cur], s_pad, s_x, s_q, s_att, s_h, s_sc, lp);
+        // lp = log_softmax(log_softmax(logit) / temp) + running score   (base.py:282-290)
+        for (int r = 0; r < R; ++r) {
+            float* row = lp + (size_t)r * V;
+            float m = -INFINITY; int mi = 0;
+            for (int n = tid; n < V; n += kThreads) m = fmaxf(m, row[n]);
+            block_argmax(m, mi, s_rv, s_ri);
+            float se = 0.f;
+            for (int n = tid; n < V; n += kThreads) se += expf(row[n] - m);
+            const float lse1 = m + logf(block_sum(se, s_rv));
+            const float inv_t = 1.0f / a.temp;
+            // second log-softmax over y = (row - lse1) / temp ; its max is (m - lse1) / temp
+            const float m2 = (m - lse1) * inv_t;
+            float se2 = 0.f;
+            for (int n = tid; n < V; n += kThreads) se2 += expf((row[n] - lse1) * inv_t - m2);
+            const float lse2 = m2 + logf(block_sum(se2, s_rv));
+            const float sc = s_score[r];
+            for (int n = tid; n < V; n += kThreads) row[n] = sc + ((row[n] - lse1) * inv_t - lse2);
+        }
+        __syncthreads();
+        // top-R of the flattened [rows * V] scores (step 0: row 0 only), R rounds of block arg-max
+        const int ncand = (t == 0 ? 1 : R) * V;
+        for (int k = 0; k < R; ++k) {
+            float best = -INFINITY; int bi = 0x7fffffff;
+            for (int n = tid; n < ncand; n += kThreads) {
+                bool taken = false;
+                for (int q = 0; q < k; ++q) taken |= (s_newidx[q] == n);
+                float v = lp[n];
+                if (!taken && (v > best || (v == best && n < bi))) { best = v; bi = n; }
+            }
+            block_argmax(best, bi, s_rv, s_ri);
+            if (tid == 0) { s_newscore[k] = best; s_newidx[k] = bi; }
+            __syncthreads();
+        }
+        // reorder beams: histories follow their parent (base.py:291-304)
+        const int nxt = cur ^ 1;
+        for (int i = tid; i < R * kMaxLen; i += kThreads) {
+            const int r = i / kMaxLen, j = i % kMaxLen;
+            const int parent = s_newidx[r] / V;
+            if (j <= t) s_anc[nxt][r][j] = s_anc[cur][parent][j];
+            if (j < t) s_seq[nxt][r][j] = s_seq[cur][parent][j];
+            if (j == t) s_seq[nxt][r][j] = s_newidx[r] % V;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int r = 0; r < R; ++r) {
+                const int wd = s_newidx[r] % V;
+                float sc = s_newscore[r];
+                const bool is_end = (wd == a.end_idx) || (t == a.max_len - 1);
+                if (is_end) {
+                    const float fs = sc / (float)(t + 1);
+                    s_ndone++;
+                    if (fs > s_best_score) {   // stable best-first: earlier beam wins ties
+                        s_best_score = fs; s_best_len = t + 1;
+                        for (int j = 0; j <= t; ++j) s_best_seq[j] = s_seq[nxt][r][j];
+                    }
+                    sc -= 1000.0f;
+                }
+                s_score[r] = sc; s_words[r] = wd;
+            }
+            if (s_ndone == R) s_stop = 1;   // equality, as the reference
+        }
+        __syncthreads();
+        cur = nxt;
+        if (s_stop) break;
+    }
+    for (int j = tid; j < a.max_len; j += kThreads)
+        a.seq[(size_t)clip * a.max_len + j] = j < s_best_len ? s_best_seq[j] : a.end_idx;
+}
+
+// rows [n, D] in place: LayerNorm(x) * g + b, eps 1e-5; one warp per row
+__global__ void layernorm_rows_kernel(float* __restrict__ x, const float* __restrict__ g,
+                                      const float* __restrict__ b, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    float* p = x + row * D;
+    float v[D / 32]; float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) { v[i] = p[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < D / 32; ++i) {
+        const int c = lane + 32 * i;
+        p[c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+    }
+}
+
+__global__ void transpose2_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)rows * cols) {
+        int r = (int)(i / cols), c = (int)(i % cols);
+        out[(size_t)c * rows + r] = in[i];
+    }
+}
+
+}  // namespace ac
+
+struct ac_trm {
+    float* blob = nullptr;
+    ac::DecW w;
+};
+
+namespace ac {
+struct TrmWs { size_t proj, kvmem, cache, logits; };
+static TrmWs trm_ws(const ac_trm* d, int clips, int rows_per_clip, int t_mem, int max_len) {
+    TrmWs s;
+    s.proj = align_up((size_t)clips * t_mem * D, 64);
+    s.kvmem = align_up((size_t)clips * d->w.nlayers * t_mem * 2 * D, 64);
+    s.cache = align_up((size_t)clips * d->w.nlayers * 2 * max_len * rows_per_clip * D, 64);
+    s.logits = align_up((size_t)clips * rows_per_clip * d->w.vocab, 64);
+    return s;
+}
+
+// attn_proj + per-layer cross-attention K/V of the audio memory (once per call)
+static int prepare_memory(const ac_trm* d, const float* attn_emb, int clips, int t_mem, float* proj, float* kvmem,
+                          cudaStream_t st) {
+    const DecW& W = d->w;
+    GemmArgs g; g.A = attn_emb; g.W = W.proj_w; g.C = proj; g.M = clips * t_mem; g.N = D; g.K = W.attn_emb_dim;
+    g.cbias = W.proj_b; g.act = ACT_RELU;
+    int rc = gemm_tn(g, st); if (rc) return rc;
+    int64_t rows = (int64_t)clips * t_mem;
+    layernorm_rows_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, st>>>(proj, W.proj_ln_g, W.proj_ln_b, rows);
+    AC_LAUNCHED("layernorm_rows_kernel");
+    for (int l = 0; l < W.nlayers; ++l) {
+        // one [clips*t_mem, D] x [D, 2D] GEMM per layer; kvmem layout [layer][clip][t][K | V]
+        GemmArgs k; k.A = proj; k.W = W.layer[l].ca_kv_w; k.M = clips * t_mem; k.N = 2 * D; k.K = D;
+        k.cbias = W.layer[l].ca_kv_b; k.act = ACT_NONE;
+        k.C = kvmem + (size_t)l * clips * t_mem * 2 * D;   // [layer][clip][t][2D]
+        rc = gemm_tn(k, st); if (rc) return rc;
+    }
+    return AC_OK;
+}
+}  // namespace ac
+
+extern "C" {
+
+int ac_trm_num_tensors(int nlayers) { return 2 + 18 * nlayers + 5; }
+
+int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, int d_model, int nhead, int nlayers,
+                  int dim_ff, int vocab, int attn_emb_dim, int pe_len, void* stream, ac_trm_t** out) {
+    using namespace ac;
+    AC_REQUIRE(t && numels && out, "ac_trm_create: null argument");
+    AC_REQUIRE(d_model == D && nhead == NH, "ac_trm_create: only d_model=256 / nhead=4 is built (got %d/%d)", d_model, nhead);
+    AC_REQUIRE(nlayers >= 1 && nlayers <= kMaxLayers, "ac_trm_create: nlayers %d not in [1,%d]", nlayers, kMaxLayers);
+    AC_REQUIRE(dim_ff % 4 == 0 && dim_ff <= 1024, "ac_trm_create: dim_feedforward %d must be <=1024 and %%4", dim_ff);
+    AC_REQUIRE(attn_emb_dim % 4 == 0, "ac_trm_create: attn_emb_dim %d must be a multiple of 4", attn_emb_dim);
+    AC_REQUIRE(n_tensors == ac_trm_num_tensors(nlayers), "ac_trm_create: expected %d tensors, got %d",
+               ac_trm_num_tensors(nlayers), n_tensors);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = dim_ff, V = vocab;
+    // expected element counts, in tensor order
+    std::vector<int64_t> want = {(int64_t)V * D, (int64_t)pe_len * D};
+    for (int l = 0; l < nlayers; ++l) {
+        int64_t per[18] = {3 * D * D, 3 * D, D * D, D, 3 * D * D, 3 * D, D * D, D, (int64_t)F * D, F, (int64_t)D * F, D,
+                           D, D, D, D, D, D};
+        want.insert(want.end(), per, per + 18);
+    }
+    int64_t tail[5] = {(int64_t)V * D, (int64_t)D * attn_emb_dim, D, D, D};
+    want.insert(want.end(), tail, tail + 5);
+    for (int i = 0; i < n_tensors; ++i)
+        AC_REQUIRE(numels[i] == want[i], "ac_trm_create: tensor %d has %lld elements, expected %lld", i,
+                   (long long)numels[i], (long long)want[i]);
+    size_t total = 0;
+    for (auto n : want) total += align_up((size_t)n, 64);
+    ac_trm_t* d = new ac_trm_t();
+    AC_CUDA(cudaMalloc(&d->blob, total * sizeof(float)));
+    size_t off = 0;
+    int ti = 0;
+    int rc = AC_OK;
+    auto plain = [&]() -> const float* {
+        float* p = d->blob + off;
+        if (rc == AC_OK) rc = check_cuda(cudaMemcpyAsync(p, t[ti], want[ti] * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy");
+        off += align_up((size_t)want[ti], 64); ++ti;
+        return p;
+    };
+    auto transposed = [&](int rows, int cols, const float* src) -> const float* {   // [rows][cols] -> [cols][rows]
+        float* p = d->blob + off;
+        transpose2_kernel<<<(unsigned)cdiv64((int64_t)rows * cols, 256), 256, 0, st>>>(src, p, rows, cols);
+        g_launches++;
+        return p;
+    };
+    DecW& W = d->w;
+    W.nlayers = nlayers; W.dff = F; W.vocab = V; W.attn_emb_dim = attn_emb_dim; W.pe_len = pe_len;
+    W.emb = plain();
+    W.pe = plain();
+    for (int l = 0; l < nlayers; ++l) {
+        LayerW& L = W.layer[l];
+        L.sa_in_wt = transposed(3 * D, D, t[ti]); off += align_up((size_t)want[ti], 64); ++ti;
+        L.sa_in_b = plain();
+        L.sa_out_wt = transposed(D, D, t[ti]); off += align_up((size_t)want[ti], 64); ++ti;
+        L.sa_out_b = plain();
+        // multihead_attn.in_proj: rows [0,D) = query projection (transposed for the decode kernel),
+        // rows [D,3D) = key/value projections (kept [2D][D] for the memory GEMM)
+        {
+            float* p = d->blob + off;
+            transpose2_kernel<<<(unsigned)cdiv64((int64_t)D * D, 256), 256, 0, st>>>(t[ti], p, D, D);
+            g_launches++;
+            if (rc == AC_OK) rc = check_cuda(cudaMemcpyAsync(p + D * D, t[ti] + (size_t)D * D, (size_t)2 * D * D * sizeof(float),
+                                                             cudaMemcpyDeviceToDevice, st), "copy kv");
+            L.ca_q_wt = p; L.ca_kv_w = p + D * D;
+            off += align_up((size_t)want[ti], 64); ++ti;
+        }
+        { const float* b = plain(); L.ca_q_b = b; L.ca_kv_b = b + D; }
+        L.ca_out_wt = transposed(D, D, t[ti]); off += align_up((size_t)want[ti], 64); ++ti;
+        L.ca_out_b = plain();
+        L.ff1_wt = transposed(F, D, t[ti]); off += align_up((size_t)want[ti], 64); ++ti;
+        L.ff1_b = plain();
+        L.ff2_wt = transposed(D, F, t[ti]); off += align_up((size_t)want[ti], 64); ++ti;
+        L.ff2_b = plain();
+        L.n1_g = plain(); L.n1_b = plain(); L.n2_g = plain(); L.n2_b = plain(); L.n3_g = plain(); L.n3_b = plain();
+    }
+    W.cls_wt = transposed(V, D, t[ti]); off += align_up((size_t)want[ti], 64); ++ti;
+    W.proj_w = plain(); W.proj_b = plain(); W.proj_ln_g = plain(); W.proj_ln_b = plain();
+    if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_trm_create pack kernels");
+    if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_trm_create sync");
+    if (rc != AC_OK) { cudaFree(d->blob); delete d; return rc; }
+    *out = d;
+    return AC_OK;
+}
+
+void ac_trm_destroy(ac_trm_t* d) {
+    if (!d) return;
+    cudaFree(d->blob);
+    delete d;
+}
+
+size_t ac_trm_workspace_bytes(const ac_trm_t* d, int rows, int t_mem, int max_len) {
+    // `rows` = rows per clip (1 for greedy, beam size for beam search) is folded by the caller:
+    // pass batch * rows_per_clip; sized for the worst case of both layouts.
+    if (!d) return 0;
+    ac::TrmWs s = ac::trm_ws(d, rows, 1, t_mem, max_len);
+    return (s.proj + s.kvmem + s.cache + s.logits) * sizeof(float);
+}
+
+static int trm_common_checks(const ac_trm_t* dec, int batch, int t_mem, int max_len) {
+    using namespace ac;
+    AC_REQUIRE(dec, "ac_trm: null decoder");
+    AC_REQUIRE(batch >= 0, "ac_trm: negative batch");
+    AC_REQUIRE(t_mem >= 1 && t_mem <= kMaxKeys, "ac_trm: t_mem %d not in [1,%d]", t_mem, kMaxKeys);
+    AC_REQUIRE(max_len >= 1 && max_len <= kMaxLen && max_len <= dec->w.pe_len,
+               "ac_trm: max_len %d not in [1,%d]", max_len, std::min(kMaxLen, dec->w.pe_len));
+    return AC_OK;
+}
+
+int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_emb_len, int batch, int t_mem,
+                  int max_len, int start_idx, int end_idx, int pad_idx, int64_t* seq, float* logprob, float* logit,
+                  float* embed, void* ws, size_t ws_bytes, void* stream) {
+    using namespace ac;
+    int rc = trm_common_checks(dec, batch, t_mem, max_len); if (rc) return rc;
+    AC_REQUIRE(attn_emb && attn_emb_len && seq, "ac_trm_greedy: null argument");
+    if (batch == 0) return AC_OK;
+    TrmWs s = trm_ws(dec, batch, 1, t_mem, max_len);
+    AC_REQUIRE(ws && ws_bytes >= (s.proj + s.kvmem + s.cache + s.logits) * sizeof(float), "ac_trm_greedy: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* proj = (float*)ws; float* kvmem = proj + s.proj; float* cache = kvmem + s.kvmem; float* lws = cache + s.cache;
+    rc = prepare_memory(dec, attn_emb, batch, t_mem, proj, kvmem, st); if (rc) return rc;
+    DecodeArgs a{};
+    a.w = dec->w; a.kv_mem = kvmem; a.n_clips = batch; a.mem_len = attn_emb_len; a.kv_cache = cache; a.logits_ws = lws;
+    a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
+    a.seq = seq; a.logprob = logprob; a.logit_out = logit; a.embed_out = embed; a.beam = 1; a.temp = 1.0f;
+    size_t sm = dec_smem_floats(1) * sizeof(float);
+    greedy_kernel<<<batch, kThreads, sm, st>>>(a);
+    AC_LAUNCHED("greedy_kernel");
+    return AC_OK;
+}
+
+int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_emb_len, int batch, int t_mem,
+                int max_len, int beam, float temp, int start_idx, int end_idx, int pad_idx, int64_t* seq, void* ws,
+                size_t ws_bytes, void* stream) {
+    using namespace ac;
+    int rc = trm_common_checks(dec, batch, t_mem, max_len); if (rc) return rc;
+    AC_REQUIRE(attn_emb && attn_emb_len && seq, "ac_trm_beam: null argument");
+    AC_REQUIRE(beam >= 1 && beam <= 5, "ac_trm_beam: beam_size %d not in [1,5]", beam);
+    AC_REQUIRE(temp > 0.f, "ac_trm_beam: temp must be > 0");
+    if (batch == 0) return AC_OK;
+    TrmWs s = trm_ws(dec, batch, beam, t_mem, max_len);
+    AC_REQUIRE(ws && ws_bytes >= (s.proj + s.kvmem + s.cache + s.logits) * sizeof(float), "ac_trm_beam: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* proj = (float*)ws; float* kvmem = proj + s.proj; float* cache = kvmem + s.kvmem; float* lws = cache + s.cache;
+    rc = prepare_memory(dec, attn_emb, batch, t_mem, proj, kvmem, st); if (rc) return rc;
+    DecodeArgs a{};
+    a.w = dec->w; a.kv_mem = kvmem; a.n_clips = batch; a.mem_len = attn_emb_len; a.kv_cache = cache; a.logits_ws = lws;
+    a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
+    a.seq = seq; a.beam = beam; a.temp = temp;
+    size_t sm = dec_smem_floats(beam) * sizeof(float);
+#define AC_BEAM_CASE(RR)                                                                                        \
+    case RR:                                                                                                    \
+        AC_CUDA(cudaFuncSetAttribute(beam_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
+        beam_kernel<RR><<<batch, kThreads, sm, st>>>(a);                                                        \
+        break;
+    switch (beam) {
+        AC_BEAM_CASE(1) AC_BEAM_CASE(2) AC_BEAM_CASE(3) AC_BEAM_CASE(4) AC_BEAM_CASE(5)
+    }
+#undef AC_BEAM_CASE
+    AC_LAUNCHED("beam_kernel");
+    return AC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+/*
+ * audiocaption_b200 -- C ABI of the B200 (sm_100a) hot path of wsntxxn/AudioCaption.
+ *
+ * The reference is pure Python: it has no FFI of its own.  The boundary this library sits
+ * behind is the reference's nn.Module call convention; every entry point
+ * below names the reference code it replaces (paths relative to the reference root).
+ * Host-side mirrors of those modules (audiocaption_b200/captioning/...) bind these symbols
+ * through ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; *_dev pointers are CUDA device pointers owned by the CALLER
+ *     (PyTorch), *_host pointers are host memory; `stream` is a cudaStream_t passed as void*.
+ *   - every call is asynchronous on `stream`; nothing synchronises unless stated.
+ *   - the library owns only the opaque handles it creates (packed, BN-folded weight copies),
+ *     freed with the matching *_destroy.
+ *   - return 0 on success, negative on error; ac_last_error() gives the message
+ *     (thread-local).
+ *   - all arithmetic is fp32 ("dtype": "f32"); token ids / lengths are int64 as in the
+ *     reference.
+ */
+#ifndef AUDIOCAPTION_B200_H
+#define AUDIOCAPTION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AC_OK 0
+#define AC_ERR_ARG (-1)
+#define AC_ERR_CUDA (-2)
+#define AC_ERR_WORKSPACE (-3)
+
+typedef struct ac_frontend ac_frontend_t;
+typedef struct ac_effb2 ac_effb2_t;
+typedef struct ac_trm ac_trm_t;
+
+int ac_version(void);
+const char* ac_last_error(void);
+/* number of kernels launched by this library since process start (bench.py "gpu_launches") */
+int64_t ac_launch_count(void);
+
+/* ------------------------------------------------------------------ log-mel front-end
+ * Replaces torchaudio MelSpectrogram + AmplitudeToDB as called at
+ *   captioning/models/hf_wrapper.py:269-279,292-293   (EffB2: n_fft 512, hop 160, HTK)
+ *   captioning/models/cnn_encoder.py:338-350,418-419  (Cnn14: n_fft 1024, hop 320, Slaney)
+ * window_host[n_fft] and fb_host[n_freqs*n_mels] (row-major [n_freqs, n_mels]) are the
+ * module's own state_dict buffers `spectrogram.window` and `mel_scale.fb`.
+ * n_fft must be 512 or 1024 and win_length == n_fft; n_mels <= 64. */
+int ac_frontend_create(const float* window_host, int n_fft, int hop, const float* fb_host,
+                       int n_freqs, int n_mels, ac_frontend_t** out);
+void ac_frontend_destroy(ac_frontend_t* fe);
+int ac_frontend_num_frames(const ac_frontend_t* fe, int n_samples);
+/* wav_dev [batch, n_samples] -> lms_dev [batch, n_mels, n_frames] = 10*log10(max(mel, 1e-10)).
+ * gmax_dev (nullable, 1 float): receives the maximum over the whole batch (the batch-global
+ * reference of AmplitudeToDB(top_db) for 3-D input); the clamp itself is applied by
+ * ac_db_clamp or fused into ac_effb2_fwd's first layer. */
+int ac_logmel_fwd(const ac_frontend_t* fe, const float* wav_dev, int batch, int n_samples,
+                  float* lms_dev, float* gmax_dev, void* stream);
+/* x = max(x, *gmax - top_db) in place (AmplitudeToDB(top_db=...)). */
+int ac_db_clamp(float* x_dev, int64_t n, const float* gmax_dev, float top_db, void* stream);
+
+/* ------------------------------------------------------------------ EfficientNet-B2 encoder
+ * Replaces hf_wrapper.py:218-241 `_EffiNet.forward` (efficientnet_pytorch 0.7.1
+ * `extract_features` + mean over frequency), eval mode.
+ * tensors_dev: the `backbone.eff_net` state_dict tensors in state_dict order WITHOUT the
+ * `num_batches_tracked` entries; numels[i] is checked against the built-in B2 plan. */
+int ac_effb2_create(const float* const* tensors_dev, const int64_t* numels, int n_tensors,
+                    void* stream, ac_effb2_t** out);
+void ac_effb2_destroy(ac_effb2_t* net);
+int ac_effb2_num_tensors(void);
+int ac_effb2_out_frames(int n_frames);
+int ac_effb2_out_dim(void);
+size_t ac_effb2_workspace_bytes(int batch, int n_mels, int n_frames);
+/* lms_dev [batch, n_mels, n_frames] (dB, NOT yet clamped when gmax_dev != NULL: the
+ * top_db clamp max(x, *gmax - top_db) is applied while the stem convolution loads its
+ * input) -> attn_emb_dev [batch, out_frames, 1408]. */
+int ac_effb2_fwd(const ac_effb2_t* net, const float* lms_dev, const float* gmax_dev, float top_db,
+                 int batch, int n_mels, int n_frames, float* attn_emb_dev,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Introspection of the built-in block plan (tests compare it with the oracle's):
+ * fills out[9] = {cin, cout, expand, k, stride, pad_lo, pad_hi, n_squeeze, has_skip}. */
+int ac_effb2_block_info(int block, int* out9);
+
+/* masked mean over time, hf_wrapper.py:330-352 `mean_with_lens`:
+ * x_dev [batch, T, D], lens_dev [batch] int64 -> out_dev [batch, D] */
+int ac_masked_mean(const float* x_dev, const int64_t* lens_dev, int batch, int T, int D,
+                   float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ Transformer caption decoder
+ * Replaces hf_wrapper.py:976-1068 / captioning/models/transformer_decoder.py:11-103
+ * (TransformerDecoder.forward) and the decode loops of captioning/models/base.py:152-218
+ * (stepwise greedy) and :254-361 (beam search), with a KV cache (eval mode, no dropout).
+ * tensors_dev order: word_embedding.weight, pos_encoder.pe, then per layer
+ *   self_attn.in_proj_weight, self_attn.in_proj_bias, self_attn.out_proj.weight, .bias,
+ *   multihead_attn.in_proj_weight, .in_proj_bias, .out_proj.weight, .bias,
+ *   linear1.weight, .bias, linear2.weight, .bias, norm1.weight, .bias, norm2.*, norm3.*,
+ * then classifier.weight, attn_proj.0.weight, attn_proj.0.bias, attn_proj.3.weight, .bias. */
+int ac_trm_create(const float* const* tensors_dev, const int64_t* numels, int n_tensors,
+                  int d_model, int nhead, int nlayers, int dim_ff, int vocab, int attn_emb_dim,
+                  int pe_len, void* stream, ac_trm_t** out);
+void ac_trm_destroy(ac_trm_t* dec);
+int ac_trm_num_tensors(int nlayers);
+size_t ac_trm_workspace_bytes(const ac_trm_t* dec, int rows, int t_mem, int max_len);
+/* Greedy decode of `batch` clips, all max_len steps on the device (rows that emitted <end>
+ * keep emitting <end>, which equals the reference's early-stopped output).
+ * attn_emb_dev [batch, t_mem, attn_emb_dim]; attn_emb_len_dev [batch] int64.
+ * seq_dev [batch, max_len] int64; logprob_dev [batch, max_len] (nullable);
+ * logit_dev [batch, max_len, vocab] (nullable); embed_dev [batch, max_len, d_model] (nullable). */
+int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb_dev, const int64_t* attn_emb_len_dev,
+                  int batch, int t_mem, int max_len, int start_idx, int end_idx, int pad_idx,
+                  int64_t* seq_dev, float* logprob_dev, float* logit_dev, float* embed_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Beam search, one independent search per clip with the reference's bookkeeping
+ * (double log-softmax with temperature, -1000 penalty, `== beam_size` stop rule,
+ * score/(t+1) ranking).  seq_dev [batch, max_len] int64 = best beam per clip. */
+int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb_dev, const int64_t* attn_emb_len_dev,
+                int batch, int t_mem, int max_len, int beam_size, float temp,
+                int start_idx, int end_idx, int pad_idx, int64_t* seq_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

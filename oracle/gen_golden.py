@@ -31,7 +31,23 @@ def effb2_trm(seed=1, batch=8, n=160000):
         g = ref.model(dict(base, sample_method="greedy"))
         b3 = ref(wav, lens, sample_method="beam", beam_size=3)
         b2 = ref(wav, lens, sample_method="beam", beam_size=2, max_length=12)
-    steps = int((g["seq"] != 2).any(0).nonzero().max().item()) + 1 if (g["seq"] != 2).any() else 1
+    # which rows are numerically well-conditioned?  re-decode (reference code) with the audio
+    # memory perturbed by 1e-3 relative noise; rows whose caption changes sit on a near-tie and
+    # are excluded from exact-match checks (fp32 summation order alone can flip them).
+    rd = ref.model.model
+    stable = {k: torch.ones(batch, dtype=torch.bool) for k in ("greedy", "beam3", "beam2")}
+    gen = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for _ in range(8):
+            e = {"attn_emb": g["attn_emb"] * (1 + 1e-3 * torch.randn(g["attn_emb"].shape, generator=gen)),
+                 "attn_emb_len": g["attn_emb_len"], "fc_emb": g["fc_emb"]}
+            pg = rd.forward_decoder({"mode": "inference", "sample_method": "greedy", "max_length": 20, "temp": 1.0}, dict(e))
+            p3 = rd.forward_decoder({"mode": "inference", "sample_method": "beam", "beam_size": 3, "max_length": 20, "temp": 1.0}, dict(e))
+            p2 = rd.forward_decoder({"mode": "inference", "sample_method": "beam", "beam_size": 2, "max_length": 12, "temp": 1.0}, dict(e))
+            stable["greedy"] &= (pg["seq"] == g["seq"]).all(1)
+            stable["beam3"] &= (p3["seq"] == b3).all(1)
+            stable["beam2"] &= (p2["seq"] == b2).all(1)
+    print("stable rows:", {k: v.tolist() for k, v in stable.items()})
     np.savez_compressed(
         os.path.join(OUT, "effb2_trm.npz"),
         seed=seed, batch=batch, n_samples=n, wav_seed=7,
@@ -40,11 +56,12 @@ def effb2_trm(seed=1, batch=8, n=160000):
         lms_stride=np.array([1, 7]),                       # lms[:, ::1, ::7] keeps the file small
         lms=lms[:, :, ::7].numpy(),
         lms_max=lms.max().item(),
-        attn_emb=g["attn_emb"][:3].numpy(),   # first 3 clips only (file size)
-         attn_emb_len=g["attn_emb_len"].numpy(), fc_emb=g["fc_emb"].numpy(),
+        attn_emb=g["attn_emb"].numpy(),  attn_emb_len=g["attn_emb_len"].numpy(), fc_emb=g["fc_emb"].numpy(),
         greedy_seq=g["seq"].numpy(), greedy_logit0=g["logit"][:, :2].numpy(),
         greedy_logprob=g["sampled_logprob"].numpy(), greedy_embed0=g["embed"][:, :2].numpy(),
         beam3_seq=b3.numpy(), beam2_len12_seq=b2.numpy(),
+        greedy_stable=stable["greedy"].numpy(), beam3_stable=stable["beam3"].numpy(),
+        beam2_stable=stable["beam2"].numpy(),
     )
     print("effb2_trm greedy\n", g["seq"], "\nbeam3\n", b3, "\nbeam2/12\n", b2)
 
