@@ -15,6 +15,8 @@ _SIGS = {
     "ac_version": (C.c_int, []),
     "ac_last_error": (C.c_char_p, []),
     "ac_launch_count": (C.c_int64, []),
+    "ac_timing_enable": (None, [C.c_int]),
+    "ac_timing_report": (C.c_int, [C.c_char_p, C.c_int]),
     "ac_frontend_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ac_frontend_destroy": (None, [C.c_void_p]),
     "ac_frontend_num_frames": (C.c_int, [C.c_void_p, C.c_int]),
@@ -84,3 +86,14 @@ def tensor_table(tensors):
 def current_stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def timing_report():
+    """{kernel_name: (launches, total_ms)} since timing was enabled; synchronises the device."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().ac_timing_report(buf, len(buf)), "ac_timing_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out

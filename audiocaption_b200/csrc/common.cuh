@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -28,6 +29,18 @@ inline int check_cuda(cudaError_t e, const char* what) {
         int _rc = ::ac::check_cuda((call), #call);                  \
         if (_rc != AC_OK) return _rc;                               \
     } while (0)
+
+// Optional per-kernel CUDA-event timing (bench.py's roofline leg): when enabled, a pair of events
+// brackets every launch on its own stream; ac_timing_report() resolves them after a sync.
+void timing_begin(const char* name, cudaStream_t st);
+void timing_end(cudaStream_t st);
+extern bool g_timing;
+struct LaunchTimer {
+    cudaStream_t st; bool on;
+    LaunchTimer(const char* name, cudaStream_t s) : st(s), on(g_timing) { if (on) timing_begin(name, st); }
+    ~LaunchTimer() { if (on) timing_end(st); }
+};
+#define AC_TIMED(name, st) ::ac::LaunchTimer _ac_timer_##__LINE__(name, st)
 
 // call after every kernel launch
 #define AC_LAUNCHED(name)                                           \

@@ -335,6 +335,7 @@ static int launch_dw(const float* in, const ConvBN& cw, float* out, float* parti
     const int strips_w = cdiv(dd.W, kDwStrip);
     dim3 grid(dd.H * strips_w, B);
     size_t sm = (size_t)G * per * sizeof(float4);
+    AC_TIMED(bp.k == 3 ? "dwconv_k3" : "dwconv_k5", st);
     if (bp.k == 3)
         dwconv_kernel<3><<<grid, threads, sm, st>>>(in, cw.w, cw.scale, cw.bias, out, partial, di.H, di.W, dd.H,
                                                     dd.W, C, bp.s, bp.pad_lo, per, G, strips_w);
@@ -485,10 +486,10 @@ void ac_effb2_destroy(ac_effb2_t* net) {
 int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, float top_db, int B, int n_mels,
                  int n_frames, float* attn_emb, void* workspace, size_t ws_bytes, void* stream) {
     using namespace ac;
-    AC_REQUIRE(net && lms && attn_emb, "ac_effb2_fwd: null argument");
     AC_REQUIRE(B >= 0 && B <= 65535, "ac_effb2_fwd: batch %d out of range", B);
     AC_REQUIRE(n_mels >= 8 && n_frames >= 32, "ac_effb2_fwd: input %dx%d too small", n_mels, n_frames);
     if (B == 0) return AC_OK;
+    AC_REQUIRE(net && lms && attn_emb, "ac_effb2_fwd: null argument");
     AC_REQUIRE(workspace && ws_bytes >= ac_effb2_workspace_bytes(B, n_mels, n_frames),
                "ac_effb2_fwd: workspace too small (%zu < %zu)", ws_bytes, ac_effb2_workspace_bytes(B, n_mels, n_frames));
     const Plan& P = plan();
@@ -507,6 +508,7 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
     walk(n_mels, n_frames, stem, din, dout);
     {
         int64_t total = (int64_t)B * stem.H * stem.W * P.stem_out / 4;
+        AC_TIMED("stem", st);
         stem_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(lms, gmax, top_db, net->stem.w, net->stem.scale,
                                                                   net->stem.bias, X0, n_mels, n_frames, stem.H,
                                                                   stem.W, P.stem_out, P.stem_pad_lo, total);
@@ -527,9 +529,12 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         }
         int rc = launch_dw(dw_in, w.dw, D, PART, B, din[i], dout[i], ce, b, st); if (rc) return rc;
         const int strips = dout[i].H * cdiv(dout[i].W, kDwStrip);
+        {
+        AC_TIMED("se", st);
         se_kernel<<<B, 256, (ce + b.nsq) * sizeof(float), st>>>(PART, strips, 1.0f / (float)pout, w.se_wr, w.se_br,
                                                                 w.se_we, w.se_be, GATE, ce, b.nsq);
         AC_LAUNCHED("se_kernel");
+        }
         GemmArgs g; g.A = D; g.W = w.project.w; g.C = nxt; g.M = B * pout; g.N = b.cout; g.K = ce;
         g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
         g.act = ACT_NONE; g.R = b.skip ? cur : nullptr;
@@ -542,6 +547,7 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         g.K = P.head_in; g.cscale = net->head.scale; g.cbias = net->head.bias; g.act = ACT_SWISH;
         int rc = gemm_tn(g, st); if (rc) return rc;
         int64_t total = (int64_t)B * last.W * P.head_out / 4;
+        AC_TIMED("freq_mean", st);
         freq_mean_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(HEAD, attn_emb, last.H, last.W, P.head_out, total);
         AC_LAUNCHED("freq_mean_kernel");
     }
@@ -549,8 +555,8 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
 }
 
 int ac_masked_mean(const float* x, const int64_t* lens, int batch, int T, int D, float* out, void* stream) {
-    AC_REQUIRE(x && lens && out, "ac_masked_mean: null argument");
     if (batch == 0 || D == 0) return AC_OK;
+    AC_REQUIRE(x && lens && out, "ac_masked_mean: null argument");
     dim3 grid(ac::cdiv(D, 128), batch);
     ac::masked_mean_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, lens, T, D, out);
     AC_LAUNCHED("masked_mean_kernel");

@@ -133,6 +133,8 @@ gemm_tn_kernel(GemmArgs g) {
 template <int BM, int BN, int TM, int TN>
 static int launch(const GemmArgs& g, cudaStream_t st) {
     dim3 grid(cdiv(g.M, BM), cdiv(g.N, BN));
+    static const std::string name = "gemm_tn_" + std::to_string(BM) + "x" + std::to_string(BN);
+    AC_TIMED(name.c_str(), st);
     gemm_tn_kernel<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g);
     AC_LAUNCHED("gemm_tn_kernel");
     return AC_OK;

@@ -34,12 +34,6 @@ constexpr int kMelWarps = kMelThreads / 32;
 constexpr int kMaxMels = 64;
 
 template <int NFFT>
-struct MelSmem {
-    static constexpr int M = NFFT / 2;
-    static constexpr int kSegMax = 0;  // dynamic: (kFramesPerCta-1)*hop + NFFT
-};
-
-template <int NFFT>
 __global__ void __launch_bounds__(kMelThreads)
 logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int hop, int n_mels,
               const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -231,11 +225,12 @@ int ac_frontend_num_frames(const ac_frontend_t* fe, int n_samples) { return 1 + 
 
 int ac_logmel_fwd(const ac_frontend_t* fe, const float* wav_dev, int batch, int n_samples,
                   float* lms_dev, float* gmax_dev, void* stream) {
-    AC_REQUIRE(fe && wav_dev && lms_dev, "ac_logmel_fwd: null argument");
+    AC_REQUIRE(fe, "ac_logmel_fwd: null front-end");
     AC_REQUIRE(batch >= 0 && batch <= 65535, "ac_logmel_fwd: batch %d out of range", batch);
     AC_REQUIRE(n_samples > fe->n_fft / 2, "ac_logmel_fwd: n_samples %d too short for reflect padding of %d",
                n_samples, fe->n_fft / 2);
     if (batch == 0) return AC_OK;
+    AC_REQUIRE(wav_dev && lms_dev, "ac_logmel_fwd: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int T = 1 + n_samples / fe->hop;
     if (gmax_dev) {
@@ -243,6 +238,7 @@ int ac_logmel_fwd(const ac_frontend_t* fe, const float* wav_dev, int batch, int 
         AC_LAUNCHED("fill_kernel");
     }
     dim3 grid(ac::cdiv(T, ac::kFramesPerCta), batch);
+    AC_TIMED("logmel", st);
     if (fe->n_fft == 512) {
         size_t sm = ac::logmel_smem_bytes<512>(fe->hop);
         ac::logmel_kernel<512><<<grid, ac::kMelThreads, sm, st>>>(

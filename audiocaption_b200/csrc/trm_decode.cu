@@ -33,7 +33,7 @@ constexpr int NH = 4;           // heads
 constexpr int HD = 64;          // head dim
 constexpr int kMaxKeys = 128;   // max(t_mem, max_len)
 constexpr int kMaxLen = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;     // 32 warps: enough loads in flight to stream the weights from L2
 constexpr int kWarps = kThreads / 32;
 
 struct LayerW {
@@ -49,31 +49,53 @@ constexpr int kMaxLayers = 4;
 struct DecW {
     const float* emb;     // [V][D]
     const float* pe;      // [pe_len][D]
-    const float* cls_wt;  // [D][V]
+    const float* cls_wt;  // [D][Vp], Vp = vocab rounded up to 4 (zero-padded columns)
     const float *proj_w, *proj_b, *proj_ln_g, *proj_ln_b;   // attn_proj: [D][attn_emb_dim] original layout
     LayerW layer[kMaxLayers];
     int nlayers, dff, vocab, attn_emb_dim, pe_len;
 };
 
 // ------------------------------------------------------------------------------------ helpers
-// out[r][n] = act(bias[n] + sum_k xin[r][k] * Wt[k][n]); xin/out in shared memory.
+// out[r][n] = act(bias[n] + sum_k xin[r][k] * Wt[k][n]); xin/out/part in shared memory.
+// Split-K inside the CTA: thread = (K-slice s, column quad c) streams its slice of 4 adjacent
+// columns with independent 128-bit loads (a warp reads 512 contiguous bytes per k), partial sums go
+// through `part` [KS][R][N] and are reduced in a fixed order (deterministic).  N % 4 == 0.
 template <int R>
 __device__ __forceinline__ void matvec_t(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                         const float* xin, int ldx, float* out, int ldo, int N, int K, bool relu) {
-    for (int n = threadIdx.x; n < N; n += kThreads) {
-        float acc[R];
-        const float b0 = bias ? __ldg(bias + n) : 0.0f;
+                                         const float* xin, int ldx, float* out, int ldo, int N, int K, bool relu,
+                                         float* part) {
+    const int NC = N >> 2;
+    const int KS = max(1, min(kThreads / NC, 16));
+    const int kslice = (K + KS - 1) / KS;
+    const int tid = threadIdx.x;
+    const int s = tid / NC, c = tid - s * NC;
+    if (s < KS) {
+        const int k0 = s * kslice, k1 = min(K, k0 + kslice);
+        float acc[R][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = b0;
-        const float* w = Wt + n;
+        for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+        const float4* w = reinterpret_cast<const float4*>(Wt) + c;
 #pragma unroll 8
-        for (int k = 0; k < K; ++k) {
-            const float wv = __ldg(w + (size_t)k * N);
+        for (int k = k0; k < k1; ++k) {
+            const float4 wv = __ldg(w + (size_t)k * NC);
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = fmaf(wv, xin[r * ldx + k], acc[r]);
+            for (int r = 0; r < R; ++r) {
+                const float xv = xin[r * ldx + k];
+                acc[r][0] = fmaf(wv.x, xv, acc[r][0]); acc[r][1] = fmaf(wv.y, xv, acc[r][1]);
+                acc[r][2] = fmaf(wv.z, xv, acc[r][2]); acc[r][3] = fmaf(wv.w, xv, acc[r][3]);
+            }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[r * ldo + n] = relu ? fmaxf(acc[r], 0.0f) : acc[r];
+        for (int r = 0; r < R; ++r)
+            *reinterpret_cast<float4*>(part + ((size_t)s * R + r) * N + 4 * c) =
+                make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < R * N; i += kThreads) {
+        const int r = i / N, n = i - r * N;
+        float v = bias ? __ldg(bias + n) : 0.0f;
+        for (int q = 0; q < KS; ++q) v += part[((size_t)q * R + r) * N + n];
+        out[r * ldo + n] = relu ? fmaxf(v, 0.0f) : v;
     }
 }
 
@@ -143,13 +165,15 @@ struct DecodeArgs {
 template <int R>
 __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* words, const int (*anc)[kMaxLen],
                              const unsigned char (*padflag)[8], float* s_x, float* s_q, float* s_att, float* s_h,
-                             float* s_sc, float* logits) {
+                             float* s_sc, float* s_part, float* logits) {
     const DecW& W = a.w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_mem = min((int)min((int64_t)a.t_mem, a.mem_len[clip]), a.t_mem);
     // embedding * sqrt(d) + positional encoding
-    for (int r = 0; r < R; ++r)
-        s_x[r * D + tid] = __ldg(W.emb + (size_t)words[r] * D + tid) * 16.0f + __ldg(W.pe + (size_t)t * D + tid);
+    for (int i = tid; i < R * D; i += kThreads) {
+        const int r = i / D, f = i - r * D;
+        s_x[i] = __ldg(W.emb + (size_t)words[r] * D + f) * 16.0f + __ldg(W.pe + (size_t)t * D + f);
+    }
     __syncthreads();
 
     for (int l = 0; l < W.nlayers; ++l) {
@@ -157,12 +181,13 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
         float* kc = a.kv_cache + ((((size_t)clip * W.nlayers + l) * 2 + 0) * a.max_len) * R * D;
         float* vc = a.kv_cache + ((((size_t)clip * W.nlayers + l) * 2 + 1) * a.max_len) * R * D;
         // ---- self attention
-        matvec_t<R>(L.sa_in_wt, L.sa_in_b, s_x, D, s_h, 3 * D, 3 * D, D, false);
+        matvec_t<R>(L.sa_in_wt, L.sa_in_b, s_x, D, s_h, 3 * D, 3 * D, D, false, s_part);
         __syncthreads();
-        for (int r = 0; r < R; ++r) {
-            s_q[r * D + tid] = s_h[r * 3 * D + tid] * 0.125f;
-            kc[((size_t)t * R + r) * D + tid] = s_h[r * 3 * D + D + tid];
-            vc[((size_t)t * R + r) * D + tid] = s_h[r * 3 * D + 2 * D + tid];
+        for (int i = tid; i < R * D; i += kThreads) {
+            const int r = i / D, f = i - r * D;
+            s_q[i] = s_h[r * 3 * D + f] * 0.125f;
+            kc[((size_t)t * R + r) * D + f] = s_h[r * 3 * D + D + f];
+            vc[((size_t)t * R + r) * D + f] = s_h[r * 3 * D + 2 * D + f];
         }
         __syncthreads();   // also orders the cache writes before the reads below (same CTA)
         const int nk = t + 1;
@@ -177,19 +202,20 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
         __syncthreads();
         softmax_rows<R>(s_sc, nk);
         __syncthreads();
-        for (int r = 0; r < R; ++r) {
-            const float* p = s_sc + (r * NH + tid / HD) * kMaxKeys;
+        for (int i = tid; i < R * D; i += kThreads) {
+            const int r = i / D, f = i - r * D;
+            const float* p = s_sc + (r * NH + f / HD) * kMaxKeys;
             float o = 0.f;
-            for (int j = 0; j < nk; ++j) o = fmaf(p[j], vc[((size_t)j * R + anc[r][j]) * D + tid], o);
-            s_att[r * D + tid] = o;
+            for (int j = 0; j < nk; ++j) o = fmaf(p[j], vc[((size_t)j * R + anc[r][j]) * D + f], o);
+            s_att[i] = o;
         }
         __syncthreads();
-        matvec_t<R>(L.sa_out_wt, L.sa_out_b, s_att, D, s_q, D, D, D, false);
+        matvec_t<R>(L.sa_out_wt, L.sa_out_b, s_att, D, s_q, D, D, D, false, s_part);
         __syncthreads();
         add_layernorm<R>(s_x, s_q, L.n1_g, L.n1_b);
         __syncthreads();
         // ---- cross attention over the projected audio memory
-        matvec_t<R>(L.ca_q_wt, L.ca_q_b, s_x, D, s_q, D, D, D, false);
+        matvec_t<R>(L.ca_q_wt, L.ca_q_b, s_x, D, s_q, D, D, D, false, s_part);
         __syncthreads();
         const float* km = a.kv_mem + (((size_t)l * a.n_clips + clip) * a.t_mem) * 2 * D;
         for (int it = warp; it < R * NH * a.t_mem; it += kWarps) {
@@ -203,40 +229,48 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
         __syncthreads();
         softmax_rows<R>(s_sc, a.t_mem);
         __syncthreads();
-        for (int r = 0; r < R; ++r) {
-            const float* p = s_sc + (r * NH + tid / HD) * kMaxKeys;
+        for (int i = tid; i < R * D; i += kThreads) {
+            const int r = i / D, f = i - r * D;
+            const float* p = s_sc + (r * NH + f / HD) * kMaxKeys;
             float o = 0.f;
-            for (int j = 0; j < n_mem; ++j) o = fmaf(p[j], __ldg(km + (size_t)j * 2 * D + D + tid), o);
-            s_att[r * D + tid] = o;
+            for (int j = 0; j < n_mem; ++j) o = fmaf(p[j], __ldg(km + (size_t)j * 2 * D + D + f), o);
+            s_att[i] = o;
         }
         __syncthreads();
-        matvec_t<R>(L.ca_out_wt, L.ca_out_b, s_att, D, s_q, D, D, D, false);
+        matvec_t<R>(L.ca_out_wt, L.ca_out_b, s_att, D, s_q, D, D, D, false, s_part);
         __syncthreads();
         add_layernorm<R>(s_x, s_q, L.n2_g, L.n2_b);
         __syncthreads();
         // ---- feed forward
-        matvec_t<R>(L.ff1_wt, L.ff1_b, s_x, D, s_h, W.dff, W.dff, D, true);
+        matvec_t<R>(L.ff1_wt, L.ff1_b, s_x, D, s_h, W.dff, W.dff, D, true, s_part);
         __syncthreads();
-        matvec_t<R>(L.ff2_wt, L.ff2_b, s_h, W.dff, s_q, D, D, W.dff, false);
+        matvec_t<R>(L.ff2_wt, L.ff2_b, s_h, W.dff, s_q, D, D, W.dff, false, s_part);
         __syncthreads();
         add_layernorm<R>(s_x, s_q, L.n3_g, L.n3_b);
         __syncthreads();
     }
-    // ---- classifier (no bias)
-    const int V = W.vocab;
-    for (int n = tid; n < V; n += kThreads) {
-        float acc[R];
+    // ---- classifier (no bias): each thread owns column quads of the zero-padded [D][Vp] weight
+    const int V = W.vocab, VC = (V + 3) >> 2;
+    for (int c = tid; c < VC; c += kThreads) {
+        float acc[R][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f;
-        const float* w = W.cls_wt + n;
+        for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+        const float4* w = reinterpret_cast<const float4*>(W.cls_wt) + c;
 #pragma unroll 8
         for (int k = 0; k < D; ++k) {
-            const float wv = __ldg(w + (size_t)k * V);
+            const float4 wv = __ldg(w + (size_t)k * VC);
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = fmaf(wv, s_x[r * D + k], acc[r]);
+            for (int r = 0; r < R; ++r) {
+                const float xv = s_x[r * D + k];
+                acc[r][0] = fmaf(wv.x, xv, acc[r][0]); acc[r][1] = fmaf(wv.y, xv, acc[r][1]);
+                acc[r][2] = fmaf(wv.z, xv, acc[r][2]); acc[r][3] = fmaf(wv.w, xv, acc[r][3]);
+            }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) logits[(size_t)r * V + n] = acc[r];
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (4 * c + q < V) logits[(size_t)r * V + 4 * c + q] = acc[r][q];
     }
     __syncthreads();
 }
@@ -280,7 +314,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_v) {
     return t;
 }
 
-constexpr size_t dec_smem_floats(int R) { return (size_t)R * (D + D + D + 1024 + NH * kMaxKeys); }
+constexpr size_t dec_smem_floats(int R) { return (size_t)R * (D + D + D + 1024 + NH * kMaxKeys + 4096); }
 
 // ------------------------------------------------------------------------------------ greedy
 __global__ void __launch_bounds__(kThreads)
@@ -288,6 +322,7 @@ greedy_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* s_x = smem; float* s_q = s_x + D; float* s_att = s_q + D; float* s_h = s_att + D;
     float* s_sc = s_h + 1024;
+    float* s_part = s_sc + NH * kMaxKeys;
     __shared__ int s_anc[1][kMaxLen];
     __shared__ unsigned char s_pad[kMaxLen][8];
     __shared__ float s_rv[kWarps];
@@ -300,16 +335,20 @@ greedy_kernel(DecodeArgs a) {
     int word = a.start_idx;
     bool finished = false;
     __syncthreads();
+    // The reference keeps running finished rows (input forced to <end>) until EVERY row of the batch
+    // has finished and records their logits/embeds; when those outputs are requested we do the same
+    // for all max_len steps (a superset: past the reference's break its buffers are uninitialised).
+    const bool full_outputs = a.logit_out != nullptr || a.embed_out != nullptr;
     for (int t = 0; t < a.max_len; ++t) {
-        if (finished) {   // rows that emitted <end> keep <end> (base.py:161-168)
+        if (finished && !full_outputs) {   // rows that emitted <end> keep <end> (base.py:161-168)
             if (tid == 0) a.seq[(size_t)clip * a.max_len + t] = a.end_idx;
             continue;
         }
         if (tid == 0) { s_pad[t][0] = (word == a.pad_idx); s_word = word; }
         __syncthreads();
         float* logits = a.logit_out ? a.logit_out + ((size_t)clip * a.max_len + t) * V : logits_ws;
-        decoder_step<1>(a, clip, t, &s_word, s_anc, s_pad, s_x, s_q, s_att, s_h, s_sc, logits);
-        if (a.embed_out) a.embed_out[((size_t)clip * a.max_len + t) * D + tid] = s_x[tid];
+        decoder_step<1>(a, clip, t, &s_word, s_anc, s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, logits);
+        if (a.embed_out && tid < D) a.embed_out[((size_t)clip * a.max_len + t) * D + tid] = s_x[tid];
         // log-softmax + argmax (first maximum wins, as torch.max on CPU)
         float best = -INFINITY; int bi = 0x7fffffff;
         for (int n = tid; n < V; n += kThreads) {
@@ -320,12 +359,12 @@ greedy_kernel(DecodeArgs a) {
         float se = 0.f;
         for (int n = tid; n < V; n += kThreads) se += expf(logits[n] - best);
         se = block_sum(se, s_rv);
-        word = bi;
+        word = finished ? a.end_idx : bi;
         if (tid == 0) {
             a.seq[(size_t)clip * a.max_len + t] = word;
             if (a.logprob) a.logprob[(size_t)clip * a.max_len + t] = -logf(se);
         }
-        finished = (word == a.end_idx);
+        finished = finished || (word == a.end_idx);
     }
 }
 
@@ -336,6 +375,7 @@ beam_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* s_x = smem; float* s_q = s_x + R * D; float* s_att = s_q + R * D; float* s_h = s_att + R * D;
     float* s_sc = s_h + R * 1024;
+    float* s_part = s_sc + R * NH * kMaxKeys;
     __shared__ int s_anc[2][R][kMaxLen];
     __shared__ unsigned char s_pad[kMaxLen][8];
     __shared__ int s_seq[2][R][kMaxLen];
@@ -360,7 +400,7 @@ beam_kernel(DecodeArgs a) {
         if (tid < R) s_pad[t][tid] = (s_words[tid] == a.pad_idx);
         if (tid < R) s_anc[cur][tid][t] = tid;
         __syncthreads();
-        decoder_step<R>(a, clip, t, s_words, s_anc[cur], s_pad, s_x, s_q, s_att, s_h, s_sc, lp);
+        decoder_step<R>(a, clip, t, s_words, s_anc[cur], s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, lp);
         // lp = log_softmax(log_softmax(logit) / temp) + running score   (base.py:282-290)
         for (int r = 0; r < R; ++r) {
             float* row = lp + (size_t)r * V;
@@ -452,6 +492,15 @@ __global__ void layernorm_rows_kernel(float* __restrict__ x, const float* __rest
     }
 }
 
+// in [rows][cols] -> out [cols][ld] (ld >= rows)
+__global__ void transpose_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int ld) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)rows * cols) {
+        int r = (int)(i / cols), c = (int)(i % cols);
+        out[(size_t)c * ld + r] = in[i];
+    }
+}
+
 __global__ void transpose2_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)rows * cols) {
@@ -486,8 +535,11 @@ static int prepare_memory(const ac_trm* d, const float* attn_emb, int clips, int
     g.cbias = W.proj_b; g.act = ACT_RELU;
     int rc = gemm_tn(g, st); if (rc) return rc;
     int64_t rows = (int64_t)clips * t_mem;
-    layernorm_rows_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, st>>>(proj, W.proj_ln_g, W.proj_ln_b, rows);
-    AC_LAUNCHED("layernorm_rows_kernel");
+    {
+        AC_TIMED("layernorm_rows", st);
+        layernorm_rows_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, st>>>(proj, W.proj_ln_g, W.proj_ln_b, rows);
+        AC_LAUNCHED("layernorm_rows_kernel");
+    }
     for (int l = 0; l < W.nlayers; ++l) {
         // one [clips*t_mem, D] x [D, 2D] GEMM per layer; kvmem layout [layer][clip][t][K | V]
         GemmArgs k; k.A = proj; k.W = W.layer[l].ca_kv_w; k.M = clips * t_mem; k.N = 2 * D; k.K = D;
@@ -527,7 +579,7 @@ int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, i
     for (int i = 0; i < n_tensors; ++i)
         AC_REQUIRE(numels[i] == want[i], "ac_trm_create: tensor %d has %lld elements, expected %lld", i,
                    (long long)numels[i], (long long)want[i]);
-    size_t total = 0;
+    size_t total = align_up((size_t)D * ((V + 3) / 4 * 4), 64);   // padded classifier copy
     for (auto n : want) total += align_up((size_t)n, 64);
     ac_trm_t* d = new ac_trm_t();
     AC_CUDA(cudaMalloc(&d->blob, total * sizeof(float)));
@@ -576,7 +628,15 @@ int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, i
         L.ff2_b = plain();
         L.n1_g = plain(); L.n1_b = plain(); L.n2_g = plain(); L.n2_b = plain(); L.n3_g = plain(); L.n3_b = plain();
     }
-    W.cls_wt = transposed(V, D, t[ti]); off += align_up((size_t)want[ti], 64); ++ti;
+    {   // classifier [V][D] -> zero-padded [D][Vp]
+        const int Vp = (V + 3) / 4 * 4;
+        float* p = d->blob + off;
+        if (rc == AC_OK) rc = check_cuda(cudaMemsetAsync(p, 0, (size_t)D * Vp * sizeof(float), st), "memset cls");
+        transpose_pad_kernel<<<(unsigned)cdiv64((int64_t)V * D, 256), 256, 0, st>>>(t[ti], p, V, D, Vp);
+        g_launches++;
+        W.cls_wt = p;
+        off += align_up((size_t)D * Vp, 64); ++ti;
+    }
     W.proj_w = plain(); W.proj_b = plain(); W.proj_ln_g = plain(); W.proj_ln_b = plain();
     if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_trm_create pack kernels");
     if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_trm_create sync");
@@ -614,8 +674,8 @@ int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* att
                   float* embed, void* ws, size_t ws_bytes, void* stream) {
     using namespace ac;
     int rc = trm_common_checks(dec, batch, t_mem, max_len); if (rc) return rc;
-    AC_REQUIRE(attn_emb && attn_emb_len && seq, "ac_trm_greedy: null argument");
     if (batch == 0) return AC_OK;
+    AC_REQUIRE(attn_emb && attn_emb_len && seq, "ac_trm_greedy: null argument");
     TrmWs s = trm_ws(dec, batch, 1, t_mem, max_len);
     AC_REQUIRE(ws && ws_bytes >= (s.proj + s.kvmem + s.cache + s.logits) * sizeof(float), "ac_trm_greedy: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -626,6 +686,7 @@ int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* att
     a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
     a.seq = seq; a.logprob = logprob; a.logit_out = logit; a.embed_out = embed; a.beam = 1; a.temp = 1.0f;
     size_t sm = dec_smem_floats(1) * sizeof(float);
+    AC_TIMED("trm_greedy", st);
     greedy_kernel<<<batch, kThreads, sm, st>>>(a);
     AC_LAUNCHED("greedy_kernel");
     return AC_OK;
@@ -636,6 +697,7 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
                 size_t ws_bytes, void* stream) {
     using namespace ac;
     int rc = trm_common_checks(dec, batch, t_mem, max_len); if (rc) return rc;
+    if (batch == 0) return AC_OK;
     AC_REQUIRE(attn_emb && attn_emb_len && seq, "ac_trm_beam: null argument");
     AC_REQUIRE(beam >= 1 && beam <= 5, "ac_trm_beam: beam_size %d not in [1,5]", beam);
     AC_REQUIRE(temp > 0.f, "ac_trm_beam: temp must be > 0");
@@ -650,6 +712,7 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
     a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
     a.seq = seq; a.beam = beam; a.temp = temp;
     size_t sm = dec_smem_floats(beam) * sizeof(float);
+    AC_TIMED("trm_beam", st);
 #define AC_BEAM_CASE(RR)                                                                                        \
     case RR:                                                                                                    \
         AC_CUDA(cudaFuncSetAttribute(beam_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \

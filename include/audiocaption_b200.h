@@ -41,6 +41,11 @@ int ac_version(void);
 const char* ac_last_error(void);
 /* number of kernels launched by this library since process start (bench.py "gpu_launches") */
 int64_t ac_launch_count(void);
+/* Optional per-kernel CUDA-event timing for bench.py's roofline leg: when enabled every launch is
+ * bracketed by an event pair on its stream; ac_timing_report synchronises the device and writes
+ * "kernel_name launches total_ms" lines into buf, then clears the record. */
+void ac_timing_enable(int on);
+int ac_timing_report(char* buf, int buf_len);
 
 /* ------------------------------------------------------------------ log-mel front-end
  * Replaces torchaudio MelSpectrogram + AmplitudeToDB as called at
