@@ -130,105 +130,157 @@ stem_kernel(const float* __restrict__ lms, const float* __restrict__ gmax, float
 }
 
 // ----------------------------------------------------------------------------- depthwise
-// in [B,Hi,Wi,C] -> out [B,Ho,Wo,C], k x k stride s, BN + swish, plus the per-strip channel sums
-// that feed squeeze-and-excitation: partial[b][strip][c] (deterministic two-level reduction).
-// One CTA = one strip of `pw` output pixels of one output row; thread = (pixel group g, channel
-// quad c4) and walks pixels g, g+G, ...  Consecutive threads hold consecutive channel quads, so
-// every global access is a coalesced 128-bit load/store.
-constexpr int kDwStrip = 32;
+// in [B,Hi,Wi,C] -> out [B,Ho,Wo,C], k x k stride s ("static same" pads), BN + swish, plus the per-segment
+// channel sums that feed squeeze-and-excitation: partial[b][ho * nseg + seg][c] (deterministic).
+//
+// One thread owns V consecutive channels of one output row and walks a segment of `lw` output pixels along
+// W with a K x K register window: per output it loads only the S new input columns (K*S vectors instead of
+// K*K), the K*K weights stay in registers.  Threads are laid out channel-fastest, then output row, so a warp
+// reads contiguous channel runs (coalesced 128-bit loads) and the K-row vertical overlap between neighbouring
+// output rows is served by L1 inside the CTA.
+template <int V> struct VecT;
+template <> struct VecT<4> { typedef float4 type; };
+template <> struct VecT<2> { typedef float2 type; };
+template <int V> __device__ __forceinline__ void vec_fma(float (&acc)[V], const float (&x)[V], const float (&w)[V]) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = fmaf(x[e], w[e], acc[e]);
+}
+template <int V> __device__ __forceinline__ void vec_load(float (&d)[V], const float* p) {
+    typedef typename VecT<V>::type T;
+    *reinterpret_cast<T*>(d) = __ldg(reinterpret_cast<const T*>(p));
+}
 
-template <int K>
-__global__ void __launch_bounds__(256)
+template <int K, int S, int V>
+__global__ void __launch_bounds__(K == 3 ? 256 : 128, K == 3 ? 2 : 3)
 dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w /*[K*K][C]*/,
               const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ out,
-              float* __restrict__ partial, int Hi, int Wi, int Ho, int Wo, int C, int stride, int pad_lo,
-              int per /*channel quads per pass*/, int G, int strips_w) {
-    extern __shared__ __align__(16) float4 s_part[];   // [G][per]
-    const int c4n = C / 4;
-    const int strip = blockIdx.x;              // ho * strips_w + ws
-    const int ho = strip / strips_w, ws = strip % strips_w;
-    const int b = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int g = tid / per, cl = tid % per;
-    const bool active = g < G;
-    const int wo0 = ws * kDwStrip;
-    const int npx = min(kDwStrip, Wo - wo0);
-    const float4* in4 = reinterpret_cast<const float4*>(in) + (size_t)b * Hi * Wi * c4n;
-    float4* out4 = reinterpret_cast<float4*>(out) + ((size_t)(b * Ho + ho) * Wo) * c4n;
-    const float4* w4 = reinterpret_cast<const float4*>(w);
+              float* __restrict__ partial, int Hi, int Wi, int Ho, int Wo, int C, int pad_lo, int lw, int nseg,
+              int64_t total) {
+    typedef typename VecT<V>::type T;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cvn = C / V;
+    const int c = (int)(idx % cvn) * V;
+    int64_t r = idx / cvn;
+    const int ho = (int)(r % Ho); r /= Ho;
+    const int seg = (int)(r % nseg);
+    const int b = (int)(r / nseg);
+    const int wo0 = seg * lw, wo1 = min(wo0 + lw, Wo);
 
-    for (int cbase = 0; cbase < c4n; cbase += per) {
-        const int c4 = cbase + cl;
-        const bool on = active && c4 < c4n;
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
-            const float4 bi = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-            for (int p = g; p < npx; p += G) {
-                const int wo = wo0 + p;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wr[K * K][V];
 #pragma unroll
-                for (int kh = 0; kh < K; ++kh) {
-                    const int ih = ho * stride + kh - pad_lo;
-                    if (ih < 0 || ih >= Hi) continue;
+    for (int q = 0; q < K * K; ++q) vec_load<V>(wr[q], w + (size_t)q * C + c);
+    float sc[V], bi[V];
+    vec_load<V>(sc, scale + c);
+    vec_load<V>(bi, bias + c);
+
+    const float* rowp[K];
 #pragma unroll
-                    for (int kw = 0; kw < K; ++kw) {
-                        const int iw = wo * stride + kw - pad_lo;
-                        if (iw < 0 || iw >= Wi) continue;
-                        const float4 v = __ldg(in4 + ((size_t)ih * Wi + iw) * c4n + c4);
-                        const float4 ww = __ldg(w4 + (kh * K + kw) * c4n + c4);
-                        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
-                        acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
-                    }
-                }
-                float4 o = make_float4(swishf(fmaf(acc.x, sc.x, bi.x)), swishf(fmaf(acc.y, sc.y, bi.y)),
-                                       swishf(fmaf(acc.z, sc.z, bi.z)), swishf(fmaf(acc.w, sc.w, bi.w)));
-                out4[(size_t)wo * c4n + c4] = o;
-                sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
-            }
-        }
-        // reduce the G pixel groups (fixed order -> deterministic)
-        if (active) s_part[g * per + cl] = sum;
-        __syncthreads();
-        if (g == 0 && c4 < c4n) {
-            float4 t = s_part[cl];
-            for (int q = 1; q < G; ++q) {
-                float4 u = s_part[q * per + cl];
-                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-            }
-            reinterpret_cast<float4*>(partial)[((size_t)b * gridDim.x + strip) * c4n + c4] = t;
-        }
-        __syncthreads();
+    for (int kh = 0; kh < K; ++kh) {
+        const int ih = ho * S + kh - pad_lo;
+        rowp[kh] = (ih >= 0 && ih < Hi) ? in + ((size_t)(b * Hi + ih) * Wi) * C + c : nullptr;
     }
+    const int iw0 = wo0 * S - pad_lo;              // input column of window slot 0 for the first output
+    float x[K][K][V];                              // [kh][column slot (input column - iw0) % K]
+    auto load_col = [&](int j, int slot) {         // j = input column relative to iw0
+        const int iw = iw0 + j;
+        const bool ok = iw >= 0 && iw < Wi;
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+            if (ok && rowp[kh] != nullptr) vec_load<V>(x[kh][slot], rowp[kh] + (size_t)iw * C);
+            else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) x[kh][slot][e] = 0.0f;
+            }
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < K - S; ++j) load_col(j, j);        // columns shared with the first output's window
+    float sum[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) sum[e] = 0.0f;
+    float* orow = out + ((size_t)(b * Ho + ho) * Wo) * C + c;
+    // outputs in groups of K so that every window slot index is a compile-time constant
+    for (int base = 0; wo0 + base < wo1; base += K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const int wo = wo0 + base + u;
+            if (wo < wo1) {
+                // new columns of this output: relative columns (base+u)*S + K-S .. (base+u)*S + K-1
+#pragma unroll
+                for (int q = 0; q < S; ++q) load_col((base + u) * S + K - S + q, (u * S + K - S + q) % K);
+                float acc[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc[e] = 0.0f;
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) vec_fma<V>(acc, x[kh][(u * S + kw) % K], wr[kh * K + kw]);
+                float o[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    o[e] = swishf(fmaf(acc[e], sc[e], bi[e]));
+                    sum[e] += o[e];
+                }
+                *reinterpret_cast<T*>(orow + (size_t)wo * C) = *reinterpret_cast<const T*>(o);
+            }
+        }
+    }
+    *reinterpret_cast<T*>(partial + ((size_t)b * (Ho * nseg) + (size_t)ho * nseg + seg) * C + c) =
+        *reinterpret_cast<const T*>(sum);
 }
 
 // ----------------------------------------------------------------------------- squeeze-excite
 // partial [B][strips][C] -> gate [B][C] = sigmoid(We * swish(Wr * mean + br) + be).  One CTA per clip.
-__global__ void __launch_bounds__(256)
-se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const float* __restrict__ wr /*[nsq][C]*/,
-          const float* __restrict__ br, const float* __restrict__ we /*[C][nsq]*/, const float* __restrict__ be,
+// wr [nsq][C], we_t [nsq][C] (transposed at pack time so that both FC layers read coalesced rows).
+constexpr int kSeThreads = 512;
+__global__ void __launch_bounds__(kSeThreads)
+se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const float* __restrict__ wr,
+          const float* __restrict__ br, const float* __restrict__ we_t, const float* __restrict__ be,
           float* __restrict__ gate, int C, int nsq) {
-    extern __shared__ float s_se[];   // mean[C] + r[nsq]
+    extern __shared__ __align__(16) float s_se[];   // mean[C] | r[nsq] | scratch[kSeThreads * 4]
     float* s_mean = s_se;
     float* s_r = s_se + C;
+    float4* s_scr = reinterpret_cast<float4*>(s_se + ((C + nsq + 3) / 4) * 4);
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* p = partial + (size_t)b * strips * C;
-    for (int c = tid; c < C; c += blockDim.x) {
-        float s = 0.f;
-        for (int q = 0; q < strips; ++q) s += p[(size_t)q * C + c];
-        s_mean[c] = s * inv_hw;
+    const int c4n = C / 4;
+    const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)b * strips * C);
+    // 1. channel means: thread = (strip group g, channel quad), fixed-order two-level sum (deterministic)
+    for (int cbase = 0; cbase < c4n; cbase += kSeThreads) {
+        const int width = min(c4n - cbase, kSeThreads);
+        const int G = max(1, min(kSeThreads / width, strips));
+        const int g = tid / width, c4 = cbase + tid % width;
+        if (g < G) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = g; q < strips; q += G) {
+                const float4 v = __ldg(p4 + (size_t)q * c4n + c4);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            s_scr[tid] = s;
+        }
+        __syncthreads();
+        if (tid < width) {
+            float4 t = s_scr[tid];
+            for (int q = 1; q < G; ++q) {
+                const float4 u = s_scr[q * width + tid];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            reinterpret_cast<float4*>(s_mean)[c4] = make_float4(t.x * inv_hw, t.y * inv_hw, t.z * inv_hw, t.w * inv_hw);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int j = warp; j < nsq; j += blockDim.x / 32) {
+    // 2. squeeze: r[j] = swish(wr[j] . mean + br[j]), one warp per output
+    for (int j = warp; j < nsq; j += kSeThreads / 32) {
         float s = 0.f;
         for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + (size_t)j * C + c), s_mean[c], s);
         s = warp_sum(s);
         if (lane == 0) s_r[j] = swishf(s + br[j]);
     }
     __syncthreads();
-    for (int c = tid; c < C; c += blockDim.x) {
+    // 3. excite: gate[c] = sigmoid(sum_j we_t[j][c] * r[j] + be[c])
+    for (int c = tid; c < C; c += kSeThreads) {
         float s = 0.f;
-        for (int j = 0; j < nsq; ++j) s = fmaf(__ldg(we + (size_t)c * nsq + j), s_r[j], s);
+        for (int j = 0; j < nsq; ++j) s = fmaf(__ldg(we_t + (size_t)j * C + c), s_r[j], s);
         gate[(size_t)b * C + c] = sigmoidf_(s + be[c]);
     }
 }
@@ -267,7 +319,7 @@ __global__ void masked_mean_kernel(const float* __restrict__ x, const int64_t* _
     out[(size_t)b * D + d] = s / (float)len;
 }
 
-struct ConvBN { float* w; float* scale; float* bias; };
+struct ConvBN { float* w; float* scale; float* bias; TcWeight tw; };
 struct BlockW {
     ConvBN expand, dw, project;
     float *se_wr, *se_br, *se_we, *se_be;
@@ -301,6 +353,17 @@ static void walk(int n_mels, int n_frames, Dims& stem, std::vector<Dims>& in_dim
     }
 }
 
+// Output pixels one depthwise thread walks along W: long segments amortise the K-1 halo columns, short ones
+// keep >= ~4 CTAs per SM in flight on the small late layers.
+static int dw_seg_len(int batch, int Ho, int Wo, int C, int k) {
+    const int V = k == 3 ? 4 : 2;
+    for (int lw = 32; lw > 8; lw /= 2) {
+        const int64_t threads = (int64_t)batch * Ho * cdiv(Wo, lw) * (C / V);
+        if (threads >= (int64_t)kNumSMs * 4 * 256) return lw;
+    }
+    return 8;
+}
+
 struct WsLayout { size_t x_elems, e_elems, d_elems, part_elems, gate_elems, head_elems; };
 
 static WsLayout ws_layout(int batch, int n_mels, int n_frames) {
@@ -315,7 +378,7 @@ static WsLayout ws_layout(int batch, int n_mels, int n_frames) {
         L.x_elems = std::max(L.x_elems, pout * b.cout);
         if (b.expand != 1) L.e_elems = std::max(L.e_elems, pin * b.cexp());
         L.d_elems = std::max(L.d_elems, pout * b.cexp());
-        size_t strips = (size_t)dout[i].H * cdiv(dout[i].W, kDwStrip);
+        size_t strips = (size_t)dout[i].H * cdiv(dout[i].W, dw_seg_len(batch, dout[i].H, dout[i].W, b.cexp(), b.k));
         L.part_elems = std::max(L.part_elems, strips * b.cexp());
         L.gate_elems = std::max(L.gate_elems, (size_t)b.cexp());
     }
@@ -327,21 +390,22 @@ static WsLayout ws_layout(int batch, int n_mels, int n_frames) {
 
 static int launch_dw(const float* in, const ConvBN& cw, float* out, float* partial, int B, Dims di, Dims dd,
                      int C, const BlockPlan& bp, cudaStream_t st) {
-    const int c4n = C / 4;
-    const int chunks = cdiv(c4n, 256);
-    const int per = cdiv(c4n, chunks);
-    const int G = std::max(1, 256 / per);
-    const int threads = (per * G + 31) / 32 * 32;
-    const int strips_w = cdiv(dd.W, kDwStrip);
-    dim3 grid(dd.H * strips_w, B);
-    size_t sm = (size_t)G * per * sizeof(float4);
+    const int lw = dw_seg_len(B, dd.H, dd.W, C, bp.k);
+    const int nseg = cdiv(dd.W, lw);
+    const int V = bp.k == 3 ? 4 : 2;
+    const int64_t total = (int64_t)B * nseg * dd.H * (C / V);
+    const int threads = bp.k == 3 ? 256 : 128;
+    const unsigned grid = (unsigned)cdiv64(total, threads);
     AC_TIMED(bp.k == 3 ? "dwconv_k3" : "dwconv_k5", st);
-    if (bp.k == 3)
-        dwconv_kernel<3><<<grid, threads, sm, st>>>(in, cw.w, cw.scale, cw.bias, out, partial, di.H, di.W, dd.H,
-                                                    dd.W, C, bp.s, bp.pad_lo, per, G, strips_w);
-    else
-        dwconv_kernel<5><<<grid, threads, sm, st>>>(in, cw.w, cw.scale, cw.bias, out, partial, di.H, di.W, dd.H,
-                                                    dd.W, C, bp.s, bp.pad_lo, per, G, strips_w);
+#define AC_DW(K, S, V)                                                                                             \
+    dwconv_kernel<K, S, V><<<grid, threads, 0, st>>>(in, cw.w, cw.scale, cw.bias, out, partial, di.H, di.W, dd.H, dd.W, C, \
+                                                 bp.pad_lo, lw, nseg, total)
+    if (bp.k == 3 && bp.s == 1) AC_DW(3, 1, 4);
+    else if (bp.k == 3 && bp.s == 2) AC_DW(3, 2, 4);
+    else if (bp.k == 5 && bp.s == 1) AC_DW(5, 1, 2);
+    else if (bp.k == 5 && bp.s == 2) AC_DW(5, 2, 2);
+    else { set_error("launch_dw: unsupported depthwise k=%d s=%d", bp.k, bp.s); return AC_ERR_ARG; }
+#undef AC_DW
     AC_LAUNCHED("dwconv_kernel");
     return AC_OK;
 }
@@ -389,21 +453,23 @@ int ac_effb2_create(const float* const* t, const int64_t* numels, int n_tensors,
     // ---- size the packed blob
     size_t total = 0;
     auto take = [&](size_t n) { size_t o = total; total += align_up(n, 64); return o; };
-    struct Off { size_t w, s, b; };
-    auto take_cb = [&](size_t wn, size_t c) { Off o; o.w = take(wn); o.s = take(c); o.b = take(c); return o; };
+    struct Off { size_t w, s, b, pk; };
+    auto take_cb = [&](size_t wn, size_t c) { Off o; o.w = take(wn); o.s = take(c); o.b = take(c); o.pk = 0; return o; };
+    // 1x1 convolutions also get a tensor-core image (BN scale folded in, hi/lo split, swizzled; see gemm.cuh)
+    auto take_pw = [&](int n, int k) { Off o = take_cb((size_t)n * k, n); o.pk = take(tc_packed_floats(n, k)); return o; };
     Off stem_o = take_cb(9 * P.stem_out, P.stem_out);
     struct BOff { Off e, d, p; size_t wr, br, we, be; };
     std::vector<BOff> bo;
     for (auto& b : P.blocks) {
         BOff o{};
         int ce = b.cexp();
-        if (b.expand != 1) o.e = take_cb((size_t)ce * b.cin, ce);
+        if (b.expand != 1) o.e = take_pw(ce, b.cin);
         o.d = take_cb((size_t)b.k * b.k * ce, ce);
         o.wr = take((size_t)b.nsq * ce); o.br = take(b.nsq); o.we = take((size_t)ce * b.nsq); o.be = take(ce);
-        o.p = take_cb((size_t)b.cout * ce, b.cout);
+        o.p = take_pw(b.cout, ce);
         bo.push_back(o);
     }
-    Off head_o = take_cb((size_t)P.head_out * P.head_in, P.head_out);
+    Off head_o = take_pw(P.head_out, P.head_in);
     ac_effb2_t* net = new ac_effb2_t();
     AC_CUDA(cudaMalloc(&net->blob, total * sizeof(float)));
     float* B0 = net->blob;
@@ -442,9 +508,13 @@ int ac_effb2_create(const float* const* t, const int64_t* numels, int n_tensors,
         }
         ti += 4;
     };
+    auto pack_pw = [&](const Off& o, int n, int k, ConvBN& cb) {
+        cb = {B0 + o.w, B0 + o.s, B0 + o.b, TcWeight()};
+        if (rc == AC_OK && k % 8 == 0) rc = tc_pack_weight(B0 + o.w, B0 + o.s, n, k, B0 + o.pk, st, &cb.tw);
+    };
     transposed(stem_o.w, P.stem_out, 9, "_conv_stem.weight");
     bn(stem_o, P.stem_out, "_bn0");
-    net->stem = {B0 + stem_o.w, B0 + stem_o.s, B0 + stem_o.b};
+    net->stem = {B0 + stem_o.w, B0 + stem_o.s, B0 + stem_o.b, TcWeight()};
     for (size_t i = 0; i < P.blocks.size(); ++i) {
         auto& b = P.blocks[i]; auto& o = bo[i];
         int ce = b.cexp();
@@ -452,27 +522,25 @@ int ac_effb2_create(const float* const* t, const int64_t* numels, int n_tensors,
         if (b.expand != 1) {
             copy(o.e.w, (int64_t)ce * b.cin, "_expand_conv.weight");
             bn(o.e, ce, "_bn0");
-            w.expand = {B0 + o.e.w, B0 + o.e.s, B0 + o.e.b};
+            pack_pw(o.e, ce, b.cin, w.expand);
         }
         transposed(o.d.w, ce, b.k * b.k, "_depthwise_conv.weight");
         bn(o.d, ce, "_bn1");
-        w.dw = {B0 + o.d.w, B0 + o.d.s, B0 + o.d.b};
+        w.dw = {B0 + o.d.w, B0 + o.d.s, B0 + o.d.b, TcWeight()};
         copy(o.wr, (int64_t)b.nsq * ce, "_se_reduce.weight"); copy(o.br, b.nsq, "_se_reduce.bias");
-        copy(o.we, (int64_t)ce * b.nsq, "_se_expand.weight"); copy(o.be, ce, "_se_expand.bias");
+        transposed(o.we, ce, b.nsq, "_se_expand.weight"); copy(o.be, ce, "_se_expand.bias");
         w.se_wr = B0 + o.wr; w.se_br = B0 + o.br; w.se_we = B0 + o.we; w.se_be = B0 + o.be;
         copy(o.p.w, (int64_t)b.cout * ce, "_project_conv.weight");
         bn(o.p, b.cout, "_bn2");
-        w.project = {B0 + o.p.w, B0 + o.p.s, B0 + o.p.b};
+        pack_pw(o.p, b.cout, ce, w.project);
         net->blocks.push_back(w);
     }
     copy(head_o.w, (int64_t)P.head_out * P.head_in, "_conv_head.weight");
     bn(head_o, P.head_out, "_bn1");
-    net->head = {B0 + head_o.w, B0 + head_o.s, B0 + head_o.b};
+    pack_pw(head_o, P.head_out, P.head_in, net->head);
     if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_effb2_create pack kernels");
     if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_effb2_create sync");
     if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
-    cudaFuncSetAttribute(dwconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(dwconv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     *out = net;
     return AC_OK;
 }
@@ -524,20 +592,22 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         if (b.expand != 1) {
             GemmArgs g; g.A = cur; g.W = w.expand.w; g.C = E; g.M = B * pin; g.N = ce; g.K = b.cin;
             g.cscale = w.expand.scale; g.cbias = w.expand.bias; g.act = ACT_SWISH;
+            g.tw = w.expand.tw.packed ? &w.expand.tw : nullptr;
             int rc = gemm_tn(g, st); if (rc) return rc;
             dw_in = E;
         }
         int rc = launch_dw(dw_in, w.dw, D, PART, B, din[i], dout[i], ce, b, st); if (rc) return rc;
-        const int strips = dout[i].H * cdiv(dout[i].W, kDwStrip);
+        const int strips = dout[i].H * cdiv(dout[i].W, dw_seg_len(B, dout[i].H, dout[i].W, ce, b.k));
         {
         AC_TIMED("se", st);
-        se_kernel<<<B, 256, (ce + b.nsq) * sizeof(float), st>>>(PART, strips, 1.0f / (float)pout, w.se_wr, w.se_br,
+        se_kernel<<<B, kSeThreads, (((ce + b.nsq + 3) / 4) * 4 + kSeThreads * 4) * sizeof(float), st>>>(PART, strips, 1.0f / (float)pout, w.se_wr, w.se_br,
                                                                 w.se_we, w.se_be, GATE, ce, b.nsq);
         AC_LAUNCHED("se_kernel");
         }
         GemmArgs g; g.A = D; g.W = w.project.w; g.C = nxt; g.M = B * pout; g.N = b.cout; g.K = ce;
         g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
         g.act = ACT_NONE; g.R = b.skip ? cur : nullptr;
+        g.tw = w.project.tw.packed ? &w.project.tw : nullptr;
         rc = gemm_tn(g, st); if (rc) return rc;
         std::swap(cur, nxt);
     }
@@ -545,6 +615,7 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
     {
         GemmArgs g; g.A = cur; g.W = net->head.w; g.C = HEAD; g.M = B * last.H * last.W; g.N = P.head_out;
         g.K = P.head_in; g.cscale = net->head.scale; g.cbias = net->head.bias; g.act = ACT_SWISH;
+        g.tw = net->head.tw.packed ? &net->head.tw : nullptr;
         int rc = gemm_tn(g, st); if (rc) return rc;
         int64_t total = (int64_t)B * last.W * P.head_out / 4;
         AC_TIMED("freq_mean", st);

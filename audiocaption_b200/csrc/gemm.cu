@@ -141,6 +141,11 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
 }
 
 int gemm_tn(const GemmArgs& g, cudaStream_t st) {
+    if (g.tw != nullptr && g.K % 8 == 0) return gemm_tc(g, st);
+    return gemm_tn_simt(g, st);
+}
+
+int gemm_tn_simt(const GemmArgs& g, cudaStream_t st) {
     AC_REQUIRE(g.K % 4 == 0 && g.N % 4 == 0, "gemm_tn: K (%d) and N (%d) must be multiples of 4", g.K, g.N);
     AC_REQUIRE(g.M >= 0 && cdiv(g.N, 32) <= 65535, "gemm_tn: M/N out of range");
     if (g.M == 0 || g.N == 0) return AC_OK;

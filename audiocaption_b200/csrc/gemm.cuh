@@ -12,6 +12,24 @@ namespace ac {
 
 enum Act { ACT_NONE = 0, ACT_SWISH = 1, ACT_RELU = 2 };
 
+// A weight matrix W[N, K] re-packed for the tcgen05 kernel (gemm_tc.cu): per (n-tile, 32-wide k-chunk)
+// one contiguous block holding the tf32 "hi" part and the fp32 residual "lo" part, each already in the
+// 128B-swizzled K-major shared-memory image the tensor core reads, so a CTA fetches a chunk with a
+// single bulk copy.  Rows/columns beyond N/K are zero.
+struct TcWeight {
+    const float* packed = nullptr;
+    const float* scale = nullptr;   // per-output-channel scale folded into the packed copy (nullptr = none)
+    int N = 0, K = 0;
+    int BN = 0;        // columns per n-tile (multiple of 16, <= 160)
+    int n_tiles = 0;
+    int k_chunks = 0;  // ceil(K / 32)
+};
+size_t tc_packed_floats(int N, int K);
+// W_dev [N, K] row-major -> dst_dev (tc_packed_floats(N, K) floats); fills *out.
+// scale_dev [N] (nullable) is multiplied into the rows before the hi/lo split (folded BN scale).
+int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, float* dst_dev, cudaStream_t st,
+                   TcWeight* out);
+
 struct GemmArgs {
     const float* A; const float* W; float* C;
     int M, N, K;
@@ -22,8 +40,13 @@ struct GemmArgs {
     const float* R = nullptr;       // [M, N] residual added after the activation
     int act = ACT_NONE;
     int ldc = 0;                    // row stride of C / R (0 -> N)
+    const TcWeight* tw = nullptr;   // packed copy of W for the tensor-core path (nullptr -> SIMT kernel)
 };
 
+// Dispatch: the tcgen05 kernel (3xTF32 split, fp32-level accuracy) when g.tw is set and K % 8 == 0,
+// otherwise the plain-fp32 SIMT kernel.
 int gemm_tn(const GemmArgs& g, cudaStream_t st);
+int gemm_tn_simt(const GemmArgs& g, cudaStream_t st);
+int gemm_tc(const GemmArgs& g, cudaStream_t st);
 
 }  // namespace ac

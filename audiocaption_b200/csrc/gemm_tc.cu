@@ -1,0 +1,509 @@
+// Tensor-core pointwise GEMM for sm_100a (see gemm.cuh for the operation):
+//     C[m, n] = act( (sum_k A[m,k] * ascale[m / rows_per_group, k] * W[n,k]) * cscale[n] + cbias[n] ) + R[m, n]
+//
+// Numerics: fp32 in, fp32 out.  Every operand is split on the fly into a tf32 "hi" part and an fp32
+// residual "lo" part and the product is accumulated as lo*hi + hi*lo + hi*hi in fp32 (TMEM), the
+// classic 3xTF32 scheme: the result carries fp32-level accuracy (error ~2^-22 per product), which is
+// what keeps the greedy token ids identical to the fp32 reference.
+//
+// Structure (one persistent CTA per SM, 20 warps, warp-specialised):
+//   warp 0       TMA producer: per 32-wide k-chunk one cp.async.bulk.tensor (A box 128 x 32 fp32, 128B
+//                swizzle, rows/cols beyond M/K zero-filled by the TMA unit).  The pre-packed weight
+//                (hi and lo images, see TcWeight) is either fetched ONCE per CTA with a single bulk copy
+//                ("resident": one n-tile and <= 64 KB -- every large-M layer) or streamed per stage.
+//   warps 12-19  transform: in place in shared memory, a *= SE gate, hi = tf32(a), lo = a - hi
+//                (the swizzled image is processed linearly -> conflict-free); the gate values of the
+//                next chunk are prefetched while the current one is processed.
+//   warp 1       MMA issuer: tcgen05.mma kind::tf32, M=128, N=BN, K=8 per instruction, 3 per k-step,
+//                accumulators double-buffered in TMEM; tcgen05.commit releases the smem stage.
+//   warps 4-11   epilogue (two warps per TMEM lane quarter, alternating 32-column panels): tcgen05.ld,
+//                folded BN scale/bias, swish/relu, residual, then the panel goes through a 128B-swizzled
+//                4 KB shared-memory slab and out with one TMA tensor store (coalesced, clipped at M/N).
+//                Overlaps the next tile's main loop.
+//   warp 2       TMEM allocator.
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace ac {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                          // fp32 elements per k-chunk = one 128-byte swizzle row
+constexpr int TC_MAX_BN_RESIDENT = 160;
+constexpr int TC_MAX_BN_STREAM = 128;
+constexpr int TC_RESIDENT_W_BYTES = 64 * 1024;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_XF_WARPS = 8;
+constexpr int TC_FIRST_EPI_WARP = 4;
+constexpr int TC_FIRST_XF_WARP = TC_FIRST_EPI_WARP + TC_EPI_WARPS;  // 12
+constexpr int TC_THREADS = (TC_FIRST_XF_WARP + TC_XF_WARPS) * 32;   // 640
+constexpr int TC_A_TILE_BYTES = TC_BM * TC_BK * 4; // 16 KB (hi image; lo image follows)
+constexpr int TC_SLAB_BYTES = 32 * 32 * 4;         // one epilogue warp's 32 rows x 32 columns
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_BAR_BYTES = 256;
+
+struct TcParams {
+    const float* wpacked; float* C; const float* R;
+    const float* ascale; const float* cbias;
+    int M, N, K, ldc, rows_per_group;
+    int BN, n_tiles, m_tiles, k_chunks, stages, tmem_cols, resident;
+};
+
+__device__ __forceinline__ float fast_swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+template <int ACT>
+__device__ __forceinline__ float4 epi_math(const uint32_t* u, float4 b) {
+    float v[4] = {__uint_as_float(u[0]) + b.x, __uint_as_float(u[1]) + b.y, __uint_as_float(u[2]) + b.z,
+                  __uint_as_float(u[3]) + b.w};
+    if (ACT == ACT_SWISH) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = fast_swish(v[e]);
+    } else if (ACT == ACT_RELU) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// The BN scale is folded into the packed weight, so the epilogue is act(acc + bias) + R.
+template <int ACT, bool GATED, bool RESID>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, const TcParams p) {
+    using namespace ptx;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;          // 128B swizzle needs 1024-byte aligned tiles
+    // [epilogue slabs][resident W][stages: A hi | A lo | (streamed W hi | lo)][barriers][per-warp bias]
+    const uint32_t slabs = base;
+    const uint32_t w_res = slabs + TC_EPI_WARPS * TC_SLAB_BYTES;
+    const uint32_t w_chunk_bytes = (uint32_t)p.BN * 256u;
+    const uint32_t stage0 = w_res + (p.resident ? (uint32_t)p.k_chunks * w_chunk_bytes : 0u);
+    const uint32_t stage_bytes = 2 * TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes);
+    const uint32_t bars = stage0 + p.stages * stage_bytes;
+    auto bar_tma = [&](int s) { return bars + 8u * s; };
+    auto bar_xf = [&](int s) { return bars + 64u + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 128u + 8u * s; };
+    auto bar_acc_full = [&](int a) { return bars + 192u + 8u * a; };
+    auto bar_acc_empty = [&](int a) { return bars + 208u + 8u * a; };
+    const uint32_t bar_w = bars + 224u;
+    const uint32_t tmem_slot_addr = bars + 232u;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - raw));
+    float* bias_all = reinterpret_cast<float*>(smem_raw + (bars + TC_BAR_BYTES - raw));   // [EPI_WARPS][TC_MAX_BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&mapA);
+        prefetch_tensormap(&mapC);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_tma(s), 1);
+            mbar_init(bar_xf(s), TC_XF_WARPS);
+            mbar_init(bar_empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_acc_full(a), 1);
+            mbar_init(bar_acc_empty(a), TC_EPI_WARPS);
+        }
+        mbar_init(bar_w, 1);
+        fence_mbar_init();
+    } else if (warp == 2) {
+        tmem_alloc(tmem_slot_addr, (uint32_t)p.tmem_cols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            if (p.resident) {
+                const uint32_t wb = (uint32_t)p.k_chunks * w_chunk_bytes;
+                mbar_expect_tx(bar_w, wb);
+                bulk_load(w_res, p.wpacked, wb, bar_w);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
+                const float* wsrc = p.wpacked + (size_t)n_t * p.k_chunks * (p.BN * 64);
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(bar_empty(stage), phase ^ 1u);
+                    const uint32_t sa = stage0 + stage * stage_bytes;
+                    mbar_expect_tx(bar_tma(stage), TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes));
+                    tma_load_2d(sa, &mapA, kc * TC_BK, m_t * TC_BM, bar_tma(stage));
+                    if (!p.resident)
+                        bulk_load(sa + 2 * TC_A_TILE_BYTES, wsrc + (size_t)kc * (p.BN * 64), w_chunk_bytes, bar_tma(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(2, TC_BM, p.BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            if (p.resident) mbar_wait(bar_w, 0u);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    if (!p.resident) mbar_wait(bar_tma(stage), phase);   // streamed weight chunk landed
+                    mbar_wait(bar_xf(stage), phase);                     // A chunk split into hi / lo
+                    tc_fence_after();
+                    const uint32_t sa = stage0 + stage * stage_bytes;
+                    const uint32_t a_hi = sa, a_lo = sa + TC_A_TILE_BYTES;
+                    const uint32_t w_hi = p.resident ? w_res + kc * w_chunk_bytes : sa + 2 * TC_A_TILE_BYTES;
+                    const uint32_t w_lo = w_hi + (uint32_t)p.BN * 128u;
+                    const int ksteps = min(TC_BK / 8, (p.K - kc * TC_BK) / 8);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t o = ks * 32u;      // 8 tf32 = 32 bytes along the swizzled row
+                        const uint64_t dah = umma_desc_sw128(a_hi + o), dal = umma_desc_sw128(a_lo + o);
+                        const uint64_t dwh = umma_desc_sw128(w_hi + o), dwl = umma_desc_sw128(w_lo + o);
+                        mma_tf32(d_tmem, dal, dwh, idesc, (kc | ks) != 0 ? 1u : 0u);   // small terms first
+                        mma_tf32(d_tmem, dah, dwl, idesc, 1u);
+                        mma_tf32(d_tmem, dah, dwh, idesc, 1u);
+                    }
+                    mma_commit(bar_empty(stage));         // smem stage reusable once these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                mma_commit(bar_acc_full(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= TC_FIRST_XF_WARP) {
+        // ------------------------------------------------------------ transform (gate, hi/lo split)
+        constexpr int NT = TC_XF_WARPS * 32;                          // 256 threads
+        constexpr int PER = (TC_A_TILE_BYTES / 16) / NT;              // float4 per thread per chunk = 4
+        constexpr int ROW_STEP = NT / 8;                              // 32 rows between a thread's float4s
+        const int t = threadIdx.x - TC_FIRST_XF_WARP * 32;
+        const int r0 = t >> 3;                                        // physical row of the first float4
+        const int lc = (t & 7) ^ (r0 & 7);                            // logical 16-byte chunk (undo the swizzle)
+        const float* grow[PER];                                       // gate rows of this thread's 4 rows
+        auto gate_rows = [&](int tile) {
+            const int m_t = tile / p.n_tiles;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int row = min(m_t * TC_BM + r0 + j * ROW_STEP, p.M - 1);
+                grow[j] = p.ascale + (size_t)(row / p.rows_per_group) * p.K + lc * 4;
+            }
+        };
+        auto load_gate = [&](int kc, float4 (&g)[PER]) {
+            const int k = kc * TC_BK;
+#pragma unroll
+            for (int j = 0; j < PER; ++j)
+                g[j] = k + lc * 4 < p.K ? __ldg(reinterpret_cast<const float4*>(grow[j] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        int stage = 0; uint32_t phase = 0;
+        int tile = blockIdx.x, kc = 0;
+        float4 g_next[PER];
+        if (GATED && tile < total_tiles) { gate_rows(tile); load_gate(kc, g_next); }
+        while (tile < total_tiles) {
+            float4 g[PER];
+            if (GATED) {
+#pragma unroll
+                for (int j = 0; j < PER; ++j) g[j] = g_next[j];
+            }
+            int kc2 = kc + 1, tile2 = tile;
+            if (kc2 == p.k_chunks) { kc2 = 0; tile2 += gridDim.x; }
+            if (GATED && tile2 < total_tiles) {                       // next chunk's gates in flight meanwhile
+                if (kc2 == 0) gate_rows(tile2);
+                load_gate(kc2, g_next);
+            }
+            mbar_wait(bar_tma(stage), phase);
+            uint8_t* a_gen = smem_raw + (stage0 - raw) + (size_t)stage * stage_bytes;
+            float4* hi = reinterpret_cast<float4*>(a_gen) + t;
+            float4* lo = reinterpret_cast<float4*>(a_gen + TC_A_TILE_BYTES) + t;
+            float4 v[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) v[j] = hi[j * NT];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                float4 x = v[j];
+                if (GATED) { x.x *= g[j].x; x.y *= g[j].y; x.z *= g[j].z; x.w *= g[j].w; }
+                const float4 h = make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
+                hi[j * NT] = h;
+                lo[j * NT] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            }
+            fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xf(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            tile = tile2; kc = kc2;
+        }
+    } else if (warp >= TC_FIRST_EPI_WARP) {
+        // ------------------------------------------------------------ epilogue
+        const int ew = warp - TC_FIRST_EPI_WARP;
+        const int q = warp & 3;                            // TMEM lane quarter this warp may read
+        const int half = ew >> 2;                          // which of the two warps of that quarter
+        const uint32_t slab = slabs + ew * TC_SLAB_BYTES;
+        uint8_t* slab_gen = smem_raw + (slab - raw);
+        float* bias = bias_all + ew * TC_MAX_BN_RESIDENT;  // this warp's private copy (zero beyond N)
+        const int ldc = p.ldc;
+        const int full_panels = p.BN / 32;
+        const bool tail16 = (p.BN & 31) != 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        int cur_nt = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
+            const int row0 = m_t * TC_BM + q * 32;
+            const int row = row0 + lane;
+            const bool row_ok = row < p.M;
+            const float* rrow = p.R + (size_t)(row_ok ? row : 0) * ldc;
+            if (n_t != cur_nt) {
+                cur_nt = n_t;
+                __syncwarp();
+                for (int c = lane; c < p.BN; c += 32) {
+                    const int col = n_t * p.BN + c;
+                    bias[c] = (p.cbias != nullptr && col < p.N) ? __ldg(p.cbias + col) : 0.0f;
+                }
+                __syncwarp();
+            }
+            mbar_wait(bar_acc_full(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+            for (int pn = half; pn < full_panels; pn += 2) {
+                const int col0 = n_t * p.BN + pn * 32;
+                float4 r[8];
+                if (RESID) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        r[j] = (row_ok && col0 + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(rrow + col0 + 4 * j))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                uint32_t u[2][16];
+                tmem_ld16(t_row + (uint32_t)(pn * 32), u[0]);
+                tmem_ld16(t_row + (uint32_t)(pn * 32 + 16), u[1]);
+                tmem_ld_wait();
+                float4 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + pn * 32 + 4 * j);
+                    o[j] = epi_math<ACT>(&u[j >> 2][(j & 3) * 4], b);
+                    if (RESID) { o[j].x += r[j].x; o[j].y += r[j].y; o[j].z += r[j].z; o[j].w += r[j].w; }
+                }
+                if (lane == 0) bulk_wait_read0();          // previous panel's store has drained the slab
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(slab_gen + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&mapC, slab, col0, row0);
+                    bulk_commit();
+                }
+            }
+            if (tail16 && half == (full_panels & 1)) {
+                // trailing 16-column half panel: direct 128-bit stores
+                const int col0 = n_t * p.BN + full_panels * 32;
+                float4 r[4];
+                if (RESID) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        r[j] = (row_ok && col0 + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(rrow + col0 + 4 * j))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                uint32_t u[16];
+                tmem_ld16(t_row + (uint32_t)(full_panels * 32), u);
+                tmem_ld_wait();
+                float* crow = p.C + (size_t)row * ldc;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + full_panels * 32 + 4 * j);
+                    float4 o = epi_math<ACT>(&u[4 * j], b);
+                    if (RESID) { o.x += r[j].x; o.y += r[j].y; o.z += r[j].z; o.w += r[j].w; }
+                    if (row_ok && col0 + 4 * j < p.N) *reinterpret_cast<float4*>(crow + col0 + 4 * j) = o;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (lane == 0) bulk_wait_read0();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------ weight packing
+// One thread per packed float4: [n_tile][k_chunk][hi|lo][row BN][16-byte chunk 8 (swizzled)].
+__global__ void tc_pack_kernel(const float* __restrict__ W, const float* __restrict__ scale, float* __restrict__ dst,
+                               int N, int K, int BN, int n_tiles, int k_chunks) {
+    const int64_t total = (int64_t)n_tiles * k_chunks * 2 * BN * 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int pc = (int)(i % 8);
+    int64_t r = i / 8;
+    const int row = (int)(r % BN); r /= BN;
+    const int hl = (int)(r % 2); r /= 2;
+    const int kc = (int)(r % k_chunks);
+    const int n_t = (int)(r / k_chunks);
+    const int lc = pc ^ (row & 7);
+    const int n = n_t * BN + row, k = kc * TC_BK + lc * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N) {
+        const float sc = scale != nullptr ? scale[n] : 1.0f;
+        for (int e = 0; e < 4; ++e)
+            if (k + e < K) v[e] = W[(size_t)n * K + k + e] * sc;
+    }
+    float o[4];
+    for (int e = 0; e < 4; ++e) {
+        const float h = ptx::tf32_rna(v[e]);
+        o[e] = hl == 0 ? h : v[e] - h;
+    }
+    reinterpret_cast<float4*>(dst)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+static bool tc_resident(int BN, int n_tiles, int k_chunks) {
+    return n_tiles == 1 && (int64_t)k_chunks * BN * 256 <= TC_RESIDENT_W_BYTES;
+}
+static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks) {
+    k_chunks = cdiv(K, TC_BK);
+    n_tiles = 1;
+    BN = cdiv(N, 16) * 16;
+    if (N <= TC_MAX_BN_RESIDENT && tc_resident(BN, 1, k_chunks)) return;
+    n_tiles = cdiv(N, TC_MAX_BN_STREAM);
+    BN = cdiv(cdiv(N, n_tiles), 16) * 16;
+}
+
+size_t tc_packed_floats(int N, int K) {
+    int BN, n_tiles, k_chunks;
+    tc_tiling(N, K, BN, n_tiles, k_chunks);
+    return (size_t)n_tiles * k_chunks * BN * 64;
+}
+
+int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, float* dst_dev, cudaStream_t st,
+                   TcWeight* out) {
+    AC_REQUIRE(W_dev && dst_dev && out && N > 0 && K > 0, "tc_pack_weight: bad argument");
+    AC_REQUIRE(((uintptr_t)dst_dev & 127) == 0, "tc_pack_weight: destination must be 128-byte aligned");
+    int BN, n_tiles, k_chunks;
+    tc_tiling(N, K, BN, n_tiles, k_chunks);
+    const int64_t total = (int64_t)n_tiles * k_chunks * 2 * BN * 8;
+    tc_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W_dev, scale_dev, dst_dev, N, K, BN, n_tiles, k_chunks);
+    AC_LAUNCHED("tc_pack_kernel");
+    out->packed = dst_dev; out->scale = scale_dev; out->N = N; out->K = K; out->BN = BN; out->n_tiles = n_tiles; out->k_chunks = k_chunks;
+    return AC_OK;
+}
+
+// ------------------------------------------------------------------------------------ launch
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+int gemm_tc(const GemmArgs& g, cudaStream_t st) {
+    AC_REQUIRE(g.tw != nullptr && g.tw->packed != nullptr, "gemm_tc: weight not packed");
+    const TcWeight& w = *g.tw;
+    AC_REQUIRE(w.N == g.N && w.K == g.K, "gemm_tc: packed weight is %dx%d, call wants %dx%d", w.N, w.K, g.N, g.K);
+    AC_REQUIRE(g.K % 8 == 0 && g.N % 4 == 0, "gemm_tc: K (%d) %% 8 and N (%d) %% 4 must be 0", g.K, g.N);
+    AC_REQUIRE(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.C & 15) == 0, "gemm_tc: A and C must be 16-byte aligned");
+    AC_REQUIRE((g.ldc ? g.ldc : g.N) % 4 == 0, "gemm_tc: ldc must be a multiple of 4");
+    if (g.M <= 0 || g.N <= 0) return AC_OK;
+    auto encode = tensor_map_encoder();
+    AC_REQUIRE(encode != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+
+    const int ldc = g.ldc ? g.ldc : g.N;
+    CUtensorMap map, mapC;
+    {
+        const cuuint64_t cdims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+        const cuuint64_t cstr[1] = {(cuuint64_t)ldc * sizeof(float)};
+        const cuuint32_t cbox[2] = {32, 32};
+        const cuuint32_t ces[2] = {1, 1};
+        CUresult cr = encode(&mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.C, cdims, cstr, cbox, ces,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        AC_REQUIRE(cr == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) for C=%p M=%d N=%d ldc=%d", (int)cr,
+                   g.C, g.M, g.N, ldc);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.K * sizeof(float)};
+    const cuuint32_t box[2] = {TC_BK, TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.A), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AC_REQUIRE(cr == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) for A=%p M=%d K=%d", (int)cr, g.A, g.M,
+               g.K);
+
+    TcParams p;
+    AC_REQUIRE(g.cscale == w.scale, "gemm_tc: the BN scale is folded into the packed weight; cscale must be the packed one");
+    p.wpacked = w.packed; p.C = g.C; p.R = g.R; p.ascale = g.ascale; p.cbias = g.cbias;
+    p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = ldc; p.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
+    p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = cdiv(g.M, TC_BM); p.k_chunks = w.k_chunks;
+    p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
+    const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_EPI_WARPS * TC_SLAB_BYTES +
+                      (p.resident ? w.k_chunks * w.BN * 256 : 0);
+    const int sb = 2 * TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
+    p.stages = std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / sb);
+    AC_REQUIRE(p.stages >= 2, "gemm_tc: tile too large for shared memory (BN=%d)", w.BN);
+    int cols = 32;
+    while (cols < 2 * w.BN) cols *= 2;
+    p.tmem_cols = cols;
+    const size_t smem = (size_t)p.stages * sb + fixed;
+
+    const int grid = std::min(p.m_tiles * p.n_tiles, kNumSMs);
+    const bool gated = g.ascale != nullptr, resid = g.R != nullptr;
+    AC_TIMED("gemm_tc", st);
+#define AC_TC_LAUNCH(ACT, GATED, RESID)                                                                            \
+    do {                                                                                                           \
+        static cudaError_t attr_rc = cudaFuncSetAttribute(gemm_tc_kernel<ACT, GATED, RESID>,                        \
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT); \
+        AC_CUDA(attr_rc);                                                                                          \
+        gemm_tc_kernel<ACT, GATED, RESID><<<grid, TC_THREADS, smem, st>>>(map, mapC, p);                           \
+    } while (0)
+#define AC_TC_ACT(ACT)                                                   \
+    do {                                                                 \
+        if (gated && resid) AC_TC_LAUNCH(ACT, true, true);               \
+        else if (gated) AC_TC_LAUNCH(ACT, true, false);                  \
+        else if (resid) AC_TC_LAUNCH(ACT, false, true);                  \
+        else AC_TC_LAUNCH(ACT, false, false);                            \
+    } while (0)
+    if (g.act == ACT_SWISH) AC_TC_ACT(ACT_SWISH);
+    else if (g.act == ACT_RELU) AC_TC_ACT(ACT_RELU);
+    else AC_TC_ACT(ACT_NONE);
+#undef AC_TC_ACT
+#undef AC_TC_LAUNCH
+    AC_LAUNCHED("gemm_tc_kernel");
+    return AC_OK;
+}
+
+}  // namespace ac
+
+extern "C" int ac_gemm(const float* A, const float* W, float* C, int M, int N, int K, const float* ascale,
+                       int rows_per_group, const float* cscale, const float* cbias, const float* R, int act, int path,
+                       void* stream) {
+    using namespace ac;
+    AC_REQUIRE(A && W && C, "ac_gemm: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmArgs g; g.A = A; g.W = W; g.C = C; g.M = M; g.N = N; g.K = K; g.ascale = ascale;
+    g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; g.cscale = cscale; g.cbias = cbias; g.R = R; g.act = act;
+    if (path == 0) return gemm_tn_simt(g, st);
+    float* packed = nullptr;
+    AC_CUDA(cudaMalloc(&packed, tc_packed_floats(N, K) * sizeof(float)));
+    TcWeight tw;
+    int rc = tc_pack_weight(W, cscale, N, K, packed, st, &tw);
+    if (rc == AC_OK) { g.tw = &tw; rc = gemm_tc(g, st); }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(packed);
+    if (rc == AC_OK && e != cudaSuccess) rc = check_cuda(e, "ac_gemm");
+    return rc;
+}

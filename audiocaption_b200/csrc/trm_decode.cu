@@ -513,6 +513,8 @@ __global__ void transpose2_kernel(const float* __restrict__ in, float* __restric
 
 struct ac_trm {
     float* blob = nullptr;
+    float* tcblob = nullptr;               // tensor-core images of the memory-side weights (gemm.cuh)
+    ac::TcWeight proj_tw, kv_tw[ac::kMaxLayers];
     ac::DecW w;
 };
 
@@ -532,7 +534,7 @@ static int prepare_memory(const ac_trm* d, const float* attn_emb, int clips, int
                           cudaStream_t st) {
     const DecW& W = d->w;
     GemmArgs g; g.A = attn_emb; g.W = W.proj_w; g.C = proj; g.M = clips * t_mem; g.N = D; g.K = W.attn_emb_dim;
-    g.cbias = W.proj_b; g.act = ACT_RELU;
+    g.cbias = W.proj_b; g.act = ACT_RELU; g.tw = d->proj_tw.packed ? &d->proj_tw : nullptr;
     int rc = gemm_tn(g, st); if (rc) return rc;
     int64_t rows = (int64_t)clips * t_mem;
     {
@@ -543,7 +545,7 @@ static int prepare_memory(const ac_trm* d, const float* attn_emb, int clips, int
     for (int l = 0; l < W.nlayers; ++l) {
         // one [clips*t_mem, D] x [D, 2D] GEMM per layer; kvmem layout [layer][clip][t][K | V]
         GemmArgs k; k.A = proj; k.W = W.layer[l].ca_kv_w; k.M = clips * t_mem; k.N = 2 * D; k.K = D;
-        k.cbias = W.layer[l].ca_kv_b; k.act = ACT_NONE;
+        k.cbias = W.layer[l].ca_kv_b; k.act = ACT_NONE; k.tw = d->kv_tw[l].packed ? &d->kv_tw[l] : nullptr;
         k.C = kvmem + (size_t)l * clips * t_mem * 2 * D;   // [layer][clip][t][2D]
         rc = gemm_tn(k, st); if (rc) return rc;
     }
@@ -638,9 +640,16 @@ int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, i
         off += align_up((size_t)D * Vp, 64); ++ti;
     }
     W.proj_w = plain(); W.proj_b = plain(); W.proj_ln_g = plain(); W.proj_ln_b = plain();
+    if (rc == AC_OK && attn_emb_dim % 8 == 0) {
+        const size_t np = align_up(tc_packed_floats(D, attn_emb_dim), 64), nk = align_up(tc_packed_floats(2 * D, D), 64);
+        rc = check_cuda(cudaMalloc(&d->tcblob, (np + nlayers * nk) * sizeof(float)), "cudaMalloc tc weights");
+        if (rc == AC_OK) rc = tc_pack_weight(W.proj_w, nullptr, D, attn_emb_dim, d->tcblob, st, &d->proj_tw);
+        for (int l = 0; l < nlayers && rc == AC_OK; ++l)
+            rc = tc_pack_weight(W.layer[l].ca_kv_w, nullptr, 2 * D, D, d->tcblob + np + l * nk, st, &d->kv_tw[l]);
+    }
     if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_trm_create pack kernels");
     if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_trm_create sync");
-    if (rc != AC_OK) { cudaFree(d->blob); delete d; return rc; }
+    if (rc != AC_OK) { cudaFree(d->blob); cudaFree(d->tcblob); delete d; return rc; }
     *out = d;
     return AC_OK;
 }
@@ -648,6 +657,7 @@ int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, i
 void ac_trm_destroy(ac_trm_t* d) {
     if (!d) return;
     cudaFree(d->blob);
+    cudaFree(d->tcblob);
     delete d;
 }
 

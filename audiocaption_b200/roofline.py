@@ -62,7 +62,7 @@ def per_clip_work(n_samples=160000, hop=160, n_mels=64, t_mem=32, d_enc=1408, d=
     gemm_w += d_enc * d * f + nlayers * 2 * d * d * f
     gemm_fl += 2 * t_mem * d_enc * d + nlayers * 2 * t_mem * d * 2 * d
     return {
-        "gemm_tn": dict(bytes=gemm_b, weight_bytes=gemm_w, flops=gemm_fl),
+        "gemm": dict(bytes=gemm_b, weight_bytes=gemm_w, flops=gemm_fl),
         "dwconv": dict(bytes=dw_b, weight_bytes=0, flops=dw_fl),
         "logmel": dict(bytes=4 * n_samples + 4 * n_mels * T, weight_bytes=0, flops=0),
         "stem": dict(bytes=4 * n_mels * T + 4 * stem[0] * stem[1] * 32, weight_bytes=0, flops=2 * stem[0] * stem[1] * 32 * 9),

@@ -67,6 +67,17 @@ int ac_logmel_fwd(const ac_frontend_t* fe, const float* wav_dev, int batch, int 
 /* x = max(x, *gmax - top_db) in place (AmplitudeToDB(top_db=...)). */
 int ac_db_clamp(float* x_dev, int64_t n, const float* gmax_dev, float top_db, void* stream);
 
+/* ------------------------------------------------------------------ pointwise GEMM (diagnostic)
+ * The kernel behind every 1x1 convolution / Linear of the path (efficientnet_pytorch
+ * `_expand_conv/_project_conv/_conv_head` + BN + swish, hf_wrapper.py:1045-1052 `attn_proj`):
+ *   C[m,n] = act((sum_k A[m,k] * ascale[m / rows_per_group, k] * W[n,k]) * cscale[n] + cbias[n]) + R[m,n]
+ * A [M,K], W [N,K], C/R [M,N] row-major fp32; ascale/cscale/cbias/R nullable; act 0 none, 1 swish, 2 relu.
+ * path 0 = plain fp32 SIMT kernel, 1 = tcgen05 tensor-core kernel (TMA-fed, 3xTF32 split, fp32-level
+ * accuracy; K % 8 == 0).  Exposed so that tests can check the kernel in isolation; synchronises. */
+int ac_gemm(const float* A_dev, const float* W_dev, float* C_dev, int M, int N, int K,
+            const float* ascale_dev, int rows_per_group, const float* cscale_dev, const float* cbias_dev,
+            const float* R_dev, int act, int path, void* stream);
+
 /* ------------------------------------------------------------------ EfficientNet-B2 encoder
  * Replaces hf_wrapper.py:218-241 `_EffiNet.forward` (efficientnet_pytorch 0.7.1
  * `extract_features` + mean over frequency), eval mode.

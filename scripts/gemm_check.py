@@ -1,0 +1,112 @@
+"""GPU check of the pointwise GEMM kernels through the C ABI (ac_gemm): tcgen05 3xTF32 path (1) and
+SIMT fp32 path (0) against a float64 torch reference, plus per-kernel CUDA-event timing on the
+EfficientNet-B2 layer shapes.   usage: python scripts/gemm_check.py [quick|shapes|all]"""
+import os, sys, warnings
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from audiocaption_b200 import _lib
+
+lib = _lib.lib()
+dev = "cuda:0"
+
+
+def run(M, N, K, gate=0, affine=True, act=1, resid=False, path=1, seed=0, check=True, time_it=False):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    C = torch.full((M, N), float("nan"), device=dev)
+    groups = (M + gate - 1) // gate if gate else 0
+    G = torch.rand(groups, K, generator=g).to(dev) if gate else None
+    S = (torch.rand(N, generator=g) + 0.5).to(dev) if affine else None
+    Bv = torch.randn(N, generator=g).to(dev) if affine else None
+    R = torch.randn(M, N, generator=g).to(dev) if resid else None
+    st = _lib.current_stream()
+    if time_it:
+        lib.ac_timing_enable(1)
+    rc = lib.ac_gemm(_lib.ptr(A), _lib.ptr(W), _lib.ptr(C), M, N, K, _lib.ptr(G), gate, _lib.ptr(S), _lib.ptr(Bv),
+                     _lib.ptr(R), act, path, st)
+    _lib.check(rc, "ac_gemm")
+    torch.cuda.synchronize()
+    ms = None
+    if time_it:
+        for _ in range(3):
+            _lib.check(lib.ac_gemm(_lib.ptr(A), _lib.ptr(W), _lib.ptr(C), M, N, K, _lib.ptr(G), gate, _lib.ptr(S),
+                                   _lib.ptr(Bv), _lib.ptr(R), act, path, st), "ac_gemm")
+        rep = _lib.timing_report()
+        lib.ac_timing_enable(0)
+        ms = min(v[1] / v[0] for k, v in rep.items() if k.startswith("gemm"))
+    err = None
+    if check:
+        Ad = A.double()
+        if gate:
+            Ad = Ad * G.double().repeat_interleave(gate, dim=0)[:M]
+        ref = Ad @ W.double().t()
+        if affine:
+            ref = ref * S.double() + Bv.double()
+        if act == 1:
+            ref = ref * torch.sigmoid(ref)
+        elif act == 2:
+            ref = ref.clamp_min(0)
+        if resid:
+            ref = ref + R.double()
+        err = ((C.double() - ref).abs().max() / ref.abs().max()).item()
+        assert not torch.isnan(C).any(), "NaN / unwritten output"
+    return err, ms
+
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "all"
+print("device", torch.cuda.get_device_name(0))
+if mode in ("quick", "all"):
+    cases = [
+        dict(M=128, N=16, K=32, affine=False, act=0),
+        dict(M=128, N=16, K=8, affine=False, act=0),
+        dict(M=256, N=32, K=64, affine=False, act=0),
+        dict(M=1000, N=96, K=16),
+        dict(M=4096, N=24, K=96, gate=1008, act=0, resid=True),
+        dict(M=777, N=144, K=24),
+        dict(M=5000, N=352, K=2112, gate=64, act=0, resid=True),
+        dict(M=2048, N=256, K=1408, act=2),
+        dict(M=4096, N=1408, K=352),
+        dict(M=40000, N=48, K=288, gate=1000, act=0, resid=True),
+    ]
+    for c in cases:
+        for path in (1, 0):
+            try:
+                err, _ = run(path=path, **c)
+                print(f"path {path} {c}: rel err {err:.3e}", "OK" if err < 2e-5 else "BAD", flush=True)
+            except Exception as e:
+                print(f"path {path} {c}: FAILED {e}", flush=True)
+                if path == 1:
+                    sys.exit(1)
+if mode in ("shapes", "all"):
+    from audiocaption_b200 import roofline as rl
+    stem, blocks, last = rl.effb2_geometry(64, 1001)
+    B = 64
+    tot = {0: 0.0, 1: 0.0}
+    ideal = 0.0
+    for i, ((cin, cout, e, k, s, lo, hi, nsq, skip), (H, W), (Ho, Wo)) in enumerate(blocks):
+        ce, pin, pout = cin * e, H * W, Ho * Wo
+        layers = []
+        if e != 1:
+            layers.append(("expand", dict(M=B * pin, N=ce, K=cin, act=1), B * pin * (cin + ce) * 4))
+        layers.append(("project", dict(M=B * pout, N=cout, K=ce, gate=pout, act=0, resid=bool(skip)),
+                       B * pout * (ce + cout * (2 if skip else 1)) * 4))
+        for name, c, nbytes in layers:
+            if c["K"] % 8:
+                continue
+            r = {}
+            for path in (1, 0):
+                _, ms = run(path=path, check=False, time_it=True, **c)
+                r[path] = ms
+                tot[path] += ms
+            ideal += nbytes / 6.55e9
+            print(f"b{i:2d} {name:7s} M={c['M']:8d} K={c['K']:5d} N={c['N']:5d}  tc {r[1]*1e3:8.1f} us ({nbytes/r[1]/1e6:7.0f} GB/s)"
+                  f"  simt {r[0]*1e3:8.1f} us  hbm-ideal {nbytes/6.55e6:7.1f} us", flush=True)
+    print(f"total tc {tot[1]:.3f} ms  simt {tot[0]:.3f} ms  hbm-ideal {ideal:.3f} ms")
+if mode == "one":
+    M, N, K, gate, act, resid = [int(x) for x in sys.argv[2:8]]
+    for _ in range(3):
+        run(M=M, N=N, K=K, gate=gate, act=act, resid=bool(resid), path=1, check=False)
+    print("one done")

@@ -154,7 +154,9 @@ def test_decoder_matches_oracle_random_memory(mirror, oracle_effb2, seed):
         t = int((seq[b] != ref["seq"][b]).nonzero()[0])
         top2 = rlg[b, t].topk(2).values
         assert top2[0] - top2[1] < 1e-4, f"row {b} step {t}: token differs without a near-tie"
-    assert (lg[:, 0] - rlg[:, 0]).abs().max() < 1e-4
+    # attn_proj (K = 1408) runs on the tensor cores as 3xTF32: fp32-level products, but the TMEM accumulation
+    # truncates instead of rounding, so the first-step logits carry ~1e-4 instead of ~2e-5 (north_star: 1e-3)
+    assert (lg[:, 0] - rlg[:, 0]).abs().max() < 3e-4
     outb = dec.beam_search(attn.to(DEV), lens, 20, 3, 0.7, cm.START, cm.END, cm.PAD)
     same = (outb["seq"].cpu() == refb["seq"]).all(1)
     assert same.float().mean() >= 0.75, (outb["seq"].cpu(), refb["seq"])
