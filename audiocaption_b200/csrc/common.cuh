@@ -76,6 +76,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
+// x * sigmoid(x) on the SFU: ex2.approx (2 ulp) + rcp.approx (1 ulp), ~2^-21 relative error
+__device__ __forceinline__ float fast_swish(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    return __fdividef(x, 1.0f + e);
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // float atomic max valid for any sign (buffer initialised to -inf)

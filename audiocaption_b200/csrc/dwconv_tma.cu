@@ -1,0 +1,277 @@
+// Depthwise convolution of the MBConv blocks, fed by TMA tiles (sm_100a).
+//
+//   out[b,ho,wo,c] = swish( bn( sum_{kh,kw} in[b, ho*s+kh-pad, wo*s+kw-pad, c] * w[kh,kw,c] ) )
+//   partial[b, tile, c] = sum of out over the tile's pixels          (squeeze-and-excitation numerator)
+//
+// (efficientnet_pytorch 0.7.1 `_depthwise_conv` (Conv2dStaticSamePadding) + `_bn1` + swish + the
+//  `adaptive_avg_pool2d` of the SE branch, as driven by captioning/models/hf_wrapper.py:218-241.)
+//
+// HBM-bound op: every input element is needed by up to k*k outputs but should be read from HBM once.  A
+// persistent CTA walks (clip, row-block, column-block, 32-channel chunk) tiles; a producer warp keeps a ring of
+// input tiles (halo included) in flight with cp.async.bulk.tensor (4-D tensor map over the NHWC activation;
+// the "static same" zero padding is simply the TMA out-of-bounds fill, negative coordinates included), so
+// ~100+ KB per SM are in flight without costing registers.  Compute threads own a channel PAIR of one output
+// row and slide along W in scatter form: one input column (k rows, LDS.64) is added into the <= k outputs it
+// touches, the k*k weights live in registers.  A pixel's 32-channel chunk is 128 contiguous bytes in shared
+// memory, so a half-warp reads/writes whole 128-byte lines (conflict-free LDS, full-line global stores).
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace ac {
+
+// CC = channels per tile (16, 32 or 64: 64 / 128 / 256 contiguous bytes per pixel); a pixel's chunk is served by
+// CC/2 threads (one channel pair each), so the 256 compute threads form 256 / (CC/2) (row, column sub-segment) groups.
+constexpr int DW_COMPUTE_THREADS = 256;
+constexpr int DW_THREADS = DW_COMPUTE_THREADS + 32;           // + producer warp
+constexpr int DW_MAX_STAGES = 4;
+constexpr int DW_SMEM_LIMIT = 200 * 1024;
+
+struct DwParams {
+    float* out; float* partial; const float* w; const float* scale; const float* bias;
+    int B, Ho, Wo, C, pad_lo;
+    int CC, groups;
+    int Ht, Ws, nsub, n_t;            // tile: Ht output rows x Ws output columns; nsub column sub-segments of n_t
+    int tiles_h, tiles_w, chunks, total_tiles;
+    int Hbox, Wbox, stages, tile_bytes;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
+// tile index -> (chunk, b, th, tw): chunk is the slowest so that a CTA's consecutive tiles share weights
+__device__ __forceinline__ void dw_tile_coords(const DwParams& p, int tile, int& chunk, int& b, int& th, int& tw) {
+    tw = tile % p.tiles_w; tile /= p.tiles_w;
+    th = tile % p.tiles_h; tile /= p.tiles_h;
+    b = tile % p.B;
+    chunk = tile / p.B;
+}
+
+template <int K, int S, int CC>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
+    using namespace ptx;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 127u) & ~127u;
+    uint8_t* tiles_gen = smem_raw + (base - raw);
+    const uint32_t bars = base + p.stages * p.tile_bytes;
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 32u + 8u * s; };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        prefetch_tensormap(&mapIn);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), DW_COMPUTE_THREADS / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == DW_COMPUTE_THREADS / 32) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int chunk, b, th, tw;
+                dw_tile_coords(p, tile, chunk, b, th, tw);
+                mbar_wait(bar_empty(stage), phase ^ 1u);
+                mbar_expect_tx(bar_full(stage), (uint32_t)p.tile_bytes);
+                tma_load_4d(base + stage * p.tile_bytes, &mapIn, chunk * CC, tw * p.Ws * S - p.pad_lo,
+                            th * p.Ht * S - p.pad_lo, b, bar_full(stage));
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- compute threads
+    constexpr int TPG = CC / 2;              // threads per pixel chunk
+    const int cp = tid % TPG;                // channel pair inside the chunk
+    const int g = tid / TPG;                 // group: output row r (fast) x column sub-segment
+    const int r = g % p.Ht, sub = g / p.Ht;
+    const int wl0 = sub * p.n_t;             // first local output column of this thread
+    float wr[K * K][2];
+    float sc[2] = {0.f, 0.f}, bi[2] = {0.f, 0.f};
+    int cur_chunk = -1;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int chunk, b, th, tw;
+        dw_tile_coords(p, tile, chunk, b, th, tw);
+        const int c = chunk * CC + 2 * cp;
+        const bool c_ok = c < p.C;
+        if (chunk != cur_chunk) {
+            cur_chunk = chunk;
+#pragma unroll
+            for (int q = 0; q < K * K; ++q) {
+                const float2 v = c_ok ? __ldg(reinterpret_cast<const float2*>(p.w + (size_t)q * p.C + c)) : make_float2(0.f, 0.f);
+                wr[q][0] = v.x; wr[q][1] = v.y;
+            }
+            if (c_ok) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(p.scale + c));
+                const float2 d = __ldg(reinterpret_cast<const float2*>(p.bias + c));
+                sc[0] = a.x; sc[1] = a.y; bi[0] = d.x; bi[1] = d.y;
+            }
+        }
+        const int ho = th * p.Ht + r;
+        const int wo_base = tw * p.Ws + wl0;
+        const int n_out = max(0, min(p.n_t, p.Wo - wo_base));
+        const bool row_ok = ho < p.Ho;
+        float* orow = p.out + ((size_t)(b * p.Ho + ho) * p.Wo + wo_base) * p.C + c;
+        float sum[2] = {0.f, 0.f};
+
+        mbar_wait(bar_full(stage), phase);
+        // tile[row][col][32 ch]: this thread reads rows r*S + kh, columns wl0*S + j
+        const uint8_t* tp = tiles_gen + (size_t)stage * p.tile_bytes +
+                            ((size_t)(r * S) * p.Wbox + (size_t)wl0 * S) * (CC * 4) + cp * 8;
+        const int rstride = p.Wbox * CC * 4;
+        if (row_ok && c_ok && n_out > 0) {
+            float acc[K][2];
+            const int n_cols = (n_out - 1) * S + K;
+            constexpr int G = K * S;
+            for (int jb = 0; jb < n_cols; jb += G) {
+#pragma unroll
+                for (int jj = 0; jj < G; ++jj) {
+                    const int j = jb + jj;
+                    if (j < n_cols) {
+                        float x[K][2];
+#pragma unroll
+                        for (int kh = 0; kh < K; ++kh) {
+                            const float2 v = *reinterpret_cast<const float2*>(tp + kh * rstride + j * (CC * 4));
+                            x[kh][0] = v.x; x[kh][1] = v.y;
+                        }
+#pragma unroll
+                        for (int kw = 0; kw < K; ++kw) {
+                            if ((jj - kw) % S != 0) continue;
+                            const int slot = ((((jj - kw) / S) % K) + K) % K;
+                            float t0 = x[0][0] * wr[kw][0], t1 = x[0][1] * wr[kw][1];
+#pragma unroll
+                            for (int kh = 1; kh < K; ++kh) {
+                                t0 = fmaf(x[kh][0], wr[kh * K + kw][0], t0);
+                                t1 = fmaf(x[kh][1], wr[kh * K + kw][1], t1);
+                            }
+                            acc[slot][0] = (kw == 0) ? t0 : acc[slot][0] + t0;
+                            acc[slot][1] = (kw == 0) ? t1 : acc[slot][1] + t1;
+                            if (kw == K - 1) {
+                                const int u = (j - kw) / S;
+                                if (j >= kw && u < n_out) {
+                                    const float o0 = fast_swish(fmaf(acc[slot][0], sc[0], bi[0]));
+                                    const float o1 = fast_swish(fmaf(acc[slot][1], sc[1], bi[1]));
+                                    sum[0] += o0; sum[1] += o1;
+                                    *reinterpret_cast<float2*>(orow + (size_t)u * p.C) = make_float2(o0, o1);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(stage));      // this warp is done reading the stage
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+
+        // channel sums of this thread's outputs.  Lanes of a warp that hold the same channel pair (32 / TPG groups)
+        // are combined by shuffles in a fixed order, then one slot per (tile, warp) is written -- no CTA-wide
+        // barrier; the SE kernel adds the slots in a fixed order (deterministic).
+#pragma unroll
+        for (int o = 16; o >= TPG; o >>= 1) {
+            sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
+            sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+        }
+        if (c_ok && lane < TPG)
+            *reinterpret_cast<float2*>(p.partial + (((size_t)b * (p.tiles_h * p.tiles_w) + th * p.tiles_w + tw) * (DW_COMPUTE_THREADS / 32) + warp) * p.C + c) =
+                make_float2(sum[0], sum[1]);
+    }
+}
+
+static int dw_chunk(int C) { return C >= 256 ? 64 : (C >= 32 ? 32 : 16); }
+
+static void dw_tile_shape(int Ho, int Wo, int C, int k, int s, int& CC, int& groups, int& Ht, int& Ws, int& nsub, int& n_t) {
+    CC = dw_chunk(C);
+    groups = DW_COMPUTE_THREADS / (CC / 2);
+    Ht = Ho >= 8 ? 8 : (Ho >= 4 ? 4 : (Ho >= 2 ? 2 : 1));
+    nsub = groups / Ht;
+    // output columns per thread: 16 when the row is long enough, never below 4
+    n_t = 16;
+    while (n_t > 4 && nsub * (n_t / 2) >= Wo) n_t /= 2;
+    if (s == 2 && n_t > 8) n_t = 8;       // keep the stride-2 input box comparable
+    Ws = nsub * n_t;
+    // at least two tiles (input box with halo) must fit in shared memory
+    while (n_t > 1 && (size_t)((Ht - 1) * s + k) * ((Ws - 1) * s + k) * CC * 4 * 2 > (size_t)DW_SMEM_LIMIT - 512) {
+        n_t /= 2;
+        Ws = nsub * n_t;
+    }
+}
+
+int dwconv_tiles_per_clip(int Ho, int Wo, int C, int k, int s) {
+    int CC, groups, Ht, Ws, nsub, n_t;
+    dw_tile_shape(Ho, Wo, C, k, s, CC, groups, Ht, Ws, nsub, n_t);
+    return cdiv(Ho, Ht) * cdiv(Wo, Ws) * (DW_COMPUTE_THREADS / 32);
+}
+
+int dwconv_tma(const DwArgs& a, cudaStream_t st) {
+    AC_REQUIRE((a.k == 3 || a.k == 5) && (a.s == 1 || a.s == 2), "dwconv_tma: unsupported k=%d s=%d", a.k, a.s);
+    AC_REQUIRE(a.C % 4 == 0 && ((uintptr_t)a.in & 15) == 0, "dwconv_tma: C %% 4 and 16-byte aligned input required");
+    if (a.B == 0) return AC_OK;
+    auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(tensor_map_encode_fn());
+    AC_REQUIRE(encode != nullptr, "dwconv_tma: cuTensorMapEncodeTiled is not available from the driver");
+    DwParams p;
+    p.out = a.out; p.partial = a.partial; p.w = a.w; p.scale = a.scale; p.bias = a.bias;
+    p.B = a.B; p.Ho = a.Ho; p.Wo = a.Wo; p.C = a.C; p.pad_lo = a.pad_lo;
+    dw_tile_shape(a.Ho, a.Wo, a.C, a.k, a.s, p.CC, p.groups, p.Ht, p.Ws, p.nsub, p.n_t);
+    p.tiles_h = cdiv(a.Ho, p.Ht); p.tiles_w = cdiv(a.Wo, p.Ws); p.chunks = cdiv(a.C, p.CC);
+    p.total_tiles = p.chunks * a.B * p.tiles_h * p.tiles_w;
+    p.Hbox = (p.Ht - 1) * a.s + a.k; p.Wbox = (p.Ws - 1) * a.s + a.k;
+    AC_REQUIRE(p.Wbox <= 256 && p.Hbox <= 256, "dwconv_tma: tile too large");
+    p.tile_bytes = (int)align_up((size_t)p.Hbox * p.Wbox * p.CC * 4, 128);
+    const int fixed = 128 + 128;
+    p.stages = std::min(DW_MAX_STAGES, (DW_SMEM_LIMIT - fixed) / p.tile_bytes);
+    AC_REQUIRE(p.stages >= 2, "dwconv_tma: tile of %d bytes does not fit twice in shared memory", p.tile_bytes);
+    const size_t smem = (size_t)p.stages * p.tile_bytes + fixed;
+
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)a.C * 4, (cuuint64_t)a.Wi * a.C * 4, (cuuint64_t)a.Hi * a.Wi * a.C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)p.CC, (cuuint32_t)p.Wbox, (cuuint32_t)p.Hbox, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AC_REQUIRE(cr == CUDA_SUCCESS, "dwconv_tma: cuTensorMapEncodeTiled failed (%d) C=%d Wi=%d Hi=%d B=%d box %dx%d", (int)cr,
+               a.C, a.Wi, a.Hi, a.B, p.Wbox, p.Hbox);
+    const int grid = std::min(p.total_tiles, kNumSMs);
+    AC_TIMED(a.k == 3 ? "dwconv_k3" : "dwconv_k5", st);
+#define AC_DW_TMA(K, S, CC)                                                                                      \
+    do {                                                                                                         \
+        static cudaError_t attr_rc = cudaFuncSetAttribute(dwconv_tma_kernel<K, S, CC>,                           \
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT); \
+        AC_CUDA(attr_rc);                                                                                        \
+        dwconv_tma_kernel<K, S, CC><<<grid, DW_THREADS, smem, st>>>(map, p);                                     \
+    } while (0)
+#define AC_DW_KS(CC)                                         \
+    do {                                                     \
+        if (a.k == 3 && a.s == 1) AC_DW_TMA(3, 1, CC);       \
+        else if (a.k == 3 && a.s == 2) AC_DW_TMA(3, 2, CC);  \
+        else if (a.k == 5 && a.s == 1) AC_DW_TMA(5, 1, CC);  \
+        else AC_DW_TMA(5, 2, CC);                            \
+    } while (0)
+    if (p.CC == 64) AC_DW_KS(64);
+    else if (p.CC == 32) AC_DW_KS(32);
+    else AC_DW_KS(16);
+#undef AC_DW_KS
+#undef AC_DW_TMA
+    AC_LAUNCHED("dwconv_tma_kernel");
+    return AC_OK;
+}
+
+}  // namespace ac

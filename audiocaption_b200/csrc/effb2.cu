@@ -16,6 +16,8 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -156,6 +158,9 @@ dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w /*[K*K][
               const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ out,
               float* __restrict__ partial, int Hi, int Wi, int Ho, int Wo, int C, int pad_lo, int lw, int nseg,
               int64_t total) {
+    // Scatter form of the sliding window: the thread reads ONE input column (K rows, V channels) per step and
+    // adds it into the <= K output pixels it touches (ring of K accumulators); an output is finished when its
+    // last column has been added.  Registers: K*K weights + one column + K accumulators -- no window copy.
     typedef typename VecT<V>::type T;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -165,7 +170,7 @@ dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w /*[K*K][
     const int ho = (int)(r % Ho); r /= Ho;
     const int seg = (int)(r % nseg);
     const int b = (int)(r / nseg);
-    const int wo0 = seg * lw, wo1 = min(wo0 + lw, Wo);
+    const int wo0 = seg * lw, n_out = min(lw, Wo - wo0);
 
     float wr[K * K][V];
 #pragma unroll
@@ -174,55 +179,65 @@ dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w /*[K*K][
     vec_load<V>(sc, scale + c);
     vec_load<V>(bi, bias + c);
 
-    const float* rowp[K];
+    const int ih0 = ho * S - pad_lo;
+    const int iw0 = wo0 * S - pad_lo;              // input column of relative column 0
+    bool rv[K];
 #pragma unroll
-    for (int kh = 0; kh < K; ++kh) {
-        const int ih = ho * S + kh - pad_lo;
-        rowp[kh] = (ih >= 0 && ih < Hi) ? in + ((size_t)(b * Hi + ih) * Wi) * C + c : nullptr;
-    }
-    const int iw0 = wo0 * S - pad_lo;              // input column of window slot 0 for the first output
-    float x[K][K][V];                              // [kh][column slot (input column - iw0) % K]
-    auto load_col = [&](int j, int slot) {         // j = input column relative to iw0
-        const int iw = iw0 + j;
-        const bool ok = iw >= 0 && iw < Wi;
-#pragma unroll
-        for (int kh = 0; kh < K; ++kh) {
-            if (ok && rowp[kh] != nullptr) vec_load<V>(x[kh][slot], rowp[kh] + (size_t)iw * C);
-            else {
-#pragma unroll
-                for (int e = 0; e < V; ++e) x[kh][slot][e] = 0.0f;
-            }
-        }
-    };
-#pragma unroll
-    for (int j = 0; j < K - S; ++j) load_col(j, j);        // columns shared with the first output's window
+    for (int kh = 0; kh < K; ++kh) rv[kh] = (ih0 + kh >= 0) && (ih0 + kh < Hi);
+    // pointer to (row ih0, column iw0) of this clip / channel run; rows are Wi*C apart (may point outside the
+    // tensor for padded rows / columns: those loads are predicated off)
+    const float* pc = in + ((int64_t)(b * Hi + ih0) * Wi + iw0) * C + c;
+    const int rstride = Wi * C;
+    float* orow = out + ((size_t)(b * Ho + ho) * Wo + wo0) * C + c;
+
+    float acc[K][V];
     float sum[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) sum[e] = 0.0f;
-    float* orow = out + ((size_t)(b * Ho + ho) * Wo) * C + c;
-    // outputs in groups of K so that every window slot index is a compile-time constant
-    for (int base = 0; wo0 + base < wo1; base += K) {
+    const int n_cols = (n_out - 1) * S + K;        // input columns this segment touches
+    constexpr int G = K * S;                        // unroll period: every slot / tap index is a constant
+    for (int base = 0; base < n_cols; base += G) {
 #pragma unroll
-        for (int u = 0; u < K; ++u) {
-            const int wo = wo0 + base + u;
-            if (wo < wo1) {
-                // new columns of this output: relative columns (base+u)*S + K-S .. (base+u)*S + K-1
+        for (int jj = 0; jj < G; ++jj) {
+            const int j = base + jj;
+            if (j < n_cols) {
+                const int iw = iw0 + j;
+                const bool cok = iw >= 0 && iw < Wi;
+                float x[K][V];
 #pragma unroll
-                for (int q = 0; q < S; ++q) load_col((base + u) * S + K - S + q, (u * S + K - S + q) % K);
-                float acc[V];
+                for (int kh = 0; kh < K; ++kh) {
+                    if (cok && rv[kh]) vec_load<V>(x[kh], pc + (int64_t)kh * rstride + (int64_t)j * C);
+                    else {
 #pragma unroll
-                for (int e = 0; e < V; ++e) acc[e] = 0.0f;
-#pragma unroll
-                for (int kh = 0; kh < K; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < K; ++kw) vec_fma<V>(acc, x[kh][(u * S + kw) % K], wr[kh * K + kw]);
-                float o[V];
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    o[e] = swishf(fmaf(acc[e], sc[e], bi[e]));
-                    sum[e] += o[e];
+                        for (int e = 0; e < V; ++e) x[kh][e] = 0.0f;
+                    }
                 }
-                *reinterpret_cast<T*>(orow + (size_t)wo * C) = *reinterpret_cast<const T*>(o);
+#pragma unroll
+                for (int kw = 0; kw < K; ++kw) {
+                    if ((jj - kw) % S != 0) continue;           // this column is not tap kw of any output
+                    // output u = (j - kw) / S, ring slot u % K; both compile-time given jj (base % (K*S) == 0)
+                    constexpr int dummy = 0; (void)dummy;
+                    const int slot = ((((jj - kw) / S) % K) + K) % K;
+                    float t[V];
+#pragma unroll
+                    for (int e = 0; e < V; ++e) t[e] = x[0][e] * wr[kw][e];
+#pragma unroll
+                    for (int kh = 1; kh < K; ++kh) vec_fma<V>(t, x[kh], wr[kh * K + kw]);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[slot][e] = (kw == 0) ? t[e] : acc[slot][e] + t[e];
+                    if (kw == K - 1) {                          // last tap: output u is complete
+                        const int u = (j - kw) / S;
+                        if (j >= kw && u < n_out) {
+                            float o[V];
+#pragma unroll
+                            for (int e = 0; e < V; ++e) {
+                                o[e] = fast_swish(fmaf(acc[slot][e], sc[e], bi[e]));
+                                sum[e] += o[e];
+                            }
+                            *reinterpret_cast<T*>(orow + (size_t)u * C) = *reinterpret_cast<const T*>(o);
+                        }
+                    }
+                }
             }
         }
     }
@@ -231,23 +246,31 @@ dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w /*[K*K][
 }
 
 // ----------------------------------------------------------------------------- squeeze-excite
-// partial [B][strips][C] -> gate [B][C] = sigmoid(We * swish(Wr * mean + br) + be).  One CTA per clip.
+// partial [B][strips][C] -> gate [B][C] = sigmoid(We * swish(Wr * mean + br) + be).
+// One thread-block CLUSTER per clip (P = 1..8 CTAs): every CTA owns 1/P of the channels (mean and gate) and
+// 1/P of the squeezed units, so each CTA streams only 1/P of the two FC weight matrices; the mean vector and
+// the squeezed vector are exchanged through distributed shared memory between the phases.
 // wr [nsq][C], we_t [nsq][C] (transposed at pack time so that both FC layers read coalesced rows).
-constexpr int kSeThreads = 512;
+constexpr int kSeThreads = 256;
 __global__ void __launch_bounds__(kSeThreads)
 se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const float* __restrict__ wr,
           const float* __restrict__ br, const float* __restrict__ we_t, const float* __restrict__ be,
           float* __restrict__ gate, int C, int nsq) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int P = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     extern __shared__ __align__(16) float s_se[];   // mean[C] | r[nsq] | scratch[kSeThreads * 4]
     float* s_mean = s_se;
     float* s_r = s_se + C;
     float4* s_scr = reinterpret_cast<float4*>(s_se + ((C + nsq + 3) / 4) * 4);
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c4n = C / 4;
+    const int q0 = (int)((int64_t)c4n * rank / P), q1 = (int)((int64_t)c4n * (rank + 1) / P);   // my channel quads
+    const int j0 = (int)((int64_t)nsq * rank / P), j1 = (int)((int64_t)nsq * (rank + 1) / P);   // my squeezed units
     const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)b * strips * C);
-    // 1. channel means: thread = (strip group g, channel quad), fixed-order two-level sum (deterministic)
-    for (int cbase = 0; cbase < c4n; cbase += kSeThreads) {
-        const int width = min(c4n - cbase, kSeThreads);
+    // 1. channel means of my quads: thread = (strip group g, quad), fixed-order two-level sum (deterministic)
+    for (int cbase = q0; cbase < q1; cbase += kSeThreads) {
+        const int width = min(q1 - cbase, kSeThreads);
         const int G = max(1, min(kSeThreads / width, strips));
         const int g = tid / width, c4 = cbase + tid % width;
         if (g < G) {
@@ -269,20 +292,48 @@ se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const flo
         }
         __syncthreads();
     }
-    // 2. squeeze: r[j] = swish(wr[j] . mean + br[j]), one warp per output
-    for (int j = warp; j < nsq; j += kSeThreads / 32) {
+    if (P > 1) {
+        cluster.sync();
+        for (int c4 = tid; c4 < c4n; c4 += kSeThreads) {        // gather the other CTAs' quads
+            if (c4 >= q0 && c4 < q1) continue;
+            int owner = (int)(((int64_t)(c4 + 1) * P - 1) / c4n);
+            while ((int)((int64_t)c4n * owner / P) > c4) --owner;
+            while ((int)((int64_t)c4n * (owner + 1) / P) <= c4) ++owner;
+            const float4* remote = reinterpret_cast<const float4*>(cluster.map_shared_rank(s_mean, owner));
+            reinterpret_cast<float4*>(s_mean)[c4] = remote[c4];
+        }
+        __syncthreads();
+    }
+    // 2. squeeze: r[j] = swish(wr[j] . mean + br[j]) for my units, one warp per unit
+    for (int j = j0 + warp; j < j1; j += kSeThreads / 32) {
         float s = 0.f;
         for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + (size_t)j * C + c), s_mean[c], s);
         s = warp_sum(s);
         if (lane == 0) s_r[j] = swishf(s + br[j]);
     }
-    __syncthreads();
-    // 3. excite: gate[c] = sigmoid(sum_j we_t[j][c] * r[j] + be[c])
-    for (int c = tid; c < C; c += kSeThreads) {
-        float s = 0.f;
-        for (int j = 0; j < nsq; ++j) s = fmaf(__ldg(we_t + (size_t)j * C + c), s_r[j], s);
-        gate[(size_t)b * C + c] = sigmoidf_(s + be[c]);
+    if (P > 1) {
+        cluster.sync();
+        for (int j = tid; j < nsq; j += kSeThreads) {
+            if (j >= j0 && j < j1) continue;
+            int owner = (int)(((int64_t)(j + 1) * P - 1) / nsq);
+            while ((int)((int64_t)nsq * owner / P) > j) --owner;
+            while ((int)((int64_t)nsq * (owner + 1) / P) <= j) ++owner;
+            s_r[j] = cluster.map_shared_rank(s_r, owner)[j];
+        }
     }
+    __syncthreads();
+    // 3. excite: gate[c] = sigmoid(sum_j we_t[j][c] * r[j] + be[c]) for my channels
+    for (int c = 4 * q0 + tid; c < 4 * q1; c += kSeThreads) {
+        float s0 = 0.f, s1 = 0.f;
+        int j = 0;
+        for (; j + 1 < nsq; j += 2) {
+            s0 = fmaf(__ldg(we_t + (size_t)j * C + c), s_r[j], s0);
+            s1 = fmaf(__ldg(we_t + (size_t)(j + 1) * C + c), s_r[j + 1], s1);
+        }
+        if (j < nsq) s0 = fmaf(__ldg(we_t + (size_t)j * C + c), s_r[j], s0);
+        gate[(size_t)b * C + c] = sigmoidf_(s0 + s1 + be[c]);
+    }
+    if (P > 1) cluster.sync();   // nobody exits while a peer may still read its shared memory
 }
 
 // ----------------------------------------------------------------------------- head tail
@@ -324,6 +375,25 @@ struct BlockW {
     ConvBN expand, dw, project;
     float *se_wr, *se_br, *se_we, *se_be;
 };
+
+static int launch_se(const float* partial, int strips, float inv_hw, const BlockW& w, float* gate, int B, int C,
+                     int nsq, cudaStream_t st) {
+    int P = 1;
+    while (P < 8 && C / (P * 2) >= 8) P *= 2;           // >= 2 channel quads per CTA
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * P); cfg.blockDim = dim3(kSeThreads);
+    cfg.dynamicSmemBytes = (((C + nsq + 3) / 4) * 4 + kSeThreads * 4) * sizeof(float);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    AC_TIMED("se", st);
+    AC_CUDA(cudaLaunchKernelEx(&cfg, se_kernel, partial, strips, inv_hw, (const float*)w.se_wr, (const float*)w.se_br,
+                               (const float*)w.se_we, (const float*)w.se_be, gate, C, nsq));
+    AC_LAUNCHED("se_kernel");
+    return AC_OK;
+}
 
 static int out_size(int in, int k, int s, int lo, int hi) { return (in + lo + hi - k) / s + 1; }
 
@@ -378,7 +448,7 @@ static WsLayout ws_layout(int batch, int n_mels, int n_frames) {
         L.x_elems = std::max(L.x_elems, pout * b.cout);
         if (b.expand != 1) L.e_elems = std::max(L.e_elems, pin * b.cexp());
         L.d_elems = std::max(L.d_elems, pout * b.cexp());
-        size_t strips = (size_t)dout[i].H * cdiv(dout[i].W, dw_seg_len(batch, dout[i].H, dout[i].W, b.cexp(), b.k));
+        size_t strips = (size_t)dwconv_tiles_per_clip(dout[i].H, dout[i].W, b.cexp(), b.k, b.s);
         L.part_elems = std::max(L.part_elems, strips * b.cexp());
         L.gate_elems = std::max(L.gate_elems, (size_t)b.cexp());
     }
@@ -596,14 +666,13 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
             int rc = gemm_tn(g, st); if (rc) return rc;
             dw_in = E;
         }
-        int rc = launch_dw(dw_in, w.dw, D, PART, B, din[i], dout[i], ce, b, st); if (rc) return rc;
-        const int strips = dout[i].H * cdiv(dout[i].W, dw_seg_len(B, dout[i].H, dout[i].W, ce, b.k));
-        {
-        AC_TIMED("se", st);
-        se_kernel<<<B, kSeThreads, (((ce + b.nsq + 3) / 4) * 4 + kSeThreads * 4) * sizeof(float), st>>>(PART, strips, 1.0f / (float)pout, w.se_wr, w.se_br,
-                                                                w.se_we, w.se_be, GATE, ce, b.nsq);
-        AC_LAUNCHED("se_kernel");
-        }
+        DwArgs da;
+        da.in = dw_in; da.out = D; da.partial = PART; da.w = w.dw.w; da.scale = w.dw.scale; da.bias = w.dw.bias;
+        da.B = B; da.Hi = din[i].H; da.Wi = din[i].W; da.Ho = dout[i].H; da.Wo = dout[i].W; da.C = ce;
+        da.k = b.k; da.s = b.s; da.pad_lo = b.pad_lo;
+        int rc = dwconv_tma(da, st); if (rc) return rc;
+        const int strips = dwconv_tiles_per_clip(dout[i].H, dout[i].W, ce, b.k, b.s);
+        rc = launch_se(PART, strips, 1.0f / (float)pout, w, GATE, B, ce, b.nsq, st); if (rc) return rc;
         GemmArgs g; g.A = D; g.W = w.project.w; g.C = nxt; g.M = B * pout; g.N = b.cout; g.K = ce;
         g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
         g.act = ACT_NONE; g.R = b.skip ? cur : nullptr;

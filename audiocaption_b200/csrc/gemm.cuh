@@ -48,5 +48,18 @@ struct GemmArgs {
 int gemm_tn(const GemmArgs& g, cudaStream_t st);
 int gemm_tn_simt(const GemmArgs& g, cudaStream_t st);
 int gemm_tc(const GemmArgs& g, cudaStream_t st);
+void* tensor_map_encode_fn();   // PFN_cuTensorMapEncodeTiled or nullptr
+
+// Depthwise k x k convolution + folded BN + swish + per-tile channel sums (SE squeeze), NHWC fp32, fed by 4-D
+// TMA tiles (dwconv_tma.cu).  in [B,Hi,Wi,C] -> out [B,Ho,Wo,C]; partial [B][dwconv_tiles_per_clip][C].
+struct DwArgs {
+    const float* in; float* out; float* partial;
+    const float* w;       // [k*k][C]
+    const float* scale;   // [C] folded BN
+    const float* bias;    // [C]
+    int B, Hi, Wi, Ho, Wo, C, k, s, pad_lo;
+};
+int dwconv_tiles_per_clip(int Ho, int Wo, int C, int k, int s);   // second dimension of `partial` (tiles x warps)
+int dwconv_tma(const DwArgs& a, cudaStream_t st);
 
 }  // namespace ac

@@ -54,8 +54,6 @@ struct TcParams {
     int BN, n_tiles, m_tiles, k_chunks, stages, tmem_cols, resident;
 };
 
-__device__ __forceinline__ float fast_swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-
 template <int ACT>
 __device__ __forceinline__ float4 epi_math(const uint32_t* u, float4 b) {
     float v[4] = {__uint_as_float(u[0]) + b.x, __uint_as_float(u[1]) + b.y, __uint_as_float(u[2]) + b.z,
@@ -397,7 +395,23 @@ int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, flo
 }
 
 // ------------------------------------------------------------------------------------ launch
+void* tensor_map_encode_fn() {   // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
+    static void* fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = p;
+    });
+    return fn;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(tensor_map_encode_fn());
+}
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder_unused() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {

@@ -10,11 +10,16 @@
 //   once per call : P = LayerNorm(ReLU(attn_emb W0^T + b0));  K_l, V_l = P Wkv_l^T + bkv_l   (GEMMs)
 //   per step      : one token per row through the 2 post-norm layers with cached self-attention
 //                   K/V, cross-attention against K_l/V_l, FFN, classifier.
-// Clips are independent, so ONE CTA owns one clip for the whole decode (all `max_len` steps,
-// `R` = 1 row for greedy, `R` = beam rows for beam search): no grid-wide synchronisation, no
-// host round trip per token, a single launch.  Weights are stored transposed ([K][N]) at pack
-// time so that thread n streams column n with coalesced loads while the R activations are
-// broadcast from shared memory.
+// Clips are independent, so one thread-block CLUSTER owns a small group of rows for the whole decode (all
+// `max_len` steps): no grid-wide synchronisation, no host round trip per token, a single launch.  A step is
+// bound by streaming the 12.4 MB of weights out of L2, so (a) the P CTAs of a cluster each stream 1/P of the
+// output columns of every projection / FFN / classifier GEMV and push their slice of the result into every
+// CTA's shared memory (distributed shared memory), and (b) greedy decoding groups 4 clips per cluster of 8 CTAs
+// (R = 4 rows share every weight load; beam search: R = beam rows of one clip, 2 CTAs), which divides the L2
+// traffic by 4 and keeps 128 of the 148 SMs pulling weights.  The cheap per-row work (attention over the
+// caches, LayerNorm, log-softmax / arg-max / top-k) is done redundantly by every CTA of the cluster, so nothing
+// but the GEMV slices has to be exchanged.  Weights are stored transposed ([K][N]) at pack time so
+// that thread n streams column n with coalesced loads while the R activations are broadcast from shared memory.
 //
 // Masks: causal by construction (only positions <= t are cached); `tgt_key_padding_mask`
 // = (prefix token == <pad>) and `memory_key_padding_mask` = (frame >= attn_emb_len) are applied
@@ -23,11 +28,17 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
 namespace ac {
 
+namespace cg = cooperative_groups;
+constexpr int kBeamCluster = 2;     // beam search: CTAs per clip (rows = beams of ONE clip)
+constexpr int kGreedyCluster = 2;   // greedy: CTAs per cluster ...
+constexpr int kGreedyClips = 1;     // ... which decodes this many clips at once (rows = clips)
 constexpr int D = 256;          // d_model
 constexpr int NH = 4;           // heads
 constexpr int HD = 64;          // head dim
@@ -63,18 +74,20 @@ struct DecW {
 template <int R>
 __device__ __forceinline__ void matvec_t(const float* __restrict__ Wt, const float* __restrict__ bias,
                                          const float* xin, int ldx, float* out, int ldo, int N, int K, bool relu,
-                                         float* part) {
-    const int NC = N >> 2;
-    const int KS = max(1, min(kThreads / NC, 16));
+                                         float* part, int rank, int P) {
+    // this CTA owns column quads [rank * NCl, (rank + 1) * NCl) and writes them into EVERY CTA's `out`
+    const int NCl = (N >> 2) / P, NC = N >> 2;
+    const int Nl = NCl * 4;
+    const int KS = max(1, min(kThreads / NCl, 4096 / Nl));
     const int kslice = (K + KS - 1) / KS;
     const int tid = threadIdx.x;
-    const int s = tid / NC, c = tid - s * NC;
+    const int s = tid / NCl, cl = tid - s * NCl;
     if (s < KS) {
         const int k0 = s * kslice, k1 = min(K, k0 + kslice);
         float acc[R][4];
 #pragma unroll
         for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-        const float4* w = reinterpret_cast<const float4*>(Wt) + c;
+        const float4* w = reinterpret_cast<const float4*>(Wt) + rank * NCl + cl;
 #pragma unroll 8
         for (int k = k0; k < k1; ++k) {
             const float4 wv = __ldg(w + (size_t)k * NC);
@@ -87,15 +100,18 @@ __device__ __forceinline__ void matvec_t(const float* __restrict__ Wt, const flo
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            *reinterpret_cast<float4*>(part + ((size_t)s * R + r) * N + 4 * c) =
+            *reinterpret_cast<float4*>(part + ((size_t)s * R + r) * Nl + 4 * cl) =
                 make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     }
     __syncthreads();
-    for (int i = tid; i < R * N; i += kThreads) {
-        const int r = i / N, n = i - r * N;
+    cg::cluster_group cluster = cg::this_cluster();
+    for (int i = tid; i < R * Nl; i += kThreads) {
+        const int r = i / Nl, nl = i - r * Nl;
+        const int n = rank * Nl + nl;
         float v = bias ? __ldg(bias + n) : 0.0f;
-        for (int q = 0; q < KS; ++q) v += part[((size_t)q * R + r) * N + n];
-        out[r * ldo + n] = relu ? fmaxf(v, 0.0f) : v;
+        for (int q = 0; q < KS; ++q) v += part[((size_t)q * R + r) * Nl + nl];
+        v = relu ? fmaxf(v, 0.0f) : v;
+        for (int pr = 0; pr < P; ++pr) cluster.map_shared_rank(out, pr)[r * ldo + n] = v;   // own copy included
     }
 }
 
@@ -159,16 +175,22 @@ struct DecodeArgs {
     int beam; float temp;
 };
 
-// One decoder step for the R rows of this clip: token ids `words[r]` at position t.
-// anc[r][j] = cache slot holding row r's ancestor at position j (greedy: always r).
-// On return s_x holds the final hidden states [R][D]; logits are written to `logits` ([R][V], global).
-template <int R>
+// One decoder step for the R rows of this cluster: token ids `words[r]` at position t.  Rows are grouped RPC
+// per clip: row r belongs to clip `clip + r / RPC` (greedy: RPC = 1, every row is its own clip; beam: RPC = R).
+// anc[r][j] = row (of this cluster, same clip) whose cache slot holds row r's ancestor at position j.
+// On return s_x holds the final hidden states [R][D]; row r's logits are written to logits[r] ([V], global).
+template <int R, int RPC>
 __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* words, const int (*anc)[kMaxLen],
                              const unsigned char (*padflag)[8], float* s_x, float* s_q, float* s_att, float* s_h,
-                             float* s_sc, float* s_part, float* logits) {
+                             float* s_sc, float* s_part, float* s_c, float* const* logits) {
+    // Buffers written through distributed shared memory by the peer CTA (GEMV outputs): s_h, s_q, s_c.  Each is
+    // only ever the output of a GEMV whose surrounding cluster.sync() interval does not touch it otherwise.
     const DecW& W = a.w;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), P = (int)cluster.num_blocks();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_mem = min((int)min((int64_t)a.t_mem, a.mem_len[clip]), a.t_mem);
+    auto clip_of = [&](int r) { return min(clip + r / RPC, a.n_clips - 1); };   // rows past the batch replay the last clip
+    auto n_mem_of = [&](int r) { return min((int)min((int64_t)a.t_mem, a.mem_len[clip_of(r)]), a.t_mem); };
     // embedding * sqrt(d) + positional encoding
     for (int i = tid; i < R * D; i += kThreads) {
         const int r = i / D, f = i - r * D;
@@ -178,23 +200,27 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
 
     for (int l = 0; l < W.nlayers; ++l) {
         const LayerW& L = W.layer[l];
-        float* kc = a.kv_cache + ((((size_t)clip * W.nlayers + l) * 2 + 0) * a.max_len) * R * D;
-        float* vc = a.kv_cache + ((((size_t)clip * W.nlayers + l) * 2 + 1) * a.max_len) * R * D;
+        // cache of row r: [clip][layer][K|V][position][RPC][D]
+        auto kcache = [&](int r, int kv) {
+            return a.kv_cache + ((((size_t)clip_of(r) * W.nlayers + l) * 2 + kv) * a.max_len) * RPC * D;
+        };
         // ---- self attention
-        matvec_t<R>(L.sa_in_wt, L.sa_in_b, s_x, D, s_h, 3 * D, 3 * D, D, false, s_part);
-        __syncthreads();
+        matvec_t<R>(L.sa_in_wt, L.sa_in_b, s_x, D, s_h, 3 * D, 3 * D, D, false, s_part, rank, P);
+        cluster.sync();
         for (int i = tid; i < R * D; i += kThreads) {
             const int r = i / D, f = i - r * D;
-            s_q[i] = s_h[r * 3 * D + f] * 0.125f;
-            kc[((size_t)t * R + r) * D + f] = s_h[r * 3 * D + D + f];
-            vc[((size_t)t * R + r) * D + f] = s_h[r * 3 * D + 2 * D + f];
+            s_c[i] = s_h[r * 3 * D + f] * 0.125f;
+            if (clip + r / RPC < a.n_clips) {   // rows past the batch only read the clip they replay
+                kcache(r, 0)[((size_t)t * RPC + r % RPC) * D + f] = s_h[r * 3 * D + D + f];
+                kcache(r, 1)[((size_t)t * RPC + r % RPC) * D + f] = s_h[r * 3 * D + 2 * D + f];
+            }
         }
         __syncthreads();   // also orders the cache writes before the reads below (same CTA)
         const int nk = t + 1;
         for (int it = warp; it < R * NH * nk; it += kWarps) {
             const int j = it % nk, hh = (it / nk) % NH, r = it / (nk * NH);
-            const float* kp = kc + ((size_t)j * R + anc[r][j]) * D + hh * HD;
-            const float* qp = s_q + r * D + hh * HD;
+            const float* kp = kcache(r, 0) + ((size_t)j * RPC + anc[r][j] % RPC) * D + hh * HD;
+            const float* qp = s_c + r * D + hh * HD;
             float s = qp[lane] * kp[lane] + qp[lane + 32] * kp[lane + 32];
             s = warp_sum(s);
             if (lane == 0) s_sc[(r * NH + hh) * kMaxKeys + j] = padflag[j][anc[r][j]] ? -INFINITY : s;
@@ -205,26 +231,27 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
         for (int i = tid; i < R * D; i += kThreads) {
             const int r = i / D, f = i - r * D;
             const float* p = s_sc + (r * NH + f / HD) * kMaxKeys;
+            const float* vc = kcache(r, 1);
             float o = 0.f;
-            for (int j = 0; j < nk; ++j) o = fmaf(p[j], vc[((size_t)j * R + anc[r][j]) * D + f], o);
+            for (int j = 0; j < nk; ++j) o = fmaf(p[j], vc[((size_t)j * RPC + anc[r][j] % RPC) * D + f], o);
             s_att[i] = o;
         }
         __syncthreads();
-        matvec_t<R>(L.sa_out_wt, L.sa_out_b, s_att, D, s_q, D, D, D, false, s_part);
-        __syncthreads();
+        matvec_t<R>(L.sa_out_wt, L.sa_out_b, s_att, D, s_q, D, D, D, false, s_part, rank, P);
+        cluster.sync();
         add_layernorm<R>(s_x, s_q, L.n1_g, L.n1_b);
         __syncthreads();
         // ---- cross attention over the projected audio memory
-        matvec_t<R>(L.ca_q_wt, L.ca_q_b, s_x, D, s_q, D, D, D, false, s_part);
-        __syncthreads();
-        const float* km = a.kv_mem + (((size_t)l * a.n_clips + clip) * a.t_mem) * 2 * D;
+        matvec_t<R>(L.ca_q_wt, L.ca_q_b, s_x, D, s_c, D, D, D, false, s_part, rank, P);
+        cluster.sync();
+        auto kmem = [&](int r) { return a.kv_mem + (((size_t)l * a.n_clips + clip_of(r)) * a.t_mem) * 2 * D; };
         for (int it = warp; it < R * NH * a.t_mem; it += kWarps) {
             const int j = it % a.t_mem, hh = (it / a.t_mem) % NH, r = it / (a.t_mem * NH);
-            const float* kp = km + (size_t)j * 2 * D + hh * HD;
-            const float* qp = s_q + r * D + hh * HD;
+            const float* kp = kmem(r) + (size_t)j * 2 * D + hh * HD;
+            const float* qp = s_c + r * D + hh * HD;
             float s = qp[lane] * __ldg(kp + lane) + qp[lane + 32] * __ldg(kp + lane + 32);
             s = warp_sum(s) * 0.125f;
-            if (lane == 0) s_sc[(r * NH + hh) * kMaxKeys + j] = j < n_mem ? s : -INFINITY;
+            if (lane == 0) s_sc[(r * NH + hh) * kMaxKeys + j] = j < n_mem_of(r) ? s : -INFINITY;
         }
         __syncthreads();
         softmax_rows<R>(s_sc, a.t_mem);
@@ -232,26 +259,29 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
         for (int i = tid; i < R * D; i += kThreads) {
             const int r = i / D, f = i - r * D;
             const float* p = s_sc + (r * NH + f / HD) * kMaxKeys;
+            const float* km = kmem(r);
+            const int n_mem = n_mem_of(r);
             float o = 0.f;
             for (int j = 0; j < n_mem; ++j) o = fmaf(p[j], __ldg(km + (size_t)j * 2 * D + D + f), o);
             s_att[i] = o;
         }
         __syncthreads();
-        matvec_t<R>(L.ca_out_wt, L.ca_out_b, s_att, D, s_q, D, D, D, false, s_part);
-        __syncthreads();
+        matvec_t<R>(L.ca_out_wt, L.ca_out_b, s_att, D, s_q, D, D, D, false, s_part, rank, P);
+        cluster.sync();
         add_layernorm<R>(s_x, s_q, L.n2_g, L.n2_b);
         __syncthreads();
         // ---- feed forward
-        matvec_t<R>(L.ff1_wt, L.ff1_b, s_x, D, s_h, W.dff, W.dff, D, true, s_part);
-        __syncthreads();
-        matvec_t<R>(L.ff2_wt, L.ff2_b, s_h, W.dff, s_q, D, D, W.dff, false, s_part);
-        __syncthreads();
+        matvec_t<R>(L.ff1_wt, L.ff1_b, s_x, D, s_h, W.dff, W.dff, D, true, s_part, rank, P);
+        cluster.sync();
+        matvec_t<R>(L.ff2_wt, L.ff2_b, s_h, W.dff, s_q, D, D, W.dff, false, s_part, rank, P);
+        cluster.sync();
         add_layernorm<R>(s_x, s_q, L.n3_g, L.n3_b);
         __syncthreads();
     }
     // ---- classifier (no bias): each thread owns column quads of the zero-padded [D][Vp] weight
     const int V = W.vocab, VC = (V + 3) >> 2;
-    for (int c = tid; c < VC; c += kThreads) {
+    const int vc0 = (int)((int64_t)VC * rank / P), vc1 = (int)((int64_t)VC * (rank + 1) / P);
+    for (int c = vc0 + tid; c < vc1; c += kThreads) {
         float acc[R][4];
 #pragma unroll
         for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
@@ -270,9 +300,9 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (4 * c + q < V) logits[(size_t)r * V + 4 * c + q] = acc[r][q];
+                if (4 * c + q < V && clip + r / RPC < a.n_clips) logits[r][4 * c + q] = acc[r][q];
     }
-    __syncthreads();
+    cluster.sync();   // both halves of the logits (global memory) are visible to both CTAs
 }
 
 // block-wide (max value, lowest index) reduction
@@ -314,57 +344,79 @@ __device__ __forceinline__ float block_sum(float v, float* s_v) {
     return t;
 }
 
-constexpr size_t dec_smem_floats(int R) { return (size_t)R * (D + D + D + 1024 + NH * kMaxKeys + 4096); }
+constexpr size_t dec_smem_floats(int R) { return (size_t)R * (D + D + D + 1024 + NH * kMaxKeys + 4096 + D); }
 
 // ------------------------------------------------------------------------------------ greedy
+// One cluster decodes G = kGreedyClips clips at once (row r = clip blockIdx.x / P * G + r).
+template <int G>
 __global__ void __launch_bounds__(kThreads)
 greedy_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) float smem[];
-    float* s_x = smem; float* s_q = s_x + D; float* s_att = s_q + D; float* s_h = s_att + D;
-    float* s_sc = s_h + 1024;
-    float* s_part = s_sc + NH * kMaxKeys;
-    __shared__ int s_anc[1][kMaxLen];
+    float* s_x = smem; float* s_q = s_x + G * D; float* s_att = s_q + G * D; float* s_h = s_att + G * D;
+    float* s_sc = s_h + G * 1024;
+    float* s_part = s_sc + G * NH * kMaxKeys;
+    float* s_c = s_part + G * 4096;
+    __shared__ int s_anc[G][kMaxLen];
     __shared__ unsigned char s_pad[kMaxLen][8];
     __shared__ float s_rv[kWarps];
     __shared__ int s_ri[kWarps];
-    __shared__ int s_word;
-    const int clip = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_word[G];
+    __shared__ float* s_logits[G];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int P = (int)cluster.num_blocks();
+    const int clip0 = (blockIdx.x / P) * G, tid = threadIdx.x;
+    const bool writer = cluster.block_rank() == 0;   // every CTA of the cluster computes the same results
     const int V = a.w.vocab;
-    for (int j = tid; j < kMaxLen; j += kThreads) s_anc[0][j] = 0;
-    float* logits_ws = a.logits_ws + (size_t)clip * V;
-    int word = a.start_idx;
-    bool finished = false;
+    for (int i = tid; i < G * kMaxLen; i += kThreads) s_anc[i / kMaxLen][i % kMaxLen] = i / kMaxLen;
+    int word[G]; bool finished[G]; bool valid[G];
+#pragma unroll
+    for (int r = 0; r < G; ++r) { word[r] = a.start_idx; valid[r] = clip0 + r < a.n_clips; finished[r] = !valid[r]; }
     __syncthreads();
     // The reference keeps running finished rows (input forced to <end>) until EVERY row of the batch
     // has finished and records their logits/embeds; when those outputs are requested we do the same
     // for all max_len steps (a superset: past the reference's break its buffers are uninitialised).
     const bool full_outputs = a.logit_out != nullptr || a.embed_out != nullptr;
     for (int t = 0; t < a.max_len; ++t) {
-        if (finished && !full_outputs) {   // rows that emitted <end> keep <end> (base.py:161-168)
-            if (tid == 0) a.seq[(size_t)clip * a.max_len + t] = a.end_idx;
+        bool all_done = true;
+#pragma unroll
+        for (int r = 0; r < G; ++r) all_done = all_done && finished[r];
+        if (all_done && !full_outputs) {   // rows that emitted <end> keep <end> (base.py:161-168)
+            if (tid < G && writer && clip0 + tid < a.n_clips) a.seq[(size_t)(clip0 + tid) * a.max_len + t] = a.end_idx;
             continue;
         }
-        if (tid == 0) { s_pad[t][0] = (word == a.pad_idx); s_word = word; }
-        __syncthreads();
-        float* logits = a.logit_out ? a.logit_out + ((size_t)clip * a.max_len + t) * V : logits_ws;
-        decoder_step<1>(a, clip, t, &s_word, s_anc, s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, logits);
-        if (a.embed_out && tid < D) a.embed_out[((size_t)clip * a.max_len + t) * D + tid] = s_x[tid];
-        // log-softmax + argmax (first maximum wins, as torch.max on CPU)
-        float best = -INFINITY; int bi = 0x7fffffff;
-        for (int n = tid; n < V; n += kThreads) {
-            float v = logits[n];
-            if (v > best) { best = v; bi = n; }
-        }
-        block_argmax(best, bi, s_rv, s_ri);
-        float se = 0.f;
-        for (int n = tid; n < V; n += kThreads) se += expf(logits[n] - best);
-        se = block_sum(se, s_rv);
-        word = finished ? a.end_idx : bi;
         if (tid == 0) {
-            a.seq[(size_t)clip * a.max_len + t] = word;
-            if (a.logprob) a.logprob[(size_t)clip * a.max_len + t] = -logf(se);
+#pragma unroll
+            for (int r = 0; r < G; ++r) {
+                const int clip = min(clip0 + r, a.n_clips - 1);
+                s_pad[t][r] = (word[r] == a.pad_idx); s_word[r] = word[r];
+                s_logits[r] = a.logit_out ? a.logit_out + ((size_t)clip * a.max_len + t) * V
+                                          : a.logits_ws + (size_t)clip * V;
+            }
         }
-        finished = finished || (word == a.end_idx);
+        __syncthreads();
+        decoder_step<G, 1>(a, clip0, t, s_word, s_anc, s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, s_c, s_logits);
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            if (a.embed_out && writer && valid[r] && tid < D)
+                a.embed_out[((size_t)(clip0 + r) * a.max_len + t) * D + tid] = s_x[r * D + tid];
+            // log-softmax + argmax (first maximum wins, as torch.max on CPU)
+            const float* logits = s_logits[r];
+            float best = -INFINITY; int bi = 0x7fffffff;
+            for (int n = tid; n < V; n += kThreads) {
+                float v = logits[n];
+                if (v > best) { best = v; bi = n; }
+            }
+            block_argmax(best, bi, s_rv, s_ri);
+            float se = 0.f;
+            for (int n = tid; n < V; n += kThreads) se += expf(logits[n] - best);
+            se = block_sum(se, s_rv);
+            word[r] = finished[r] ? a.end_idx : bi;
+            if (tid == 0 && writer && valid[r]) {
+                a.seq[(size_t)(clip0 + r) * a.max_len + t] = word[r];
+                if (a.logprob) a.logprob[(size_t)(clip0 + r) * a.max_len + t] = -logf(se);
+            }
+            finished[r] = finished[r] || (word[r] == a.end_idx);
+        }
     }
 }
 
@@ -372,10 +424,12 @@ greedy_kernel(DecodeArgs a) {
 template <int R>
 __global__ void __launch_bounds__(kThreads)
 beam_kernel(DecodeArgs a) {
+    __shared__ float* s_logits[R];
     extern __shared__ __align__(16) float smem[];
     float* s_x = smem; float* s_q = s_x + R * D; float* s_att = s_q + R * D; float* s_h = s_att + R * D;
     float* s_sc = s_h + R * 1024;
     float* s_part = s_sc + R * NH * kMaxKeys;
+    float* s_c = s_part + R * 4096;
     __shared__ int s_anc[2][R][kMaxLen];
     __shared__ unsigned char s_pad[kMaxLen][8];
     __shared__ int s_seq[2][R][kMaxLen];
@@ -388,10 +442,13 @@ beam_kernel(DecodeArgs a) {
     __shared__ int s_best_seq[kMaxLen];
     __shared__ int s_best_len, s_ndone, s_stop;
     __shared__ float s_best_score;
-    const int clip = blockIdx.x, tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int P = (int)cluster.num_blocks();
+    const int clip = blockIdx.x / P, tid = threadIdx.x;
     const int V = a.w.vocab;
     float* lp = a.logits_ws + (size_t)clip * R * V;
-    if (tid < R) { s_words[tid] = a.start_idx; s_score[tid] = 0.f; }
+    if (tid < R) { s_words[tid] = a.start_idx; s_score[tid] = 0.f; s_logits[tid] = lp + (size_t)tid * V; }
     if (tid == 0) { s_ndone = 0; s_stop = 0; s_best_len = 0; s_best_score = -INFINITY; }
     for (int i = tid; i < R * kMaxLen; i += kThreads) { s_anc[0][i / kMaxLen][i % kMaxLen] = i / kMaxLen; }
     __syncthreads();
@@ -400,7 +457,7 @@ beam_kernel(DecodeArgs a) {
         if (tid < R) s_pad[t][tid] = (s_words[tid] == a.pad_idx);
         if (tid < R) s_anc[cur][tid][t] = tid;
         __syncthreads();
-        decoder_step<R>(a, clip, t, s_words, s_anc[cur], s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, lp);
+        decoder_step<R, R>(a, clip, t, s_words, s_anc[cur], s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, s_c, s_logits);
         // lp = log_softmax(log_softmax(logit) / temp) + running score   (base.py:282-290)
         for (int r = 0; r < R; ++r) {
             float* row = lp + (size_t)r * V;
@@ -417,9 +474,12 @@ beam_kernel(DecodeArgs a) {
             for (int n = tid; n < V; n += kThreads) se2 += expf((row[n] - lse1) * inv_t - m2);
             const float lse2 = m2 + logf(block_sum(se2, s_rv));
             const float sc = s_score[r];
-            for (int n = tid; n < V; n += kThreads) row[n] = sc + ((row[n] - lse1) * inv_t - lse2);
+            // in-place rewrite of the shared (global) row: each CTA rewrites its own half exactly once
+            const int n0 = (int)((int64_t)V * rank / P), n1 = (int)((int64_t)V * (rank + 1) / P);
+            cluster.sync();   // every read of the raw logits above is done in both CTAs
+            for (int n = n0 + tid; n < n1; n += kThreads) row[n] = sc + ((row[n] - lse1) * inv_t - lse2);
         }
-        __syncthreads();
+        cluster.sync();
         // top-R of the flattened [rows * V] scores (step 0: row 0 only), R rounds of block arg-max
         const int ncand = (t == 0 ? 1 : R) * V;
         for (int k = 0; k < R; ++k) {
@@ -466,8 +526,9 @@ beam_kernel(DecodeArgs a) {
         cur = nxt;
         if (s_stop) break;
     }
-    for (int j = tid; j < a.max_len; j += kThreads)
-        a.seq[(size_t)clip * a.max_len + j] = j < s_best_len ? s_best_seq[j] : a.end_idx;
+    if (rank == 0)
+        for (int j = tid; j < a.max_len; j += kThreads)
+            a.seq[(size_t)clip * a.max_len + j] = j < s_best_len ? s_best_seq[j] : a.end_idx;
 }
 
 // rows [n, D] in place: LayerNorm(x) * g + b, eps 1e-5; one warp per row
@@ -563,7 +624,7 @@ int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, i
     AC_REQUIRE(t && numels && out, "ac_trm_create: null argument");
     AC_REQUIRE(d_model == D && nhead == NH, "ac_trm_create: only d_model=256 / nhead=4 is built (got %d/%d)", d_model, nhead);
     AC_REQUIRE(nlayers >= 1 && nlayers <= kMaxLayers, "ac_trm_create: nlayers %d not in [1,%d]", nlayers, kMaxLayers);
-    AC_REQUIRE(dim_ff % 4 == 0 && dim_ff <= 1024, "ac_trm_create: dim_feedforward %d must be <=1024 and %%4", dim_ff);
+    AC_REQUIRE(dim_ff % 32 == 0 && dim_ff <= 1024, "ac_trm_create: dim_feedforward %d must be <=1024 and %%32", dim_ff);
     AC_REQUIRE(attn_emb_dim % 4 == 0, "ac_trm_create: attn_emb_dim %d must be a multiple of 4", attn_emb_dim);
     AC_REQUIRE(n_tensors == ac_trm_num_tensors(nlayers), "ac_trm_create: expected %d tensors, got %d",
                ac_trm_num_tensors(nlayers), n_tensors);
@@ -669,6 +730,21 @@ size_t ac_trm_workspace_bytes(const ac_trm_t* d, int rows, int t_mem, int max_le
     return (s.proj + s.kvmem + s.cache + s.logits) * sizeof(float);
 }
 
+// `clusters` thread-block clusters of P CTAs
+static int launch_decode(void (*kernel)(ac::DecodeArgs), int clusters, int P, size_t smem, cudaStream_t st,
+                         const ac::DecodeArgs& a) {
+    using namespace ac;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * P); cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    AC_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
+    return AC_OK;
+}
+
 static int trm_common_checks(const ac_trm_t* dec, int batch, int t_mem, int max_len) {
     using namespace ac;
     AC_REQUIRE(dec, "ac_trm: null decoder");
@@ -695,9 +771,19 @@ int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* att
     a.w = dec->w; a.kv_mem = kvmem; a.n_clips = batch; a.mem_len = attn_emb_len; a.kv_cache = cache; a.logits_ws = lws;
     a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
     a.seq = seq; a.logprob = logprob; a.logit_out = logit; a.embed_out = embed; a.beam = 1; a.temp = 1.0f;
-    size_t sm = dec_smem_floats(1) * sizeof(float);
+    // (CTAs per cluster, clips per cluster); AC_GREEDY="P,G" overrides for experiments
+    int P = kGreedyCluster, G = kGreedyClips;
+    if (const char* e = getenv("AC_GREEDY")) sscanf(e, "%d,%d", &P, &G);
+    AC_REQUIRE((P == 1 || P == 2 || P == 4 || P == 8) && (G == 1 || G == 2 || G == 4), "ac_trm_greedy: bad cluster shape %d,%d", P, G);
+    size_t sm = dec_smem_floats(G) * sizeof(float);
     AC_TIMED("trm_greedy", st);
-    greedy_kernel<<<batch, kThreads, sm, st>>>(a);
+#define AC_GREEDY_CASE(GG)                                                                                       \
+    case GG:                                                                                                     \
+        AC_CUDA(cudaFuncSetAttribute(greedy_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  \
+        rc = launch_decode(greedy_kernel<GG>, cdiv(batch, GG), P, sm, st, a); if (rc) return rc;                 \
+        break;
+    switch (G) { AC_GREEDY_CASE(1) AC_GREEDY_CASE(2) AC_GREEDY_CASE(4) }
+#undef AC_GREEDY_CASE
     AC_LAUNCHED("greedy_kernel");
     return AC_OK;
 }
@@ -726,7 +812,7 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
 #define AC_BEAM_CASE(RR)                                                                                        \
     case RR:                                                                                                    \
         AC_CUDA(cudaFuncSetAttribute(beam_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
-        beam_kernel<RR><<<batch, kThreads, sm, st>>>(a);                                                        \
+        rc = launch_decode(beam_kernel<RR>, batch, kBeamCluster, sm, st, a); if (rc) return rc;                 \
         break;
     switch (beam) {
         AC_BEAM_CASE(1) AC_BEAM_CASE(2) AC_BEAM_CASE(3) AC_BEAM_CASE(4) AC_BEAM_CASE(5)
