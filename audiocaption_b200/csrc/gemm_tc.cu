@@ -11,11 +11,13 @@
 //                swizzle, rows/cols beyond M/K zero-filled by the TMA unit).  The pre-packed weight
 //                (hi and lo images, see TcWeight) is either fetched ONCE per CTA with a single bulk copy
 //                ("resident": one n-tile and <= 64 KB -- every large-M layer) or streamed per stage.
-//   warps 12-19  transform: in place in shared memory, a *= SE gate, hi = tf32(a), lo = a - hi
-//                (the swizzled image is processed linearly -> conflict-free); the gate values of the
-//                next chunk are prefetched while the current one is processed.
-//   warp 1       MMA issuer: tcgen05.mma kind::tf32, M=128, N=BN, K=8 per instruction, 3 per k-step,
-//                accumulators double-buffered in TMEM; tcgen05.commit releases the smem stage.
+//   warps 12-19  transform: thread = one row (TMEM lane) x 16 k: reads the landed chunk from shared memory (the
+//                128B swizzle makes the row-per-lane reads conflict-free), a *= SE gate, hi = tf32(a),
+//                lo = a - hi, and writes both images straight into TENSOR MEMORY (tcgen05.st) -- the A operand
+//                never goes back to shared memory; the gate values of the next chunk are prefetched.
+//   warp 1       MMA issuer: tcgen05.mma kind::tf32 with A from TMEM and W from shared memory, M=128, N=BN,
+//                K=8 per instruction, 3 per k-step (lo*hi, hi*lo, hi*hi); accumulators double-buffered in
+//                TMEM; tcgen05.commit releases the smem stage and the TMEM A slot.
 //   warps 4-11   epilogue (two warps per TMEM lane quarter, alternating 32-column panels): tcgen05.ld,
 //                folded BN scale/bias, swish/relu, residual, then the panel goes through a 128B-swizzled
 //                4 KB shared-memory slab and out with one TMA tensor store (coalesced, clipped at M/N).
@@ -51,8 +53,14 @@ struct TcParams {
     const float* wpacked; float* C; const float* R;
     const float* ascale; const float* cbias;
     int M, N, K, ldc, rows_per_group;
-    int BN, n_tiles, m_tiles, k_chunks, stages, tmem_cols, resident;
+    int BN, n_tiles, m_tiles, k_chunks, stages, tmem_cols, resident, a_slots;
+    long long* dbg;   // optional pipeline trace of CTA 0 (AC_TC_TRACE): [event kind 0..7][256] clock64 stamps
 };
+
+#define AC_TC_STAMP(kind, idx)                                                               \
+    do {                                                                                     \
+        if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(kind) * 256 + (idx)] = clock64(); \
+    } while (0)
 
 template <int ACT>
 __device__ __forceinline__ float4 epi_math(const uint32_t* u, float4 b) {
@@ -76,16 +84,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // 128B swizzle needs 1024-byte aligned tiles
-    // [epilogue slabs][resident W][stages: A hi | A lo | (streamed W hi | lo)][barriers][per-warp bias]
+    // smem: [epilogue slabs][resident W][stages: raw A chunk | (streamed W hi | lo)][barriers][per-warp bias]
+    // TMEM: [accumulator 0 | accumulator 1 (BN columns each)][A ring: a_slots x (hi 32 columns | lo 32 columns)]
     const uint32_t slabs = base;
     const uint32_t w_res = slabs + TC_EPI_WARPS * TC_SLAB_BYTES;
     const uint32_t w_chunk_bytes = (uint32_t)p.BN * 256u;
     const uint32_t stage0 = w_res + (p.resident ? (uint32_t)p.k_chunks * w_chunk_bytes : 0u);
-    const uint32_t stage_bytes = 2 * TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes);
+    const uint32_t stage_bytes = TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes);
     const uint32_t bars = stage0 + p.stages * stage_bytes;
     auto bar_tma = [&](int s) { return bars + 8u * s; };
-    auto bar_xf = [&](int s) { return bars + 64u + 8u * s; };
-    auto bar_empty = [&](int s) { return bars + 128u + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 64u + 8u * s; };
+    auto bar_axf = [&](int a) { return bars + 128u + 8u * a; };       // A slot (TMEM) holds hi / lo
+    auto bar_aempty = [&](int a) { return bars + 160u + 8u * a; };    // A slot consumed by the tensor core
     auto bar_acc_full = [&](int a) { return bars + 192u + 8u * a; };
     auto bar_acc_empty = [&](int a) { return bars + 208u + 8u * a; };
     const uint32_t bar_w = bars + 224u;
@@ -101,8 +111,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         prefetch_tensormap(&mapC);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_tma(s), 1);
-            mbar_init(bar_xf(s), TC_XF_WARPS);
             mbar_init(bar_empty(s), 1);
+        }
+        for (int a = 0; a < p.a_slots; ++a) {
+            mbar_init(bar_axf(a), TC_XF_WARPS);
+            mbar_init(bar_aempty(a), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_acc_full(a), 1);
@@ -127,16 +140,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 bulk_load(w_res, p.wpacked, wb, bar_w);
             }
             int stage = 0; uint32_t phase = 0;
+            int ev = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
                 const float* wsrc = p.wpacked + (size_t)n_t * p.k_chunks * (p.BN * 64);
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(bar_empty(stage), phase ^ 1u);
+                    AC_TC_STAMP(0, ev); ++ev;
                     const uint32_t sa = stage0 + stage * stage_bytes;
                     mbar_expect_tx(bar_tma(stage), TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes));
                     tma_load_2d(sa, &mapA, kc * TC_BK, m_t * TC_BM, bar_tma(stage));
                     if (!p.resident)
-                        bulk_load(sa + 2 * TC_A_TILE_BYTES, wsrc + (size_t)kc * (p.BN * 64), w_chunk_bytes, bar_tma(stage));
+                        bulk_load(sa + TC_A_TILE_BYTES, wsrc + (size_t)kc * (p.BN * 64), w_chunk_bytes, bar_tma(stage));
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -145,8 +160,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(2, TC_BM, p.BN);
+            const uint32_t a_ring = tmem_base + 2u * (uint32_t)p.BN;
             int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            int ev = 0;
             if (p.resident) mbar_wait(bar_w, 0u);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);
@@ -154,86 +172,99 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     if (!p.resident) mbar_wait(bar_tma(stage), phase);   // streamed weight chunk landed
-                    mbar_wait(bar_xf(stage), phase);                     // A chunk split into hi / lo
+                    mbar_wait(bar_axf(as), aphase);                      // A chunk split into hi / lo (TMEM)
                     tc_fence_after();
+                    AC_TC_STAMP(3, ev);
                     const uint32_t sa = stage0 + stage * stage_bytes;
-                    const uint32_t a_hi = sa, a_lo = sa + TC_A_TILE_BYTES;
-                    const uint32_t w_hi = p.resident ? w_res + kc * w_chunk_bytes : sa + 2 * TC_A_TILE_BYTES;
+                    const uint32_t a_hi = a_ring + (uint32_t)as * 64u, a_lo = a_hi + 32u;
+                    const uint32_t w_hi = p.resident ? w_res + kc * w_chunk_bytes : sa + TC_A_TILE_BYTES;
                     const uint32_t w_lo = w_hi + (uint32_t)p.BN * 128u;
                     const int ksteps = min(TC_BK / 8, (p.K - kc * TC_BK) / 8);
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t o = ks * 32u;      // 8 tf32 = 32 bytes along the swizzled row
-                        const uint64_t dah = umma_desc_sw128(a_hi + o), dal = umma_desc_sw128(a_lo + o);
+                        const uint32_t o = ks * 32u;      // 8 tf32 = 32 bytes along the swizzled W row
                         const uint64_t dwh = umma_desc_sw128(w_hi + o), dwl = umma_desc_sw128(w_lo + o);
-                        mma_tf32(d_tmem, dal, dwh, idesc, (kc | ks) != 0 ? 1u : 0u);   // small terms first
-                        mma_tf32(d_tmem, dah, dwl, idesc, 1u);
-                        mma_tf32(d_tmem, dah, dwh, idesc, 1u);
+                        mma_tf32_ts(d_tmem, a_lo + ks * 8u, dwh, idesc, (kc | ks) != 0 ? 1u : 0u);   // small terms first
+                        mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwl, idesc, 1u);
+                        mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh, idesc, 1u);
                     }
                     mma_commit(bar_empty(stage));         // smem stage reusable once these MMAs retire
+                    mma_commit(bar_aempty(as));           // ... and so is the TMEM A slot
+                    AC_TC_STAMP(4, ev); ++ev;
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
                 }
                 mma_commit(bar_acc_full(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else if (warp >= TC_FIRST_XF_WARP) {
-        // ------------------------------------------------------------ transform (gate, hi/lo split)
-        constexpr int NT = TC_XF_WARPS * 32;                          // 256 threads
-        constexpr int PER = (TC_A_TILE_BYTES / 16) / NT;              // float4 per thread per chunk = 4
-        constexpr int ROW_STEP = NT / 8;                              // 32 rows between a thread's float4s
-        const int t = threadIdx.x - TC_FIRST_XF_WARP * 32;
-        const int r0 = t >> 3;                                        // physical row of the first float4
-        const int lc = (t & 7) ^ (r0 & 7);                            // logical 16-byte chunk (undo the swizzle)
-        const float* grow[PER];                                       // gate rows of this thread's 4 rows
-        auto gate_rows = [&](int tile) {
-            const int m_t = tile / p.n_tiles;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int row = min(m_t * TC_BM + r0 + j * ROW_STEP, p.M - 1);
-                grow[j] = p.ascale + (size_t)(row / p.rows_per_group) * p.K + lc * 4;
-            }
+        // ------------------------------------------------------------ transform (gate, hi/lo split -> TMEM)
+        const int wq = warp & 3;                                      // TMEM lane quarter of this warp
+        const int wh = (warp - TC_FIRST_XF_WARP) >> 2;                // which 16 of the chunk's 32 k
+        const int r = wq * 32 + lane;                                 // row of the tile = TMEM lane
+        const uint32_t a_ring = tmem_base + 2u * (uint32_t)p.BN + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wh * 16);
+        const float* grow = nullptr;                                  // gate row of this thread's row
+        auto gate_row = [&](int tile) {
+            const int row = min((tile / p.n_tiles) * TC_BM + r, p.M - 1);
+            grow = p.ascale + (size_t)(row / p.rows_per_group) * p.K + wh * 16;
         };
-        auto load_gate = [&](int kc, float4 (&g)[PER]) {
-            const int k = kc * TC_BK;
+        auto load_gate = [&](int kc, float4 (&g)[4]) {
+            const int k = kc * TC_BK + wh * 16;
 #pragma unroll
-            for (int j = 0; j < PER; ++j)
-                g[j] = k + lc * 4 < p.K ? __ldg(reinterpret_cast<const float4*>(grow[j] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j)
+                g[j] = k + 4 * j < p.K ? __ldg(reinterpret_cast<const float4*>(grow + kc * TC_BK + 4 * j))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         int stage = 0; uint32_t phase = 0;
+        int as = 0; uint32_t aphase = 0;
         int tile = blockIdx.x, kc = 0;
-        float4 g_next[PER];
-        if (GATED && tile < total_tiles) { gate_rows(tile); load_gate(kc, g_next); }
+        int xev = 0;
+        const bool t0 = threadIdx.x == TC_FIRST_XF_WARP * 32;
+        float4 g_next[4];
+        if (GATED && tile < total_tiles) { gate_row(tile); load_gate(kc, g_next); }
         while (tile < total_tiles) {
-            float4 g[PER];
+            float4 g[4];
             if (GATED) {
 #pragma unroll
-                for (int j = 0; j < PER; ++j) g[j] = g_next[j];
+                for (int j = 0; j < 4; ++j) g[j] = g_next[j];
             }
             int kc2 = kc + 1, tile2 = tile;
             if (kc2 == p.k_chunks) { kc2 = 0; tile2 += gridDim.x; }
             if (GATED && tile2 < total_tiles) {                       // next chunk's gates in flight meanwhile
-                if (kc2 == 0) gate_rows(tile2);
+                if (kc2 == 0) gate_row(tile2);
                 load_gate(kc2, g_next);
             }
             mbar_wait(bar_tma(stage), phase);
-            uint8_t* a_gen = smem_raw + (stage0 - raw) + (size_t)stage * stage_bytes;
-            float4* hi = reinterpret_cast<float4*>(a_gen) + t;
-            float4* lo = reinterpret_cast<float4*>(a_gen + TC_A_TILE_BYTES) + t;
-            float4 v[PER];
+            if (t0) AC_TC_STAMP(1, xev);
+            // row r of the 128B-swizzled chunk: logical 16-byte piece c sits at piece c ^ (r & 7)
+            const uint8_t* arow = smem_raw + (stage0 - raw) + (size_t)stage * stage_bytes + r * 128;
+            float4 v[4];
 #pragma unroll
-            for (int j = 0; j < PER; ++j) v[j] = hi[j * NT];
+            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(arow + (((wh * 4 + j) ^ (r & 7)) << 4));
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                float4 x = v[j];
-                if (GATED) { x.x *= g[j].x; x.y *= g[j].y; x.z *= g[j].z; x.w *= g[j].w; }
-                const float4 h = make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
-                hi[j * NT] = h;
-                lo[j * NT] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            for (int j = 0; j < 4; ++j) {
+                float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                if (GATED) { x[0] *= g[j].x; x[1] *= g[j].y; x[2] *= g[j].z; x[3] *= g[j].w; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float h = tf32_rna(x[e]);
+                    hi[4 * j + e] = __float_as_uint(h);
+                    lo[4 * j + e] = __float_as_uint(x[e] - h);
+                }
             }
-            fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core
+            mbar_wait(bar_aempty(as), aphase ^ 1u);        // the tensor core is done with this TMEM A slot
+            tc_fence_after();
+            tmem_st16(a_ring + (uint32_t)as * 64u, hi);
+            tmem_st16(a_ring + (uint32_t)as * 64u + 32u, lo);
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_xf(stage));
+            if (lane == 0) mbar_arrive(bar_axf(as));
+            if (t0) AC_TC_STAMP(2, xev);
+            ++xev;
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
             tile = tile2; kc = kc2;
         }
     } else if (warp >= TC_FIRST_EPI_WARP) {
@@ -249,6 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool tail16 = (p.BN & 31) != 0;
         int acc = 0; uint32_t acc_phase = 0;
         int cur_nt = -1;
+        int eev = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
             const int row0 = m_t * TC_BM + q * 32;
@@ -266,6 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             mbar_wait(bar_acc_full(acc), acc_phase);
             tc_fence_after();
+            if (ew == 0 && lane == 0) AC_TC_STAMP(5, eev);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
             for (int pn = half; pn < full_panels; pn += 2) {
                 const int col0 = n_t * p.BN + pn * 32;
@@ -324,6 +357,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+            if (ew == 0 && lane == 0) AC_TC_STAMP(6, eev);
+            ++eev;
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) bulk_wait_read0();
@@ -424,6 +459,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder_unused() {
     return fn;
 }
 
+static long long* g_tc_trace = nullptr;   // device buffer [8][256], set by ac_gemm_trace
+
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     AC_REQUIRE(g.tw != nullptr && g.tw->packed != nullptr, "gemm_tc: weight not packed");
     const TcWeight& w = *g.tw;
@@ -464,14 +501,15 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = ldc; p.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
     p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = cdiv(g.M, TC_BM); p.k_chunks = w.k_chunks;
     p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
+    p.dbg = g_tc_trace;
     const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_EPI_WARPS * TC_SLAB_BYTES +
                       (p.resident ? w.k_chunks * w.BN * 256 : 0);
-    const int sb = 2 * TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
+    const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
     p.stages = std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / sb);
     AC_REQUIRE(p.stages >= 2, "gemm_tc: tile too large for shared memory (BN=%d)", w.BN);
-    int cols = 32;
-    while (cols < 2 * w.BN) cols *= 2;
-    p.tmem_cols = cols;
+    p.tmem_cols = 512;                                         // one CTA per SM owns the whole tensor memory
+    p.a_slots = std::min(4, (512 - 2 * w.BN) / 64);
+    AC_REQUIRE(p.a_slots >= 2, "gemm_tc: BN=%d leaves no tensor memory for the A operand", w.BN);
     const size_t smem = (size_t)p.stages * sb + fixed;
 
     const int grid = std::min(p.m_tiles * p.n_tiles, kNumSMs);
@@ -520,4 +558,22 @@ extern "C" int ac_gemm(const float* A, const float* W, float* C, int M, int N, i
     cudaFree(packed);
     if (rc == AC_OK && e != cudaSuccess) rc = check_cuda(e, "ac_gemm");
     return rc;
+}
+
+// Diagnostic: enable (on != 0) / read back the pipeline trace of CTA 0 of the most recent gemm_tc launch.
+// out_host receives 8 x 256 clock64 stamps: 0 TMA issue, 1 chunk landed (transform), 2 transform done,
+// 3 MMA start, 4 MMA issued, 5 accumulator full (epilogue), 6 epilogue done.
+extern "C" int ac_gemm_trace(int on, long long* out_host) {
+    using namespace ac;
+    if (on && g_tc_trace == nullptr) {
+        AC_CUDA(cudaMalloc(&g_tc_trace, 8 * 256 * sizeof(long long)));
+        AC_CUDA(cudaMemset(g_tc_trace, 0, 8 * 256 * sizeof(long long)));
+    }
+    if (out_host != nullptr && g_tc_trace != nullptr) {
+        AC_CUDA(cudaDeviceSynchronize());
+        AC_CUDA(cudaMemcpy(out_host, g_tc_trace, 8 * 256 * sizeof(long long), cudaMemcpyDeviceToHost));
+        AC_CUDA(cudaMemset(g_tc_trace, 0, 8 * 256 * sizeof(long long)));
+    }
+    if (!on && g_tc_trace != nullptr) { cudaFree(g_tc_trace); g_tc_trace = nullptr; }
+    return AC_OK;
 }

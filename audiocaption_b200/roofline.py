@@ -92,3 +92,16 @@ def kernel_families(report, n_steps, batch):
             fam[name] = {"name": name, "bound": "latency", "unit": "GB/s", "peak": hbm, "achieved": 0.0,
                          "ms_per_step": ms, "launches_per_step": sum(v[0] for v in sel.values()) / n_steps}
     return fam
+
+
+def measured_traffic(family):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the family's launches in one step, from the committed ncu
+    capture (profiles/r1_dram_traffic.json, produced by scripts/gpu_profile.sh); None when absent."""
+    p = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    try:
+        d = json.load(open(p))
+        f = d["families"][family]
+        return {"bytes_per_step": f["dram_bytes"], "launches_per_step": f["launches"],
+                "bytes_per_launch": f["dram_bytes"] / max(f["launches"], 1), "source": d.get("source", p)}
+    except Exception:
+        return None

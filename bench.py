@@ -160,6 +160,8 @@ def run_native(args):
     def step_e2e(i):
         return model(host[i % n_rot], lens, sample_method="greedy", max_length=MAX_LEN)
 
+    from audiocaption_b200 import sharding
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -178,10 +180,7 @@ def run_native(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.ac_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+        ms = sharding.max_over_ranks(ms, device=dev)      # multi-GPU: the slowest rank, never wall clock
         return ms / steps, launches
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -208,9 +207,10 @@ def run_native(args):
         # once (fp32) -- computed from the block plan in audiocaption_b200.roofline
         from audiocaption_b200 import roofline as rl
         fam = rl.kernel_families(rep, n_prof, BATCH)
-        top = max(fam.values(), key=lambda f: f["ms_per_step"])
+        hbm_fams = [f for f in fam.values() if f["bound"] == "hbm"]
+        top = max(hbm_fams, key=lambda f: f["ms_per_step"])      # dominant roofline-bounded kernel family
         roof = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
-                "frac": top["achieved"] / top["peak"], "traffic": None, "kernel": top["name"],
+                "frac": top["achieved"] / top["peak"], "traffic": rl.measured_traffic(top["name"]), "kernel": top["name"],
                 "launches_per_step": top["launches_per_step"], "ms_per_step": top["ms_per_step"],
                 "share_of_step": top["ms_per_step"] / (tot / n_prof), "peak_source": which,
                 "kernel_shares": shares, "families": fam}

@@ -78,6 +78,11 @@ int ac_gemm(const float* A_dev, const float* W_dev, float* C_dev, int M, int N, 
             const float* ascale_dev, int rows_per_group, const float* cscale_dev, const float* cbias_dev,
             const float* R_dev, int act, int path, void* stream);
 
+/* Diagnostic: pipeline trace of CTA 0 of the tensor-core GEMM (clock64 stamps, 8 event kinds x 256 events:
+ * 0 TMA issue, 1 chunk landed, 2 transform done, 3 MMA start, 4 MMA issued, 5 accumulator full, 6 epilogue done).
+ * on != 0 enables tracing for subsequent launches; out_host (nullable, 2048 int64) receives and clears the trace. */
+int ac_gemm_trace(int on, long long* out_host);
+
 /* ------------------------------------------------------------------ EfficientNet-B2 encoder
  * Replaces hf_wrapper.py:218-241 `_EffiNet.forward` (efficientnet_pytorch 0.7.1
  * `extract_features` + mean over frequency), eval mode.

@@ -110,3 +110,21 @@ if mode == "one":
     for _ in range(3):
         run(M=M, N=N, K=K, gate=gate, act=act, resid=bool(resid), path=1, check=False)
     print("one done")
+if mode == "trace":
+    import numpy as np
+    M, N, K, gate, act, resid = [int(x) for x in sys.argv[2:8]]
+    for _ in range(2):
+        run(M=M, N=N, K=K, gate=gate, act=act, resid=bool(resid), path=1, check=False)
+    lib.ac_gemm_trace(1, None)
+    run(M=M, N=N, K=K, gate=gate, act=act, resid=bool(resid), path=1, check=False)
+    buf = np.zeros((8, 256), dtype=np.int64)
+    lib.ac_gemm_trace(0, buf.ctypes.data)
+    t0 = buf[buf > 0].min()
+    names = ["tma_issue", "landed", "xf_done", "mma_start", "mma_issued", "acc_full", "epi_done"]
+    n = int((buf[0] > 0).sum())
+    print(f"trace M={M} N={N} K={K}: {n} chunks, cycles relative to first event")
+    for i in range(min(n, 40)):
+        print(i, " ".join(f"{names[k]}={int(buf[k][i]-t0) if buf[k][i] else -1:7d}" for k in range(5)))
+    ne = int((buf[5] > 0).sum())
+    for i in range(min(ne, 12)):
+        print("tile", i, f"acc_full={int(buf[5][i]-t0)} epi_done={int(buf[6][i]-t0)}")

@@ -1,0 +1,73 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: clip sharding, token gather, the batch-global dB maximum
+and the max-over-ranks timing rule.  The data path itself has no collective (clips are independent)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from audiocaption_b200 import sharding
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 64, 129):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, n_clips, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        wav = torch.randn(n_clips, 100, generator=g)
+        lens = torch.arange(n_clips) + 50
+        w, l = sharding.shard_clips(wav, lens, rank, world)
+        a, b = sharding.shard_range(n_clips, rank, world)
+        assert w.shape[0] == b - a and (l == lens[a:b]).all()
+        # "decode": token ids that encode the global clip index, so the gather order can be checked
+        seq = (torch.arange(a, b)[:, None] * 100 + torch.arange(20)[None, :]).to(torch.int64)
+        full = sharding.gather_tokens(seq, n_clips)
+        if rank == 0:
+            want = torch.arange(n_clips)[:, None] * 100 + torch.arange(20)[None, :]
+            assert full.shape == (n_clips, 20) and (full == want).all()
+        else:
+            assert full is None
+        # batch-global dB maximum == maximum over the unsharded batch
+        gmax = w.max().reshape(1).clone() if w.numel() else torch.full((1,), float("-inf"))
+        sharding.global_db_max(gmax)
+        assert gmax.item() == wav.max().item()
+        # timing rule: every rank reports the slowest rank's time
+        assert sharding.max_over_ranks(1.0 + rank) == float(world)
+        q.put((rank, "ok"))
+    except Exception as e:   # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_clips", [7, 64])
+def test_two_rank_gloo(n_clips):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_clips, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
