@@ -57,6 +57,9 @@ class CaptionModel(nn.Module, CaptionMetaMixin):
                 forward_dict["beam_size"] = input_dict.get("beam_size", 3)
                 if input_dict.get("n_best", False):
                     raise NotImplementedError("n_best beam output is not built")
+            for key in ("need_logit", "_device_seq"):      # B200-side options (not in the reference)
+                if key in input_dict:
+                    forward_dict[key] = input_dict[key]
             forward_dict.update(encoder_output_dict)
             output = self.inference_forward(forward_dict)
         else:

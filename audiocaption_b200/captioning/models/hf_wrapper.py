@@ -50,6 +50,21 @@ class Effb2TrmConfig:
         self.vocab_size = vocab_size
 
 
+class PendingCaptions:
+    """Handle returned by `Effb2TrmCaptioningModel.submit`: the token ids land in pinned host memory when the
+    recorded event completes."""
+
+    def __init__(self, seq_host: torch.Tensor, done: "torch.cuda.Event"):
+        self._seq, self._done = seq_host, done
+
+    def done(self) -> bool:
+        return self._done.query()
+
+    def result(self) -> torch.Tensor:
+        self._done.synchronize()
+        return self._seq
+
+
 class Effb2TrmCaptioningModel(nn.Module):
     config_class = Effb2TrmConfig
 
@@ -85,3 +100,34 @@ class Effb2TrmCaptioningModel(nn.Module):
         if sample_method == "beam":
             input_dict["beam_size"] = beam_size
         return self.model(input_dict)["seq"].cpu()
+
+    def submit(self, audio: torch.Tensor, audio_length, sample_method: str = "beam", beam_size: int = 3,
+               max_length: int = 20, temp: float = 1.0) -> PendingCaptions:
+        """Asynchronous `forward` for back-to-back batches (serving): the host->device copy of `audio` runs on a
+        private copy stream, the kernels on the current stream, the token ids come back into pinned memory, and
+        nothing blocks the host -- so batch i+1's upload overlaps batch i's kernels.  `result()` of the returned
+        handle gives the same LongTensor[B, max_length] (CPU) as `forward`.  `audio` should be pinned."""
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        if audio.is_cuda:
+            wav = audio
+        else:
+            # (the buffer is allocated in the copy stream's pool and handed to the compute stream with
+            #  record_stream, so the caching allocator keeps reuse of earlier batches ordered)
+            with torch.cuda.stream(self._copy_stream):
+                wav = audio.to(dev, non_blocking=True)
+            cur.wait_stream(self._copy_stream)
+            wav.record_stream(cur)
+        input_dict = {"wav": wav, "wav_len": audio_length, "specaug": False, "mode": "inference",
+                      "sample_method": sample_method, "max_length": max_length, "temp": temp,
+                      "need_logit": False, "_device_seq": True}
+        if sample_method == "beam":
+            input_dict["beam_size"] = beam_size
+        seq_dev = self.model(input_dict)["seq"]
+        seq_host = torch.empty(seq_dev.shape, dtype=seq_dev.dtype, pin_memory=True)
+        seq_host.copy_(seq_dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        return PendingCaptions(seq_host, done)

@@ -18,13 +18,15 @@ class TransformerModel(CaptionModel):
         out = self.decoder.greedy(input_dict["attn_emb"], input_dict["attn_emb_len"], input_dict["max_length"],
                                   self.start_idx, self.end_idx, self.pad_idx,
                                   need_logit=input_dict.get("need_logit", True))
-        out["seq"] = out["seq"].cpu()
-        out["sampled_logprob"] = out["sampled_logprob"].cpu()
+        if not input_dict.get("_device_seq", False):      # internal: the async submit() path copies later
+            out["seq"] = out["seq"].cpu()
+            out["sampled_logprob"] = out["sampled_logprob"].cpu()
         return out
 
     def beam_search(self, input_dict):
         out = self.decoder.beam_search(input_dict["attn_emb"], input_dict["attn_emb_len"], input_dict["max_length"],
                                        input_dict["beam_size"], input_dict["temp"],
                                        self.start_idx, self.end_idx, self.pad_idx)
-        out["seq"] = out["seq"].cpu()
+        if not input_dict.get("_device_seq", False):
+            out["seq"] = out["seq"].cpu()
         return out

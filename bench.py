@@ -160,6 +160,18 @@ def run_native(args):
     def step_e2e(i):
         return model(host[i % n_rot], lens, sample_method="greedy", max_length=MAX_LEN)
 
+    def run_e2e_pipelined(steps, first):
+        """`steps` batches through the public serving call `submit()`: every batch's pinned-host -> device upload,
+        its kernels and the read-back of its token ids are inside the timed region; the upload of batch i+1
+        overlaps the kernels of batch i (copy stream), the host never blocks except on the results."""
+        pending, seq = None, None
+        for i in range(steps):
+            nxt = model.submit(host[(first + i) % n_rot], lens, sample_method="greedy", max_length=MAX_LEN)
+            if pending is not None:
+                seq = pending.result()
+            pending = nxt
+        return pending.result()
+
     from audiocaption_b200 import sharding
 
     def barrier():
@@ -188,7 +200,18 @@ def run_native(args):
         sampler.start()
     ms_step, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.summary() if sampler else None
-    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    ms_e2e_sync, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    # pipelined end-to-end: same public API family (submit / result), uploads overlapped with the previous batch
+    run_e2e_pipelined(max(3, args.warmup // 2), 0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    run_e2e_pipelined(args.steps, 3)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    ms_e2e = sharding.max_over_ranks(max(e0.elapsed_time(e1), wall_ms), device=dev) / args.steps
 
     # ---- roofline leg: the same steps with every launch bracketed by CUDA events
     roof = None
@@ -227,7 +250,11 @@ def run_native(args):
                        "l2": f"rotating {n_rot} input batches (328 MB > 126 MB L2)", "parallelism": f"clips sharded x{world}"},
             "clocks": clocks,
             "e2e": {"value": total / (ms_e2e / 1000.0), "unit": "clips/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": BATCH * N_SAMPLES * 4, "d2h_bytes_per_step": BATCH * MAX_LEN * 8},
+                    "h2d_bytes_per_step": BATCH * N_SAMPLES * 4, "d2h_bytes_per_step": BATCH * MAX_LEN * 8,
+                    "api": "Effb2TrmCaptioningModel.submit()/result(): pinned host input, upload of batch i+1 overlaps "
+                           "the kernels of batch i; timed as max(CUDA events, host wall clock) over all batches",
+                    "synchronous_forward_ms_per_step": ms_e2e_sync,
+                    "synchronous_forward_value": total / (ms_e2e_sync / 1000.0)},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",

@@ -228,6 +228,20 @@ def test_model_end_to_end(mirror, oracle_effb2, golden_effb2, golden_wav):
     assert (beam.numpy()[st3] == g["beam3_seq"][st3]).all()
 
 
+def test_submit_matches_forward(mirror, golden_wav):
+    """The asynchronous serving call returns exactly what the synchronous forward returns, also when several
+    batches are in flight."""
+    wav, lens = golden_wav
+    want = mirror(wav, lens, sample_method="greedy")
+    pin = wav.pin_memory()
+    pend = [mirror.submit(pin, lens, sample_method="greedy") for _ in range(3)]
+    for p in pend:
+        got = p.result()
+        assert got.device.type == "cpu" and (got == want).all()
+    assert (mirror.submit(pin, lens, sample_method="beam", beam_size=3).result() ==
+            mirror(wav, lens, sample_method="beam", beam_size=3)).all()
+
+
 def test_empty_batch_and_errors(mirror):
     from audiocaption_b200 import AudioCaptionB200Error
     enc = mirror.model.model.encoder
