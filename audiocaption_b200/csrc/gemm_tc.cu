@@ -158,44 +158,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(2, TC_BM, p.BN);
-            const uint32_t a_ring = tmem_base + 2u * (uint32_t)p.BN;
-            int stage = 0; uint32_t phase = 0;
-            int as = 0; uint32_t aphase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            int ev = 0;
-            if (p.resident) mbar_wait(bar_w, 0u);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);
+        // The whole warp runs this loop converged (all operands are warp-uniform, so descriptors live in uniform
+        // registers and nothing is recomputed per lane); one elected lane issues the tcgen05 instructions.  The MMA
+        // thread's own instruction stream is the limiter for small N, so the per-instruction work is kept minimal:
+        // descriptors are formed once per stage and advanced by adding to their low word.
+        const uint32_t idesc = umma_idesc(2, TC_BM, p.BN);
+        const uint32_t a_ring = tmem_base + 2u * (uint32_t)p.BN;
+        const uint64_t desc_hi_bits = umma_desc_sw128(0) & 0xffffffff00000000ull;   // SBO / version / swizzle fields
+        const bool leader = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        int as = 0; uint32_t aphase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        int ev = 0;
+        if (p.resident) mbar_wait(bar_w, 0u);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                if (!p.resident) mbar_wait(bar_tma(stage), phase);   // streamed weight chunk landed
+                mbar_wait(bar_axf(as), aphase);                      // A chunk split into hi / lo (TMEM)
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int kc = 0; kc < p.k_chunks; ++kc) {
-                    if (!p.resident) mbar_wait(bar_tma(stage), phase);   // streamed weight chunk landed
-                    mbar_wait(bar_axf(as), aphase);                      // A chunk split into hi / lo (TMEM)
-                    tc_fence_after();
-                    AC_TC_STAMP(3, ev);
-                    const uint32_t sa = stage0 + stage * stage_bytes;
-                    const uint32_t a_hi = a_ring + (uint32_t)as * 64u, a_lo = a_hi + 32u;
-                    const uint32_t w_hi = p.resident ? w_res + kc * w_chunk_bytes : sa + TC_A_TILE_BYTES;
-                    const uint32_t w_lo = w_hi + (uint32_t)p.BN * 128u;
-                    const int ksteps = min(TC_BK / 8, (p.K - kc * TC_BK) / 8);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t o = ks * 32u;      // 8 tf32 = 32 bytes along the swizzled W row
-                        const uint64_t dwh = umma_desc_sw128(w_hi + o), dwl = umma_desc_sw128(w_lo + o);
-                        mma_tf32_ts(d_tmem, a_lo + ks * 8u, dwh, idesc, (kc | ks) != 0 ? 1u : 0u);   // small terms first
-                        mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwl, idesc, 1u);
-                        mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh, idesc, 1u);
+                if (lane == 0) AC_TC_STAMP(3, ev);
+                const uint32_t sa = stage0 + stage * stage_bytes;
+                const uint32_t a_hi = a_ring + (uint32_t)as * 64u, a_lo = a_hi + 32u;
+                const uint32_t w_hi = p.resident ? w_res + kc * w_chunk_bytes : sa + TC_A_TILE_BYTES;
+                const uint32_t w_lo = w_hi + (uint32_t)p.BN * 128u;
+                const uint64_t dwh0 = desc_hi_bits | (uint64_t)((w_hi & 0x3ffffu) >> 4);
+                const uint64_t dwl0 = desc_hi_bits | (uint64_t)((w_lo & 0x3ffffu) >> 4);
+                const int ksteps = min(TC_BK / 8, (p.K - kc * TC_BK) / 8);
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        if (ks < ksteps) {
+                            // 8 tf32 = 32 bytes along the swizzled W row = +2 in the descriptor's address field
+                            mma_tf32_ts(d_tmem, a_lo + ks * 8u, dwh0 + 2u * ks, idesc, (kc | ks) != 0 ? 1u : 0u);   // small terms first
+                            mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwl0 + 2u * ks, idesc, 1u);
+                            mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh0 + 2u * ks, idesc, 1u);
+                        }
                     }
                     mma_commit(bar_empty(stage));         // smem stage reusable once these MMAs retire
                     mma_commit(bar_aempty(as));           // ... and so is the TMEM A slot
-                    AC_TC_STAMP(4, ev); ++ev;
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                    if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+                    if (kc + 1 == p.k_chunks) mma_commit(bar_acc_full(acc));
                 }
-                mma_commit(bar_acc_full(acc));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                __syncwarp();
+                if (lane == 0) { AC_TC_STAMP(4, ev); }
+                ++ev;
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= TC_FIRST_XF_WARP) {
         // ------------------------------------------------------------ transform (gate, hi/lo split -> TMEM)
