@@ -58,6 +58,13 @@ struct LaunchTimer {
         }                                                           \
     } while (0)
 
+inline cudaLaunchAttribute pdl_attr() {
+    cudaLaunchAttribute a;
+    a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    a.val.programmaticStreamSerializationAllowed = 1;
+    return a;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -65,6 +72,13 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 constexpr int kNumSMs = 148;  // B200
 
 #ifdef __CUDACC__
+// Programmatic dependent launch: a kernel launched with pdl_attr() may start while its predecessor in the stream
+// is still running; everything before pdl_wait() (barrier init, TMEM allocation, weight prefetch, index math)
+// overlaps the predecessor's tail, everything after it sees the predecessor's memory.  pdl_trigger() lets the
+// NEXT kernel start early in turn.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -77,6 +77,8 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_trigger();
+    pdl_wait();        // the input activation is the previous kernel's output
 
     if (warp == DW_COMPUTE_THREADS / 32) {
         // ------------------------------------------------------------ producer
@@ -256,7 +258,11 @@ int dwconv_tma(const DwArgs& a, cudaStream_t st) {
         static cudaError_t attr_rc = cudaFuncSetAttribute(dwconv_tma_kernel<K, S, CC>,                           \
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT); \
         AC_CUDA(attr_rc);                                                                                        \
-        dwconv_tma_kernel<K, S, CC><<<grid, DW_THREADS, smem, st>>>(map, p);                                     \
+        cudaLaunchConfig_t cfg = {};                                                                             \
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
+        cudaLaunchAttribute at[1] = {pdl_attr()};                                                                \
+        cfg.attrs = at; cfg.numAttrs = 1;                                                                        \
+        AC_CUDA(cudaLaunchKernelEx(&cfg, dwconv_tma_kernel<K, S, CC>, map, p));                                  \
     } while (0)
 #define AC_DW_KS(CC)                                         \
     do {                                                     \

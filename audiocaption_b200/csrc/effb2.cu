@@ -268,6 +268,8 @@ se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const flo
     const int q0 = (int)((int64_t)c4n * rank / P), q1 = (int)((int64_t)c4n * (rank + 1) / P);   // my channel quads
     const int j0 = (int)((int64_t)nsq * rank / P), j1 = (int)((int64_t)nsq * (rank + 1) / P);   // my squeezed units
     const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)b * strips * C);
+    pdl_trigger();
+    pdl_wait();        // `partial` is the depthwise kernel's output
     // 1. channel means of my quads: thread = (strip group g, quad), fixed-order two-level sum (deterministic)
     for (int cbase = q0; cbase < q1; cbase += kSeThreads) {
         const int width = min(q1 - cbase, kSeThreads);
@@ -384,10 +386,11 @@ static int launch_se(const float* partial, int strips, float inv_hw, const Block
     cfg.gridDim = dim3(B * P); cfg.blockDim = dim3(kSeThreads);
     cfg.dynamicSmemBytes = (((C + nsq + 3) / 4) * 4 + kSeThreads * 4) * sizeof(float);
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1] = pdl_attr();
+    cfg.attrs = attr; cfg.numAttrs = 2;
     AC_TIMED("se", st);
     AC_CUDA(cudaLaunchKernelEx(&cfg, se_kernel, partial, strips, inv_hw, (const float*)w.se_wr, (const float*)w.se_br,
                                (const float*)w.se_we, (const float*)w.se_be, gate, C, nsq));

@@ -130,15 +130,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                                   // the next kernel may start its own prologue
+    if (warp == 0 && lane == 0 && p.resident) {      // weights are constants: fetch them before the dependency wait
+        const uint32_t wb = (uint32_t)p.k_chunks * w_chunk_bytes;
+        mbar_expect_tx(bar_w, wb);
+        bulk_load(w_res, p.wpacked, wb, bar_w);
+    }
+    pdl_wait();                                      // A, the SE gate, the residual: produced by earlier kernels
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            if (p.resident) {
-                const uint32_t wb = (uint32_t)p.k_chunks * w_chunk_bytes;
-                mbar_expect_tx(bar_w, wb);
-                bulk_load(w_res, p.wpacked, wb, bar_w);
-            }
             int stage = 0; uint32_t phase = 0;
             int ev = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -532,7 +534,11 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
         static cudaError_t attr_rc = cudaFuncSetAttribute(gemm_tc_kernel<ACT, GATED, RESID>,                        \
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT); \
         AC_CUDA(attr_rc);                                                                                          \
-        gemm_tc_kernel<ACT, GATED, RESID><<<grid, TC_THREADS, smem, st>>>(map, mapC, p);                           \
+        cudaLaunchConfig_t cfg = {};                                                                               \
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;   \
+        cudaLaunchAttribute at[1] = {pdl_attr()};                                                                  \
+        cfg.attrs = at; cfg.numAttrs = 1;                                                                          \
+        AC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<ACT, GATED, RESID>, map, mapC, p));                        \
     } while (0)
 #define AC_TC_ACT(ACT)                                                   \
     do {                                                                 \
