@@ -56,7 +56,7 @@ __device__ __forceinline__ void dw_tile_coords(const DwParams& p, int tile, int&
 }
 
 template <int K, int S, int CC>
-__global__ void __launch_bounds__(DW_THREADS, 1)
+__global__ void __launch_bounds__(DW_THREADS, K == 3 ? 2 : 1)     // 3x3: 2 CTAs per SM (16 compute warps)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     using namespace ptx;
     extern __shared__ uint8_t smem_raw[];
@@ -196,10 +196,10 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     }
 }
 
-static int dw_chunk(int C) { return C >= 256 ? 64 : (C >= 32 ? 32 : 16); }
+static int dw_chunk(int C, int k) { (void)k; return C >= 256 ? 64 : (C >= 32 ? 32 : 16); }
 
 static void dw_tile_shape(int Ho, int Wo, int C, int k, int s, int& CC, int& groups, int& Ht, int& Ws, int& nsub, int& n_t) {
-    CC = dw_chunk(C);
+    CC = dw_chunk(C, k);
     groups = DW_COMPUTE_THREADS / (CC / 2);
     Ht = Ho >= 8 ? 8 : (Ho >= 4 ? 4 : (Ho >= 2 ? 2 : 1));
     nsub = groups / Ht;
@@ -209,7 +209,8 @@ static void dw_tile_shape(int Ho, int Wo, int C, int k, int s, int& CC, int& gro
     if (s == 2 && n_t > 8) n_t = 8;       // keep the stride-2 input box comparable
     Ws = nsub * n_t;
     // at least two tiles (input box with halo) must fit in shared memory
-    while (n_t > 1 && (size_t)((Ht - 1) * s + k) * ((Ws - 1) * s + k) * CC * 4 * 2 > (size_t)DW_SMEM_LIMIT - 512) {
+    const size_t cap = k == 3 ? 110 * 1024 : DW_SMEM_LIMIT;      // 3x3 kernels run 2 CTAs per SM
+    while (n_t > 1 && (size_t)((Ht - 1) * s + k) * ((Ws - 1) * s + k) * CC * 4 * 2 > cap - 512) {
         n_t /= 2;
         Ws = nsub * n_t;
     }
@@ -237,7 +238,9 @@ int dwconv_tma(const DwArgs& a, cudaStream_t st) {
     AC_REQUIRE(p.Wbox <= 256 && p.Hbox <= 256, "dwconv_tma: tile too large");
     p.tile_bytes = (int)align_up((size_t)p.Hbox * p.Wbox * p.CC * 4, 128);
     const int fixed = 128 + 128;
-    p.stages = std::min(DW_MAX_STAGES, (DW_SMEM_LIMIT - fixed) / p.tile_bytes);
+    const int ctas_per_sm = a.k == 3 ? 2 : 1;     // the 5x5 kernels need > 113 registers (measured slower when capped)
+    const int smem_cap = a.k == 3 ? 110 * 1024 : DW_SMEM_LIMIT;
+    p.stages = std::min(DW_MAX_STAGES, (smem_cap - fixed) / p.tile_bytes);
     AC_REQUIRE(p.stages >= 2, "dwconv_tma: tile of %d bytes does not fit twice in shared memory", p.tile_bytes);
     const size_t smem = (size_t)p.stages * p.tile_bytes + fixed;
 
@@ -251,7 +254,7 @@ int dwconv_tma(const DwArgs& a, cudaStream_t st) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AC_REQUIRE(cr == CUDA_SUCCESS, "dwconv_tma: cuTensorMapEncodeTiled failed (%d) C=%d Wi=%d Hi=%d B=%d box %dx%d", (int)cr,
                a.C, a.Wi, a.Hi, a.B, p.Wbox, p.Hbox);
-    const int grid = std::min(p.total_tiles, kNumSMs);
+    const int grid = std::min(p.total_tiles, kNumSMs * ctas_per_sm);
     AC_TIMED(a.k == 3 ? "dwconv_k3" : "dwconv_k5", st);
 #define AC_DW_TMA(K, S, CC)                                                                                      \
     do {                                                                                                         \
