@@ -42,6 +42,7 @@ _SIGS = {
     "ac_trm_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ac_trm_greedy": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 c_i64p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_trm_trace": (C.c_int, [C.c_int, C.c_void_p]),
     "ac_trm_beam": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_int, C.c_int, C.c_int, c_i64p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

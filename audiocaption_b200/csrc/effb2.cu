@@ -126,8 +126,8 @@ stem_kernel(const float* __restrict__ lms, const float* __restrict__ gmax, float
     }
     float4 s = __ldg(reinterpret_cast<const float4*>(scale) + c4);
     float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-    float4 o = make_float4(swishf(fmaf(acc.x, s.x, bb.x)), swishf(fmaf(acc.y, s.y, bb.y)),
-                           swishf(fmaf(acc.z, s.z, bb.z)), swishf(fmaf(acc.w, s.w, bb.w)));
+    float4 o = make_float4(fast_swish(fmaf(acc.x, s.x, bb.x)), fast_swish(fmaf(acc.y, s.y, bb.y)),
+                           fast_swish(fmaf(acc.z, s.z, bb.z)), fast_swish(fmaf(acc.w, s.w, bb.w)));
     reinterpret_cast<float4*>(out)[idx] = o;
 }
 

@@ -158,6 +158,60 @@ __device__ __forceinline__ void softmax_rows(float* sc, int n) {
     }
 }
 
+// One warp = one (row, head): scores over `nk` keys (lane j owns key j, j + 32, ...: a 64-long dot product against
+// the query broadcast from shared memory), soft-max through warp shuffles, then the probability-weighted sum of the
+// value rows with lanes across the 64 head dimensions.  No shared-memory score buffer, no block barrier.
+// kptr(j) / vptr(j) give key j's K / V head slice (64 floats, 16-byte aligned); masked(j) keys get -inf.
+constexpr int kStageStride = 2 * D + 4;   // padded frame stride of the staged cross K|V: conflict-free LDS.128 per key
+template <class KP, class VP, class MK>
+__device__ __forceinline__ void attend_head(const float* q, float scale, int nk, KP kptr, VP vptr, MK masked, float* out) {
+    const int lane = threadIdx.x & 31;
+    constexpr int NC = kMaxKeys / 32;
+    float sc[NC];
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int j = lane + 32 * i;
+        float sv = -INFINITY;
+        if (i * 32 < nk && j < nk && !masked(j)) {
+            const float4* k4 = reinterpret_cast<const float4*>(kptr(j));
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD / 4; ++d) {
+                const float4 kv = k4[d], qv = q4[d];
+                acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc);
+                acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+            }
+            sv = acc * scale;
+        }
+        sc[i] = sv;
+    }
+    float m = sc[0];
+#pragma unroll
+    for (int i = 1; i < NC; ++i) m = fmaxf(m, sc[i]);
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { sc[i] = (i * 32 < nk) ? expf(sc[i] - m) : 0.f; sum += sc[i]; }
+    const float inv = 1.0f / warp_sum(sum);
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        if (i * 32 < nk) {
+            const float pi = sc[i] * inv;
+            const int n = min(32, nk - i * 32);
+            for (int jj = 0; jj < n; ++jj) {
+                const float pj = __shfl_sync(0xffffffffu, pi, jj);
+                const float* v = vptr(i * 32 + jj);
+                o0 = fmaf(pj, v[lane], o0);
+                o1 = fmaf(pj, v[lane + 32], o1);
+            }
+        }
+    }
+    out[lane] = o0;
+    out[lane + 32] = o1;
+}
+
 struct DecodeArgs {
     DecW w;
     const float* kv_mem;        // [nlayers][clips][t_mem][2D]  (K | V per frame)
@@ -173,7 +227,14 @@ struct DecodeArgs {
     float* embed_out;           // nullable [clips][max_len][D]
     // beam
     int beam; float temp;
+    long long* dbg;             // optional phase trace of CTA 0 (ac_trm_trace): clock64 stamps
+    int kv_in_smem;             // the launch reserved shared memory for the cross-attention K/V
 };
+
+#define AC_DEC_STAMP(id)                                                                                         \
+    do {                                                                                                         \
+        if (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && t == 5 && (id) < 64) a.dbg[id] = clock64(); \
+    } while (0)
 
 // One decoder step for the R rows of this cluster: token ids `words[r]` at position t.  Rows are grouped RPC
 // per clip: row r belongs to clip `clip + r / RPC` (greedy: RPC = 1, every row is its own clip; beam: RPC = R).
@@ -182,7 +243,7 @@ struct DecodeArgs {
 template <int R, int RPC>
 __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* words, const int (*anc)[kMaxLen],
                              const unsigned char (*padflag)[8], float* s_x, float* s_q, float* s_att, float* s_h,
-                             float* s_sc, float* s_part, float* s_c, float* const* logits) {
+                             float* s_sc, float* s_part, float* s_c, float* const* logits, const float* s_kv = nullptr) {
     // Buffers written through distributed shared memory by the peer CTA (GEMV outputs): s_h, s_q, s_c.  Each is
     // only ever the output of a GEMV whose surrounding cluster.sync() interval does not touch it otherwise.
     const DecW& W = a.w;
@@ -191,6 +252,7 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto clip_of = [&](int r) { return min(clip + r / RPC, a.n_clips - 1); };   // rows past the batch replay the last clip
     auto n_mem_of = [&](int r) { return min((int)min((int64_t)a.t_mem, a.mem_len[clip_of(r)]), a.t_mem); };
+    AC_DEC_STAMP(0);
     // embedding * sqrt(d) + positional encoding
     for (int i = tid; i < R * D; i += kThreads) {
         const int r = i / D, f = i - r * D;
@@ -205,8 +267,11 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
             return a.kv_cache + ((((size_t)clip_of(r) * W.nlayers + l) * 2 + kv) * a.max_len) * RPC * D;
         };
         // ---- self attention
+        AC_DEC_STAMP(1 + 12 * l);
         matvec_t<R>(L.sa_in_wt, L.sa_in_b, s_x, D, s_h, 3 * D, 3 * D, D, false, s_part, rank, P);
+        AC_DEC_STAMP(2 + 12 * l);
         cluster.sync();
+        AC_DEC_STAMP(3 + 12 * l);
         for (int i = tid; i < R * D; i += kThreads) {
             const int r = i / D, f = i - r * D;
             s_c[i] = s_h[r * 3 * D + f] * 0.125f;
@@ -217,67 +282,59 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
         }
         __syncthreads();   // also orders the cache writes before the reads below (same CTA)
         const int nk = t + 1;
-        for (int it = warp; it < R * NH * nk; it += kWarps) {
-            const int j = it % nk, hh = (it / nk) % NH, r = it / (nk * NH);
-            const float* kp = kcache(r, 0) + ((size_t)j * RPC + anc[r][j] % RPC) * D + hh * HD;
-            const float* qp = s_c + r * D + hh * HD;
-            float s = qp[lane] * kp[lane] + qp[lane + 32] * kp[lane + 32];
-            s = warp_sum(s);
-            if (lane == 0) s_sc[(r * NH + hh) * kMaxKeys + j] = padflag[j][anc[r][j]] ? -INFINITY : s;
+        for (int task = warp; task < R * NH; task += kWarps) {
+            const int r = task / NH, hh = task - r * NH;
+            const float* kc = kcache(r, 0) + hh * HD;
+            const float* vc = kcache(r, 1) + hh * HD;
+            attend_head(s_c + r * D + hh * HD, 1.0f, nk,
+                        [&](int j) { return kc + ((size_t)j * RPC + anc[r][j] % RPC) * D; },
+                        [&](int j) { return vc + ((size_t)j * RPC + anc[r][j] % RPC) * D; },
+                        [&](int j) { return padflag[j][anc[r][j]] != 0; }, s_att + r * D + hh * HD);
         }
         __syncthreads();
-        softmax_rows<R>(s_sc, nk);
-        __syncthreads();
-        for (int i = tid; i < R * D; i += kThreads) {
-            const int r = i / D, f = i - r * D;
-            const float* p = s_sc + (r * NH + f / HD) * kMaxKeys;
-            const float* vc = kcache(r, 1);
-            float o = 0.f;
-            for (int j = 0; j < nk; ++j) o = fmaf(p[j], vc[((size_t)j * RPC + anc[r][j] % RPC) * D + f], o);
-            s_att[i] = o;
-        }
-        __syncthreads();
+        AC_DEC_STAMP(4 + 12 * l);
         matvec_t<R>(L.sa_out_wt, L.sa_out_b, s_att, D, s_q, D, D, D, false, s_part, rank, P);
         cluster.sync();
+        AC_DEC_STAMP(5 + 12 * l);
         add_layernorm<R>(s_x, s_q, L.n1_g, L.n1_b);
         __syncthreads();
         // ---- cross attention over the projected audio memory
+        AC_DEC_STAMP(6 + 12 * l);
         matvec_t<R>(L.ca_q_wt, L.ca_q_b, s_x, D, s_c, D, D, D, false, s_part, rank, P);
         cluster.sync();
-        auto kmem = [&](int r) { return a.kv_mem + (((size_t)l * a.n_clips + clip_of(r)) * a.t_mem) * 2 * D; };
-        for (int it = warp; it < R * NH * a.t_mem; it += kWarps) {
-            const int j = it % a.t_mem, hh = (it / a.t_mem) % NH, r = it / (a.t_mem * NH);
-            const float* kp = kmem(r) + (size_t)j * 2 * D + hh * HD;
-            const float* qp = s_c + r * D + hh * HD;
-            float s = qp[lane] * __ldg(kp + lane) + qp[lane + 32] * __ldg(kp + lane + 32);
-            s = warp_sum(s) * 0.125f;
-            if (lane == 0) s_sc[(r * NH + hh) * kMaxKeys + j] = j < n_mem_of(r) ? s : -INFINITY;
-        }
-        __syncthreads();
-        softmax_rows<R>(s_sc, a.t_mem);
-        __syncthreads();
-        for (int i = tid; i < R * D; i += kThreads) {
-            const int r = i / D, f = i - r * D;
-            const float* p = s_sc + (r * NH + f / HD) * kMaxKeys;
-            const float* km = kmem(r);
+        AC_DEC_STAMP(7 + 12 * l);
+        // cross-attention K | V of row r's clip: staged shared-memory copy ([layer][clip of the cluster][frame], padded
+        // frame stride) when the kernel made one, else global memory
+        for (int task = warp; task < R * NH; task += kWarps) {
+            const int r = task / NH, hh = task - r * NH;
+            const float* km; int stride;
+            if (s_kv != nullptr) { km = s_kv + (((size_t)l * (R / RPC) + r / RPC) * a.t_mem) * kStageStride; stride = kStageStride; }
+            else { km = a.kv_mem + (((size_t)l * a.n_clips + clip_of(r)) * a.t_mem) * 2 * D; stride = 2 * D; }
             const int n_mem = n_mem_of(r);
-            float o = 0.f;
-            for (int j = 0; j < n_mem; ++j) o = fmaf(p[j], __ldg(km + (size_t)j * 2 * D + D + f), o);
-            s_att[i] = o;
+            attend_head(s_c + r * D + hh * HD, 0.125f, a.t_mem,
+                        [&](int j) { return km + (size_t)j * stride + hh * HD; },
+                        [&](int j) { return km + (size_t)j * stride + D + hh * HD; },
+                        [&](int j) { return j >= n_mem; }, s_att + r * D + hh * HD);
         }
         __syncthreads();
+        AC_DEC_STAMP(8 + 12 * l);
         matvec_t<R>(L.ca_out_wt, L.ca_out_b, s_att, D, s_q, D, D, D, false, s_part, rank, P);
         cluster.sync();
+        AC_DEC_STAMP(9 + 12 * l);
         add_layernorm<R>(s_x, s_q, L.n2_g, L.n2_b);
         __syncthreads();
         // ---- feed forward
+        AC_DEC_STAMP(10 + 12 * l);
         matvec_t<R>(L.ff1_wt, L.ff1_b, s_x, D, s_h, W.dff, W.dff, D, true, s_part, rank, P);
         cluster.sync();
+        AC_DEC_STAMP(11 + 12 * l);
         matvec_t<R>(L.ff2_wt, L.ff2_b, s_h, W.dff, s_q, D, D, W.dff, false, s_part, rank, P);
         cluster.sync();
+        AC_DEC_STAMP(12 + 12 * l);
         add_layernorm<R>(s_x, s_q, L.n3_g, L.n3_b);
         __syncthreads();
     }
+    AC_DEC_STAMP(40);
     // ---- classifier (no bias): each thread owns column quads of the zero-padded [D][Vp] weight
     const int V = W.vocab, VC = (V + 3) >> 2;
     const int vc0 = (int)((int64_t)VC * rank / P), vc1 = (int)((int64_t)VC * (rank + 1) / P);
@@ -303,6 +360,7 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
                 if (4 * c + q < V && clip + r / RPC < a.n_clips) logits[r][4 * c + q] = acc[r][q];
     }
     cluster.sync();   // both halves of the logits (global memory) are visible to both CTAs
+    AC_DEC_STAMP(41);
 }
 
 // block-wide (max value, lowest index) reduction
@@ -344,6 +402,29 @@ __device__ __forceinline__ float block_sum(float v, float* s_v) {
     return t;
 }
 
+// cross-attention K/V of the cluster's clips staged in shared memory when it fits (128 KB for 2 layers x 32 frames)
+constexpr int kDecSmemLimit = 224 * 1024;
+static size_t kv_smem_floats(int nlayers, int clips_per_cluster, int t_mem) {
+    return (size_t)nlayers * clips_per_cluster * t_mem * kStageStride;
+}
+template <int NCLIPS>
+__device__ __forceinline__ const float* stage_cross_kv(const DecodeArgs& a, int clip0, float* dst) {
+    if (!a.kv_in_smem) return nullptr;
+    const int per_clip4 = a.t_mem * 2 * D / 4;
+    for (int l = 0; l < a.w.nlayers; ++l)
+        for (int c = 0; c < NCLIPS; ++c) {
+            const int clip = min(clip0 + c, a.n_clips - 1);
+            const float4* src = reinterpret_cast<const float4*>(a.kv_mem + (((size_t)l * a.n_clips + clip) * a.t_mem) * 2 * D);
+            float* d = dst + (((size_t)l * NCLIPS + c) * a.t_mem) * kStageStride;
+            for (int i = threadIdx.x; i < per_clip4; i += kThreads) {
+                const int frame = i / (2 * D / 4), q = i - frame * (2 * D / 4);
+                reinterpret_cast<float4*>(d + (size_t)frame * kStageStride)[q] = __ldg(src + i);
+            }
+        }
+    __syncthreads();
+    return dst;
+}
+
 constexpr size_t dec_smem_floats(int R) { return (size_t)R * (D + D + D + 1024 + NH * kMaxKeys + 4096 + D); }
 
 // ------------------------------------------------------------------------------------ greedy
@@ -367,6 +448,7 @@ greedy_kernel(DecodeArgs a) {
     const int clip0 = (blockIdx.x / P) * G, tid = threadIdx.x;
     const bool writer = cluster.block_rank() == 0;   // every CTA of the cluster computes the same results
     const int V = a.w.vocab;
+    const float* s_kv = stage_cross_kv<G>(a, clip0, s_c + G * D);
     for (int i = tid; i < G * kMaxLen; i += kThreads) s_anc[i / kMaxLen][i % kMaxLen] = i / kMaxLen;
     int word[G]; bool finished[G]; bool valid[G];
 #pragma unroll
@@ -394,7 +476,7 @@ greedy_kernel(DecodeArgs a) {
             }
         }
         __syncthreads();
-        decoder_step<G, 1>(a, clip0, t, s_word, s_anc, s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, s_c, s_logits);
+        decoder_step<G, 1>(a, clip0, t, s_word, s_anc, s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, s_c, s_logits, s_kv);
 #pragma unroll
         for (int r = 0; r < G; ++r) {
             if (a.embed_out && writer && valid[r] && tid < D)
@@ -417,6 +499,7 @@ greedy_kernel(DecodeArgs a) {
             }
             finished[r] = finished[r] || (word[r] == a.end_idx);
         }
+        AC_DEC_STAMP(42);
     }
 }
 
@@ -448,6 +531,7 @@ beam_kernel(DecodeArgs a) {
     const int clip = blockIdx.x / P, tid = threadIdx.x;
     const int V = a.w.vocab;
     float* lp = a.logits_ws + (size_t)clip * R * V;
+    const float* s_kv = stage_cross_kv<1>(a, clip, s_c + R * D);
     if (tid < R) { s_words[tid] = a.start_idx; s_score[tid] = 0.f; s_logits[tid] = lp + (size_t)tid * V; }
     if (tid == 0) { s_ndone = 0; s_stop = 0; s_best_len = 0; s_best_score = -INFINITY; }
     for (int i = tid; i < R * kMaxLen; i += kThreads) { s_anc[0][i / kMaxLen][i % kMaxLen] = i / kMaxLen; }
@@ -457,7 +541,7 @@ beam_kernel(DecodeArgs a) {
         if (tid < R) s_pad[t][tid] = (s_words[tid] == a.pad_idx);
         if (tid < R) s_anc[cur][tid][t] = tid;
         __syncthreads();
-        decoder_step<R, R>(a, clip, t, s_words, s_anc[cur], s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, s_c, s_logits);
+        decoder_step<R, R>(a, clip, t, s_words, s_anc[cur], s_pad, s_x, s_q, s_att, s_h, s_sc, s_part, s_c, s_logits, s_kv);
         // lp = log_softmax(log_softmax(logit) / temp) + running score   (base.py:282-290)
         for (int r = 0; r < R; ++r) {
             float* row = lp + (size_t)r * V;
@@ -730,6 +814,8 @@ size_t ac_trm_workspace_bytes(const ac_trm_t* d, int rows, int t_mem, int max_le
     return (s.proj + s.kvmem + s.cache + s.logits) * sizeof(float);
 }
 
+static long long* g_dec_trace = nullptr;
+
 // `clusters` thread-block clusters of P CTAs
 static int launch_decode(void (*kernel)(ac::DecodeArgs), int clusters, int P, size_t smem, cudaStream_t st,
                          const ac::DecodeArgs& a) {
@@ -771,11 +857,15 @@ int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* att
     a.w = dec->w; a.kv_mem = kvmem; a.n_clips = batch; a.mem_len = attn_emb_len; a.kv_cache = cache; a.logits_ws = lws;
     a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
     a.seq = seq; a.logprob = logprob; a.logit_out = logit; a.embed_out = embed; a.beam = 1; a.temp = 1.0f;
+    a.dbg = g_dec_trace;
     // (CTAs per cluster, clips per cluster); AC_GREEDY="P,G" overrides for experiments
     int P = kGreedyCluster, G = kGreedyClips;
     if (const char* e = getenv("AC_GREEDY")) sscanf(e, "%d,%d", &P, &G);
     AC_REQUIRE((P == 1 || P == 2 || P == 4 || P == 8) && (G == 1 || G == 2 || G == 4), "ac_trm_greedy: bad cluster shape %d,%d", P, G);
     size_t sm = dec_smem_floats(G) * sizeof(float);
+    const size_t kvb = kv_smem_floats(dec->w.nlayers, G, t_mem) * sizeof(float);
+    a.kv_in_smem = sm + kvb <= (size_t)kDecSmemLimit ? 1 : 0;
+    if (a.kv_in_smem) sm += kvb;
     AC_TIMED("trm_greedy", st);
 #define AC_GREEDY_CASE(GG)                                                                                       \
     case GG:                                                                                                     \
@@ -808,6 +898,9 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
     a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
     a.seq = seq; a.beam = beam; a.temp = temp;
     size_t sm = dec_smem_floats(beam) * sizeof(float);
+    const size_t kvb = kv_smem_floats(dec->w.nlayers, 1, t_mem) * sizeof(float);
+    a.kv_in_smem = sm + kvb <= (size_t)kDecSmemLimit ? 1 : 0;
+    if (a.kv_in_smem) sm += kvb;
     AC_TIMED("trm_beam", st);
 #define AC_BEAM_CASE(RR)                                                                                        \
     case RR:                                                                                                    \
@@ -819,6 +912,21 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
     }
 #undef AC_BEAM_CASE
     AC_LAUNCHED("beam_kernel");
+    return AC_OK;
+}
+
+/* Diagnostic: phase trace (clock64) of decode step 5 of CTA 0 of the next greedy launches; out_host: 64 int64. */
+int ac_trm_trace(int on, long long* out_host) {
+    using namespace ac;
+    if (on && g_dec_trace == nullptr) {
+        AC_CUDA(cudaMalloc(&g_dec_trace, 64 * sizeof(long long)));
+        AC_CUDA(cudaMemset(g_dec_trace, 0, 64 * sizeof(long long)));
+    }
+    if (out_host != nullptr && g_dec_trace != nullptr) {
+        AC_CUDA(cudaDeviceSynchronize());
+        AC_CUDA(cudaMemcpy(out_host, g_dec_trace, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    if (!on && g_dec_trace != nullptr) { cudaFree(g_dec_trace); g_dec_trace = nullptr; }
     return AC_OK;
 }
 

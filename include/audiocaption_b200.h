@@ -142,6 +142,11 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb_dev, const int64_t* a
                 int start_idx, int end_idx, int pad_idx, int64_t* seq_dev,
                 void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Diagnostic: clock64 stamps of the phases of decode step 5 (CTA 0) of subsequent ac_trm_greedy launches
+ * (0 step start; per layer l: 1+12l .. 12+12l around the six GEMVs and their cluster barriers; 40 classifier start,
+ * 41 classifier done, 42 arg-max done).  out_host (nullable): 64 int64. */
+int ac_trm_trace(int on, long long* out_host);
+
 #ifdef __cplusplus
 }
 #endif
