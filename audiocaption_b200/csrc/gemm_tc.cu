@@ -460,19 +460,6 @@ void* tensor_map_encode_fn() {   // cuTensorMapEncodeTiled resolved through the 
 static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
     return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(tensor_map_encode_fn());
 }
-static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder_unused() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-    });
-    return fn;
-}
-
 static long long* g_tc_trace = nullptr;   // device buffer [8][256], set by ac_gemm_trace
 
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {

@@ -6,7 +6,7 @@
 // One CTA = 32 consecutive frames of one clip.  The waveform segment the 32 frames cover is
 // staged once in shared memory (reflect padding resolved while loading, coalesced reads); each
 // warp then transforms 4 frames: window multiply, N/2-point complex FFT of the even/odd packed
-// frame in its private shared-memory buffer, real-FFT unpacking to the power spectrum, banded
+// frame (radix-4 Stockham passes between two private shared-memory buffers), real-FFT unpacking to the power spectrum, banded
 // mel accumulation (only the non-zero band of each filter, detected from the module's own
 // `fb` buffer at create time), dB.  The 64x32 result tile is written back with frames
 // contiguous (128 B rows) in the [B, n_mels, T] layout the reference produces.
@@ -40,7 +40,6 @@ logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int ho
               const float* __restrict__ fbw, const int* __restrict__ band,
               float* __restrict__ out, float* __restrict__ gmax) {
     constexpr int M = NFFT / 2;           // complex FFT size
-    constexpr int LOG2M = (NFFT == 512) ? 8 : 9;
     constexpr int NF = NFFT / 2 + 1;      // one-sided bins
     constexpr int PSTRIDE = NF + 7;       // power buffer stride per warp
 
@@ -48,8 +47,8 @@ logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int ho
     const int seg_len = (kFramesPerCta - 1) * hop + NFFT;
     float* s_seg = reinterpret_cast<float*>(smem_raw);                       // [seg_len] (+pad to 4)
     float2* s_tw = reinterpret_cast<float2*>(s_seg + ((seg_len + 3) & ~3));  // [M+1]
-    float2* s_fft = s_tw + (M + 2);                                          // [warps][M]
-    float* s_pow = reinterpret_cast<float*>(s_fft + kMelWarps * M);          // [warps][PSTRIDE]
+    float2* s_fft = s_tw + (M + 2);                                          // [warps][2][M]
+    float* s_pow = reinterpret_cast<float*>(s_fft + 2 * kMelWarps * M);      // [warps][PSTRIDE]
     float* s_win = s_pow + kMelWarps * PSTRIDE;                              // [NFFT]
     float* s_tile = s_win + NFFT;                                            // [kMaxMels][33]
     __shared__ float s_red[kMelWarps];
@@ -72,7 +71,8 @@ logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int ho
     for (int i = tid; i < NFFT; i += kMelThreads) s_win[i] = window[i];
     __syncthreads();
 
-    float2* z = s_fft + warp * M;
+    float2* za = s_fft + warp * 2 * M;       // ping-pong buffers of the Stockham FFT
+    float2* zb = za + M;
     float* pw = s_pow + warp * PSTRIDE;
     float local_max = -INFINITY;
 
@@ -80,31 +80,58 @@ logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int ho
         const int t = t0 + f;
         if (t >= n_frames) break;   // warp-uniform
         const float* x = s_seg + f * hop;
-        // windowed frame packed as z[n] = x[2n] + i x[2n+1], stored bit-reversed
+        // windowed frame packed as z[n] = x[2n] + i x[2n+1] (natural order)
         for (int n = lane; n < M; n += 32) {
             float2 v = *reinterpret_cast<const float2*>(x + 2 * n);
             float2 wv = *reinterpret_cast<const float2*>(s_win + 2 * n);
-            int r = __brev((unsigned)n) >> (32 - LOG2M);
-            z[r] = make_float2(v.x * wv.x, v.y * wv.y);
+            za[n] = make_float2(v.x * wv.x, v.y * wv.y);
         }
         __syncwarp();
-        // radix-2 decimation-in-time butterflies
-#pragma unroll
-        for (int s = 0; s < LOG2M; ++s) {
-            const int half = 1 << s;
-            const int tw_shift = LOG2M - s;   // twiddle index = pos * (M / (2*half)) * 2 (table is for NFFT)
-            for (int j = lane; j < M / 2; j += 32) {
-                int pos = j & (half - 1);
-                int i0 = ((j >> s) << (s + 1)) + pos;
-                int i1 = i0 + half;
-                float2 tw = s_tw[pos << tw_shift];
-                float2 a = z[i0], c = z[i1];
-                float2 tt = make_float2(c.x * tw.x - c.y * tw.y, c.x * tw.y + c.y * tw.x);
-                z[i0] = make_float2(a.x + tt.x, a.y + tt.y);
-                z[i1] = make_float2(a.x - tt.x, a.y - tt.y);
+        // Stockham autosort FFT (no bit reversal; ping-pong between the warp's two buffers): radix-4 passes in
+        // registers -- 4 passes for M = 256 instead of 8 radix-2 round trips through shared memory -- plus one
+        // radix-2 pass when M is not a power of 4.  twid(m) = e^{-2 pi i m / NFFT}; the table covers m <= M.
+        auto twid = [&](int m) {
+            float2 t = s_tw[m > M ? m - M : m];
+            return m > M ? make_float2(-t.x, -t.y) : t;
+        };
+        auto cmul = [](float2 p, float2 q) { return make_float2(p.x * q.x - p.y * q.y, p.x * q.y + p.y * q.x); };
+        float2* in = za; float2* out = zb;
+        int Ns = 1;
+        for (; Ns * 4 <= M; Ns *= 4) {
+            const int tstep = NFFT / (4 * Ns);
+            for (int j = lane; j < M / 4; j += 32) {
+                const int k = j & (Ns - 1);
+                float2 v0 = in[j], v1 = in[j + M / 4], v2 = in[j + M / 2], v3 = in[j + 3 * M / 4];
+                if (Ns > 1) {
+                    v1 = cmul(v1, twid(k * tstep));
+                    v2 = cmul(v2, twid(2 * k * tstep));
+                    v3 = cmul(v3, twid(3 * k * tstep));
+                }
+                // forward DFT-4: multiplication by -i is (a, b) -> (b, -a)
+                const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+                const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+                const int j0 = ((j - k) << 2) + k;
+                out[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+                out[j0 + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);
+                out[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+                out[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);
             }
             __syncwarp();
+            float2* tmp = in; in = out; out = tmp;
         }
+        if (Ns < M) {   // M = 2 * 4^p: final radix-2 pass
+            const int tstep = NFFT / (2 * Ns);
+            for (int j = lane; j < M / 2; j += 32) {
+                const int k = j & (Ns - 1);
+                const float2 v0 = in[j], v1 = cmul(in[j + M / 2], twid(k * tstep));
+                const int j0 = ((j - k) << 1) + k;
+                out[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+                out[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+            }
+            __syncwarp();
+            float2* tmp = in; in = out; out = tmp;
+        }
+        const float2* z = in;
         // unpack the real FFT and take |X|^2
         for (int k = lane; k <= M; k += 32) {
             float2 A = z[k & (M - 1)];
@@ -152,7 +179,7 @@ static size_t logmel_smem_bytes(int hop) {
     constexpr int M = NFFT / 2;
     constexpr int NF = NFFT / 2 + 1;
     int seg_len = (kFramesPerCta - 1) * hop + NFFT;
-    size_t fl = ((seg_len + 3) & ~3) + 2 * (M + 2) + 2 * kMelWarps * M + kMelWarps * (NF + 7) + NFFT +
+    size_t fl = ((seg_len + 3) & ~3) + 2 * (M + 2) + 4 * kMelWarps * M + kMelWarps * (NF + 7) + NFFT +
                 kMaxMels * 33;
     return fl * sizeof(float);
 }
