@@ -149,7 +149,19 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on the C-level stdout at communicator creation: keep stdout clean (the one
+        # JSON line) by routing fd 1 to stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     orc, model = build_models(dev)
     enc, dec = model.model.model.encoder, model.model.model.decoder
     lib = _lib.lib()
