@@ -284,3 +284,19 @@ int dwconv_tma(const DwArgs& a, cudaStream_t st) {
 }
 
 }  // namespace ac
+
+// Diagnostic entry point (tests): one depthwise layer on caller buffers; w_dev is [k*k][C] (tap-major).
+extern "C" int ac_dwconv(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev,
+                         float* out_dev, float* partial_dev, int B, int Hi, int Wi, int C, int k, int s, int pad_lo,
+                         int pad_hi, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(in_dev && w_dev && scale_dev && bias_dev && out_dev && partial_dev, "ac_dwconv: null argument");
+    DwArgs a;
+    a.in = in_dev; a.out = out_dev; a.partial = partial_dev; a.w = w_dev; a.scale = scale_dev; a.bias = bias_dev;
+    a.B = B; a.Hi = Hi; a.Wi = Wi; a.C = C; a.k = k; a.s = s; a.pad_lo = pad_lo;
+    a.Ho = (Hi + pad_lo + pad_hi - k) / s + 1;
+    a.Wo = (Wi + pad_lo + pad_hi - k) / s + 1;
+    return dwconv_tma(a, (cudaStream_t)stream);
+}
+extern "C" int ac_dwconv_partial_rows(int Ho, int Wo, int C, int k, int s) { return ac::dwconv_tiles_per_clip(Ho, Wo, C, k, s); }
+

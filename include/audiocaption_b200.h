@@ -83,6 +83,14 @@ int ac_gemm(const float* A_dev, const float* W_dev, float* C_dev, int M, int N, 
  * on != 0 enables tracing for subsequent launches; out_host (nullable, 2048 int64) receives and clears the trace. */
 int ac_gemm_trace(int on, long long* out_host);
 
+/* Diagnostic: one depthwise layer of an MBConv block on caller buffers (efficientnet_pytorch `_depthwise_conv`
+ * with static-same padding (pad_lo before, pad_hi after, both axes) + `_bn1` folded to scale/bias + swish).
+ * in [B,Hi,Wi,C] NHWC, w [k*k][C], out [B,Ho,Wo,C]; partial [B][ac_dwconv_partial_rows(...)][C] receives per-tile
+ * channel sums of `out` (the SE squeeze numerator).  k in {3,5}, s in {1,2}, C % 4 == 0. */
+int ac_dwconv(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev, float* out_dev,
+              float* partial_dev, int B, int Hi, int Wi, int C, int k, int s, int pad_lo, int pad_hi, void* stream);
+int ac_dwconv_partial_rows(int Ho, int Wo, int C, int k, int s);
+
 /* ------------------------------------------------------------------ EfficientNet-B2 encoder
  * Replaces hf_wrapper.py:218-241 `_EffiNet.forward` (efficientnet_pytorch 0.7.1
  * `extract_features` + mean over frequency), eval mode.

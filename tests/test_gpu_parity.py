@@ -115,6 +115,53 @@ def test_tensor_core_gemm_matches_float64(case):
     assert _gemm(path=0, **case) < 5e-6
 
 
+# ------------------------------------------------------------------ depthwise kernel (TMA tiles) vs torch conv2d
+DW_CASES = [  # (B, Hi, Wi, C, k, s, pad_lo, pad_hi)
+    (2, 32, 501, 32, 3, 1, 1, 1),      # block 0
+    (3, 32, 100, 16, 3, 1, 1, 1),      # 16-channel chunks
+    (2, 32, 501, 96, 3, 2, 0, 1),      # block 2: stride 2, asymmetric static-same padding
+    (2, 16, 251, 144, 5, 2, 2, 2),     # block 5: 5x5 stride 2, partial last channel chunk
+    (2, 8, 126, 288, 5, 1, 2, 2),      # 64-channel chunks
+    (3, 4, 63, 528, 3, 1, 1, 1),
+    (2, 4, 63, 720, 5, 2, 2, 2),       # block 16
+    (5, 2, 32, 1248, 5, 1, 2, 2),      # two output rows
+    (1, 7, 33, 2112, 3, 1, 1, 1),      # odd sizes, widest layer
+    (1, 1, 5, 32, 3, 1, 1, 1),         # tiny image
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES, ids=lambda c: "x".join(str(v) for v in c))
+def test_depthwise_matches_torch(case):
+    """dwconv_tma_kernel against F.conv2d(groups=C) in float64: zero padding through the TMA out-of-bounds fill
+    (negative coordinates), folded BN, swish, and the per-tile channel sums that feed squeeze-and-excitation."""
+    import torch.nn.functional as F
+    from audiocaption_b200 import _lib
+    B, Hi, Wi, Cc, k, s_, lo, hi = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Hi, Wi, Cc, generator=g).to(DEV)
+    w = (torch.randn(k * k, Cc, generator=g) / k).to(DEV)
+    sc = (torch.rand(Cc, generator=g) + 0.5).to(DEV)
+    bi = torch.randn(Cc, generator=g).to(DEV)
+    Ho, Wo = (Hi + lo + hi - k) // s_ + 1, (Wi + lo + hi - k) // s_ + 1
+    l = _lib.lib()
+    rows = l.ac_dwconv_partial_rows(Ho, Wo, Cc, k, s_)
+    out = torch.full((B, Ho, Wo, Cc), float("nan"), device=DEV)
+    part = torch.full((B, rows, Cc), float("nan"), device=DEV)
+    _lib.check(l.ac_dwconv(_lib.ptr(x), _lib.ptr(w), _lib.ptr(sc), _lib.ptr(bi), _lib.ptr(out), _lib.ptr(part), B, Hi, Wi,
+                           Cc, k, s_, lo, hi, _lib.current_stream()), "ac_dwconv")
+    torch.cuda.synchronize()
+    xd = F.pad(x.double().permute(0, 3, 1, 2), (lo, hi, lo, hi))
+    wd = w.double().t().reshape(Cc, 1, k, k)
+    ref = F.conv2d(xd, wd, stride=s_, groups=Cc) * sc.double()[None, :, None, None] + bi.double()[None, :, None, None]
+    ref = (ref * torch.sigmoid(ref)).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and not torch.isnan(out).any()
+    assert (out.double() - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert not torch.isnan(part).any()
+    sums = part.double().sum(dim=1)
+    want = ref.sum(dim=(1, 2))
+    assert (sums - want).abs().max() < 1e-4 * max(1.0, want.abs().max().item())
+
+
 # ------------------------------------------------------------------ EfficientNet-B2 encoder
 @pytest.mark.parametrize("batch,n_samples", [(1, 160000), (3, 32000), (2, 51317)])
 def test_encoder_matches_oracle(mirror, oracle_effb2, batch, n_samples):
@@ -226,6 +273,48 @@ def test_model_end_to_end(mirror, oracle_effb2, golden_effb2, golden_wav):
     beam = mirror(wav, lens, sample_method="beam", beam_size=3)
     st3 = g["beam3_stable"]
     assert (beam.numpy()[st3] == g["beam3_seq"][st3]).all()
+
+
+def test_single_clip_demo_config(mirror, oracle_effb2):
+    """BASELINE configs[0]: one 10 s clip, greedy (the reference's demo.py path)."""
+    wav, lens = cm.synth_wav(1, 160000, seed=11, varied=True)
+    with torch.no_grad():
+        ref = oracle_effb2.encoder({"wav": wav, "wav_len": lens})
+        refd = cm.greedy_decode(oracle_effb2.decoder, ref["attn_emb"], ref["attn_emb_len"], 20)
+    got = mirror.model.model.encoder({"wav": wav.to(DEV), "wav_len": lens, "specaug": False})
+    scale = ref["attn_emb"].abs().max()
+    assert (got["attn_emb"].cpu() - ref["attn_emb"]).abs().max() < 1e-3 * scale
+    out = mirror.model.model.decoder.greedy(ref["attn_emb"].to(DEV), ref["attn_emb_len"], 20, cm.START, cm.END, cm.PAD)
+    assert (out["seq"].cpu() == refd["seq"]).all()
+    assert mirror(wav, lens, sample_method="greedy").shape == (1, 20)
+
+
+@pytest.mark.parametrize("batch", [5, 70, 130])
+def test_decoder_batches_beyond_one_wave(mirror, oracle_effb2, batch):
+    """Batches that are not a multiple of anything and exceed one wave of clusters (2 CTAs per clip on 148 SMs):
+    every clip must decode exactly as it does alone / in a small batch."""
+    gen = torch.Generator().manual_seed(batch)
+    attn = torch.randn(batch, 32, 1408, generator=gen)
+    lens = torch.randint(1, 33, (batch,), generator=gen)
+    dec = _decoder(mirror)
+    full = dec.greedy(attn.to(DEV), lens, 20, cm.START, cm.END, cm.PAD, need_logit=False)["seq"].cpu()
+    idx = torch.tensor([0, batch // 2, batch - 1])
+    sub = dec.greedy(attn[idx].to(DEV), lens[idx], 20, cm.START, cm.END, cm.PAD, need_logit=False)["seq"].cpu()
+    assert (full[idx] == sub).all()
+    with torch.no_grad():
+        ref = cm.greedy_decode(oracle_effb2.decoder, attn[idx], lens[idx], 20)
+    assert (sub == ref["seq"]).float().mean() > 0.9     # near-ties aside (checked strictly on the golden set)
+
+
+@pytest.mark.parametrize("beam", [1, 2, 4, 5])
+def test_beam_sizes_match_oracle(mirror, oracle_effb2, beam):
+    gen = torch.Generator().manual_seed(40 + beam)
+    attn = torch.randn(4, 32, 1408, generator=gen)
+    lens = torch.tensor([32, 17, 5, 31])
+    with torch.no_grad():
+        ref = cm.beam_search(oracle_effb2.decoder, attn, lens, beam, 20)
+    got = _decoder(mirror).beam_search(attn.to(DEV), lens, 20, beam, 1.0, cm.START, cm.END, cm.PAD)["seq"].cpu()
+    assert (got == ref["seq"]).all(1).float().mean() >= 0.75, (got, ref["seq"])
 
 
 def test_submit_matches_forward(mirror, golden_wav):
