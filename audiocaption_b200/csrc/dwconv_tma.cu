@@ -133,49 +133,71 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
         float sum[2] = {0.f, 0.f};
 
         mbar_wait(bar_full(stage), phase);
-        // tile[row][col][32 ch]: this thread reads rows r*S + kh, columns wl0*S + j
-        const uint8_t* tp = tiles_gen + (size_t)stage * p.tile_bytes +
-                            ((size_t)(r * S) * p.Wbox + (size_t)wl0 * S) * (CC * 4) + cp * 8;
-        const int rstride = p.Wbox * CC * 4;
+        // tile[row][col][CC ch]: this thread reads rows r*S + kh, columns wl0*S + j.  32-bit shared addresses, one per
+        // kernel row, advanced once per group of G columns; the columns inside a group are immediate offsets.
+        uint32_t rowaddr[K];
+        {
+            const uint32_t a0 = base + (uint32_t)stage * (uint32_t)p.tile_bytes +
+                                (uint32_t)(((r * S) * p.Wbox + wl0 * S) * (CC * 4) + cp * 8);
+            const uint32_t rstride = (uint32_t)(p.Wbox * CC * 4);
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh) rowaddr[kh] = a0 + kh * rstride;
+        }
         if (row_ok && c_ok && n_out > 0) {
             float acc[K][2];
             const int n_cols = (n_out - 1) * S + K;
             constexpr int G = K * S;
-            for (int jb = 0; jb < n_cols; jb += G) {
+            // one input column (relative index jb + JJ): load its K rows, add it into the outputs it touches, finish
+            // the output whose last tap it is.  FIRST: outputs with negative index exist (skip their store);
+            // TAIL: the column itself may lie beyond the segment.
+            auto column = [&](int jb, int jj, bool first, bool tail) {
+                const int j = jb + jj;
+                if (tail && j >= n_cols) return;
+                float x[K][2];
 #pragma unroll
-                for (int jj = 0; jj < G; ++jj) {
-                    const int j = jb + jj;
-                    if (j < n_cols) {
-                        float x[K][2];
+                for (int kh = 0; kh < K; ++kh)
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                                 : "=f"(x[kh][0]), "=f"(x[kh][1]) : "r"(rowaddr[kh] + (uint32_t)(jj * CC * 4)));
 #pragma unroll
-                        for (int kh = 0; kh < K; ++kh) {
-                            const float2 v = *reinterpret_cast<const float2*>(tp + kh * rstride + j * (CC * 4));
-                            x[kh][0] = v.x; x[kh][1] = v.y;
-                        }
+                for (int kw = 0; kw < K; ++kw) {
+                    if ((jj - kw) % S != 0) continue;
+                    const int slot = ((((jj - kw) / S) % K) + K) % K;
+                    float t0 = kw == 0 ? x[0][0] * wr[0][0] : fmaf(x[0][0], wr[kw][0], acc[slot][0]);
+                    float t1 = kw == 0 ? x[0][1] * wr[0][1] : fmaf(x[0][1], wr[kw][1], acc[slot][1]);
 #pragma unroll
-                        for (int kw = 0; kw < K; ++kw) {
-                            if ((jj - kw) % S != 0) continue;
-                            const int slot = ((((jj - kw) / S) % K) + K) % K;
-                            float t0 = x[0][0] * wr[kw][0], t1 = x[0][1] * wr[kw][1];
-#pragma unroll
-                            for (int kh = 1; kh < K; ++kh) {
-                                t0 = fmaf(x[kh][0], wr[kh * K + kw][0], t0);
-                                t1 = fmaf(x[kh][1], wr[kh * K + kw][1], t1);
-                            }
-                            acc[slot][0] = (kw == 0) ? t0 : acc[slot][0] + t0;
-                            acc[slot][1] = (kw == 0) ? t1 : acc[slot][1] + t1;
-                            if (kw == K - 1) {
-                                const int u = (j - kw) / S;
-                                if (j >= kw && u < n_out) {
-                                    const float o0 = fast_swish(fmaf(acc[slot][0], sc[0], bi[0]));
-                                    const float o1 = fast_swish(fmaf(acc[slot][1], sc[1], bi[1]));
-                                    sum[0] += o0; sum[1] += o1;
-                                    *reinterpret_cast<float2*>(orow + (size_t)u * p.C) = make_float2(o0, o1);
-                                }
-                            }
+                    for (int kh = 1; kh < K; ++kh) {
+                        t0 = fmaf(x[kh][0], wr[kh * K + kw][0], t0);
+                        t1 = fmaf(x[kh][1], wr[kh * K + kw][1], t1);
+                    }
+                    acc[slot][0] = t0; acc[slot][1] = t1;
+                    if (kw == K - 1) {                     // last tap: output u = (j - kw) / S is complete
+                        if (!first || j >= kw) {
+                            const float o0 = fast_swish(fmaf(t0, sc[0], bi[0]));
+                            const float o1 = fast_swish(fmaf(t1, sc[1], bi[1]));
+                            sum[0] += o0; sum[1] += o1;
+                            *reinterpret_cast<float2*>(orow + (size_t)((j - kw) / S) * p.C) = make_float2(o0, o1);
                         }
                     }
                 }
+            };
+            auto advance = [&]() {
+#pragma unroll
+                for (int kh = 0; kh < K; ++kh) rowaddr[kh] += (uint32_t)(G * CC * 4);
+            };
+            int jb = 0;
+            if (n_cols >= G) {                             // first group: no column is beyond the segment
+#pragma unroll
+                for (int jj = 0; jj < G; ++jj) column(0, jj, true, false);
+                advance(); jb = G;
+                for (; jb + G <= n_cols; jb += G) {        // interior groups: no checks at all
+#pragma unroll
+                    for (int jj = 0; jj < G; ++jj) column(jb, jj, false, false);
+                    advance();
+                }
+            }
+            if (jb < n_cols) {                             // last, partial group
+#pragma unroll
+                for (int jj = 0; jj < G; ++jj) column(jb, jj, jb == 0, true);
             }
         }
         __syncwarp();
