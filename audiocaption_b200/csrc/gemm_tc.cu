@@ -47,13 +47,14 @@ constexpr int TC_A_TILE_BYTES = TC_BM * TC_BK * 4; // 16 KB (hi image; lo image 
 constexpr int TC_SLAB_BYTES = 32 * 32 * 4;         // one epilogue warp's 32 rows x 32 columns
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_BAR_BYTES = 256;
+constexpr int TC_BAR_BYTES = 320;
+constexpr int TC_MAX_ACC = 4;                     // accumulator stages in TMEM (2 for wide tiles, 4 for BN <= 64)
 
 struct TcParams {
     const float* wpacked; float* C; const float* R;
     const float* ascale; const float* cbias;
     int M, N, K, ldc, rows_per_group;
-    int BN, n_tiles, m_tiles, k_chunks, stages, tmem_cols, resident, a_slots;
+    int BN, n_tiles, m_tiles, k_chunks, stages, tmem_cols, resident, a_slots, acc_stages;
     long long* dbg;   // optional pipeline trace of CTA 0 (AC_TC_TRACE): [event kind 0..7][256] clock64 stamps
 };
 
@@ -85,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // 128B swizzle needs 1024-byte aligned tiles
     // smem: [epilogue slabs][resident W][stages: raw A chunk | (streamed W hi | lo)][barriers][per-warp bias]
-    // TMEM: [accumulator 0 | accumulator 1 (BN columns each)][A ring: a_slots x (hi 32 columns | lo 32 columns)]
+    // TMEM: [acc_stages accumulators (BN columns each)][A ring: a_slots x (hi 32 columns | lo 32 columns)]
     const uint32_t slabs = base;
     const uint32_t w_res = slabs + TC_EPI_WARPS * TC_SLAB_BYTES;
     const uint32_t w_chunk_bytes = (uint32_t)p.BN * 256u;
@@ -97,9 +98,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto bar_axf = [&](int a) { return bars + 128u + 8u * a; };       // A slot (TMEM) holds hi / lo
     auto bar_aempty = [&](int a) { return bars + 160u + 8u * a; };    // A slot consumed by the tensor core
     auto bar_acc_full = [&](int a) { return bars + 192u + 8u * a; };
-    auto bar_acc_empty = [&](int a) { return bars + 208u + 8u * a; };
-    const uint32_t bar_w = bars + 224u;
-    const uint32_t tmem_slot_addr = bars + 232u;
+    auto bar_acc_empty = [&](int a) { return bars + 224u + 8u * a; };
+    const uint32_t bar_w = bars + 256u;
+    const uint32_t tmem_slot_addr = bars + 264u;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - raw));
     float* bias_all = reinterpret_cast<float*>(smem_raw + (bars + TC_BAR_BYTES - raw));   // [EPI_WARPS][TC_MAX_BN]
 
@@ -117,7 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_init(bar_axf(a), TC_XF_WARPS);
             mbar_init(bar_aempty(a), 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < p.acc_stages; ++a) {
             mbar_init(bar_acc_full(a), 1);
             mbar_init(bar_acc_empty(a), TC_EPI_WARPS);
         }
@@ -165,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // thread's own instruction stream is the limiter for small N, so the per-instruction work is kept minimal:
         // descriptors are formed once per stage and advanced by adding to their low word.
         const uint32_t idesc = umma_idesc(2, TC_BM, p.BN);
-        const uint32_t a_ring = tmem_base + 2u * (uint32_t)p.BN;
+        const uint32_t a_ring = tmem_base + (uint32_t)(p.acc_stages * p.BN);
         const uint64_t desc_hi_bits = umma_desc_sw128(0) & 0xffffffff00000000ull;   // SBO / version / swizzle fields
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
@@ -209,14 +210,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= TC_FIRST_XF_WARP) {
         // ------------------------------------------------------------ transform (gate, hi/lo split -> TMEM)
         const int wq = warp & 3;                                      // TMEM lane quarter of this warp
         const int wh = (warp - TC_FIRST_XF_WARP) >> 2;                // which 16 of the chunk's 32 k
         const int r = wq * 32 + lane;                                 // row of the tile = TMEM lane
-        const uint32_t a_ring = tmem_base + 2u * (uint32_t)p.BN + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wh * 16);
+        const uint32_t a_ring = tmem_base + (uint32_t)(p.acc_stages * p.BN) + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wh * 16);
         const float* grow = nullptr;                                  // gate row of this thread's row
         auto gate_row = [&](int tile) {
             const int row = min((tile / p.n_tiles) * TC_BM + r, p.M - 1);
@@ -314,7 +315,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_after();
             if (ew == 0 && lane == 0) AC_TC_STAMP(5, eev);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-            for (int pn = half; pn < full_panels; pn += 2) {
+            // a tile with a single work item (one panel or only the half panel) alternates between the two warps of
+            // a lane quarter from tile to tile, so two tiles' epilogues overlap
+            const bool single = full_panels + (tail16 ? 1 : 0) == 1;
+            const int first_pn = single ? ((eev & 1) == half ? 0 : full_panels) : half;
+            const bool tail_mine = tail16 && (single ? (eev & 1) == half : half == (full_panels & 1));
+            for (int pn = first_pn; pn < full_panels; pn += 2) {
                 const int col0 = n_t * p.BN + pn * 32;
                 float4 r[8];
                 if (RESID) {
@@ -346,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     bulk_commit();
                 }
             }
-            if (tail16 && half == (full_panels & 1)) {
+            if (tail_mine) {
                 // trailing 16-column half panel: direct 128-bit stores
                 const int col0 = n_t * p.BN + full_panels * 32;
                 float4 r[4];
@@ -373,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (lane == 0) mbar_arrive(bar_acc_empty(acc));
             if (ew == 0 && lane == 0) AC_TC_STAMP(6, eev);
             ++eev;
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) bulk_wait_read0();
     }
@@ -509,7 +515,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.stages = std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / sb);
     AC_REQUIRE(p.stages >= 2, "gemm_tc: tile too large for shared memory (BN=%d)", w.BN);
     p.tmem_cols = 512;                                         // one CTA per SM owns the whole tensor memory
-    p.a_slots = std::min(4, (512 - 2 * w.BN) / 64);
+    p.acc_stages = w.BN <= 64 ? TC_MAX_ACC : 2;
+    p.a_slots = std::min(4, (512 - p.acc_stages * w.BN) / 64);
     AC_REQUIRE(p.a_slots >= 2, "gemm_tc: BN=%d leaves no tensor memory for the A operand", w.BN);
     const size_t smem = (size_t)p.stages * sb + fixed;
 
