@@ -26,3 +26,14 @@ class Workspace:
 def params_signature(tensors):
     """Changes whenever a parameter is re-assigned, moved or written in place."""
     return tuple((t.data_ptr(), t._version) for t in tensors)
+
+
+def to_device_async(t: torch.Tensor, device, dtype=None) -> torch.Tensor:
+    """Small host tensor -> device without synchronising the stream: a pageable `.to(device)` makes torch wait for
+    everything queued so far (the host then cannot run ahead of the GPU); staging through pinned memory (torch's
+    caching host allocator makes this cheap) keeps the copy asynchronous."""
+    if t.is_cuda:
+        return t.to(device=device, dtype=dtype) if dtype is not None else t.to(device)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous().pin_memory().to(device, non_blocking=True)

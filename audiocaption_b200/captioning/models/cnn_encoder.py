@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
-from ._native import Workspace, params_signature, require_cuda
+from ._native import Workspace, params_signature, require_cuda, to_device_async
 
 
 # ----------------------------------------------------------------------------- parameter holders
@@ -252,7 +252,7 @@ class EfficientNetB2(nn.Module):
             wave_length = torch.as_tensor(wav_len)
             feat_length = torch.div(wave_length, self.hop_length, rounding_mode="floor") + 1
             feat_length = torch.div(feat_length, self.downsample_ratio, rounding_mode="floor")
-            len_dev = feat_length.to(device=wav.device, dtype=torch.int64)
+            len_dev = to_device_async(feat_length, wav.device, torch.int64)
             fc_emb = torch.empty(B, self.fc_emb_size, device=wav.device, dtype=torch.float32)
             _lib.check(l.ac_masked_mean(_lib.ptr(attn_emb), _lib.ptr(len_dev), B, Tp, self.fc_emb_size,
                                         _lib.ptr(fc_emb), _lib.current_stream()), "ac_masked_mean")

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from ... import _lib
 from . import BaseDecoder
-from ._native import Workspace, params_signature, require_cuda
+from ._native import Workspace, params_signature, require_cuda, to_device_async
 
 
 class PositionalEncoding(nn.Module):
@@ -105,7 +105,7 @@ class TransformerDecoder(BaseDecoder):
         if self.training:
             raise NotImplementedError("the B200 decoder implements the eval-mode (inference) path")
         attn_emb = attn_emb.float().contiguous()
-        lens = torch.as_tensor(attn_emb_len).to(device=attn_emb.device, dtype=torch.int64).contiguous()
+        lens = to_device_async(torch.as_tensor(attn_emb_len), attn_emb.device, torch.int64).contiguous()
         return attn_emb, lens
 
     def greedy(self, attn_emb, attn_emb_len, max_length, start_idx, end_idx, pad_idx, need_logit=True):
