@@ -27,6 +27,8 @@ _SIGS = {
     "ac_gemm_trace": (C.c_int, [C.c_int, C.c_void_p]),
     "ac_dwconv": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ac_conv3x3": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                             C.c_void_p]),
     "ac_dwconv_partial_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ac_effb2_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ac_effb2_destroy": (None, [C.c_void_p]),

@@ -39,13 +39,7 @@ struct DwParams {
     int Hbox, Wbox, stages, tile_bytes;
 };
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
+using ptx::tma_load_4d;
 
 // tile index -> (chunk, b, th, tw): chunk is the slowest so that a CTA's consecutive tiles share weights
 __device__ __forceinline__ void dw_tile_coords(const DwParams& p, int tile, int& chunk, int& b, int& th, int& tw) {

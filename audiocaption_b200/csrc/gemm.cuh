@@ -50,6 +50,19 @@ int gemm_tn_simt(const GemmArgs& g, cudaStream_t st);
 int gemm_tc(const GemmArgs& g, cudaStream_t st);
 void* tensor_map_encode_fn();   // PFN_cuTensorMapEncodeTiled or nullptr
 
+// 3x3 / stride 1 / pad 1 convolution + bias + activation on the tensor-core pipeline (gemm_tc.cu), NHWC fp32.
+// tw packs the [Cout, 9*Cin] tap-major weight made by conv3x3_permute_weight (BN scale folded by tc_pack_weight).
+struct Conv3Args {
+    const float* in; float* out;
+    int B, H, W, Cin, Cout;
+    const float* bias = nullptr;    // [Cout]
+    const TcWeight* tw = nullptr;
+    int act = ACT_NONE;
+};
+int conv3x3_tc(const Conv3Args& a, cudaStream_t st);
+int conv3x3_permute_weight(const float* w_dev, float* out_dev, int Cout, int Cin, cudaStream_t st);
+void conv3x3_tile_shape(int H, int W, int& Hbox, int& Bbox);
+
 // Depthwise k x k convolution + folded BN + swish + per-tile channel sums (SE squeeze), NHWC fp32, fed by 4-D
 // TMA tiles (dwconv_tma.cu).  in [B,Hi,Wi,C] -> out [B,Ho,Wo,C]; partial [B][dwconv_tiles_per_clip][C].
 struct DwArgs {

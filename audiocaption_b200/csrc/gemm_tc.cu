@@ -55,6 +55,9 @@ struct TcParams {
     const float* ascale; const float* cbias;
     int M, N, K, ldc, rows_per_group;
     int BN, n_tiles, m_tiles, k_chunks, stages, tmem_cols, resident, a_slots, acc_stages;
+    // 3x3 convolution mode (CONV): A is the NHWC activation [cB, cH, cW, Cin] seen through a 4-D tensor map; an
+    // m-tile is cBbox clips x cHbox rows x cW columns (<= 128 pixels), k-chunk kc = (tap, 32-channel chunk)
+    int cW, cH, cB, cHbox, cBbox, c_tiles_h, c_cpc, a_bytes;
     long long* dbg;   // optional pipeline trace of CTA 0 (AC_TC_TRACE): [event kind 0..7][256] clock64 stamps
 };
 
@@ -78,7 +81,7 @@ __device__ __forceinline__ float4 epi_math(const uint32_t* u, float4 b) {
 }
 
 // The BN scale is folded into the packed weight, so the epilogue is act(acc + bias) + R.
-template <int ACT, bool GATED, bool RESID>
+template <int ACT, bool GATED, bool RESID, bool CONV = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC, const TcParams p) {
     using namespace ptx;
@@ -147,12 +150,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
                 const float* wsrc = p.wpacked + (size_t)n_t * p.k_chunks * (p.BN * 64);
+                int tap = 0, cc = 0;                       // CONV: kc = tap * c_cpc + cc
+                const int c_b0 = CONV ? (m_t / p.c_tiles_h) * p.cBbox : 0;
+                const int c_h0 = CONV ? (m_t % p.c_tiles_h) * p.cHbox : 0;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(bar_empty(stage), phase ^ 1u);
                     AC_TC_STAMP(0, ev); ++ev;
                     const uint32_t sa = stage0 + stage * stage_bytes;
-                    mbar_expect_tx(bar_tma(stage), TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes));
-                    tma_load_2d(sa, &mapA, kc * TC_BK, m_t * TC_BM, bar_tma(stage));
+                    mbar_expect_tx(bar_tma(stage), (uint32_t)p.a_bytes + (p.resident ? 0u : w_chunk_bytes));
+                    if (CONV) {
+                        // the tile's pixels shifted by the tap; rows / columns outside the image arrive as zeros
+                        tma_load_4d(sa, &mapA, cc * TC_BK, tap % 3 - 1, c_h0 + tap / 3 - 1, c_b0, bar_tma(stage));
+                        if (++cc == p.c_cpc) { cc = 0; ++tap; }
+                    } else {
+                        tma_load_2d(sa, &mapA, kc * TC_BK, m_t * TC_BM, bar_tma(stage));
+                    }
                     if (!p.resident)
                         bulk_load(sa + TC_A_TILE_BYTES, wsrc + (size_t)kc * (p.BN * 64), w_chunk_bytes, bar_tma(stage));
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -315,6 +327,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_after();
             if (ew == 0 && lane == 0) AC_TC_STAMP(5, eev);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+            if (CONV) {
+                // row of the tile -> pixel (clip, h, w); every thread stores its pixel's 32-channel runs directly
+                const int r = q * 32 + lane;
+                const int w_ = r % p.cW, t_ = r / p.cW;
+                const int hl = t_ % p.cHbox, bl = t_ / p.cHbox;
+                const int h_ = (m_t % p.c_tiles_h) * p.cHbox + hl, b_ = (m_t / p.c_tiles_h) * p.cBbox + bl;
+                const bool ok = bl < p.cBbox && h_ < p.cH && b_ < p.cB;
+                float* crow = p.C + (((size_t)b_ * p.cH + h_) * p.cW + w_) * ldc;
+                for (int pn = half; pn < full_panels; pn += 2) {
+                    const int col0 = n_t * p.BN + pn * 32;
+                    uint32_t u[2][16];
+                    tmem_ld16(t_row + (uint32_t)(pn * 32), u[0]);
+                    tmem_ld16(t_row + (uint32_t)(pn * 32 + 16), u[1]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + pn * 32 + 4 * j);
+                        const float4 o = epi_math<ACT>(&u[j >> 2][(j & 3) * 4], b);
+                        if (ok && col0 + 4 * j < p.N) *reinterpret_cast<float4*>(crow + col0 + 4 * j) = o;
+                    }
+                }
+                if (tail16 && half == (full_panels & 1)) {
+                    const int col0 = n_t * p.BN + full_panels * 32;
+                    uint32_t u[16];
+                    tmem_ld16(t_row + (uint32_t)(full_panels * 32), u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + full_panels * 32 + 4 * j);
+                        const float4 o = epi_math<ACT>(&u[4 * j], b);
+                        if (ok && col0 + 4 * j < p.N) *reinterpret_cast<float4*>(crow + col0 + 4 * j) = o;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+                if (ew == 0 && lane == 0) AC_TC_STAMP(6, eev);
+                ++eev;
+                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                continue;
+            }
             // a tile with a single work item (one panel or only the half panel) alternates between the two warps of
             // a lane quarter from tile to tile, so two tiles' epilogues overlap
             const bool single = full_panels + (tail16 ? 1 : 0) == 1;
@@ -418,6 +471,23 @@ __global__ void tc_pack_kernel(const float* __restrict__ W, const float* __restr
     reinterpret_cast<float4*>(dst)[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// PyTorch Conv2d weight [Cout, Cin, 3, 3] -> [Cout, 9 * Cin] with k = (ky*3+kx) * Cin + c (tap-major: a 32-wide
+// k-chunk is 32 consecutive input channels of one tap, i.e. one shifted NHWC box)
+__global__ void conv3x3_permute_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Cout * Cin * 9) return;
+    const int c = (int)(i % Cin);
+    const int tap = (int)((i / Cin) % 9);
+    const int n = (int)(i / ((int64_t)Cin * 9));
+    o[i] = w[((size_t)n * Cin + c) * 9 + tap];
+}
+int conv3x3_permute_weight(const float* w_dev, float* out_dev, int Cout, int Cin, cudaStream_t st) {
+    const int64_t total = (int64_t)Cout * Cin * 9;
+    conv3x3_permute_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(w_dev, out_dev, Cout, Cin);
+    AC_LAUNCHED("conv3x3_permute_kernel");
+    return AC_OK;
+}
+
 static bool tc_resident(int BN, int n_tiles, int k_chunks) {
     return n_tiles == 1 && (int64_t)k_chunks * BN * 256 <= TC_RESIDENT_W_BYTES;
 }
@@ -509,6 +579,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = cdiv(g.M, TC_BM); p.k_chunks = w.k_chunks;
     p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
     p.dbg = g_tc_trace;
+    p.cW = p.cH = p.cB = p.cHbox = p.cBbox = p.c_tiles_h = p.c_cpc = 0; p.a_bytes = TC_A_TILE_BYTES;
     const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_EPI_WARPS * TC_SLAB_BYTES +
                       (p.resident ? w.k_chunks * w.BN * 256 : 0);
     const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
@@ -550,7 +621,102 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     return AC_OK;
 }
 
+// 3x3 / stride 1 / pad 1 convolution + folded BN + activation as an implicit GEMM on the same pipeline:
+//   out[b,h,w,n] = act( sum_{ky,kx,c} in[b, h+ky-1, w+kx-1, c] * Wp[n, (ky*3+kx)*Cin + c] + bias[n] )
+// (captioning/models/cnn_encoder.py:32-75 `ConvBlock`: conv -> BatchNorm -> ReLU, eval mode.)  in/out NHWC fp32;
+// the weight is the [Cout, 9*Cin] matrix (tap-major, BN scale folded) packed by tc_pack_weight.
+void conv3x3_tile_shape(int H, int W, int& Hbox, int& Bbox) {
+    if (W * H <= TC_BM / 2) { Hbox = H; Bbox = TC_BM / (W * H); }
+    else { Hbox = std::max(1, std::min(H, TC_BM / W)); Bbox = 1; }
+}
+
+int conv3x3_tc(const Conv3Args& a, cudaStream_t st) {
+    AC_REQUIRE(a.tw != nullptr && a.tw->packed != nullptr, "conv3x3_tc: weight not packed");
+    const TcWeight& w = *a.tw;
+    AC_REQUIRE(a.Cin % TC_BK == 0 && a.Cout % 4 == 0, "conv3x3_tc: Cin (%d) %% 32 and Cout (%d) %% 4 must be 0", a.Cin, a.Cout);
+    AC_REQUIRE(w.N == a.Cout && w.K == 9 * a.Cin, "conv3x3_tc: packed weight is %dx%d, call wants %dx%d", w.N, w.K,
+               a.Cout, 9 * a.Cin);
+    AC_REQUIRE(a.W >= 1 && a.W <= TC_BM && a.H >= 1, "conv3x3_tc: width %d must be in 1..128", a.W);
+    AC_REQUIRE(((uintptr_t)a.in & 15) == 0 && ((uintptr_t)a.out & 15) == 0, "conv3x3_tc: buffers must be 16-byte aligned");
+    if (a.B <= 0) return AC_OK;
+    auto encode = tensor_map_encoder();
+    AC_REQUIRE(encode != nullptr, "conv3x3_tc: cuTensorMapEncodeTiled is not available from the driver");
+    int Hbox, Bbox;
+    conv3x3_tile_shape(a.H, a.W, Hbox, Bbox);
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {(cuuint64_t)a.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)a.Cin * 4, (cuuint64_t)a.W * a.Cin * 4, (cuuint64_t)a.H * a.W * a.Cin * 4};
+    const cuuint32_t box[4] = {TC_BK, (cuuint32_t)a.W, (cuuint32_t)Hbox, (cuuint32_t)Bbox};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AC_REQUIRE(cr == CUDA_SUCCESS, "conv3x3_tc: cuTensorMapEncodeTiled failed (%d) for in=%p [%d,%d,%d,%d]", (int)cr, a.in,
+               a.B, a.H, a.W, a.Cin);
+
+    TcParams p;
+    p.wpacked = w.packed; p.C = a.out; p.R = nullptr; p.ascale = nullptr; p.cbias = a.bias;
+    p.M = a.B * a.H * a.W; p.N = a.Cout; p.K = 9 * a.Cin; p.ldc = a.Cout; p.rows_per_group = 1;
+    p.BN = w.BN; p.n_tiles = w.n_tiles; p.k_chunks = w.k_chunks;
+    p.cW = a.W; p.cH = a.H; p.cB = a.B; p.cHbox = Hbox; p.cBbox = Bbox; p.c_tiles_h = cdiv(a.H, Hbox); p.c_cpc = a.Cin / TC_BK;
+    p.m_tiles = cdiv(a.B, Bbox) * p.c_tiles_h;
+    p.a_bytes = a.W * Hbox * Bbox * TC_BK * 4;
+    p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
+    p.dbg = g_tc_trace;
+    const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_EPI_WARPS * TC_SLAB_BYTES +
+                      (p.resident ? w.k_chunks * w.BN * 256 : 0);
+    const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
+    p.stages = std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / sb);
+    AC_REQUIRE(p.stages >= 2, "conv3x3_tc: tile too large for shared memory (BN=%d)", w.BN);
+    p.tmem_cols = 512;
+    p.acc_stages = w.BN <= 64 ? TC_MAX_ACC : 2;
+    p.a_slots = std::min(4, (512 - p.acc_stages * w.BN) / 64);
+    const size_t smem = (size_t)p.stages * sb + fixed;
+    const int grid = std::min(p.m_tiles * p.n_tiles, kNumSMs);
+    AC_TIMED("conv3x3_tc", st);
+    auto launch = [&](auto kernel) -> int {
+        AC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1] = {pdl_attr()};
+        cfg.attrs = at; cfg.numAttrs = 1;
+        AC_CUDA(cudaLaunchKernelEx(&cfg, kernel, map, map, p));
+        return AC_OK;
+    };
+    int rc;
+    if (a.act == ACT_RELU) rc = launch(gemm_tc_kernel<ACT_RELU, false, false, true>);
+    else if (a.act == ACT_NONE) rc = launch(gemm_tc_kernel<ACT_NONE, false, false, true>);
+    else { set_error("conv3x3_tc: activation %d not supported", a.act); return AC_ERR_ARG; }
+    if (rc != AC_OK) return rc;
+    AC_LAUNCHED("gemm_tc_kernel<conv3x3>");
+    return AC_OK;
+}
+
 }  // namespace ac
+
+// Diagnostic / test entry: 3x3 pad-1 convolution + per-channel scale/bias + activation (NHWC fp32).
+// w_dev is the PyTorch Conv2d weight [Cout, Cin, 3, 3]; scale/bias [Cout] nullable; act 0 none, 2 relu.
+extern "C" int ac_conv3x3(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev,
+                          float* out_dev, int B, int H, int W, int Cin, int Cout, int act, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(in_dev && w_dev && out_dev, "ac_conv3x3: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *perm = nullptr, *packed = nullptr;
+    AC_CUDA(cudaMalloc(&perm, (size_t)Cout * 9 * Cin * sizeof(float)));
+    AC_CUDA(cudaMalloc(&packed, tc_packed_floats(Cout, 9 * Cin) * sizeof(float)));
+    TcWeight tw;
+    int rc = conv3x3_permute_weight(w_dev, perm, Cout, Cin, st);
+    if (rc == AC_OK) rc = tc_pack_weight(perm, scale_dev, Cout, 9 * Cin, packed, st, &tw);
+    if (rc == AC_OK) {
+        Conv3Args a; a.in = in_dev; a.out = out_dev; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+        a.bias = bias_dev; a.tw = &tw; a.act = act;
+        rc = conv3x3_tc(a, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(perm); cudaFree(packed);
+    if (rc == AC_OK && e != cudaSuccess) rc = check_cuda(e, "ac_conv3x3");
+    return rc;
+}
 
 extern "C" int ac_gemm(const float* A, const float* W, float* C, int M, int N, int K, const float* ascale,
                        int rows_per_group, const float* cscale, const float* cbias, const float* R, int act, int path,

@@ -73,6 +73,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// 4-D tiled load (NHWC activations: c0 = channel, c1 = w, c2 = h, c3 = clip; out-of-range coordinates, negative
+// ones included, are zero-filled -- that is the convolution's zero padding)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
 // 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned)
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

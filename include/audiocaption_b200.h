@@ -91,6 +91,14 @@ int ac_dwconv(const float* in_dev, const float* w_dev, const float* scale_dev, c
               float* partial_dev, int B, int Hi, int Wi, int C, int k, int s, int pad_lo, int pad_hi, void* stream);
 int ac_dwconv_partial_rows(int Ho, int Wo, int C, int k, int s);
 
+/* Diagnostic: one 3x3 / stride 1 / pad 1 convolution + per-channel scale and bias + activation, the body of
+ * captioning/models/cnn_encoder.py:32-75 `ConvBlock` (conv -> BatchNorm(eval) -> ReLU), as an implicit GEMM on the
+ * tcgen05 pipeline (4-D TMA boxes shifted per tap; 3xTF32 split).  in [B,H,W,Cin] NHWC, w [Cout,Cin,3,3] (PyTorch
+ * layout), scale/bias [Cout] nullable, out [B,H,W,Cout] NHWC; Cin % 32 == 0, Cout % 32 == 0, W <= 128; act 0 | 2.
+ * Synchronises. */
+int ac_conv3x3(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev, float* out_dev,
+               int B, int H, int W, int Cin, int Cout, int act, void* stream);
+
 /* ------------------------------------------------------------------ EfficientNet-B2 encoder
  * Replaces hf_wrapper.py:218-241 `_EffiNet.forward` (efficientnet_pytorch 0.7.1
  * `extract_features` + mean over frequency), eval mode.
