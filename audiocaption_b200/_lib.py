@@ -30,6 +30,14 @@ _SIGS = {
     "ac_conv3x3": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_void_p]),
     "ac_dwconv_partial_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ac_cnn14_num_tensors": (C.c_int, []),
+    "ac_cnn14_out_dim": (C.c_int, []),
+    "ac_cnn14_out_frames": (C.c_int, [C.c_int]),
+    "ac_cnn14_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ac_cnn14_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ac_cnn14_destroy": (None, [C.c_void_p]),
+    "ac_cnn14_fwd": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_f32p, c_f32p, C.c_void_p,
+                               C.c_size_t, C.c_void_p]),
     "ac_effb2_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ac_effb2_destroy": (None, [C.c_void_p]),
     "ac_effb2_num_tensors": (C.c_int, []),

@@ -1,5 +1,9 @@
 """Mirror of the reference's waveform encoders (captioning/models/cnn_encoder.py).
 
+``Cnn14Encoder`` -- cnn_encoder.py:326-464 / hf_wrapper.py:1185-1304: 32 kHz log-mel front-end (n_fft 1024, hop 320,
+64 slaney mels, 50-14000 Hz, no top_db) + bn0 + six 3x3 ConvBlocks + fc1; arithmetic in csrc/logmel.cu and
+csrc/cnn14.cu (tcgen05 implicit-GEMM convolutions).
+
 ``EfficientNetB2`` -- cnn_encoder.py:769-839 / hf_wrapper.py:260-315: 16 kHz log-mel front-end
 (n_fft 512, hop 160, 64 HTK mels, top_db 120) + EfficientNet-B2 backbone + mean over
 frequency.  The modules below only HOLD parameters under the reference's state_dict names
@@ -256,4 +260,113 @@ class EfficientNetB2(nn.Module):
             fc_emb = torch.empty(B, self.fc_emb_size, device=wav.device, dtype=torch.float32)
             _lib.check(l.ac_masked_mean(_lib.ptr(attn_emb), _lib.ptr(len_dev), B, Tp, self.fc_emb_size,
                                         _lib.ptr(fc_emb), _lib.current_stream()), "ac_masked_mean")
+        return {"fc_emb": fc_emb, "attn_emb": attn_emb, "attn_emb_len": feat_length.cpu()}
+
+
+# ----------------------------------------------------------------------------- Cnn14
+class _ConvBlock(nn.Module):
+    """Parameter holder with the state_dict layout of cnn_encoder.py:32-50 `ConvBlock`."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = _Conv(cin, cout, 3)
+        self.conv2 = _Conv(cout, cout, 3)
+        self.bn1 = _BN(cout)
+        self.bn2 = _BN(cout)
+        nn.init.xavier_uniform_(self.conv1.weight)       # init_layer, cnn_encoder.py:17-23
+        nn.init.xavier_uniform_(self.conv2.weight)
+
+
+class Cnn14Encoder(nn.Module):
+    """Drop-in for captioning.models.cnn_encoder.Cnn14Encoder (cnn_encoder.py:326-464; HF copy
+    hf_wrapper.py:1185-1304).  Inference only (eval-mode BatchNorm, no dropout, no SpecAugment)."""
+
+    def __init__(self, sample_rate: int = 32000, freeze: bool = False):
+        super().__init__()
+        sr_to_fmax = {32000: 14000, 16000: 8000}
+        self.melspec_extractor = MelSpectrogram(sample_rate, 32 * sample_rate // 1000, 10 * sample_rate // 1000,
+                                                50, sr_to_fmax[sample_rate], 64, norm="slaney", mel_scale="slaney")
+        self.hop_length = 10 * sample_rate // 1000
+        self.db_transform = AmplitudeToDB()
+        self.bn0 = _BN(64)
+        chans = (1, 64, 128, 256, 512, 1024, 2048)
+        for i in range(6):
+            setattr(self, f"conv_block{i + 1}", _ConvBlock(chans[i], chans[i + 1]))
+        self.downsample_ratio = 32
+        self.fc1 = nn.Linear(2048, 2048, bias=True)
+        nn.init.xavier_uniform_(self.fc1.weight)
+        nn.init.zeros_(self.fc1.bias)
+        self.fc_emb_size = 2048
+        self.freeze = freeze
+        self._ws = Workspace()
+        self._handle = None
+        self._sig = None
+        if freeze:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def load_pretrained(self, pretrained, output_fn=print):
+        raise NotImplementedError("PANNs / COLA / BLAT checkpoint conversion (cnn_encoder.py:368-412) is out of scope; "
+                                  "load a state_dict with the reference's key names instead")
+
+    def _body_tensors(self):
+        ts = [self.bn0.weight, self.bn0.bias, self.bn0.running_mean, self.bn0.running_var]
+        for i in range(1, 7):
+            blk = getattr(self, f"conv_block{i}")
+            ts += [blk.conv1.weight, blk.conv2.weight]
+            for bn in (blk.bn1, blk.bn2):
+                ts += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        return ts + [self.fc1.weight, self.fc1.bias]
+
+    def _net(self):
+        tensors = self._body_tensors()
+        sig = params_signature(tensors)
+        if self._handle is None or sig != self._sig:
+            self.release()
+            ts = [t.detach().float().contiguous() for t in tensors]
+            for t in ts:
+                require_cuda(t, "Cnn14Encoder parameters")
+            ptrs, numels, n = _lib.tensor_table(ts)
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().ac_cnn14_create(ptrs, numels, n, _lib.current_stream(), ctypes.byref(h)),
+                       "ac_cnn14_create")
+            self._handle, self._sig = h, sig
+        return self._handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib().ac_cnn14_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def log_mel(self, wav):
+        """The reference's `db_transform(melspec_extractor(wav))` [B, 64, T]."""
+        return self.melspec_extractor(wav)[0]
+
+    def forward(self, input_dict):
+        wav = input_dict["wav"]
+        wav_len = input_dict["wav_len"]
+        if self.training and input_dict.get("specaug", False):
+            raise NotImplementedError("SpecAugment (training) is out of scope of the B200 inference path")
+        require_cuda(wav, "Cnn14Encoder.forward")
+        l = _lib.lib()
+        with torch.cuda.device(wav.device):
+            lms = self.log_mel(wav)
+            B, F, T = lms.shape
+            Tp = l.ac_cnn14_out_frames(T)
+            wave_length = torch.as_tensor(wav_len)
+            feat_length = torch.div(wave_length, self.hop_length, rounding_mode="floor") + 1
+            feat_length = torch.div(feat_length, self.downsample_ratio, rounding_mode="floor")
+            len_dev = to_device_async(feat_length, wav.device, torch.int64)
+            attn_emb = torch.empty(B, Tp, self.fc_emb_size, device=wav.device, dtype=torch.float32)
+            fc_emb = torch.empty(B, self.fc_emb_size, device=wav.device, dtype=torch.float32)
+            nbytes = l.ac_cnn14_workspace_bytes(B, F, T)
+            ws = self._ws.get(nbytes, wav.device)
+            _lib.check(l.ac_cnn14_fwd(self._net(), _lib.ptr(lms), B, F, T, _lib.ptr(len_dev), _lib.ptr(attn_emb),
+                                      _lib.ptr(fc_emb), _lib.ptr(ws), nbytes, _lib.current_stream()), "ac_cnn14_fwd")
         return {"fc_emb": fc_emb, "attn_emb": attn_emb, "attn_emb_len": feat_length.cpu()}

@@ -1,0 +1,336 @@
+// Cnn14 (PANNs) audio encoder body for sm_100a.
+//
+// Replaces captioning/models/cnn_encoder.py:414-464 `Cnn14Encoder.forward` after the log-mel front-end (HF copy:
+// hf_wrapper.py:1259-1304), eval mode: bn0 over the mel axis -> 6 x ConvBlock (cnn_encoder.py:32-75:
+// [conv3x3 -> BatchNorm -> ReLU] x 2 -> avg_pool 2x2, block 6 without pooling) -> mean over mel -> attn_emb;
+// fc_emb = relu(fc1(max_with_lens + mean_with_lens)) (model_util.py:41-84).  Dropout is the identity in eval mode.
+//
+// Layout: activations NHWC fp32 [B, H = time, W = mel, C].  The 11 convolutions with Cin >= 64 (99.8 % of the
+// 40 GFLOP per clip) run as implicit GEMMs on the tcgen05 pipeline of gemm_tc.cu (`conv3x3_tc`: 4-D TMA boxes
+// shifted per tap, 3xTF32 split, BN scale folded into the packed weight, bias + ReLU in the epilogue).  The first
+// convolution (Cin = 1, 9 MACs per output) is an HBM-write-bound SIMT kernel that also applies bn0 and the
+// [B, mel, T] -> [B, T, mel] transposition while loading.
+#include <algorithm>
+#include <vector>
+
+#include "gemm.cuh"
+
+namespace ac {
+
+constexpr int kCnn14Blocks = 6;
+constexpr int kCnn14Ch[kCnn14Blocks + 1] = {1, 64, 128, 256, 512, 1024, 2048};
+constexpr float kCnn14BnEps = 1e-5f;   // nn.BatchNorm2d default
+constexpr int kC1Time = 16;            // time steps per CTA of the first convolution
+constexpr int kC1Threads = 256;
+
+__global__ void cnn14_bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                     float* __restrict__ scale, float* __restrict__ bias, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float s = gamma[i] / sqrtf(var[i] + eps);
+        scale[i] = s;
+        bias[i] = beta[i] - mean[i] * s;
+    }
+}
+// conv_block1.conv1.weight [64, 1, 3, 3] -> [9][64]
+__global__ void cnn14_w1_kernel(const float* __restrict__ w, float* __restrict__ o, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * C) o[(i % 9) * C + i / 9] = w[i];
+}
+
+// First convolution: lms [B, M = mel, T] (dB) -> out [B, T, M, 64] = relu(bn1(conv3x3(bn0(lms^T)))).
+// A CTA owns kC1Time time steps of one clip: the (kC1Time + 2) x (M + 2) input patch (bn0 applied, zero padding
+// outside the image) sits in shared memory; 16 threads serve one pixel (4 output channels each, 36 weights in
+// registers), so a pixel's 64 channels leave as one 256-byte run.
+__global__ void __launch_bounds__(kC1Threads)
+cnn14_conv1_kernel(const float* __restrict__ lms, const float* __restrict__ s0, const float* __restrict__ t0,
+                   const float* __restrict__ w /*[9][64]*/, const float* __restrict__ scale,
+                   const float* __restrict__ bias, float* __restrict__ out, int M, int T) {
+    extern __shared__ float patch[];                     // [(kC1Time + 2)][M + 2]
+    const int b = blockIdx.y, tb = blockIdx.x * kC1Time;
+    const int PW = M + 2;
+    pdl_trigger();
+    pdl_wait();
+    for (int i = threadIdx.x; i < (kC1Time + 2) * PW; i += kC1Threads) {
+        // i -> (m, dt) with dt fastest so that consecutive threads read consecutive time steps of one mel row
+        const int dt = i % (kC1Time + 2), mm = i / (kC1Time + 2);
+        const int t = tb + dt - 1, m = mm - 1;
+        float v = 0.0f;
+        if (t >= 0 && t < T && m >= 0 && m < M) v = __ldg(lms + ((size_t)b * M + m) * T + t) * __ldg(s0 + m) + __ldg(t0 + m);
+        patch[dt * PW + mm] = v;
+    }
+    const int cg = threadIdx.x & 15, slot = threadIdx.x >> 4;   // 4 channels, pixel slot 0..15
+    float wr[9][4], sc[4], bi[4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(w + k * 64) + cg);
+        wr[k][0] = v.x; wr[k][1] = v.y; wr[k][2] = v.z; wr[k][3] = v.w;
+    }
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(scale) + cg), c = __ldg(reinterpret_cast<const float4*>(bias) + cg);
+        sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; bi[0] = c.x; bi[1] = c.y; bi[2] = c.z; bi[3] = c.w;
+    }
+    __syncthreads();
+    const int npix = kC1Time * M;
+    for (int px = slot; px < npix; px += kC1Threads / 16) {
+        const int dt = px / M, m = px % M;
+        if (tb + dt >= T) break;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float x = patch[(dt + ky) * PW + m + kx];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] = fmaf(x, wr[ky * 3 + kx][e], acc[e]);
+            }
+        float4 o;
+        o.x = fmaxf(fmaf(acc[0], sc[0], bi[0]), 0.f); o.y = fmaxf(fmaf(acc[1], sc[1], bi[1]), 0.f);
+        o.z = fmaxf(fmaf(acc[2], sc[2], bi[2]), 0.f); o.w = fmaxf(fmaf(acc[3], sc[3], bi[3]), 0.f);
+        reinterpret_cast<float4*>(out + (((size_t)b * T + tb + dt) * M + m) * 64)[cg] = o;
+    }
+}
+
+// avg_pool2d(kernel 2x2, stride 2, floor): in [B, H, W, C] -> out [B, H/2, W/2, C]; one float4 per thread.
+__global__ void __launch_bounds__(256)
+cnn14_avgpool_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4, int Ho, int Wo,
+                     int64_t total) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int64_t b = r / Ho;
+    const float4* p = in + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+    const float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)W * C4), d = __ldg(p + (size_t)W * C4 + C4);
+    out[i] = make_float4(0.25f * (a.x + bb.x + cc.x + d.x), 0.25f * (a.y + bb.y + cc.y + d.y),
+                         0.25f * (a.z + bb.z + cc.z + d.z), 0.25f * (a.w + bb.w + cc.w + d.w));
+}
+
+// y [B, H, W, C] -> attn_emb [B, H, C] = mean over W (torch.mean(x, dim=3), 'b c t f -> b t c') and
+// pooled [B, C] = max_{t < len} attn_emb + (sum_{t < len} attn_emb) / len   (max_with_lens + mean_with_lens)
+__global__ void __launch_bounds__(128)
+cnn14_tail_kernel(const float* __restrict__ y, const int64_t* __restrict__ lens, float* __restrict__ attn,
+                  float* __restrict__ pooled, int H, int W, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int64_t len = lens[b];
+    const float inv_w = 1.0f / (float)W;
+    float mx = -INFINITY, sum = 0.0f;
+    for (int t = 0; t < H; ++t) {
+        float s = 0.0f;
+        for (int w = 0; w < W; ++w) s += __ldg(y + (((size_t)b * H + t) * W + w) * C + c);
+        s *= inv_w;
+        attn[((size_t)b * H + t) * C + c] = s;
+        if (t < len) { mx = fmaxf(mx, s); sum += s; }
+    }
+    pooled[(size_t)b * C + c] = mx + sum / (float)len;
+}
+
+struct Cnn14Conv { float* scale; float* bias; TcWeight tw; int cin, cout; };
+
+}  // namespace ac
+
+struct ac_cnn14 {
+    float* blob = nullptr;
+    float *bn0_s, *bn0_b, *w1, *s1, *b1;
+    ac::Cnn14Conv conv[2 * ac::kCnn14Blocks - 1];   // block1.conv2, block2.conv1, ... block6.conv2
+    float *fc_w, *fc_b;
+    ac::TcWeight fc_tw;
+};
+
+namespace ac {
+struct Cnn14Dims { int H, W; };
+static void cnn14_walk(int n_mels, int n_frames, Cnn14Dims (&d)[kCnn14Blocks]) {   // input dims of each block
+    int H = n_frames, W = n_mels;
+    for (int i = 0; i < kCnn14Blocks; ++i) { d[i] = {H, W}; if (i + 1 < kCnn14Blocks) { H /= 2; W /= 2; } }
+}
+static size_t cnn14_act_elems(int batch, int n_mels, int n_frames) {
+    Cnn14Dims d[kCnn14Blocks];
+    cnn14_walk(n_mels, n_frames, d);
+    size_t m = 0;
+    for (int i = 0; i < kCnn14Blocks; ++i) m = std::max(m, (size_t)d[i].H * d[i].W * kCnn14Ch[i + 1]);
+    return align_up(m * batch, 64);
+}
+template <typename... Args>
+static int launch_pdl(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1] = {pdl_attr()};
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kernel, args...), "cudaLaunchKernelEx");
+}
+}  // namespace ac
+
+extern "C" {
+
+int ac_cnn14_num_tensors(void) { return 4 + ac::kCnn14Blocks * 10 + 2; }
+int ac_cnn14_out_dim(void) { return ac::kCnn14Ch[ac::kCnn14Blocks]; }
+int ac_cnn14_out_frames(int n_frames) {
+    for (int i = 0; i + 1 < ac::kCnn14Blocks; ++i) n_frames /= 2;
+    return n_frames;
+}
+size_t ac_cnn14_workspace_bytes(int batch, int n_mels, int n_frames) {
+    return (2 * ac::cnn14_act_elems(batch, n_mels, n_frames) + ac::align_up((size_t)batch * ac_cnn14_out_dim(), 64)) * sizeof(float);
+}
+
+int ac_cnn14_create(const float* const* t, const int64_t* numels, int n_tensors, void* stream, ac_cnn14_t** out) {
+    using namespace ac;
+    AC_REQUIRE(t && numels && out, "ac_cnn14_create: null argument");
+    AC_REQUIRE(n_tensors == ac_cnn14_num_tensors(), "ac_cnn14_create: expected %d tensors, got %d", ac_cnn14_num_tensors(),
+               n_tensors);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = ac_cnn14_out_dim();
+    // expected element counts, in the order documented in the header
+    std::vector<int64_t> want;
+    for (int q = 0; q < 4; ++q) want.push_back(64);
+    for (int i = 0; i < kCnn14Blocks; ++i) {
+        const int ci = kCnn14Ch[i], co = kCnn14Ch[i + 1];
+        want.push_back((int64_t)co * ci * 9); want.push_back((int64_t)co * co * 9);
+        for (int q = 0; q < 8; ++q) want.push_back(co);
+    }
+    want.push_back((int64_t)D * D); want.push_back(D);
+    for (int i = 0; i < n_tensors; ++i)
+        AC_REQUIRE(numels[i] == want[i], "ac_cnn14_create: tensor %d has %lld elements, expected %lld", i,
+                   (long long)numels[i], (long long)want[i]);
+
+    size_t total = 0;
+    auto take = [&](size_t n) { size_t o = total; total += align_up(n, 64); return o; };
+    const size_t o_bn0s = take(64), o_bn0b = take(64), o_w1 = take(9 * 64), o_s1 = take(64), o_b1 = take(64);
+    struct Off { size_t s, b, pk; };
+    Off co_[2 * kCnn14Blocks - 1];
+    int cin_[2 * kCnn14Blocks - 1], cout_[2 * kCnn14Blocks - 1];
+    size_t perm_max = 0;
+    {
+        int l = 0;
+        for (int i = 0; i < kCnn14Blocks; ++i)
+            for (int j = 0; j < 2; ++j) {
+                if (i == 0 && j == 0) continue;
+                cin_[l] = j == 0 ? kCnn14Ch[i] : kCnn14Ch[i + 1]; cout_[l] = kCnn14Ch[i + 1];
+                co_[l].s = take(cout_[l]); co_[l].b = take(cout_[l]);
+                co_[l].pk = take(tc_packed_floats(cout_[l], 9 * cin_[l]));
+                perm_max = std::max(perm_max, (size_t)cout_[l] * 9 * cin_[l]);
+                ++l;
+            }
+    }
+    const size_t o_fcw = take((size_t)D * D), o_fcb = take(D), o_fcpk = take(tc_packed_floats(D, D));
+    ac_cnn14_t* net = new ac_cnn14_t();
+    float* perm = nullptr;
+    int rc = check_cuda(cudaMalloc(&net->blob, total * sizeof(float)), "ac_cnn14_create: cudaMalloc(weights)");
+    if (rc == AC_OK) rc = check_cuda(cudaMalloc(&perm, perm_max * sizeof(float)), "ac_cnn14_create: cudaMalloc(scratch)");
+    if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
+    float* B0 = net->blob;
+    auto fold = [&](int ti, int c, float* s, float* b) {
+        cnn14_bn_fold_kernel<<<cdiv(c, 256), 256, 0, st>>>(t[ti], t[ti + 1], t[ti + 2], t[ti + 3], kCnn14BnEps, s, b, c);
+        g_launches++;
+    };
+    net->bn0_s = B0 + o_bn0s; net->bn0_b = B0 + o_bn0b; net->w1 = B0 + o_w1; net->s1 = B0 + o_s1; net->b1 = B0 + o_b1;
+    fold(0, 64, net->bn0_s, net->bn0_b);
+    int l = 0;
+    for (int i = 0; i < kCnn14Blocks && rc == AC_OK; ++i) {
+        const int base = 4 + i * 10;   // conv1.weight, conv2.weight, bn1 x4, bn2 x4
+        for (int j = 0; j < 2 && rc == AC_OK; ++j) {
+            const int bn_ti = base + 2 + 4 * j;
+            if (i == 0 && j == 0) {
+                cnn14_w1_kernel<<<cdiv(9 * 64, 256), 256, 0, st>>>(t[base], net->w1, 64);
+                g_launches++;
+                fold(bn_ti, 64, net->s1, net->b1);
+                continue;
+            }
+            Cnn14Conv& c = net->conv[l];
+            c.cin = cin_[l]; c.cout = cout_[l]; c.scale = B0 + co_[l].s; c.bias = B0 + co_[l].b;
+            fold(bn_ti, c.cout, c.scale, c.bias);
+            rc = conv3x3_permute_weight(t[base + j], perm, c.cout, c.cin, st);
+            if (rc == AC_OK) rc = tc_pack_weight(perm, c.scale, c.cout, 9 * c.cin, B0 + co_[l].pk, st, &c.tw);
+            ++l;
+        }
+    }
+    const int fc_ti = 4 + kCnn14Blocks * 10;
+    net->fc_w = B0 + o_fcw; net->fc_b = B0 + o_fcb;
+    if (rc == AC_OK) rc = check_cuda(cudaMemcpyAsync(net->fc_w, t[fc_ti], (size_t)D * D * sizeof(float), cudaMemcpyDeviceToDevice, st), "fc1.weight");
+    if (rc == AC_OK) rc = check_cuda(cudaMemcpyAsync(net->fc_b, t[fc_ti + 1], (size_t)D * sizeof(float), cudaMemcpyDeviceToDevice, st), "fc1.bias");
+    if (rc == AC_OK) rc = tc_pack_weight(net->fc_w, nullptr, D, D, B0 + o_fcpk, st, &net->fc_tw);
+    if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_cnn14_create pack kernels");
+    if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_cnn14_create sync");
+    cudaFree(perm);
+    if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
+    *out = net;
+    return AC_OK;
+}
+
+void ac_cnn14_destroy(ac_cnn14_t* net) {
+    if (!net) return;
+    cudaFree(net->blob);
+    delete net;
+}
+
+int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int n_frames, const int64_t* lens,
+                 float* attn_emb, float* fc_emb, void* workspace, size_t ws_bytes, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(B >= 0 && B <= 65535, "ac_cnn14_fwd: batch %d out of range", B);
+    AC_REQUIRE(n_mels == 64, "ac_cnn14_fwd: bn0 is defined over 64 mel bins, got %d", n_mels);
+    AC_REQUIRE(n_frames >= 32, "ac_cnn14_fwd: %d frames is fewer than the down-sampling ratio 32", n_frames);
+    if (B == 0) return AC_OK;
+    AC_REQUIRE(net && lms && lens && attn_emb && fc_emb, "ac_cnn14_fwd: null argument");
+    AC_REQUIRE(workspace && ws_bytes >= ac_cnn14_workspace_bytes(B, n_mels, n_frames),
+               "ac_cnn14_fwd: workspace too small (%zu < %zu)", ws_bytes, ac_cnn14_workspace_bytes(B, n_mels, n_frames));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t act = cnn14_act_elems(B, n_mels, n_frames);
+    float* cur = (float*)workspace;
+    float* nxt = cur + act;
+    float* pooled = nxt + act;
+    Cnn14Dims d[kCnn14Blocks];
+    cnn14_walk(n_mels, n_frames, d);
+    int rc;
+    {
+        AC_TIMED("cnn14_conv1", st);
+        dim3 grid(cdiv(n_frames, kC1Time), B);
+        const size_t smem = (size_t)(kC1Time + 2) * (n_mels + 2) * sizeof(float);
+        rc = launch_pdl(cnn14_conv1_kernel, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s,
+                        (const float*)net->bn0_b, (const float*)net->w1, (const float*)net->s1, (const float*)net->b1, cur,
+                        n_mels, n_frames);
+        if (rc) return rc;
+        AC_LAUNCHED("cnn14_conv1_kernel");
+    }
+    int l = 0;
+    for (int i = 0; i < kCnn14Blocks; ++i) {
+        for (int j = 0; j < 2; ++j) {
+            if (i == 0 && j == 0) continue;
+            const Cnn14Conv& c = net->conv[l++];
+            Conv3Args a; a.in = cur; a.out = nxt; a.B = B; a.H = d[i].H; a.W = d[i].W; a.Cin = c.cin; a.Cout = c.cout;
+            a.bias = c.bias; a.tw = &c.tw; a.act = ACT_RELU;
+            rc = conv3x3_tc(a, st); if (rc) return rc;
+            std::swap(cur, nxt);
+        }
+        if (i + 1 < kCnn14Blocks) {
+            const int C4 = kCnn14Ch[i + 1] / 4, Ho = d[i].H / 2, Wo = d[i].W / 2;
+            const int64_t total = (int64_t)B * Ho * Wo * C4;
+            AC_TIMED("cnn14_avgpool", st);
+            rc = launch_pdl(cnn14_avgpool_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st,
+                            (const float4*)cur, (float4*)nxt, d[i].H, d[i].W, C4, Ho, Wo, total);
+            if (rc) return rc;
+            AC_LAUNCHED("cnn14_avgpool_kernel");
+            std::swap(cur, nxt);
+        }
+    }
+    const Cnn14Dims last = d[kCnn14Blocks - 1];
+    const int D = ac_cnn14_out_dim();
+    {
+        AC_TIMED("cnn14_tail", st);
+        rc = launch_pdl(cnn14_tail_kernel, dim3(cdiv(D, 128), B), dim3(128), 0, st, (const float*)cur, lens, attn_emb, pooled,
+                        last.H, last.W, D);
+        if (rc) return rc;
+        AC_LAUNCHED("cnn14_tail_kernel");
+    }
+    GemmArgs g; g.A = pooled; g.W = net->fc_w; g.C = fc_emb; g.M = B; g.N = D; g.K = D; g.cbias = net->fc_b; g.act = ACT_RELU;
+    g.tw = &net->fc_tw;
+    return gemm_tn(g, st);
+}
+
+}  // extern "C"

@@ -36,6 +36,7 @@ extern "C" {
 typedef struct ac_frontend ac_frontend_t;
 typedef struct ac_effb2 ac_effb2_t;
 typedef struct ac_trm ac_trm_t;
+typedef struct ac_cnn14 ac_cnn14_t;
 
 int ac_version(void);
 const char* ac_last_error(void);
@@ -120,6 +121,28 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms_dev, const float* gmax_
 /* Introspection of the built-in block plan (tests compare it with the oracle's):
  * fills out[9] = {cin, cout, expand, k, stride, pad_lo, pad_hi, n_squeeze, has_skip}. */
 int ac_effb2_block_info(int block, int* out9);
+
+/* ------------------------------------------------------------------ Cnn14 (PANNs) encoder
+ * Replaces captioning/models/cnn_encoder.py:414-464 `Cnn14Encoder.forward` after the log-mel front-end (HF copy
+ * hf_wrapper.py:1259-1304), eval mode: bn0 over mel -> 6 x `ConvBlock` (cnn_encoder.py:32-75) with 2x2 average
+ * pooling (block 6: none) -> mean over mel -> attn_emb; fc_emb = relu(fc1(max_with_lens + mean_with_lens))
+ * (captioning/utils/model_util.py:41-84).
+ * tensors_dev (ac_cnn14_num_tensors() = 66 entries, the module's state_dict order without the
+ * `melspec_extractor.*` buffers and the `num_batches_tracked` entries): bn0.{weight,bias,running_mean,running_var};
+ * for block 1..6: conv1.weight [Cout,Cin,3,3], conv2.weight, bn1.{weight,bias,running_mean,running_var}, bn2.{...};
+ * fc1.weight [2048,2048], fc1.bias. */
+int ac_cnn14_num_tensors(void);
+int ac_cnn14_out_dim(void);
+int ac_cnn14_out_frames(int n_frames);
+size_t ac_cnn14_workspace_bytes(int batch, int n_mels, int n_frames);
+int ac_cnn14_create(const float* const* tensors_dev, const int64_t* numels, int n_tensors, void* stream,
+                    ac_cnn14_t** out);
+void ac_cnn14_destroy(ac_cnn14_t* net);
+/* lms_dev [batch, 64, n_frames] (dB, the reference's AmplitudeToDB output), lens_dev [batch] int64 (valid output
+ * frames per clip, `feat_length`) -> attn_emb_dev [batch, out_frames, 2048], fc_emb_dev [batch, 2048]. */
+int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms_dev, int batch, int n_mels, int n_frames,
+                 const int64_t* lens_dev, float* attn_emb_dev, float* fc_emb_dev,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* masked mean over time, hf_wrapper.py:330-352 `mean_with_lens`:
  * x_dev [batch, T, D], lens_dev [batch] int64 -> out_dev [batch, D] */

@@ -66,6 +66,29 @@ def effb2_trm(seed=1, batch=8, n=160000):
     print("effb2_trm greedy\n", g["seq"], "\nbeam3\n", b3, "\nbeam2/12\n", b2)
 
 
+def cnn14(seed=3, batch=3, n=64000):
+    """Golden vectors of the reference's own `Cnn14Encoder` (captioning/models/cnn_encoder.py:326-464) on seeded
+    weights (oracle.cnn14.build_state_dict) and 2 s ragged clips."""
+    from . import cnn14 as oc
+    ce = ref_import.load("captioning.models.cnn_encoder")
+    ref = ce.Cnn14Encoder(sample_rate=32000).eval()
+    ref.load_state_dict(oc.build_state_dict(seed), strict=True)
+    wav, lens = cm.synth_wav(batch, n, seed=9, ragged=True, varied=True, sample_rate=32000)
+    with torch.no_grad():
+        lms = ref.db_transform(ref.melspec_extractor(wav))
+        out = ref({"wav": wav, "wav_len": lens, "specaug": False})
+    print("cnn14 feat lengths", out["attn_emb_len"].tolist(), "attn_emb", tuple(out["attn_emb"].shape))
+    np.savez_compressed(
+        os.path.join(OUT, "cnn14.npz"), seed=seed, batch=batch, n_samples=n, wav_seed=9, wav_len=lens.numpy(),
+        lms=lms[:, :, ::5].numpy(), attn_emb=out["attn_emb"].numpy(), fc_emb=out["fc_emb"].numpy(),
+        attn_emb_len=out["attn_emb_len"].numpy())
+
+
 if __name__ == "__main__":
+    import sys
     os.makedirs(OUT, exist_ok=True)
-    effb2_trm()
+    which = sys.argv[1:] or ["effb2_trm", "cnn14"]
+    if "effb2_trm" in which:
+        effb2_trm()
+    if "cnn14" in which:
+        cnn14()

@@ -353,3 +353,93 @@ def test_full_size_properties(mirror):
     assert (a == b).all()
     sub = mirror(wd[[0, 17, 63]], lens[[0, 17, 63]], sample_method="greedy")
     assert (sub == a[[0, 17, 63]]).all()
+
+
+# ------------------------------------------------------------------ Cnn14 encoder
+@pytest.mark.parametrize("B,H,W,Cin,Cout,act", [
+    (1, 4, 32, 32, 32, 2),        # one tile, W rows of 32
+    (2, 9, 64, 64, 64, 2),        # H not a multiple of the tile's 2 rows
+    (3, 31, 2, 64, 128, 2),       # two clips per tile (block-6 geometry), odd clip count
+    (2, 62, 4, 96, 160, 0),       # half-panel n-tile (80 columns), no activation
+    (2, 125, 8, 64, 256, 2),      # ragged last row tile, two n-tiles
+    (5, 7, 2, 128, 64, 2),        # 9 clips' worth of rows per tile (Bbox = 9), ragged last tile
+])
+def test_conv3x3_matches_float64(B, H, W, Cin, Cout, act):
+    """tcgen05 implicit-GEMM 3x3 convolution (ac_conv3x3) vs torch float64 conv2d: < 2e-5 of the output scale
+    (3xTF32 split: fp32-level products, truncating TMEM accumulation)."""
+    import torch.nn.functional as F
+    from audiocaption_b200 import _lib
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = torch.randn(B, H, W, Cin, generator=g).to(DEV)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).to(DEV)
+    sc = (torch.rand(Cout, generator=g) + 0.5).to(DEV)
+    bi = torch.randn(Cout, generator=g).to(DEV)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    _lib.check(_lib.lib().ac_conv3x3(_lib.ptr(x), _lib.ptr(w), _lib.ptr(sc), _lib.ptr(bi), _lib.ptr(out), B, H, W, Cin,
+                                     Cout, act, _lib.current_stream()), "ac_conv3x3")
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1) * sc.double().view(1, -1, 1, 1) \
+        + bi.double().view(1, -1, 1, 1)
+    if act == 2:
+        ref = ref.clamp_min(0)
+    ref = ref.permute(0, 2, 3, 1)
+    assert not torch.isnan(out).any()
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
+
+
+@pytest.fixture(scope="module")
+def cnn14_mirror():
+    from audiocaption_b200.captioning.models.cnn_encoder import Cnn14Encoder
+    from oracle import cnn14 as oc
+    g = np.load(__file__.rsplit("/", 1)[0] + "/golden/cnn14.npz")
+    sd = oc.build_state_dict(int(g["seed"]))
+    m = Cnn14Encoder().eval()
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV), sd, g
+
+
+def test_cnn14_encoder_matches_golden_and_oracle(cnn14_mirror):
+    """Cnn14Encoder.forward through the C ABI vs the reference's own output (golden) and the oracle.
+    Tolerance 1e-4 of the tensor's scale: 12 stacked 3xTF32 convolutions (each ~2e-6) + the fp32 log-mel."""
+    from oracle import cnn14 as oc
+    m, sd, g = cnn14_mirror
+    wav, lens = cm.synth_wav(int(g["batch"]), int(g["n_samples"]), seed=int(g["wav_seed"]), ragged=True, varied=True,
+                             sample_rate=32000)
+    with torch.no_grad():
+        out = m({"wav": wav.to(DEV), "wav_len": lens, "specaug": False})
+    torch.cuda.synchronize()
+    assert out["attn_emb_len"].tolist() == g["attn_emb_len"].tolist()
+    assert not out["attn_emb_len"].is_cuda
+    orc = oc.forward(sd, wav, lens)
+    for k in ("attn_emb", "fc_emb"):
+        got = out[k].cpu().numpy()
+        assert got.shape == g[k].shape
+        assert np.abs(got - g[k]).max() < 1e-4 * np.abs(g[k]).max(), (k, np.abs(got - g[k]).max())
+        assert np.abs(got - orc[k].numpy()).max() < 1e-4 * np.abs(g[k]).max(), k
+
+
+def test_cnn14_encoder_batch_independence_and_full_length(cnn14_mirror):
+    """Full 10 s clips: a clip's output does not depend on its batch neighbours (bitwise), and clip 0 agrees with the
+    oracle at full length (T = 1001 -> 31 frames)."""
+    from oracle import cnn14 as oc
+    m, sd, _ = cnn14_mirror
+    wav, lens = cm.synth_wav(5, 320000, seed=12, ragged=True, varied=True, sample_rate=32000)
+    with torch.no_grad():
+        full = m({"wav": wav.to(DEV), "wav_len": lens, "specaug": False})
+        part = m({"wav": wav[1:3].to(DEV), "wav_len": lens[1:3], "specaug": False})
+    assert full["attn_emb"].shape == (5, 31, 2048)
+    assert torch.equal(full["attn_emb"][1:3], part["attn_emb"])
+    assert torch.equal(full["fc_emb"][1:3], part["fc_emb"])
+    orc = oc.forward(sd, wav[:1], lens[:1])
+    for k in ("attn_emb", "fc_emb"):
+        ref = orc[k].numpy()
+        assert np.abs(full[k][:1].cpu().numpy() - ref).max() < 1e-4 * np.abs(ref).max(), k
+
+
+def test_cnn14_rejects_bad_arguments(cnn14_mirror):
+    from audiocaption_b200 import _lib
+    m, _, _ = cnn14_mirror
+    with pytest.raises(_lib.AudioCaptionB200Error):
+        m({"wav": torch.zeros(1, 32000), "wav_len": [32000], "specaug": False})          # CPU tensor
+    with pytest.raises(_lib.AudioCaptionB200Error):
+        m({"wav": torch.zeros(1, 3200, device=DEV), "wav_len": [3200], "specaug": False})  # < 32 frames

@@ -182,3 +182,57 @@ def test_product_path_has_no_cpu_fallback():
         for f in fs:
             if f.endswith(".py"):
                 assert "oracle" not in open(os.path.join(dp, f)).read().replace("no oracle", ""), f
+
+
+# ------------------------------------------------------------------ Cnn14 encoder
+def _golden_cnn14():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "cnn14.npz"))
+
+
+def test_cnn14_oracle_matches_golden():
+    """oracle/cnn14.py against the vectors produced by the reference's own Cnn14Encoder (oracle/gen_golden.py)."""
+    from oracle import cnn14 as oc
+    g = _golden_cnn14()
+    sd = oc.build_state_dict(int(g["seed"]))
+    wav, lens = cm.synth_wav(int(g["batch"]), int(g["n_samples"]), seed=int(g["wav_seed"]), ragged=True, varied=True,
+                             sample_rate=32000)
+    assert lens.tolist() == g["wav_len"].tolist()
+    out = oc.forward(sd, wav, lens)
+    assert out["attn_emb_len"].tolist() == g["attn_emb_len"].tolist()
+    assert len(set(g["attn_emb_len"].tolist())) > 1                       # the length masks are exercised
+    lms = oc.log_mel(sd, wav)[:, :, ::5]
+    assert np.abs(lms.numpy() - g["lms"]).max() < 2e-3                    # dB
+    for k in ("attn_emb", "fc_emb"):
+        ref = g[k]
+        assert np.abs(out[k].numpy() - ref).max() < 2e-5 * np.abs(ref).max(), k   # fp32 summation order only
+    assert g["attn_emb"].std() > 0.1 and g["fc_emb"].std() > 0.1          # not a degenerate network
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_cnn14_oracle_matches_imported_reference():
+    from oracle import cnn14 as oc
+    ce = ref_import.load("captioning.models.cnn_encoder")
+    ref = ce.Cnn14Encoder(sample_rate=32000).eval()
+    assert list(ref.state_dict().keys()) == oc.state_dict_keys()
+    sd = oc.build_state_dict(5)
+    ref.load_state_dict(sd, strict=True)
+    wav, lens = cm.synth_wav(2, 40000, seed=4, ragged=True, varied=True, sample_rate=32000)
+    with torch.no_grad():
+        r = ref({"wav": wav, "wav_len": lens, "specaug": False})
+    o = oc.forward(sd, wav, lens)
+    assert r["attn_emb_len"].tolist() == o["attn_emb_len"].tolist()
+    for k in ("attn_emb", "fc_emb"):
+        assert (r[k] - o[k]).abs().max() < 2e-5 * r[k].abs().max(), k
+
+
+def test_cnn14_mirror_state_dict_matches_reference_layout():
+    from audiocaption_b200.captioning.models.cnn_encoder import Cnn14Encoder
+    from oracle import cnn14 as oc
+    m = Cnn14Encoder()
+    sd = oc.build_state_dict(3)
+    assert list(m.state_dict().keys()) == oc.state_dict_keys()
+    assert all(m.state_dict()[k].shape == v.shape for k, v in sd.items())
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(Exception):                                        # no CPU fallback
+        m({"wav": torch.zeros(1, 32000), "wav_len": [32000], "specaug": False})
