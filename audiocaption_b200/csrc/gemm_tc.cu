@@ -48,6 +48,7 @@ constexpr int TC_SLAB_BYTES = 32 * 32 * 4;         // one epilogue warp's 32 row
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_BAR_BYTES = 320;
+constexpr int TC_CONV_SEG_CHUNKS = 16;              // conv: k-chunks per TMEM accumulation segment (K = 512)
 constexpr int TC_MAX_ACC = 4;                     // accumulator stages in TMEM (2 for wide tiles, 4 for BN <= 64)
 
 struct TcParams {
@@ -58,6 +59,10 @@ struct TcParams {
     // 3x3 convolution mode (CONV): A is the NHWC activation [cB, cH, cW, Cin] seen through a 4-D tensor map; an
     // m-tile is cBbox clips x cHbox rows x cW columns (<= 128 pixels), k-chunk kc = (tap, 32-channel chunk)
     int cW, cH, cB, cHbox, cBbox, c_tiles_h, c_cpc, a_bytes;
+    // CONV: the k loop is cut into segments of seg_chunks chunks; each segment accumulates in TMEM from zero and the
+    // epilogue warps add the segments in fp32 (round-to-nearest).  The tensor core truncates when it accumulates, a
+    // bias that grows linearly with the number of MMAs: ~2e-4 relative over K = 18432, ~5e-6 over a 512-wide segment.
+    int seg_chunks;
     long long* dbg;   // optional pipeline trace of CTA 0 (AC_TC_TRACE): [event kind 0..7][256] clock64 stamps
 };
 
@@ -91,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // smem: [epilogue slabs][resident W][stages: raw A chunk | (streamed W hi | lo)][barriers][per-warp bias]
     // TMEM: [acc_stages accumulators (BN columns each)][A ring: a_slots x (hi 32 columns | lo 32 columns)]
     const uint32_t slabs = base;
-    const uint32_t w_res = slabs + TC_EPI_WARPS * TC_SLAB_BYTES;
+    const uint32_t w_res = slabs + (CONV ? (uint32_t)(TC_BM * p.BN * 4) : (uint32_t)(TC_EPI_WARPS * TC_SLAB_BYTES));   // CONV: fp32 running sums [BN][128]
     const uint32_t w_chunk_bytes = (uint32_t)p.BN * 256u;
     const uint32_t stage0 = w_res + (p.resident ? (uint32_t)p.k_chunks * w_chunk_bytes : 0u);
     const uint32_t stage_bytes = TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes);
@@ -187,10 +192,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int ev = 0;
         if (p.resident) mbar_wait(bar_w, 0u);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+            uint32_t d_tmem = 0;
+            int in_seg = 0;                                   // chunk index within the current accumulation segment
             for (int kc = 0; kc < p.k_chunks; ++kc) {
+                if (in_seg == 0) {                            // (pointwise: one segment = the whole k loop)
+                    mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                    d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                }
                 if (!p.resident) mbar_wait(bar_tma(stage), phase);   // streamed weight chunk landed
                 mbar_wait(bar_axf(as), aphase);                      // A chunk split into hi / lo (TMEM)
                 tc_fence_after();
@@ -202,27 +211,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint64_t dwh0 = desc_hi_bits | (uint64_t)((w_hi & 0x3ffffu) >> 4);
                 const uint64_t dwl0 = desc_hi_bits | (uint64_t)((w_lo & 0x3ffffu) >> 4);
                 const int ksteps = min(TC_BK / 8, (p.K - kc * TC_BK) / 8);
+                const bool seg_end = kc + 1 == p.k_chunks || (CONV && in_seg + 1 == p.seg_chunks);
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
                         if (ks < ksteps) {
                             // 8 tf32 = 32 bytes along the swizzled W row = +2 in the descriptor's address field
-                            mma_tf32_ts(d_tmem, a_lo + ks * 8u, dwh0 + 2u * ks, idesc, (kc | ks) != 0 ? 1u : 0u);   // small terms first
+                            mma_tf32_ts(d_tmem, a_lo + ks * 8u, dwh0 + 2u * ks, idesc, (in_seg | ks) != 0 ? 1u : 0u);   // small terms first
                             mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwl0 + 2u * ks, idesc, 1u);
                             mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh0 + 2u * ks, idesc, 1u);
                         }
                     }
                     mma_commit(bar_empty(stage));         // smem stage reusable once these MMAs retire
                     mma_commit(bar_aempty(as));           // ... and so is the TMEM A slot
-                    if (kc + 1 == p.k_chunks) mma_commit(bar_acc_full(acc));
+                    if (seg_end) mma_commit(bar_acc_full(acc));
                 }
                 __syncwarp();
                 if (lane == 0) { AC_TC_STAMP(4, ev); }
                 ++ev;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+                ++in_seg;
+                if (seg_end) {
+                    in_seg = 0;
+                    if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                }
             }
-            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
     } else if (warp >= TC_FIRST_XF_WARP) {
         // ------------------------------------------------------------ transform (gate, hi/lo split -> TMEM)
@@ -335,37 +349,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int h_ = (m_t % p.c_tiles_h) * p.cHbox + hl, b_ = (m_t / p.c_tiles_h) * p.cBbox + bl;
                 const bool ok = bl < p.cBbox && h_ < p.cH && b_ < p.cB;
                 float* crow = p.C + (((size_t)b_ * p.cH + h_) * p.cW + w_) * ldc;
-                for (int pn = half; pn < full_panels; pn += 2) {
-                    const int col0 = n_t * p.BN + pn * 32;
-                    uint32_t u[2][16];
-                    tmem_ld16(t_row + (uint32_t)(pn * 32), u[0]);
-                    tmem_ld16(t_row + (uint32_t)(pn * 32 + 16), u[1]);
-                    tmem_ld_wait();
+                float* sums = reinterpret_cast<float*>(slab_gen - ew * TC_SLAB_BYTES) + r;   // running sums [BN][128], mine: [.][r]
+                const int nseg = (p.k_chunks + p.seg_chunks - 1) / p.seg_chunks;
+                for (int sg = 0; sg < nseg; ++sg) {
+                    if (sg != 0) { mbar_wait(bar_acc_full(acc), acc_phase); tc_fence_after(); }
+                    const bool first = sg == 0, last = sg + 1 == nseg;
+                    const uint32_t t_seg = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+                    const int my_items = full_panels + (tail16 ? 1 : 0);
+                    for (int pn = half; pn < my_items; pn += 2) {
+                        const bool is_tail = pn == full_panels;          // trailing 16-column half panel
+                        const int col0 = n_t * p.BN + pn * 32;
+                        uint32_t u[2][16];
+                        tmem_ld16(t_seg + (uint32_t)(pn * 32), u[0]);
+                        if (!is_tail) tmem_ld16(t_seg + (uint32_t)(pn * 32 + 16), u[1]);
+                        tmem_ld_wait();
+                        float* sp = sums + (size_t)(pn * 32) * TC_BM;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias + pn * 32 + 4 * j);
-                        const float4 o = epi_math<ACT>(&u[j >> 2][(j & 3) * 4], b);
-                        if (ok && col0 + 4 * j < p.N) *reinterpret_cast<float4*>(crow + col0 + 4 * j) = o;
-                    }
-                }
-                if (tail16 && half == (full_panels & 1)) {
-                    const int col0 = n_t * p.BN + full_panels * 32;
-                    uint32_t u[16];
-                    tmem_ld16(t_row + (uint32_t)(full_panels * 32), u);
-                    tmem_ld_wait();
+                        for (int c = 0; c < 32; ++c) {
+                            if (c < 16 || !is_tail) {
+                                float v = __uint_as_float(u[c >> 4][c & 15]);
+                                if (!first) v += sp[c * TC_BM];
+                                if (!last) sp[c * TC_BM] = v;
+                                u[c >> 4][c & 15] = __float_as_uint(v);
+                            }
+                        }
+                        if (last) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias + full_panels * 32 + 4 * j);
-                        const float4 o = epi_math<ACT>(&u[4 * j], b);
-                        if (ok && col0 + 4 * j < p.N) *reinterpret_cast<float4*>(crow + col0 + 4 * j) = o;
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 bq = *reinterpret_cast<const float4*>(bias + pn * 32 + 4 * j);
+                                const float4 o = epi_math<ACT>(&u[j >> 2][(j & 3) * 4], bq);
+                                if (ok && (j < 4 || !is_tail) && col0 + 4 * j < p.N)
+                                    *reinterpret_cast<float4*>(crow + col0 + 4 * j) = o;
+                            }
+                        }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acc_empty(acc));
+                    if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty(acc));
                 if (ew == 0 && lane == 0) AC_TC_STAMP(6, eev);
                 ++eev;
-                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
                 continue;
             }
             // a tile with a single work item (one panel or only the half panel) alternates between the two warps of
@@ -579,7 +603,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = cdiv(g.M, TC_BM); p.k_chunks = w.k_chunks;
     p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
     p.dbg = g_tc_trace;
-    p.cW = p.cH = p.cB = p.cHbox = p.cBbox = p.c_tiles_h = p.c_cpc = 0; p.a_bytes = TC_A_TILE_BYTES;
+    p.cW = p.cH = p.cB = p.cHbox = p.cBbox = p.c_tiles_h = p.c_cpc = 0; p.a_bytes = TC_A_TILE_BYTES; p.seg_chunks = w.k_chunks;
     const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_EPI_WARPS * TC_SLAB_BYTES +
                       (p.resident ? w.k_chunks * w.BN * 256 : 0);
     const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
@@ -661,9 +685,10 @@ int conv3x3_tc(const Conv3Args& a, cudaStream_t st) {
     p.cW = a.W; p.cH = a.H; p.cB = a.B; p.cHbox = Hbox; p.cBbox = Bbox; p.c_tiles_h = cdiv(a.H, Hbox); p.c_cpc = a.Cin / TC_BK;
     p.m_tiles = cdiv(a.B, Bbox) * p.c_tiles_h;
     p.a_bytes = a.W * Hbox * Bbox * TC_BK * 4;
+    p.seg_chunks = TC_CONV_SEG_CHUNKS;
     p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
     p.dbg = g_tc_trace;
-    const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_EPI_WARPS * TC_SLAB_BYTES +
+    const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_BM * w.BN * 4 +
                       (p.resident ? w.k_chunks * w.BN * 256 : 0);
     const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
     p.stages = std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / sb);

@@ -363,6 +363,8 @@ def test_full_size_properties(mirror):
     (2, 62, 4, 96, 160, 0),       # half-panel n-tile (80 columns), no activation
     (2, 125, 8, 64, 256, 2),      # ragged last row tile, two n-tiles
     (5, 7, 2, 128, 64, 2),        # 9 clips' worth of rows per tile (Bbox = 9), ragged last tile
+    (2, 31, 2, 2048, 128, 2),     # K = 18432: 36 accumulation segments (truncation bias would be ~1e-4 unsegmented)
+    (1, 16, 8, 544, 64, 2),       # 153 chunks: last segment is partial
 ])
 def test_conv3x3_matches_float64(B, H, W, Cin, Cout, act):
     """tcgen05 implicit-GEMM 3x3 convolution (ac_conv3x3) vs torch float64 conv2d: < 2e-5 of the output scale
