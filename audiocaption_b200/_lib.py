@@ -38,6 +38,13 @@ _SIGS = {
     "ac_cnn14_destroy": (None, [C.c_void_p]),
     "ac_cnn14_fwd": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_f32p, c_f32p, C.c_void_p,
                                C.c_size_t, C.c_void_p]),
+    "ac_bigru_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.POINTER(C.c_void_p)]),
+    "ac_bigru_destroy": (None, [C.c_void_p]),
+    "ac_bigru_out_dim": (C.c_int, [C.c_void_p]),
+    "ac_bigru_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "ac_bigru_fwd": (C.c_int, [C.c_void_p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
+                               C.c_void_p]),
     "ac_effb2_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ac_effb2_destroy": (None, [C.c_void_p]),
     "ac_effb2_num_tensors": (C.c_int, []),

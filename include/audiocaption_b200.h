@@ -37,6 +37,7 @@ typedef struct ac_frontend ac_frontend_t;
 typedef struct ac_effb2 ac_effb2_t;
 typedef struct ac_trm ac_trm_t;
 typedef struct ac_cnn14 ac_cnn14_t;
+typedef struct ac_bigru ac_bigru_t;
 
 int ac_version(void);
 const char* ac_last_error(void);
@@ -143,6 +144,23 @@ void ac_cnn14_destroy(ac_cnn14_t* net);
 int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms_dev, int batch, int n_mels, int n_frames,
                  const int64_t* lens_dev, float* attn_emb_dev, float* fc_emb_dev,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ bidirectional GRU encoder
+ * Replaces captioning/models/rnn_encoder.py:34-49 `RnnEncoder.forward` = pack_wrapper(nn.GRU(batch_first=True,
+ * bidirectional=True, num_layers=L), x, lens) (captioning/utils/model_util.py:10-27; HF copy hf_wrapper.py:1307-1347),
+ * eval mode: every clip runs over its own t < lens[b] (the reverse direction starts at lens[b]-1), outputs at
+ * t >= lens[b] are zero.  hidden must be 256.
+ * tensors_dev: nn.GRU state_dict order, 8 per layer: weight_ih_l{k} [768, D], weight_hh_l{k} [768, 256],
+ * bias_ih_l{k}, bias_hh_l{k}, then the same four with the `_reverse` suffix. */
+int ac_bigru_create(const float* const* tensors_dev, const int64_t* numels, int n_tensors, int input_dim, int hidden,
+                    int num_layers, void* stream, ac_bigru_t** out);
+void ac_bigru_destroy(ac_bigru_t* net);
+int ac_bigru_out_dim(const ac_bigru_t* net);
+size_t ac_bigru_workspace_bytes(const ac_bigru_t* net, int batch, int T);
+/* x_dev [batch, T_in, input_dim], lens_dev [batch] int64 -> out_dev [batch, T_out, 512] with T_out <= T_in
+ * (pad_packed_sequence returns max(lens) frames: pass T_out = max(lens)). */
+int ac_bigru_fwd(const ac_bigru_t* net, const float* x_dev, const int64_t* lens_dev, int batch, int T_in, int T_out,
+                 float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* masked mean over time, hf_wrapper.py:330-352 `mean_with_lens`:
  * x_dev [batch, T, D], lens_dev [batch] int64 -> out_dev [batch, D] */

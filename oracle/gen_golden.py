@@ -84,11 +84,59 @@ def cnn14(seed=3, batch=3, n=64000):
         attn_emb_len=out["attn_emb_len"].numpy())
 
 
+def build_reference_cnn14rnn_trm():
+    """The reference's Cnn14Rnn-Transformer exactly as eg_configs/audiocaps/waveform/cnn14rnn_trm.yaml:7-38 builds it."""
+    ce = ref_import.load("captioning.models.cnn_encoder")
+    re_ = ref_import.load("captioning.models.rnn_encoder")
+    cte = ref_import.load("captioning.models.crnn_trm_encoder")
+    td = ref_import.load("captioning.models.transformer_decoder")
+    tm = ref_import.load("captioning.models.transformer_model")
+    enc = cte.CrnnEncoder(ce.Cnn14Encoder(sample_rate=32000),
+                          re_.RnnEncoder(spec_dim=-1, fc_feat_dim=2048, attn_feat_dim=2048, bidirectional=True,
+                                         hidden_size=256, dropout=0.5, num_layers=3),
+                          freeze_cnn=True, freeze_cnn_bn=True)
+    dec = td.TransformerDecoder(emb_dim=256, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, nlayers=2, dropout=0.2)
+    return tm.TransformerModel(enc, dec).eval()
+
+
+def cnn14rnn_trm(cnn_seed=3, rnn_seed=4, dec_seed=6, batch=4, n=96000):
+    """Golden vectors of the reference's Cnn14Rnn-Transformer (greedy + beam 3) on seeded weights and 3 s ragged clips."""
+    from . import cnn14 as oc
+    from . import crnn
+    ref = build_reference_cnn14rnn_trm()
+    dec = crnn.build_decoder(dec_seed)
+    ref.load_state_dict(crnn.model_state_dict(oc.build_state_dict(cnn_seed), crnn.build_gru_state_dict(rnn_seed), dec), strict=True)
+    wav, lens = cm.synth_wav(batch, n, seed=13, ragged=True, varied=True, sample_rate=32000)
+    base = {"wav": wav, "wav_len": lens, "specaug": False, "mode": "inference", "temp": 1.0, "max_length": 20}
+    with torch.no_grad():
+        g = ref(dict(base, sample_method="greedy"))
+        b3 = ref(dict(base, sample_method="beam", beam_size=3))
+    stable = {k: torch.ones(batch, dtype=torch.bool) for k in ("greedy", "beam3")}
+    gen = torch.Generator().manual_seed(17)
+    with torch.no_grad():
+        for _ in range(8):
+            e = {"attn_emb": g["attn_emb"] * (1 + 1e-3 * torch.randn(g["attn_emb"].shape, generator=gen)),
+                 "attn_emb_len": g["attn_emb_len"], "fc_emb": g["fc_emb"]}
+            pg = ref.forward_decoder({"mode": "inference", "sample_method": "greedy", "max_length": 20, "temp": 1.0}, dict(e))
+            p3 = ref.forward_decoder({"mode": "inference", "sample_method": "beam", "beam_size": 3, "max_length": 20, "temp": 1.0}, dict(e))
+            stable["greedy"] &= (pg["seq"] == g["seq"]).all(1)
+            stable["beam3"] &= (p3["seq"] == b3["seq"]).all(1)
+    print("cnn14rnn_trm lens", g["attn_emb_len"].tolist(), "stable", {k: v.tolist() for k, v in stable.items()})
+    print("greedy\n", g["seq"], "\nbeam3\n", b3["seq"])
+    np.savez_compressed(
+        os.path.join(OUT, "cnn14rnn_trm.npz"), cnn_seed=cnn_seed, rnn_seed=rnn_seed, dec_seed=dec_seed, batch=batch,
+        n_samples=n, wav_seed=13, wav_len=lens.numpy(), attn_emb=g["attn_emb"].numpy(), fc_emb=g["fc_emb"].numpy(),
+        attn_emb_len=g["attn_emb_len"].numpy(), greedy_seq=g["seq"].numpy(), greedy_logit0=g["logit"][:, :2].numpy(),
+        beam3_seq=b3["seq"].numpy(), greedy_stable=stable["greedy"].numpy(), beam3_stable=stable["beam3"].numpy())
+
+
 if __name__ == "__main__":
     import sys
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["effb2_trm", "cnn14"]
+    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm"]
     if "effb2_trm" in which:
         effb2_trm()
     if "cnn14" in which:
         cnn14()
+    if "cnn14rnn_trm" in which:
+        cnn14rnn_trm()

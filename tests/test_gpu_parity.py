@@ -445,3 +445,75 @@ def test_cnn14_rejects_bad_arguments(cnn14_mirror):
         m({"wav": torch.zeros(1, 32000), "wav_len": [32000], "specaug": False})          # CPU tensor
     with pytest.raises(_lib.AudioCaptionB200Error):
         m({"wav": torch.zeros(1, 3200, device=DEV), "wav_len": [3200], "specaug": False})  # < 32 frames
+
+
+# ------------------------------------------------------------------ bi-GRU encoder, Cnn14Rnn-Transformer (rows A5 / A6)
+@pytest.mark.parametrize("B,T,lens", [
+    (1, 5, [5]),
+    (4, 7, [5, 6, 1, 4]),                 # max(lens) < T: the output has 6 frames
+    (11, 31, None),                       # two clip groups in the second cluster row, ragged
+    (64, 31, None),                       # the benchmark batch: 16 clusters
+])
+def test_bigru_matches_oracle(B, T, lens):
+    """ac_bigru_fwd through the RnnEncoder mirror vs the explicit-loop oracle: outputs live in [-1, 1]; 5e-5 absolute
+    (3xTF32 input projections, fp32 recurrence, 3 layers x up to 31 steps)."""
+    from audiocaption_b200.captioning.models.rnn_encoder import RnnEncoder
+    from oracle import crnn
+    g = torch.Generator().manual_seed(B * 100 + T)
+    x = torch.randn(B, T, 2048, generator=g).abs()
+    lens = torch.tensor(lens) if lens is not None else torch.randint(1, T + 1, (B,), generator=g)
+    if B > 4:
+        lens[0] = T
+    sd = crnn.build_gru_state_dict(21)
+    m = RnnEncoder(-1, 2048, 2048, bidirectional=True, hidden_size=256, dropout=0.5, num_layers=3).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    with torch.no_grad():
+        out = m({"attn": x.to(DEV), "attn_len": lens})
+    ref = crnn.rnn_encoder(sd, x, lens)
+    assert out["attn_emb"].shape == ref["attn_emb"].shape
+    assert (out["attn_emb"].cpu() - ref["attn_emb"]).abs().max() < 5e-5
+    assert (out["fc_emb"].cpu() - ref["fc_emb"]).abs().max() < 5e-5
+    pad = torch.arange(out["attn_emb"].shape[1]).unsqueeze(0) >= lens.unsqueeze(1)
+    assert (out["attn_emb"].cpu()[pad] == 0).all()                       # pad_packed_sequence zeros
+
+
+@pytest.fixture(scope="module")
+def crnn_mirror():
+    from audiocaption_b200.captioning.models.cnn_encoder import Cnn14Encoder
+    from audiocaption_b200.captioning.models.crnn_trm_encoder import CrnnEncoder
+    from audiocaption_b200.captioning.models.rnn_encoder import RnnEncoder
+    from audiocaption_b200.captioning.models.transformer_decoder import TransformerDecoder
+    from audiocaption_b200.captioning.models.transformer_model import TransformerModel
+    from oracle import cnn14 as oc, crnn
+    g = np.load(__file__.rsplit("/", 1)[0] + "/golden/cnn14rnn_trm.npz")
+    enc = CrnnEncoder(Cnn14Encoder(sample_rate=32000),
+                      RnnEncoder(spec_dim=-1, fc_feat_dim=2048, attn_feat_dim=2048, bidirectional=True, hidden_size=256,
+                                 dropout=0.5, num_layers=3), freeze_cnn=True, freeze_cnn_bn=True)
+    dec = TransformerDecoder(emb_dim=256, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, nlayers=2, dropout=0.2)
+    m = TransformerModel(enc, dec).eval()
+    m.load_state_dict(crnn.model_state_dict(oc.build_state_dict(int(g["cnn_seed"])), crnn.build_gru_state_dict(int(g["rnn_seed"])),
+                                            crnn.build_decoder(int(g["dec_seed"]))), strict=True)
+    return m.to(DEV), g
+
+
+def test_cnn14rnn_trm_matches_golden(crnn_mirror):
+    """Cnn14Rnn-Transformer (eg_configs/audiocaps/waveform/cnn14rnn_trm.yaml) end to end vs the reference's own output:
+    encoder memory within 2e-4 absolute (values in [-1, 1]), token ids exact on the numerically stable rows."""
+    m, g = crnn_mirror
+    wav, lens = cm.synth_wav(int(g["batch"]), int(g["n_samples"]), seed=int(g["wav_seed"]), ragged=True, varied=True,
+                             sample_rate=32000)
+    base = {"wav": wav.to(DEV), "wav_len": lens, "specaug": False, "mode": "inference", "temp": 1.0, "max_length": 20}
+    with torch.no_grad():
+        out = m(dict(base, sample_method="greedy"))
+        b3 = m(dict(base, sample_method="beam", beam_size=3))
+    assert out["attn_emb_len"].tolist() == g["attn_emb_len"].tolist()
+    assert out["attn_emb"].shape == g["attn_emb"].shape
+    assert np.abs(out["attn_emb"].cpu().numpy() - g["attn_emb"]).max() < 2e-4
+    assert np.abs(out["fc_emb"].cpu().numpy() - g["fc_emb"]).max() < 2e-4
+    st = g["greedy_stable"]
+    assert not out["seq"].is_cuda
+    assert (out["seq"].numpy()[st] == g["greedy_seq"][st]).all()
+    assert np.abs(out["logit"][:, :2].cpu().numpy() - g["greedy_logit0"]).max() < 2e-3
+    st = g["beam3_stable"]
+    assert (b3["seq"].numpy()[st] == g["beam3_seq"][st]).all()

@@ -236,3 +236,69 @@ def test_cnn14_mirror_state_dict_matches_reference_layout():
     m.load_state_dict(sd, strict=True)
     with pytest.raises(Exception):                                        # no CPU fallback
         m({"wav": torch.zeros(1, 32000), "wav_len": [32000], "specaug": False})
+
+
+# ------------------------------------------------------------------ bi-GRU encoder + Cnn14Rnn-Transformer (rows A5 / A6)
+def _golden_crnn():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "cnn14rnn_trm.npz"))
+
+
+def test_crnn_oracle_matches_golden():
+    """oracle/crnn.py (explicit GRU loops, Cnn14 restatement, decode loops) against the vectors produced by the
+    reference's own TransformerModel(CrnnEncoder(Cnn14Encoder, RnnEncoder), TransformerDecoder)."""
+    from oracle import cnn14 as oc, crnn
+    g = _golden_crnn()
+    cnn_sd, rnn_sd = oc.build_state_dict(int(g["cnn_seed"])), crnn.build_gru_state_dict(int(g["rnn_seed"]))
+    dec = crnn.build_decoder(int(g["dec_seed"]))
+    wav, lens = cm.synth_wav(int(g["batch"]), int(g["n_samples"]), seed=int(g["wav_seed"]), ragged=True, varied=True,
+                             sample_rate=32000)
+    out = crnn.caption(cnn_sd, rnn_sd, dec, wav, lens, "greedy")
+    assert out["attn_emb_len"].tolist() == g["attn_emb_len"].tolist()
+    assert len(set(g["attn_emb_len"].tolist())) > 1
+    assert out["attn_emb"].shape == g["attn_emb"].shape                   # max(lens) frames, 512 wide
+    assert np.abs(out["attn_emb"].numpy() - g["attn_emb"]).max() < 2e-5
+    assert np.abs(out["fc_emb"].numpy() - g["fc_emb"]).max() < 2e-5
+    st = g["greedy_stable"]
+    assert st.any() and (out["seq"].numpy()[st] == g["greedy_seq"][st]).all()
+    b3 = crnn.caption(cnn_sd, rnn_sd, dec, wav, lens, "beam", beam_size=3)
+    st = g["beam3_stable"]
+    assert st.any() and (b3["seq"].numpy()[st] == g["beam3_seq"][st]).all()
+    assert len({tuple(r) for r in g["greedy_seq"].tolist()}) > 1          # captions depend on the audio
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_gru_oracle_matches_imported_reference():
+    from oracle import crnn
+    re_ = ref_import.load("captioning.models.rnn_encoder")
+    ref = re_.RnnEncoder(-1, 2048, 2048, bidirectional=True, hidden_size=256, dropout=0.5, num_layers=3).eval()
+    assert list(ref.state_dict().keys()) == crnn.gru_state_dict_keys()
+    sd = crnn.build_gru_state_dict(8)
+    ref.load_state_dict(sd, strict=True)
+    x = torch.randn(5, 7, 2048, generator=torch.Generator().manual_seed(0)).abs()
+    lens = torch.tensor([5, 6, 1, 4, 6])
+    with torch.no_grad():
+        r = ref({"attn": x, "attn_len": lens})
+    o = crnn.rnn_encoder(sd, x, lens)
+    assert r["attn_emb"].shape == o["attn_emb"].shape == (5, 6, 512)
+    for k in ("attn_emb", "fc_emb"):
+        assert (r[k] - o[k]).abs().max() < 1e-5, k
+
+
+def test_cnn14rnn_trm_mirror_state_dict_matches_reference_layout():
+    from audiocaption_b200.captioning.models.cnn_encoder import Cnn14Encoder
+    from audiocaption_b200.captioning.models.crnn_trm_encoder import CrnnEncoder
+    from audiocaption_b200.captioning.models.rnn_encoder import RnnEncoder
+    from audiocaption_b200.captioning.models.transformer_decoder import TransformerDecoder
+    from audiocaption_b200.captioning.models.transformer_model import TransformerModel
+    from oracle import cnn14 as oc, crnn
+    enc = CrnnEncoder(Cnn14Encoder(sample_rate=32000),
+                      RnnEncoder(spec_dim=-1, fc_feat_dim=2048, attn_feat_dim=2048, bidirectional=True, hidden_size=256,
+                                 dropout=0.5, num_layers=3), freeze_cnn=True, freeze_cnn_bn=True)
+    dec = TransformerDecoder(emb_dim=256, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, nlayers=2, dropout=0.2)
+    m = TransformerModel(enc, dec)
+    sd = crnn.model_state_dict(oc.build_state_dict(3), crnn.build_gru_state_dict(4), crnn.build_decoder(6))
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(NotImplementedError):
+        RnnEncoder(-1, 2048, 2048, bidirectional=False, hidden_size=256)
