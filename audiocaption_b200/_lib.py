@@ -45,6 +45,14 @@ _SIGS = {
     "ac_bigru_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "ac_bigru_fwd": (C.c_int, [C.c_void_p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                C.c_void_p]),
+    "ac_bah_num_tensors": (C.c_int, []),
+    "ac_bah_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ac_bah_destroy": (None, [C.c_void_p]),
+    "ac_bah_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "ac_bah_greedy": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_bah_beam": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                              C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ac_effb2_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ac_effb2_destroy": (None, [C.c_void_p]),
     "ac_effb2_num_tensors": (C.c_int, []),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libaudiocaption_b200.so")
-SOURCES = ["capi.cu", "logmel.cu", "gemm.cu", "gemm_tc.cu", "dwconv_tma.cu", "effb2.cu", "cnn14.cu", "bigru.cu", "trm_decode.cu"]
+SOURCES = ["capi.cu", "logmel.cu", "gemm.cu", "gemm_tc.cu", "dwconv_tma.cu", "effb2.cu", "cnn14.cu", "bigru.cu", "trm_decode.cu", "bah_decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -52,7 +52,7 @@ class CaptionModel(nn.Module, CaptionMetaMixin):
             forward_dict = {"mode": "inference"}
             default_args = {"sample_method": "greedy", "max_length": self.max_length, "temp": 1.0}
             for key in self.inference_forward_keys:
-                forward_dict[key] = input_dict.get(key, default_args[key])
+                forward_dict[key] = input_dict[key] if key in input_dict else default_args[key]
             if forward_dict["sample_method"] == "beam":
                 forward_dict["beam_size"] = input_dict.get("beam_size", 3)
                 if input_dict.get("n_best", False):

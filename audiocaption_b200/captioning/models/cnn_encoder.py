@@ -349,14 +349,15 @@ class Cnn14Encoder(nn.Module):
         return self.melspec_extractor(wav)[0]
 
     def forward(self, input_dict):
-        wav = input_dict["wav"]
+        # the HF copy (hf_wrapper.py:1259-1261) receives the log-mel as `lms`, the training class the waveform
+        wav = input_dict["lms"] if "lms" in input_dict else input_dict["wav"]
         wav_len = input_dict["wav_len"]
         if self.training and input_dict.get("specaug", False):
             raise NotImplementedError("SpecAugment (training) is out of scope of the B200 inference path")
         require_cuda(wav, "Cnn14Encoder.forward")
         l = _lib.lib()
         with torch.cuda.device(wav.device):
-            lms = self.log_mel(wav)
+            lms = wav.float().contiguous() if "lms" in input_dict else self.log_mel(wav)
             B, F, T = lms.shape
             Tp = l.ac_cnn14_out_frames(T)
             wave_length = torch.as_tensor(wav_len)

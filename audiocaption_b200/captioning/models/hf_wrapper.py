@@ -10,8 +10,14 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .base import CaptionMetaMixin
-from .cnn_encoder import EfficientNetB2
+import ctypes
+
+from ... import _lib
+from . import BaseDecoder
+from ._native import Workspace, params_signature, require_cuda, to_device_async
+from .base import CaptionMetaMixin, CaptionModel
+from .cnn_encoder import Cnn14Encoder, EfficientNetB2
+from .rnn_encoder import RnnEncoder
 from .transformer_decoder import TransformerDecoder
 from .transformer_model import TransformerModel
 
@@ -131,3 +137,224 @@ class Effb2TrmCaptioningModel(nn.Module):
         done = torch.cuda.Event()
         done.record(cur)
         return PendingCaptions(seq_host, done)
+
+
+# ----------------------------------------------------------------------------- temporal GRU captioner
+class Cnn14RnnEncoder(nn.Module):
+    """hf_wrapper.py:1350-1374."""
+
+    def __init__(self, sample_rate, rnn_bidirectional, rnn_hidden_size, rnn_dropout, rnn_num_layers):
+        super().__init__()
+        self.cnn = Cnn14Encoder(sample_rate=sample_rate)
+        self.rnn = RnnEncoder(-1, 2048, 2048, bidirectional=rnn_bidirectional, hidden_size=rnn_hidden_size,
+                              dropout=rnn_dropout, num_layers=rnn_num_layers)
+
+    def forward(self, input_dict):
+        output_dict = self.cnn(input_dict)
+        output_dict["attn"] = output_dict["attn_emb"]
+        output_dict["attn_len"] = output_dict["attn_emb_len"]
+        del output_dict["attn_emb"], output_dict["attn_emb_len"]
+        return self.rnn(output_dict)
+
+
+class Seq2SeqAttention(nn.Module):
+    """Parameter holder of hf_wrapper.py:1377-1414."""
+
+    def __init__(self, hs_enc, hs_dec, attn_size):
+        super().__init__()
+        self.h2attn = nn.Linear(hs_enc + hs_dec, attn_size)
+        self.v = nn.Parameter(torch.randn(attn_size))
+
+
+class TemporalBahAttnDecoder(BaseDecoder):
+    """hf_wrapper.py:1417-1554 (`RnnDecoder` -> `BahAttnCatFcDecoder` -> `TemporalBahAttnDecoder`): parameters under the
+    reference's state_dict names; the decode loops run in csrc/bah_decode.cu (single launch, GRU state on chip)."""
+
+    def __init__(self, emb_dim, vocab_size, fc_emb_dim, attn_emb_dim, dropout, d_model, **kwargs):
+        super().__init__(emb_dim, vocab_size, fc_emb_dim, attn_emb_dim, dropout)
+        self.d_model = d_model
+        self.num_layers = kwargs.get("num_layers", 1)
+        self.bidirectional = kwargs.get("bidirectional", False)
+        self.rnn_type = kwargs.get("rnn_type", "GRU")
+        attn_size = kwargs.get("attn_size", d_model)
+        if (self.rnn_type != "GRU" or self.num_layers != 1 or self.bidirectional
+                or not (emb_dim == d_model == attn_size == fc_emb_dim == attn_emb_dim == 512)):
+            raise NotImplementedError("the B200 GRU-attention decoder is built for the released configuration "
+                                      "(1-layer GRU, all widths 512: Cnn14RnnTempAttnGruConfig)")
+        self.classifier = nn.Linear(d_model, vocab_size)
+        self.model = nn.GRU(input_size=emb_dim * 3, hidden_size=d_model, batch_first=True, num_layers=1)
+        self.attn = Seq2SeqAttention(attn_emb_dim, d_model, attn_size)
+        self.fc_proj = nn.Linear(fc_emb_dim, emb_dim)
+        self.ctx_proj = nn.Linear(attn_emb_dim, emb_dim)
+        self.temporal_embedding = nn.Embedding(4, emb_dim)
+        self._ws = Workspace()
+        self._handle = None
+        self._sig = None
+
+    def _tensors(self):
+        return [self.word_embedding.weight, self.classifier.weight, self.classifier.bias, self.model.weight_ih_l0,
+                self.model.weight_hh_l0, self.model.bias_ih_l0, self.model.bias_hh_l0, self.attn.v,
+                self.attn.h2attn.weight, self.attn.h2attn.bias, self.fc_proj.weight, self.fc_proj.bias,
+                self.ctx_proj.weight, self.ctx_proj.bias, self.temporal_embedding.weight]
+
+    def _dec(self):
+        tensors = self._tensors()
+        sig = params_signature(tensors)
+        if self._handle is None or sig != self._sig:
+            self.release()
+            ts = [t.detach().float().contiguous() for t in tensors]
+            for t in ts:
+                require_cuda(t, "TemporalBahAttnDecoder parameters")
+            ptrs, numels, n = _lib.tensor_table(ts)
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().ac_bah_create(ptrs, numels, n, self.vocab_size, _lib.current_stream(), ctypes.byref(h)),
+                       "ac_bah_create")
+            self._handle, self._sig = h, sig
+        return self._handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib().ac_bah_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _prep(self, fc_emb, attn_emb, attn_emb_len, temporal_tag):
+        require_cuda(attn_emb, "TemporalBahAttnDecoder")
+        if self.training:
+            raise NotImplementedError("the B200 decoder implements the eval-mode (inference) path")
+        dev = attn_emb.device
+        lens = to_device_async(torch.as_tensor(attn_emb_len), dev, torch.int64).contiguous()
+        tags = to_device_async(torch.as_tensor(temporal_tag), dev, torch.int64).contiguous()
+        return fc_emb.float().contiguous(), attn_emb.float().contiguous(), lens, tags
+
+    def greedy(self, fc_emb, attn_emb, attn_emb_len, temporal_tag, max_length, start_idx, end_idx, need_logit=True):
+        fc_emb, attn_emb, lens, tags = self._prep(fc_emb, attn_emb, attn_emb_len, temporal_tag)
+        B, T, _ = attn_emb.shape
+        dev = attn_emb.device
+        l = _lib.lib()
+        with torch.cuda.device(dev):
+            dec = self._dec()
+            seq = torch.empty(B, max_length, dtype=torch.int64, device=dev)
+            logprob = torch.zeros(B, max_length, dtype=torch.float32, device=dev)
+            logit = torch.zeros(B, max_length, self.vocab_size, device=dev) if need_logit else None
+            nbytes = l.ac_bah_workspace_bytes(dec, B, T)
+            ws = self._ws.get(nbytes, dev)
+            _lib.check(l.ac_bah_greedy(dec, _lib.ptr(fc_emb), _lib.ptr(attn_emb), _lib.ptr(lens), _lib.ptr(tags), B, T,
+                                       max_length, start_idx, end_idx, _lib.ptr(seq), _lib.ptr(logprob), _lib.ptr(logit),
+                                       _lib.ptr(ws), nbytes, _lib.current_stream()), "ac_bah_greedy")
+        return {"seq": seq, "sampled_logprob": logprob, "logit": logit}
+
+    def beam_search(self, fc_emb, attn_emb, attn_emb_len, temporal_tag, max_length, beam_size, temp, start_idx, end_idx):
+        fc_emb, attn_emb, lens, tags = self._prep(fc_emb, attn_emb, attn_emb_len, temporal_tag)
+        B, T, _ = attn_emb.shape
+        dev = attn_emb.device
+        l = _lib.lib()
+        with torch.cuda.device(dev):
+            dec = self._dec()
+            seq = torch.empty(B, max_length, dtype=torch.int64, device=dev)
+            nbytes = l.ac_bah_workspace_bytes(dec, B * beam_size, T)
+            ws = self._ws.get(nbytes, dev)
+            _lib.check(l.ac_bah_beam(dec, _lib.ptr(fc_emb), _lib.ptr(attn_emb), _lib.ptr(lens), _lib.ptr(tags), B, T,
+                                     max_length, beam_size, float(temp), start_idx, end_idx, _lib.ptr(seq), _lib.ptr(ws),
+                                     nbytes, _lib.current_stream()), "ac_bah_beam")
+        return {"seq": seq}
+
+    def forward(self, input_dict):
+        raise NotImplementedError("single-step TemporalBahAttnDecoder.forward is the training-time call; inference goes "
+                                  "through greedy()/beam_search() (whole decode in one launch)")
+
+
+class TemporalSeq2SeqAttnModel(CaptionModel):
+    """hf_wrapper.py:1557-1788 (`Seq2SeqAttnModel` + `TemporalSeq2SeqAttnModel`), inference modes greedy and beam."""
+
+    def __init__(self, encoder, decoder, **kwargs):
+        if not hasattr(self, "compatible_decoders"):
+            self.compatible_decoders = (TemporalBahAttnDecoder,)
+        super().__init__(encoder, decoder, **kwargs)
+        self.train_forward_keys = ["cap", "cap_len", "ss_ratio", "temporal_tag"]
+        self.inference_forward_keys = ["sample_method", "max_length", "temp", "temporal_tag"]
+
+    def stepwise_forward(self, input_dict):
+        out = self.decoder.greedy(input_dict["fc_emb"], input_dict["attn_emb"], input_dict["attn_emb_len"],
+                                  input_dict["temporal_tag"], input_dict["max_length"], self.start_idx, self.end_idx,
+                                  need_logit=input_dict.get("need_logit", True))
+        if not input_dict.get("_device_seq", False):
+            out["seq"] = out["seq"].cpu()
+            out["sampled_logprob"] = out["sampled_logprob"].cpu()
+        return out
+
+    def beam_search(self, input_dict):
+        out = self.decoder.beam_search(input_dict["fc_emb"], input_dict["attn_emb"], input_dict["attn_emb_len"],
+                                       input_dict["temporal_tag"], input_dict["max_length"], input_dict["beam_size"],
+                                       input_dict["temp"], self.start_idx, self.end_idx)
+        if not input_dict.get("_device_seq", False):
+            out["seq"] = out["seq"].cpu()
+        return out
+
+
+class Cnn14RnnTempAttnGruConfig:
+    """hf_wrapper.py:1862-1894."""
+
+    def __init__(self, sample_rate: int = 32000, encoder_rnn_bidirectional: bool = True, encoder_rnn_hidden_size: int = 256,
+                 encoder_rnn_dropout: float = 0.5, encoder_rnn_num_layers: int = 3, decoder_emb_dim: int = 512,
+                 vocab_size: int = 4981, fc_emb_dim: int = 512, attn_emb_dim: int = 512, decoder_rnn_type: str = "GRU",
+                 decoder_num_layers: int = 1, decoder_d_model: int = 512, decoder_dropout: float = 0.5, **kwargs):
+        self.sample_rate = sample_rate
+        self.encoder_rnn_bidirectional = encoder_rnn_bidirectional
+        self.encoder_rnn_hidden_size = encoder_rnn_hidden_size
+        self.encoder_rnn_dropout = encoder_rnn_dropout
+        self.encoder_rnn_num_layers = encoder_rnn_num_layers
+        self.decoder_emb_dim = decoder_emb_dim
+        self.vocab_size = vocab_size
+        self.fc_emb_dim = fc_emb_dim
+        self.attn_emb_dim = attn_emb_dim
+        self.decoder_rnn_type = decoder_rnn_type
+        self.decoder_num_layers = decoder_num_layers
+        self.decoder_d_model = decoder_d_model
+        self.decoder_dropout = decoder_dropout
+
+
+class Cnn14RnnTempAttnGruModel(nn.Module):
+    """hf_wrapper.py:1897-1974 WITHOUT the SED tagger (`sed_model`, Cnn8rnnSedModel, is not built): `temporal_tag` must be
+    given and is used as is -- the reference would lower it to min(temporal_tag, SED tag).  state_dict keys of the
+    captioner (`melspec_extractor.*`, `cap_model.*`) equal the reference's; load with strict=False to skip `sed_model.*`."""
+    config_class = Cnn14RnnTempAttnGruConfig
+
+    def __init__(self, config=None):
+        super().__init__()
+        config = config or Cnn14RnnTempAttnGruConfig()
+        self.config = config
+        encoder = Cnn14RnnEncoder(sample_rate=config.sample_rate, rnn_bidirectional=config.encoder_rnn_bidirectional,
+                                  rnn_hidden_size=config.encoder_rnn_hidden_size, rnn_dropout=config.encoder_rnn_dropout,
+                                  rnn_num_layers=config.encoder_rnn_num_layers)
+        decoder = TemporalBahAttnDecoder(emb_dim=config.decoder_emb_dim, vocab_size=config.vocab_size,
+                                         fc_emb_dim=config.fc_emb_dim, attn_emb_dim=config.attn_emb_dim,
+                                         rnn_type=config.decoder_rnn_type, num_layers=config.decoder_num_layers,
+                                         d_model=config.decoder_d_model, dropout=config.decoder_dropout)
+        self.melspec_extractor = encoder.cnn.melspec_extractor.__class__(
+            config.sample_rate, 32 * config.sample_rate // 1000, 10 * config.sample_rate // 1000, 50,
+            {32000: 14000, 16000: 8000}[config.sample_rate], 64, norm="slaney", mel_scale="slaney")
+        self.cap_model = TemporalSeq2SeqAttnModel(encoder, decoder)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward(self, audio, audio_length, temporal_tag=None, sample_method: str = "beam", beam_size: int = 3,
+                max_length: int = 20, temp: float = 1.0):
+        if temporal_tag is None:
+            raise NotImplementedError("the SED tagger that derives temporal_tag from the audio (hf_wrapper.py:1791-1859) "
+                                      "is not built: pass temporal_tag")
+        dev = self.device
+        lms, _ = self.melspec_extractor(audio.to(dev, non_blocking=True))
+        input_dict = {"lms": lms, "wav_len": audio_length, "temporal_tag": torch.as_tensor(temporal_tag), "specaug": False,
+                      "mode": "inference", "sample_method": sample_method, "max_length": max_length, "temp": temp,
+                      "need_logit": False}
+        if sample_method == "beam":
+            input_dict["beam_size"] = beam_size
+        return self.cap_model(input_dict)["seq"].cpu()

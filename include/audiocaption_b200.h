@@ -38,6 +38,7 @@ typedef struct ac_effb2 ac_effb2_t;
 typedef struct ac_trm ac_trm_t;
 typedef struct ac_cnn14 ac_cnn14_t;
 typedef struct ac_bigru ac_bigru_t;
+typedef struct ac_bah ac_bah_t;
 
 int ac_version(void);
 const char* ac_last_error(void);
@@ -203,6 +204,33 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb_dev, const int64_t* a
  * (0 step start; per layer l: 1+12l .. 12+12l around the six GEMVs and their cluster barriers; 40 classifier start,
  * 41 classifier done, 42 arg-max done).  out_host (nullable): 64 int64. */
 int ac_trm_trace(int on, long long* out_host);
+
+/* ------------------------------------------------------------------ temporal Bahdanau-attention GRU decoder
+ * Replaces captioning/models/hf_wrapper.py:1377-1414 (`Seq2SeqAttention`), :1444-1554 (`BahAttnCatFcDecoder`,
+ * `TemporalBahAttnDecoder.forward`) and the decode glue :1557-1788 (`Seq2SeqAttnModel`, `TemporalSeq2SeqAttnModel`)
+ * under `CaptionModel.stepwise_forward` / `beam_search` (captioning/models/base.py:152-218, 254-361), eval mode.
+ * All widths (embedding, GRU hidden, attention, memory, fc) are 512 as in `Cnn14RnnTempAttnGruConfig`.
+ * tensors_dev (15, the decoder's state_dict order): word_embedding.weight [V,512], classifier.weight [V,512],
+ * classifier.bias [V], model.weight_ih_l0 [1536,1536], model.weight_hh_l0 [1536,512], model.bias_ih_l0,
+ * model.bias_hh_l0, attn.v [512], attn.h2attn.weight [512,1024], attn.h2attn.bias, fc_proj.weight [512,512],
+ * fc_proj.bias, ctx_proj.weight [512,512], ctx_proj.bias, temporal_embedding.weight [4,512]. */
+int ac_bah_num_tensors(void);
+int ac_bah_create(const float* const* tensors_dev, const int64_t* numels, int n_tensors, int vocab, void* stream,
+                  ac_bah_t** out);
+void ac_bah_destroy(ac_bah_t* dec);
+/* rows = batch for greedy, batch * beam for beam search */
+size_t ac_bah_workspace_bytes(const ac_bah_t* dec, int rows, int T);
+/* fc_emb_dev [batch,512], attn_emb_dev [batch,T,512], lens_dev / tags_dev [batch] int64 (tags in 0..3) ->
+ * seq_dev [batch,max_len] int64 (rows that emitted <end> stay <end>), logprob_dev [batch,max_len] (nullable),
+ * logit_dev [batch,max_len,V] (nullable; when given, finished rows keep being evaluated as the reference does). */
+int ac_bah_greedy(const ac_bah_t* dec, const float* fc_emb_dev, const float* attn_emb_dev, const int64_t* lens_dev,
+                  const int64_t* tags_dev, int batch, int T, int max_len, int start_idx, int end_idx,
+                  int64_t* seq_dev, float* logprob_dev, float* logit_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+/* per-clip beam search with the reference's bookkeeping (beam 1..5); the GRU state follows `prev_words_beam`. */
+int ac_bah_beam(const ac_bah_t* dec, const float* fc_emb_dev, const float* attn_emb_dev, const int64_t* lens_dev,
+                const int64_t* tags_dev, int batch, int T, int max_len, int beam, float temp, int start_idx,
+                int end_idx, int64_t* seq_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

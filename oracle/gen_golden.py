@@ -130,13 +130,51 @@ def cnn14rnn_trm(cnn_seed=3, rnn_seed=4, dec_seed=6, batch=4, n=96000):
         beam3_seq=b3["seq"].numpy(), greedy_stable=stable["greedy"].numpy(), beam3_stable=stable["beam3"].numpy())
 
 
+def temp_gru(seed=8, mem_seed=1, batch=8, T=9):
+    """Golden token ids of the reference's TemporalSeq2SeqAttnModel + TemporalBahAttnDecoder (hf_wrapper.py:1502-1788) on
+    seeded decoder weights and seeded encoder outputs: greedy, beam 3, beam 4."""
+    import torch.nn as nn
+    from . import bah_decoder as bd
+    hf = ref_import.load("captioning.models.hf_wrapper")
+    dec = hf.TemporalBahAttnDecoder(emb_dim=512, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, rnn_type="GRU",
+                                    num_layers=1, d_model=512, dropout=0.5)
+    dec.load_state_dict(bd.build_state_dict(seed), strict=True)
+    model = hf.TemporalSeq2SeqAttnModel(nn.Identity(), dec).eval()
+    fc, attn, lens, tags = bd.synth_memory(mem_seed, batch, T)
+
+    def run(attn_, fc_, method, beam=None):
+        d = {"mode": "inference", "sample_method": method, "max_length": 20, "temp": 1.0, "temporal_tag": tags}
+        if beam:
+            d["beam_size"] = beam
+        with torch.no_grad():
+            return model.forward_decoder(d, {"fc_emb": fc_, "attn_emb": attn_, "attn_emb_len": lens})
+    g, b3, b4 = run(attn, fc, "greedy"), run(attn, fc, "beam", 3), run(attn, fc, "beam", 4)
+    stable = {k: torch.ones(batch, dtype=torch.bool) for k in ("greedy", "beam3", "beam4")}
+    gen = torch.Generator().manual_seed(23)
+    for _ in range(8):
+        pa = attn * (1 + 1e-3 * torch.randn(attn.shape, generator=gen))
+        pf = fc * (1 + 1e-3 * torch.randn(fc.shape, generator=gen))
+        stable["greedy"] &= (run(pa, pf, "greedy")["seq"] == g["seq"]).all(1)
+        stable["beam3"] &= (run(pa, pf, "beam", 3)["seq"] == b3["seq"]).all(1)
+        stable["beam4"] &= (run(pa, pf, "beam", 4)["seq"] == b4["seq"]).all(1)
+    print("temp_gru stable", {k: v.tolist() for k, v in stable.items()})
+    print("greedy\n", g["seq"], "\nbeam4\n", b4["seq"])
+    np.savez_compressed(
+        os.path.join(OUT, "temp_gru.npz"), seed=seed, mem_seed=mem_seed, batch=batch, T=T, lens=lens.numpy(), tags=tags.numpy(),
+        greedy_seq=g["seq"].numpy(), greedy_logit0=g["logit"][:, :2].numpy(), greedy_logprob=g["sampled_logprob"].numpy(),
+        beam3_seq=b3["seq"].numpy(), beam4_seq=b4["seq"].numpy(), greedy_stable=stable["greedy"].numpy(),
+        beam3_stable=stable["beam3"].numpy(), beam4_stable=stable["beam4"].numpy())
+
+
 if __name__ == "__main__":
     import sys
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm"]
+    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm", "temp_gru"]
     if "effb2_trm" in which:
         effb2_trm()
     if "cnn14" in which:
         cnn14()
     if "cnn14rnn_trm" in which:
         cnn14rnn_trm()
+    if "temp_gru" in which:
+        temp_gru()

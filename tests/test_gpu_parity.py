@@ -517,3 +517,88 @@ def test_cnn14rnn_trm_matches_golden(crnn_mirror):
     assert np.abs(out["logit"][:, :2].cpu().numpy() - g["greedy_logit0"]).max() < 2e-3
     st = g["beam3_stable"]
     assert (b3["seq"].numpy()[st] == g["beam3_seq"][st]).all()
+
+
+# ------------------------------------------------------------------ temporal GRU-attention decoder (rows A11-A13)
+@pytest.fixture(scope="module")
+def temp_gru():
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    from oracle import bah_decoder as bd
+    g = np.load(__file__.rsplit("/", 1)[0] + "/golden/temp_gru.npz")
+    sd = bd.build_state_dict(int(g["seed"]))
+    dec = hw.TemporalBahAttnDecoder(emb_dim=512, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, rnn_type="GRU",
+                                    num_layers=1, d_model=512, dropout=0.5).eval()
+    dec.load_state_dict(sd, strict=True)
+    return dec.to(DEV), sd, g
+
+
+def test_temp_gru_decoder_matches_golden(temp_gru):
+    """Greedy / beam-3 / beam-4 token ids of the GRU-attention decoder vs the reference's own output (exact on the
+    numerically stable rows), first-step logits within 2e-4, log-probs within 1e-4."""
+    from oracle import bah_decoder as bd
+    dec, sd, g = temp_gru
+    fc, attn, lens, tags = bd.synth_memory(int(g["mem_seed"]), int(g["batch"]), int(g["T"]))
+    out = dec.greedy(fc.to(DEV), attn.to(DEV), lens, tags, 20, 1, 2)
+    seq = out["seq"].cpu().numpy()
+    st = g["greedy_stable"]
+    assert (seq[st] == g["greedy_seq"][st]).all(), (seq, g["greedy_seq"])
+    assert np.abs(out["logit"][:, :2].cpu().numpy() - g["greedy_logit0"]).max() < 2e-4
+    live = np.cumsum(g["greedy_seq"] == 2, axis=1) <= 1                   # the reference stops writing after <end>
+    assert np.abs(out["sampled_logprob"].cpu().numpy() - g["greedy_logprob"])[live & st[:, None]].max() < 1e-4
+    lean = dec.greedy(fc.to(DEV), attn.to(DEV), lens, tags, 20, 1, 2, need_logit=False)["seq"].cpu().numpy()
+    assert (lean == seq).all()                                            # early-exit path gives the same ids
+    for beam in (3, 4):
+        b = dec.beam_search(fc.to(DEV), attn.to(DEV), lens, tags, 20, beam, 1.0, 1, 2)["seq"].cpu().numpy()
+        st = g[f"beam{beam}_stable"]
+        assert (b[st] == g[f"beam{beam}_seq"][st]).all(), (beam, b, g[f"beam{beam}_seq"])
+
+
+@pytest.mark.parametrize("B,T,beam", [(1, 31, 1), (5, 31, 2), (19, 17, 4), (64, 31, 5)])
+def test_temp_gru_decoder_matches_oracle(temp_gru, B, T, beam):
+    """Random memories of the benchmark shape vs the oracle: rows whose oracle caption survives a 1e-3 perturbation of
+    the memory must match exactly."""
+    from oracle import bah_decoder as bd
+    dec, sd, _ = temp_gru
+    fc, attn, lens, tags = bd.synth_memory(100 + B, B, T)
+    ref = bd.greedy_decode(sd, fc, attn, lens, tags, 20)["seq"]
+    pert = bd.greedy_decode(sd, fc * 1.001, attn * 0.999, lens, tags, 20)["seq"]
+    st = (ref == pert).all(1).numpy()
+    got = dec.greedy(fc.to(DEV), attn.to(DEV), lens, tags, 20, 1, 2, need_logit=False)["seq"].cpu().numpy()
+    assert st.mean() > 0.5 and (got[st] == ref.numpy()[st]).all()
+    nb = min(B, 6)                                                        # the per-clip oracle loop is slow
+    refb = bd.beam_search(sd, fc[:nb], attn[:nb], lens[:nb], tags[:nb], beam, 20, 1.0)["seq"]
+    pertb = bd.beam_search(sd, fc[:nb] * 1.001, attn[:nb] * 0.999, lens[:nb], tags[:nb], beam, 20, 1.0)["seq"]
+    stb = (refb == pertb).all(1).numpy()
+    gotb = dec.beam_search(fc.to(DEV), attn.to(DEV), lens, tags, 20, beam, 1.0, 1, 2)["seq"].cpu().numpy()
+    assert (gotb[:nb][stb] == refb.numpy()[stb]).all()
+
+
+def test_temp_gru_model_end_to_end(temp_gru):
+    """Cnn14RnnTempAttnGruModel.forward (log-mel -> Cnn14 -> bi-GRU -> GRU-attention beam search) vs the oracle chain on
+    two 2 s clips with given temporal tags."""
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    from oracle import bah_decoder as bd, cnn14 as oc, crnn
+    _, dsd, _ = temp_gru
+    cnn_sd, rnn_sd = oc.build_state_dict(3), crnn.build_gru_state_dict(4)
+    m = hw.Cnn14RnnTempAttnGruModel().eval()
+    sd = {f"cap_model.encoder.cnn.{k}": v for k, v in cnn_sd.items()}
+    sd.update({f"cap_model.encoder.rnn.{k}": v for k, v in rnn_sd.items()})
+    sd.update({f"cap_model.decoder.{k}": v for k, v in dsd.items()})
+    sd.update({f"melspec_extractor.{k[len('melspec_extractor.'):]}": v for k, v in cnn_sd.items() if k.startswith("melspec")})
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    wav, lens = cm.synth_wav(3, 64000, seed=21, ragged=True, varied=True, sample_rate=32000)
+    tags = torch.tensor([1, 3, 0])
+    enc = crnn.crnn_encoder(cnn_sd, rnn_sd, wav, lens)
+    for method, beam in (("greedy", None), ("beam", 3)):
+        if beam:
+            ref = bd.beam_search(dsd, enc["fc_emb"], enc["attn_emb"], enc["attn_emb_len"], tags, beam, 20, 1.0)["seq"]
+            pert = bd.beam_search(dsd, enc["fc_emb"] * 1.001, enc["attn_emb"] * 0.999, enc["attn_emb_len"], tags, beam, 20, 1.0)["seq"]
+        else:
+            ref = bd.greedy_decode(dsd, enc["fc_emb"], enc["attn_emb"], enc["attn_emb_len"], tags, 20)["seq"]
+            pert = bd.greedy_decode(dsd, enc["fc_emb"] * 1.001, enc["attn_emb"] * 0.999, enc["attn_emb_len"], tags, 20)["seq"]
+        with torch.no_grad():
+            got = m(wav, lens, temporal_tag=tags, sample_method=method, beam_size=beam or 3, max_length=20)
+        assert got.shape == (3, 20) and not got.is_cuda
+        st = (ref == pert).all(1)
+        assert (got[st] == ref[st]).all(), (method, got, ref)

@@ -302,3 +302,63 @@ def test_cnn14rnn_trm_mirror_state_dict_matches_reference_layout():
     m.load_state_dict(sd, strict=True)
     with pytest.raises(NotImplementedError):
         RnnEncoder(-1, 2048, 2048, bidirectional=False, hidden_size=256)
+
+
+# ------------------------------------------------------------------ temporal GRU-attention decoder (rows A11-A13)
+def _golden_temp_gru():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "temp_gru.npz"))
+
+
+def test_temp_gru_oracle_matches_golden():
+    """oracle/bah_decoder.py against the token ids produced by the reference's TemporalSeq2SeqAttnModel."""
+    from oracle import bah_decoder as bd
+    g = _golden_temp_gru()
+    sd = bd.build_state_dict(int(g["seed"]))
+    fc, attn, lens, tags = bd.synth_memory(int(g["mem_seed"]), int(g["batch"]), int(g["T"]))
+    assert lens.tolist() == g["lens"].tolist() and tags.tolist() == g["tags"].tolist()
+    out = bd.greedy_decode(sd, fc, attn, lens, tags, 20)
+    st = g["greedy_stable"]
+    assert st.sum() >= 4 and (out["seq"].numpy()[st] == g["greedy_seq"][st]).all()
+    assert np.abs(out["logit"][:, :2].numpy() - g["greedy_logit0"]).max() < 1e-4
+    for beam in (3, 4):
+        b = bd.beam_search(sd, fc, attn, lens, tags, beam, 20, 1.0)
+        st = g[f"beam{beam}_stable"]
+        assert st.sum() >= 4 and (b["seq"].numpy()[st] == g[f"beam{beam}_seq"][st]).all()
+    ends = [(r.tolist() + [2]).index(2) for r in g["greedy_seq"]]
+    assert len(set(ends)) >= 3                                            # early stop is exercised
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_temp_gru_oracle_matches_imported_reference():
+    import torch.nn as nn
+    from oracle import bah_decoder as bd
+    hf = ref_import.load("captioning.models.hf_wrapper")
+    dec = hf.TemporalBahAttnDecoder(emb_dim=512, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, rnn_type="GRU",
+                                    num_layers=1, d_model=512, dropout=0.5)
+    assert list(dec.state_dict().keys()) == bd.KEYS
+    sd = bd.build_state_dict(11)
+    dec.load_state_dict(sd, strict=True)
+    model = hf.TemporalSeq2SeqAttnModel(nn.Identity(), dec).eval()
+    fc, attn, lens, tags = bd.synth_memory(5, 4, 7)
+    enc = {"fc_emb": fc, "attn_emb": attn, "attn_emb_len": lens}
+    with torch.no_grad():
+        rg = model.forward_decoder({"mode": "inference", "sample_method": "greedy", "max_length": 12, "temp": 1.0,
+                                    "temporal_tag": tags}, dict(enc))
+        rb = model.forward_decoder({"mode": "inference", "sample_method": "beam", "beam_size": 4, "max_length": 12, "temp": 1.0,
+                                    "temporal_tag": tags}, dict(enc))
+    og = bd.greedy_decode(sd, fc, attn, lens, tags, 12)
+    ob = bd.beam_search(sd, fc, attn, lens, tags, 4, 12, 1.0)
+    assert (rg["seq"] == og["seq"]).all() and (rb["seq"] == ob["seq"]).all()
+    assert (rg["logit"][:, 0] - og["logit"][:, 0]).abs().max() < 1e-4
+
+
+def test_temp_gru_mirror_state_dict_matches_reference_layout():
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    from oracle import bah_decoder as bd
+    m = hw.Cnn14RnnTempAttnGruModel()
+    dec_keys = [k[len("cap_model.decoder."):] for k in m.state_dict() if k.startswith("cap_model.decoder.")]
+    assert dec_keys == bd.KEYS
+    m.cap_model.decoder.load_state_dict(bd.build_state_dict(8), strict=True)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 32000), [32000])                                   # SED tagger not built: tag required
