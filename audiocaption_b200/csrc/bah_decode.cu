@@ -13,11 +13,12 @@
 //   * W_ih[:, 512:1024] . ctx_proj folds into ONE [1536 x 512] matrix applied to ctx;
 //   * W_ih[:, 1024:1536] . fc_proj(fc_emb) + all input-side biases is one vector per clip (two small GEMMs per call).
 // What remains per step is three GEMVs (W_q h, W_hh h, M_c ctx: 7.3 MB of weights) + the classifier (10.2 MB), streamed
-// from L2 by a 2-CTA cluster per clip exactly like the Transformer decoder (decode_common.cuh: each CTA computes half
+// from L2 by a 1/2/4-CTA cluster per clip (chosen from the batch size) exactly like the Transformer decoder (decode_common.cuh: each CTA computes half
 // of the output columns and writes them into both CTAs' shared memory); attention, the cell update and the
 // arg-max / top-k bookkeeping run redundantly in both CTAs.  Beam search: the R beams of a clip are the R rows of one
 // cluster (every weight load is shared by R rows); the GRU state follows `prev_words_beam` (hf_wrapper.py:1656-1661).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -31,7 +32,13 @@ constexpr int BH = 512;            // embedding = hidden = attention = memory = 
 constexpr int BG = 3 * BH;
 constexpr int kBahMaxT = 64;       // memory frames
 constexpr int kBahMaxLen = 64;     // decode steps
-constexpr int kBahCluster = 2;
+// CTAs per clip: small batches spread each clip's 17.5 MB of weights per step over more SMs, large ones keep one wave
+static int bah_cluster_size(int clips) {
+    if (const char* e = getenv("AC_BAH_CLUSTER")) { const int p = atoi(e); if (p == 1 || p == 2 || p == 4 || p == 8) return p; }   // tuning aid
+    // measured on B200 (scripts/bah_time.py): 16 clips beam-4 2.2 ms at P = 4 vs 3.2 ms at P = 2 / 3.3 ms at P = 8;
+    // 128 clips 5.5 ms at P = 1 vs 6.3 ms at P = 2 (a second wave of CTAs costs more than the wider split saves)
+    return clips <= kNumSMs / 4 ? 4 : clips <= kNumSMs / 2 ? 2 : 1;
+}
 
 struct BahW {
     const float* emb_tab;   // [V + 4][BG]  W_ih[:, 0:512] . (word | temporal) embedding
@@ -85,8 +92,11 @@ __device__ __forceinline__ void bah_step(const BahArgs& a, int clip, const int* 
         if (s < len) {
             const float* e = E + (size_t)s * BH;
             const float* q = s_q + r * BH;
-#pragma unroll 4
-            for (int c = lane; c < BH; c += 32) acc = fmaf(__ldg(W.v + c), tanhf(q[c] + __ldg(e + c)), acc);
+            float ev[BH / 32];
+#pragma unroll
+            for (int j = 0; j < BH / 32; ++j) ev[j] = __ldg(e + lane + 32 * j);      // all 16 L2 loads in flight at once
+#pragma unroll
+            for (int j = 0; j < BH / 32; ++j) acc = fmaf(__ldg(W.v + lane + 32 * j), tanhf(q[lane + 32 * j] + ev[j]), acc);
             acc = warp_sum(acc);
         }
         if (lane == 0) s_sc[r * kBahMaxT + s] = s < len ? acc : -1e10f;   // masked_fill(mask == 0, -1e10)
@@ -108,7 +118,13 @@ __device__ __forceinline__ void bah_step(const BahArgs& a, int clip, const int* 
         const int r = i / BH, c = i - r * BH;
         const float* sc = s_sc + r * kBahMaxT;
         float acc = 0.f;
-        for (int s = 0; s < len; ++s) acc = fmaf(sc[s], __ldg(enc + (size_t)s * BH + c), acc);
+        for (int s0 = 0; s0 < len; s0 += 8) {                  // 8 independent L2 loads per batch
+            float ev[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ev[j] = s0 + j < len ? __ldg(enc + (size_t)(s0 + j) * BH + c) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(s0 + j < len ? sc[s0 + j] : 0.0f, ev[j], acc);
+        }
         s_ctx[i] = acc;
     }
     __syncthreads();
@@ -132,17 +148,23 @@ __device__ __forceinline__ void bah_step(const BahArgs& a, int clip, const int* 
     __syncthreads();
     for (int i = tid; i < R * BH; i += kThreads) s_h[i] = s_hn[i];
     __syncthreads();
-    // ---- classifier (with bias): each thread owns column quads of the zero-padded [BH][Vp] weight
+    // ---- classifier (with bias): each thread owns column quads of the zero-padded [BH][Vp] weight; when the CTA's
+    // share of the columns is smaller than the block (large clusters) the k range is split across thread groups
     const int V = W.vocab, VC = W.vp >> 2;
     const int vc0 = (int)((int64_t)VC * rank / P), vc1 = (int)((int64_t)VC * (rank + 1) / P);
-    for (int c = vc0 + tid; c < vc1; c += kThreads) {
+    const int ncq = vc1 - vc0;
+    const int KS = ncq >= kThreads ? 1 : max(1, min(kThreads / ncq, 4096 / (4 * ncq)));
+    const int kslice = (BH + KS - 1) / KS;
+    for (int cc = tid; cc < ncq * KS; cc += kThreads) {
+        const int ks = cc / ncq, c = vc0 + (cc - ks * ncq);
+        const int k0 = ks * kslice, k1 = min(BH, k0 + kslice);
         float acc[R][4];
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(W.cls_b) + c);
+        const float4 b4 = ks == 0 ? __ldg(reinterpret_cast<const float4*>(W.cls_b) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < R; ++r) { acc[r][0] = b4.x; acc[r][1] = b4.y; acc[r][2] = b4.z; acc[r][3] = b4.w; }
         const float4* w = reinterpret_cast<const float4*>(W.cls_t) + c;
 #pragma unroll 8
-        for (int k = 0; k < BH; ++k) {
+        for (int k = k0; k < k1; ++k) {
             const float4 wv = __ldg(w + (size_t)k * VC);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -151,11 +173,28 @@ __device__ __forceinline__ void bah_step(const BahArgs& a, int clip, const int* 
                 acc[r][2] = fmaf(wv.z, xv, acc[r][2]); acc[r][3] = fmaf(wv.w, xv, acc[r][3]);
             }
         }
+        if (KS == 1) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (4 * c + q < V) logits[r][4 * c + q] = acc[r][q];
+                for (int q = 0; q < 4; ++q)
+                    if (4 * c + q < V) logits[r][4 * c + q] = acc[r][q];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                *reinterpret_cast<float4*>(s_part + ((size_t)(ks * R + r) * ncq + (c - vc0)) * 4) =
+                    make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
+    }
+    if (KS > 1) {
+        __syncthreads();
+        for (int i = tid; i < R * ncq * 4; i += kThreads) {
+            const int r = i / (ncq * 4), j = i - r * (ncq * 4);
+            float v = 0.f;
+            for (int ks = 0; ks < KS; ++ks) v += s_part[(size_t)(ks * R + r) * ncq * 4 + j];   // fixed order
+            const int n = 4 * vc0 + j;
+            if (n < V) logits[r][n] = v;
+        }
     }
     cluster.sync();   // both halves of the logits (global memory) are visible to both CTAs
 }
@@ -334,10 +373,6 @@ __global__ void bah_transpose_kernel(const float* __restrict__ in, float* __rest
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)rows * cols) out[(i % cols) * ld + i / cols] = in[i];
 }
-__global__ void bah_add_kernel(float* __restrict__ x, const float* __restrict__ y, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] += y[i];
-}
 
 }  // namespace ac
 
@@ -469,6 +504,7 @@ static int bah_prepare(const ac_bah_t* d, const float* fc_emb, const float* attn
 template <typename K>
 static int bah_launch(K kernel, int clusters, size_t smem, cudaStream_t st, const BahArgs& a) {
     AC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int kBahCluster = bah_cluster_size(clusters);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * kBahCluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -23,6 +23,11 @@ Contents
 ``caption_model``    restatement of the Transformer caption decoder and the
                      greedy / beam decoding loops (hf_wrapper.py:389-726,845-1068),
                      pinned against the imported reference (see gen_golden.py).
+``cnn14`` / ``crnn``  Cnn14 body (cnn_encoder.py:32-75,414-464), explicit-loop bi-GRU with packed-sequence
+                     semantics (rnn_encoder.py:34-49, model_util.py:10-27), CrnnEncoder and the
+                     Cnn14Rnn-Transformer captioner; pinned against the imported classes.
+``bah_decoder``      temporal Bahdanau-attention GRU decoder + greedy / beam loops with state re-ordering
+                     (hf_wrapper.py:1377-1788); pinned exactly against the imported classes.
 ``ref_import``       imports the real reference from /root/reference with import
                      stubs (build container only; never used on the GPU box).
 ``gen_golden``       regenerates tests/golden/*.npz from the imported reference.

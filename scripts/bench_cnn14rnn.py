@@ -19,6 +19,8 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--out", default=None)
 ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--decoder", default="trm", choices=["trm", "tempgru"], help="trm: cnn14rnn_trm.yaml; tempgru: HF Cnn14RnnTempAttnGru (config 5)")
+ap.add_argument("--beam", type=int, default=0, help="0 = greedy")
 args = ap.parse_args()
 
 from oracle import cnn14 as oc, crnn, caption_model as cm          # weights + CPU baseline only
@@ -37,14 +39,30 @@ enc = CrnnEncoder(Cnn14Encoder(sample_rate=32000),
                              dropout=0.5, num_layers=3), freeze_cnn=True, freeze_cnn_bn=True)
 model = TransformerModel(enc, TransformerDecoder(emb_dim=256, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512,
                                                  nlayers=2, dropout=0.2)).eval()
-model.load_state_dict(crnn.model_state_dict(cnn_sd, rnn_sd, dec_o), strict=True)
+if args.decoder == "trm":
+    model.load_state_dict(crnn.model_state_dict(cnn_sd, rnn_sd, dec_o), strict=True)
+else:
+    from oracle import bah_decoder as bd
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    dsd = bd.build_state_dict(8)
+    dec = hw.TemporalBahAttnDecoder(emb_dim=512, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, rnn_type="GRU",
+                                    num_layers=1, d_model=512, dropout=0.5)
+    dec.load_state_dict(dsd, strict=True)
+    enc.cnn.load_state_dict(cnn_sd, strict=True)
+    enc.rnn.load_state_dict(rnn_sd, strict=True)
+    model = hw.TemporalSeq2SeqAttnModel(enc, dec).eval()
 model = model.to(dev)
 lib = _lib.lib()
 n_rot = 4                                                   # 4 x 82 MB of input > 126 MB L2
 host = [cm.synth_wav(B, N, seed=i, sample_rate=32000)[0].pin_memory() for i in range(n_rot)]
 devb = [h.to(dev) for h in host]
 lens = torch.full((B,), N, dtype=torch.long)
-base = {"wav_len": lens, "specaug": False, "mode": "inference", "sample_method": "greedy", "max_length": MAX_LEN, "temp": 1.0}
+base = {"wav_len": lens, "specaug": False, "mode": "inference", "sample_method": "beam" if args.beam else "greedy",
+        "max_length": MAX_LEN, "temp": 1.0}
+if args.beam:
+    base["beam_size"] = args.beam
+if args.decoder == "tempgru":
+    base["temporal_tag"] = torch.arange(B) % 4
 
 
 def step_resident(i):
@@ -90,10 +108,10 @@ bf16 = float(peaks.get("bf16_tflops", peaks.get("bf16_dense_tflops", 1593.5)))
 tf32_peak = bf16 / 2
 achieved = 3 * flops * B / (conv_ms * 1e-3) / 1e12          # tf32 tensor-pipe work actually issued (3 MMAs per product)
 out = {
-    "metric": "clips/sec (10s@32kHz clips) Cnn14Rnn-Trm greedy inference", "value": B / (ms / 1e3), "unit": "clips/s",
+    "metric": "clips/sec (10s@32kHz clips) Cnn14Rnn-%s %s inference" % ("Trm" if args.decoder == "trm" else "TempAttnGru", "beam-%d" % args.beam if args.beam else "greedy"), "value": B / (ms / 1e3), "unit": "clips/s",
     "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32",
     "data": "synthetic", "gpu_launches": launches,
-    "config": {"workload": "Cnn14Rnn-Transformer greedy inference, batch=%d x 10 s @ 32 kHz synthetic clips (cnn14rnn_trm.yaml)" % B,
+    "config": {"workload": "Cnn14Rnn-%s %s inference, batch=%d x 10 s @ 32 kHz synthetic clips" % ("Transformer (cnn14rnn_trm.yaml)" if args.decoder == "trm" else "TempAttnGru (HF config, temporal tags given)", "beam-%d" % args.beam if args.beam else "greedy", B),
                "l2": "rotating %d input batches (%d MB)" % (n_rot, n_rot * B * N * 4 // 2 ** 20)},
     "e2e": {"value": B / (ms_e2e / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * N * 4,
             "d2h_bytes_per_step": B * MAX_LEN * 8, "api": "TransformerModel.forward(input_dict), pinned host wav"},
@@ -104,7 +122,7 @@ out = {
                  "peak_source": "MEASURED_PEAKS.json dense bf16 / 2 (kind::tf32 runs at half the bf16 rate)",
                  "kernel_ms_per_step": {k: round(v, 4) for k, v in per.items()}},
 }
-if not args.no_cpu:
+if not args.no_cpu and args.decoder == "trm" and not args.beam:
     torch.set_num_threads(os.cpu_count())
     w1, l1 = cm.synth_wav(1, N, seed=0, sample_rate=32000)
     crnn.caption(cnn_sd, rnn_sd, dec_o, w1[:, :32000], torch.tensor([32000]))       # warm-up
