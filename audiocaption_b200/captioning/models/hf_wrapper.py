@@ -297,6 +297,129 @@ class TemporalSeq2SeqAttnModel(CaptionModel):
         return out
 
 
+class Cnn8rnnSedModel(nn.Module):
+    """hf_wrapper.py:1791-1859: CNN8 + bi-GRU sound-event tagger -> one temporal tag (0..3) per clip.  Parameters under the
+    reference's state_dict names; network and double threshold in csrc/cnn14.cu (`ac_sed_*`), only the 0/1 segment labels
+    come back to the host for the pairwise segment rule (hf_wrapper.py:180-216)."""
+
+    def __init__(self, classes_num):
+        super().__init__()
+        from .cnn_encoder import _BN, _ConvBlock
+        self.time_resolution = 0.01
+        self.interpolate_ratio = 4
+        self.classes_num = classes_num
+        self.bn0 = _BN(64)
+        self.conv_block1 = _ConvBlock(1, 64)
+        self.conv_block2 = _ConvBlock(64, 128)
+        self.conv_block3 = _ConvBlock(128, 256)
+        self.conv_block4 = _ConvBlock(256, 512)
+        self.fc1 = nn.Linear(512, 512, bias=True)
+        self.rnn = nn.GRU(512, 256, bidirectional=True, batch_first=True)
+        self.fc_audioset = nn.Linear(512, classes_num, bias=True)
+        self._ws = Workspace()
+        self._handle = None
+        self._sig = None
+
+    def _tensors(self):
+        ts = [self.bn0.weight, self.bn0.bias, self.bn0.running_mean, self.bn0.running_var]
+        for i in range(1, 5):
+            blk = getattr(self, f"conv_block{i}")
+            ts += [blk.conv1.weight, blk.conv2.weight]
+            for bn in (blk.bn1, blk.bn2):
+                ts += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        ts += [self.fc1.weight, self.fc1.bias]
+        for sfx in ("", "_reverse"):
+            ts += [getattr(self.rnn, f"{n}_l0{sfx}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        return ts + [self.fc_audioset.weight, self.fc_audioset.bias]
+
+    def _net(self):
+        tensors = self._tensors()
+        sig = params_signature(tensors)
+        if self._handle is None or sig != self._sig:
+            self.release()
+            ts = [t.detach().float().contiguous() for t in tensors]
+            for t in ts:
+                require_cuda(t, "Cnn8rnnSedModel parameters")
+            ptrs, numels, n = _lib.tensor_table(ts)
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().ac_sed_create(ptrs, numels, n, self.classes_num, _lib.current_stream(), ctypes.byref(h)),
+                       "ac_sed_create")
+            self._handle, self._sig = h, sig
+        return self._handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib().ac_sed_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _run(self, lms, want_prob):
+        require_cuda(lms, "Cnn8rnnSedModel")
+        if self.training:
+            raise NotImplementedError("the B200 tagger implements the eval-mode (inference) path")
+        lms = lms.float().contiguous()
+        B, F, T = lms.shape
+        l = _lib.lib()
+        dev = lms.device
+        with torch.cuda.device(dev):
+            net = self._net()
+            S = l.ac_sed_segments(T)
+            labels = torch.empty(B, S, self.classes_num, dtype=torch.uint8, device=dev)
+            prob = torch.empty(B, S, self.classes_num, dtype=torch.float32, device=dev) if want_prob else None
+            nbytes = l.ac_sed_workspace_bytes(net, B, F, T)
+            ws = self._ws.get(nbytes, dev)
+            _lib.check(l.ac_sed_fwd(net, _lib.ptr(lms), B, F, T, 0.75, 0.25, _lib.ptr(prob), _lib.ptr(labels), _lib.ptr(ws), nbytes,
+                                    _lib.current_stream()), "ac_sed_fwd")
+        return prob, labels, T
+
+    def forward_prob(self, lms):
+        """{"segmentwise_output" [B, T//4, classes], "framewise_output" [B, T, classes]} as hf_wrapper.py:1823-1859."""
+        seg, _, T = self._run(lms, True)
+        frame = seg.repeat_interleave(self.interpolate_ratio, dim=1)
+        if frame.shape[1] < T:
+            frame = torch.cat((frame, frame[:, -1:].expand(-1, T - frame.shape[1], -1)), dim=1)
+        return {"segmentwise_output": seg, "framewise_output": frame}
+
+    def forward(self, lms):
+        _, labels, T = self._run(lms, False)
+        return decode_segment_labels(labels.cpu().numpy(), T, self.interpolate_ratio, self.time_resolution)
+
+
+def decode_segment_labels(labels, frames_num, ratio=4, time_resolution=0.01, thre=0.5):
+    """`decode_with_timestamps` + `segments_to_temporal_tag` (hf_wrapper.py:180-216) from the 0/1 decisions at SEGMENT
+    resolution [B, S, classes]: a run of segments [s0, s1) is the frame run [ratio*s0, ratio*s1), except that a run
+    reaching the last segment extends to `frames_num` (the reference pads the frame matrix with its last row).  The pairwise
+    rule is evaluated in float64 on onset/offset = frame * time_resolution, exactly the reference's arithmetic."""
+    out = []
+    B, S, C = labels.shape
+    for b in range(B):
+        lab = labels[b].astype(np.int8)
+        pad = np.zeros((1, C), dtype=np.int8)
+        d = np.diff(np.concatenate((pad, lab, pad), axis=0), axis=0)          # +1 at run starts, -1 one past run ends
+        on_s, on_c = np.nonzero(d.T == 1)[::-1]                                # ordered by class, then time (as the reference)
+        off_s, off_c = np.nonzero(d.T == -1)[::-1]
+        assert (on_c == off_c).all()
+        off_f = np.where(off_s == S, frames_num, off_s * ratio)
+        on = (on_s * ratio) * time_resolution
+        off = off_f * time_resolution
+        if len(on) == 0:
+            out.append(0)
+            continue
+        dur = off - on
+        min_dur = np.minimum(dur[:, None], dur[None, :])
+        overlap = off[:, None] - on[None, :]
+        other = on_c[:, None] != on_c[None, :]
+        after = 2 if (other & (overlap < thre * min_dur)).any() else 0
+        whil = 1 if (other & (on[:, None] < on[None, :]) & (overlap > thre * min_dur)).any() else 0
+        out.append(after + whil)
+    return out
+
+
 class Cnn14RnnTempAttnGruConfig:
     """hf_wrapper.py:1862-1894."""
 
@@ -320,9 +443,8 @@ class Cnn14RnnTempAttnGruConfig:
 
 
 class Cnn14RnnTempAttnGruModel(nn.Module):
-    """hf_wrapper.py:1897-1974 WITHOUT the SED tagger (`sed_model`, Cnn8rnnSedModel, is not built): `temporal_tag` must be
-    given and is used as is -- the reference would lower it to min(temporal_tag, SED tag).  state_dict keys of the
-    captioner (`melspec_extractor.*`, `cap_model.*`) equal the reference's; load with strict=False to skip `sed_model.*`."""
+    """hf_wrapper.py:1897-1974: log-mel -> SED tagger -> temporal tag (min with the caller's, if given) -> Cnn14 + bi-GRU
+    encoder -> temporal GRU-attention decoder.  state_dict keys equal the reference's (187 keys)."""
     config_class = Cnn14RnnTempAttnGruConfig
 
     def __init__(self, config=None):
@@ -340,6 +462,7 @@ class Cnn14RnnTempAttnGruModel(nn.Module):
             config.sample_rate, 32 * config.sample_rate // 1000, 10 * config.sample_rate // 1000, 50,
             {32000: 14000, 16000: 8000}[config.sample_rate], 64, norm="slaney", mel_scale="slaney")
         self.cap_model = TemporalSeq2SeqAttnModel(encoder, decoder)
+        self.sed_model = Cnn8rnnSedModel(classes_num=447)
 
     @property
     def device(self):
@@ -347,12 +470,14 @@ class Cnn14RnnTempAttnGruModel(nn.Module):
 
     def forward(self, audio, audio_length, temporal_tag=None, sample_method: str = "beam", beam_size: int = 3,
                 max_length: int = 20, temp: float = 1.0):
-        if temporal_tag is None:
-            raise NotImplementedError("the SED tagger that derives temporal_tag from the audio (hf_wrapper.py:1791-1859) "
-                                      "is not built: pass temporal_tag")
         dev = self.device
         lms, _ = self.melspec_extractor(audio.to(dev, non_blocking=True))
-        input_dict = {"lms": lms, "wav_len": audio_length, "temporal_tag": torch.as_tensor(temporal_tag), "specaug": False,
+        sed_tag = torch.as_tensor(self.sed_model(lms))
+        if temporal_tag is not None:          # hf_wrapper.py:1954-1958: the caller's tag can only lower the SED tag
+            temporal_tag = torch.min(torch.stack([torch.as_tensor(temporal_tag).cpu(), sed_tag], dim=0), dim=0).values
+        else:
+            temporal_tag = sed_tag
+        input_dict = {"lms": lms, "wav_len": audio_length, "temporal_tag": temporal_tag, "specaug": False,
                       "mode": "inference", "sample_method": sample_method, "max_length": max_length, "temp": temp,
                       "need_logit": False}
         if sample_method == "beam":

@@ -111,6 +111,89 @@ cnn14_avgpool_kernel(const float4* __restrict__ in, float4* __restrict__ out, in
                          0.25f * (a.z + bb.z + cc.z + d.z), 0.25f * (a.w + bb.w + cc.w + d.w));
 }
 
+// ConvBlock pooling of the SED tagger (hf_wrapper.py:1204-1212, pool_type 'avg+max'): avg_pool2d + max_pool2d over
+// (ph x pw) windows, stride = window, floor.  in [B, H, W, C] -> out [B, H/ph, W/pw, C]; one float4 per thread.
+__global__ void __launch_bounds__(256)
+cnn_avgmax_pool_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4, int Ho, int Wo, int ph,
+                       int pw, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int64_t b = r / Ho;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = 0; dy < ph; ++dy)
+        for (int dx = 0; dx < pw; ++dx) {
+            const float4 v = __ldg(in + (((size_t)b * H + ho * ph + dy) * W + wo * pw + dx) * C4 + c);
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+        }
+    const float inv = 1.0f / (float)(ph * pw);
+    out[i] = make_float4(sum.x * inv + mx.x, sum.y * inv + mx.y, sum.z * inv + mx.z, sum.w * inv + mx.w);
+}
+
+// y [B, H, W, C] -> out [B, H, C] = mean over W   (torch.mean(x, dim=3) then transpose(1, 2))
+__global__ void __launch_bounds__(256)
+cnn_wmean_kernel(const float4* __restrict__ y, float4* __restrict__ out, int W, int C4, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C4);
+    const int64_t bh = i / C4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < W; ++w) {
+        const float4 v = __ldg(y + ((size_t)bh * W + w) * C4 + c);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float inv = 1.0f / (float)W;
+    out[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+}
+
+// logits [rows, ld] (first `classes` columns valid) -> prob = clamp(sigmoid(logit), 1e-7, 1) in place
+__global__ void sed_sigmoid_kernel(float* __restrict__ x, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) x[i] = fminf(fmaxf(1.0f / (1.0f + expf(-x[i])), 1e-7f), 1.0f);
+}
+
+__global__ void sed_fill_kernel(int64_t* __restrict__ x, int64_t v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+// Double threshold (hysteresis) along time for every (clip, class) column: a maximal run of prob > low is kept when
+// it contains a value > high (hf_wrapper.py:123-162 `double_threshold`; at the repeat-upsampled frame resolution the
+// n_connect = 1 merge can never fire because runs are >= 4 frames apart).  prob [B, S, ld] -> labels [B, S, classes] u8.
+__global__ void sed_hysteresis_kernel(const float* __restrict__ prob, unsigned char* __restrict__ labels, int S, int ld,
+                                      int classes, float high, float low, int total) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = i % classes, b = i / classes;
+    const float* p = prob + (size_t)b * S * ld + c;
+    unsigned char* l = labels + (size_t)b * S * classes + c;
+    int start = -1; bool has_high = false;
+    for (int s = 0; s <= S; ++s) {
+        const float v = s < S ? p[(size_t)s * ld] : -1.0f;
+        if (v > low) {
+            if (start < 0) { start = s; has_high = false; }
+            has_high = has_high || v > high;
+        } else if (start >= 0) {
+            const unsigned char keep = has_high ? 1 : 0;
+            for (int q = start; q < s; ++q) l[(size_t)q * classes] = keep;
+            start = -1;
+        }
+        if (s < S && !(v > low)) l[(size_t)s * classes] = 0;
+    }
+}
+
 // y [B, H, W, C] -> attn_emb [B, H, C] = mean over W (torch.mean(x, dim=3), 'b c t f -> b t c') and
 // pooled [B, C] = max_{t < len} attn_emb + (sum_{t < len} attn_emb) / len   (max_with_lens + mean_with_lens)
 __global__ void __launch_bounds__(128)
@@ -331,6 +414,241 @@ int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int
     GemmArgs g; g.A = pooled; g.W = net->fc_w; g.C = fc_emb; g.M = B; g.N = D; g.K = D; g.cbias = net->fc_b; g.act = ACT_RELU;
     g.tw = &net->fc_tw;
     return gemm_tn(g, st);
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// CNN8 + bi-GRU sound-event tagger of the temporal captioner (SED): captioning/models/hf_wrapper.py:1791-1859
+// `Cnn8rnnSedModel.forward_prob` + the double threshold of :123-162.  Same building blocks as Cnn14: bn0 + first
+// convolution (SIMT), 7 tensor-core 3x3 convolutions, 'avg+max' pooling (2,2) (2,2) (1,2) (1,2), mean over mel,
+// fc1 + ReLU, one bidirectional GRU layer over all T/4 segments (csrc/bigru.cu), fc_audioset + sigmoid + clamp.
+// The reference then repeat-upsamples x4 to frames, pads to the input length and thresholds on the CPU in numpy; here
+// the hysteresis runs on the device at SEGMENT resolution (identical decisions: the upsampling is a pure repeat), and
+// only the 0/1 label matrix goes back to the host for the tiny pairwise segment rule.
+struct ac_sed {
+    float* blob = nullptr;
+    float *bn0_s, *bn0_b, *w1, *s1, *b1;
+    ac::Cnn14Conv conv[7];
+    float *fc1_w, *fc1_b, *fco_w, *fco_b;
+    ac::TcWeight fc1_tw, fco_tw;
+    ac_bigru_t* gru = nullptr;
+    int classes = 0, classes_pad = 0;
+};
+
+namespace ac {
+constexpr int kSedBlocks = 4;
+constexpr int kSedCh[kSedBlocks + 1] = {1, 64, 128, 256, 512};
+constexpr int kSedPoolH[kSedBlocks] = {2, 2, 1, 1};
+static void sed_walk(int n_mels, int n_frames, Cnn14Dims (&d)[kSedBlocks + 1]) {   // input dims of each block, then the output
+    int H = n_frames, W = n_mels;
+    for (int i = 0; i < kSedBlocks; ++i) { d[i] = {H, W}; H /= kSedPoolH[i]; W /= 2; }
+    d[kSedBlocks] = {H, W};
+}
+static size_t sed_act_elems(int batch, int n_mels, int n_frames) {
+    Cnn14Dims d[kSedBlocks + 1];
+    sed_walk(n_mels, n_frames, d);
+    size_t m = 0;
+    for (int i = 0; i < kSedBlocks; ++i) m = std::max(m, (size_t)d[i].H * d[i].W * kSedCh[i + 1]);
+    return align_up(m * batch, 64);
+}
+}  // namespace ac
+
+extern "C" {
+
+int ac_sed_num_tensors(void) { return 4 + ac::kSedBlocks * 10 + 2 + 8 + 2; }
+int ac_sed_segments(int n_frames) { return n_frames / 4; }
+
+int ac_sed_create(const float* const* t, const int64_t* numels, int n_tensors, int classes, void* stream, ac_sed_t** out) {
+    using namespace ac;
+    AC_REQUIRE(t && numels && out, "ac_sed_create: null argument");
+    AC_REQUIRE(n_tensors == ac_sed_num_tensors(), "ac_sed_create: expected %d tensors, got %d", ac_sed_num_tensors(), n_tensors);
+    AC_REQUIRE(classes >= 1, "ac_sed_create: bad class count %d", classes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = kSedCh[kSedBlocks], CP = (classes + 15) / 16 * 16;
+    std::vector<int64_t> want;
+    for (int q = 0; q < 4; ++q) want.push_back(64);
+    for (int i = 0; i < kSedBlocks; ++i) {
+        const int ci = kSedCh[i], co = kSedCh[i + 1];
+        want.push_back((int64_t)co * ci * 9); want.push_back((int64_t)co * co * 9);
+        for (int q = 0; q < 8; ++q) want.push_back(co);
+    }
+    want.push_back((int64_t)D * D); want.push_back(D);
+    for (int d = 0; d < 2; ++d) { want.push_back(768 * (int64_t)D); want.push_back(768 * 256); want.push_back(768); want.push_back(768); }
+    want.push_back((int64_t)classes * D); want.push_back(classes);
+    for (int i = 0; i < n_tensors; ++i)
+        AC_REQUIRE(numels[i] == want[i], "ac_sed_create: tensor %d has %lld elements, expected %lld", i, (long long)numels[i],
+                   (long long)want[i]);
+    size_t total = 0;
+    auto take = [&](size_t n) { size_t o = total; total += align_up(n, 64); return o; };
+    const size_t o_bn0s = take(64), o_bn0b = take(64), o_w1 = take(9 * 64), o_s1 = take(64), o_b1 = take(64);
+    struct Off { size_t s, b, pk; };
+    Off co_[7]; int cin_[7], cout_[7];
+    size_t perm_max = 0;
+    {
+        int l = 0;
+        for (int i = 0; i < kSedBlocks; ++i)
+            for (int j = 0; j < 2; ++j) {
+                if (i == 0 && j == 0) continue;
+                cin_[l] = j == 0 ? kSedCh[i] : kSedCh[i + 1]; cout_[l] = kSedCh[i + 1];
+                co_[l].s = take(cout_[l]); co_[l].b = take(cout_[l]); co_[l].pk = take(tc_packed_floats(cout_[l], 9 * cin_[l]));
+                perm_max = std::max(perm_max, (size_t)cout_[l] * 9 * cin_[l]);
+                ++l;
+            }
+    }
+    const size_t o_fc1w = take((size_t)D * D), o_fc1b = take(D), o_fc1pk = take(tc_packed_floats(D, D));
+    const size_t o_fcow = take((size_t)CP * D), o_fcob = take(CP), o_fcopk = take(tc_packed_floats(CP, D));
+    ac_sed_t* net = new ac_sed_t();
+    net->classes = classes; net->classes_pad = CP;
+    float* perm = nullptr;
+    int rc = check_cuda(cudaMalloc(&net->blob, total * sizeof(float)), "ac_sed_create: cudaMalloc(weights)");
+    if (rc == AC_OK) rc = check_cuda(cudaMalloc(&perm, perm_max * sizeof(float)), "ac_sed_create: cudaMalloc(scratch)");
+    if (rc == AC_OK) rc = check_cuda(cudaMemsetAsync(net->blob, 0, total * sizeof(float), st), "memset");
+    if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
+    float* B0 = net->blob;
+    auto fold = [&](int ti, int c, float* s, float* b) {
+        cnn14_bn_fold_kernel<<<cdiv(c, 256), 256, 0, st>>>(t[ti], t[ti + 1], t[ti + 2], t[ti + 3], kCnn14BnEps, s, b, c);
+        g_launches++;
+    };
+    net->bn0_s = B0 + o_bn0s; net->bn0_b = B0 + o_bn0b; net->w1 = B0 + o_w1; net->s1 = B0 + o_s1; net->b1 = B0 + o_b1;
+    fold(0, 64, net->bn0_s, net->bn0_b);
+    int l = 0;
+    for (int i = 0; i < kSedBlocks && rc == AC_OK; ++i) {
+        const int base = 4 + i * 10;
+        for (int j = 0; j < 2 && rc == AC_OK; ++j) {
+            const int bn_ti = base + 2 + 4 * j;
+            if (i == 0 && j == 0) {
+                cnn14_w1_kernel<<<cdiv(9 * 64, 256), 256, 0, st>>>(t[base], net->w1, 64);
+                g_launches++;
+                fold(bn_ti, 64, net->s1, net->b1);
+                continue;
+            }
+            Cnn14Conv& c = net->conv[l];
+            c.cin = cin_[l]; c.cout = cout_[l]; c.scale = B0 + co_[l].s; c.bias = B0 + co_[l].b;
+            fold(bn_ti, c.cout, c.scale, c.bias);
+            rc = conv3x3_permute_weight(t[base + j], perm, c.cout, c.cin, st);
+            if (rc == AC_OK) rc = tc_pack_weight(perm, c.scale, c.cout, 9 * c.cin, B0 + co_[l].pk, st, &c.tw);
+            ++l;
+        }
+    }
+    int ti = 4 + kSedBlocks * 10;
+    auto copy = [&](float* dst, const float* src, size_t n) {
+        if (rc == AC_OK) rc = check_cuda(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st), "ac_sed_create copy");
+    };
+    net->fc1_w = B0 + o_fc1w; net->fc1_b = B0 + o_fc1b; net->fco_w = B0 + o_fcow; net->fco_b = B0 + o_fcob;
+    copy(net->fc1_w, t[ti], (size_t)D * D); copy(net->fc1_b, t[ti + 1], D);
+    if (rc == AC_OK) rc = tc_pack_weight(net->fc1_w, nullptr, D, D, B0 + o_fc1pk, st, &net->fc1_tw);
+    if (rc == AC_OK) rc = ac_bigru_create(t + ti + 2, numels + ti + 2, 8, D, 256, 1, stream, &net->gru);
+    copy(net->fco_w, t[ti + 10], (size_t)classes * D); copy(net->fco_b, t[ti + 11], classes);   // rows >= classes stay zero
+    if (rc == AC_OK) rc = tc_pack_weight(net->fco_w, nullptr, CP, D, B0 + o_fcopk, st, &net->fco_tw);
+    if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_sed_create pack kernels");
+    if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_sed_create sync");
+    cudaFree(perm);
+    if (rc != AC_OK) { ac_bigru_destroy(net->gru); cudaFree(net->blob); delete net; return rc; }
+    *out = net;
+    return AC_OK;
+}
+
+void ac_sed_destroy(ac_sed_t* net) {
+    if (!net) return;
+    ac_bigru_destroy(net->gru);
+    cudaFree(net->blob);
+    delete net;
+}
+
+size_t ac_sed_workspace_bytes(const ac_sed_t* net, int batch, int n_mels, int n_frames) {
+    if (!net) return 0;
+    using namespace ac;
+    const int S = ac_sed_segments(n_frames), D = kSedCh[kSedBlocks];
+    const size_t rows = (size_t)batch * S;
+    return (2 * sed_act_elems(batch, n_mels, n_frames) + 3 * align_up(rows * D, 64) + align_up(rows * net->classes_pad, 64)) * sizeof(float) +
+           align_up((size_t)batch * sizeof(int64_t), 256) + ac_bigru_workspace_bytes(net->gru, batch, S);
+}
+
+int ac_sed_fwd(const ac_sed_t* net, const float* lms, int B, int n_mels, int n_frames, float high, float low, float* prob_out,
+               unsigned char* labels_out, void* workspace, size_t ws_bytes, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(B >= 0 && B <= 65535, "ac_sed_fwd: batch %d out of range", B);
+    AC_REQUIRE(n_mels == 64 && n_frames >= 16, "ac_sed_fwd: expects 64 mel bins and >= 16 frames (got %d x %d)", n_mels, n_frames);
+    if (B == 0) return AC_OK;
+    AC_REQUIRE(net && lms && labels_out, "ac_sed_fwd: null argument");
+    AC_REQUIRE(workspace && ws_bytes >= ac_sed_workspace_bytes(net, B, n_mels, n_frames), "ac_sed_fwd: workspace too small (%zu < %zu)",
+               ws_bytes, ac_sed_workspace_bytes(net, B, n_mels, n_frames));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = ac_sed_segments(n_frames), D = kSedCh[kSedBlocks], CP = net->classes_pad;
+    const size_t rows = (size_t)B * S;
+    const size_t act = sed_act_elems(B, n_mels, n_frames);
+    float* cur = (float*)workspace;
+    float* nxt = cur + act;
+    float* X = nxt + act;                        // [B, S, D] mean over mel
+    float* F1 = X + align_up(rows * D, 64);      // relu(fc1)
+    float* G = F1 + align_up(rows * D, 64);      // GRU output [B, S, 512]
+    float* P = G + align_up(rows * D, 64);       // logits / probabilities [B, S, CP]
+    int64_t* lens = (int64_t*)(P + align_up(rows * CP, 64));
+    char* gws = (char*)lens + align_up((size_t)B * sizeof(int64_t), 256);
+    Cnn14Dims d[kSedBlocks + 1];
+    sed_walk(n_mels, n_frames, d);
+    AC_REQUIRE(d[kSedBlocks].H == S, "ac_sed_fwd: internal frame count mismatch");
+    int rc;
+    {
+        AC_TIMED("sed_conv1", st);
+        dim3 grid(cdiv(n_frames, kC1Time), B);
+        const size_t smem = (size_t)(kC1Time + 2) * (n_mels + 2) * sizeof(float);
+        rc = launch_pdl(cnn14_conv1_kernel, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s, (const float*)net->bn0_b,
+                        (const float*)net->w1, (const float*)net->s1, (const float*)net->b1, cur, n_mels, n_frames);
+        if (rc) return rc;
+        AC_LAUNCHED("cnn14_conv1_kernel");
+    }
+    int l = 0;
+    for (int i = 0; i < kSedBlocks; ++i) {
+        for (int j = 0; j < 2; ++j) {
+            if (i == 0 && j == 0) continue;
+            const Cnn14Conv& c = net->conv[l++];
+            Conv3Args a; a.in = cur; a.out = nxt; a.B = B; a.H = d[i].H; a.W = d[i].W; a.Cin = c.cin; a.Cout = c.cout;
+            a.bias = c.bias; a.tw = &c.tw; a.act = ACT_RELU;
+            rc = conv3x3_tc(a, st); if (rc) return rc;
+            std::swap(cur, nxt);
+        }
+        const int C4 = kSedCh[i + 1] / 4, Ho = d[i + 1].H, Wo = d[i + 1].W;
+        const int64_t total = (int64_t)B * Ho * Wo * C4;
+        AC_TIMED("sed_pool", st);
+        rc = launch_pdl(cnn_avgmax_pool_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st, (const float4*)cur, (float4*)nxt,
+                        d[i].H, d[i].W, C4, Ho, Wo, kSedPoolH[i], 2, total);
+        if (rc) return rc;
+        AC_LAUNCHED("cnn_avgmax_pool_kernel");
+        std::swap(cur, nxt);
+    }
+    {
+        const int64_t total = (int64_t)rows * (D / 4);
+        rc = launch_pdl(cnn_wmean_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st, (const float4*)cur, (float4*)X,
+                        d[kSedBlocks].W, D / 4, total);
+        if (rc) return rc;
+        AC_LAUNCHED("cnn_wmean_kernel");
+    }
+    GemmArgs g; g.A = X; g.W = net->fc1_w; g.C = F1; g.M = (int)rows; g.N = D; g.K = D; g.cbias = net->fc1_b; g.act = ACT_RELU; g.tw = &net->fc1_tw;
+    rc = gemm_tn(g, st); if (rc) return rc;
+    // the SED GRU runs over the full sequence of every clip (no packing): lens = S
+    sed_fill_kernel<<<cdiv(B, 256), 256, 0, st>>>(lens, (int64_t)S, B);
+    AC_LAUNCHED("sed_fill_kernel");
+    rc = ac_bigru_fwd(net->gru, F1, lens, B, S, S, G, gws, ac_bigru_workspace_bytes(net->gru, B, S), stream); if (rc) return rc;
+    GemmArgs go; go.A = G; go.W = net->fco_w; go.C = P; go.M = (int)rows; go.N = CP; go.K = D; go.cbias = net->fco_b; go.act = ACT_NONE; go.tw = &net->fco_tw;
+    rc = gemm_tn(go, st); if (rc) return rc;
+    {
+        const int64_t total = (int64_t)rows * CP;
+        rc = launch_pdl(sed_sigmoid_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st, P, total);
+        if (rc) return rc;
+        AC_LAUNCHED("sed_sigmoid_kernel");
+        const int tot = B * net->classes;
+        AC_TIMED("sed_hysteresis", st);
+        rc = launch_pdl(sed_hysteresis_kernel, dim3(cdiv(tot, 128)), dim3(128), 0, st, (const float*)P, labels_out, S, CP, net->classes,
+                        high, low, tot);
+        if (rc) return rc;
+        AC_LAUNCHED("sed_hysteresis_kernel");
+    }
+    if (prob_out != nullptr)   // [B, S, classes] (un-padded copy for inspection / tests)
+        AC_CUDA(cudaMemcpy2DAsync(prob_out, (size_t)net->classes * sizeof(float), P, (size_t)CP * sizeof(float),
+                                  (size_t)net->classes * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+    return AC_OK;
 }
 
 }  // extern "C"

@@ -39,6 +39,7 @@ typedef struct ac_trm ac_trm_t;
 typedef struct ac_cnn14 ac_cnn14_t;
 typedef struct ac_bigru ac_bigru_t;
 typedef struct ac_bah ac_bah_t;
+typedef struct ac_sed ac_sed_t;
 
 int ac_version(void);
 const char* ac_last_error(void);
@@ -145,6 +146,25 @@ void ac_cnn14_destroy(ac_cnn14_t* net);
 int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms_dev, int batch, int n_mels, int n_frames,
                  const int64_t* lens_dev, float* attn_emb_dev, float* fc_emb_dev,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ sound-event tagger of the temporal captioner
+ * Replaces captioning/models/hf_wrapper.py:1791-1859 `Cnn8rnnSedModel.forward_prob` (bn0, 4 ConvBlocks with 'avg+max'
+ * pooling (2,2)(2,2)(1,2)(1,2), mean over mel, fc1 + ReLU, bidirectional GRU(512 -> 256), fc_audioset, sigmoid,
+ * clamp(1e-7, 1)) and the double threshold of :123-162 (`double_threshold(x, high, low)`), eval mode.
+ * tensors_dev (ac_sed_num_tensors() = 56, state_dict order without `num_batches_tracked`): bn0 x4; blocks 1..4:
+ * conv1.weight, conv2.weight, bn1 x4, bn2 x4; fc1.weight [512,512], fc1.bias; rnn.{weight_ih,weight_hh,bias_ih,bias_hh}_l0
+ * and the `_reverse` four; fc_audioset.weight [classes,512], fc_audioset.bias. */
+int ac_sed_num_tensors(void);
+int ac_sed_segments(int n_frames);   /* n_frames / 4 */
+int ac_sed_create(const float* const* tensors_dev, const int64_t* numels, int n_tensors, int classes, void* stream,
+                  ac_sed_t** out);
+void ac_sed_destroy(ac_sed_t* net);
+size_t ac_sed_workspace_bytes(const ac_sed_t* net, int batch, int n_mels, int n_frames);
+/* lms_dev [batch, 64, n_frames] -> prob_dev (nullable) [batch, segments, classes] = `segmentwise_output`;
+ * labels_dev [batch, segments, classes] uint8 = the double-thresholded decisions at segment resolution (the
+ * reference's frame-level matrix is this one repeated 4x along time and padded with its last row). */
+int ac_sed_fwd(const ac_sed_t* net, const float* lms_dev, int batch, int n_mels, int n_frames, float high, float low,
+               float* prob_dev, unsigned char* labels_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ bidirectional GRU encoder
  * Replaces captioning/models/rnn_encoder.py:34-49 `RnnEncoder.forward` = pack_wrapper(nn.GRU(batch_first=True,

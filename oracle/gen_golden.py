@@ -166,10 +166,33 @@ def temp_gru(seed=8, mem_seed=1, batch=8, T=9):
         beam3_stable=stable["beam3"].numpy(), beam4_stable=stable["beam4"].numpy())
 
 
+def sed(seed=12, batch=8, n=96000):
+    """Golden outputs of the reference's Cnn8rnnSedModel (hf_wrapper.py:1791-1859) on seeded weights and 3 s clips:
+    temporal tags, a sample of the segment-wise probabilities, and which clips keep their tag under input noise."""
+    from . import cnn14 as oc
+    from . import sed as so
+    hf = ref_import.load("captioning.models.hf_wrapper")
+    ref = hf.Cnn8rnnSedModel(classes_num=447).eval()
+    ref.load_state_dict(so.build_state_dict(seed), strict=True)
+    wav, lens = cm.synth_wav(batch, n, seed=31, ragged=True, varied=True, sample_rate=32000)
+    lms = oc.log_mel(oc.build_state_dict(3), wav)
+    with torch.no_grad():
+        seg = ref.forward_prob(lms)["segmentwise_output"]
+        tags = ref(lms)
+    stable = torch.ones(batch, dtype=torch.bool)
+    gen = torch.Generator().manual_seed(29)
+    with torch.no_grad():
+        for _ in range(6):       # a tag that survives 1e-2 dB of input noise cannot flip on fp32 reordering
+            stable &= torch.tensor(ref(lms + 1e-2 * torch.randn(lms.shape, generator=gen))) == torch.tensor(tags)
+    print("sed tags", tags, "stable", stable.tolist())
+    np.savez_compressed(os.path.join(OUT, "sed.npz"), seed=seed, batch=batch, n_samples=n, wav_seed=31, tags=np.array(tags),
+                        seg=seg[:, ::3, ::7].numpy(), stable=stable.numpy())
+
+
 if __name__ == "__main__":
     import sys
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm", "temp_gru"]
+    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm", "temp_gru", "sed"]
     if "effb2_trm" in which:
         effb2_trm()
     if "cnn14" in which:
@@ -178,3 +201,5 @@ if __name__ == "__main__":
         cnn14rnn_trm()
     if "temp_gru" in which:
         temp_gru()
+    if "sed" in which:
+        sed()

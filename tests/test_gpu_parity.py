@@ -602,3 +602,64 @@ def test_temp_gru_model_end_to_end(temp_gru):
         assert got.shape == (3, 20) and not got.is_cuda
         st = (ref == pert).all(1)
         assert (got[st] == ref[st]).all(), (method, got, ref)
+
+
+# ------------------------------------------------------------------ sound-event tagger (row A14)
+def test_sed_matches_golden_and_oracle():
+    """Cnn8rnnSedModel through the C ABI: segment-wise probabilities vs the reference's (golden sample) within 2e-4, tags
+    exact for the clips whose tag survives 1e-2 dB of input noise in the reference; device-side double threshold vs the
+    oracle's frame-level one on the device's own probabilities (exact)."""
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    from oracle import cnn14 as oc, sed
+    g = np.load(__file__.rsplit("/", 1)[0] + "/golden/sed.npz")
+    sd = sed.build_state_dict(int(g["seed"]))
+    m = hw.Cnn8rnnSedModel(447).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    wav, _ = cm.synth_wav(int(g["batch"]), int(g["n_samples"]), seed=int(g["wav_seed"]), ragged=True, varied=True,
+                          sample_rate=32000)
+    lms = oc.log_mel(oc.build_state_dict(3), wav)
+    out = m.forward_prob(lms.to(DEV))
+    seg = out["segmentwise_output"].cpu()
+    assert out["framewise_output"].shape == (lms.shape[0], lms.shape[2], 447)
+    assert np.abs(seg[:, ::3, ::7].numpy() - g["seg"]).max() < 2e-4
+    tags = np.array(m(lms.to(DEV)))
+    st = g["stable"]
+    assert (tags[st] == g["tags"][st]).all(), (tags, g["tags"])
+    # thresholding + decoding on exactly the device's probabilities
+    frame = out["framewise_output"].cpu().numpy()
+    for b in range(frame.shape[0]):
+        lab = np.stack([sed.double_threshold_column(frame[b, :, c]) for c in range(447)], axis=1)
+        assert sed.temporal_tag(lab) == tags[b]
+
+
+def test_temp_gru_model_with_sed_tagger(temp_gru):
+    """Full HF forward (no temporal_tag given): tag from the device SED path, caption equal to the oracle chain run with
+    that tag; a caller-supplied tag can only lower it."""
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    from oracle import bah_decoder as bd, cnn14 as oc, crnn, sed
+    _, dsd, _ = temp_gru
+    cnn_sd, rnn_sd, sed_sd = oc.build_state_dict(3), crnn.build_gru_state_dict(4), sed.build_state_dict(12)
+    m = hw.Cnn14RnnTempAttnGruModel().eval()
+    sd = {f"cap_model.encoder.cnn.{k}": v for k, v in cnn_sd.items()}
+    sd.update({f"cap_model.encoder.rnn.{k}": v for k, v in rnn_sd.items()})
+    sd.update({f"cap_model.decoder.{k}": v for k, v in dsd.items()})
+    sd.update({f"sed_model.{k}": v for k, v in sed_sd.items()})
+    sd.update({k: v for k, v in cnn_sd.items() if k.startswith("melspec")})
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    wav, lens = cm.synth_wav(4, 96000, seed=31, ragged=True, varied=True, sample_rate=32000)
+    lms_dev, _ = m.melspec_extractor(wav.to(DEV))
+    tags = torch.as_tensor(m.sed_model(lms_dev))
+    enc = crnn.crnn_encoder(cnn_sd, rnn_sd, wav, lens)
+    ref = bd.greedy_decode(dsd, enc["fc_emb"], enc["attn_emb"], enc["attn_emb_len"], tags, 20)["seq"]
+    pert = bd.greedy_decode(dsd, enc["fc_emb"] * 1.001, enc["attn_emb"] * 0.999, enc["attn_emb_len"], tags, 20)["seq"]
+    with torch.no_grad():
+        got = m(wav, lens, sample_method="greedy")
+        low = m(wav, lens, temporal_tag=torch.zeros(4, dtype=torch.long), sample_method="greedy")
+    st = (ref == pert).all(1)
+    assert (got[st] == ref[st]).all()
+    ref0 = bd.greedy_decode(dsd, enc["fc_emb"], enc["attn_emb"], enc["attn_emb_len"], torch.zeros(4, dtype=torch.long), 20)["seq"]
+    pert0 = bd.greedy_decode(dsd, enc["fc_emb"] * 1.001, enc["attn_emb"] * 0.999, enc["attn_emb_len"], torch.zeros(4, dtype=torch.long), 20)["seq"]
+    st0 = (ref0 == pert0).all(1)
+    assert (low[st0] == ref0[st0]).all()
