@@ -573,22 +573,30 @@ def test_temp_gru_decoder_matches_oracle(temp_gru, B, T, beam):
     assert (gotb[:nb][stb] == refb.numpy()[stb]).all()
 
 
-def test_temp_gru_model_end_to_end(temp_gru):
-    """Cnn14RnnTempAttnGruModel.forward (log-mel -> Cnn14 -> bi-GRU -> GRU-attention beam search) vs the oracle chain on
-    two 2 s clips with given temporal tags."""
+def _temp_gru_model(dsd):
     from audiocaption_b200.captioning.models import hf_wrapper as hw
-    from oracle import bah_decoder as bd, cnn14 as oc, crnn
-    _, dsd, _ = temp_gru
-    cnn_sd, rnn_sd = oc.build_state_dict(3), crnn.build_gru_state_dict(4)
+    from oracle import cnn14 as oc, crnn, sed
+    cnn_sd, rnn_sd, sed_sd = oc.build_state_dict(3), crnn.build_gru_state_dict(4), sed.build_state_dict(12)
     m = hw.Cnn14RnnTempAttnGruModel().eval()
     sd = {f"cap_model.encoder.cnn.{k}": v for k, v in cnn_sd.items()}
     sd.update({f"cap_model.encoder.rnn.{k}": v for k, v in rnn_sd.items()})
     sd.update({f"cap_model.decoder.{k}": v for k, v in dsd.items()})
-    sd.update({f"melspec_extractor.{k[len('melspec_extractor.'):]}": v for k, v in cnn_sd.items() if k.startswith("melspec")})
+    sd.update({f"sed_model.{k}": v for k, v in sed_sd.items()})
+    sd.update({k: v for k, v in cnn_sd.items() if k.startswith("melspec")})
     m.load_state_dict(sd, strict=True)
-    m = m.to(DEV)
+    return m.to(DEV), cnn_sd, rnn_sd
+
+
+def test_temp_gru_model_end_to_end(temp_gru):
+    """Cnn14RnnTempAttnGruModel.forward (log-mel -> SED tag -> Cnn14 -> bi-GRU -> GRU-attention decode) vs the oracle chain
+    on 2 s clips; the caller's temporal tags are lowered to min(tag, SED tag) as in hf_wrapper.py:1954-1958."""
+    from oracle import bah_decoder as bd, crnn
+    _, dsd, _ = temp_gru
+    m, cnn_sd, rnn_sd = _temp_gru_model(dsd)
     wav, lens = cm.synth_wav(3, 64000, seed=21, ragged=True, varied=True, sample_rate=32000)
-    tags = torch.tensor([1, 3, 0])
+    given = torch.tensor([1, 3, 0])
+    lms_dev, _ = m.melspec_extractor(wav.to(DEV))
+    tags = torch.minimum(given, torch.as_tensor(m.sed_model(lms_dev)))
     enc = crnn.crnn_encoder(cnn_sd, rnn_sd, wav, lens)
     for method, beam in (("greedy", None), ("beam", 3)):
         if beam:
@@ -598,7 +606,7 @@ def test_temp_gru_model_end_to_end(temp_gru):
             ref = bd.greedy_decode(dsd, enc["fc_emb"], enc["attn_emb"], enc["attn_emb_len"], tags, 20)["seq"]
             pert = bd.greedy_decode(dsd, enc["fc_emb"] * 1.001, enc["attn_emb"] * 0.999, enc["attn_emb_len"], tags, 20)["seq"]
         with torch.no_grad():
-            got = m(wav, lens, temporal_tag=tags, sample_method=method, beam_size=beam or 3, max_length=20)
+            got = m(wav, lens, temporal_tag=given, sample_method=method, beam_size=beam or 3, max_length=20)
         assert got.shape == (3, 20) and not got.is_cuda
         st = (ref == pert).all(1)
         assert (got[st] == ref[st]).all(), (method, got, ref)
@@ -636,18 +644,9 @@ def test_sed_matches_golden_and_oracle():
 def test_temp_gru_model_with_sed_tagger(temp_gru):
     """Full HF forward (no temporal_tag given): tag from the device SED path, caption equal to the oracle chain run with
     that tag; a caller-supplied tag can only lower it."""
-    from audiocaption_b200.captioning.models import hf_wrapper as hw
-    from oracle import bah_decoder as bd, cnn14 as oc, crnn, sed
+    from oracle import bah_decoder as bd, crnn
     _, dsd, _ = temp_gru
-    cnn_sd, rnn_sd, sed_sd = oc.build_state_dict(3), crnn.build_gru_state_dict(4), sed.build_state_dict(12)
-    m = hw.Cnn14RnnTempAttnGruModel().eval()
-    sd = {f"cap_model.encoder.cnn.{k}": v for k, v in cnn_sd.items()}
-    sd.update({f"cap_model.encoder.rnn.{k}": v for k, v in rnn_sd.items()})
-    sd.update({f"cap_model.decoder.{k}": v for k, v in dsd.items()})
-    sd.update({f"sed_model.{k}": v for k, v in sed_sd.items()})
-    sd.update({k: v for k, v in cnn_sd.items() if k.startswith("melspec")})
-    m.load_state_dict(sd, strict=True)
-    m = m.to(DEV)
+    m, cnn_sd, rnn_sd = _temp_gru_model(dsd)
     wav, lens = cm.synth_wav(4, 96000, seed=31, ragged=True, varied=True, sample_rate=32000)
     lms_dev, _ = m.melspec_extractor(wav.to(DEV))
     tags = torch.as_tensor(m.sed_model(lms_dev))
