@@ -59,7 +59,7 @@ _SIGS = {
     "ac_sed_destroy": (None, [C.c_void_p]),
     "ac_sed_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ac_sed_fwd": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, c_f32p, C.c_void_p,
-                             C.c_void_p, C.c_size_t, C.c_void_p]),
+                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ac_effb2_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ac_effb2_destroy": (None, [C.c_void_p]),
     "ac_effb2_num_tensors": (C.c_int, []),

@@ -371,23 +371,59 @@ class Cnn8rnnSedModel(nn.Module):
             S = l.ac_sed_segments(T)
             labels = torch.empty(B, S, self.classes_num, dtype=torch.uint8, device=dev)
             prob = torch.empty(B, S, self.classes_num, dtype=torch.float32, device=dev) if want_prob else None
+            max_runs = 1024 * B
+            runs = torch.empty(max_runs, 4, dtype=torch.int32, device=dev)
+            n_runs = torch.empty(1, dtype=torch.int32, device=dev)
             nbytes = l.ac_sed_workspace_bytes(net, B, F, T)
             ws = self._ws.get(nbytes, dev)
-            _lib.check(l.ac_sed_fwd(net, _lib.ptr(lms), B, F, T, 0.75, 0.25, _lib.ptr(prob), _lib.ptr(labels), _lib.ptr(ws), nbytes,
-                                    _lib.current_stream()), "ac_sed_fwd")
-        return prob, labels, T
+            _lib.check(l.ac_sed_fwd(net, _lib.ptr(lms), B, F, T, 0.75, 0.25, _lib.ptr(prob), _lib.ptr(labels), _lib.ptr(runs),
+                                    max_runs, _lib.ptr(n_runs), _lib.ptr(ws), nbytes, _lib.current_stream()), "ac_sed_fwd")
+        return prob, labels, T, runs, n_runs
 
     def forward_prob(self, lms):
         """{"segmentwise_output" [B, T//4, classes], "framewise_output" [B, T, classes]} as hf_wrapper.py:1823-1859."""
-        seg, _, T = self._run(lms, True)
+        seg, _, T, _, _ = self._run(lms, True)
         frame = seg.repeat_interleave(self.interpolate_ratio, dim=1)
         if frame.shape[1] < T:
             frame = torch.cat((frame, frame[:, -1:].expand(-1, T - frame.shape[1], -1)), dim=1)
         return {"segmentwise_output": seg, "framewise_output": frame}
 
     def forward(self, lms):
-        _, labels, T = self._run(lms, False)
-        return decode_segment_labels(labels.cpu().numpy(), T, self.interpolate_ratio, self.time_resolution)
+        _, labels, T, runs, n_runs = self._run(lms, False)
+        n = int(n_runs.item())
+        if n > runs.shape[0]:         # more runs than the compact list holds: decode from the label matrix instead
+            return decode_segment_labels(labels.cpu().numpy(), T, self.interpolate_ratio, self.time_resolution)
+        return decode_runs(runs[:n].cpu().numpy(), labels.shape[0], labels.shape[1], T, self.interpolate_ratio,
+                           self.time_resolution)
+
+
+def _tags_from_runs(on_b, on_c, on_s, off_s, B, S, frames_num, ratio, time_resolution, thre):
+    """`segments_to_temporal_tag` (hf_wrapper.py:180-199) per clip from runs sorted by clip; float64 arithmetic on
+    onset/offset = frame * time_resolution, exactly the reference's."""
+    on_all = (on_s * ratio) * time_resolution
+    off_all = np.where(off_s == S, frames_num, off_s * ratio) * time_resolution
+    first = np.searchsorted(on_b, np.arange(B + 1))
+    out = []
+    for b in range(B):
+        lo, hi = first[b], first[b + 1]
+        if hi - lo < 2:
+            out.append(0)
+            continue
+        on, off, cls = on_all[lo:hi], off_all[lo:hi], on_c[lo:hi]
+        dur = off - on
+        min_dur = np.minimum(dur[:, None], dur[None, :])
+        overlap = off[:, None] - on[None, :]
+        other = cls[:, None] != cls[None, :]
+        after = 2 if (other & (overlap < thre * min_dur)).any() else 0
+        whil = 1 if (other & (on[:, None] < on[None, :]) & (overlap > thre * min_dur)).any() else 0
+        out.append(after + whil)
+    return out
+
+
+def decode_runs(runs, B, S, frames_num, ratio=4, time_resolution=0.01, thre=0.5):
+    """Tags from the device's compact run list [n, 4] = (clip, class, first segment, one past the last segment)."""
+    runs = runs[np.argsort(runs[:, 0], kind="stable")].astype(np.int64)
+    return _tags_from_runs(runs[:, 0], runs[:, 1], runs[:, 2], runs[:, 3], B, S, frames_num, ratio, time_resolution, thre)
 
 
 def decode_segment_labels(labels, frames_num, ratio=4, time_resolution=0.01, thre=0.5):
@@ -395,29 +431,14 @@ def decode_segment_labels(labels, frames_num, ratio=4, time_resolution=0.01, thr
     resolution [B, S, classes]: a run of segments [s0, s1) is the frame run [ratio*s0, ratio*s1), except that a run
     reaching the last segment extends to `frames_num` (the reference pads the frame matrix with its last row).  The pairwise
     rule is evaluated in float64 on onset/offset = frame * time_resolution, exactly the reference's arithmetic."""
-    out = []
     B, S, C = labels.shape
-    for b in range(B):
-        lab = labels[b].astype(np.int8)
-        pad = np.zeros((1, C), dtype=np.int8)
-        d = np.diff(np.concatenate((pad, lab, pad), axis=0), axis=0)          # +1 at run starts, -1 one past run ends
-        on_s, on_c = np.nonzero(d.T == 1)[::-1]                                # ordered by class, then time (as the reference)
-        off_s, off_c = np.nonzero(d.T == -1)[::-1]
-        assert (on_c == off_c).all()
-        off_f = np.where(off_s == S, frames_num, off_s * ratio)
-        on = (on_s * ratio) * time_resolution
-        off = off_f * time_resolution
-        if len(on) == 0:
-            out.append(0)
-            continue
-        dur = off - on
-        min_dur = np.minimum(dur[:, None], dur[None, :])
-        overlap = off[:, None] - on[None, :]
-        other = on_c[:, None] != on_c[None, :]
-        after = 2 if (other & (overlap < thre * min_dur)).any() else 0
-        whil = 1 if (other & (on[:, None] < on[None, :]) & (overlap > thre * min_dur)).any() else 0
-        out.append(after + whil)
-    return out
+    # run boundaries of the whole batch at once: +1 at run starts, -1 one past run ends, ordered by (clip, class, time)
+    lab = np.ascontiguousarray(labels.transpose(0, 2, 1)).astype(np.int8)      # [B, C, S]
+    pad = np.zeros((B, C, 1), dtype=np.int8)
+    d = np.diff(np.concatenate((pad, lab, pad), axis=2), axis=2)
+    on_b, on_c, on_s = np.nonzero(d == 1)
+    off_b, _, off_s = np.nonzero(d == -1)
+    return _tags_from_runs(on_b, on_c, on_s, off_s, B, S, frames_num, ratio, time_resolution, thre)
 
 
 class Cnn14RnnTempAttnGruConfig:

@@ -170,8 +170,12 @@ __global__ void sed_fill_kernel(int64_t* __restrict__ x, int64_t v, int n) {
 // Double threshold (hysteresis) along time for every (clip, class) column: a maximal run of prob > low is kept when
 // it contains a value > high (hf_wrapper.py:123-162 `double_threshold`; at the repeat-upsampled frame resolution the
 // n_connect = 1 merge can never fire because runs are >= 4 frames apart).  prob [B, S, ld] -> labels [B, S, classes] u8.
+// Every kept run is also appended to `runs` as (clip, class, first segment, one past the last segment) through an atomic
+// cursor (order unspecified; the pairwise rule that consumes them is order-free), so the host needs a few hundred bytes
+// instead of the label matrix.
 __global__ void sed_hysteresis_kernel(const float* __restrict__ prob, unsigned char* __restrict__ labels, int S, int ld,
-                                      int classes, float high, float low, int total) {
+                                      int classes, float high, float low, int total, int4* __restrict__ runs, int max_runs,
+                                      int* __restrict__ n_runs) {
     pdl_trigger();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,6 +192,10 @@ __global__ void sed_hysteresis_kernel(const float* __restrict__ prob, unsigned c
         } else if (start >= 0) {
             const unsigned char keep = has_high ? 1 : 0;
             for (int q = start; q < s; ++q) l[(size_t)q * classes] = keep;
+            if (keep && n_runs != nullptr) {
+                const int idx = atomicAdd(n_runs, 1);
+                if (idx < max_runs) runs[idx] = make_int4(b, c, start, s);
+            }
             start = -1;
         }
         if (s < S && !(v > low)) l[(size_t)s * classes] = 0;
@@ -566,7 +574,8 @@ size_t ac_sed_workspace_bytes(const ac_sed_t* net, int batch, int n_mels, int n_
 }
 
 int ac_sed_fwd(const ac_sed_t* net, const float* lms, int B, int n_mels, int n_frames, float high, float low, float* prob_out,
-               unsigned char* labels_out, void* workspace, size_t ws_bytes, void* stream) {
+               unsigned char* labels_out, int* runs_out, int max_runs, int* n_runs_out, void* workspace, size_t ws_bytes,
+               void* stream) {
     using namespace ac;
     AC_REQUIRE(B >= 0 && B <= 65535, "ac_sed_fwd: batch %d out of range", B);
     AC_REQUIRE(n_mels == 64 && n_frames >= 16, "ac_sed_fwd: expects 64 mel bins and >= 16 frames (got %d x %d)", n_mels, n_frames);
@@ -639,9 +648,10 @@ int ac_sed_fwd(const ac_sed_t* net, const float* lms, int B, int n_mels, int n_f
         if (rc) return rc;
         AC_LAUNCHED("sed_sigmoid_kernel");
         const int tot = B * net->classes;
+        if (n_runs_out != nullptr) AC_CUDA(cudaMemsetAsync(n_runs_out, 0, sizeof(int), st));
         AC_TIMED("sed_hysteresis", st);
         rc = launch_pdl(sed_hysteresis_kernel, dim3(cdiv(tot, 128)), dim3(128), 0, st, (const float*)P, labels_out, S, CP, net->classes,
-                        high, low, tot);
+                        high, low, tot, (int4*)runs_out, runs_out ? max_runs : 0, runs_out ? n_runs_out : (int*)nullptr);
         if (rc) return rc;
         AC_LAUNCHED("sed_hysteresis_kernel");
     }

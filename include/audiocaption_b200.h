@@ -162,9 +162,12 @@ void ac_sed_destroy(ac_sed_t* net);
 size_t ac_sed_workspace_bytes(const ac_sed_t* net, int batch, int n_mels, int n_frames);
 /* lms_dev [batch, 64, n_frames] -> prob_dev (nullable) [batch, segments, classes] = `segmentwise_output`;
  * labels_dev [batch, segments, classes] uint8 = the double-thresholded decisions at segment resolution (the
- * reference's frame-level matrix is this one repeated 4x along time and padded with its last row). */
+ * reference's frame-level matrix is this one repeated 4x along time and padded with its last row).
+ * runs_dev (nullable, 16-byte aligned) [max_runs][4] int32 + n_runs_dev (1 int32): every kept run as (clip, class, first
+ * segment, one past the last segment), unordered; *n_runs_dev counts all runs even beyond max_runs (overflow check). */
 int ac_sed_fwd(const ac_sed_t* net, const float* lms_dev, int batch, int n_mels, int n_frames, float high, float low,
-               float* prob_dev, unsigned char* labels_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+               float* prob_dev, unsigned char* labels_dev, int* runs_dev, int max_runs, int* n_runs_dev,
+               void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ bidirectional GRU encoder
  * Replaces captioning/models/rnn_encoder.py:34-49 `RnnEncoder.forward` = pack_wrapper(nn.GRU(batch_first=True,

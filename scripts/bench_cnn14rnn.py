@@ -21,6 +21,7 @@ ap.add_argument("--out", default=None)
 ap.add_argument("--no-cpu", action="store_true")
 ap.add_argument("--decoder", default="trm", choices=["trm", "tempgru"], help="trm: cnn14rnn_trm.yaml; tempgru: HF Cnn14RnnTempAttnGru (config 5)")
 ap.add_argument("--beam", type=int, default=0, help="0 = greedy")
+ap.add_argument("--sed", action="store_true", help="tempgru only: full HF forward, temporal tags from the SED tagger")
 args = ap.parse_args()
 
 from oracle import cnn14 as oc, crnn, caption_model as cm          # weights + CPU baseline only
@@ -65,11 +66,28 @@ if args.decoder == "tempgru":
     base["temporal_tag"] = torch.arange(B) % 4
 
 
+hf_model = None
+if args.sed:
+    from oracle import sed as sed_o
+    hf_model = hw.Cnn14RnnTempAttnGruModel().eval()
+    sd = {f"cap_model.encoder.cnn.{k}": v for k, v in cnn_sd.items()}
+    sd.update({f"cap_model.encoder.rnn.{k}": v for k, v in rnn_sd.items()})
+    sd.update({f"cap_model.decoder.{k}": v for k, v in dsd.items()})
+    sd.update({f"sed_model.{k}": v for k, v in sed_o.build_state_dict(12).items()})
+    sd.update({k: v for k, v in cnn_sd.items() if k.startswith("melspec")})
+    hf_model.load_state_dict(sd, strict=True)
+    hf_model = hf_model.to(dev)
+
+
 def step_resident(i):
+    if hf_model is not None:
+        return hf_model(devb[i % n_rot], lens, sample_method="beam" if args.beam else "greedy", beam_size=args.beam or 3, max_length=MAX_LEN)
     return model(dict(base, wav=devb[i % n_rot], need_logit=False, _device_seq=True))["seq"]
 
 
 def step_e2e(i):
+    if hf_model is not None:
+        return hf_model(host[i % n_rot], lens, sample_method="beam" if args.beam else "greedy", beam_size=args.beam or 3, max_length=MAX_LEN)
     return model(dict(base, wav=host[i % n_rot].to(dev, non_blocking=True), need_logit=False))["seq"]
 
 
@@ -111,7 +129,7 @@ out = {
     "metric": "clips/sec (10s@32kHz clips) Cnn14Rnn-%s %s inference" % ("Trm" if args.decoder == "trm" else "TempAttnGru", "beam-%d" % args.beam if args.beam else "greedy"), "value": B / (ms / 1e3), "unit": "clips/s",
     "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32",
     "data": "synthetic", "gpu_launches": launches,
-    "config": {"workload": "Cnn14Rnn-%s %s inference, batch=%d x 10 s @ 32 kHz synthetic clips" % ("Transformer (cnn14rnn_trm.yaml)" if args.decoder == "trm" else "TempAttnGru (HF config, temporal tags given)", "beam-%d" % args.beam if args.beam else "greedy", B),
+    "config": {"workload": "Cnn14Rnn-%s %s inference, batch=%d x 10 s @ 32 kHz synthetic clips" % ("Transformer (cnn14rnn_trm.yaml)" if args.decoder == "trm" else ("TempAttnGru (HF forward incl. SED tagger)" if args.sed else "TempAttnGru (HF config, temporal tags given)"), "beam-%d" % args.beam if args.beam else "greedy", B),
                "l2": "rotating %d input batches (%d MB)" % (n_rot, n_rot * B * N * 4 // 2 ** 20)},
     "e2e": {"value": B / (ms_e2e / 1e3), "unit": "clips/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * N * 4,
             "d2h_bytes_per_step": B * MAX_LEN * 8, "api": "TransformerModel.forward(input_dict), pinned host wav"},
