@@ -423,7 +423,7 @@ def test_sed_host_decode_matches_oracle_decode():
         assert hw.decode_segment_labels(lab, T)[0] == tag
         # the device's compact run list (unordered) decodes to the same tag
         rl = [(0, c, a, b) for c in range(C) for a, b in sed.runs(lab[0, :, c] != 0)]
-        rng.shuffle(rl)
+        np.random.default_rng(len(rl)).shuffle(rl)
         assert hw.decode_runs(np.array(rl, dtype=np.int32).reshape(-1, 4), 1, S, T)[0] == tag
         seen.add(tag)
     assert seen == {0, 1, 2, 3}
