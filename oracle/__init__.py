@@ -28,6 +28,8 @@ Contents
                      Cnn14Rnn-Transformer captioner; pinned against the imported classes.
 ``bah_decoder``      temporal Bahdanau-attention GRU decoder + greedy / beam loops with state re-ordering
                      (hf_wrapper.py:1377-1788); pinned exactly against the imported classes.
+``sed``              CNN8 + bi-GRU sound-event tagger and its numpy post-processing (hf_wrapper.py:54-216,
+                     1791-1859) restated at frame level; pinned against the imported class.
 ``ref_import``       imports the real reference from /root/reference with import
                      stubs (build container only; never used on the GPU box).
 ``gen_golden``       regenerates tests/golden/*.npz from the imported reference.
