@@ -662,3 +662,84 @@ def test_temp_gru_model_with_sed_tagger(temp_gru):
     pert0 = bd.greedy_decode(dsd, enc["fc_emb"] * 1.001, enc["attn_emb"] * 0.999, enc["attn_emb_len"], torch.zeros(4, dtype=torch.long), 20)["seq"]
     st0 = (ref0 == pert0).all(1)
     assert (low[st0] == ref0[st0]).all()
+
+
+# ------------------------------------------------------------------ edge cases of the widened paths
+def test_cnn14_minimal_and_odd_lengths(cnn14_mirror):
+    """Shortest legal clip (32 frames -> 1 output frame) and frame counts that leave odd sizes at every pooling stage."""
+    from oracle import cnn14 as oc
+    m, sd, _ = cnn14_mirror
+    for n in (31 * 320, 77 * 320 + 123, 191 * 320 + 7):
+        wav, lens = cm.synth_wav(2, n, seed=n % 97, ragged=False, varied=True, sample_rate=32000)
+        with torch.no_grad():
+            out = m({"wav": wav.to(DEV), "wav_len": lens, "specaug": False})
+        ref = oc.forward(sd, wav, lens)
+        assert out["attn_emb"].shape == ref["attn_emb"].shape and out["attn_emb_len"].tolist() == ref["attn_emb_len"].tolist()
+        for k in ("attn_emb", "fc_emb"):
+            assert (out[k].cpu() - ref[k]).abs().max() < 1e-4 * ref[k].abs().max(), (n, k)
+
+
+def test_widened_paths_empty_batch_and_bad_arguments():
+    from audiocaption_b200 import _lib
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    from audiocaption_b200.captioning.models.rnn_encoder import RnnEncoder
+    from oracle import bah_decoder as bd, crnn
+    l = _lib.lib()
+    st = _lib.current_stream()
+    # empty batches are no-ops (rc 0) on every new entry point
+    assert l.ac_cnn14_fwd(None, None, 0, 64, 1001, None, None, None, None, 0, st) == 0
+    assert l.ac_bigru_fwd(None, None, None, 0, 31, 31, None, None, 0, st) == 0
+    assert l.ac_bah_greedy(None, None, None, None, None, 0, 31, 20, 1, 2, None, None, None, None, 0, st) == 0
+    assert l.ac_sed_fwd(None, None, 0, 64, 1001, 0.75, 0.25, None, None, None, 0, None, None, 0, st) == 0
+    # argument errors are reported, not crashed on
+    x = torch.zeros(4, device=DEV)
+    assert l.ac_conv3x3(_lib.ptr(x), _lib.ptr(x), None, None, _lib.ptr(x), 1, 4, 4, 24, 32, 2, st) != 0      # Cin % 32
+    assert b"Cin" in l.ac_last_error()
+    assert l.ac_cnn14_fwd(None, None, 1, 40, 1001, None, None, None, None, 0, st) != 0                         # 40 mel bins
+    assert l.ac_bah_beam(None, None, None, None, None, 1, 31, 20, 9, 1.0, 1, 2, None, None, 0, st) != 0        # beam 9
+    assert l.ac_bah_greedy(None, None, None, None, None, 1, 200, 20, 1, 2, None, None, None, None, 0, st) != 0  # T too long
+    # RnnEncoder: a zero length is rejected before the launch; one-frame clips work
+    sd = crnn.build_gru_state_dict(21)
+    m = RnnEncoder(-1, 2048, 2048, bidirectional=True, hidden_size=256, dropout=0.5, num_layers=3).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    xx = torch.randn(2, 3, 2048, generator=torch.Generator().manual_seed(0)).abs()
+    with pytest.raises(_lib.AudioCaptionB200Error):
+        m({"attn": xx.to(DEV), "attn_len": torch.tensor([0, 3])})
+    out = m({"attn": xx.to(DEV), "attn_len": torch.tensor([1, 1])})
+    ref = crnn.rnn_encoder(sd, xx, torch.tensor([1, 1]))
+    assert out["attn_emb"].shape == (2, 1, 512) and (out["attn_emb"].cpu() - ref["attn_emb"]).abs().max() < 5e-5
+    # GRU-attention decoder: one memory frame, one decode step
+    dsd = bd.build_state_dict(8)
+    dec = hw.TemporalBahAttnDecoder(emb_dim=512, vocab_size=4981, fc_emb_dim=512, attn_emb_dim=512, rnn_type="GRU",
+                                    num_layers=1, d_model=512, dropout=0.5).eval()
+    dec.load_state_dict(dsd, strict=True)
+    dec = dec.to(DEV)
+    fc, attn, lens, tags = bd.synth_memory(9, 3, 1)
+    got = dec.greedy(fc.to(DEV), attn.to(DEV), lens, tags, 1, 1, 2)
+    ref = bd.greedy_decode(dsd, fc, attn, lens, tags, 1)
+    assert (got["seq"].cpu() == ref["seq"]).all()
+    assert (got["logit"].cpu() - ref["logit"]).abs().max() < 2e-4
+    b = dec.beam_search(fc.to(DEV), attn.to(DEV), lens, tags, 1, 3, 1.0, 1, 2)["seq"].cpu()
+    assert (b == bd.beam_search(dsd, fc, attn, lens, tags, 3, 1, 1.0)["seq"]).all()
+
+
+def test_sed_short_clip_and_batch_independence():
+    """16-frame minimum (4 segments), an odd frame count, and bitwise independence of a clip from its batch neighbours."""
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    from oracle import cnn14 as oc, sed
+    sd = sed.build_state_dict(12)
+    m = hw.Cnn8rnnSedModel(447).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    cnn_sd = oc.build_state_dict(3)
+    for n in (15 * 320, 130 * 320 + 50):
+        wav, _ = cm.synth_wav(3, n, seed=n % 89, varied=True, sample_rate=32000)
+        lms = oc.log_mel(cnn_sd, wav)
+        out = m.forward_prob(lms.to(DEV))
+        seg, frame = sed.forward_prob(sd, lms)
+        assert out["segmentwise_output"].shape == seg.shape and out["framewise_output"].shape == frame.shape
+        assert (out["segmentwise_output"].cpu() - seg).abs().max() < 2e-4
+        one = m.forward_prob(lms[1:2].to(DEV))["segmentwise_output"]
+        assert torch.equal(one, out["segmentwise_output"][1:2])
+        assert len(m(lms.to(DEV))) == 3
