@@ -63,6 +63,9 @@ struct TcParams {
     // epilogue warps add the segments in fp32 (round-to-nearest).  The tensor core truncates when it accumulates, a
     // bias that grows linearly with the number of MMAs: ~2e-4 relative over K = 18432, ~5e-6 over a 512-wide segment.
     int seg_chunks;
+    // merge != 0: the TMEM A ring has as many slots as there are smem stages, slot index == stage index, and ONE
+    // tcgen05.commit per chunk (on bar_empty) releases both (every commit costs the issuing thread ~165 cycles)
+    int merge;
     long long* dbg;   // optional pipeline trace of CTA 0 (AC_TC_TRACE): [event kind 0..7][256] clock64 stamps
 };
 
@@ -110,6 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t bar_w = bars + 256u;
     const uint32_t tmem_slot_addr = bars + 264u;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot_addr - raw));
+    volatile int* s_ready = reinterpret_cast<volatile int*>(smem_raw + (tmem_slot_addr + 4u - raw));   // chunks cleared for the MMA issuer
     float* bias_all = reinterpret_cast<float*>(smem_raw + (bars + TC_BAR_BYTES - raw));   // [EPI_WARPS][TC_MAX_BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,6 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_init(bar_acc_empty(a), TC_EPI_WARPS);
         }
         mbar_init(bar_w, 1);
+        *s_ready = 0;
         fence_mbar_init();
     } else if (warp == 2) {
         tmem_alloc(tmem_slot_addr, (uint32_t)p.tmem_cols);
@@ -176,6 +181,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
         }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ gatekeeper: does the MMA issuer's barrier waits
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            int n = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    if (!p.resident) mbar_wait(bar_tma(stage), phase);
+                    mbar_wait(bar_axf(as), aphase);
+                    ++n;
+                    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(tmem_slot_addr + 4u), "r"(n) : "memory");
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+                }
+            }
+        }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         // The whole warp runs this loop converged (all operands are warp-uniform, so descriptors live in uniform
@@ -190,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int as = 0; uint32_t aphase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         int ev = 0;
+        int n_issued = 0;
         if (p.resident) mbar_wait(bar_w, 0u);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             uint32_t d_tmem = 0;
@@ -200,8 +223,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tc_fence_after();
                     d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                 }
-                if (!p.resident) mbar_wait(bar_tma(stage), phase);   // streamed weight chunk landed
-                mbar_wait(bar_axf(as), aphase);                      // A chunk split into hi / lo (TMEM)
+                {   // chunk cleared by the gatekeeper (plain shared-memory flag: no mbarrier instruction on this thread)
+                    int seen;
+                    do {
+                        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(seen) : "r"(tmem_slot_addr + 4u) : "memory");
+                    } while (seen <= n_issued);
+                    ++n_issued;
+                }
                 tc_fence_after();
                 if (lane == 0) AC_TC_STAMP(3, ev);
                 const uint32_t sa = stage0 + stage * stage_bytes;
@@ -222,8 +250,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh0 + 2u * ks, idesc, 1u);
                         }
                     }
+                    AC_TC_STAMP(7, ev);
                     mma_commit(bar_empty(stage));         // smem stage reusable once these MMAs retire
-                    mma_commit(bar_aempty(as));           // ... and so is the TMEM A slot
+                    if (!p.merge) mma_commit(bar_aempty(as));   // ... and so is the TMEM A slot
                     if (seg_end) mma_commit(bar_acc_full(acc));
                 }
                 __syncwarp();
@@ -294,7 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     lo[4 * j + e] = __float_as_uint(x[e] - h);
                 }
             }
-            mbar_wait(bar_aempty(as), aphase ^ 1u);        // the tensor core is done with this TMEM A slot
+            if (p.merge) mbar_wait(bar_empty(stage), phase ^ 1u);   // (slot == stage: released together)
+            else mbar_wait(bar_aempty(as), aphase ^ 1u);   // the tensor core is done with this TMEM A slot
             tc_fence_after();
             tmem_st16(a_ring + (uint32_t)as * 64u, hi);
             tmem_st16(a_ring + (uint32_t)as * 64u + 32u, lo);
@@ -613,6 +643,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.acc_stages = w.BN <= 64 ? TC_MAX_ACC : 2;
     p.a_slots = std::min(4, (512 - p.acc_stages * w.BN) / 64);
     AC_REQUIRE(p.a_slots >= 2, "gemm_tc: BN=%d leaves no tensor memory for the A operand", w.BN);
+    p.merge = p.stages <= p.a_slots ? 1 : 0;
+    if (p.merge) p.a_slots = p.stages;
     const size_t smem = (size_t)p.stages * sb + fixed;
 
     const int grid = std::min(p.m_tiles * p.n_tiles, kNumSMs);
@@ -696,6 +728,8 @@ int conv3x3_tc(const Conv3Args& a, cudaStream_t st) {
     p.tmem_cols = 512;
     p.acc_stages = w.BN <= 64 ? TC_MAX_ACC : 2;
     p.a_slots = std::min(4, (512 - p.acc_stages * w.BN) / 64);
+    p.merge = p.stages <= p.a_slots ? 1 : 0;
+    if (p.merge) p.a_slots = p.stages;
     const size_t smem = (size_t)p.stages * sb + fixed;
     const int grid = std::min(p.m_tiles * p.n_tiles, kNumSMs);
     AC_TIMED("conv3x3_tc", st);

@@ -83,7 +83,8 @@ int ac_gemm(const float* A_dev, const float* W_dev, float* C_dev, int M, int N, 
             const float* R_dev, int act, int path, void* stream);
 
 /* Diagnostic: pipeline trace of CTA 0 of the tensor-core GEMM (clock64 stamps, 8 event kinds x 256 events:
- * 0 TMA issue, 1 chunk landed, 2 transform done, 3 MMA start, 4 MMA issued, 5 accumulator full, 6 epilogue done).
+ * 0 TMA issue, 1 chunk landed, 2 transform done, 3 MMA start, 4 MMAs + commits issued, 5 accumulator full, 6 epilogue done,
+ * 7 MMAs issued (before the commits)).
  * on != 0 enables tracing for subsequent launches; out_host (nullable, 2048 int64) receives and clears the trace. */
 int ac_gemm_trace(int on, long long* out_host);
 

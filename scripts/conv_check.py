@@ -68,3 +68,20 @@ if mode == "one":
     B, H, W, Cin, Cout = [int(x) for x in sys.argv[2:7]]
     run(B, H, W, Cin, Cout, check=False, reps=2)
     print("one done")
+if mode == "trace":
+    import numpy as np
+    B, H, W, Cin, Cout = [int(x) for x in sys.argv[2:7]]
+    run(B, H, W, Cin, Cout, check=False)
+    lib.ac_gemm_trace(1, None)
+    run(B, H, W, Cin, Cout, check=False)
+    buf = np.zeros((8, 256), dtype=np.int64)
+    lib.ac_gemm_trace(0, buf.ctypes.data)
+    t0 = buf[buf > 0].min()
+    n = int((buf[3] > 0).sum())
+    print(f"conv trace B={B} H={H} W={W} Cin={Cin} Cout={Cout}: {n} chunks")
+    prev_commit = None
+    for i in range(min(n, 60)):
+        st, iss, com = int(buf[3][i] - t0), int(buf[7][i] - t0), int(buf[4][i] - t0)
+        gap = st - prev_commit if prev_commit is not None else 0
+        print(f"{i:3d} landed={int(buf[1][i]-t0):7d} xf_done={int(buf[2][i]-t0):7d} mma_start={st:7d} issue={iss-st:5d} commits={com-iss:5d} wait_gap={gap:5d}")
+        prev_commit = com
