@@ -23,6 +23,10 @@
 //                4 KB shared-memory slab and out with one TMA tensor store (coalesced, clipped at M/N).
 //                Overlaps the next tile's main loop.
 //   warp 2       TMEM allocator.
+//   warp 3       gatekeeper: executes the mbarrier waits that gate each k-chunk (weights landed, A slot filled,
+//                accumulator free) on behalf of the MMA issuer and publishes a running count in shared memory; the
+//                issuer only polls that word -- an mbarrier.try_wait issued behind tcgen05.commit costs it 150-350
+//                cycles even when the phase completed long ago ("The MMA issuer's instruction stream").
 #include <cudaTypedefs.h>
 
 #include <algorithm>
