@@ -15,14 +15,14 @@
 //                128B swizzle makes the row-per-lane reads conflict-free), a *= SE gate, hi = tf32(a),
 //                lo = a - hi, and writes both images straight into TENSOR MEMORY (tcgen05.st) -- the A operand
 //                never goes back to shared memory; the gate values of the next chunk are prefetched.
-//   warp 1       MMA issuer: tcgen05.mma kind::tf32 with A from TMEM and W from shared memory, M=128, N=BN,
-//                K=8 per instruction, 3 per k-step (lo*hi, hi*lo, hi*hi); accumulators double-buffered in
-//                TMEM; tcgen05.commit releases the smem stage and the TMEM A slot.
+//   warps 1, 2   MMA issuers, alternating k-chunks (warp 2 also allocates the tensor memory): tcgen05.mma kind::tf32
+//                with A from TMEM and W from shared memory, M=128, N=BN, K=8 per instruction, 3 per k-step (lo*hi,
+//                hi*lo, hi*hi); accumulators double-buffered in TMEM; tcgen05.commit releases the smem stage and the
+//                TMEM A slot.  A commit parks its thread while the pipe drains, hence two issuers in ping-pong.
 //   warps 4-11   epilogue (two warps per TMEM lane quarter, alternating 32-column panels): tcgen05.ld,
 //                folded BN scale/bias, swish/relu, residual, then the panel goes through a 128B-swizzled
 //                4 KB shared-memory slab and out with one TMA tensor store (coalesced, clipped at M/N).
 //                Overlaps the next tile's main loop.
-//   warp 2       TMEM allocator.
 //   warp 3       gatekeeper: executes the mbarrier waits that gate each k-chunk (weights landed, A slot filled,
 //                accumulator free) on behalf of the MMA issuer and publishes a running count in shared memory; the
 //                issuer only polls that word -- an mbarrier.try_wait issued behind tcgen05.commit costs it 150-350
@@ -140,6 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         mbar_init(bar_w, 1);
         *s_ready = 0;
+        s_ready[1] = 0;                                  // "MMAs issued" chunk count (issuer ping-pong)
         fence_mbar_init();
     } else if (warp == 2) {
         tmem_alloc(tmem_slot_addr, (uint32_t)p.tmem_cols);
@@ -191,19 +192,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             int n = 0;
+            int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int in_seg = 0;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    if (in_seg == 0) mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);   // the segment's accumulator is free
                     if (!p.resident) mbar_wait(bar_tma(stage), phase);
                     mbar_wait(bar_axf(as), aphase);
                     ++n;
+                    ++in_seg;
+                    if (kc + 1 == p.k_chunks || (CONV && in_seg == p.seg_chunks)) {
+                        in_seg = 0;
+                        if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+                    }
                     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(tmem_slot_addr + 4u), "r"(n) : "memory");
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------------------ MMA issuers (two warps, alternating k-chunks)
+        // tcgen05.commit parks the thread that executes it for ~330 cycles while the tensor pipe drains, so ONE issuer
+        // leaves the pipe idle between chunks.  Two issuers ping-pong: while one sits in its commit the other (which has
+        // seen the gatekeeper's clearance and the first one's "MMAs issued" flag) is already feeding the next chunk.
+        // MMAs reach the pipe in flag order, and the pipe retires them in order, so a commit by either thread also
+        // covers the other thread's earlier chunks.
+        const int me = warp - 1;
         // The whole warp runs this loop converged (all operands are warp-uniform, so descriptors live in uniform
         // registers and nothing is recomputed per lane); one elected lane issues the tcgen05 instructions.  The MMA
         // thread's own instruction stream is the limiter for small N, so the per-instruction work is kept minimal:
@@ -215,27 +230,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int stage = 0; uint32_t phase = 0;
         int as = 0; uint32_t aphase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        int ev = 0;
-        int n_issued = 0;
+        int n_chunk = 0;                                  // running chunk index of this CTA (both issuers count all)
         if (p.resident) mbar_wait(bar_w, 0u);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             uint32_t d_tmem = 0;
             int in_seg = 0;                                   // chunk index within the current accumulation segment
             for (int kc = 0; kc < p.k_chunks; ++kc) {
-                if (in_seg == 0) {                            // (pointwise: one segment = the whole k loop)
-                    mbar_wait(bar_acc_empty(acc), acc_phase ^ 1u);
-                    tc_fence_after();
-                    d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                }
-                {   // chunk cleared by the gatekeeper (plain shared-memory flag: no mbarrier instruction on this thread)
+                if (in_seg == 0) d_tmem = tmem_base + (uint32_t)(acc * p.BN);   // (the gatekeeper checked that it is free)
+                const bool mine = (n_chunk & 1) == me;
+                if (mine) {
+                    // chunk cleared by the gatekeeper, previous chunk's MMAs issued by the other warp (plain shared-memory
+                    // words: no mbarrier instruction on the issuing threads)
                     int seen;
                     do {
                         asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(seen) : "r"(tmem_slot_addr + 4u) : "memory");
-                    } while (seen <= n_issued);
-                    ++n_issued;
+                    } while (seen <= n_chunk);
+                    do {
+                        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(seen) : "r"(tmem_slot_addr + 8u) : "memory");
+                    } while (seen < n_chunk);
+                    tc_fence_after();
                 }
-                tc_fence_after();
-                if (lane == 0) AC_TC_STAMP(3, ev);
+                if (mine && lane == 0) AC_TC_STAMP(3, n_chunk);
                 const uint32_t sa = stage0 + stage * stage_bytes;
                 const uint32_t a_hi = a_ring + (uint32_t)as * 64u, a_lo = a_hi + 32u;
                 const uint32_t w_hi = p.resident ? w_res + kc * w_chunk_bytes : sa + TC_A_TILE_BYTES;
@@ -244,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint64_t dwl0 = desc_hi_bits | (uint64_t)((w_lo & 0x3ffffu) >> 4);
                 const int ksteps = min(TC_BK / 8, (p.K - kc * TC_BK) / 8);
                 const bool seg_end = kc + 1 == p.k_chunks || (CONV && in_seg + 1 == p.seg_chunks);
-                if (leader) {
+                if (leader && mine) {
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
                         if (ks < ksteps) {
@@ -254,14 +269,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh0 + 2u * ks, idesc, 1u);
                         }
                     }
-                    AC_TC_STAMP(7, ev);
+                    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(tmem_slot_addr + 8u), "r"(n_chunk + 1) : "memory");
+                    AC_TC_STAMP(7, n_chunk);
                     mma_commit(bar_empty(stage));         // smem stage reusable once these MMAs retire
                     if (!p.merge) mma_commit(bar_aempty(as));   // ... and so is the TMEM A slot
                     if (seg_end) mma_commit(bar_acc_full(acc));
                 }
                 __syncwarp();
-                if (lane == 0) { AC_TC_STAMP(4, ev); }
-                ++ev;
+                if (mine && lane == 0) { AC_TC_STAMP(4, n_chunk); }
+                ++n_chunk;
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
                 ++in_seg;
