@@ -56,7 +56,6 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 127u) & ~127u;
-    uint8_t* tiles_gen = smem_raw + (base - raw);
     const uint32_t bars = base + p.stages * p.tile_bytes;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 32u + 8u * s; };

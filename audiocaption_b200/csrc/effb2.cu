@@ -131,122 +131,8 @@ stem_kernel(const float* __restrict__ lms, const float* __restrict__ gmax, float
     reinterpret_cast<float4*>(out)[idx] = o;
 }
 
-// ----------------------------------------------------------------------------- depthwise
-// in [B,Hi,Wi,C] -> out [B,Ho,Wo,C], k x k stride s ("static same" pads), BN + swish, plus the per-segment
-// channel sums that feed squeeze-and-excitation: partial[b][ho * nseg + seg][c] (deterministic).
-//
-// One thread owns V consecutive channels of one output row and walks a segment of `lw` output pixels along
-// W with a K x K register window: per output it loads only the S new input columns (K*S vectors instead of
-// K*K), the K*K weights stay in registers.  Threads are laid out channel-fastest, then output row, so a warp
-// reads contiguous channel runs (coalesced 128-bit loads) and the K-row vertical overlap between neighbouring
-// output rows is served by L1 inside the CTA.
-template <int V> struct VecT;
-template <> struct VecT<4> { typedef float4 type; };
-template <> struct VecT<2> { typedef float2 type; };
-template <int V> __device__ __forceinline__ void vec_fma(float (&acc)[V], const float (&x)[V], const float (&w)[V]) {
-#pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = fmaf(x[e], w[e], acc[e]);
-}
-template <int V> __device__ __forceinline__ void vec_load(float (&d)[V], const float* p) {
-    typedef typename VecT<V>::type T;
-    *reinterpret_cast<T*>(d) = __ldg(reinterpret_cast<const T*>(p));
-}
-
-template <int K, int S, int V>
-__global__ void __launch_bounds__(K == 3 ? 256 : 128, K == 3 ? 2 : 3)
-dwconv_kernel(const float* __restrict__ in, const float* __restrict__ w /*[K*K][C]*/,
-              const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ out,
-              float* __restrict__ partial, int Hi, int Wi, int Ho, int Wo, int C, int pad_lo, int lw, int nseg,
-              int64_t total) {
-    // Scatter form of the sliding window: the thread reads ONE input column (K rows, V channels) per step and
-    // adds it into the <= K output pixels it touches (ring of K accumulators); an output is finished when its
-    // last column has been added.  Registers: K*K weights + one column + K accumulators -- no window copy.
-    typedef typename VecT<V>::type T;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cvn = C / V;
-    const int c = (int)(idx % cvn) * V;
-    int64_t r = idx / cvn;
-    const int ho = (int)(r % Ho); r /= Ho;
-    const int seg = (int)(r % nseg);
-    const int b = (int)(r / nseg);
-    const int wo0 = seg * lw, n_out = min(lw, Wo - wo0);
-
-    float wr[K * K][V];
-#pragma unroll
-    for (int q = 0; q < K * K; ++q) vec_load<V>(wr[q], w + (size_t)q * C + c);
-    float sc[V], bi[V];
-    vec_load<V>(sc, scale + c);
-    vec_load<V>(bi, bias + c);
-
-    const int ih0 = ho * S - pad_lo;
-    const int iw0 = wo0 * S - pad_lo;              // input column of relative column 0
-    bool rv[K];
-#pragma unroll
-    for (int kh = 0; kh < K; ++kh) rv[kh] = (ih0 + kh >= 0) && (ih0 + kh < Hi);
-    // pointer to (row ih0, column iw0) of this clip / channel run; rows are Wi*C apart (may point outside the
-    // tensor for padded rows / columns: those loads are predicated off)
-    const float* pc = in + ((int64_t)(b * Hi + ih0) * Wi + iw0) * C + c;
-    const int rstride = Wi * C;
-    float* orow = out + ((size_t)(b * Ho + ho) * Wo + wo0) * C + c;
-
-    float acc[K][V];
-    float sum[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) sum[e] = 0.0f;
-    const int n_cols = (n_out - 1) * S + K;        // input columns this segment touches
-    constexpr int G = K * S;                        // unroll period: every slot / tap index is a constant
-    for (int base = 0; base < n_cols; base += G) {
-#pragma unroll
-        for (int jj = 0; jj < G; ++jj) {
-            const int j = base + jj;
-            if (j < n_cols) {
-                const int iw = iw0 + j;
-                const bool cok = iw >= 0 && iw < Wi;
-                float x[K][V];
-#pragma unroll
-                for (int kh = 0; kh < K; ++kh) {
-                    if (cok && rv[kh]) vec_load<V>(x[kh], pc + (int64_t)kh * rstride + (int64_t)j * C);
-                    else {
-#pragma unroll
-                        for (int e = 0; e < V; ++e) x[kh][e] = 0.0f;
-                    }
-                }
-#pragma unroll
-                for (int kw = 0; kw < K; ++kw) {
-                    if ((jj - kw) % S != 0) continue;           // this column is not tap kw of any output
-                    // output u = (j - kw) / S, ring slot u % K; both compile-time given jj (base % (K*S) == 0)
-                    constexpr int dummy = 0; (void)dummy;
-                    const int slot = ((((jj - kw) / S) % K) + K) % K;
-                    float t[V];
-#pragma unroll
-                    for (int e = 0; e < V; ++e) t[e] = x[0][e] * wr[kw][e];
-#pragma unroll
-                    for (int kh = 1; kh < K; ++kh) vec_fma<V>(t, x[kh], wr[kh * K + kw]);
-#pragma unroll
-                    for (int e = 0; e < V; ++e) acc[slot][e] = (kw == 0) ? t[e] : acc[slot][e] + t[e];
-                    if (kw == K - 1) {                          // last tap: output u is complete
-                        const int u = (j - kw) / S;
-                        if (j >= kw && u < n_out) {
-                            float o[V];
-#pragma unroll
-                            for (int e = 0; e < V; ++e) {
-                                o[e] = fast_swish(fmaf(acc[slot][e], sc[e], bi[e]));
-                                sum[e] += o[e];
-                            }
-                            *reinterpret_cast<T*>(orow + (size_t)u * C) = *reinterpret_cast<const T*>(o);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    *reinterpret_cast<T*>(partial + ((size_t)b * (Ho * nseg) + (size_t)ho * nseg + seg) * C + c) =
-        *reinterpret_cast<const T*>(sum);
-}
-
-// ----------------------------------------------------------------------------- squeeze-excite
-// partial [B][strips][C] -> gate [B][C] = sigmoid(We * swish(Wr * mean + br) + be).
+// ----------------------------------------------------------------------------- squeeze-and-excitation
+// (the depthwise convolution itself lives in dwconv_tma.cu)
 // One thread-block CLUSTER per clip (P = 1..8 CTAs): every CTA owns 1/P of the channels (mean and gate) and
 // 1/P of the squeezed units, so each CTA streams only 1/P of the two FC weight matrices; the mean vector and
 // the squeezed vector are exchanged through distributed shared memory between the phases.
@@ -426,17 +312,6 @@ static void walk(int n_mels, int n_frames, Dims& stem, std::vector<Dims>& in_dim
     }
 }
 
-// Output pixels one depthwise thread walks along W: long segments amortise the K-1 halo columns, short ones
-// keep >= ~4 CTAs per SM in flight on the small late layers.
-static int dw_seg_len(int batch, int Ho, int Wo, int C, int k) {
-    const int V = k == 3 ? 4 : 2;
-    for (int lw = 32; lw > 8; lw /= 2) {
-        const int64_t threads = (int64_t)batch * Ho * cdiv(Wo, lw) * (C / V);
-        if (threads >= (int64_t)kNumSMs * 4 * 256) return lw;
-    }
-    return 8;
-}
-
 struct WsLayout { size_t x_elems, e_elems, d_elems, part_elems, gate_elems, head_elems; };
 
 static WsLayout ws_layout(int batch, int n_mels, int n_frames) {
@@ -459,28 +334,6 @@ static WsLayout ws_layout(int batch, int n_mels, int n_frames) {
     L.x_elems *= batch; L.e_elems *= batch; L.d_elems *= batch; L.part_elems *= batch;
     L.gate_elems *= batch; L.head_elems *= batch;
     return L;
-}
-
-static int launch_dw(const float* in, const ConvBN& cw, float* out, float* partial, int B, Dims di, Dims dd,
-                     int C, const BlockPlan& bp, cudaStream_t st) {
-    const int lw = dw_seg_len(B, dd.H, dd.W, C, bp.k);
-    const int nseg = cdiv(dd.W, lw);
-    const int V = bp.k == 3 ? 4 : 2;
-    const int64_t total = (int64_t)B * nseg * dd.H * (C / V);
-    const int threads = bp.k == 3 ? 256 : 128;
-    const unsigned grid = (unsigned)cdiv64(total, threads);
-    AC_TIMED(bp.k == 3 ? "dwconv_k3" : "dwconv_k5", st);
-#define AC_DW(K, S, V)                                                                                             \
-    dwconv_kernel<K, S, V><<<grid, threads, 0, st>>>(in, cw.w, cw.scale, cw.bias, out, partial, di.H, di.W, dd.H, dd.W, C, \
-                                                 bp.pad_lo, lw, nseg, total)
-    if (bp.k == 3 && bp.s == 1) AC_DW(3, 1, 4);
-    else if (bp.k == 3 && bp.s == 2) AC_DW(3, 2, 4);
-    else if (bp.k == 5 && bp.s == 1) AC_DW(5, 1, 2);
-    else if (bp.k == 5 && bp.s == 2) AC_DW(5, 2, 2);
-    else { set_error("launch_dw: unsupported depthwise k=%d s=%d", bp.k, bp.s); return AC_ERR_ARG; }
-#undef AC_DW
-    AC_LAUNCHED("dwconv_kernel");
-    return AC_OK;
 }
 
 }  // namespace ac

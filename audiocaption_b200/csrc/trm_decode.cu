@@ -199,7 +199,7 @@ __device__ void decoder_step(const DecodeArgs& a, int clip, int t, const int* wo
     const DecW& W = a.w;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), P = (int)cluster.num_blocks();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     auto clip_of = [&](int r) { return min(clip + r / RPC, a.n_clips - 1); };   // rows past the batch replay the last clip
     auto n_mem_of = [&](int r) { return min((int)min((int64_t)a.t_mem, a.mem_len[clip_of(r)]), a.t_mem); };
     AC_DEC_STAMP(0);
