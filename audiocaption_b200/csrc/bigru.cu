@@ -13,10 +13,13 @@
 //   1. the input projections of BOTH directions for all time steps as one tensor-core GEMM (gemm_tc, 3xTF32):
 //      G[b*T + t, dir*3H + gate*H + u] = W_ih x + b_ih;
 //   2. the recurrence: one 8-CTA cluster per (direction, group of 8 clips).  CTA c of a cluster owns hidden units
-//      [32c, 32c+32): its 96 rows of W_hh stay in shared memory (96 KB) for the whole sequence, the hidden state of
-//      the group (8 x 256) is replicated in every CTA and refreshed through distributed shared memory after each
-//      step (one cluster barrier per step).  Latency-bound by construction (T sequential steps); the batch is
-//      spread over 2 x ceil(B/8) clusters so all SMs work at batch 64.
+//      [32c, 32c+32): its 96 rows of W_hh stay in shared memory (97 KB, rows padded to 97 floats so that both the
+//      transposing fill and the matvec reads are bank-conflict-free) for the whole sequence; the hidden state of the
+//      group (8 x 256) is replicated in every CTA.  Per step: 384 threads compute the 96 x 8 dot products (row x clip
+//      half x k half), 256 threads apply the gates, then the CTA's contiguous 1 KB state slice goes to the 7 peers as
+//      128-bit distributed-shared-memory stores and one cluster barrier closes the step (4 us per step at 16 clips;
+//      measured split before this layout: matvec 45 %, scalar remote stores 25 %, barrier 10 %).  Latency-bound by
+//      construction (T sequential steps); the batch is spread over 2 x ceil(B/8) clusters.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -33,8 +36,9 @@ constexpr int kGruCluster = 8;
 constexpr int kGruUnits = kGruH / kGruCluster;   // 32 hidden units per CTA
 constexpr int kGruRows = 3 * kGruUnits;          // 96 rows of W_hh per CTA (r, z, n)
 constexpr int kGruClips = 8;          // clips per cluster
-constexpr int kGruThreads = 256;
-constexpr size_t kGruSmem = ((size_t)kGruH * kGruRows + 2 * kGruH * kGruClips + kGruRows * kGruClips) * sizeof(float);
+constexpr int kGruThreads = 512;
+constexpr int kGruWtStride = kGruRows + 1;       // 97: conflict-free transposed staging AND conflict-free matvec reads
+constexpr size_t kGruSmem = ((size_t)kGruH * kGruWtStride + 2 * kGruH * kGruClips + 2 * kGruRows * kGruClips) * sizeof(float);
 
 struct GruStepArgs {
     const float* G;        // [B*T_in, 2*3H] input projections (+ b_ih), both directions
@@ -47,10 +51,10 @@ struct GruStepArgs {
 
 __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1)
 bigru_recurrence_kernel(const GruStepArgs a) {
-    extern __shared__ float gsm[];
-    float* Wt = gsm;                                  // [H k][96 j]   (transposed slice of W_hh)
-    float* Hs = Wt + kGruH * kGruRows;                // [2][H k][8 clips]  double-buffered hidden state
-    float* pre = Hs + 2 * kGruH * kGruClips;          // [96 j][8 clips]    W_hh h of this step
+    extern __shared__ __align__(16) float gsm[];
+    float* Hs = gsm;                                  // [2][H k][8 clips]  double-buffered hidden state (16-byte aligned)
+    float* pre = Hs + 2 * kGruH * kGruClips;          // [2 k-halves][96 j][8 clips]  partial W_hh h of this step
+    float* Wt = pre + 2 * kGruRows * kGruClips;       // [H k][97]   (transposed slice of W_hh, padded rows)
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank();          // owns hidden units [32c, 32c + 32)
     const int cl = blockIdx.x / kGruCluster;          // cluster index -> (direction, clip group)
@@ -62,21 +66,25 @@ bigru_recurrence_kernel(const GruStepArgs a) {
     // constants first (weights), then wait for the projection GEMM
     const float* W = a.whh[dir];
     for (int i = tid; i < kGruRows * kGruH; i += kGruThreads) {
-        const int j = i / kGruH, k = i % kGruH;       // coalesced along k
+        const int j = i / kGruH, k = i % kGruH;       // coalesced along k; smem bank = (k + j) % 32: conflict-free
         const int row = (j / kGruUnits) * kGruH + c * kGruUnits + (j % kGruUnits);
-        Wt[k * kGruRows + j] = __ldg(W + (size_t)row * kGruH + k);
+        Wt[k * kGruWtStride + j] = __ldg(W + (size_t)row * kGruH + k);
     }
     for (int i = tid; i < 2 * kGruH * kGruClips; i += kGruThreads) Hs[i] = 0.0f;
-    // cell-update role: thread = (unit u, clip bl)
-    const int u = tid % kGruUnits, bl = tid / kGruUnits;
+    // cell-update role (threads 0..255): thread = (unit u, clip bl)
+    const int u = tid % kGruUnits, bl = (tid / kGruUnits) % kGruClips;
+    const bool cell = tid < kGruUnits * kGruClips;
     const int b = b0 + bl;
-    const bool clip_ok = b < a.B;
+    const bool clip_ok = cell && b < a.B;
     const int unit = c * kGruUnits + u;
     const float bh_r = __ldg(a.bhh[dir] + unit), bh_z = __ldg(a.bhh[dir] + kGruH + unit), bh_n = __ldg(a.bhh[dir] + 2 * kGruH + unit);
     const int len = clip_ok ? (int)min((int64_t)a.T_out, max((int64_t)0, a.lens[b])) : 0;
     float h_own = 0.0f;
-    // matvec role: threads 0..191 = (row j, half of the clips)
-    const int mj = tid % kGruRows, mh = tid / kGruRows;
+    // matvec role (threads 0..383): (row j, half of the clips, half of k)
+    const int mj = tid % kGruRows, mq = tid / kGruRows;
+    const int mh = mq & 1, kq = mq >> 1;
+    // publish role (all 512 threads): float4 `pv` of this CTA's 1 KB state slice goes to peer `prk`
+    const int prk = tid >> 6, pv = tid & 63;
     pdl_wait();
     cluster.sync();
 
@@ -86,39 +94,47 @@ bigru_recurrence_kernel(const GruStepArgs a) {
         float* Hn = Hs + ((s + 1) & 1) * kGruH * kGruClips;
         // input-side pre-activations of this step: issue the loads before the matvec
         float gr = 0.f, gz = 0.f, gn = 0.f;
-        const bool active = t < len;
+        const bool active = cell && t < len;
         if (active) {
             const float* g = a.G + ((size_t)b * a.T_in + t) * (6 * kGruH) + dir * 3 * kGruH + unit;
             gr = __ldg(g); gz = __ldg(g + kGruH); gn = __ldg(g + 2 * kGruH);
         }
-        if (mh < 2) {
+        if (mq < 4) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* wp = Wt + mj;
-            const float4* hp = reinterpret_cast<const float4*>(Hc) + mh;
+            const float* wp = Wt + (kq * (kGruH / 2)) * kGruWtStride + mj;
+            const float4* hp = reinterpret_cast<const float4*>(Hc) + (kq * (kGruH / 2)) * 2 + mh;
 #pragma unroll 8
-            for (int k = 0; k < kGruH; ++k) {
-                const float w = wp[k * kGruRows];
+            for (int k = 0; k < kGruH / 2; ++k) {
+                const float w = wp[k * kGruWtStride];
                 const float4 h4 = hp[k * 2];
                 acc[0] = fmaf(w, h4.x, acc[0]); acc[1] = fmaf(w, h4.y, acc[1]);
                 acc[2] = fmaf(w, h4.z, acc[2]); acc[3] = fmaf(w, h4.w, acc[3]);
             }
-            *reinterpret_cast<float4*>(pre + mj * kGruClips + mh * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(pre + (kq * kGruRows + mj) * kGruClips + mh * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
         __syncthreads();
-        float h_new = h_own;
-        if (active) {
-            const float r = 1.0f / (1.0f + expf(-(gr + pre[u * kGruClips + bl] + bh_r)));
-            const float z = 1.0f / (1.0f + expf(-(gz + pre[(kGruUnits + u) * kGruClips + bl] + bh_z)));
-            const float n = tanhf(gn + r * (pre[(2 * kGruUnits + u) * kGruClips + bl] + bh_n));
-            h_new = (1.0f - z) * n + z * h_own;
+        if (cell) {
+            float h_new = h_own;
+            if (active) {
+                const float* p1 = pre + kGruRows * kGruClips;      // second k-half
+                const float pr = pre[u * kGruClips + bl] + p1[u * kGruClips + bl];
+                const float pz = pre[(kGruUnits + u) * kGruClips + bl] + p1[(kGruUnits + u) * kGruClips + bl];
+                const float pn = pre[(2 * kGruUnits + u) * kGruClips + bl] + p1[(2 * kGruUnits + u) * kGruClips + bl];
+                const float r = 1.0f / (1.0f + expf(-(gr + pr + bh_r)));
+                const float z = 1.0f / (1.0f + expf(-(gz + pz + bh_z)));
+                const float n = tanhf(gn + r * (pn + bh_n));
+                h_new = (1.0f - z) * n + z * h_own;
+            }
+            h_own = h_new;
+            if (clip_ok) a.out[((size_t)b * a.T_out + t) * (2 * kGruH) + dir * kGruH + unit] = active ? h_new : 0.0f;
+            Hn[unit * kGruClips + bl] = h_new;                 // own copy first ...
         }
-        h_own = h_new;
-        if (clip_ok) a.out[((size_t)b * a.T_out + t) * (2 * kGruH) + dir * kGruH + unit] = active ? h_new : 0.0f;
-        // publish this unit's new state into every CTA's next-step buffer
-#pragma unroll
-        for (int rk = 0; rk < kGruCluster; ++rk) {
-            float* remote = cluster.map_shared_rank(Hn, rk);
-            remote[unit * kGruClips + bl] = h_new;
+        __syncthreads();
+        // ... then the CTA's contiguous 1 KB slice (32 units x 8 clips) goes to the 7 peers as 128-bit stores
+        if (prk != c) {
+            const float4* src = reinterpret_cast<const float4*>(Hn + c * kGruUnits * kGruClips);
+            float4* dst = reinterpret_cast<float4*>(cluster.map_shared_rank(Hn, prk) + c * kGruUnits * kGruClips);
+            dst[pv] = src[pv];
         }
         cluster.sync();
     }
