@@ -25,6 +25,7 @@
 // = (prefix token == <pad>) and `memory_key_padding_mask` = (frame >= attn_emb_len) are applied
 // as -inf before the softmax exactly as nn.MultiheadAttention merges them.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -39,6 +40,12 @@ namespace ac {
 constexpr int kBeamCluster = 2;     // beam search: CTAs per clip (rows = beams of ONE clip)
 constexpr int kGreedyCluster = 2;   // greedy: CTAs per cluster ...
 constexpr int kGreedyClips = 1;     // ... which decodes this many clips at once (rows = clips)
+// Small batches leave SMs idle at 2 CTAs per clip: spread each clip's 12.4 MB of weights per step over 4 CTAs while
+// 4 x batch still fits the 148 SMs (AC_TRM_CLUSTER overrides for measurements).
+static int trm_cluster_size(int clips, int dflt) {
+    if (const char* e = getenv("AC_TRM_CLUSTER")) { const int p = atoi(e); if (p == 1 || p == 2 || p == 4 || p == 8) return p; }
+    return clips <= kNumSMs / 4 ? 4 : dflt;
+}
 constexpr int D = 256;          // d_model
 constexpr int NH = 4;           // heads
 constexpr int HD = 64;          // head dim
@@ -771,7 +778,7 @@ int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* att
     a.seq = seq; a.logprob = logprob; a.logit_out = logit; a.embed_out = embed; a.beam = 1; a.temp = 1.0f;
     a.dbg = g_dec_trace;
     // (CTAs per cluster, clips per cluster); AC_GREEDY="P,G" overrides for experiments
-    int P = kGreedyCluster, G = kGreedyClips;
+    int P = trm_cluster_size(batch, kGreedyCluster), G = kGreedyClips;
     if (const char* e = getenv("AC_GREEDY")) sscanf(e, "%d,%d", &P, &G);
     AC_REQUIRE((P == 1 || P == 2 || P == 4 || P == 8) && (G == 1 || G == 2 || G == 4), "ac_trm_greedy: bad cluster shape %d,%d", P, G);
     size_t sm = dec_smem_floats(G) * sizeof(float);
@@ -817,7 +824,7 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
 #define AC_BEAM_CASE(RR)                                                                                        \
     case RR:                                                                                                    \
         AC_CUDA(cudaFuncSetAttribute(beam_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
-        rc = launch_decode(beam_kernel<RR>, batch, kBeamCluster, sm, st, a); if (rc) return rc;                 \
+        rc = launch_decode(beam_kernel<RR>, batch, trm_cluster_size(batch, kBeamCluster), sm, st, a); if (rc) return rc; \
         break;
     switch (beam) {
         AC_BEAM_CASE(1) AC_BEAM_CASE(2) AC_BEAM_CASE(3) AC_BEAM_CASE(4) AC_BEAM_CASE(5)
