@@ -12,11 +12,26 @@ __version__ = "0.1.0"
 
 
 def install_as_captioning():
-    """Make ``import captioning.models...`` resolve to the B200 mirrors, so the reference's
-    YAML ``type:`` strings (captioning/utils/train_util.py:63-68) work unchanged."""
+    """Make ``import captioning.models...`` resolve to the B200 mirrors, so the reference's YAML ``type:`` strings
+    (captioning/utils/train_util.py:63-68 resolves them with importlib) work unchanged.
+
+    Every mirror module is imported under its real name first (their relative imports reach up to this package) and
+    then registered under the ``captioning.*`` alias; importing them lazily under the alias would re-execute the files
+    as a different top-level package.  Returns the list of aliased module names."""
+    import importlib
+    import pkgutil
     import sys
     from . import captioning
-    sys.modules.setdefault("captioning", captioning)
-    for name, mod in list(sys.modules.items()):
-        if name.startswith(__name__ + ".captioning."):
-            sys.modules.setdefault(name[len(__name__) + 1:], mod)
+    prefix = captioning.__name__ + "."
+    names = [captioning.__name__] + [m.name for m in pkgutil.walk_packages(captioning.__path__, prefix)]
+    aliased = []
+    for name in names:
+        mod = importlib.import_module(name)
+        alias = name[len(__name__) + 1:]
+        other = sys.modules.get(alias)
+        if other is not None and other is not mod:
+            raise ImportError(f"install_as_captioning: a different module named {alias!r} is already imported "
+                              f"({getattr(other, '__file__', '?')}); install the alias before importing the reference")
+        sys.modules[alias] = mod
+        aliased.append(alias)
+    return aliased

@@ -33,7 +33,10 @@ class _Conv(nn.Module):
         self.out_channels = cout
 
 
-class _BN(nn.Module):
+class _BatchNormParams(nn.Module):
+    """Holder of eval-mode BatchNorm statistics (the class name contains "BatchNorm" so that
+    crnn_trm_encoder.py:195-203's `freeze_cnn_bn` walk finds it)."""
+
     def __init__(self, c):
         super().__init__()
         self.weight = nn.Parameter(torch.ones(c))
@@ -41,6 +44,9 @@ class _BN(nn.Module):
         self.register_buffer("running_mean", torch.zeros(c))
         self.register_buffer("running_var", torch.ones(c))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+_BN = _BatchNormParams
 
 
 class _MBConv(nn.Module):

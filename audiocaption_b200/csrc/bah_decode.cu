@@ -30,7 +30,7 @@ namespace ac {
 
 constexpr int BH = 512;            // embedding = hidden = attention = memory = fc width of the released model
 constexpr int BG = 3 * BH;
-constexpr int kBahMaxT = 64;       // memory frames
+constexpr int kBahMaxT = 128;      // memory frames (41 s of 32 kHz audio; s_sc is only R x kBahMaxT floats)
 constexpr int kBahMaxLen = 64;     // decode steps
 // CTAs per clip: small batches spread each clip's 17.5 MB of weights per step over more SMs, large ones keep one wave
 static int bah_cluster_size(int clips) {
@@ -222,7 +222,7 @@ bah_greedy_kernel(BahArgs a) {
     for (int i = tid; i < BH; i += kThreads) s_h[i] = 0.0f;      // init_hidden: zeros
     int word = a.start_idx;
     bool finished = false;
-    __syncthreads();
+    cluster.sync();   // every CTA of the cluster is resident before the first GEMV writes into its peers' shared memory
     // like the reference, a finished row keeps running (input forced to <end>) while logits are requested
     const bool full_outputs = a.logit_out != nullptr;
     for (int t = 0; t < a.max_len; ++t) {
@@ -281,7 +281,7 @@ bah_beam_kernel(BahArgs a) {
     if (tid < R) { s_tok[tid] = tag_tok; s_score[tid] = 0.f; s_logits[tid] = lp + (size_t)tid * Vp; s_parent[tid] = tid; }
     if (tid == 0) { s_ndone = 0; s_stop = 0; s_best_len = 0; s_best_score = -INFINITY; }
     for (int i = tid; i < R * BH; i += kThreads) s_h[i] = 0.0f;
-    __syncthreads();
+    cluster.sync();   // peers resident before the first distributed-shared-memory write (decode_common.cuh matvec_t)
     int cur = 0;
     for (int t = 0; t < a.max_len; ++t) {
         if (t > 0) {   // the state follows its parent beam (state[:, prev_words_beam, :])

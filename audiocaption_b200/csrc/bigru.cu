@@ -25,30 +25,15 @@
 #include <algorithm>
 #include <vector>
 
-#include "gemm.cuh"
+#include "bigru.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace ac {
 
-constexpr int kGruH = 256;            // hidden size (8 CTAs x 32 units)
-constexpr int kGruCluster = 8;
-constexpr int kGruUnits = kGruH / kGruCluster;   // 32 hidden units per CTA
-constexpr int kGruRows = 3 * kGruUnits;          // 96 rows of W_hh per CTA (r, z, n)
-constexpr int kGruClips = 8;          // clips per cluster
-constexpr int kGruThreads = 512;
-constexpr int kGruWtStride = kGruRows + 1;       // 97: conflict-free transposed staging AND conflict-free matvec reads
-constexpr size_t kGruSmem = ((size_t)kGruH * kGruWtStride + 2 * kGruH * kGruClips + 2 * kGruRows * kGruClips) * sizeof(float);
-
-struct GruStepArgs {
-    const float* G;        // [B*T_in, 2*3H] input projections (+ b_ih), both directions
-    const float* whh[2];   // [3H, H] per direction
-    const float* bhh[2];   // [3H]
-    const int64_t* lens;   // [B]
-    float* out;            // [B, T_out, 2H]
-    int B, T_in, T_out;
-};
-
+// SAVE (training, bigru_train.cu): also records what the backward pass needs -- the gates r, z, n, the hidden-side
+// candidate pre-activation hn = W_hn h + b_hn, and the previous hidden state of every (clip, frame, direction).
+template <bool SAVE>
 __global__ void __cluster_dims__(kGruCluster, 1, 1) __launch_bounds__(kGruThreads, 1)
 bigru_recurrence_kernel(const GruStepArgs a) {
     extern __shared__ __align__(16) float gsm[];
@@ -122,9 +107,15 @@ bigru_recurrence_kernel(const GruStepArgs a) {
                 const float pn = pre[(2 * kGruUnits + u) * kGruClips + bl] + p1[(2 * kGruUnits + u) * kGruClips + bl];
                 const float r = 1.0f / (1.0f + expf(-(gr + pr + bh_r)));
                 const float z = 1.0f / (1.0f + expf(-(gz + pz + bh_z)));
-                const float n = tanhf(gn + r * (pn + bh_n));
+                const float hn = pn + bh_n;
+                const float n = tanhf(gn + r * hn);
                 h_new = (1.0f - z) * n + z * h_own;
+                if (SAVE) {
+                    float* sv = a.save + (((size_t)b * a.T_out + t) * 2 + dir) * 4 * kGruH + unit;
+                    sv[0] = r; sv[kGruH] = z; sv[2 * kGruH] = n; sv[3 * kGruH] = hn;
+                }
             }
+            if (SAVE && clip_ok) a.hprev[((size_t)b * a.T_out + t) * (2 * kGruH) + dir * kGruH + unit] = active ? h_own : 0.0f;
             h_own = h_new;
             if (clip_ok) a.out[((size_t)b * a.T_out + t) * (2 * kGruH) + dir * kGruH + unit] = active ? h_new : 0.0f;
             Hn[unit * kGruClips + bl] = h_new;                 // own copy first ...
@@ -141,6 +132,24 @@ bigru_recurrence_kernel(const GruStepArgs a) {
 }
 
 struct GruLayer { float* wih; float* bih; TcWeight tw; float* whh[2]; float* bhh[2]; int din; };
+
+int bigru_recurrence_launch(const GruStepArgs& a, bool save, cudaStream_t st) {
+    static cudaError_t attr_rc = cudaFuncSetAttribute(bigru_recurrence_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmem);
+    static cudaError_t attr_rc2 = cudaFuncSetAttribute(bigru_recurrence_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmem);
+    AC_CUDA(attr_rc);
+    AC_CUDA(attr_rc2);
+    AC_REQUIRE(!save || (a.save != nullptr && a.hprev != nullptr), "bigru_recurrence_launch: save buffers missing");
+    const int groups = cdiv(a.B, kGruClips);
+    AC_TIMED("bigru_recurrence", st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * groups * kGruCluster); cfg.blockDim = dim3(kGruThreads); cfg.dynamicSmemBytes = kGruSmem; cfg.stream = st;
+    cudaLaunchAttribute at[1] = {pdl_attr()};
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (save) AC_CUDA(cudaLaunchKernelEx(&cfg, bigru_recurrence_kernel<true>, a));
+    else AC_CUDA(cudaLaunchKernelEx(&cfg, bigru_recurrence_kernel<false>, a));
+    AC_LAUNCHED("bigru_recurrence_kernel");
+    return AC_OK;
+}
 
 }  // namespace ac
 
@@ -233,8 +242,6 @@ int ac_bigru_fwd(const ac_bigru_t* net, const float* x, const int64_t* lens, int
     float* G = (float*)workspace;
     float* Y0 = G + align_up((size_t)B * T_in * 6 * H, 64);
     float* Y1 = Y0 + align_up((size_t)B * T_in * 2 * H, 64);
-    static cudaError_t attr_rc = cudaFuncSetAttribute(bigru_recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruSmem);
-    AC_CUDA(attr_rc);
     const float* in = x;
     int t_in = T_in;                       // time stride of the current layer's input
     for (int l = 0; l < net->layers; ++l) {
@@ -246,14 +253,7 @@ int ac_bigru_fwd(const ac_bigru_t* net, const float* x, const int64_t* lens, int
         GruStepArgs a;
         a.G = G; a.lens = lens; a.out = y; a.B = B; a.T_in = t_in; a.T_out = T_out;
         for (int d = 0; d < 2; ++d) { a.whh[d] = L.whh[d]; a.bhh[d] = L.bhh[d]; }
-        const int groups = cdiv(B, kGruClips);
-        AC_TIMED("bigru_recurrence", st);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * groups * kGruCluster); cfg.blockDim = dim3(kGruThreads); cfg.dynamicSmemBytes = kGruSmem; cfg.stream = st;
-        cudaLaunchAttribute at[1] = {pdl_attr()};
-        cfg.attrs = at; cfg.numAttrs = 1;
-        AC_CUDA(cudaLaunchKernelEx(&cfg, bigru_recurrence_kernel, a));
-        AC_LAUNCHED("bigru_recurrence_kernel");
+        rc = bigru_recurrence_launch(a, false, st); if (rc) return rc;
         in = y; t_in = T_out;              // the next layer reads [B, T_out, 2H]
     }
     return AC_OK;

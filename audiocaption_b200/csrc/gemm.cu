@@ -36,7 +36,7 @@ gemm_tn_kernel(GemmArgs g) {
             int row = m0 + r, k = k0 + kv;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (v < A_VECS && row < M && k < K) {
-                x = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * K + k));
+                x = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * (g.lda ? g.lda : K) + k));
                 if (g.ascale != nullptr) {
                     float4 s = __ldg(reinterpret_cast<const float4*>(
                         g.ascale + (size_t)(row / g.rows_per_group) * K + k));

@@ -30,6 +30,11 @@ size_t tc_packed_floats(int N, int K);
 int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, float* dst_dev, cudaStream_t st,
                    TcWeight* out);
 
+// Same, for a matrix seen through strides: element (n, k) is W_dev[n * sn + k * sk] (sn = 1, sk = ld packs the
+// TRANSPOSE of a row-major matrix: the backward GEMMs of the training path, train_ops.cu).
+int tc_pack_weight_strided(const float* W_dev, const float* scale_dev, int N, int K, int64_t sn, int64_t sk, float* dst_dev,
+                           cudaStream_t st, TcWeight* out);
+
 struct GemmArgs {
     const float* A; const float* W; float* C;
     int M, N, K;
@@ -40,6 +45,7 @@ struct GemmArgs {
     const float* R = nullptr;       // [M, N] residual added after the activation
     int act = ACT_NONE;
     int ldc = 0;                    // row stride of C / R (0 -> N)
+    int lda = 0;                    // row stride of A (0 -> K); a multiple of 4 floats
     const TcWeight* tw = nullptr;   // packed copy of W for the tensor-core path (nullptr -> SIMT kernel)
 };
 

@@ -519,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // ------------------------------------------------------------------------------------ weight packing
 // One thread per packed float4: [n_tile][k_chunk][hi|lo][row BN][16-byte chunk 8 (swizzled)].
 __global__ void tc_pack_kernel(const float* __restrict__ W, const float* __restrict__ scale, float* __restrict__ dst,
-                               int N, int K, int BN, int n_tiles, int k_chunks) {
+                               int N, int K, int BN, int n_tiles, int k_chunks, int64_t sn, int64_t sk) {
     const int64_t total = (int64_t)n_tiles * k_chunks * 2 * BN * 8;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -535,7 +535,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ W, const float* __restr
     if (n < N) {
         const float sc = scale != nullptr ? scale[n] : 1.0f;
         for (int e = 0; e < 4; ++e)
-            if (k + e < K) v[e] = W[(size_t)n * K + k + e] * sc;
+            if (k + e < K) v[e] = W[(size_t)n * sn + (size_t)(k + e) * sk] * sc;
     }
     float o[4];
     for (int e = 0; e < 4; ++e) {
@@ -582,12 +582,17 @@ size_t tc_packed_floats(int N, int K) {
 
 int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, float* dst_dev, cudaStream_t st,
                    TcWeight* out) {
+    return tc_pack_weight_strided(W_dev, scale_dev, N, K, K, 1, dst_dev, st, out);
+}
+
+int tc_pack_weight_strided(const float* W_dev, const float* scale_dev, int N, int K, int64_t sn, int64_t sk, float* dst_dev,
+                           cudaStream_t st, TcWeight* out) {
     AC_REQUIRE(W_dev && dst_dev && out && N > 0 && K > 0, "tc_pack_weight: bad argument");
     AC_REQUIRE(((uintptr_t)dst_dev & 127) == 0, "tc_pack_weight: destination must be 128-byte aligned");
     int BN, n_tiles, k_chunks;
     tc_tiling(N, K, BN, n_tiles, k_chunks);
     const int64_t total = (int64_t)n_tiles * k_chunks * 2 * BN * 8;
-    tc_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W_dev, scale_dev, dst_dev, N, K, BN, n_tiles, k_chunks);
+    tc_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W_dev, scale_dev, dst_dev, N, K, BN, n_tiles, k_chunks, sn, sk);
     AC_LAUNCHED("tc_pack_kernel");
     out->packed = dst_dev; out->scale = scale_dev; out->N = N; out->K = K; out->BN = BN; out->n_tiles = n_tiles; out->k_chunks = k_chunks;
     return AC_OK;
@@ -637,7 +642,9 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
                    g.C, g.M, g.N, ldc);
     }
     const cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.M};
-    const cuuint64_t strides[1] = {(cuuint64_t)g.K * sizeof(float)};
+    const int lda = g.lda ? g.lda : g.K;
+    AC_REQUIRE(lda % 4 == 0 && lda >= g.K, "gemm_tc: lda (%d) must be a multiple of 4 and >= K (%d)", lda, g.K);
+    const cuuint64_t strides[1] = {(cuuint64_t)lda * sizeof(float)};
     const cuuint32_t box[2] = {TC_BK, TC_BM};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.A), dims, strides, box, estr,

@@ -372,7 +372,7 @@ greedy_kernel(DecodeArgs a) {
     int word[G]; bool finished[G]; bool valid[G];
 #pragma unroll
     for (int r = 0; r < G; ++r) { word[r] = a.start_idx; valid[r] = clip0 + r < a.n_clips; finished[r] = !valid[r]; }
-    __syncthreads();
+    cluster.sync();   // every CTA of the cluster is resident before the first GEMV writes into its peers' shared memory
     // The reference keeps running finished rows (input forced to <end>) until EVERY row of the batch
     // has finished and records their logits/embeds; when those outputs are requested we do the same
     // for all max_len steps (a superset: past the reference's break its buffers are uninitialised).
@@ -454,7 +454,7 @@ beam_kernel(DecodeArgs a) {
     if (tid < R) { s_words[tid] = a.start_idx; s_score[tid] = 0.f; s_logits[tid] = lp + (size_t)tid * V; }
     if (tid == 0) { s_ndone = 0; s_stop = 0; s_best_len = 0; s_best_score = -INFINITY; }
     for (int i = tid; i < R * kMaxLen; i += kThreads) { s_anc[0][i / kMaxLen][i % kMaxLen] = i / kMaxLen; }
-    __syncthreads();
+    cluster.sync();   // peers resident before the first distributed-shared-memory write (decode_common.cuh matvec_t)
     int cur = 0;
     for (int t = 0; t < a.max_len; ++t) {
         if (tid < R) s_pad[t][tid] = (s_words[tid] == a.pad_idx);

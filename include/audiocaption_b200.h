@@ -40,6 +40,8 @@ typedef struct ac_cnn14 ac_cnn14_t;
 typedef struct ac_bigru ac_bigru_t;
 typedef struct ac_bah ac_bah_t;
 typedef struct ac_sed ac_sed_t;
+typedef struct ac_trm_train ac_trm_train_t;
+typedef struct ac_bigru_train ac_bigru_train_t;
 
 int ac_version(void);
 const char* ac_last_error(void);
@@ -255,6 +257,80 @@ int ac_bah_greedy(const ac_bah_t* dec, const float* fc_emb_dev, const float* att
 int ac_bah_beam(const ac_bah_t* dec, const float* fc_emb_dev, const float* attn_emb_dev, const int64_t* lens_dev,
                 const int64_t* tags_dev, int batch, int T, int max_len, int beam, float temp, int start_idx,
                 int end_idx, int64_t* seq_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ================================================================== training step
+ * The training entry points read LIVE parameter storage (the module's own tensors) and write gradients into caller-owned
+ * buffers; nothing is copied at create time.  Call *_refresh once after every optimizer step (it re-packs the weights for
+ * the tensor-core GEMMs), then forward, then backward.  Activations needed by the backward pass live in the caller's
+ * workspace between the two calls.  Dropout masks are functions of (seed, site, element index): pass the same p_drop /
+ * seed to the forward and backward calls of one step; p_drop = 0 gives the deterministic (eval-mode) arithmetic. */
+
+/* ------------------------------------------------------------------ bi-GRU encoder, training
+ * Replaces captioning/models/rnn_encoder.py:34-49 `RnnEncoder.forward` in train mode (nn.GRU inter-layer dropout) and its
+ * autograd backward.  params_dev / grads_dev: nn.GRU order as for ac_bigru_create (a NULL grads entry = frozen). */
+int ac_bigru_train_create(const float* const* params_dev, float* const* grads_dev, const int64_t* numels, int n_tensors,
+                          int input_dim, int hidden, int num_layers, void* stream, ac_bigru_train_t** out);
+void ac_bigru_train_destroy(ac_bigru_train_t* net);
+size_t ac_bigru_train_workspace_bytes(const ac_bigru_train_t* net, int batch, int T);
+int ac_bigru_train_refresh(ac_bigru_train_t* net, void* stream);
+/* x_dev [batch, T, input_dim], lens_dev [batch] int64 (1..T) -> out_dev [batch, T, 512] (zero past each length). */
+int ac_bigru_train_fwd(ac_bigru_train_t* net, const float* x_dev, const int64_t* lens_dev, int batch, int T, float p_drop,
+                       uint64_t seed, float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* dout_dev [batch, T, 512] -> every non-NULL grads_dev tensor is overwritten; dx_dev (nullable) [batch, T, input_dim]. */
+int ac_bigru_train_bwd(ac_bigru_train_t* net, const float* x_dev, const int64_t* lens_dev, const float* dout_dev, int batch,
+                       int T, float p_drop, uint64_t seed, float* dx_dev, void* workspace_dev, size_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------ Transformer decoder, dense full-prefix forward + backward
+ * Replaces captioning/models/transformer_decoder.py:80-103 `TransformerDecoder.forward` as the training loop calls it
+ * (captioning/models/transformer_model.py:20-57 under captioning/models/base.py:131-170) and its autograd backward.
+ * With p_drop = 0 it is also the eval-mode `forward(input_dict)` on a full prefix.
+ * params_dev / grads_dev: the tensor order of ac_trm_create.  Token rows: word_dev [n_seq_max, L] int64 and key_pad_dev
+ * [n_seq_max, L] uint8 (`cap_padding_mask`); row s attends to the memory of clip s % B (scheduled sampling runs the
+ * ground-truth captions as rows [0, B) and the model's own samples as rows [B, 2B)).  n_seq_max, L, B, T fix the workspace
+ * layout and must be the same in every call of one step. */
+int ac_trm_train_num_tensors(int nlayers);
+int ac_trm_train_create(const float* const* params_dev, float* const* grads_dev, const int64_t* numels, int n_tensors,
+                        int d_model, int nhead, int nlayers, int dim_ff, int vocab, int attn_emb_dim, int pe_len, void* stream,
+                        ac_trm_train_t** out);
+void ac_trm_train_destroy(ac_trm_train_t* dec);
+size_t ac_trm_train_workspace_bytes(const ac_trm_train_t* dec, int n_seq_max, int L, int B, int T);
+int ac_trm_train_vocab_padded(const ac_trm_train_t* dec);      /* row stride of the logits: vocab rounded up to 8 */
+int ac_trm_train_refresh(ac_trm_train_t* dec, void* stream);
+/* attn_emb_dev [B, T, attn_emb_dim] -> projected memory + per-layer cross-attention keys / values (in the workspace) */
+int ac_trm_train_memory_fwd(ac_trm_train_t* dec, const float* attn_emb_dev, int B, int T, int n_seq_max, int L, float p_drop,
+                            uint64_t seed, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* token rows [seq0, seq0 + n_seq) through the decoder layers; attn_len_dev [B] int64 = valid memory frames */
+int ac_trm_train_seq_fwd(ac_trm_train_t* dec, const int64_t* word_dev, const unsigned char* key_pad_dev, int seq0, int n_seq,
+                         int n_seq_max, int L, const int64_t* attn_len_dev, int B, int T, float p_drop, uint64_t seed,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
+/* logits_dev [n_rows, vocab_padded] = classifier(hidden[rows_dev[i]]) (rows_dev int32, NULL = identity); embed_dev (nullable)
+ * [n_rows, d_model]; keep != 0 records the selection for ac_trm_train_bwd. */
+int ac_trm_train_logits(ac_trm_train_t* dec, const int* rows_dev, int n_rows, int n_seq_max, int L, int B, int T,
+                        float* logits_dev, float* embed_dev, int keep, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* dlogits_dev [n_rows, vocab_padded] -> all parameter gradients (overwritten) and dattn_emb_dev (nullable) [B, T, attn_emb_dim] */
+int ac_trm_train_bwd(ac_trm_train_t* dec, const float* dlogits_dev, const int* rows_dev, int n_rows, const int64_t* word_dev,
+                     const unsigned char* key_pad_dev, int n_seq, int n_seq_max, int L, const float* attn_emb_dev,
+                     const int64_t* attn_len_dev, int B, int T, float p_drop, uint64_t seed, float* dattn_emb_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ loss and optimizer
+ * captioning/losses/loss.py:51-74 `LabelSmoothingLoss.forward` (reduction "mean") fused with its gradient:
+ * logit_dev [B, L, ld_logit >= V], tgt_dev [B, *] int64 with row stride ld_tgt (tgt = cap[:, 1:] is a strided view),
+ * tgt_len_dev [B] int64 -> loss_dev[0]; dlogit_dev (nullable, same layout as logit) = grad_scale * dloss/dlogit
+ * (columns V..ld_logit-1 are zeroed).  workspace: B * L floats. */
+int ac_ls_ce_fwd_bwd(const float* logit_dev, int ld_logit, const int64_t* tgt_dev, int ld_tgt, const int64_t* tgt_len_dev, int B,
+                     int L, int V, float smoothing, float grad_scale, float* loss_dev, float* dlogit_dev, void* workspace_dev,
+                     size_t workspace_bytes, void* stream);
+/* python_scripts/train_eval/run.py:123-127: skip when the loss is NaN, else clip_grad_norm_(max_norm) over the flat
+ * gradient, then torch.optim.Adam.step (L2 weight decay, bias correction from the device-side step counter).
+ * grad_scale multiplies the gradient first (1 / world_size after a sum all-reduce).  norm_out_dev (nullable) receives the
+ * total gradient norm before clipping. */
+size_t ac_clip_adam_workspace_bytes(void);
+int ac_clip_adam(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                 const float* loss_dev, int* step_dev, float* norm_out_dev, void* workspace_dev, size_t workspace_bytes,
+                 void* stream);
 
 #ifdef __cplusplus
 }

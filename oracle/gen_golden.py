@@ -189,10 +189,25 @@ def sed(seed=12, batch=8, n=96000):
                         seg=seg[:, ::3, ::7].numpy(), stable=stable.numpy())
 
 
+def eg_configs():
+    """The `model:` sections of the two Cnn14Rnn-Transformer training YAMLs (eg_configs/{audiocaps,clotho_v2}/waveform/
+    cnn14rnn_trm.yaml:7-38) as fixtures for the factory tests (tests/test_boundary_cpu.py)."""
+    import yaml
+    os.makedirs(os.path.join(OUT, "eg_configs"), exist_ok=True)
+    for ds in ("audiocaps", "clotho_v2"):
+        with open(os.path.join(ref_import.REF_ROOT, "eg_configs", ds, "waveform", "cnn14rnn_trm.yaml")) as f:
+            cfg = yaml.load(f, Loader=yaml.FullLoader)
+        with open(os.path.join(OUT, "eg_configs", f"{ds}_cnn14rnn_trm.yaml"), "w") as f:
+            f.write(f"# model section of the reference's eg_configs/{ds}/waveform/cnn14rnn_trm.yaml (oracle/gen_golden.py eg_configs)\n")
+            yaml.safe_dump({"model": cfg["model"]}, f, default_flow_style=False)
+
+
 if __name__ == "__main__":
     import sys
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm", "temp_gru", "sed"]
+    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm", "temp_gru", "sed", "eg_configs"]
+    if "eg_configs" in which:
+        eg_configs()
     if "effb2_trm" in which:
         effb2_trm()
     if "cnn14" in which:
