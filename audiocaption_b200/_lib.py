@@ -80,6 +80,43 @@ _SIGS = {
     "ac_trm_trace": (C.c_int, [C.c_int, C.c_void_p]),
     "ac_trm_beam": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_int, C.c_int, C.c_int, c_i64p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    # ---- training step
+    "ac_cnn14_fwd_train": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint64,
+                                     c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_trm_update": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    "ac_trm_sample_forced": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       c_i64p, c_i64p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_bigru_train_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ac_bigru_train_destroy": (None, [C.c_void_p]),
+    "ac_bigru_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "ac_bigru_train_refresh": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ac_bigru_train_fwd": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_float, C.c_uint64, c_f32p, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
+    "ac_bigru_train_bwd": (C.c_int, [C.c_void_p, c_f32p, c_i64p, c_f32p, C.c_int, C.c_int, C.c_float, C.c_uint64, c_f32p,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_trm_train_num_tensors": (C.c_int, [C.c_int]),
+    "ac_trm_train_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ac_trm_train_destroy": (None, [C.c_void_p]),
+    "ac_trm_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ac_trm_train_vocab_padded": (C.c_int, [C.c_void_p]),
+    "ac_trm_train_refresh": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ac_trm_train_memory_fwd": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint64,
+                                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_trm_train_seq_fwd": (C.c_int, [C.c_void_p, c_i64p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_i64p, C.c_int,
+                                       C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_trm_train_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p,
+                                      C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_trm_train_bwd": (C.c_int, [C.c_void_p, c_f32p, C.c_void_p, C.c_int, c_i64p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   c_f32p, c_i64p, C.c_int, C.c_int, C.c_float, C.c_uint64, c_f32p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p]),
+    "ac_ls_ce_fwd_bwd": (C.c_int, [c_f32p, C.c_int, c_i64p, C.c_int, c_i64p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                   c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_argmax_rows": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_i64p, c_f32p, C.c_void_p]),
+    "ac_clip_adam_workspace_bytes": (C.c_size_t, []),
+    "ac_clip_adam": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                               C.c_float, C.c_float, c_f32p, C.c_void_p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -113,6 +150,14 @@ def check(rc: int, what: str = ""):
 def ptr(t):
     """device/host pointer of a torch tensor (None -> NULL)"""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def pointer_table(tensors):
+    """(void* array, int64 numel array, n) where a None entry becomes a NULL pointer (a frozen parameter's gradient)."""
+    n = len(tensors)
+    ptrs = (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in tensors])
+    numels = (C.c_int64 * n)(*[0 if t is None else t.numel() for t in tensors])
+    return ptrs, numels, n
 
 
 def tensor_table(tensors):

@@ -1,6 +1,7 @@
-"""Mirror of captioning/models/base.py: CaptionMetaMixin (:11-21) and the inference side of
-CaptionModel (:24-361).  The python per-token loops of the reference are replaced by single
-launches of the decode kernels; the dict-in / dict-out contract is unchanged."""
+"""Mirror of captioning/models/base.py: CaptionMetaMixin (:11-21) and CaptionModel (:24-361): the train-mode forward
+(teacher forcing / scheduled sampling, :131-170) and the inference modes greedy and beam.  The python per-token loops of
+the reference are replaced by single launches of the decode kernels (inference) and by dense full-prefix passes
+(training); the dict-in / dict-out contract is unchanged."""
 from typing import Dict
 
 import torch
@@ -47,7 +48,11 @@ class CaptionModel(nn.Module, CaptionMetaMixin):
 
     def forward_decoder(self, input_dict: Dict, encoder_output_dict: Dict):
         if input_dict["mode"] == "train":
-            raise NotImplementedError("training forward is not built on the B200 path yet")
+            forward_dict = {"mode": "train", "sample_method": "greedy", "temp": 1.0}
+            for key in self.train_forward_keys:
+                forward_dict[key] = input_dict[key]
+            forward_dict.update(encoder_output_dict)
+            output = self.train_forward(forward_dict)
         elif input_dict["mode"] == "inference":
             forward_dict = {"mode": "inference"}
             default_args = {"sample_method": "greedy", "max_length": self.max_length, "temp": 1.0}
@@ -66,6 +71,22 @@ class CaptionModel(nn.Module, CaptionMetaMixin):
             raise Exception("mode should be either 'train' or 'inference'")
         output.update(encoder_output_dict)
         return output
+
+    def train_forward(self, input_dict):
+        """base.py:131-137: scheduled sampling whenever ss_ratio != 1 (always, from the first iteration on:
+        run.py:55-65 lowers it before the forward), plain teacher forcing otherwise."""
+        if input_dict["ss_ratio"] != 1:
+            input_dict["mode"] = "train"
+            return self.stepwise_forward(input_dict)
+        output = self.seq_forward(input_dict)
+        self.train_process(output, input_dict)
+        return output
+
+    def seq_forward(self, input_dict):
+        raise NotImplementedError
+
+    def train_process(self, output, input_dict):
+        pass
 
     def inference_forward(self, input_dict):
         method = input_dict["sample_method"]

@@ -199,6 +199,7 @@ class EfficientNetB2(nn.Module):
         self.backbone = _EffiNet()
         self.fc_emb_size = self.backbone.eff_net._conv_head.out_channels
         self.downsample_ratio = 32
+        self.db_max_reduce = None       # optional callable(gmax [1] device tensor) -> tensor, see forward()
         self._ws = Workspace()
         self._handle = None
         self._sig = None
@@ -251,6 +252,10 @@ class EfficientNetB2(nn.Module):
         l = _lib.lib()
         with torch.cuda.device(wav.device):
             lms, gmax = self.melspec_extractor(wav, want_max=True)   # clamp is fused into the stem conv
+            if self.db_max_reduce is not None:
+                # a batch split across ranks: one scalar all-reduce(max) (audiocaption_b200.sharding.global_db_max) restores
+                # the batch-global top_db reference of hf_wrapper.py:292-293; runs between the two kernels, on the stream
+                gmax = self.db_max_reduce(gmax)
             B, F, T = lms.shape
             Tp = l.ac_effb2_out_frames(T)
             attn_emb = torch.empty(B, Tp, self.fc_emb_size, device=wav.device, dtype=torch.float32)
@@ -285,7 +290,12 @@ class _ConvBlock(nn.Module):
 
 class Cnn14Encoder(nn.Module):
     """Drop-in for captioning.models.cnn_encoder.Cnn14Encoder (cnn_encoder.py:326-464; HF copy
-    hf_wrapper.py:1185-1304).  Inference only (eval-mode BatchNorm, no dropout, no SpecAugment)."""
+    hf_wrapper.py:1185-1304).  Forward only: BatchNorm always uses its running statistics (the training configs freeze
+    the CNN and its BatchNorm, eg_configs/*/waveform/cnn14rnn_trm.yaml:11-12); in train mode the functional dropouts of
+    cnn_encoder.py:432-456 are applied (p = 0.2 after every ConvBlock, 0.5 around fc1).  No SpecAugment."""
+
+    conv_dropout = 0.2
+    fc_dropout = 0.5
 
     def __init__(self, sample_rate: int = 32000, freeze: bool = False):
         super().__init__()
@@ -312,8 +322,29 @@ class Cnn14Encoder(nn.Module):
                 p.requires_grad = False
 
     def load_pretrained(self, pretrained, output_fn=print):
-        raise NotImplementedError("PANNs / COLA / BLAT checkpoint conversion (cnn_encoder.py:368-412) is out of scope; "
-                                  "load a state_dict with the reference's key names instead")
+        """cnn_encoder.py:376-412: accepts the three checkpoint layouts the reference knows -- PANNs ({"model": state_dict
+        with this module's key names plus spectrogram / logmel extractor and fc_audioset entries that do not match and
+        are skipped}), COLA ({"model": {"backbone.<key>": ...}}) and BLAT ({"state_dict": {"...audio_encoder.<key>": ...}})
+        -- and merge-loads the entries whose key and shape match.  With `freeze`, exactly the loaded parameters are
+        frozen.  `pretrained` may also be an already-loaded checkpoint dict."""
+        from ..utils.train_util import merge_load_state_dict
+        checkpoint = pretrained if isinstance(pretrained, dict) else torch.load(pretrained, map_location="cpu")
+        if "model" in checkpoint:
+            model_sd = checkpoint["model"]
+            if any(key.startswith("backbone.") for key in model_sd):          # COLA
+                state_dict = {key.replace("backbone.", ""): value for key, value in model_sd.items()
+                              if key.startswith("backbone.")}
+            else:                                                              # PANNs
+                state_dict = model_sd
+        elif "state_dict" in checkpoint:                                       # BLAT
+            state_dict = {key.replace("audio_encoder.", ""): value for key, value in checkpoint["state_dict"].items()
+                          if "audio_encoder" in key}
+        else:
+            raise Exception("Unkown checkpoint format")
+        loaded_keys = merge_load_state_dict(state_dict, self, output_fn)
+        if self.freeze:
+            for name, param in self.named_parameters():
+                param.requires_grad = name not in loaded_keys
 
     def _body_tensors(self):
         ts = [self.bn0.weight, self.bn0.bias, self.bn0.running_mean, self.bn0.running_var]
@@ -374,6 +405,17 @@ class Cnn14Encoder(nn.Module):
             fc_emb = torch.empty(B, self.fc_emb_size, device=wav.device, dtype=torch.float32)
             nbytes = l.ac_cnn14_workspace_bytes(B, F, T)
             ws = self._ws.get(nbytes, wav.device)
-            _lib.check(l.ac_cnn14_fwd(self._net(), _lib.ptr(lms), B, F, T, _lib.ptr(len_dev), _lib.ptr(attn_emb),
-                                      _lib.ptr(fc_emb), _lib.ptr(ws), nbytes, _lib.current_stream()), "ac_cnn14_fwd")
+            if self.training:
+                if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                    raise _lib.AudioCaptionB200Error(
+                        "Cnn14Encoder has no backward pass on the B200 path: freeze it (freeze_cnn: True, as in "
+                        "eg_configs/*/waveform/cnn14rnn_trm.yaml) or call .eval()")
+                seed = input_dict.get("_dropout_seed")
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else seed
+                _lib.check(l.ac_cnn14_fwd_train(self._net(), _lib.ptr(lms), B, F, T, _lib.ptr(len_dev), float(self.conv_dropout),
+                                                float(self.fc_dropout), seed, _lib.ptr(attn_emb), _lib.ptr(fc_emb), _lib.ptr(ws),
+                                                nbytes, _lib.current_stream()), "ac_cnn14_fwd_train")
+            else:
+                _lib.check(l.ac_cnn14_fwd(self._net(), _lib.ptr(lms), B, F, T, _lib.ptr(len_dev), _lib.ptr(attn_emb),
+                                          _lib.ptr(fc_emb), _lib.ptr(ws), nbytes, _lib.current_stream()), "ac_cnn14_fwd")
         return {"fc_emb": fc_emb, "attn_emb": attn_emb, "attn_emb_len": feat_length.cpu()}

@@ -2,7 +2,10 @@
 
 ``self.network`` is a torch ``nn.GRU`` used purely as the parameter container (state_dict keys
 ``network.weight_ih_l0`` ... ``network.bias_hh_l2_reverse`` as in the reference); the arithmetic runs in
-csrc/bigru.cu through the C ABI (tensor-core input projections + cluster-resident recurrence).  Eval mode only."""
+csrc/bigru.cu through the C ABI (tensor-core input projections + cluster-resident recurrence).  In train mode the forward
+saves its gates and the backward runs csrc/bigru_train.cu (back-propagation through time on the same cluster layout),
+wrapped in a ``torch.autograd.Function``; ``train_engine`` exposes the same kernels without autograd for the fused train
+step (audiocaption_b200/train_step.py)."""
 import ctypes
 
 import torch
@@ -35,6 +38,13 @@ class RnnEncoder(BaseEncoder):
         self._ws = Workspace()
         self._handle = None
         self._sig = None
+        self._engine = None
+
+    @property
+    def train_engine(self):
+        if self._engine is None:
+            self._engine = GruTrainEngine(self)
+        return self._engine
 
     def _tensors(self):
         ts = []
@@ -62,6 +72,9 @@ class RnnEncoder(BaseEncoder):
         if self._handle is not None:
             _lib.lib().ac_bigru_destroy(self._handle)
             self._handle = None
+        if self._engine is not None:
+            self._engine.release()
+            self._engine = None
 
     def __del__(self):
         try:
@@ -73,13 +86,22 @@ class RnnEncoder(BaseEncoder):
         x = input_dict["attn"]
         lens = torch.as_tensor(input_dict["attn_len"])
         require_cuda(x, "RnnEncoder.forward")
-        if self.training:
-            raise NotImplementedError("the B200 GRU encoder implements the eval-mode (inference) path")
         x = x.float().contiguous()
         B, T, D = x.shape
         t_out = int(lens.max()) if B > 0 else 0       # pad_packed_sequence: max(lens) frames (lens lives on the host)
         if t_out > T or (B > 0 and int(lens.min()) < 1):
             raise _lib.AudioCaptionB200Error(f"RnnEncoder: lengths must be in 1..{T}, got {lens.tolist()}")
+        params = self._tensors()
+        if self.training and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+            with torch.cuda.device(x.device):
+                len_dev = to_device_async(lens, x.device, torch.int64)
+                p_drop = float(self.dropout) if self.num_layers > 1 else 0.0
+                out = _GruForwardFn.apply(x[:, :t_out].contiguous(), self, len_dev, p_drop, *params)
+                fc_emb = (out.sum(1) / len_dev.unsqueeze(1).to(out.dtype))      # mean_with_lens: padded frames are zero
+            return {"attn_emb": out, "fc_emb": fc_emb, "attn_emb_len": lens}
+        if self.training and self.num_layers > 1 and self.dropout > 0:
+            raise _lib.AudioCaptionB200Error("RnnEncoder in train mode without gradients: call .eval() for inference "
+                                             "(the inter-layer dropout only exists on the training path)")
         l = _lib.lib()
         dev = x.device
         with torch.cuda.device(dev):
@@ -94,3 +116,105 @@ class RnnEncoder(BaseEncoder):
             _lib.check(l.ac_masked_mean(_lib.ptr(out), _lib.ptr(len_dev), B, t_out, self.embed_dim, _lib.ptr(fc_emb),
                                         _lib.current_stream()), "ac_masked_mean")
         return {"attn_emb": out, "fc_emb": fc_emb, "attn_emb_len": lens}
+
+
+class GruTrainEngine:
+    """bi-GRU training forward / backward on csrc/bigru_train.cu without autograd (see DecoderTrainEngine)."""
+
+    def __init__(self, enc: "RnnEncoder"):
+        self.enc = enc
+        self._handle = None
+        self._key = None
+        self._ws = Workspace()
+        self._scratch = None
+        self._grads = None
+        self._ctx = None
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib().ac_bigru_train_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def handle(self, grads="param"):
+        enc = self.enc
+        params = enc._tensors()
+        for p in params:
+            require_cuda(p, "RnnEncoder parameters")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.AudioCaptionB200Error("RnnEncoder training needs contiguous fp32 parameters")
+        if grads == "param":
+            gts = []
+            for p in params:
+                if p.requires_grad and p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                gts.append(p.grad if p.requires_grad else None)
+        else:
+            if self._scratch is None or self._scratch[0].device != params[0].device:
+                self._scratch = [torch.zeros_like(p) for p in params]
+            gts = [g if p.requires_grad else None for p, g in zip(params, self._scratch)]
+        key = (tuple(p.data_ptr() for p in params), tuple(0 if g is None else g.data_ptr() for g in gts))
+        if self._handle is None or key != self._key:
+            self.release()
+            pp, numels, n = _lib.tensor_table([p.detach() for p in params])
+            gp, _, _ = _lib.pointer_table(gts)
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().ac_bigru_train_create(pp, gp, numels, n, enc.attn_feat_dim, enc.hidden_size, enc.num_layers,
+                                                        _lib.current_stream(), ctypes.byref(h)), "ac_bigru_train_create")
+            self._handle, self._key, self._grads = h, key, gts
+        return self._handle
+
+    def forward(self, x, len_dev, p_drop=0.0, seed=None, grads="param"):
+        """x [B, T, D] fp32 cuda (T = max length), len_dev [B] int64 cuda -> out [B, T, 512]"""
+        l = _lib.lib()
+        dev = x.device
+        B, T, _ = x.shape
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else seed
+        with torch.cuda.device(dev):
+            h = self.handle(grads)
+            st = _lib.current_stream()
+            nbytes = l.ac_bigru_train_workspace_bytes(h, B, T)
+            ws = self._ws.get(nbytes, dev)
+            out = torch.empty(B, T, self.enc.embed_dim, dtype=torch.float32, device=dev)
+            _lib.check(l.ac_bigru_train_refresh(h, st), "ac_bigru_train_refresh")
+            _lib.check(l.ac_bigru_train_fwd(h, _lib.ptr(x), _lib.ptr(len_dev), B, T, p_drop, seed, _lib.ptr(out), _lib.ptr(ws),
+                                            nbytes, st), "ac_bigru_train_fwd")
+        self._ctx = dict(x=x, lens=len_dev, B=B, T=T, p_drop=p_drop, seed=seed, nbytes=nbytes)
+        return out
+
+    def backward(self, dout, need_dx=False):
+        c = self._ctx
+        if c is None:
+            raise _lib.AudioCaptionB200Error("GruTrainEngine.backward without a forward")
+        l = _lib.lib()
+        dev = dout.device
+        with torch.cuda.device(dev):
+            ws = self._ws.get(c["nbytes"], dev)
+            dx = torch.empty_like(c["x"]) if need_dx else None
+            dout = dout.float().contiguous()
+            _lib.check(l.ac_bigru_train_bwd(self._handle, _lib.ptr(c["x"]), _lib.ptr(c["lens"]), _lib.ptr(dout), c["B"], c["T"],
+                                            c["p_drop"], c["seed"], _lib.ptr(dx), _lib.ptr(ws), c["nbytes"],
+                                            _lib.current_stream()), "ac_bigru_train_bwd")
+        return dx
+
+
+class _GruForwardFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, enc, len_dev, p_drop, *params):
+        eng = enc.train_engine
+        out = eng.forward(x.detach(), len_dev, p_drop=p_drop, grads="scratch")
+        ctx.enc, ctx.need_dx = enc, x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng = ctx.enc.train_engine
+        dx = eng.backward(dout, ctx.need_dx)
+        grads = [None if g is None else g.clone() for g in eng._grads]
+        return (dx, None, None, None, *grads)

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "train_ops.cuh"
 
 namespace ac {
 
@@ -95,7 +96,7 @@ cnn14_conv1_kernel(const float* __restrict__ lms, const float* __restrict__ s0, 
 // avg_pool2d(kernel 2x2, stride 2, floor): in [B, H, W, C] -> out [B, H/2, W/2, C]; one float4 per thread.
 __global__ void __launch_bounds__(256)
 cnn14_avgpool_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int C4, int Ho, int Wo,
-                     int64_t total) {
+                     int64_t total, Dropout dp, uint32_t site) {
     pdl_trigger();
     pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,8 +108,13 @@ cnn14_avgpool_kernel(const float4* __restrict__ in, float4* __restrict__ out, in
     const int64_t b = r / Ho;
     const float4* p = in + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
     const float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)W * C4), d = __ldg(p + (size_t)W * C4 + C4);
-    out[i] = make_float4(0.25f * (a.x + bb.x + cc.x + d.x), 0.25f * (a.y + bb.y + cc.y + d.y),
-                         0.25f * (a.z + bb.z + cc.z + d.z), 0.25f * (a.w + bb.w + cc.w + d.w));
+    float4 o = make_float4(0.25f * (a.x + bb.x + cc.x + d.x), 0.25f * (a.y + bb.y + cc.y + d.y),
+                           0.25f * (a.z + bb.z + cc.z + d.z), 0.25f * (a.w + bb.w + cc.w + d.w));
+    if (dp.p > 0.0f) {     // F.dropout(x, p=0.2, training=self.training) after the block (cnn_encoder.py:432-456)
+        o.x *= drop_scale(dp.seed, site, (uint64_t)i * 4, dp.p); o.y *= drop_scale(dp.seed, site, (uint64_t)i * 4 + 1, dp.p);
+        o.z *= drop_scale(dp.seed, site, (uint64_t)i * 4 + 2, dp.p); o.w *= drop_scale(dp.seed, site, (uint64_t)i * 4 + 3, dp.p);
+    }
+    out[i] = o;
 }
 
 // ConvBlock pooling of the SED tagger (hf_wrapper.py:1204-1212, pool_type 'avg+max'): avg_pool2d + max_pool2d over
@@ -363,7 +369,18 @@ void ac_cnn14_destroy(ac_cnn14_t* net) {
 
 int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int n_frames, const int64_t* lens,
                  float* attn_emb, float* fc_emb, void* workspace, size_t ws_bytes, void* stream) {
+    return ac_cnn14_fwd_train(net, lms, B, n_mels, n_frames, lens, 0.0f, 0.0f, 0, attn_emb, fc_emb, workspace, ws_bytes, stream);
+}
+
+// Train-mode forward of the FROZEN encoder (eg_configs/*/waveform/cnn14rnn_trm.yaml: freeze_cnn + freeze_cnn_bn): BatchNorm
+// stays in eval mode (folded), but the functional dropouts of cnn_encoder.py:432-456 are active -- p_conv after every
+// ConvBlock (0.2 in the reference), p_fc around fc1 (0.5).  Masks come from the counter RNG (seed); p = 0 is ac_cnn14_fwd.
+int ac_cnn14_fwd_train(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int n_frames, const int64_t* lens,
+                       float p_conv, float p_fc, uint64_t seed, float* attn_emb, float* fc_emb, void* workspace,
+                       size_t ws_bytes, void* stream) {
     using namespace ac;
+    const Dropout dpc{p_conv, seed}, dpf{p_fc, seed};
+    constexpr uint32_t kSiteCnn = 96;      // dropout streams 96..101: after block 1..6; 102, 103: around fc1
     AC_REQUIRE(B >= 0 && B <= 65535, "ac_cnn14_fwd: batch %d out of range", B);
     AC_REQUIRE(n_mels == 64, "ac_cnn14_fwd: bn0 is defined over 64 mel bins, got %d", n_mels);
     AC_REQUIRE(n_frames >= 32, "ac_cnn14_fwd: %d frames is fewer than the down-sampling ratio 32", n_frames);
@@ -404,7 +421,7 @@ int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int
             const int64_t total = (int64_t)B * Ho * Wo * C4;
             AC_TIMED("cnn14_avgpool", st);
             rc = launch_pdl(cnn14_avgpool_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st,
-                            (const float4*)cur, (float4*)nxt, d[i].H, d[i].W, C4, Ho, Wo, total);
+                            (const float4*)cur, (float4*)nxt, d[i].H, d[i].W, C4, Ho, Wo, total, dpc, kSiteCnn + (uint32_t)i);
             if (rc) return rc;
             AC_LAUNCHED("cnn14_avgpool_kernel");
             std::swap(cur, nxt);
@@ -412,6 +429,7 @@ int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int
     }
     const Cnn14Dims last = d[kCnn14Blocks - 1];
     const int D = ac_cnn14_out_dim();
+    rc = dropout_apply(cur, 0, (int64_t)B * last.H * last.W * D, dpc, kSiteCnn + kCnn14Blocks - 1, st); if (rc) return rc;
     {
         AC_TIMED("cnn14_tail", st);
         rc = launch_pdl(cnn14_tail_kernel, dim3(cdiv(D, 128), B), dim3(128), 0, st, (const float*)cur, lens, attn_emb, pooled,
@@ -419,9 +437,11 @@ int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int
         if (rc) return rc;
         AC_LAUNCHED("cnn14_tail_kernel");
     }
+    rc = dropout_apply(pooled, 0, (int64_t)B * D, dpf, kSiteCnn + kCnn14Blocks, st); if (rc) return rc;
     GemmArgs g; g.A = pooled; g.W = net->fc_w; g.C = fc_emb; g.M = B; g.N = D; g.K = D; g.cbias = net->fc_b; g.act = ACT_RELU;
     g.tw = &net->fc_tw;
-    return gemm_tn(g, st);
+    rc = gemm_tn(g, st); if (rc) return rc;
+    return dropout_apply(fc_emb, 0, (int64_t)B * D, dpf, kSiteCnn + kCnn14Blocks + 1, st);
 }
 
 }  // extern "C"

@@ -328,11 +328,11 @@ __device__ __forceinline__ float block_max256(float v, float* s) {
     return t;
 }
 
-__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ X, int V, int64_t* __restrict__ idx,
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ X, int ld, int V, int64_t* __restrict__ idx,
                                                           float* __restrict__ logprob) {
     __shared__ float s_f[8];
     __shared__ int s_i[8];
-    const float* row = X + (size_t)blockIdx.x * V;
+    const float* row = X + (size_t)blockIdx.x * ld;
     float best = -INFINITY; int bi = 0x7fffffff;
     for (int v = threadIdx.x; v < V; v += 256) {
         const float x = row[v];
@@ -360,9 +360,9 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
     }
     if (threadIdx.x == 0) idx[blockIdx.x] = bi;
 }
-int argmax_rows(const float* X, int M, int V, int64_t* idx, float* logprob, cudaStream_t st) {
+int argmax_rows(const float* X, int ld, int M, int V, int64_t* idx, float* logprob, cudaStream_t st) {
     if (M <= 0) return AC_OK;
-    argmax_rows_kernel<<<M, 256, 0, st>>>(X, V, idx, logprob);
+    argmax_rows_kernel<<<M, 256, 0, st>>>(X, ld, V, idx, logprob);
     AC_LAUNCHED("argmax_rows_kernel");
     return AC_OK;
 }
@@ -650,6 +650,14 @@ int ac_ls_ce_fwd_bwd(const float* logit_dev, int ld_logit, const int64_t* tgt_de
     ls_ce_reduce_kernel<<<1, 256, 0, st>>>(row_loss, tgt_len_dev, B, L, loss_dev);
     AC_LAUNCHED("ls_ce_reduce_kernel");
     return AC_OK;
+}
+
+// sample_next_word(method="greedy") of captioning/models/base.py:214-218 over a batch of logit rows:
+// idx_dev[m] = first arg-max of logit_dev[m, :V] (row stride ld), logprob_dev[m] (nullable) = its log-softmax value.
+int ac_argmax_rows(const float* logit_dev, int ld, int M, int V, int64_t* idx_dev, float* logprob_dev, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(logit_dev && idx_dev && ld >= V && V >= 1 && M >= 0, "ac_argmax_rows: bad argument");
+    return argmax_rows(logit_dev, ld, M, V, idx_dev, logprob_dev, (cudaStream_t)stream);
 }
 
 size_t ac_clip_adam_workspace_bytes(void) { return ac::kNormBlocks * sizeof(float); }

@@ -77,8 +77,8 @@ int relu_drop_bwd(const float* dY, const float* Y, int64_t n, Dropout dp, uint32
 // dst[i, :] = src[rows[i], :] ;  dst[rows[i], :] (+)= src[i, :]
 int gather_rows(const float* src, const int* rows, int n, int D, float* dst, cudaStream_t st);
 int scatter_rows(const float* src, const int* rows, int n, int D, float* dst, cudaStream_t st);
-// idx[m] = argmax_v X[m, v] (first maximum), logprob[m] = max log-softmax (nullable)
-int argmax_rows(const float* X, int M, int V, int64_t* idx, float* logprob, cudaStream_t st);
+// idx[m] = argmax_v X[m * ld + v] (first maximum), logprob[m] = max log-softmax (nullable)
+int argmax_rows(const float* X, int ld, int M, int V, int64_t* idx, float* logprob, cudaStream_t st);
 
 // Multi-head attention core on projected tensors (nn.MultiheadAttention, batch-major rows m = seq * L + t).
 //   Q rows [n_seq * L] (row stride ldq), K / V rows [n_kv_seq * Lk] (row stride ldkv); head h = columns [h*64, h*64+64).

@@ -184,6 +184,10 @@ struct DecodeArgs {
     float* embed_out;           // nullable [clips][max_len][D]
     // beam
     int beam; float temp;
+    // scheduled-sampling decode (training, base.py:152-170 with mode == "train"): no early stop, no <end> forcing, and
+    // where forced[clip][t] >= 0 that token is emitted (and fed back) instead of the arg-max
+    const int64_t* forced;      // nullable [clips][max_len]
+    int train_mode;
     long long* dbg;             // optional phase trace of CTA 0 (ac_trm_trace): clock64 stamps
     int kv_in_smem;             // the launch reserved shared memory for the cross-attention K/V
 };
@@ -412,11 +416,15 @@ greedy_kernel(DecodeArgs a) {
             for (int n = tid; n < V; n += kThreads) se += expf(logits[n] - best);
             se = block_sum(se, s_rv);
             word[r] = finished[r] ? a.end_idx : bi;
+            if (a.forced != nullptr && valid[r]) {
+                const int64_t f = a.forced[(size_t)(clip0 + r) * a.max_len + t];
+                if (f >= 0) word[r] = (int)f;
+            }
             if (tid == 0 && writer && valid[r]) {
                 a.seq[(size_t)(clip0 + r) * a.max_len + t] = word[r];
                 if (a.logprob) a.logprob[(size_t)(clip0 + r) * a.max_len + t] = -logf(se);
             }
-            finished[r] = finished[r] || (word[r] == a.end_idx);
+            finished[r] = !valid[r] || (!a.train_mode && (finished[r] || (word[r] == a.end_idx)));
         }
         AC_DEC_STAMP(42);
     }
@@ -580,6 +588,7 @@ struct ac_trm {
     float* tcblob = nullptr;               // tensor-core images of the memory-side weights (gemm.cuh)
     ac::TcWeight proj_tw, kv_tw[ac::kMaxLayers];
     ac::DecW w;
+    std::vector<int64_t> want;             // element count of every source tensor, in tensor order
 };
 
 namespace ac {
@@ -617,38 +626,11 @@ static int prepare_memory(const ac_trm* d, const float* attn_emb, int clips, int
 }
 }  // namespace ac
 
-extern "C" {
-
-int ac_trm_num_tensors(int nlayers) { return 2 + 18 * nlayers + 5; }
-
-int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, int d_model, int nhead, int nlayers,
-                  int dim_ff, int vocab, int attn_emb_dim, int pe_len, void* stream, ac_trm_t** out) {
+// (Re)builds every packed / transposed weight image of `d` from the source tensors `t` (asynchronous on `st`, no allocation).
+static int trm_fill(ac_trm_t* d, const float* const* t, cudaStream_t st) {
     using namespace ac;
-    AC_REQUIRE(t && numels && out, "ac_trm_create: null argument");
-    AC_REQUIRE(d_model == D && nhead == NH, "ac_trm_create: only d_model=256 / nhead=4 is built (got %d/%d)", d_model, nhead);
-    AC_REQUIRE(nlayers >= 1 && nlayers <= kMaxLayers, "ac_trm_create: nlayers %d not in [1,%d]", nlayers, kMaxLayers);
-    AC_REQUIRE(dim_ff % 32 == 0 && dim_ff <= 1024, "ac_trm_create: dim_feedforward %d must be <=1024 and %%32", dim_ff);
-    AC_REQUIRE(attn_emb_dim % 4 == 0, "ac_trm_create: attn_emb_dim %d must be a multiple of 4", attn_emb_dim);
-    AC_REQUIRE(n_tensors == ac_trm_num_tensors(nlayers), "ac_trm_create: expected %d tensors, got %d",
-               ac_trm_num_tensors(nlayers), n_tensors);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int F = dim_ff, V = vocab;
-    // expected element counts, in tensor order
-    std::vector<int64_t> want = {(int64_t)V * D, (int64_t)pe_len * D};
-    for (int l = 0; l < nlayers; ++l) {
-        int64_t per[18] = {3 * D * D, 3 * D, D * D, D, 3 * D * D, 3 * D, D * D, D, (int64_t)F * D, F, (int64_t)D * F, D,
-                           D, D, D, D, D, D};
-        want.insert(want.end(), per, per + 18);
-    }
-    int64_t tail[5] = {(int64_t)V * D, (int64_t)D * attn_emb_dim, D, D, D};
-    want.insert(want.end(), tail, tail + 5);
-    for (int i = 0; i < n_tensors; ++i)
-        AC_REQUIRE(numels[i] == want[i], "ac_trm_create: tensor %d has %lld elements, expected %lld", i,
-                   (long long)numels[i], (long long)want[i]);
-    size_t total = align_up((size_t)D * ((V + 3) / 4 * 4), 64);   // padded classifier copy
-    for (auto n : want) total += align_up((size_t)n, 64);
-    ac_trm_t* d = new ac_trm_t();
-    AC_CUDA(cudaMalloc(&d->blob, total * sizeof(float)));
+    const std::vector<int64_t>& want = d->want;
+    const int nlayers = d->w.nlayers, F = d->w.dff, V = d->w.vocab, attn_emb_dim = d->w.attn_emb_dim;
     size_t off = 0;
     int ti = 0;
     int rc = AC_OK;
@@ -665,7 +647,6 @@ int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, i
         return p;
     };
     DecW& W = d->w;
-    W.nlayers = nlayers; W.dff = F; W.vocab = V; W.attn_emb_dim = attn_emb_dim; W.pe_len = pe_len;
     W.emb = plain();
     W.pe = plain();
     for (int l = 0; l < nlayers; ++l) {
@@ -706,16 +687,67 @@ int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, i
     W.proj_w = plain(); W.proj_b = plain(); W.proj_ln_g = plain(); W.proj_ln_b = plain();
     if (rc == AC_OK && attn_emb_dim % 8 == 0) {
         const size_t np = align_up(tc_packed_floats(D, attn_emb_dim), 64), nk = align_up(tc_packed_floats(2 * D, D), 64);
-        rc = check_cuda(cudaMalloc(&d->tcblob, (np + nlayers * nk) * sizeof(float)), "cudaMalloc tc weights");
         if (rc == AC_OK) rc = tc_pack_weight(W.proj_w, nullptr, D, attn_emb_dim, d->tcblob, st, &d->proj_tw);
         for (int l = 0; l < nlayers && rc == AC_OK; ++l)
             rc = tc_pack_weight(W.layer[l].ca_kv_w, nullptr, 2 * D, D, d->tcblob + np + l * nk, st, &d->kv_tw[l]);
     }
+    if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "trm_fill pack kernels");
+    return rc;
+}
+
+extern "C" {
+
+int ac_trm_num_tensors(int nlayers) { return 2 + 18 * nlayers + 5; }
+
+int ac_trm_create(const float* const* t, const int64_t* numels, int n_tensors, int d_model, int nhead, int nlayers,
+                  int dim_ff, int vocab, int attn_emb_dim, int pe_len, void* stream, ac_trm_t** out) {
+    using namespace ac;
+    AC_REQUIRE(t && numels && out, "ac_trm_create: null argument");
+    AC_REQUIRE(d_model == D && nhead == NH, "ac_trm_create: only d_model=256 / nhead=4 is built (got %d/%d)", d_model, nhead);
+    AC_REQUIRE(nlayers >= 1 && nlayers <= kMaxLayers, "ac_trm_create: nlayers %d not in [1,%d]", nlayers, kMaxLayers);
+    AC_REQUIRE(dim_ff % 32 == 0 && dim_ff <= 1024, "ac_trm_create: dim_feedforward %d must be <=1024 and %%32", dim_ff);
+    AC_REQUIRE(attn_emb_dim % 4 == 0, "ac_trm_create: attn_emb_dim %d must be a multiple of 4", attn_emb_dim);
+    AC_REQUIRE(n_tensors == ac_trm_num_tensors(nlayers), "ac_trm_create: expected %d tensors, got %d",
+               ac_trm_num_tensors(nlayers), n_tensors);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = dim_ff, V = vocab;
+    // expected element counts, in tensor order
+    std::vector<int64_t> want = {(int64_t)V * D, (int64_t)pe_len * D};
+    for (int l = 0; l < nlayers; ++l) {
+        int64_t per[18] = {3 * D * D, 3 * D, D * D, D, 3 * D * D, 3 * D, D * D, D, (int64_t)F * D, F, (int64_t)D * F, D,
+                           D, D, D, D, D, D};
+        want.insert(want.end(), per, per + 18);
+    }
+    int64_t tail[5] = {(int64_t)V * D, (int64_t)D * attn_emb_dim, D, D, D};
+    want.insert(want.end(), tail, tail + 5);
+    for (int i = 0; i < n_tensors; ++i)
+        AC_REQUIRE(numels[i] == want[i], "ac_trm_create: tensor %d has %lld elements, expected %lld", i,
+                   (long long)numels[i], (long long)want[i]);
+    size_t total = align_up((size_t)D * ((V + 3) / 4 * 4), 64);   // padded classifier copy
+    for (auto n : want) total += align_up((size_t)n, 64);
+    ac_trm_t* d = new ac_trm_t();
+    d->want = want;
+    DecW& W0 = d->w;
+    W0.nlayers = nlayers; W0.dff = F; W0.vocab = V; W0.attn_emb_dim = attn_emb_dim; W0.pe_len = pe_len;
+    int rc = check_cuda(cudaMalloc(&d->blob, total * sizeof(float)), "ac_trm_create: cudaMalloc");
+    if (rc == AC_OK && attn_emb_dim % 8 == 0) {
+        const size_t np = align_up(tc_packed_floats(D, attn_emb_dim), 64), nk = align_up(tc_packed_floats(2 * D, D), 64);
+        rc = check_cuda(cudaMalloc(&d->tcblob, (np + nlayers * nk) * sizeof(float)), "cudaMalloc tc weights");
+    }
+    if (rc == AC_OK) rc = trm_fill(d, t, st);
     if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_trm_create pack kernels");
     if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_trm_create sync");
     if (rc != AC_OK) { cudaFree(d->blob); cudaFree(d->tcblob); delete d; return rc; }
     *out = d;
     return AC_OK;
+}
+
+// Re-reads the source tensors (same order and sizes as at creation) into the existing handle: asynchronous, no allocation.
+// The training loop calls it once per optimizer step so that the sampling decode of scheduled sampling sees the updated weights.
+int ac_trm_update(ac_trm_t* d, const float* const* t, int n_tensors, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(d && t && n_tensors == (int)d->want.size(), "ac_trm_update: bad argument");
+    return trm_fill(d, t, (cudaStream_t)stream);
 }
 
 void ac_trm_destroy(ac_trm_t* d) {
@@ -760,9 +792,34 @@ static int trm_common_checks(const ac_trm_t* dec, int batch, int t_mem, int max_
     return AC_OK;
 }
 
+static int trm_greedy_impl(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_emb_len, int batch, int t_mem,
+                           int max_len, int start_idx, int end_idx, int pad_idx, const int64_t* forced, int train_mode,
+                           int64_t* seq, float* logprob, float* logit, float* embed, void* ws, size_t ws_bytes, void* stream);
+
 int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_emb_len, int batch, int t_mem,
                   int max_len, int start_idx, int end_idx, int pad_idx, int64_t* seq, float* logprob, float* logit,
                   float* embed, void* ws, size_t ws_bytes, void* stream) {
+    return trm_greedy_impl(dec, attn_emb, attn_emb_len, batch, t_mem, max_len, start_idx, end_idx, pad_idx, nullptr, 0, seq,
+                           logprob, logit, embed, ws, ws_bytes, stream);
+}
+
+// The sampling half of scheduled-sampling training (captioning/models/transformer_model.py:34-57 under
+// captioning/models/base.py:152-170, mode == "train"): builds the model's own token row step by step, KV-cached.
+// forced_dev [batch, max_len] int64: where >= 0 that token is emitted at the step (the step's coin chose the ground-truth
+// prefix, whose arg-max the caller already knows from the dense pass), where < 0 the arg-max of this decode is taken.
+// No early stop and no <end> forcing (the reference only does that in inference mode).  seq_dev [batch, max_len].
+int ac_trm_sample_forced(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_emb_len, int batch, int t_mem,
+                         int max_len, int start_idx, int end_idx, int pad_idx, const int64_t* forced_dev, int64_t* seq,
+                         float* logprob, void* ws, size_t ws_bytes, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(forced_dev != nullptr, "ac_trm_sample_forced: forced_dev is NULL");
+    return trm_greedy_impl(dec, attn_emb, attn_emb_len, batch, t_mem, max_len, start_idx, end_idx, pad_idx, forced_dev, 1, seq,
+                           logprob, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+static int trm_greedy_impl(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_emb_len, int batch, int t_mem,
+                           int max_len, int start_idx, int end_idx, int pad_idx, const int64_t* forced, int train_mode,
+                           int64_t* seq, float* logprob, float* logit, float* embed, void* ws, size_t ws_bytes, void* stream) {
     using namespace ac;
     int rc = trm_common_checks(dec, batch, t_mem, max_len); if (rc) return rc;
     if (batch == 0) return AC_OK;
@@ -776,6 +833,7 @@ int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb, const int64_t* att
     a.w = dec->w; a.kv_mem = kvmem; a.n_clips = batch; a.mem_len = attn_emb_len; a.kv_cache = cache; a.logits_ws = lws;
     a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
     a.seq = seq; a.logprob = logprob; a.logit_out = logit; a.embed_out = embed; a.beam = 1; a.temp = 1.0f;
+    a.forced = forced; a.train_mode = train_mode;
     a.dbg = g_dec_trace;
     // (CTAs per cluster, clips per cluster); AC_GREEDY="P,G" overrides for experiments
     int P = trm_cluster_size(batch, kGreedyCluster), G = kGreedyClips;

@@ -1,0 +1,148 @@
+"""The training step of python_scripts/train_eval/run.py:77-148 (`Runner._train_epoch` body) as one fused device pipeline.
+
+Per iteration, in the reference's order: scheduled-sampling ratio update (:55-65), learning-rate step (:105,
+captioning/utils/lr_scheduler.py:5-45), zero_grad, forward (:21-47 -> captioning/models/base.py:48-137), label-smoothing
+loss (captioning/losses/loss.py:51-74), backward, `clip_grad_norm_(model.parameters(), max_grad_norm)` (:125-126),
+Adam step (:127), skipped when the loss is NaN (:123).  Here:
+
+  * the trainable parameters (bi-GRU + Transformer decoder, 10.7 M) are re-homed as views of ONE flat fp32 buffer, their
+    `.grad`s as views of a second one; the backward kernels write gradients straight into it (no autograd, no zero_grad:
+    every gradient is overwritten each step);
+  * data parallel: ONE `all_reduce(sum)` over the flat gradient buffer (NCCL over NVLink / NVSwitch,
+    python_scripts/train_eval/run_ddp.py:105-107 wraps the model in DDP for the same exchange), the 1/world scale is
+    folded into the optimizer kernel;
+  * global-norm clip + Adam (+ L2 weight decay, bias correction, NaN skip) run as two launches over the flat buffers
+    (csrc/train_ops.cu `ac_clip_adam`); nothing synchronises with the host -- the loss stays on the device until read.
+
+The frozen Cnn14 runs forward only (BatchNorm in eval mode, dropout active: `freeze_cnn`, `freeze_cnn_bn`)."""
+import random
+
+import torch
+
+from . import _lib
+from .captioning.models._native import to_device_async
+from .captioning.utils.lr_scheduler import exponential_decay_lr
+
+
+class TrainStep:
+    """`step(batch)` = one optimizer step of the reference's training loop on the Cnn14Rnn-Transformer captioner
+    (eg_configs/*/waveform/cnn14rnn_trm.yaml): TransformerModel(CrnnEncoder(Cnn14Encoder, RnnEncoder), TransformerDecoder)."""
+
+    def __init__(self, model, total_iters, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, max_grad_norm=1.0,
+                 smoothing=0.1, final_lr=5e-7, warmup_iters=None, ss_mode="linear", ss_final_ratio=0.7, use_ss=True,
+                 process_group=None):
+        from .captioning.models.crnn_trm_encoder import CrnnEncoder
+        from .captioning.models.transformer_model import TransformerModel
+        if not isinstance(model, TransformerModel) or not isinstance(model.encoder, CrnnEncoder):
+            raise NotImplementedError("TrainStep is built for TransformerModel(CrnnEncoder(...), TransformerDecoder)")
+        if any(p.requires_grad for p in model.encoder.cnn.parameters()):
+            raise NotImplementedError("the CNN has no backward pass on the B200 path: build it with freeze_cnn: True")
+        self.model = model
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise _lib.AudioCaptionB200Error("TrainStep needs the model on a CUDA device (no CPU fallback)")
+        self.total_iters = int(total_iters)
+        self.warmup_iters = self.total_iters // 5 if warmup_iters is None else int(warmup_iters)     # run.py:249-251
+        self.base_lr, self.final_lr = float(lr), float(final_lr)
+        self.betas, self.eps, self.weight_decay = betas, float(eps), float(weight_decay)
+        self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
+        self.smoothing = float(smoothing)
+        self.use_ss, self.ss_mode, self.ss_final_ratio = use_ss, ss_mode, float(ss_final_ratio)
+        self.ss_ratio = 1.0
+        self.iteration = 0
+        self.group = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self._flatten()
+        l = _lib.lib()
+        with torch.cuda.device(self.device):
+            self._adam_ws = torch.empty(l.ac_clip_adam_workspace_bytes(), dtype=torch.uint8, device=self.device)
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.grad_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.lr = 0.0
+        model.train()
+
+    # ---- flat parameter / gradient storage -------------------------------------------------------------------------
+    def _flatten(self):
+        params, seen = [], set()
+        for p in self.model.parameters():
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        offs, total = [], 0
+        for p in params:
+            if p.dtype != torch.float32:
+                raise _lib.AudioCaptionB200Error("TrainStep needs fp32 master parameters")
+            offs.append(total)
+            total += (p.numel() + 31) // 32 * 32          # 128-byte aligned: gradients are written by TMA stores
+        dev = self.device
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, o in zip(params, offs):
+            view = self.flat_param[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        self.params = params
+        self.n_trainable = sum(p.numel() for p in params)
+
+    # ---- schedules (host) ---------------------------------------------------------------------------------------------
+    def _update_ss_ratio(self):
+        """run.py:55-65"""
+        if not self.use_ss:
+            return
+        if self.ss_mode == "exponential":
+            self.ss_ratio *= 0.01 ** (1.0 / self.total_iters)
+        elif self.ss_mode == "linear":
+            self.ss_ratio -= (1.0 - self.ss_final_ratio) / self.total_iters
+        else:
+            raise Exception(f"mode {self.ss_mode} not supported")
+
+    # ---- one step -------------------------------------------------------------------------------------------------------
+    def step(self, batch, coins=None):
+        """batch: {"wav" [B, N] fp32 (host, ideally pinned, or cuda), "wav_len" [B], "cap" [B, Lc] int64, "cap_len" [B]}.
+        Returns {"loss": device scalar tensor [1], "tokens": int, "lr": float, "ss_ratio": float}."""
+        m = self.model
+        dev = self.device
+        l = _lib.lib()
+        self._update_ss_ratio()
+        # the scheduler was stepped once by its constructor; iteration k (0-based) steps it for the (k+2)-th time (run.py:105)
+        self.lr = exponential_decay_lr(self.iteration + 2, self.base_lr, self.final_lr, self.total_iters, self.warmup_iters)
+        with torch.cuda.device(dev), torch.no_grad():
+            wav = batch["wav"]
+            wav = wav.to(dev, torch.float32, non_blocking=True)
+            cap = batch["cap"].to(dev, torch.int64, non_blocking=True)
+            cap_len = torch.as_tensor(batch["cap_len"]).to(torch.int64)
+            tgt_len_dev = to_device_async(cap_len - 1, dev, torch.int64)
+            # frozen CNN (dropout on, BatchNorm eval) -> frames; bi-GRU; decoder
+            cnn_out = m.encoder.cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": False})
+            lens = cnn_out["attn_emb_len"]
+            t_out = int(lens.max())
+            x = cnn_out["attn_emb"][:, :t_out].contiguous()
+            len_dev = to_device_async(lens, dev, torch.int64)
+            rnn = m.encoder.rnn
+            mem = rnn.train_engine.forward(x, len_dev, p_drop=float(rnn.dropout) if rnn.num_layers > 1 else 0.0, grads="param")
+            L = cap.size(1) - 1
+            if coins is None:
+                coins = [random.random() < self.ss_ratio for _ in range(L)] if self.ss_ratio != 1 else None
+            dec = m.decoder
+            out = dec.train_engine.forward(mem, len_dev, cap[:, :-1].contiguous(), coins=coins,
+                                           p_drop=float(dec.in_dropout.p), grads="param", start_idx=m.start_idx,
+                                           end_idx=m.end_idx, pad_idx=m.pad_idx)
+            from .captioning.losses.loss import ls_ce_fwd_bwd
+            loss, dlogit = ls_ce_fwd_bwd(out["logit_padded"][:, :, :dec.vocab_size], cap[:, 1:], tgt_len_dev, self.smoothing)
+            dmem = dec.train_engine.backward(dlogit, need_dattn=True)
+            rnn.train_engine.backward(dmem, need_dx=False)
+            if self.world > 1:
+                torch.distributed.all_reduce(self.flat_grad, group=self.group)
+            _lib.check(l.ac_clip_adam(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                      _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), self.lr, self.betas[0], self.betas[1],
+                                      self.eps, self.weight_decay, self.max_grad_norm, 1.0 / self.world, _lib.ptr(loss),
+                                      _lib.ptr(self._step_dev), _lib.ptr(self.grad_norm), _lib.ptr(self._adam_ws),
+                                      self._adam_ws.numel(), _lib.current_stream()), "ac_clip_adam")
+        self.iteration += 1
+        self.last_output = out
+        return {"loss": loss, "tokens": int((cap_len - 1).sum()), "lr": self.lr, "ss_ratio": self.ss_ratio}

@@ -150,6 +150,13 @@ int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms_dev, int batch, int n_m
                  const int64_t* lens_dev, float* attn_emb_dev, float* fc_emb_dev,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Train-mode forward of the frozen encoder (BatchNorm folded = eval, `freeze_cnn_bn`), with the functional dropouts of
+ * captioning/models/cnn_encoder.py:432-456 active: p_conv after each ConvBlock (reference 0.2), p_fc around fc1 (0.5).
+ * Masks are a function of (seed, site, element index).  p_conv = p_fc = 0 is ac_cnn14_fwd. */
+int ac_cnn14_fwd_train(const ac_cnn14_t* net, const float* lms_dev, int batch, int n_mels, int n_frames,
+                       const int64_t* lens_dev, float p_conv, float p_fc, uint64_t seed, float* attn_emb_dev,
+                       float* fc_emb_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ sound-event tagger of the temporal captioner
  * Replaces captioning/models/hf_wrapper.py:1791-1859 `Cnn8rnnSedModel.forward_prob` (bn0, 4 ConvBlocks with 'avg+max'
  * pooling (2,2)(2,2)(1,2)(1,2), mean over mel, fc1 + ReLU, bidirectional GRU(512 -> 256), fc_audioset, sigmoid,
@@ -218,6 +225,17 @@ int ac_trm_greedy(const ac_trm_t* dec, const float* attn_emb_dev, const int64_t*
                   int batch, int t_mem, int max_len, int start_idx, int end_idx, int pad_idx,
                   int64_t* seq_dev, float* logprob_dev, float* logit_dev, float* embed_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Re-read the source tensors (same order / sizes as at creation) into an existing handle: asynchronous, no allocation.
+ * The training loop calls it once per optimizer step. */
+int ac_trm_update(ac_trm_t* dec, const float* const* tensors_dev, int n_tensors, void* stream);
+/* The sampling half of scheduled-sampling training (captioning/models/transformer_model.py:34-57 under
+ * captioning/models/base.py:152-170 with mode == "train"): the model's own token row, step by step with the KV cache.
+ * forced_dev [batch, max_len] int64: >= 0 = emit (and feed back) that token at the step -- the step's coin chose the
+ * ground-truth prefix, whose arg-max the dense pass already produced; < 0 = take this decode's arg-max.  No early stop,
+ * no <end> forcing (train mode).  seq_dev [batch, max_len] int64, logprob_dev nullable. */
+int ac_trm_sample_forced(const ac_trm_t* dec, const float* attn_emb_dev, const int64_t* attn_emb_len_dev, int batch, int t_mem,
+                         int max_len, int start_idx, int end_idx, int pad_idx, const int64_t* forced_dev, int64_t* seq_dev,
+                         float* logprob_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Beam search, one independent search per clip with the reference's bookkeeping
  * (double log-softmax with temperature, -1000 penalty, `== beam_size` stop rule,
  * score/(t+1) ranking).  seq_dev [batch, max_len] int64 = best beam per clip. */
@@ -322,6 +340,9 @@ int ac_trm_train_bwd(ac_trm_train_t* dec, const float* dlogits_dev, const int* r
 int ac_ls_ce_fwd_bwd(const float* logit_dev, int ld_logit, const int64_t* tgt_dev, int ld_tgt, const int64_t* tgt_len_dev, int B,
                      int L, int V, float smoothing, float grad_scale, float* loss_dev, float* dlogit_dev, void* workspace_dev,
                      size_t workspace_bytes, void* stream);
+/* `sample_next_word(method="greedy")` (captioning/models/base.py:214-218) over M logit rows of stride ld_logit:
+ * idx_dev[m] = first arg-max over the V valid columns, logprob_dev[m] (nullable) = its log-softmax value. */
+int ac_argmax_rows(const float* logit_dev, int ld_logit, int M, int V, int64_t* idx_dev, float* logprob_dev, void* stream);
 /* python_scripts/train_eval/run.py:123-127: skip when the loss is NaN, else clip_grad_norm_(max_norm) over the flat
  * gradient, then torch.optim.Adam.step (L2 weight decay, bias correction from the device-side step counter).
  * grad_scale multiplies the gradient first (1 / world_size after a sum all-reduce).  norm_out_dev (nullable) receives the

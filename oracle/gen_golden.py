@@ -189,6 +189,75 @@ def sed(seed=12, batch=8, n=96000):
                         seg=seg[:, ::3, ::7].numpy(), stable=stable.numpy())
 
 
+def reference_train_step(ss_ratio=0.6, coin_seed=22, batch=4, n=96000, cap_max=9, lr=2e-4, vocab=4981):
+    """ONE training step of the reference's own classes (python_scripts/train_eval/run.py:116-127 on
+    TransformerModel(CrnnEncoder(Cnn14Encoder, RnnEncoder), TransformerDecoder) + LabelSmoothingLoss + Adam) with every
+    dropout disabled: returns (inputs, loss, grads, updated parameters)."""
+    import random
+    from . import cnn14 as oc
+    from . import crnn
+    from . import train_step as ts
+    ref = build_reference_cnn14rnn_trm() if vocab == 4981 else None
+    assert ref is not None
+    loss_mod = ref_import.load("captioning.losses.loss")
+    dec = crnn.build_decoder(6, vocab_size=vocab)
+    sd = crnn.model_state_dict(oc.build_state_dict(3), crnn.build_gru_state_dict(4), dec)
+    ref.load_state_dict(sd, strict=True)
+    ref.train()
+    for m in ref.modules():                                  # dropout off everywhere (deterministic parity)
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, (torch.nn.MultiheadAttention, torch.nn.GRU)):
+            m.dropout = 0.0
+    wav, lens = cm.synth_wav(batch, n, seed=13, ragged=True, varied=True, sample_rate=32000)
+    cap, cap_len = ts.synth_captions(batch, cap_max, vocab, seed=1)
+    real_dropout = torch.nn.functional.dropout
+    torch.nn.functional.dropout = lambda x, p=0.5, training=True, inplace=False: x     # the frozen CNN's F.dropout calls
+    try:
+        random.seed(coin_seed)
+        out = ref({"mode": "train", "wav": wav, "wav_len": lens, "specaug": False, "cap": cap, "cap_len": cap_len.numpy(),
+                   "ss_ratio": ss_ratio})
+    finally:
+        torch.nn.functional.dropout = real_dropout
+    out["tgt"], out["tgt_len"] = cap[:, 1:], torch.as_tensor(cap_len.numpy() - 1)
+    loss = loss_mod.LabelSmoothingLoss(smoothing=0.1)(out)
+    opt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=lr, weight_decay=1e-6)
+    opt.zero_grad()
+    loss.backward()
+    grads = {k: v.grad.detach().clone() for k, v in ref.named_parameters() if v.requires_grad}
+    gnorm = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    opt.step()
+    new_params = {k: v.detach().clone() for k, v in ref.named_parameters() if v.requires_grad}
+    random.seed(coin_seed)
+    coins = [random.random() < ss_ratio for _ in range(cap.size(1) - 1)]
+    return dict(wav=wav, wav_len=lens, cap=cap, cap_len=cap_len, coins=coins, loss=loss.detach(), grads=grads, gnorm=gnorm,
+                new_params=new_params, seq=out["seq"], logit=out["logit"].detach(), lr=lr, ss_ratio=ss_ratio,
+                coin_seed=coin_seed, vocab=vocab, batch=batch, n=n, cap_max=cap_max)
+
+
+def train_step():
+    """tests/golden/train_step.npz: loss, total gradient norm, per-parameter gradient norms and leading entries, and the
+    per-parameter update norms of one reference training step (reference_train_step above)."""
+    r = reference_train_step()
+    names = sorted(r["grads"])
+    init = {k: v for k, v in build_reference_state(r["vocab"]).items()}
+    np.savez_compressed(
+        os.path.join(OUT, "train_step.npz"), names=np.array(names), loss=r["loss"].numpy(), gnorm=r["gnorm"].numpy(),
+        coins=np.array(r["coins"]), cap=r["cap"].numpy(), cap_len=r["cap_len"].numpy(), wav_len=r["wav_len"].numpy(),
+        seq=r["seq"].numpy(), lr=r["lr"], ss_ratio=r["ss_ratio"], coin_seed=r["coin_seed"], vocab=r["vocab"], batch=r["batch"],
+        n_samples=r["n"], cap_max=r["cap_max"], logit_head=r["logit"][:, :, :16].numpy(),
+        grad_norms=np.array([r["grads"][k].norm().item() for k in names]),
+        grad_heads=np.stack([np.resize(r["grads"][k].flatten()[:16].numpy(), 16) for k in names]),
+        update_norms=np.array([(r["new_params"][k] - init[k]).norm().item() for k in names]))
+    print("train_step loss", float(r["loss"]), "gnorm", float(r["gnorm"]), "coins", r["coins"], "seq\n", r["seq"])
+
+
+def build_reference_state(vocab=4981):
+    from . import cnn14 as oc
+    from . import crnn
+    return crnn.model_state_dict(oc.build_state_dict(3), crnn.build_gru_state_dict(4), crnn.build_decoder(6, vocab_size=vocab))
+
+
 def eg_configs():
     """The `model:` sections of the two Cnn14Rnn-Transformer training YAMLs (eg_configs/{audiocaps,clotho_v2}/waveform/
     cnn14rnn_trm.yaml:7-38) as fixtures for the factory tests (tests/test_boundary_cpu.py)."""
@@ -205,9 +274,11 @@ def eg_configs():
 if __name__ == "__main__":
     import sys
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm", "temp_gru", "sed", "eg_configs"]
+    which = sys.argv[1:] or ["effb2_trm", "cnn14", "cnn14rnn_trm", "temp_gru", "sed", "eg_configs", "train_step"]
     if "eg_configs" in which:
         eg_configs()
+    if "train_step" in which:
+        train_step()
     if "effb2_trm" in which:
         effb2_trm()
     if "cnn14" in which:

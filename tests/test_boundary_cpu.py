@@ -87,7 +87,7 @@ def test_factory_builds_the_yaml_model_and_loads_reference_state_dict(yaml_name,
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
     n_gru = sum(p.numel() for p in model.encoder.rnn.parameters())
     n_dec = sum(p.numel() for n, p in model.decoder.named_parameters() if n != "pos_encoder.pe")
-    assert n_train == n_gru + n_dec and n_gru == 5_912_064 and n_train == n_gru + 2 * 256 * V + 2_237_184
+    assert n_train == n_gru + n_dec and n_gru == 5_907_456 and n_dec == 2 * 256 * V + 2_238_720
     sd = {f"encoder.cnn.{k}": v for k, v in oc.build_state_dict(3).items()}
     sd.update({f"encoder.rnn.{k}": v for k, v in crnn.build_gru_state_dict(4).items()})
     sd.update({f"decoder.{k}": v for k, v in crnn.build_decoder(6, 512, V).state_dict().items()})

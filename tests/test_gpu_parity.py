@@ -194,6 +194,18 @@ def test_encoder_matches_golden(mirror, golden_effb2, golden_wav):
 
 
 # ------------------------------------------------------------------ decoder: greedy / beam
+def _stable_rows(decode, attn, n_pert=4, eps=1e-3, seed=99):
+    """Rows whose ORACLE tokens survive `n_pert` relative perturbations of size `eps` of the audio memory: on those a
+    different token from the device cannot be blamed on fp32 re-ordering (3e-4 on the logits), so equality must be
+    exact.  The criterion the golden files use (oracle/gen_golden.py `*_stable`)."""
+    gen = torch.Generator().manual_seed(seed)
+    base = decode(attn)
+    stable = torch.ones(attn.shape[0], dtype=torch.bool)
+    for _ in range(n_pert):
+        stable &= (decode(attn * (1 + eps * torch.randn(attn.shape, generator=gen))) == base).all(1)
+    return base, stable
+
+
 def _decoder(mirror):
     return mirror.model.model.decoder
 
@@ -254,8 +266,10 @@ def test_decoder_matches_oracle_random_memory(mirror, oracle_effb2, seed):
     # truncates instead of rounding, so the first-step logits carry ~1e-4 instead of ~2e-5 (north_star: 1e-3)
     assert (lg[:, 0] - rlg[:, 0]).abs().max() < 3e-4
     outb = dec.beam_search(attn.to(DEV), lens, 20, 3, 0.7, cm.START, cm.END, cm.PAD)
-    same = (outb["seq"].cpu() == refb["seq"]).all(1)
-    assert same.float().mean() >= 0.75, (outb["seq"].cpu(), refb["seq"])
+    with torch.no_grad():
+        base, stable = _stable_rows(lambda a: cm.beam_search(oracle_effb2.decoder, a, lens, 3, 20, temp=0.7)["seq"], attn)
+    assert (base == refb["seq"]).all() and stable.any()
+    assert (outb["seq"].cpu()[stable] == refb["seq"][stable]).all(), (outb["seq"].cpu(), refb["seq"], stable)
 
 
 # ------------------------------------------------------------------ whole model through the public API
@@ -303,7 +317,12 @@ def test_decoder_batches_beyond_one_wave(mirror, oracle_effb2, batch):
     assert (full[idx] == sub).all()
     with torch.no_grad():
         ref = cm.greedy_decode(oracle_effb2.decoder, attn[idx], lens[idx], 20)
-    assert (sub == ref["seq"]).float().mean() > 0.9     # near-ties aside (checked strictly on the golden set)
+    for b in range(len(idx)):                           # a differing row must START at a top-2 near-tie of the oracle's logits
+        if (sub[b] == ref["seq"][b]).all():
+            continue
+        t = int((sub[b] != ref["seq"][b]).nonzero()[0])
+        top2 = ref["logit"][b, t].topk(2).values
+        assert top2[0] - top2[1] < 1e-4, f"batch {batch} row {b} step {t}: token differs without a near-tie"
 
 
 @pytest.mark.parametrize("beam", [1, 2, 4, 5])
@@ -312,9 +331,10 @@ def test_beam_sizes_match_oracle(mirror, oracle_effb2, beam):
     attn = torch.randn(4, 32, 1408, generator=gen)
     lens = torch.tensor([32, 17, 5, 31])
     with torch.no_grad():
-        ref = cm.beam_search(oracle_effb2.decoder, attn, lens, beam, 20)
+        ref, stable = _stable_rows(lambda a: cm.beam_search(oracle_effb2.decoder, a, lens, beam, 20)["seq"], attn)
     got = _decoder(mirror).beam_search(attn.to(DEV), lens, 20, beam, 1.0, cm.START, cm.END, cm.PAD)["seq"].cpu()
-    assert (got == ref["seq"]).all(1).float().mean() >= 0.75, (got, ref["seq"])
+    assert stable.any()
+    assert (got[stable] == ref[stable]).all(), (got, ref, stable)
 
 
 def test_submit_matches_forward(mirror, golden_wav):
@@ -341,10 +361,32 @@ def test_empty_batch_and_errors(mirror):
         enc({"wav": torch.zeros(1, 100, device=DEV), "wav_len": [100], "specaug": False})   # shorter than the reflect pad
 
 
+def test_config2_full_batch_matches_oracle(mirror, oracle_effb2):
+    """BASELINE configs[1] at full size -- 64 clips x 10 s through `Effb2TrmCaptioningModel.forward`, greedy -- against the
+    oracle chain on the same clips: encoder memory within 1e-3 of its scale per clip, token ids exact on every row whose
+    oracle caption survives 1e-3 relative perturbations of the memory (hf_wrapper.py:218-241,1162-1181)."""
+    wav, lens = cm.synth_wav(64, 160000, seed=5, ragged=True, varied=True)
+    with torch.no_grad():
+        ref = oracle_effb2.encoder({"wav": wav, "wav_len": lens})
+        base, stable = _stable_rows(lambda a: cm.greedy_decode(oracle_effb2.decoder, a, ref["attn_emb_len"], 20)["seq"],
+                                    ref["attn_emb"])
+    enc = mirror.model.model.encoder({"wav": wav.to(DEV), "wav_len": lens, "specaug": False})
+    assert enc["attn_emb_len"].tolist() == ref["attn_emb_len"].tolist()
+    err = (enc["attn_emb"].cpu() - ref["attn_emb"]).abs().amax(dim=(1, 2)) / ref["attn_emb"].abs().amax(dim=(1, 2))
+    assert (err < 1e-3).all(), err
+    seq = mirror(wav, lens, sample_method="greedy")
+    assert seq.shape == (64, 20)
+    assert stable.float().mean() > 0.5, stable          # the criterion must not be vacuous
+    assert (seq[stable] == base[stable]).all(), (seq[stable], base[stable])
+    # device decode on the ORACLE's memory: exact on the same rows (decoder alone, no encoder rounding in the way)
+    out = _decoder(mirror).greedy(ref["attn_emb"].to(DEV), ref["attn_emb_len"], 20, cm.START, cm.END, cm.PAD, need_logit=False)
+    assert (out["seq"].cpu()[stable] == base[stable]).all()
+
+
 def test_full_size_properties(mirror):
-    """BASELINE config 2 size (64 x 10 s): size-independent properties instead of the (slow) oracle:
-    batch independence of the encoder+decoder (clip i alone == clip i inside the batch, except the
-    batch-global top_db reference, so the loudest clip is included in both) and determinism."""
+    """BASELINE config 2 size (64 x 10 s): size-independent properties: batch independence of the encoder+decoder
+    (clip i alone == clip i inside the batch, except the batch-global top_db reference, so the loudest clip is included
+    in both) and determinism."""
     wav, lens = cm.synth_wav(64, 160000, seed=0)
     wav[0] *= 3.0                                              # the batch-global dB maximum lives in clip 0
     wd = wav.to(DEV)
@@ -610,6 +652,33 @@ def test_temp_gru_model_end_to_end(temp_gru):
         assert got.shape == (3, 20) and not got.is_cuda
         st = (ref == pert).all(1)
         assert (got[st] == ref[st]).all(), (method, got, ref)
+
+
+def test_config5_shape_matches_oracle_chain(temp_gru):
+    """BASELINE configs[4] at the size ONE GPU sees: 16 clips x 10 s @ 32 kHz, beam 4, SED tagger on
+    (`Cnn14RnnTempAttnGruModel.forward`, hf_wrapper.py:1942-1974), against the oracle chain log-mel -> SED tags -> Cnn14 ->
+    bi-GRU -> per-clip beam search: tags equal, encoder memory within 2e-4 absolute, captions exact on the rows whose
+    oracle caption survives a 1e-3 perturbation of the memory."""
+    from oracle import bah_decoder as bd, cnn14 as oc, crnn, sed
+    _, dsd, _ = temp_gru
+    m, cnn_sd, rnn_sd = _temp_gru_model(dsd)
+    wav, lens = cm.synth_wav(16, 320000, seed=41, ragged=True, varied=True, sample_rate=32000)
+    with torch.no_grad():
+        lms = oc.log_mel(cnn_sd, wav)
+        tags_ref = torch.as_tensor(sed.tags(sed.build_state_dict(12), lms))
+        enc = crnn.crnn_encoder(cnn_sd, rnn_sd, wav, lens)
+        tags_dev = torch.as_tensor(m.sed_model(m.melspec_extractor(wav.to(DEV))[0]))
+        enc_dev = m.cap_model.encoder({"wav": wav.to(DEV), "wav_len": lens, "specaug": False})
+        got = m(wav, lens, sample_method="beam", beam_size=4, max_length=20)
+    assert enc_dev["attn_emb"].shape == enc["attn_emb"].shape == (16, 31, 512)
+    assert (enc_dev["attn_emb"].cpu() - enc["attn_emb"]).abs().max() < 2e-4
+    same_tag = tags_dev == tags_ref             # a tag can only differ where a probability sits on a threshold
+    assert same_tag.float().mean() >= 0.75, (tags_dev, tags_ref)
+    ref = bd.beam_search(dsd, enc["fc_emb"], enc["attn_emb"], enc["attn_emb_len"], tags_dev, 4, 20, 1.0)["seq"]
+    pert = bd.beam_search(dsd, enc["fc_emb"] * 1.001, enc["attn_emb"] * 0.999, enc["attn_emb_len"], tags_dev, 4, 20, 1.0)["seq"]
+    st = (ref == pert).all(1)
+    assert got.shape == (16, 20) and st.float().mean() >= 0.5, st
+    assert (got[st] == ref[st]).all(), (got[st], ref[st])
 
 
 # ------------------------------------------------------------------ sound-event tagger (row A14)

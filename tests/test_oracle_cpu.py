@@ -427,3 +427,72 @@ def test_sed_host_decode_matches_oracle_decode():
         assert hw.decode_runs(np.array(rl, dtype=np.int32).reshape(-1, 4), 1, S, T)[0] == tag
         seen.add(tag)
     assert seen == {0, 1, 2, 3}
+
+
+# ------------------------------------------------------------------ EfficientNet-B2 restatement vs torchvision (executable anchor)
+def test_effnet_plan_matches_torchvision_b2():
+    """Widths, depths, kernels, strides and squeeze widths of the restated B2 (round_filters / round_repeats of
+    efficientnet_pytorch) equal torchvision's own EfficientNet-B2 (`_make_divisible` / `ceil`), block by block."""
+    import torchvision
+    tv = torchvision.models.efficientnet_b2(weights=None)
+    plan = eb.layer_plan()
+    tv_blocks = [blk for stage in list(tv.features)[1:-1] for blk in stage]
+    assert len(tv_blocks) == len(plan) == 23
+    assert tv.features[0][0].out_channels == 32 and tv.features[-1][0].out_channels == 1408
+    for p, blk in zip(plan, tv_blocks):
+        layers = list(blk.block)
+        dw = layers[-3][0]
+        se = layers[-2]
+        assert dw.groups == dw.in_channels == p["cin"] * p["expand"]
+        assert dw.kernel_size == (p["k"], p["k"]) and dw.stride == (p["s"], p["s"])
+        assert layers[-1][0].out_channels == p["cout"]
+        assert se.fc1.out_channels == p["nsq"]
+        assert (len(layers) == 4) == (p["expand"] != 1)
+        assert blk.use_res_connect == p["skip"]
+
+
+def test_effnet_blocks_match_torchvision_mbconv():
+    """Every one of the 23 restated MBConv blocks against `torchvision.models.efficientnet.MBConv` (an independent,
+    installed implementation of the same published block: expand 1x1 -> BN -> SiLU -> depthwise -> BN -> SiLU ->
+    squeeze-excite (avg-pool, FC, SiLU, FC, sigmoid) -> project 1x1 -> BN -> residual), with the SAME weights and
+    BatchNorm statistics.  torchvision pads symmetrically, efficientnet_pytorch pads 'static same' computed for a
+    260-pixel image: the restated pads are applied explicitly in front of torchvision's depthwise layer (padding 0) --
+    for stride-1 blocks they coincide with torchvision's own padding, which is asserted."""
+    from functools import partial
+    from torchvision.models.efficientnet import MBConv, MBConvConfig
+    torch.manual_seed(0)
+    net = eb.EfficientNet().eval()
+    norm = partial(torch.nn.BatchNorm2d, eps=1e-3, momentum=0.01)
+    for i, ((a, img), blk) in enumerate(zip(net.block_cfgs, net._blocks)):
+        for m in blk.modules():                     # non-trivial BN statistics / affines
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5)
+                m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+        cnf = MBConvConfig(a.expand_ratio, a.kernel_size, a.stride, a.input_filters, a.output_filters, 1, 1.0, 1.0)
+        tv = MBConv(cnf, 0.2, norm).eval()
+        layers = list(tv.block)
+        pairs = []
+        if a.expand_ratio != 1:
+            pairs += [(layers[0][0], blk._expand_conv), (layers[0][1], blk._bn0)]
+        pairs += [(layers[-3][0], blk._depthwise_conv), (layers[-3][1], blk._bn1), (layers[-2].fc1, blk._se_reduce),
+                  (layers[-2].fc2, blk._se_expand), (layers[-1][0], blk._project_conv), (layers[-1][1], blk._bn2)]
+        for dst, src in pairs:
+            dst.load_state_dict(src.state_dict(), strict=True)
+        x = torch.randn(2, a.input_filters, 9, 21)
+        with torch.no_grad():
+            want = blk(x)
+            pads = blk._depthwise_conv.pads
+            if a.stride == 1:                       # static-same == torchvision's symmetric padding: the stock forward
+                half = (a.kernel_size - 1) // 2
+                assert pads == (half, half, half, half)
+                got = tv(x)
+            else:                                   # asymmetric static-same pads in front of an unpadded depthwise conv
+                dw = layers[-3][0]
+                dw.padding = (0, 0)
+                y = layers[0](x) if a.expand_ratio != 1 else x
+                y = layers[-3](torch.nn.functional.pad(y, pads))
+                got = layers[-1](layers[-2](y))
+                assert not tv.use_res_connect
+        assert got.shape == want.shape
+        err = (got - want).abs().max().item() / want.abs().max().item()
+        assert err < 2e-6, (i, err)
