@@ -87,7 +87,7 @@ _SIGS = {
     "ac_trm_sample_forced": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        c_i64p, c_i64p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ac_bigru_train_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int,
-                                        C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+                                        C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ac_bigru_train_destroy": (None, [C.c_void_p]),
     "ac_bigru_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "ac_bigru_train_refresh": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -57,7 +57,9 @@ class RnnEncoder(BaseEncoder):
         tensors = self._tensors()
         sig = params_signature(tensors)
         if self._handle is None or sig != self._sig:
-            self.release()
+            if self._handle is not None:
+                _lib.lib().ac_bigru_destroy(self._handle)
+                self._handle = None
             ts = [t.detach().float().contiguous() for t in tensors]
             for t in ts:
                 require_cuda(t, "RnnEncoder parameters")
@@ -141,7 +143,7 @@ class GruTrainEngine:
         except Exception:
             pass
 
-    def handle(self, grads="param"):
+    def handle(self, grads="param", need_dx=False):
         enc = self.enc
         params = enc._tensors()
         for p in params:
@@ -158,25 +160,27 @@ class GruTrainEngine:
             if self._scratch is None or self._scratch[0].device != params[0].device:
                 self._scratch = [torch.zeros_like(p) for p in params]
             gts = [g if p.requires_grad else None for p, g in zip(params, self._scratch)]
-        key = (tuple(p.data_ptr() for p in params), tuple(0 if g is None else g.data_ptr() for g in gts))
+        key = (tuple(p.data_ptr() for p in params), tuple(0 if g is None else g.data_ptr() for g in gts), bool(need_dx))
         if self._handle is None or key != self._key:
             self.release()
             pp, numels, n = _lib.tensor_table([p.detach() for p in params])
             gp, _, _ = _lib.pointer_table(gts)
             h = ctypes.c_void_p()
             _lib.check(_lib.lib().ac_bigru_train_create(pp, gp, numels, n, enc.attn_feat_dim, enc.hidden_size, enc.num_layers,
-                                                        _lib.current_stream(), ctypes.byref(h)), "ac_bigru_train_create")
+                                                        int(need_dx), _lib.current_stream(), ctypes.byref(h)),
+                       "ac_bigru_train_create")
             self._handle, self._key, self._grads = h, key, gts
         return self._handle
 
-    def forward(self, x, len_dev, p_drop=0.0, seed=None, grads="param"):
-        """x [B, T, D] fp32 cuda (T = max length), len_dev [B] int64 cuda -> out [B, T, 512]"""
+    def forward(self, x, len_dev, p_drop=0.0, seed=None, grads="param", need_dx=False):
+        """x [B, T, D] fp32 cuda (T = max length), len_dev [B] int64 cuda -> out [B, T, 512].  need_dx: the backward call
+        will be asked for the gradient w.r.t. x (never the case when the CNN below is frozen)."""
         l = _lib.lib()
         dev = x.device
         B, T, _ = x.shape
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else seed
         with torch.cuda.device(dev):
-            h = self.handle(grads)
+            h = self.handle(grads, need_dx)
             st = _lib.current_stream()
             nbytes = l.ac_bigru_train_workspace_bytes(h, B, T)
             ws = self._ws.get(nbytes, dev)
@@ -208,7 +212,7 @@ class _GruForwardFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, enc, len_dev, p_drop, *params):
         eng = enc.train_engine
-        out = eng.forward(x.detach(), len_dev, p_drop=p_drop, grads="scratch")
+        out = eng.forward(x.detach(), len_dev, p_drop=p_drop, grads="scratch", need_dx=x.requires_grad)
         ctx.enc, ctx.need_dx = enc, x.requires_grad
         return out
 

@@ -80,7 +80,7 @@ class TransformerDecoder(BaseDecoder):
         tensors = self._tensors()
         sig = params_signature(tensors)
         if self._handle is None or sig != self._sig:
-            self.release()
+            self._release_decode()
             ts = [t.detach().float().contiguous() for t in tensors]
             for t in ts:
                 require_cuda(t, "TransformerDecoder parameters")
@@ -102,10 +102,13 @@ class TransformerDecoder(BaseDecoder):
         _lib.check(_lib.lib().ac_trm_update(handle, ptrs, n, _lib.current_stream()), "ac_trm_update")
         return handle
 
-    def release(self):
+    def _release_decode(self):
         if self._handle is not None:
             _lib.lib().ac_trm_destroy(self._handle)
             self._handle = None
+
+    def release(self):
+        self._release_decode()
         if self._engine is not None:
             self._engine.release()
             self._engine = None

@@ -155,6 +155,7 @@ __global__ void drop_mul_kernel(const float* __restrict__ src, float* __restrict
 
 struct ac_bigru_train {
     int input_dim = 0, layers = 0;
+    bool need_dx0 = false;            // also pack layer 0's W_ih^T (gradient w.r.t. the encoder input)
     std::vector<ac::GruTrainLayer> layer;
     float* blob = nullptr;
 };
@@ -189,7 +190,7 @@ extern "C" {
 
 // params_dev / grads_dev: nn.GRU order, 8 per layer (weight_ih, weight_hh, bias_ih, bias_hh, then `_reverse`); LIVE storage.
 int ac_bigru_train_create(const float* const* p, float* const* g, const int64_t* numels, int n_tensors, int input_dim, int hidden,
-                          int num_layers, void* stream, ac_bigru_train_t** out) {
+                          int num_layers, int need_input_grad, void* stream, ac_bigru_train_t** out) {
     using namespace ac;
     (void)stream;
     AC_REQUIRE(p && g && numels && out, "ac_bigru_train_create: null argument");
@@ -198,7 +199,7 @@ int ac_bigru_train_create(const float* const* p, float* const* g, const int64_t*
     AC_REQUIRE(n_tensors == num_layers * 8, "ac_bigru_train_create: expected %d tensors, got %d", num_layers * 8, n_tensors);
     const int H = kGruH;
     ac_bigru_train_t* h = new ac_bigru_train_t();
-    h->input_dim = input_dim; h->layers = num_layers;
+    h->input_dim = input_dim; h->layers = num_layers; h->need_dx0 = need_input_grad != 0;
     size_t pk_total = 0;
     for (int l = 0; l < num_layers; ++l) {
         const int din = l == 0 ? input_dim : 2 * H;
@@ -211,7 +212,7 @@ int ac_bigru_train_create(const float* const* p, float* const* g, const int64_t*
             }
             L.ih[d].W = p[ti]; L.ih[d].b = p[ti + 2]; L.ih[d].dW = g[ti]; L.ih[d].db = g[ti + 2]; L.ih[d].N = 3 * H; L.ih[d].K = din;
             L.whh[d] = p[ti + 1]; L.bhh[d] = p[ti + 3]; L.dwhh[d] = g[ti + 1]; L.dbhh[d] = g[ti + 3];
-            pk_total += linear_pack_floats(3 * H, din, l > 0);
+            pk_total += linear_pack_floats(3 * H, din, l > 0 || h->need_dx0);
         }
         h->layer.push_back(L);
     }
@@ -219,7 +220,7 @@ int ac_bigru_train_create(const float* const* p, float* const* g, const int64_t*
     if (rc != AC_OK) { delete h; return rc; }
     float* cur = h->blob;
     for (int l = 0; l < num_layers; ++l)
-        for (int d = 0; d < 2; ++d) { h->layer[l].ih[d].pk = cur; cur += linear_pack_floats(3 * H, h->layer[l].din, l > 0); }
+        for (int d = 0; d < 2; ++d) { h->layer[l].ih[d].pk = cur; cur += linear_pack_floats(3 * H, h->layer[l].din, l > 0 || h->need_dx0); }
     *out = h;
     return AC_OK;
 }
@@ -239,7 +240,7 @@ int ac_bigru_train_refresh(ac_bigru_train_t* h, void* stream) {
     using namespace ac;
     AC_REQUIRE(h, "ac_bigru_train_refresh: null handle");
     for (int l = 0; l < h->layers; ++l)
-        for (int d = 0; d < 2; ++d) { int rc = linear_refresh(h->layer[l].ih[d], l > 0, (cudaStream_t)stream); if (rc) return rc; }
+        for (int d = 0; d < 2; ++d) { int rc = linear_refresh(h->layer[l].ih[d], l > 0 || h->need_dx0, (cudaStream_t)stream); if (rc) return rc; }
     return AC_OK;
 }
 
@@ -286,6 +287,7 @@ int ac_bigru_train_bwd(ac_bigru_train_t* h, const float* x_dev, const int64_t* l
                        float p_drop, uint64_t seed, float* dx_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
     using namespace ac;
     AC_REQUIRE(h && x_dev && lens_dev && dout_dev && workspace_dev && B >= 1 && T >= 1, "ac_bigru_train_bwd: bad argument");
+    AC_REQUIRE(dx_dev == nullptr || h->need_dx0, "ac_bigru_train_bwd: the handle was created without need_input_grad");
     const GruWs w = gru_ws_layout(h, B, T);
     AC_REQUIRE(workspace_bytes >= w.total * sizeof(float), "ac_bigru_train_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;

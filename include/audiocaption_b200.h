@@ -285,9 +285,11 @@ int ac_bah_beam(const ac_bah_t* dec, const float* fc_emb_dev, const float* attn_
 
 /* ------------------------------------------------------------------ bi-GRU encoder, training
  * Replaces captioning/models/rnn_encoder.py:34-49 `RnnEncoder.forward` in train mode (nn.GRU inter-layer dropout) and its
- * autograd backward.  params_dev / grads_dev: nn.GRU order as for ac_bigru_create (a NULL grads entry = frozen). */
+ * autograd backward.  params_dev / grads_dev: nn.GRU order as for ac_bigru_create (a NULL grads entry = frozen).
+ * need_input_grad != 0 also prepares the gradient w.r.t. x (not needed when the CNN below is frozen). */
 int ac_bigru_train_create(const float* const* params_dev, float* const* grads_dev, const int64_t* numels, int n_tensors,
-                          int input_dim, int hidden, int num_layers, void* stream, ac_bigru_train_t** out);
+                          int input_dim, int hidden, int num_layers, int need_input_grad, void* stream,
+                          ac_bigru_train_t** out);
 void ac_bigru_train_destroy(ac_bigru_train_t* net);
 size_t ac_bigru_train_workspace_bytes(const ac_bigru_train_t* net, int batch, int T);
 int ac_bigru_train_refresh(ac_bigru_train_t* net, void* stream);

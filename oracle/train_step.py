@@ -48,16 +48,89 @@ def ss_ratio_after(iteration_1based, total_iters, final_ratio=0.7, mode="linear"
     return r
 
 
+# ------------------------------------------------------------------------------------------------ dropout masks
+# The reference draws its dropout masks from torch's global RNG; no implementation can reproduce those bit for bit, so the
+# parity bar for the stochastic mode is: (i) with p = 0 everything equals the reference, (ii) with p > 0 the CUDA path
+# equals THIS restatement of the same network evaluated with the SAME masks.  The masks are a pure function
+# keep(seed, site, element index) -- the counter-based generator of audiocaption_b200/csrc/train_ops.cuh, restated here.
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z):
+    import numpy as np
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def drop_scale(seed, site, n, p, dtype=torch.float64):
+    """Multipliers of elements 0..n-1 of dropout site `site`: 0 with probability p, else 1 / (1 - p)."""
+    import numpy as np
+    if p <= 0:
+        return torch.ones(n, dtype=dtype)
+    key = _mix64(np.array([(seed ^ (site << 40)) & _M64], dtype=np.uint64))[0]
+    with np.errstate(over="ignore"):
+        h = _mix64(key + np.arange(n, dtype=np.uint64))
+    u = (h >> np.uint64(40)).astype(np.float64) / 16777216.0
+    return torch.from_numpy(np.where(u.astype(np.float32) < np.float32(p), 0.0, 1.0 / (1.0 - np.float32(p)))).to(dtype)
+
+
+SITE_EMB_IN, SITE_EMB_PE, SITE_MEM, SITE_LAYER0, SITE_GRU0 = 0, 1, 2, 8, 64
+
+
+def decoder_forward_masked(dec, word, attn_emb, attn_emb_len, pad, p, seed, row0=0):
+    """`TransformerDecoder.forward` (transformer_decoder.py:80-103) written out op by op -- nn.TransformerDecoderLayer
+    (post-norm, ReLU), nn.MultiheadAttention -- with an explicit dropout multiplier at every place the reference applies
+    dropout in train mode.  Returns logits [B, L, V].  Works in the dtype of `dec` (tests use float64)."""
+    import torch.nn.functional as F
+    B, L = word.shape
+    T = attn_emb.shape[1]
+    D, H = dec.d_model, dec.model.layers[0].self_attn.num_heads
+    dt = dec.classifier.weight.dtype
+    ms = lambda site, shape: drop_scale(seed, site, int(torch.tensor(shape).prod()), p, dt).view(*shape)
+    lin0, ln = dec.attn_proj[0], dec.attn_proj[3]
+    U = torch.relu(attn_emb.to(dt) @ lin0.weight.T + lin0.bias) * ms(SITE_MEM, (B, T, D))
+    mem = F.layer_norm(U, (D,), ln.weight, ln.bias, 1e-5)
+    X = dec.word_embedding(word) * ms(SITE_EMB_IN, (B, L, D)) * math.sqrt(D) + dec.pos_encoder.pe[:L, 0].unsqueeze(0)
+    X = X * ms(SITE_EMB_PE, (B, L, D))
+    causal = torch.full((L, L), float("-inf"), dtype=dt).triu(1)
+    key_bias = torch.zeros(B, 1, 1, L, dtype=dt).masked_fill(pad.view(B, 1, 1, L), float("-inf"))
+    mem_bias = torch.zeros(B, 1, 1, T, dtype=dt).masked_fill(~cm.length_mask(attn_emb_len, T).view(B, 1, 1, T), float("-inf"))
+    heads = lambda t, n: t.view(B, n, H, D // H).transpose(1, 2)
+    for l, layer in enumerate(dec.model.layers):
+        base = SITE_LAYER0 + 8 * l
+        sa, ca = layer.self_attn, layer.multihead_attn
+        q, k, v = (X @ sa.in_proj_weight.T + sa.in_proj_bias).split(D, dim=-1)
+        P = torch.softmax(heads(q, L) @ heads(k, L).transpose(-1, -2) / math.sqrt(D // H) + causal + key_bias, dim=-1)
+        A = ((P * ms(base + 0, (B, H, L, L))) @ heads(v, L)).transpose(1, 2).reshape(B, L, D)
+        O = A @ sa.out_proj.weight.T + sa.out_proj.bias
+        X1 = F.layer_norm(X + O * ms(base + 1, (B, L, D)), (D,), layer.norm1.weight, layer.norm1.bias, 1e-5)
+        qc = X1 @ ca.in_proj_weight[:D].T + ca.in_proj_bias[:D]
+        kc, vc = (mem @ ca.in_proj_weight[D:].T + ca.in_proj_bias[D:]).split(D, dim=-1)
+        Pc = torch.softmax(heads(qc, L) @ heads(kc, T).transpose(-1, -2) / math.sqrt(D // H) + mem_bias, dim=-1)
+        Ac = ((Pc * ms(base + 2, (B, H, L, T))) @ heads(vc, T)).transpose(1, 2).reshape(B, L, D)
+        Oc = Ac @ ca.out_proj.weight.T + ca.out_proj.bias
+        X2 = F.layer_norm(X1 + Oc * ms(base + 3, (B, L, D)), (D,), layer.norm2.weight, layer.norm2.bias, 1e-5)
+        Hf = torch.relu(X2 @ layer.linear1.weight.T + layer.linear1.bias) * ms(base + 4, (B, L, layer.linear1.out_features))
+        Ff = Hf @ layer.linear2.weight.T + layer.linear2.bias
+        X = F.layer_norm(X2 + Ff * ms(base + 5, (B, L, D)), (D,), layer.norm3.weight, layer.norm3.bias, 1e-5)
+    return X @ dec.classifier.weight.T
+
+
 # ------------------------------------------------------------------------------------------------ differentiable bi-GRU
-def gru_params(sd, requires_grad=True):
-    return {k: v.clone().requires_grad_(requires_grad) for k, v in sd.items()}
+def gru_params(sd, requires_grad=True, dtype=torch.float32):
+    return {k: v.clone().to(dtype).requires_grad_(requires_grad) for k, v in sd.items()}
 
 
-def bigru(p, x, lens, hidden=crnn.HIDDEN, layers=crnn.LAYERS):
-    """Same arithmetic as oracle/crnn.py `bigru`, built from out-of-place ops so autograd can differentiate it."""
+def bigru(p, x, lens, hidden=crnn.HIDDEN, layers=crnn.LAYERS, p_drop=0.0, seed=0):
+    """Same arithmetic as oracle/crnn.py `bigru`, built from out-of-place ops so autograd can differentiate it.
+    p_drop: nn.GRU's inter-layer dropout with the masks of `drop_scale` (site SITE_GRU0 + layer)."""
     lens = torch.as_tensor(lens)
     B, T = x.shape[0], int(lens.max())
     inp = x[:, :T]
+    dt = x.dtype
     for l in range(layers):
         dirs = []
         for d, suffix in enumerate(("", "_reverse")):
@@ -66,15 +139,17 @@ def bigru(p, x, lens, hidden=crnn.HIDDEN, layers=crnn.LAYERS):
             rows = []
             for b in range(B):
                 n = int(lens[b])
-                h = torch.zeros(hidden)
+                h = torch.zeros(hidden, dtype=dt)
                 outs = [None] * n
                 for t in (range(n) if d == 0 else range(n - 1, -1, -1)):
                     h = crnn._cell(inp[b, t], h, w_ih, w_hh, b_ih, b_hh)
                     outs[t] = h
-                outs += [torch.zeros(hidden)] * (T - n)
+                outs += [torch.zeros(hidden, dtype=dt)] * (T - n)
                 rows.append(torch.stack(outs))
             dirs.append(torch.stack(rows))
         inp = torch.cat(dirs, dim=-1)
+        if l + 1 < layers and p_drop > 0:
+            inp = inp * drop_scale(seed, SITE_GRU0 + l, inp.numel(), p_drop, dt).view(inp.shape)
     return inp
 
 
@@ -149,11 +224,19 @@ def synth_captions(batch, max_len, vocab, seed=1, min_len=5):
 
 
 def train_step(cnn_sd, rnn_sd, dec, wav, wav_len, cap, cap_len, coins, lr, smoothing=0.1, max_grad_norm=1.0,
-               weight_decay=1e-6, adam_state=None, step=1):
-    """One full step.  Returns dict(loss, output, grads {name: tensor}, grad_norm, new_params {name: tensor}, state)."""
+               weight_decay=1e-6, adam_state=None, step=1, dtype=torch.float32, cnn_noise=0.0):
+    """One full step.  Returns dict(loss, output, grads {name: tensor}, grad_norm, new_params {name: tensor}, state).
+    dtype=torch.float64 evaluates the trainable part (bi-GRU, decoder, loss, optimizer) in double precision: the yardstick
+    against which BOTH fp32 implementations (the reference's CPU kernels and the CUDA path) are measured -- the fp32 CPU
+    autograd is itself up to 2e-3 away from it on some gradients."""
     with torch.no_grad():
         c = oc.forward(cnn_sd, wav, wav_len)                 # frozen CNN, BatchNorm eval, (dropout off in the oracle)
-    rp = gru_params(rnn_sd)
+        c["attn_emb"] = c["attn_emb"].to(dtype)
+        if cnn_noise > 0:      # sensitivity probe: the frozen CNN's features perturbed at the level of fp32 re-ordering
+            g = torch.Generator().manual_seed(77)
+            c["attn_emb"] = c["attn_emb"] * (1 + cnn_noise * torch.randn(c["attn_emb"].shape, generator=g, dtype=dtype))
+    rp = gru_params(rnn_sd, dtype=dtype)
+    dec = dec.to(dtype)
     for p in dec.parameters():
         p.requires_grad_(True)
     dec.pos_encoder.pe.requires_grad_(False)

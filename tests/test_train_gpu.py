@@ -84,7 +84,7 @@ def test_clip_adam_matches_oracle_including_nan_skip():
         rp_last = p.cpu().clone()
         assert step.item() == k
         assert abs(norm.item() - total.item()) < 1e-4 * total.item()
-        assert (p.cpu() - rp).abs().max() < 2e-7, it
+        assert (p.cpu() - rp).abs().max() < 1e-6, it          # 1-2 ulp of |p| ~ 4
         assert (m.cpu() - rm).abs().max() < 1e-6 * max(1.0, rm.abs().max().item())
         assert (v.cpu() - rv).abs().max() < 1e-6 * max(1.0, rv.abs().max().item())
 
@@ -130,7 +130,9 @@ def test_decoder_forward_input_dict_matches_oracle(B, T, L, vocab):
 
 @pytest.mark.parametrize("B,T,L,vocab,tied", [(4, 9, 8, 4981, False), (3, 31, 21, 4368, False), (2, 5, 6, 520, True)])
 def test_decoder_gradients_match_oracle_autograd(B, T, L, vocab, tied):
-    """d(sum(logit * R)) w.r.t. every decoder parameter and the audio memory: CUDA backward vs torch autograd on the oracle."""
+    """d(sum(logit * R)) w.r.t. every decoder parameter and the audio memory: CUDA backward vs torch autograd on the oracle
+    evaluated in float64 (the fp32 CPU autograd of the same oracle is itself 1e-3 .. 2e-2 away from float64 on these
+    gradients -- scripts/train_debug.py -- so it cannot serve as the yardstick): <= 3e-4 of each tensor's scale."""
     from audiocaption_b200.captioning.models.transformer_decoder import TransformerDecoder
     if tied:
         orc = cm.TransformerDecoder(emb_dim=256, vocab_size=vocab, attn_emb_dim=512, tie_weights=True)
@@ -152,23 +154,24 @@ def test_decoder_gradients_match_oracle_autograd(B, T, L, vocab, tied):
     mem, lens, word = _decoder_inputs(B, T, L, vocab, seed=7 * B + L)
     pad = word == cm.PAD
     R = torch.randn(B, L, vocab, generator=torch.Generator().manual_seed(1)) * (~pad).unsqueeze(-1)
+    orc = orc.double()
     for p in orc.parameters():
         p.requires_grad_(True)
     orc.pos_encoder.pe.requires_grad_(False)
     orc.zero_grad()
-    mem_ref = mem.clone().requires_grad_(True)
-    (orc(word, mem_ref, lens, pad)["logit"] * R).sum().backward()
+    mem_ref = mem.double().requires_grad_(True)
+    (orc(word, mem_ref, lens, pad)["logit"] * R.double()).sum().backward()
     mem_dev = mem.to(DEV).requires_grad_(True)
     out = dec({"word": word, "attn_emb": mem_dev, "attn_emb_len": lens, "cap_padding_mask": pad})
     (out["logit"] * R.to(DEV)).sum().backward()
-    assert _relerr(mem_dev.grad, mem_ref.grad) < 2e-4
+    assert _relerr(mem_dev.grad, mem_ref.grad) < 3e-4
     ref = dict(orc.named_parameters())
     for name, p in dec.named_parameters():
         if name == "pos_encoder.pe":
             assert p.grad is None
             continue
         assert p.grad is not None, name
-        assert _relerr(p.grad, ref[name].grad) < 2e-4, name
+        assert _relerr(p.grad, ref[name].grad) < 3e-4, name
 
 
 # ------------------------------------------------------------------ bi-GRU training forward / backward (row A5 + A16)
@@ -184,19 +187,19 @@ def test_bigru_train_forward_backward_matches_oracle(B, T, lens):
     x = torch.randn(B, T, 2048, generator=g) * 0.3
     R = torch.randn(B, T, 512, generator=g)
     lens_t = torch.tensor(lens)
-    rp = ts.gru_params(sd)
-    x_ref = x.clone().requires_grad_(True)
+    rp = ts.gru_params(sd, dtype=torch.float64)
+    x_ref = x.double().requires_grad_(True)
     want = ts.bigru(rp, x_ref, lens_t)
-    (want * R).sum().backward()
+    (want * R.double()).sum().backward()
     x_dev = x.to(DEV).requires_grad_(True)
     out = enc({"attn": x_dev, "attn_len": lens_t})
     assert (out["attn_emb"].cpu() - want.detach()).abs().max() < 5e-5
     (out["attn_emb"] * R.to(DEV)).sum().backward()
-    assert _relerr(x_dev.grad, x_ref.grad) < 2e-4
+    assert _relerr(x_dev.grad, x_ref.grad) < 3e-4
     for name, p in enc.named_parameters():
-        assert _relerr(p.grad, rp[name].grad) < 2e-4, name
+        assert _relerr(p.grad, rp[name].grad) < 3e-4, name
     # fc_emb = mean over the valid frames, differentiable too
-    assert (out["fc_emb"].cpu().detach() - oc.mean_with_lens(want.detach(), lens_t)).abs().max() < 5e-5
+    assert (out["fc_emb"].cpu().detach() - oc.mean_with_lens(want.detach().float(), lens_t)).abs().max() < 5e-5
 
 
 # ------------------------------------------------------------------ the whole training step (rows A9, A15, A16)
@@ -282,7 +285,8 @@ def test_train_step_matches_oracle_for_every_coin_pattern(pattern):
     if pattern != "seq_forward":
         step.ss_ratio = 0.5
     dec = crnn.build_decoder(6, vocab_size=vocab)
-    o = ts.train_step(oc.build_state_dict(3), crnn.build_gru_state_dict(4), dec, wav, lens, cap, cap_len, coins, lr)
+    o = ts.train_step(oc.build_state_dict(3), crnn.build_gru_state_dict(4), dec, wav, lens, cap, cap_len, coins, lr,
+                      dtype=torch.float64)            # the yardstick (see test_decoder_gradients_match_oracle_autograd)
     res = step.step({"wav": wav, "wav_len": lens, "cap": cap, "cap_len": cap_len.numpy()}, coins=coins)
     torch.cuda.synchronize()
     assert abs(res["lr"] - lr) < 1e-12
@@ -296,14 +300,22 @@ def test_train_step_matches_oracle_for_every_coin_pattern(pattern):
         assert (step.last_output["seq"].cpu()[stable] == o["output"]["seq"][stable]).all()
         if not stable.all():
             return                      # a flipped sample changes the rest of that row; gradients are compared on stable batches
-    assert abs(step.grad_norm.item() - float(o["grad_norm"])) < 2e-3 * float(o["grad_norm"])
+    # Conditioning: the device's Cnn14 features differ from the CPU's by ~1e-4 relative (3xTF32 convolutions, summation
+    # order).  Where a batch parks many FFN pre-activations on the ReLU kink (degenerate sampled rows: the same token at
+    # every step) such a difference moves some gradients by percents in ANY implementation; the oracle's own response to a
+    # 1e-4 perturbation of the features measures that, and the tolerance is 5e-4 or 3x that response, whichever is larger.
+    dec2 = crnn.build_decoder(6, vocab_size=vocab)
+    o2 = ts.train_step(oc.build_state_dict(3), crnn.build_gru_state_dict(4), dec2, wav, lens, cap, cap_len, coins, lr,
+                       dtype=torch.float64, cnn_noise=1e-4)
+    sens = {k: _relerr(o2["grads"][k], o["grads"][k]) for k in o["grads"]}
+    assert abs(step.grad_norm.item() - float(o["grad_norm"])) < max(5e-4, 3 * max(sens.values())) * float(o["grad_norm"])
     for k, p in m.named_parameters():
         if not p.requires_grad:
             continue
-        assert _relerr(p.grad, o["grads"][k]) < 2e-3, k
+        assert _relerr(p.grad, o["grads"][k]) < max(5e-4, 3 * sens[k]), (k, sens[k])
         big = o["grads"][k].abs() > 1e-4
         if big.any():
-            assert (p.detach().cpu() - o["new_params"][k])[big].abs().max() < 0.03 * lr, k
+            assert (p.detach().cpu().double() - o["new_params"][k])[big].abs().max() < 0.03 * lr, k
 
 
 def test_module_api_training_loop_matches_fused_step():
@@ -347,69 +359,72 @@ def test_module_api_training_loop_matches_fused_step():
         assert (p2[k].detach() - dict(m.named_parameters())[k].detach()).abs().max() < 2e-6, k
 
 
-def test_dropout_masks_are_seeded_and_agree_between_forward_and_backward():
-    """Train mode with the YAML's dropout probabilities: the same torch seed reproduces the step bit for bit, another seed
-    does not, and the analytic gradient matches a central finite difference of the (mask-frozen) loss along a random
-    direction -- which only holds if the backward pass regenerates exactly the forward pass's masks."""
-    from audiocaption_b200.captioning.losses.loss import ls_ce_fwd_bwd
+def test_train_mode_dropout_matches_the_oracle_evaluated_with_the_same_masks():
+    """Train mode with the YAML's dropout probabilities (decoder 0.2 at all 15 places the reference applies it, GRU 0.5
+    between layers).  The masks are a pure function of (seed, site, element index); the oracle restates the generator and
+    evaluates the same network in float64 with the SAME masks: logits / GRU output and every gradient must agree, which
+    only holds if each kernel -- forward and backward -- regenerates exactly its site's mask.  Also: same seed ->
+    bit-identical, other seed -> different."""
     vocab = 520
     from audiocaption_b200.captioning.models.rnn_encoder import RnnEncoder
-    dec, _ = _decoder_pair(vocab)
+    dec, orc = _decoder_pair(vocab)
     dec.train()
+    B, T, L = 4, 7, 8
+    mem, lens, word = _decoder_inputs(B, T, L, vocab, seed=17)
+    pad = word == cm.PAD
+    len_dev = lens.to(DEV)
+    R = torch.randn(B, L, vocab, generator=torch.Generator().manual_seed(1)) * (~pad).unsqueeze(-1)
+    eng = dec.train_engine
+    seed = 1234567
+    out = eng.forward(mem.to(DEV), len_dev, word.to(DEV), key_pad=pad.to(DEV), p_drop=0.2, seed=seed, grads="scratch")
+    again = eng.forward(mem.to(DEV), len_dev, word.to(DEV), key_pad=pad.to(DEV), p_drop=0.2, seed=seed, grads="scratch")
+    other = eng.forward(mem.to(DEV), len_dev, word.to(DEV), key_pad=pad.to(DEV), p_drop=0.2, seed=seed + 1, grads="scratch")
+    assert (out["logit"] == again["logit"]).all() and not (out["logit"] == other["logit"]).all()
+    out = eng.forward(mem.to(DEV), len_dev, word.to(DEV), key_pad=pad.to(DEV), p_drop=0.2, seed=seed, grads="scratch")
+    dl = torch.zeros_like(out["logit_padded"])
+    dl[:, :, :vocab] = R.to(DEV)
+    dmem = eng.backward(dl)
+    orc = orc.double()
+    for p in orc.parameters():
+        p.requires_grad_(True)
+    orc.pos_encoder.pe.requires_grad_(False)
+    mem_ref = mem.double().requires_grad_(True)
+    want = ts.decoder_forward_masked(orc, word, mem_ref, lens, pad, 0.2, seed)
+    assert (want.detach() - orc(word, mem.double(), lens, pad)["logit"].detach()).abs().max() > 0.1     # dropout is really on
+    valid = ~pad
+    assert _relerr(out["logit"].cpu()[valid], want.detach()[valid]) < 1e-4
+    (want * R.double()).sum().backward()
+    assert _relerr(dmem, mem_ref.grad) < 3e-4
+    ref = dict(orc.named_parameters())
+    names = [n for n, _ in dec.named_parameters()]
+    for p, g in zip(dec._tensors(), eng._grads):
+        name = next(n for n, q in dec.named_parameters() if q is p)
+        if g is None:
+            continue
+        assert _relerr(g, ref[name].grad) < 3e-4, name
+    # ---- bi-GRU, inter-layer dropout 0.5
+    sd = crnn.build_gru_state_dict(4)
     rnn = RnnEncoder(spec_dim=-1, fc_feat_dim=2048, attn_feat_dim=2048, bidirectional=True, hidden_size=256, dropout=0.5,
                      num_layers=3)
-    rnn.load_state_dict(crnn.build_gru_state_dict(4), strict=True)
+    rnn.load_state_dict(sd, strict=True)
     rnn = rnn.to(DEV).train()
     g = torch.Generator().manual_seed(2)
-    x = (torch.randn(4, 7, 2048, generator=g) * 0.3).to(DEV)
-    lens = torch.tensor([7, 5, 7, 2])
-    len_dev = lens.to(DEV)
-    cap, cap_len = ts.synth_captions(4, 9, vocab, seed=3)
-    cap = cap.to(DEV)
-    tl = (cap_len - 1).to(DEV)
-    coins = [True, False, True, True, False, True, True, True][:cap.size(1) - 1]
-
-    def run(seed, grads, coins=coins):
-        mem = rnn.train_engine.forward(x, len_dev, p_drop=0.5, seed=seed, grads=grads)
-        out = dec.train_engine.forward(mem, len_dev, cap[:, :-1].contiguous(), coins=coins, p_drop=0.2, seed=seed + 1, grads=grads)
-        loss, dl = ls_ce_fwd_bwd(out["logit_padded"][:, :, :vocab], cap[:, 1:], tl, 0.1)
-        return loss, dl, out
-
-    loss1, dl, out1 = run(11, "param")
-    loss1b, _, out1b = run(11, "param")
-    assert loss1b.item() == loss1.item() and (out1b["logit"] == out1["logit"]).all()        # seeded: bit-identical
-    loss2, _, _ = run(12, "param")
-    assert loss2.item() != loss1.item()
-    # gradients of the teacher-forced loss (no discrete sampling in the way of the finite differences below)
-    _, dl, _ = run(11, "param", None)
-    dmem = dec.train_engine.backward(dl)
-    rnn.train_engine.backward(dmem)
-    torch.cuda.synchronize()
-    g_dec = {k: p.grad.clone() for k, p in dec.named_parameters() if p.grad is not None}
-    g_rnn = {k: p.grad.clone() for k, p in rnn.named_parameters()}
-    # about 20 % of the decoder's hidden activations and 50 % of the GRU's inter-layer activations are dropped:
-    # the train-mode loss differs from the dropout-free one
-    mem0 = rnn.train_engine.forward(x, len_dev, p_drop=0.0, seed=11, grads="param")
-    out0 = dec.train_engine.forward(mem0, len_dev, cap[:, :-1].contiguous(), coins=coins, p_drop=0.0, seed=12, grads="param")
-    assert (out0["logit"] - out1["logit"]).abs().max() > 1e-2
-    # finite differences along a random direction (sampled rows are discrete: keep the same coins, compare on the loss)
-    torch.manual_seed(0)
-    for params, grads in ((dict(dec.named_parameters()), g_dec), (dict(rnn.named_parameters()), g_rnn)):
-        names = [k for k in grads if grads[k].abs().max() > 0][:6]
-        dirs = {k: torch.randn_like(params[k]) for k in names}
-        analytic = sum((grads[k] * dirs[k]).sum().item() for k in names)
-        eps = 2e-3
-        vals = []
-        for sgn in (1.0, -1.0):
-            with torch.no_grad():
-                for k in names:
-                    params[k].add_(dirs[k], alpha=sgn * eps)
-            vals.append(run(11, "param", None)[0].item())
-            with torch.no_grad():
-                for k in names:
-                    params[k].add_(dirs[k], alpha=-sgn * eps)
-        numeric = (vals[0] - vals[1]) / (2 * eps)
-        assert abs(numeric - analytic) < 0.05 * abs(analytic) + 2e-3, (numeric, analytic)
+    x = torch.randn(4, 7, 2048, generator=g) * 0.3
+    Rg = torch.randn(4, 7, 512, generator=g)
+    glens = torch.tensor([7, 5, 7, 2])
+    ge = rnn.train_engine
+    y = ge.forward(x.to(DEV), glens.to(DEV), p_drop=0.5, seed=seed, grads="scratch", need_dx=True)
+    dx = ge.backward(Rg.to(DEV), need_dx=True)
+    rp = ts.gru_params(sd, dtype=torch.float64)
+    x_ref = x.double().requires_grad_(True)
+    want = ts.bigru(rp, x_ref, glens, p_drop=0.5, seed=seed)
+    assert (want.detach() - ts.bigru(rp, x.double(), glens).detach()).abs().max() > 0.05
+    assert (y.cpu() - want.detach()).abs().max() < 5e-5
+    (want * Rg.double()).sum().backward()
+    assert _relerr(dx, x_ref.grad) < 3e-4
+    for p, gr in zip(rnn._tensors(), ge._grads):
+        name = next(n for n, q in rnn.named_parameters() if q is p)
+        assert _relerr(gr, rp[name].grad) < 3e-4, name
 
 
 def test_cnn14_train_mode_dropout():
