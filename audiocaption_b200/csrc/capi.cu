@@ -22,16 +22,17 @@ struct TimedLaunch { std::string name; cudaEvent_t e0, e1; };
 static std::vector<TimedLaunch> g_timed;
 static std::mutex g_timed_mu;
 
-void timing_begin(const char* name, cudaStream_t st) {
+int timing_begin(const char* name, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_timed_mu);
     TimedLaunch t; t.name = name;
     cudaEventCreate(&t.e0); cudaEventCreate(&t.e1);
     cudaEventRecord(t.e0, st);
     g_timed.push_back(t);
+    return (int)g_timed.size() - 1;
 }
-void timing_end(cudaStream_t st) {
+void timing_end(int index, cudaStream_t st) {     // timers nest (a "span_*" wrapper around per-kernel timers): end by index
     std::lock_guard<std::mutex> lk(g_timed_mu);
-    cudaEventRecord(g_timed.back().e1, st);
+    if (index >= 0 && index < (int)g_timed.size()) cudaEventRecord(g_timed[index].e1, st);
 }
 }  // namespace ac
 
@@ -52,6 +53,8 @@ int ac_timing_report(char* buf, int buf_len) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
             auto& a = agg[t.name]; a.first++; a.second += ms;
+        } else {
+            cudaGetLastError();      // an event that was never recorded: do not leave the error for the next launch check
         }
         cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
     }

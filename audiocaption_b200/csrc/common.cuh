@@ -32,13 +32,13 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 // Optional per-kernel CUDA-event timing (bench.py's roofline leg): when enabled, a pair of events
 // brackets every launch on its own stream; ac_timing_report() resolves them after a sync.
-void timing_begin(const char* name, cudaStream_t st);
-void timing_end(cudaStream_t st);
+int timing_begin(const char* name, cudaStream_t st);
+void timing_end(int index, cudaStream_t st);
 extern bool g_timing;
 struct LaunchTimer {
-    cudaStream_t st; bool on;
-    LaunchTimer(const char* name, cudaStream_t s) : st(s), on(g_timing) { if (on) timing_begin(name, st); }
-    ~LaunchTimer() { if (on) timing_end(st); }
+    cudaStream_t st; bool on; int index = -1;
+    LaunchTimer(const char* name, cudaStream_t s) : st(s), on(g_timing) { if (on) index = timing_begin(name, st); }
+    ~LaunchTimer() { if (on) timing_end(index, st); }
 };
 #define AC_TIMED(name, st) ::ac::LaunchTimer _ac_timer_##__LINE__(name, st)
 

@@ -230,7 +230,7 @@ int ac_trm_train_memory_fwd(ac_trm_train_t* h, const float* attn_emb_dev, int B,
     float* ws = (float*)workspace_dev;
     const int Mm = B * T, D = h->D;
     const Dropout dp{p_drop, seed};
-    AC_TIMED("trm_train_memory_fwd", st);
+    AC_TIMED("span_trm_train_memory_fwd", st);      // wrapper span: contains the per-kernel timers below
     int rc = linear_fwd(h->ap0, attn_emb_dev, Mm, ws + w.U, D, ACT_RELU, nullptr, st); if (rc) return rc;
     rc = dropout_apply(ws + w.U, 0, (int64_t)Mm * D, dp, SITE_MEM, st); if (rc) return rc;
     rc = add_ln_fwd(nullptr, ws + w.U, h->ap_lnw, h->ap_lnb, 0, Mm, D, Dropout{}, 0, nullptr, ws + w.m_mean, ws + w.m_rstd, ws + w.Pm, st);
@@ -258,7 +258,7 @@ int ac_trm_train_seq_fwd(ac_trm_train_t* h, const int64_t* word_dev, const unsig
     float* ws = (float*)workspace_dev;
     const int D = h->D, FF = h->FF, r0 = seq0 * L, M = n_seq * L;
     const Dropout dp{p_drop, seed};
-    AC_TIMED("trm_train_seq_fwd", st);
+    AC_TIMED("span_trm_train_seq_fwd", st);      // wrapper span: contains the per-kernel timers below
     int rc = embed_fwd(h->emb, h->pe, word_dev, r0, M, L, D, h->V, sqrtf((float)D), dp, ws + w.X0, st); if (rc) return rc;
     const float* X = ws + w.X0;
     for (int l = 0; l < h->NL; ++l) {
@@ -312,7 +312,7 @@ int ac_trm_train_logits(ac_trm_train_t* h, const int* rows_dev, int n_rows, int 
     float* ws = (float*)workspace_dev;
     const float* Xf = ws + w.layer[h->NL - 1].X3;
     const float* X = Xf;
-    AC_TIMED("trm_train_logits", st);
+    AC_TIMED("span_trm_train_logits", st);      // wrapper span: contains the per-kernel timers below
     int rc = AC_OK;
     if (rows_dev != nullptr || keep) {
         float* dst = keep ? ws + w.Xsel : ws + w.dA;
@@ -346,7 +346,7 @@ int ac_trm_train_bwd(ac_trm_train_t* h, const float* dlogits_dev, const int* row
     const int D = h->D, FF = h->FF, M = n_seq * L, Mm = B * T;
     const Dropout dp{p_drop, seed};
     float* lin = ws + w.lin; float* lns = ws + w.ln;
-    AC_TIMED("trm_train_bwd", st);
+    AC_TIMED("span_trm_train_bwd", st);      // wrapper span: contains the per-kernel timers below
     int rc = AC_OK;
     // ---- classifier: dXsel = dlogits W, dW = dlogits^T Xsel
     float* dXf = ws + w.dA;              // gradient of the current layer's output [M, D]

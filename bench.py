@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: EffB2-Transformer batched greedy inference (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload effb2_trm|train]
 
 A "step" is one pass of the hot path (log-mel -> EfficientNet-B2 -> KV-cached greedy decode,
 max_length 20) over one batch of 64 synthetic 10 s clips (0.1*randn, the model's 16 kHz input =
@@ -15,7 +15,12 @@ back to the host; roofline = the dominant kernel's algorithmic bytes/flops over 
 time, against MEASURED_PEAKS.json; cpu_baseline = the CPU oracle port on a bounded sample.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port: the reference is pure
-Python/PyTorch and /root/reference does not travel to the GPU box) on all host cores.
+Python/PyTorch and /root/reference does not travel to the GPU box) on all host cores, on the SAME 64 clips per step.
+
+The second half of BASELINE.json's metric -- "tokens/sec Cnn14-Trm train @1/2/4/8 B200" (configs[2..3]) -- is measured
+by `--workload train` (one step = one optimizer step of the fused TrainStep on 32 synthetic 10 s @ 32 kHz clips per
+GPU, captions of 8..22 tokens, one NCCL all-reduce of the flat gradient when N > 1); the default run attaches the same
+measurement to its JSON line under "train", so the driver's bench and scaling runs carry both halves of the metric.
 """
 import argparse
 import json
@@ -34,6 +39,10 @@ BATCH = 64
 N_SAMPLES = 160000
 MAX_LEN = 20
 METRIC = "clips/sec (10s clips) EffB2-Trm greedy inference"
+TRAIN_METRIC = "tokens/sec Cnn14Rnn-Trm training step"
+TRAIN_WORKLOAD = ("Cnn14_Rnn-Transformer training step (clotho_v2/waveform/cnn14rnn_trm.yaml), random-init, synthetic "
+                  "batch=32x10s @ 32 kHz per GPU, captions 8..22 tokens (configs[2]; configs[3] = the same on 8 GPUs)")
+TRAIN_BATCH, TRAIN_SAMPLES, TRAIN_VOCAB = 32, 320000, 4368
 WORKLOAD = "EffB2-Transformer batched greedy inference, batch=64x10s synthetic clips per GPU (configs[1])"
 
 
@@ -117,8 +126,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "train":
+        return run_reference_train(args)
     orc, _ = build_models(None)
-    n = 8
+    n = BATCH
     times = []
     for i in range(args.warmup + args.steps):
         v, cores, dt = cpu_sample(orc, n)
@@ -126,7 +137,7 @@ def run_reference(args):
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
     value = n / (ms / 1000.0)
-    sample = f"{n} of the {BATCH} clips per step (full 10 s clips, greedy, max_length {MAX_LEN})"
+    sample = f"all {n} clips of a step (full 10 s clips, greedy, max_length {MAX_LEN})"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -134,6 +145,164 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ====================================================================================================== training workload
+def build_train_model(device):
+    """TransformerModel(CrnnEncoder(Cnn14Encoder, RnnEncoder), TransformerDecoder) as the Clotho YAML builds it, seeded
+    random-init weights (oracle builders: BatchNorm statistics randomised so that folding bugs cannot hide)."""
+    from oracle import cnn14 as oc, crnn
+    from audiocaption_b200.captioning.models.cnn_encoder import Cnn14Encoder
+    from audiocaption_b200.captioning.models.crnn_trm_encoder import CrnnEncoder
+    from audiocaption_b200.captioning.models.rnn_encoder import RnnEncoder
+    from audiocaption_b200.captioning.models.transformer_decoder import TransformerDecoder
+    from audiocaption_b200.captioning.models.transformer_model import TransformerModel
+    enc = CrnnEncoder(Cnn14Encoder(sample_rate=32000),
+                      RnnEncoder(spec_dim=-1, fc_feat_dim=2048, attn_feat_dim=2048, bidirectional=True, hidden_size=256,
+                                 dropout=0.5, num_layers=3), freeze_cnn=True, freeze_cnn_bn=True)
+    dec = TransformerDecoder(emb_dim=256, vocab_size=TRAIN_VOCAB, fc_emb_dim=512, attn_emb_dim=512, nlayers=2, dropout=0.2)
+    m = TransformerModel(enc, dec)
+    m.load_state_dict(crnn.model_state_dict(oc.build_state_dict(3), crnn.build_gru_state_dict(4),
+                                            crnn.build_decoder(6, vocab_size=TRAIN_VOCAB)), strict=True)
+    return m.to(device)
+
+
+def train_batches(rank, n_rot):
+    """wav = 0.1 * randn(B, 320000) (full length), captions seed 1 with cap_len ~ U{8..22}, tokens U{4..V-1},
+    pad 0, sorted by length."""
+    from oracle import caption_model as cm, train_step as ts
+    out = []
+    for i in range(n_rot):
+        wav, lens = cm.synth_wav(TRAIN_BATCH, TRAIN_SAMPLES, seed=1000 * rank + i, sample_rate=32000)
+        cap, cap_len = ts.synth_captions(TRAIN_BATCH, 22, TRAIN_VOCAB, seed=1 + 17 * rank + i, min_len=8)
+        out.append({"wav": wav.pin_memory(), "wav_len": lens, "cap": cap.pin_memory(), "cap_len": cap_len.numpy()})
+    return out
+
+
+def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
+    """K optimizer steps; returns the "train" record (rank 0) or None."""
+    import random
+    import torch
+    from audiocaption_b200 import _lib
+    from audiocaption_b200.train_step import TrainStep
+    model = build_train_model(dev)
+    step = TrainStep(model, total_iters=10 ** 9, lr=5e-4, warmup_iters=3000)     # ss_ratio and lr effectively constant
+    n_rot = 4                                                                      # 4 x 41 MB of waveforms > 126 MB L2
+    host = train_batches(rank, n_rot)
+    devb = [dict(b, wav=b["wav"].to(dev), cap=b["cap"].to(dev)) for b in host]
+    torch.manual_seed(1 + rank)
+    random.seed(1)                       # the same coin sequence on every rank keeps the step shapes in lock-step
+    step.ss_ratio = ss_ratio
+    tokens_per_step = [int((b["cap_len"] - 1).sum()) for b in host]
+    keep = {}
+
+    def step_resident(i):
+        keep["loss"] = step.step(devb[i % n_rot])["loss"]
+
+    def step_e2e(i):
+        keep["loss_host"] = step.step(host[i % n_rot])["loss"].item()          # pinned H2D in, loss D2H out, every step
+
+    ms_step, launches = timed(step_resident, steps, warmup)
+    ms_e2e, _ = timed(step_e2e, steps, 3)
+    # share of the sampled (two-row) path in real training: the YAML's ratio goes 1.0 -> 0.7, mean 0.85
+    step.ss_ratio = 0.85
+    ms_ss085, _ = timed(step_resident, steps, 3)
+    step.ss_ratio = ss_ratio
+    rec = None
+    if rank == 0:
+        lib.ac_timing_enable(1)
+        n_prof = min(steps, 5)
+        for i in range(n_prof):
+            step_resident(i)
+        rep = _lib.timing_report()
+        lib.ac_timing_enable(0)
+        spans = {k: round(ms / n_prof, 4) for k, (n, ms) in rep.items() if k.startswith("span_")}
+        rep = {k: v for k, v in rep.items() if not k.startswith("span_")}      # spans contain the per-kernel timers
+        tot = sum(ms for _, ms in rep.values())
+        shares = {k: round(ms / tot, 4) for k, (n, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1])}
+        per_kernel = {k: {"launches_per_step": n / n_prof, "ms_per_step": round(ms / n_prof, 4)} for k, (n, ms) in rep.items()}
+        conv_ms = rep.get("conv3x3_tc", (0, 0.0))[1] / n_prof
+        bf16_burst, bf16_sust = measured_tensor_peaks()
+        flop = 40.07e9 * TRAIN_BATCH                       # SURVEY.md 8(d): Cnn14 = 40.07 GFLOP per clip (2 x MAC)
+        achieved = flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        tok = sum(tokens_per_step) / len(tokens_per_step)
+        rec = {
+            "metric": TRAIN_METRIC, "value": world * tok / (ms_step / 1000.0), "unit": "tokens/s", "n_gpus": world,
+            "ms_per_step": ms_step, "steps": steps, "clips_per_s": world * TRAIN_BATCH / (ms_step / 1000.0),
+            "tokens_per_step_per_gpu": tok, "dtype": "f32 (3xTF32 tensor-core GEMMs, fp32 master weights and optimizer)",
+            "scaling": "weak", "data": "synthetic",
+            "config": {"workload": TRAIN_WORKLOAD, "clips_per_gpu": TRAIN_BATCH, "vocab": TRAIN_VOCAB,
+                       "ss_ratio": ss_ratio, "dropout": "on (YAML values)", "trainable_params": step.n_trainable,
+                       "collective": "one all_reduce(sum) of the flat fp32 gradient per step" if world > 1 else "none (1 GPU)",
+                       "l2": f"rotating {n_rot} batches (4 x 41 MB of waveforms > 126 MB L2)"},
+            "ms_per_step_ss_ratio_0.85": ms_ss085,
+            "e2e": {"value": world * tok / (ms_e2e / 1000.0), "unit": "tokens/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": TRAIN_BATCH * TRAIN_SAMPLES * 4 + int(host[0]["cap"].numel()) * 8,
+                    "d2h_bytes_per_step": 4, "api": "TrainStep.step(batch): pinned host waveforms + captions in, loss.item() out"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc (frozen Cnn14 forward, 11 launches)", "achieved": achieved,
+                         "peak": bf16_sust, "unit": "TFLOP/s", "frac": achieved / bf16_sust if bf16_sust else None,
+                         "traffic": None, "ms_per_step": conv_ms, "share_of_step": conv_ms / (tot / n_prof),
+                         "note": "achieved = algorithmic fp32 flops (40.07 GFLOP/clip); every product is issued as 3 TF32 "
+                                 "MMAs, so the tensor pipe does 3x this",
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "kernel_shares": shares,
+                         "per_kernel": per_kernel, "spans_ms_per_step": spans},
+        }
+    del step, model
+    torch.cuda.empty_cache()
+    return rec
+
+
+def measured_tensor_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops", 1600.0)), float(d.get("bf16_tflops_sustained", 1400.0))
+    except Exception:
+        return 1600.0, 1400.0
+
+
+def cpu_train_sample(n_clips, reps=1):
+    """The oracle's literal training step (oracle/train_step.py: step-by-step decoder loop, torch autograd, Adam) on the
+    host cores; returns tokens/s, cores, seconds per step."""
+    import random
+    import torch
+    from oracle import caption_model as cm, cnn14 as oc, crnn, train_step as ts
+    torch.set_num_threads(os.cpu_count())
+    wav, lens = cm.synth_wav(n_clips, TRAIN_SAMPLES, seed=0, sample_rate=32000)
+    cap, cap_len = ts.synth_captions(n_clips, 22, TRAIN_VOCAB, seed=1, min_len=8)
+    cnn_sd, rnn_sd = oc.build_state_dict(3), crnn.build_gru_state_dict(4)
+    dec = crnn.build_decoder(6, vocab_size=TRAIN_VOCAB)
+    random.seed(1)
+    L = cap.size(1) - 1
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        coins = [random.random() < 0.99 for _ in range(L)]
+        ts.train_step(cnn_sd, rnn_sd, dec, wav, lens, cap, cap_len, coins, 5e-4)
+    dt = (time.perf_counter() - t0) / reps
+    return float((cap_len - 1).sum()) / dt, torch.get_num_threads(), dt
+
+
+def run_reference_train(args):
+    times, toks = [], None
+    n = 8
+    for i in range(args.warmup + args.steps):
+        v, cores, dt = cpu_train_sample(n)
+        if i >= args.warmup:
+            times.append(dt)
+            toks = v * dt
+        if sum(times) > 150:          # bounded: the whole run stays within a few minutes
+            break
+    ms = 1000.0 * sum(times) / len(times)
+    value = toks / (ms / 1000.0)
+    sample = f"{n} of the {TRAIN_BATCH} clips per step, {len(times)} timed steps (full 10 s clips, oracle port of the reference step)"
+    print(json.dumps({
+        "impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": TRAIN_WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
@@ -162,9 +331,49 @@ def run_native(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    from audiocaption_b200 import sharding
+    lib = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = lib.ac_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.ac_launch_count() - l0
+        ms = sharding.max_over_ranks(ms, device=dev)      # multi-GPU: the slowest rank, never wall clock
+        return ms / steps, launches
+
+    if args.workload == "train":
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        rec = run_train_leg(dev, rank, world, args.steps, args.warmup, timed, lib)
+        clocks = sampler.summary() if sampler else None
+        if rank == 0:
+            cpu_v, cores, cpu_dt = cpu_train_sample(4)
+            rec.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "clocks": clocks,
+                        "cpu_baseline": {"value": cpu_v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                         "sample": f"4 of the {TRAIN_BATCH} clips, one step ({cpu_dt:.1f} s of CPU work), oracle port "
+                                                   "of the reference training step"}})
+            print(json.dumps(rec))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     orc, model = build_models(dev)
     enc, dec = model.model.model.encoder, model.model.model.decoder
-    lib = _lib.lib()
 
     # rotating input set larger than L2 (8 x 41 MB = 328 MB > 126 MB): every step reads its clips from HBM
     n_rot = 8
@@ -191,28 +400,6 @@ def run_native(args):
             pending = nxt
         return pending.result()
 
-    from audiocaption_b200 import sharding
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        barrier()
-        l0 = lib.ac_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(warmup + i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = lib.ac_launch_count() - l0
-        ms = sharding.max_over_ranks(ms, device=dev)      # multi-GPU: the slowest rank, never wall clock
-        return ms / steps, launches
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -231,6 +418,43 @@ def run_native(args):
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1000.0
     ms_e2e = sharding.max_over_ranks(max(e0.elapsed_time(e1), wall_ms), device=dev) / args.steps
+
+    # sustained figure: the same step looped for >= 2 s (the K-step region above is a ~0.1 s burst)
+    n_sust = max(args.steps, int(2000.0 / max(ms_step, 0.1)) + 1)
+    ms_sust, _ = timed(step_resident, n_sust, 0)
+
+    # like-for-like GPU baseline: the oracle port (stock PyTorch eager: cuFFT / cuDNN / cuBLAS kernels) on the same B200
+    eager = None
+    if rank == 0:
+        try:
+            orc_dev = orc.to(dev).eval()
+            with torch.no_grad():
+                def eager_step(i):
+                    return orc_dev(devb[i % n_rot], lens, sample_method="greedy", max_length=MAX_LEN)
+                for i in range(2):
+                    eager_step(i)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n_eager = 5
+                for i in range(n_eager):
+                    eager_step(i)
+                torch.cuda.synchronize()
+                ms_eager = (time.perf_counter() - t0) * 1000.0 / n_eager
+            eager = {"value": BATCH / (ms_eager / 1000.0), "unit": "clips/s", "ms_per_step": ms_eager, "steps": n_eager,
+                     "what": "oracle port of the reference moved to the same GPU with .to('cuda'): stock PyTorch eager "
+                             "(cuFFT, cuDNN, cuBLAS, python decode loop); fp32 with torch's default TF32 settings"}
+        except Exception as e:                 # a baseline leg must never take the bench line down
+            eager = {"unavailable": repr(e)[:200]}
+        finally:
+            orc.to("cpu")
+
+    # ---- second half of the metric: the training step (tokens/s), same process, same GPUs
+    train = None
+    if not args.no_train:
+        del devb
+        torch.cuda.empty_cache()
+        train = run_train_leg(dev, rank, world, min(args.steps, 30), args.warmup, timed, lib)
+        devb = [h.to(dev) for h in host]
 
     # ---- roofline leg: the same steps with every launch bracketed by CUDA events
     roof = None
@@ -275,6 +499,10 @@ def run_native(args):
                     "synchronous_forward_ms_per_step": ms_e2e_sync,
                     "synchronous_forward_value": total / (ms_e2e_sync / 1000.0)},
             "gpu_launches": launches,
+            "sustained": {"value": total / (ms_sust / 1000.0), "unit": "clips/s", "ms_per_step": ms_sust, "steps": n_sust,
+                          "seconds": ms_sust * n_sust / 1000.0},
+            "gpu_eager_baseline": eager,
+            "train": train,
             "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",
                              "sample": f"8 of the {BATCH} clips per pass, {cpu_sample.last_reps} passes ({cpu_dt * cpu_sample.last_reps:.1f} s of CPU work), "
@@ -291,6 +519,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="effb2_trm", choices=["effb2_trm", "train"])
+    ap.add_argument("--no-train", action="store_true", help="effb2_trm workload: skip the attached training measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

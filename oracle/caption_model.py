@@ -130,13 +130,15 @@ class TransformerDecoder(nn.Module):
                 nn.init.xavier_uniform_(p)
 
     def forward(self, word, attn_emb, attn_emb_len, cap_padding_mask):
+        dev = attn_emb.device                  # (device-agnostic so that bench.py can time the same code as GPU eager)
+        word, cap_padding_mask = word.to(dev), cap_padding_mask.to(dev)
         mem = self.attn_proj(attn_emb).transpose(0, 1)
         emb = self.word_embedding(word) * math.sqrt(self.d_model)
         emb = emb.transpose(0, 1)
         emb = emb + self.pos_encoder.pe[:emb.size(0)]
         L = emb.size(0)
-        causal = torch.full((L, L), float("-inf")).triu(1)
-        mem_pad = ~length_mask(attn_emb_len, attn_emb.size(1))
+        causal = torch.full((L, L), float("-inf"), device=dev).triu(1)
+        mem_pad = ~length_mask(attn_emb_len, attn_emb.size(1)).to(dev)
         out = self.model(emb, mem, tgt_mask=causal, tgt_key_padding_mask=cap_padding_mask,
                          memory_key_padding_mask=mem_pad).transpose(0, 1)
         return {"embed": out, "logit": self.classifier(out)}
@@ -146,10 +148,11 @@ def greedy_decode(decoder, attn_emb, attn_emb_len, max_length=20):
     """stepwise_forward(mode=inference, sample_method=greedy): full-prefix recompute per step,
     rows that emitted <end> stay <end>, stop when every row has finished."""
     B = attn_emb.size(0)
-    seq = torch.full((B, max_length), END, dtype=torch.long)
-    logit = torch.zeros(B, max_length, decoder.vocab_size)
+    dev = attn_emb.device
+    seq = torch.full((B, max_length), END, dtype=torch.long)           # host tensor, as base.py:122
+    logit = torch.zeros(B, max_length, decoder.vocab_size, device=dev)
     logprob = torch.zeros(B, max_length)
-    embed = torch.zeros(B, max_length, decoder.d_model)
+    embed = torch.zeros(B, max_length, decoder.d_model, device=dev)
     steps = 0
     unfinished = None
     for t in range(max_length):
@@ -158,7 +161,7 @@ def greedy_decode(decoder, attn_emb, attn_emb_len, max_length=20):
         out = decoder(word, attn_emb, attn_emb_len, word == PAD)
         lg, em = out["logit"][:, -1], out["embed"][:, -1]
         lp, w = torch.max(torch.log_softmax(lg, dim=1), 1)
-        logit[:, t], embed[:, t], logprob[:, t], seq[:, t] = lg, em, lp, w
+        logit[:, t], embed[:, t], logprob[:, t], seq[:, t] = lg, em, lp.cpu(), w.cpu()
         steps = t + 1
         un_t = seq[:, t] != END
         unfinished = un_t if t == 0 else unfinished * un_t

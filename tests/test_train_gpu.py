@@ -312,8 +312,10 @@ def test_train_step_matches_oracle_for_every_coin_pattern(pattern):
     for k, p in m.named_parameters():
         if not p.requires_grad:
             continue
-        assert _relerr(p.grad, o["grads"][k]) < max(5e-4, 3 * sens[k]), (k, sens[k])
-        big = o["grads"][k].abs() > 1e-4
+        tol = max(5e-4, 3 * sens[k])
+        assert _relerr(p.grad, o["grads"][k]) < tol, (k, sens[k])
+        # the first Adam step is lr * g / (|g| + eps) ~ lr * sign(g): compared where g is well above its own uncertainty
+        big = o["grads"][k].abs() > max(1e-4, 20 * tol * o["grads"][k].abs().max().item())
         if big.any():
             assert (p.detach().cpu().double() - o["new_params"][k])[big].abs().max() < 0.03 * lr, k
 
