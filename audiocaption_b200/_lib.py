@@ -51,6 +51,8 @@ _SIGS = {
     "ac_bah_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "ac_bah_greedy": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_bah_greedy_ex": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   c_f32p, c_i64p, C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ac_bah_beam": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ac_sed_num_tensors": (C.c_int, []),
@@ -80,6 +82,8 @@ _SIGS = {
     "ac_trm_trace": (C.c_int, [C.c_int, C.c_void_p]),
     "ac_trm_beam": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                               C.c_int, C.c_int, C.c_int, c_i64p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_resample_out_len": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "ac_resample": (C.c_int, [c_f32p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     # ---- training step
     "ac_cnn14_fwd_train": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint64,
                                      c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -232,7 +232,10 @@ class TemporalBahAttnDecoder(BaseDecoder):
         tags = to_device_async(torch.as_tensor(temporal_tag), dev, torch.int64).contiguous()
         return fc_emb.float().contiguous(), attn_emb.float().contiguous(), lens, tags
 
-    def greedy(self, fc_emb, attn_emb, attn_emb_len, temporal_tag, max_length, start_idx, end_idx, need_logit=True):
+    def greedy(self, fc_emb, attn_emb, attn_emb_len, temporal_tag, max_length, start_idx, end_idx, need_logit=True,
+               state=None, first_word=None):
+        """Whole greedy decode in one launch.  With need_logit also returns `attn_weight` [B, T, max_length]
+        (hf_wrapper.py:1572-1607) and the final GRU `state` [1, B, 512].  state / first_word: see forward()."""
         fc_emb, attn_emb, lens, tags = self._prep(fc_emb, attn_emb, attn_emb_len, temporal_tag)
         B, T, _ = attn_emb.shape
         dev = attn_emb.device
@@ -242,12 +245,23 @@ class TemporalBahAttnDecoder(BaseDecoder):
             seq = torch.empty(B, max_length, dtype=torch.int64, device=dev)
             logprob = torch.zeros(B, max_length, dtype=torch.float32, device=dev)
             logit = torch.zeros(B, max_length, self.vocab_size, device=dev) if need_logit else None
+            attn_w = torch.zeros(B, max_length, T, device=dev) if need_logit else None
+            state_out = torch.zeros(B, self.d_model, device=dev) if need_logit else None
+            if state is not None:
+                state = state.to(dev).float().reshape(B, self.d_model).contiguous()
+            if first_word is not None:
+                first_word = to_device_async(torch.as_tensor(first_word).reshape(B), dev, torch.int64).contiguous()
             nbytes = l.ac_bah_workspace_bytes(dec, B, T)
             ws = self._ws.get(nbytes, dev)
-            _lib.check(l.ac_bah_greedy(dec, _lib.ptr(fc_emb), _lib.ptr(attn_emb), _lib.ptr(lens), _lib.ptr(tags), B, T,
-                                       max_length, start_idx, end_idx, _lib.ptr(seq), _lib.ptr(logprob), _lib.ptr(logit),
-                                       _lib.ptr(ws), nbytes, _lib.current_stream()), "ac_bah_greedy")
-        return {"seq": seq, "sampled_logprob": logprob, "logit": logit}
+            _lib.check(l.ac_bah_greedy_ex(dec, _lib.ptr(fc_emb), _lib.ptr(attn_emb), _lib.ptr(lens), _lib.ptr(tags), B, T,
+                                          max_length, start_idx, end_idx, _lib.ptr(state), _lib.ptr(first_word), _lib.ptr(seq),
+                                          _lib.ptr(logprob), _lib.ptr(logit), _lib.ptr(state_out), _lib.ptr(attn_w),
+                                          _lib.ptr(ws), nbytes, _lib.current_stream()), "ac_bah_greedy_ex")
+        out = {"seq": seq, "sampled_logprob": logprob, "logit": logit}
+        if need_logit:
+            out["attn_weight"] = attn_w.transpose(1, 2)
+            out["state"] = state_out.unsqueeze(0)
+        return out
 
     def beam_search(self, fc_emb, attn_emb, attn_emb_len, temporal_tag, max_length, beam_size, temp, start_idx, end_idx):
         fc_emb, attn_emb, lens, tags = self._prep(fc_emb, attn_emb, attn_emb_len, temporal_tag)
@@ -265,8 +279,20 @@ class TemporalBahAttnDecoder(BaseDecoder):
         return {"seq": seq}
 
     def forward(self, input_dict):
-        raise NotImplementedError("single-step TemporalBahAttnDecoder.forward is the training-time call; inference goes "
-                                  "through greedy()/beam_search() (whole decode in one launch)")
+        """ONE decoder step (hf_wrapper.py:1513-1554): word [N, 1] i64, state [1, N, 512] | None, fc_emb [N, 512],
+        attn_emb [N, T, 512], attn_emb_len [N], temporal_tag [N], t -> {"state" [1, N, 512], "embed" [N, 1, 512],
+        "logit" [N, 1, V], "attn_weight" [N, T]}.  At t == 0 the input embedding is temporal_embedding(tag), else the
+        word's.  Eval mode (the decoder's training / backward pass is not built).  The word-is-an-embedding branch of the
+        reference (`word.size(-1) == fc_emb_dim`) is not built."""
+        word = torch.as_tensor(input_dict["word"])
+        if word.dim() != 2 or word.size(-1) != 1:
+            raise NotImplementedError(f"problem with word input size {tuple(word.size())}: only word ids [N, 1] are built")
+        t = input_dict["t"]
+        out = self.greedy(input_dict["fc_emb"], input_dict["attn_emb"], input_dict["attn_emb_len"], input_dict["temporal_tag"],
+                          1, -1, -1, need_logit=True, state=input_dict.get("state", None),
+                          first_word=None if t == 0 else word[:, 0])
+        return {"state": out["state"], "embed": out["state"].transpose(0, 1), "logit": out["logit"],
+                "attn_weight": out["attn_weight"][:, :, 0]}
 
 
 class TemporalSeq2SeqAttnModel(CaptionModel):
@@ -286,6 +312,8 @@ class TemporalSeq2SeqAttnModel(CaptionModel):
         if not input_dict.get("_device_seq", False):
             out["seq"] = out["seq"].cpu()
             out["sampled_logprob"] = out["sampled_logprob"].cpu()
+            if "attn_weight" in out:
+                out["attn_weight"] = out["attn_weight"].cpu()          # hf_wrapper.py:1574: a host tensor
         return out
 
     def beam_search(self, input_dict):

@@ -15,6 +15,14 @@ import yaml
 from torch.optim.swa_utils import AveragedModel as _TorchAveragedModel
 
 
+def pad_sequence(data, pad_value=0):
+    """List of 1-D (or [T, D]) arrays -> (padded tensor [N, max_len, ...], lengths) (train_util.py:24-31)."""
+    if isinstance(data[0], (np.ndarray, torch.Tensor)):
+        data = [torch.as_tensor(arr) for arr in data]
+    padded = torch.nn.utils.rnn.pad_sequence(data, batch_first=True, padding_value=pad_value)
+    return padded, np.array([x.shape[0] for x in data])
+
+
 def get_cls_from_str(string, reload=False):
     """'pkg.module.Class' -> the class object (train_util.py:63-68)."""
     module_name, cls_name = string.rsplit(".", 1)

@@ -65,13 +65,18 @@ struct BahArgs {
     float* logprob;           // nullable [clips][max_len]
     float* logit_out;         // nullable [clips][max_len][V]
     int beam; float temp;
+    // single-step / stepwise extras of the greedy kernel (`TemporalBahAttnDecoder.forward`, hf_wrapper.py:1513-1554)
+    const float* h0;          // nullable [clips][BH]: initial GRU state (default zeros, `init_hidden`)
+    float* state_out;         // nullable [clips][BH]: GRU state after the last executed step
+    float* attn_w_out;        // nullable [clips][max_len][T]: attention weights of every step
+    const int64_t* first_tok; // nullable [clips]: word fed at step 0 instead of the temporal-tag embedding
 };
 
 // One decoder step for the R rows of this cluster.  s_tok[r] = row index into emb_tab; s_h is updated in place.
 template <int R>
 __device__ __forceinline__ void bah_step(const BahArgs& a, int clip, const int* s_tok, float* s_h, float* s_hn, float* s_q,
                                          float* s_ctx, float* s_gh, float* s_gc, float* s_sc, float* s_part,
-                                         float* const* logits) {
+                                         float* const* logits, float* aw = nullptr) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank(), P = (int)cluster.num_blocks();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,7 +116,10 @@ __device__ __forceinline__ void bah_step(const BahArgs& a, int clip, const int* 
         for (int s = lane; s < T; s += 32) { const float e = expf(sc[s] - m); sc[s] = e; se += e; }
         se = warp_sum(se);
         const float inv = 1.0f / se;
-        for (int s = lane; s < T; s += 32) sc[s] *= inv;
+        for (int s = lane; s < T; s += 32) {
+            sc[s] *= inv;
+            if (aw != nullptr && rank == 0) aw[warp * T + s] = sc[s];       // `attn_weight` of the step (row-major [R][T])
+        }
     }
     __syncthreads();
     for (int i = tid; i < R * BH; i += kThreads) {
@@ -219,7 +227,7 @@ bah_greedy_kernel(BahArgs a) {
     const int clip = blockIdx.x / P, tid = threadIdx.x;
     const bool writer = cluster.block_rank() == 0;
     const int V = a.w.vocab;
-    for (int i = tid; i < BH; i += kThreads) s_h[i] = 0.0f;      // init_hidden: zeros
+    for (int i = tid; i < BH; i += kThreads) s_h[i] = a.h0 ? a.h0[(size_t)clip * BH + i] : 0.0f;      // init_hidden: zeros
     int word = a.start_idx;
     bool finished = false;
     cluster.sync();   // every CTA of the cluster is resident before the first GEMV writes into its peers' shared memory
@@ -231,11 +239,16 @@ bah_greedy_kernel(BahArgs a) {
             continue;
         }
         if (tid == 0) {
-            s_tok[0] = t == 0 ? V + (int)min((int64_t)3, max((int64_t)0, a.tags[clip])) : word;
+            s_tok[0] = t > 0 ? word
+                     : a.first_tok ? (int)min((int64_t)V - 1, max((int64_t)0, a.first_tok[clip]))
+                                   : V + (int)min((int64_t)3, max((int64_t)0, a.tags[clip]));
             s_logits[0] = a.logit_out ? a.logit_out + ((size_t)clip * a.max_len + t) * V : a.logits_ws + (size_t)clip * a.w.vp;
         }
         __syncthreads();
-        bah_step<1>(a, clip, s_tok, s_h, s_hn, s_q, s_ctx, s_gh, s_gc, s_sc, s_part, s_logits);
+        bah_step<1>(a, clip, s_tok, s_h, s_hn, s_q, s_ctx, s_gh, s_gc, s_sc, s_part, s_logits,
+                    a.attn_w_out ? a.attn_w_out + ((size_t)clip * a.max_len + t) * a.T : nullptr);
+        if (a.state_out != nullptr && writer)
+            for (int i = tid; i < BH; i += kThreads) a.state_out[(size_t)clip * BH + i] = s_h[i];
         const float* logits = s_logits[0];
         float best = -INFINITY; int bi = 0x7fffffff;
         for (int n = tid; n < V; n += kThreads) {
@@ -521,6 +534,14 @@ extern "C" {
 int ac_bah_greedy(const ac_bah_t* d, const float* fc_emb, const float* attn_emb, const int64_t* lens, const int64_t* tags,
                   int B, int T, int max_len, int start_idx, int end_idx, int64_t* seq, float* logprob, float* logit_out,
                   void* ws, size_t ws_bytes, void* stream) {
+    return ac_bah_greedy_ex(d, fc_emb, attn_emb, lens, tags, B, T, max_len, start_idx, end_idx, nullptr, nullptr, seq, logprob,
+                            logit_out, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+int ac_bah_greedy_ex(const ac_bah_t* d, const float* fc_emb, const float* attn_emb, const int64_t* lens, const int64_t* tags,
+                     int B, int T, int max_len, int start_idx, int end_idx, const float* state_in, const int64_t* first_word,
+                     int64_t* seq, float* logprob, float* logit_out, float* state_out, float* attn_w_out,
+                     void* ws, size_t ws_bytes, void* stream) {
     using namespace ac;
     AC_REQUIRE(B >= 0 && T >= 1 && T <= kBahMaxT && max_len >= 1 && max_len <= kBahMaxLen,
                "ac_bah_greedy: sizes out of range (B=%d T=%d max_len=%d; T <= %d, max_len <= %d)", B, T, max_len, kBahMaxT, kBahMaxLen);
@@ -533,6 +554,7 @@ int ac_bah_greedy(const ac_bah_t* d, const float* fc_emb, const float* attn_emb,
     int rc = bah_prepare(d, fc_emb, attn_emb, B, T, (float*)ws, B, a, st); if (rc) return rc;
     a.mem_len = lens; a.tags = tags; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx;
     a.seq = seq; a.logprob = logprob; a.logit_out = logit_out; a.beam = 1; a.temp = 1.0f;
+    a.h0 = state_in; a.first_tok = first_word; a.state_out = state_out; a.attn_w_out = attn_w_out;
     AC_TIMED("bah_greedy", st);
     rc = bah_launch(bah_greedy_kernel, B, bah_smem_bytes(1), st, a); if (rc) return rc;
     AC_LAUNCHED("bah_greedy_kernel");

@@ -73,6 +73,15 @@ int ac_logmel_fwd(const ac_frontend_t* fe, const float* wav_dev, int batch, int 
 /* x = max(x, *gmax - top_db) in place (AmplitudeToDB(top_db=...)). */
 int ac_db_clamp(float* x_dev, int64_t n, const float* gmax_dev, float top_db, void* stream);
 
+/* ------------------------------------------------------------------ resampling (input pipeline)
+ * Replaces torchaudio.functional.resample (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) as called at demo.py:36,
+ * python_scripts/inference/inference.py:37 and captioning/datasets/caption_dataset.py:110-120.
+ * orig / nw = orig_freq / new_freq divided by their gcd; coef_dev [nw][taps] (taps = 2 * width + orig) is the polyphase
+ * kernel of torchaudio's `_get_sinc_resample_kernel`; wav_dev [batch, n_in] -> out_dev [batch, ac_resample_out_len]. */
+int ac_resample_out_len(int n_in, int orig, int nw);
+int ac_resample(const float* wav_dev, int batch, int n_in, const float* coef_dev, int orig, int nw, int taps, int width,
+                float* out_dev, void* stream);
+
 /* ------------------------------------------------------------------ pointwise GEMM (diagnostic)
  * The kernel behind every 1x1 convolution / Linear of the path (efficientnet_pytorch
  * `_expand_conv/_project_conv/_conv_head` + BN + swish, hf_wrapper.py:1045-1052 `attn_proj`):
@@ -271,6 +280,17 @@ int ac_bah_greedy(const ac_bah_t* dec, const float* fc_emb_dev, const float* att
                   const int64_t* tags_dev, int batch, int T, int max_len, int start_idx, int end_idx,
                   int64_t* seq_dev, float* logprob_dev, float* logit_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+/* The same decode with the decoder's step-level inputs / outputs exposed (`TemporalBahAttnDecoder.forward`,
+ * hf_wrapper.py:1513-1554, is ONE step: call with max_len = 1): state_in_dev (nullable) [batch,512] = the GRU state to
+ * start from (`state`; default zeros), first_word_dev (nullable) [batch] int64 = the word fed at step 0 (when NULL step 0
+ * feeds temporal_embedding(tag), the reference's `t == 0` branch); state_out_dev (nullable) [batch,512] = state after the
+ * last executed step (= `embed`: the 1-layer GRU's output), attn_w_out_dev (nullable) [batch,max_len,T] = `attn_weight`
+ * of every step (hf_wrapper.py:1603-1607 stores them as [batch,T,max_len]). */
+int ac_bah_greedy_ex(const ac_bah_t* dec, const float* fc_emb_dev, const float* attn_emb_dev, const int64_t* lens_dev,
+                     const int64_t* tags_dev, int batch, int T, int max_len, int start_idx, int end_idx,
+                     const float* state_in_dev, const int64_t* first_word_dev, int64_t* seq_dev, float* logprob_dev,
+                     float* logit_dev, float* state_out_dev, float* attn_w_out_dev, void* workspace_dev,
+                     size_t workspace_bytes, void* stream);
 /* per-clip beam search with the reference's bookkeeping (beam 1..5); the GRU state follows `prev_words_beam`. */
 int ac_bah_beam(const ac_bah_t* dec, const float* fc_emb_dev, const float* attn_emb_dev, const int64_t* lens_dev,
                 const int64_t* tags_dev, int batch, int T, int max_len, int beam, float temp, int start_idx,

@@ -619,6 +619,44 @@ def test_temp_gru_decoder_matches_oracle(temp_gru, B, T, beam):
     assert (gotb[:nb][stb] == refb.numpy()[stb]).all()
 
 
+def test_temp_gru_decoder_single_step_forward_and_attn_weight(temp_gru):
+    """`TemporalBahAttnDecoder.forward(input_dict)` (hf_wrapper.py:1513-1554) called step by step the way
+    `Seq2SeqAttnModel.decode_step` does (word [N, 1], carried `state`, `t`): logit / state / embed / attn_weight of every
+    step vs the oracle's `step` (pinned to the imported class); and the `attn_weight` [B, T, L] / final `state` outputs of
+    the single-launch greedy decode (hf_wrapper.py:1572-1607)."""
+    from oracle import bah_decoder as bd
+    dec, sd, _ = temp_gru
+    B, T = 5, 31
+    fc, attn, lens, tags = bd.synth_memory(7, B, T)
+    state_ref = torch.zeros(B, 512)
+    state_dev = None
+    word = torch.full((B, 1), cm.START, dtype=torch.long)
+    ws = []
+    for t in range(4):
+        with torch.no_grad():
+            lg, state_ref, w = bd.step(sd, t, word[:, 0], torch.as_tensor(tags).long(), state_ref, fc, attn, lens)
+        inp = {"word": word, "fc_emb": fc.to(DEV), "attn_emb": attn.to(DEV), "attn_emb_len": lens, "temporal_tag": tags, "t": t}
+        if state_dev is not None:
+            inp["state"] = state_dev
+        out = dec(inp)
+        assert out["logit"].shape == (B, 1, lg.shape[1]) and out["state"].shape == (1, B, 512)
+        assert out["embed"].shape == (B, 1, 512) and out["attn_weight"].shape == (B, T)
+        assert (out["logit"][:, 0].cpu() - lg).abs().max() < 2e-4
+        assert (out["state"][0].cpu() - state_ref).abs().max() < 2e-5
+        assert (out["embed"][:, 0].cpu() - state_ref).abs().max() < 2e-5
+        assert (out["attn_weight"].cpu() - w).abs().max() < 2e-5
+        assert (out["attn_weight"].cpu().sum(1) - 1).abs().max() < 1e-5
+        state_dev = out["state"]
+        word = lg.argmax(1, keepdim=True)                    # feed the oracle's word to both
+        ws.append(w)
+    full = dec.greedy(fc.to(DEV), attn.to(DEV), lens, tags, 6, cm.START, cm.END, need_logit=True)
+    assert full["attn_weight"].shape == (B, T, 6) and full["state"].shape == (1, B, 512)
+    ref = bd.greedy_decode(sd, fc, attn, lens, tags, 6)
+    same = (full["seq"].cpu() == ref["seq"]).all(1)
+    assert (full["attn_weight"][:, :, 0].cpu() - ws[0]).abs().max() < 2e-5
+    assert same.any()
+
+
 def _temp_gru_model(dsd):
     from audiocaption_b200.captioning.models import hf_wrapper as hw
     from oracle import cnn14 as oc, crnn, sed

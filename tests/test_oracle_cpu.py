@@ -351,6 +351,21 @@ def test_temp_gru_oracle_matches_imported_reference():
     ob = bd.beam_search(sd, fc, attn, lens, tags, 4, 12, 1.0)
     assert (rg["seq"] == og["seq"]).all() and (rb["seq"] == ob["seq"]).all()
     assert (rg["logit"][:, 0] - og["logit"][:, 0]).abs().max() < 1e-4
+    # the single decoder call (hf_wrapper.py:1513-1554): state, logit and attention weights of two chained steps
+    with torch.no_grad():
+        state_o = torch.zeros(4, 512)
+        state_r = None
+        word = torch.full((4, 1), 1, dtype=torch.long)
+        for t in range(2):
+            lg, state_o, w = bd.step(sd, t, word[:, 0], torch.as_tensor(tags).long(), state_o, fc, attn, lens)
+            inp = {"word": word, "fc_emb": fc, "attn_emb": attn, "attn_emb_len": lens, "temporal_tag": torch.as_tensor(tags), "t": t}
+            if state_r is not None:
+                inp["state"] = state_r
+            out = dec.eval()(inp)
+            state_r = out["state"]
+            assert (out["logit"][:, 0] - lg).abs().max() < 1e-4 and (out["state"][0] - state_o).abs().max() < 1e-5
+            assert (out["attn_weight"] - w).abs().max() < 1e-6
+            word = lg.argmax(1, keepdim=True)
 
 
 def test_temp_gru_mirror_state_dict_matches_reference_layout():
