@@ -154,8 +154,9 @@ class AveragedModel(_TorchAveragedModel):
             list(zip(list(self.buffers())[1:], model.buffers()))          # buffers()[0] is n_averaged itself
         for avg, cur in pairs:
             cur = cur.detach().to(avg.device)
-            if first:
+            if first or not cur.is_floating_point():
                 avg.detach().copy_(cur)
-            else:
-                avg.detach().copy_(self.avg_fn(avg.detach(), cur, self.n_averaged.to(avg.device)))
+            else:                                     # the default avg_fn of swa_utils: equal-weight running mean
+                n = self.n_averaged.to(avg.device)
+                avg.detach().copy_(avg.detach() + (cur - avg.detach()) / (n + 1))
         self.n_averaged += 1

@@ -24,6 +24,44 @@ from .captioning.models._native import to_device_async
 from .captioning.utils.lr_scheduler import exponential_decay_lr
 
 
+def flatten_trainable(model, device=None):
+    """Re-home every trainable parameter of `model` as a view of ONE flat fp32 buffer and its `.grad` as a view of a
+    second one (each tensor 128-byte aligned: gradients are written by TMA stores).  Returns (params, flat_param,
+    flat_grad).  After this, one `all_reduce(flat_grad)` is the whole data-parallel gradient exchange and one fused kernel
+    over the two buffers is the whole optimizer step; `state_dict()` keeps working (the views ARE the parameters)."""
+    params, seen = [], set()
+    for p in model.parameters():
+        if p.requires_grad and id(p) not in seen:
+            seen.add(id(p))
+            params.append(p)
+    offs, total = [], 0
+    for p in params:
+        if p.dtype != torch.float32:
+            raise _lib.AudioCaptionB200Error("flatten_trainable needs fp32 master parameters")
+        offs.append(total)
+        total += (p.numel() + 31) // 32 * 32
+    device = params[0].device if device is None else device
+    flat_param = torch.zeros(total, dtype=torch.float32, device=device)
+    flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+    for p, o in zip(params, offs):
+        view = flat_param[o:o + p.numel()].view_as(p)
+        view.copy_(p.data)
+        p.data = view
+        p.grad = flat_grad[o:o + p.numel()].view_as(p)
+    return params, flat_param, flat_grad
+
+
+def allreduce_gradients(flat_grad, group=None):
+    """The data-parallel exchange (python_scripts/train_eval/run_ddp.py:105-107 gets it from DistributedDataParallel): one
+    sum all-reduce over the flat gradient; returns the factor (1 / world) the optimizer kernel folds in."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return 1.0
+    world = torch.distributed.get_world_size(group)
+    if world > 1:
+        torch.distributed.all_reduce(flat_grad, group=group)
+    return 1.0 / world
+
+
 class TrainStep:
     """`step(batch)` = one optimizer step of the reference's training loop on the Cnn14Rnn-Transformer captioner
     (eg_configs/*/waveform/cnn14rnn_trm.yaml): TransformerModel(CrnnEncoder(Cnn14Encoder, RnnEncoder), TransformerDecoder)."""
@@ -65,29 +103,10 @@ class TrainStep:
 
     # ---- flat parameter / gradient storage -------------------------------------------------------------------------
     def _flatten(self):
-        params, seen = [], set()
-        for p in self.model.parameters():
-            if p.requires_grad and id(p) not in seen:
-                seen.add(id(p))
-                params.append(p)
-        offs, total = [], 0
-        for p in params:
-            if p.dtype != torch.float32:
-                raise _lib.AudioCaptionB200Error("TrainStep needs fp32 master parameters")
-            offs.append(total)
-            total += (p.numel() + 31) // 32 * 32          # 128-byte aligned: gradients are written by TMA stores
-        dev = self.device
-        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        for p, o in zip(params, offs):
-            view = self.flat_param[o:o + p.numel()].view_as(p)
-            view.copy_(p.data)
-            p.data = view
-            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-        self.params = params
-        self.n_trainable = sum(p.numel() for p in params)
+        self.params, self.flat_param, self.flat_grad = flatten_trainable(self.model, self.device)
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.n_trainable = sum(p.numel() for p in self.params)
 
     # ---- schedules (host) ---------------------------------------------------------------------------------------------
     def _update_ss_ratio(self):
@@ -136,11 +155,10 @@ class TrainStep:
             loss, dlogit = ls_ce_fwd_bwd(out["logit_padded"][:, :, :dec.vocab_size], cap[:, 1:], tgt_len_dev, self.smoothing)
             dmem = dec.train_engine.backward(dlogit, need_dattn=True)
             rnn.train_engine.backward(dmem, need_dx=False)
-            if self.world > 1:
-                torch.distributed.all_reduce(self.flat_grad, group=self.group)
+            grad_scale = allreduce_gradients(self.flat_grad, self.group) if self.world > 1 else 1.0
             _lib.check(l.ac_clip_adam(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
                                       _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), self.lr, self.betas[0], self.betas[1],
-                                      self.eps, self.weight_decay, self.max_grad_norm, 1.0 / self.world, _lib.ptr(loss),
+                                      self.eps, self.weight_decay, self.max_grad_norm, grad_scale, _lib.ptr(loss),
                                       _lib.ptr(self._step_dev), _lib.ptr(self.grad_norm), _lib.ptr(self._adam_ws),
                                       self._adam_ws.numel(), _lib.current_stream()), "ac_clip_adam")
         self.iteration += 1

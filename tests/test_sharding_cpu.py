@@ -71,3 +71,47 @@ def test_two_rank_gloo(n_clips):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+# ------------------------------------------------------------------ training: flat gradient all-reduce (2 gloo ranks)
+def _ddp_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from audiocaption_b200.train_step import allreduce_gradients, flatten_trainable
+    torch.manual_seed(0)                                   # identical replicas
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.LayerNorm(7), torch.nn.Linear(7, 3))
+    model[1].bias.requires_grad_(False)                    # a frozen parameter stays out of the flat buffers
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    params, flat_p, flat_g = flatten_trainable(model)
+    assert len(params) == 5 and flat_p.numel() % 32 == 0 and flat_p.numel() >= sum(p.numel() for p in params)
+    assert all((model.state_dict()[k] == v).all() for k, v in before.items())          # values survive the re-homing
+    assert all(p.data_ptr() >= flat_p.data_ptr() and p.grad.data_ptr() >= flat_g.data_ptr() for p in params)
+    for i, p in enumerate(params):                         # each rank writes its own gradients THROUGH the views
+        p.grad.fill_(float(rank + 1) * (i + 1))
+    scale = allreduce_gradients(flat_g)
+    ok = abs(scale - 1.0 / world) < 1e-12
+    for i, p in enumerate(params):                         # sum over ranks, visible through the views
+        ok = ok and bool((p.grad == float((1 + 2) * (i + 1))).all())
+    with torch.no_grad():
+        flat_p.add_(flat_g, alpha=-scale)                  # "optimizer" on the flat buffer updates the module's parameters
+    ok = ok and bool(torch.allclose(model[0].weight, before["0.weight"] - 1.5 * 1))
+    ok = ok and bool((model[1].bias == before["1.bias"]).all())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_two_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
