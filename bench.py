@@ -210,11 +210,14 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
     ms_ss085, _ = timed(step_resident, steps, 3)
     step.ss_ratio = ss_ratio
     rec = None
+    # per-kernel CUDA-event timing: EVERY rank runs the same steps (each contains the gradient all-reduce); rank 0 records
+    n_prof = min(steps, 5)
     if rank == 0:
         lib.ac_timing_enable(1)
-        n_prof = min(steps, 5)
-        for i in range(n_prof):
-            step_resident(i)
+    for i in range(n_prof):
+        step_resident(i)
+    torch.cuda.synchronize()
+    if rank == 0:
         rep = _lib.timing_report()
         lib.ac_timing_enable(0)
         spans = {k: round(ms / n_prof, 4) for k, (n, ms) in rep.items() if k.startswith("span_")}
@@ -324,7 +327,8 @@ def run_native(args):
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            import datetime
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
             dist.barrier()
             torch.cuda.synchronize()
         finally:

@@ -629,15 +629,15 @@ def test_temp_gru_decoder_single_step_forward_and_attn_weight(temp_gru):
     B, T = 5, 31
     fc, attn, lens, tags = bd.synth_memory(7, B, T)
     state_ref = torch.zeros(B, 512)
-    state_dev = None
+    state_in = None
     word = torch.full((B, 1), cm.START, dtype=torch.long)
     ws = []
     for t in range(4):
+        inp = {"word": word, "fc_emb": fc.to(DEV), "attn_emb": attn.to(DEV), "attn_emb_len": lens, "temporal_tag": tags, "t": t}
+        if state_in is not None:
+            inp["state"] = state_in                      # the oracle's state goes in: every step is compared on equal input
         with torch.no_grad():
             lg, state_ref, w = bd.step(sd, t, word[:, 0], torch.as_tensor(tags).long(), state_ref, fc, attn, lens)
-        inp = {"word": word, "fc_emb": fc.to(DEV), "attn_emb": attn.to(DEV), "attn_emb_len": lens, "temporal_tag": tags, "t": t}
-        if state_dev is not None:
-            inp["state"] = state_dev
         out = dec(inp)
         assert out["logit"].shape == (B, 1, lg.shape[1]) and out["state"].shape == (1, B, 512)
         assert out["embed"].shape == (B, 1, 512) and out["attn_weight"].shape == (B, T)
@@ -646,7 +646,7 @@ def test_temp_gru_decoder_single_step_forward_and_attn_weight(temp_gru):
         assert (out["embed"][:, 0].cpu() - state_ref).abs().max() < 2e-4
         assert (out["attn_weight"].cpu() - w).abs().max() < 1e-4
         assert (out["attn_weight"].cpu().sum(1) - 1).abs().max() < 1e-5
-        state_dev = out["state"]
+        state_in = state_ref.unsqueeze(0).to(DEV)
         word = lg.argmax(1, keepdim=True)                    # feed the oracle's word to both
         ws.append(w)
     full = dec.greedy(fc.to(DEV), attn.to(DEV), lens, tags, 6, cm.START, cm.END, need_logit=True)
