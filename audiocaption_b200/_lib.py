@@ -84,6 +84,10 @@ _SIGS = {
                               C.c_int, C.c_int, C.c_int, c_i64p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ac_resample_out_len": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ac_resample": (C.c_int, [c_f32p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    "ac_cnn14_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "ac_sed_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "ac_conv3x3_p": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_void_p]),
     # ---- training step
     "ac_cnn14_fwd_train": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint64,
                                      c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -240,6 +240,7 @@ struct ac_cnn14 {
     ac::Cnn14Conv conv[2 * ac::kCnn14Blocks - 1];   // block1.conv2, block2.conv1, ... block6.conv2
     float *fc_w, *fc_b;
     ac::TcWeight fc_tw;
+    int conv_passes = 3;          // 3 = 3xTF32 (fp32-level), 1 = plain TF32 (ac_cnn14_set_precision)
 };
 
 namespace ac {
@@ -367,6 +368,16 @@ void ac_cnn14_destroy(ac_cnn14_t* net) {
     delete net;
 }
 
+// tf32_passes = 3 (default): every 3x3 convolution product as three TF32 MMAs -- fp32-level accuracy, the mode all
+// fp32 parity numbers are quoted in; 1: plain TF32 operands (10-bit mantissa, fp32 accumulate), the tensor-core mode for
+// the configurations BASELINE.json states in bf16 (training, temporal captioner).
+int ac_cnn14_set_precision(ac_cnn14_t* net, int tf32_passes) {
+    using namespace ac;
+    AC_REQUIRE(net && (tf32_passes == 1 || tf32_passes == 3), "ac_cnn14_set_precision: passes must be 1 or 3");
+    net->conv_passes = tf32_passes;
+    return AC_OK;
+}
+
 int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int n_frames, const int64_t* lens,
                  float* attn_emb, float* fc_emb, void* workspace, size_t ws_bytes, void* stream) {
     return ac_cnn14_fwd_train(net, lms, B, n_mels, n_frames, lens, 0.0f, 0.0f, 0, attn_emb, fc_emb, workspace, ws_bytes, stream);
@@ -412,7 +423,7 @@ int ac_cnn14_fwd_train(const ac_cnn14_t* net, const float* lms, int B, int n_mel
             if (i == 0 && j == 0) continue;
             const Cnn14Conv& c = net->conv[l++];
             Conv3Args a; a.in = cur; a.out = nxt; a.B = B; a.H = d[i].H; a.W = d[i].W; a.Cin = c.cin; a.Cout = c.cout;
-            a.bias = c.bias; a.tw = &c.tw; a.act = ACT_RELU;
+            a.bias = c.bias; a.tw = &c.tw; a.act = ACT_RELU; a.passes = net->conv_passes;
             rc = conv3x3_tc(a, st); if (rc) return rc;
             std::swap(cur, nxt);
         }
@@ -462,6 +473,7 @@ struct ac_sed {
     ac::TcWeight fc1_tw, fco_tw;
     ac_bigru_t* gru = nullptr;
     int classes = 0, classes_pad = 0;
+    int conv_passes = 3;
 };
 
 namespace ac {
@@ -483,6 +495,13 @@ static size_t sed_act_elems(int batch, int n_mels, int n_frames) {
 }  // namespace ac
 
 extern "C" {
+
+int ac_sed_set_precision(ac_sed_t* net, int tf32_passes) {
+    using namespace ac;
+    AC_REQUIRE(net && (tf32_passes == 1 || tf32_passes == 3), "ac_sed_set_precision: passes must be 1 or 3");
+    net->conv_passes = tf32_passes;
+    return AC_OK;
+}
 
 int ac_sed_num_tensors(void) { return 4 + ac::kSedBlocks * 10 + 2 + 8 + 2; }
 int ac_sed_segments(int n_frames) { return n_frames / 4; }
@@ -634,7 +653,7 @@ int ac_sed_fwd(const ac_sed_t* net, const float* lms, int B, int n_mels, int n_f
             if (i == 0 && j == 0) continue;
             const Cnn14Conv& c = net->conv[l++];
             Conv3Args a; a.in = cur; a.out = nxt; a.B = B; a.H = d[i].H; a.W = d[i].W; a.Cin = c.cin; a.Cout = c.cout;
-            a.bias = c.bias; a.tw = &c.tw; a.act = ACT_RELU;
+            a.bias = c.bias; a.tw = &c.tw; a.act = ACT_RELU; a.passes = net->conv_passes;
             rc = conv3x3_tc(a, st); if (rc) return rc;
             std::swap(cur, nxt);
         }

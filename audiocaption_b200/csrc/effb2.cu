@@ -500,23 +500,16 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
 
     Dims stem; std::vector<Dims> din, dout;
     walk(n_mels, n_frames, stem, din, dout);
-    {
-        int64_t total = (int64_t)B * stem.H * stem.W * P.stem_out / 4;
-        AC_TIMED("stem", st);
-        stem_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(lms, gmax, top_db, net->stem.w, net->stem.scale,
-                                                                  net->stem.bias, X0, n_mels, n_frames, stem.H,
-                                                                  stem.W, P.stem_out, P.stem_pad_lo, total);
-        AC_LAUNCHED("stem_kernel");
-    }
-    float* cur = X0; float* nxt = X1;
-    for (size_t i = 0; i < P.blocks.size(); ++i) {
+    // One MBConv block on clips [c0, c0 + nb) of the block's input `in` / output `out` (both [B, pixels, C]); the
+    // expanded tensor E, the depthwise output D, the SE partial sums and gates are scratch reused by every chunk.
+    auto run_block = [&](size_t i, const float* in, float* out, int nb) -> int {
         const BlockPlan& b = P.blocks[i];
         const BlockW& w = net->blocks[i];
         const int ce = b.cexp();
         const int pin = din[i].H * din[i].W, pout = dout[i].H * dout[i].W;
-        const float* dw_in = cur;
+        const float* dw_in = in;
         if (b.expand != 1) {
-            GemmArgs g; g.A = cur; g.W = w.expand.w; g.C = E; g.M = B * pin; g.N = ce; g.K = b.cin;
+            GemmArgs g; g.A = in; g.W = w.expand.w; g.C = E; g.M = nb * pin; g.N = ce; g.K = b.cin;
             g.cscale = w.expand.scale; g.cbias = w.expand.bias; g.act = ACT_SWISH;
             g.tw = w.expand.tw.packed ? &w.expand.tw : nullptr;
             int rc = gemm_tn(g, st); if (rc) return rc;
@@ -524,16 +517,62 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         }
         DwArgs da;
         da.in = dw_in; da.out = D; da.partial = PART; da.w = w.dw.w; da.scale = w.dw.scale; da.bias = w.dw.bias;
-        da.B = B; da.Hi = din[i].H; da.Wi = din[i].W; da.Ho = dout[i].H; da.Wo = dout[i].W; da.C = ce;
+        da.B = nb; da.Hi = din[i].H; da.Wi = din[i].W; da.Ho = dout[i].H; da.Wo = dout[i].W; da.C = ce;
         da.k = b.k; da.s = b.s; da.pad_lo = b.pad_lo;
         int rc = dwconv_tma(da, st); if (rc) return rc;
         const int strips = dwconv_tiles_per_clip(dout[i].H, dout[i].W, ce, b.k, b.s);
-        rc = launch_se(PART, strips, 1.0f / (float)pout, w, GATE, B, ce, b.nsq, st); if (rc) return rc;
-        GemmArgs g; g.A = D; g.W = w.project.w; g.C = nxt; g.M = B * pout; g.N = b.cout; g.K = ce;
+        rc = launch_se(PART, strips, 1.0f / (float)pout, w, GATE, nb, ce, b.nsq, st); if (rc) return rc;
+        GemmArgs g; g.A = D; g.W = w.project.w; g.C = out; g.M = nb * pout; g.N = b.cout; g.K = ce;
         g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
-        g.act = ACT_NONE; g.R = b.skip ? cur : nullptr;
+        g.act = ACT_NONE; g.R = b.skip ? in : nullptr;
         g.tw = w.project.tw.packed ? &w.project.tw : nullptr;
-        rc = gemm_tn(g, st); if (rc) return rc;
+        return gemm_tn(g, st);
+    };
+    auto run_stem = [&](const float* lms_c, float* out, int nb) -> int {
+        int64_t total = (int64_t)nb * stem.H * stem.W * P.stem_out / 4;
+        AC_TIMED("stem", st);
+        stem_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(lms_c, gmax, top_db, net->stem.w, net->stem.scale,
+                                                                  net->stem.bias, out, n_mels, n_frames, stem.H,
+                                                                  stem.W, P.stem_out, P.stem_pad_lo, total);
+        AC_LAUNCHED("stem_kernel");
+        return AC_OK;
+    };
+    // ---- L2-resident head of the network (experiment).  The high-resolution blocks move 28 MB per clip between kernels (the 6x
+    // expanded tensor is written by the expand GEMM, read and written by the depthwise kernel, read by the project GEMM);
+    // at 64 clips no tensor survives in the 126 MB L2 from its producer to its consumer.  Running the stem and the first
+    // `head_blocks` blocks one group of `chunk` clips at a time keeps a group's working set (<= 9.1 MB per clip) in L2, so
+    // only the group's input and final output touch HBM.  Per-clip tensor sizes shrink along the chain, hence group g's
+    // intermediates (at clip offset g * chunk in the ping-pong buffers) never reach the finished outputs of groups < g
+    // nor the unread stem input of groups > g.
+    // MEASURED (scripts/effb2_chunk_sweep.py, 64 clips): slower, not faster -- 5 blocks x 8 clips: encoder 2.75 -> 3.36 ms,
+    // sum of kernel times 3.17 -> 4.44 ms.  Every extra launch of the tensor-core GEMM / SE kernels costs ~8 us of fixed
+    // prologue + drain, which outweighs whatever DRAM traffic the L2 residency saves.  Off by default; the switch stays
+    // for the record: AC_EFFB2_CHUNK="blocks,clips".
+    int head_blocks = 0, chunk = 0;
+    if (const char* e = getenv("AC_EFFB2_CHUNK")) sscanf(e, "%d,%d", &head_blocks, &chunk);
+    head_blocks = std::max(0, std::min(head_blocks, (int)P.blocks.size()));
+    if (chunk <= 0 || chunk >= B) head_blocks = 0;
+    float* cur = X0; float* nxt = X1;
+    if (head_blocks == 0) {
+        int rc = run_stem(lms, X0, B); if (rc) return rc;
+    } else {
+        const size_t s_stem = (size_t)stem.H * stem.W * P.stem_out;
+        for (int c0 = 0; c0 < B; c0 += chunk) {
+            const int nb = std::min(chunk, B - c0);
+            float* a = X0; float* bb = X1;
+            int rc = run_stem(lms + (size_t)c0 * n_mels * n_frames, a + (size_t)c0 * s_stem, nb); if (rc) return rc;
+            size_t s_in = s_stem;
+            for (int i = 0; i < head_blocks; ++i) {
+                const size_t s_out = (size_t)dout[i].H * dout[i].W * P.blocks[i].cout;
+                rc = run_block(i, a + (size_t)c0 * s_in, bb + (size_t)c0 * s_out, nb); if (rc) return rc;
+                std::swap(a, bb);
+                s_in = s_out;
+            }
+        }
+        if (head_blocks & 1) std::swap(cur, nxt);
+    }
+    for (size_t i = head_blocks; i < P.blocks.size(); ++i) {
+        int rc = run_block(i, cur, nxt, B); if (rc) return rc;
         std::swap(cur, nxt);
     }
     const Dims last = dout.back();

@@ -46,6 +46,7 @@ struct GemmArgs {
     int act = ACT_NONE;
     int ldc = 0;                    // row stride of C / R (0 -> N)
     int lda = 0;                    // row stride of A (0 -> K); a multiple of 4 floats
+    int passes = 3;                 // tensor-core path: 3 = 3xTF32 (fp32-level accuracy), 1 = plain TF32
     const TcWeight* tw = nullptr;   // packed copy of W for the tensor-core path (nullptr -> SIMT kernel)
 };
 
@@ -64,6 +65,7 @@ struct Conv3Args {
     const float* bias = nullptr;    // [Cout]
     const TcWeight* tw = nullptr;
     int act = ACT_NONE;
+    int passes = 3;                 // 3 = 3xTF32, 1 = plain TF32 ("tf32" precision mode)
 };
 int conv3x3_tc(const Conv3Args& a, cudaStream_t st);
 int conv3x3_permute_weight(const float* w_dev, float* out_dev, int Cout, int Cin, cudaStream_t st);

@@ -70,6 +70,11 @@ struct TcParams {
     // merge != 0: the TMEM A ring has as many slots as there are smem stages, slot index == stage index, and ONE
     // tcgen05.commit per chunk (on bar_empty) releases both (every commit costs the issuing thread ~165 cycles)
     int merge;
+    // passes = 3: every fp32 product is issued as three TF32 MMAs (lo*hi + hi*lo + hi*hi, fp32-level accuracy);
+    // passes = 1: the hi*hi MMA only (plain TF32, ~2^-11 relative per product): the "tf32" precision mode of the
+    // Cnn14 / SED convolutions for the bf16-class configurations (BASELINE configs[2..4]).  The lo halves are then
+    // neither fetched (streamed weights) nor written to tensor memory.
+    int passes;
     long long* dbg;   // optional pipeline trace of CTA 0 (AC_TC_TRACE): [event kind 0..7][256] clock64 stamps
 };
 
@@ -105,8 +110,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t slabs = base;
     const uint32_t w_res = slabs + (CONV ? (uint32_t)(TC_BM * p.BN * 4) : (uint32_t)(TC_EPI_WARPS * TC_SLAB_BYTES));   // CONV: fp32 running sums [BN][128]
     const uint32_t w_chunk_bytes = (uint32_t)p.BN * 256u;
+    const uint32_t w_load_bytes = p.passes == 1 ? (uint32_t)p.BN * 128u : w_chunk_bytes;   // hi image only in tf32 mode
     const uint32_t stage0 = w_res + (p.resident ? (uint32_t)p.k_chunks * w_chunk_bytes : 0u);
-    const uint32_t stage_bytes = TC_A_TILE_BYTES + (p.resident ? 0u : w_chunk_bytes);
+    const uint32_t stage_bytes = TC_A_TILE_BYTES + (p.resident ? 0u : w_load_bytes);
     const uint32_t bars = stage0 + p.stages * stage_bytes;
     auto bar_tma = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 64u + 8u * s; };
@@ -172,7 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(bar_empty(stage), phase ^ 1u);
                     AC_TC_STAMP(0, ev); ++ev;
                     const uint32_t sa = stage0 + stage * stage_bytes;
-                    mbar_expect_tx(bar_tma(stage), (uint32_t)p.a_bytes + (p.resident ? 0u : w_chunk_bytes));
+                    mbar_expect_tx(bar_tma(stage), (uint32_t)p.a_bytes + (p.resident ? 0u : w_load_bytes));
                     if (CONV) {
                         // the tile's pixels shifted by the tap; rows / columns outside the image arrive as zeros
                         tma_load_4d(sa, &mapA, cc * TC_BK, tap % 3 - 1, c_h0 + tap / 3 - 1, c_b0, bar_tma(stage));
@@ -181,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tma_load_2d(sa, &mapA, kc * TC_BK, m_t * TC_BM, bar_tma(stage));
                     }
                     if (!p.resident)
-                        bulk_load(sa + TC_A_TILE_BYTES, wsrc + (size_t)kc * (p.BN * 64), w_chunk_bytes, bar_tma(stage));
+                        bulk_load(sa + TC_A_TILE_BYTES, wsrc + (size_t)kc * (p.BN * 64), w_load_bytes, bar_tma(stage));
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -264,9 +270,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
                         if (ks < ksteps) {
                             // 8 tf32 = 32 bytes along the swizzled W row = +2 in the descriptor's address field
-                            mma_tf32_ts(d_tmem, a_lo + ks * 8u, dwh0 + 2u * ks, idesc, (in_seg | ks) != 0 ? 1u : 0u);   // small terms first
-                            mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwl0 + 2u * ks, idesc, 1u);
-                            mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh0 + 2u * ks, idesc, 1u);
+                            if (p.passes == 1) {
+                                mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh0 + 2u * ks, idesc, (in_seg | ks) != 0 ? 1u : 0u);
+                            } else {
+                                mma_tf32_ts(d_tmem, a_lo + ks * 8u, dwh0 + 2u * ks, idesc, (in_seg | ks) != 0 ? 1u : 0u);   // small terms first
+                                mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwl0 + 2u * ks, idesc, 1u);
+                                mma_tf32_ts(d_tmem, a_hi + ks * 8u, dwh0 + 2u * ks, idesc, 1u);
+                            }
                         }
                     }
                     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(tmem_slot_addr + 8u), "r"(n_chunk + 1) : "memory");
@@ -347,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             else mbar_wait(bar_aempty(as), aphase ^ 1u);   // the tensor core is done with this TMEM A slot
             tc_fence_after();
             tmem_st16(a_ring + (uint32_t)as * 64u, hi);
-            tmem_st16(a_ring + (uint32_t)as * 64u + 32u, lo);
+            if (p.passes != 1) tmem_st16(a_ring + (uint32_t)as * 64u + 32u, lo);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -659,11 +669,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = ldc; p.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
     p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = cdiv(g.M, TC_BM); p.k_chunks = w.k_chunks;
     p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
+    p.passes = g.passes == 1 ? 1 : 3;
     p.dbg = g_tc_trace;
     p.cW = p.cH = p.cB = p.cHbox = p.cBbox = p.c_tiles_h = p.c_cpc = 0; p.a_bytes = TC_A_TILE_BYTES; p.seg_chunks = w.k_chunks;
     const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_EPI_WARPS * TC_SLAB_BYTES +
                       (p.resident ? w.k_chunks * w.BN * 256 : 0);
-    const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
+    const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * (p.passes == 1 ? 128 : 256));
     p.stages = std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / sb);
     AC_REQUIRE(p.stages >= 2, "gemm_tc: tile too large for shared memory (BN=%d)", w.BN);
     p.tmem_cols = 512;                                         // one CTA per SM owns the whole tensor memory
@@ -747,9 +758,10 @@ int conv3x3_tc(const Conv3Args& a, cudaStream_t st) {
     p.seg_chunks = TC_CONV_SEG_CHUNKS;
     p.resident = tc_resident(w.BN, w.n_tiles, w.k_chunks) ? 1 : 0;
     p.dbg = g_tc_trace;
+    p.passes = a.passes == 1 ? 1 : 3;
     const int fixed = 1024 + TC_BAR_BYTES + TC_EPI_WARPS * TC_MAX_BN_RESIDENT * 4 + TC_BM * w.BN * 4 +
                       (p.resident ? w.k_chunks * w.BN * 256 : 0);
-    const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * 256);
+    const int sb = TC_A_TILE_BYTES + (p.resident ? 0 : w.BN * (p.passes == 1 ? 128 : 256));   // tf32 mode streams hi only
     p.stages = std::min(TC_MAX_STAGES, (TC_SMEM_LIMIT - fixed) / sb);
     AC_REQUIRE(p.stages >= 2, "conv3x3_tc: tile too large for shared memory (BN=%d)", w.BN);
     p.tmem_cols = 512;
@@ -784,6 +796,11 @@ int conv3x3_tc(const Conv3Args& a, cudaStream_t st) {
 // w_dev is the PyTorch Conv2d weight [Cout, Cin, 3, 3]; scale/bias [Cout] nullable; act 0 none, 2 relu.
 extern "C" int ac_conv3x3(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev,
                           float* out_dev, int B, int H, int W, int Cin, int Cout, int act, void* stream) {
+    return ac_conv3x3_p(in_dev, w_dev, scale_dev, bias_dev, out_dev, B, H, W, Cin, Cout, act, 3, stream);
+}
+
+extern "C" int ac_conv3x3_p(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev,
+                            float* out_dev, int B, int H, int W, int Cin, int Cout, int act, int passes, void* stream) {
     using namespace ac;
     AC_REQUIRE(in_dev && w_dev && out_dev, "ac_conv3x3: null argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -795,7 +812,7 @@ extern "C" int ac_conv3x3(const float* in_dev, const float* w_dev, const float* 
     if (rc == AC_OK) rc = tc_pack_weight(perm, scale_dev, Cout, 9 * Cin, packed, st, &tw);
     if (rc == AC_OK) {
         Conv3Args a; a.in = in_dev; a.out = out_dev; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
-        a.bias = bias_dev; a.tw = &tw; a.act = act;
+        a.bias = bias_dev; a.tw = &tw; a.act = act; a.passes = passes;
         rc = conv3x3_tc(a, st);
     }
     cudaError_t e = cudaStreamSynchronize(st);

@@ -159,6 +159,15 @@ int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms_dev, int batch, int n_m
                  const int64_t* lens_dev, float* attn_emb_dev, float* fc_emb_dev,
                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Precision of the 3x3 convolutions: tf32_passes = 3 (default) issues every product as three TF32 MMAs (fp32-level accuracy:
+ * the mode of every fp32 parity claim), 1 uses plain TF32 operands (10-bit mantissa, fp32 accumulation) -- the tensor-core
+ * mode for the configurations BASELINE.json states in bf16 (training, temporal captioner). */
+int ac_cnn14_set_precision(ac_cnn14_t* net, int tf32_passes);
+int ac_sed_set_precision(ac_sed_t* net, int tf32_passes);
+/* ac_conv3x3 with the precision switch (diagnostic). */
+int ac_conv3x3_p(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev, float* out_dev,
+                 int B, int H, int W, int Cin, int Cout, int act, int tf32_passes, void* stream);
+
 /* Train-mode forward of the frozen encoder (BatchNorm folded = eval, `freeze_cnn_bn`), with the functional dropouts of
  * captioning/models/cnn_encoder.py:432-456 active: p_conv after each ConvBlock (reference 0.2), p_fc around fc1 (0.5).
  * Masks are a function of (seed, site, element index).  p_conv = p_fc = 0 is ac_cnn14_fwd. */

@@ -467,3 +467,43 @@ def test_training_reduces_the_loss_on_a_fixed_batch():
     assert all(np.isfinite(losses))
     assert losses[-1] < losses[0] - 0.5, losses
     assert step._step_dev.item() == 10
+
+
+def test_tf32_convolution_mode():
+    """The "tf32" precision mode of the Cnn14 convolutions (plain TF32 operands, fp32 accumulation; BASELINE configs[2..4]
+    are stated in bf16): one convolution vs float64 (<= 2e-3 of the output scale, against 2e-5 in the default 3xTF32
+    mode), the whole encoder vs its own fp32-mode output, and one training step's loss vs the fp32-mode step."""
+    from audiocaption_b200 import _lib
+    from audiocaption_b200.train_step import TrainStep
+    l = _lib.lib()
+    g = torch.Generator().manual_seed(0)
+    B, H, W, Cin, Cout = 2, 31, 8, 256, 128
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1).permute(0, 2, 3, 1)
+    errs = {}
+    for passes in (3, 1):
+        out = torch.empty(B, H, W, Cout, device=DEV)
+        _lib.check(l.ac_conv3x3_p(_lib.ptr(x.to(DEV)), _lib.ptr(w.to(DEV)), None, None, _lib.ptr(out), B, H, W, Cin, Cout, 0, passes,
+                                  None), "ac_conv3x3_p")
+        errs[passes] = ((out.cpu().double() - ref).abs().max() / ref.abs().max()).item()
+    assert errs[3] < 2e-5 and 2e-5 < errs[1] < 2e-3, errs
+    vocab = 4368
+    m = _no_dropout(_train_model(vocab))
+    wav, lens = cm.synth_wav(3, 64000, seed=21, ragged=True, varied=True, sample_rate=32000)
+    inp = {"wav": wav.to(DEV), "wav_len": lens, "specaug": False}
+    with torch.no_grad():
+        m.eval()
+        a = m.encoder.cnn(dict(inp))["attn_emb"]
+        m.encoder.cnn.conv_precision = "tf32"
+        b = m.encoder.cnn(dict(inp))["attn_emb"]
+    rel = ((a - b).abs().max() / a.abs().max()).item()
+    assert 1e-6 < rel < 1e-2, rel
+    cap, cap_len = ts.synth_captions(3, 7, vocab, seed=4)
+    losses = {}
+    for prec in ("fp32", "tf32"):
+        m2 = _no_dropout(_train_model(vocab))
+        m2.encoder.cnn.conv_precision = prec
+        step = TrainStep(m2, total_iters=1000, lr=1e-3, warmup_iters=10)
+        losses[prec] = step.step({"wav": wav, "wav_len": lens, "cap": cap, "cap_len": cap_len.numpy()}, coins=None)["loss"].item()
+    assert abs(losses["fp32"] - losses["tf32"]) < 2e-3 * abs(losses["fp32"]), losses
