@@ -318,6 +318,63 @@ def run_reference_train(args):
     }))
 
 
+# ====================================================================================================== other BASELINE configs
+def run_config1_leg(model, dev, timed):
+    """configs[0]: EffB2-Transformer greedy, batch = 1, one 10 s 32 kHz clip, the reference's demo.py path (demo.py:36
+    resamples to the model's 16 kHz first) -- here the resample runs on the device inside the timed call."""
+    import torch
+    from oracle import caption_model as cm
+    from audiocaption_b200.resample import resample
+    clips = [cm.synth_wav(1, 320000, seed=50 + i, sample_rate=32000)[0].pin_memory() for i in range(4)]
+    lens = torch.tensor([160000])
+
+    def one(i):
+        wav16 = resample(clips[i % 4].to(dev, non_blocking=True), 32000, 16000)
+        return model(wav16, lens, sample_method="greedy", max_length=MAX_LEN)           # host -> ... -> token ids on the host
+
+    ms, launches = timed(one, 30, 5)
+    return {"workload": "EffB2-Transformer greedy inference, batch=1, single 10 s 32 kHz clip, resample 32->16 kHz on the device "
+                        "(configs[0], demo.py path)", "latency_ms": ms, "value": 1000.0 / ms, "unit": "clips/s",
+            "launches_per_call": launches / 30, "h2d_bytes": 320000 * 4, "d2h_bytes": MAX_LEN * 8}
+
+
+def run_config5_leg(dev, rank, world, timed, steps=10):
+    """configs[4]: Cnn14Rnn-TempAttnGru (HF `Cnn14RnnTempAttnGruModel.forward`: log-mel -> SED tagger -> Cnn14 -> bi-GRU ->
+    GRU-attention beam search), beam 4, 16 clips per GPU (128 over 8 GPUs), sharded over clips, no collective."""
+    import torch
+    from oracle import bah_decoder as bd, caption_model as cm, cnn14 as oc, crnn, sed as sed_o
+    from audiocaption_b200.captioning.models import hf_wrapper as hw
+    m = hw.Cnn14RnnTempAttnGruModel().eval()
+    cnn_sd = oc.build_state_dict(3)
+    sd = {f"cap_model.encoder.cnn.{k}": v for k, v in cnn_sd.items()}
+    sd.update({f"cap_model.encoder.rnn.{k}": v for k, v in crnn.build_gru_state_dict(4).items()})
+    sd.update({f"cap_model.decoder.{k}": v for k, v in bd.build_state_dict(8).items()})
+    sd.update({f"sed_model.{k}": v for k, v in sed_o.build_state_dict(12).items()})
+    sd.update({k: v for k, v in cnn_sd.items() if k.startswith("melspec")})
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    B = 16
+    host = [cm.synth_wav(B, 320000, seed=200 + 10 * rank + i, sample_rate=32000)[0].pin_memory() for i in range(8)]   # 164 MB > L2
+    devb = [h.to(dev) for h in host]
+    lens = torch.full((B,), 320000, dtype=torch.long)
+    out = {}
+    for prec in ("fp32", "tf32"):
+        m.cap_model.encoder.cnn.conv_precision = prec
+        m.sed_model.conv_precision = prec
+        ms, launches = timed(lambda i: m(devb[i % 8], lens, sample_method="beam", beam_size=4, max_length=MAX_LEN), steps, 3)
+        ms_e2e, _ = timed(lambda i: m(host[i % 8], lens, sample_method="beam", beam_size=4, max_length=MAX_LEN), steps, 3)
+        out[prec] = {"value": world * B / (ms / 1000.0), "unit": "clips/s", "ms_per_step": ms,
+                     "e2e": {"value": world * B / (ms_e2e / 1000.0), "unit": "clips/s", "ms_per_step": ms_e2e,
+                             "h2d_bytes_per_step": B * 320000 * 4, "d2h_bytes_per_step": B * MAX_LEN * 8},
+                     "launches_per_step": launches / steps}
+    del m, devb
+    torch.cuda.empty_cache()
+    return {"workload": "Cnn14Rnn-TempGRU temporal model, beam 4, SED tagger on, 16 clips x 10 s @ 32 kHz per GPU "
+                        f"(configs[4]: 128 clips over 8 GPUs), {world} GPU(s), sharded over clips, no collective",
+            "n_gpus": world, "tf32": out["tf32"], "fp32": out["fp32"],
+            "note": "tf32 = plain-TF32 convolutions (configs[4] sits in BASELINE's bf16 group); fp32 = 3xTF32 everywhere"}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -418,7 +475,6 @@ def run_native(args):
     if sampler:
         sampler.start()
     ms_step, launches = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.summary() if sampler else None
     ms_e2e_sync, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     # pipelined end-to-end: same public API family (submit / result), uploads overlapped with the previous batch
     run_e2e_pipelined(max(3, args.warmup // 2), 0)
@@ -435,6 +491,7 @@ def run_native(args):
     # sustained figure: the same step looped for >= 2 s (the K-step region above is a ~0.1 s burst)
     n_sust = max(args.steps, int(2000.0 / max(ms_step, 0.1)) + 1)
     ms_sust, _ = timed(step_resident, n_sust, 0)
+    clocks = sampler.summary() if sampler else None        # sampled over the K-step region AND the 2 s sustained loop
 
     # like-for-like GPU baseline: the oracle port (stock PyTorch eager: cuFFT / cuDNN / cuBLAS kernels) on the same B200
     eager = None
@@ -461,12 +518,15 @@ def run_native(args):
         finally:
             orc.to("cpu")
 
-    # ---- second half of the metric: the training step (tokens/s), same process, same GPUs
-    train = None
+    # ---- the other BASELINE configs, same process, same GPUs: configs[0] (B = 1 demo path), configs[2..3] (training step,
+    # tokens/s: the second half of the metric), configs[4] (temporal captioner, beam 4)
+    train = config1 = config5 = None
     if not args.no_train:
+        config1 = run_config1_leg(model, dev, timed)
         del devb
         torch.cuda.empty_cache()
         train = run_train_leg(dev, rank, world, min(args.steps, 30), args.warmup, timed, lib)
+        config5 = run_config5_leg(dev, rank, world, timed)
         devb = [h.to(dev) for h in host]
 
     # ---- roofline leg: the same steps with every launch bracketed by CUDA events
@@ -516,6 +576,8 @@ def run_native(args):
                           "seconds": ms_sust * n_sust / 1000.0},
             "gpu_eager_baseline": eager,
             "train": train,
+            "config1_single_clip": config1,
+            "config5_tempgru_beam4": config5,
             "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",
                              "sample": f"8 of the {BATCH} clips per pass, {cpu_sample.last_reps} passes ({cpu_dt * cpu_sample.last_reps:.1f} s of CPU work), "
