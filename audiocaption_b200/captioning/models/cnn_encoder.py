@@ -271,7 +271,9 @@ class EfficientNetB2(nn.Module):
             fc_emb = torch.empty(B, self.fc_emb_size, device=wav.device, dtype=torch.float32)
             _lib.check(l.ac_masked_mean(_lib.ptr(attn_emb), _lib.ptr(len_dev), B, Tp, self.fc_emb_size,
                                         _lib.ptr(fc_emb), _lib.current_stream()), "ac_masked_mean")
-        return {"fc_emb": fc_emb, "attn_emb": attn_emb, "attn_emb_len": feat_length.cpu()}
+        # (lengths given as a CUDA tensor stay on the device: nothing here synchronises, so the call can be captured in a
+        #  CUDA graph -- Effb2TrmCaptioningModel.forward does that for repeated shapes)
+        return {"fc_emb": fc_emb, "attn_emb": attn_emb, "attn_emb_len": len_dev if feat_length.is_cuda else feat_length.cpu()}
 
 
 # ----------------------------------------------------------------------------- Cnn14

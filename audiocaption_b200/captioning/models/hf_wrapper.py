@@ -90,9 +90,82 @@ class Effb2TrmCaptioningModel(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    # ---- CUDA-graph replay of repeated call shapes ------------------------------------------------------------------
+    # A call enqueues ~100 kernels and encodes ~75 TMA descriptors (2 ms of host work at 64 clips, more than the device
+    # needs for one clip).  The second time a (batch, samples, decode settings) shape is seen the whole device side --
+    # log-mel, encoder, memory projections, decode -- is captured into a CUDA graph over static input / length / output
+    # buffers; later calls copy their input in, replay (one launch) and read the tokens out.
+    cuda_graphs = True
+
+    def reset_graphs(self):
+        """Drop every captured graph (they hold the packed-weight handles' device pointers): called automatically by
+        `load_state_dict` / `.to()` / `.cuda()`; call it yourself after editing parameters in place."""
+        self._graphs, self._graph_seen = {}, {}
+
+    def load_state_dict(self, *args, **kwargs):
+        self.reset_graphs()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.reset_graphs()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _graph_key(self, audio, sample_method, beam_size, max_length, temp):
+        if not hasattr(self, "_sentinels"):                  # a cheap guard against in-place weight edits between calls
+            ps = list(self.parameters())
+            self._sentinels = [ps[0], ps[len(ps) // 2], ps[-1]]
+        sig = tuple((p.data_ptr(), p._version) for p in self._sentinels)
+        return (tuple(audio.shape), sample_method, beam_size if sample_method == "beam" else 0, max_length, float(temp), sig)
+
+    def _graph_entry(self, audio, sample_method, beam_size, max_length, temp):
+        """None until a shape has been seen twice (or when graphs are off / the model is training)."""
+        if not self.cuda_graphs or self.training or audio.dim() != 2 or audio.shape[0] == 0:
+            return None
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._graph_seen = {}, {}
+        key = self._graph_key(audio, sample_method, beam_size, max_length, temp)
+        if key in self._graphs:
+            return self._graphs[key]
+        self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+        if self._graph_seen[key] < 2:
+            return None
+        if len(self._graphs) >= 8:                          # bounded cache (each entry pins its activations)
+            self._graphs.pop(next(iter(self._graphs)))
+        dev = self.device
+        B, N = audio.shape
+        wav_s = torch.zeros(B, N, device=dev, dtype=torch.float32)
+        len_s = torch.full((B,), N, device=dev, dtype=torch.int64)
+        input_dict = {"wav": wav_s, "wav_len": len_s, "specaug": False, "mode": "inference", "sample_method": sample_method,
+                      "max_length": max_length, "temp": temp, "need_logit": False, "_device_seq": True}
+        if sample_method == "beam":
+            input_dict["beam_size"] = beam_size
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                               # warm-up off the capture: workspaces, attributes, handles
+                self.model(dict(input_dict))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            seq_s = self.model(dict(input_dict))["seq"]
+        entry = {"graph": graph, "wav": wav_s, "len": len_s, "seq": seq_s}
+        self._graphs[key] = entry
+        return entry
+
+    def _replay(self, entry, wav_dev, audio_length):
+        """Enqueue one replay on the current stream; returns the static token buffer (valid until the next replay)."""
+        entry["wav"].copy_(wav_dev, non_blocking=True)
+        lens = torch.as_tensor(audio_length).to(torch.int64)
+        entry["len"].copy_(lens if lens.is_cuda else lens.pin_memory(), non_blocking=True)
+        entry["graph"].replay()
+        return entry["seq"]
+
     def forward(self, audio: torch.Tensor, audio_length: Union[List, np.ndarray, torch.Tensor],
                 sample_method: str = "beam", beam_size: int = 3, max_length: int = 20, temp: float = 1.0):
         """hf_wrapper.py:1162-1181: returns LongTensor[B, max_length] on the CPU."""
+        entry = self._graph_entry(audio, sample_method, beam_size, max_length, temp)
+        if entry is not None:
+            return self._replay(entry, audio, audio_length).cpu()
         input_dict = {
             "wav": audio.to(self.device, non_blocking=True),
             "wav_len": audio_length,
@@ -126,12 +199,16 @@ class Effb2TrmCaptioningModel(nn.Module):
                 wav = audio.to(dev, non_blocking=True)
             cur.wait_stream(self._copy_stream)
             wav.record_stream(cur)
-        input_dict = {"wav": wav, "wav_len": audio_length, "specaug": False, "mode": "inference",
-                      "sample_method": sample_method, "max_length": max_length, "temp": temp,
-                      "need_logit": False, "_device_seq": True}
-        if sample_method == "beam":
-            input_dict["beam_size"] = beam_size
-        seq_dev = self.model(input_dict)["seq"]
+        entry = self._graph_entry(audio, sample_method, beam_size, max_length, temp)
+        if entry is not None:
+            seq_dev = self._replay(entry, wav, audio_length)
+        else:
+            input_dict = {"wav": wav, "wav_len": audio_length, "specaug": False, "mode": "inference",
+                          "sample_method": sample_method, "max_length": max_length, "temp": temp,
+                          "need_logit": False, "_device_seq": True}
+            if sample_method == "beam":
+                input_dict["beam_size"] = beam_size
+            seq_dev = self.model(input_dict)["seq"]
         seq_host = torch.empty(seq_dev.shape, dtype=seq_dev.dtype, pin_memory=True)
         seq_host.copy_(seq_dev, non_blocking=True)
         done = torch.cuda.Event()

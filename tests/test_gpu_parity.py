@@ -854,3 +854,32 @@ def test_sed_short_clip_and_batch_independence():
         one = m.forward_prob(lms[1:2].to(DEV))["segmentwise_output"]
         assert torch.equal(one, out["segmentwise_output"][1:2])
         assert len(m(lms.to(DEV))) == 3
+
+
+def test_cuda_graph_replay_matches_eager_calls(mirror, golden_wav):
+    """`Effb2TrmCaptioningModel.forward` / `submit` replay a captured CUDA graph from the second call of a shape on: the
+    token ids must equal the eager (graphs off) result for every batch, also when the input changes between replays and
+    for a second shape / decode setting; loading weights drops the graphs."""
+    wav, lens = golden_wav
+    mirror.cuda_graphs = False
+    want_g = mirror(wav, lens, sample_method="greedy")
+    want_b = mirror(wav, lens, sample_method="beam", beam_size=3)
+    want_g2 = mirror(wav.flip(0), lens.flip(0), sample_method="greedy")
+    mirror.cuda_graphs = True
+    mirror.reset_graphs()
+    try:
+        for _ in range(3):                                  # call 1 eager, call 2 captures, call 3 replays
+            assert (mirror(wav, lens, sample_method="greedy") == want_g).all()
+        assert len(mirror._graphs) == 1
+        assert (mirror(wav.flip(0), lens.flip(0), sample_method="greedy") == want_g2).all()       # same shape, new input
+        for _ in range(3):
+            assert (mirror(wav, lens, sample_method="beam", beam_size=3) == want_b).all()
+        assert len(mirror._graphs) == 2
+        pin = wav.pin_memory()
+        pend = [mirror.submit(pin, lens, sample_method="greedy") for _ in range(3)]
+        assert all((p.result() == want_g).all() for p in pend)
+        mirror.load_state_dict(mirror.state_dict())
+        assert len(mirror._graphs) == 0
+        assert (mirror(wav, lens, sample_method="greedy") == want_g).all()
+    finally:
+        mirror.reset_graphs()
