@@ -60,8 +60,10 @@ class CaptionModel(nn.Module, CaptionMetaMixin):
                 forward_dict[key] = input_dict[key] if key in input_dict else default_args[key]
             if forward_dict["sample_method"] == "beam":
                 forward_dict["beam_size"] = input_dict.get("beam_size", 3)
-                if input_dict.get("n_best", False):
-                    raise NotImplementedError("n_best beam output is not built")
+                forward_dict["n_best"] = input_dict.get("n_best", False)
+                forward_dict["n_best_size"] = input_dict.get("n_best_size", forward_dict["beam_size"])
+            elif forward_dict["sample_method"] == "dbs":
+                raise NotImplementedError("diverse beam search (base.py:363-471) is not built on the B200 path")
             for key in ("need_logit", "_device_seq"):      # B200-side options (not in the reference)
                 if key in input_dict:
                     forward_dict[key] = input_dict[key]
@@ -89,12 +91,37 @@ class CaptionModel(nn.Module, CaptionMetaMixin):
         pass
 
     def inference_forward(self, input_dict):
-        method = input_dict["sample_method"]
-        if method == "beam":
+        if input_dict["sample_method"] == "beam":
             return self.beam_search(input_dict)
+        return self.stepwise_forward(input_dict)          # greedy (one fused launch) or a sampling method (step loop)
+
+    def sample_next_word(self, logit, method, temp):
+        """base.py:214-252 on device tensors: greedy arg-max, Gumbel-max, top-k ("top5"), nucleus ("top0.9") and plain
+        temperature sampling.  logit [N, V] -> {"word" [N] i64, "probs" [N] log-probability of the drawn word}."""
+        logprob = torch.log_softmax(logit, dim=1)
         if method == "greedy":
-            return self.stepwise_forward(input_dict)
-        raise NotImplementedError(f"sample_method {method!r} is not built (greedy and beam are)")
+            sampled_logprob, word = torch.max(logprob, 1)
+            return {"word": word, "probs": sampled_logprob}
+        if method == "gumbel":
+            u = torch.rand_like(logprob)
+            y = logprob - torch.log(-torch.log(u + 1e-20) + 1e-20)
+            word = torch.log_softmax(y / temp, dim=-1).argmax(1)
+            return {"word": word, "probs": logprob.gather(1, word.unsqueeze(-1)).squeeze(1)}
+        logprob = logprob / temp
+        if method.startswith("top"):
+            top_num = float(method[3:])
+            if 0 < top_num < 1:                        # nucleus: the shortest prefix of the sorted distribution reaching top_num
+                sorted_probs, sorted_indices = torch.sort(torch.softmax(logit, dim=1), descending=True, dim=1)
+                keep = sorted_probs.cumsum(1) < top_num
+                keep = torch.cat([torch.ones_like(keep[:, :1]), keep[:, :-1]], 1)
+                sorted_probs = sorted_probs * keep.to(sorted_probs)
+                sorted_probs = sorted_probs / sorted_probs.sum(1, keepdim=True)
+                logprob = logprob.scatter(1, sorted_indices, sorted_probs.log())
+            else:                                      # top-k
+                topk, indices = torch.topk(logprob, int(top_num), dim=1)
+                logprob = torch.full_like(logprob, float("-inf")).scatter(1, indices, topk)
+        word = torch.multinomial(torch.softmax(logprob, dim=1), 1).squeeze(1)
+        return {"word": word, "probs": logprob.gather(1, word.unsqueeze(-1)).squeeze(1)}
 
     def stepwise_forward(self, input_dict):
         raise NotImplementedError

@@ -383,6 +383,9 @@ class TemporalSeq2SeqAttnModel(CaptionModel):
         self.inference_forward_keys = ["sample_method", "max_length", "temp", "temporal_tag"]
 
     def stepwise_forward(self, input_dict):
+        if input_dict.get("sample_method", "greedy") != "greedy":
+            raise NotImplementedError("the GRU-attention captioner decodes with greedy or beam search on the B200 path "
+                                      f"(sample_method {input_dict['sample_method']!r} is not built)")
         out = self.decoder.greedy(input_dict["fc_emb"], input_dict["attn_emb"], input_dict["attn_emb_len"],
                                   input_dict["temporal_tag"], input_dict["max_length"], self.start_idx, self.end_idx,
                                   need_logit=input_dict.get("need_logit", True))
@@ -394,6 +397,8 @@ class TemporalSeq2SeqAttnModel(CaptionModel):
         return out
 
     def beam_search(self, input_dict):
+        if input_dict.get("n_best", False):
+            raise NotImplementedError("n_best beam output is not built for the GRU-attention captioner")
         out = self.decoder.beam_search(input_dict["fc_emb"], input_dict["attn_emb"], input_dict["attn_emb_len"],
                                        input_dict["temporal_tag"], input_dict["max_length"], input_dict["beam_size"],
                                        input_dict["temp"], self.start_idx, self.end_idx)

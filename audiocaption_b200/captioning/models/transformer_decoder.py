@@ -297,10 +297,12 @@ class DecoderTrainEngine:
         dec = self.dec
         dev = attn_emb.device
         B, T, _ = attn_emb.shape
-        L = words.shape[1]
+        R, L = words.shape                    # R token rows: B, or k * B (row r attends to the memory of clip r % B: beams)
         seed = self.new_seed() if seed is None else seed
         sampled = [] if coins is None else [t for t, c in enumerate(coins) if not c]
-        n_seq = 2 * B if sampled else B
+        if R % B != 0 or (sampled and R != B):
+            raise _lib.AudioCaptionB200Error(f"DecoderTrainEngine: {R} token rows for {B} clips")
+        n_seq = 2 * B if sampled else R
         with torch.cuda.device(dev):
             h = self.handle(grads)
             st = _lib.current_stream()
@@ -311,14 +313,14 @@ class DecoderTrainEngine:
             _lib.check(l.ac_trm_train_memory_fwd(h, _lib.ptr(attn_emb), B, T, n_seq, L, p_drop, seed, _lib.ptr(ws), nbytes, st),
                        "ac_trm_train_memory_fwd")
             word_rows = torch.full((n_seq, L), pad_idx, dtype=torch.int64, device=dev)
-            word_rows[:B] = words
+            word_rows[:R] = words
             pad_rows = torch.ones(n_seq, L, dtype=torch.uint8, device=dev)
-            pad_rows[:B] = (words == pad_idx) if key_pad is None else key_pad
-            _lib.check(l.ac_trm_train_seq_fwd(h, _lib.ptr(word_rows), _lib.ptr(pad_rows), 0, B, n_seq, L, _lib.ptr(attn_len_dev),
+            pad_rows[:R] = (words == pad_idx) if key_pad is None else key_pad
+            _lib.check(l.ac_trm_train_seq_fwd(h, _lib.ptr(word_rows), _lib.ptr(pad_rows), 0, R, n_seq, L, _lib.ptr(attn_len_dev),
                                               B, T, p_drop, seed, _lib.ptr(ws), nbytes, st), "ac_trm_train_seq_fwd")
             rows = None
-            logits = torch.empty(B * L, Vp, dtype=torch.float32, device=dev)
-            embed = torch.empty(B, L, dec.d_model, dtype=torch.float32, device=dev)
+            logits = torch.empty(R * L, Vp, dtype=torch.float32, device=dev)
+            embed = torch.empty(R, L, dec.d_model, dtype=torch.float32, device=dev)
             if sampled:
                 t_star = sampled[-1]
                 word_rows[B:, 0] = start_idx
@@ -347,15 +349,15 @@ class DecoderTrainEngine:
                 sel = torch.arange(B * L, dtype=torch.int32).view(B, L)
                 sel[:, sampled] += B * L
                 rows = to_device_async(sel.reshape(-1).contiguous(), dev)
-            _lib.check(l.ac_trm_train_logits(h, _lib.ptr(rows), B * L, n_seq, L, B, T, _lib.ptr(logits), _lib.ptr(embed), 1,
+            _lib.check(l.ac_trm_train_logits(h, _lib.ptr(rows), R * L, n_seq, L, B, T, _lib.ptr(logits), _lib.ptr(embed), 1,
                                              _lib.ptr(ws), nbytes, st), "ac_trm_train_logits")
-            seq = torch.empty(B, L, dtype=torch.int64, device=dev)
-            logprob = torch.empty(B, L, dtype=torch.float32, device=dev)
-            _lib.check(l.ac_argmax_rows(_lib.ptr(logits), Vp, B * L, dec.vocab_size, _lib.ptr(seq), _lib.ptr(logprob), st),
+            seq = torch.empty(R, L, dtype=torch.int64, device=dev)
+            logprob = torch.empty(R, L, dtype=torch.float32, device=dev)
+            _lib.check(l.ac_argmax_rows(_lib.ptr(logits), Vp, R * L, dec.vocab_size, _lib.ptr(seq), _lib.ptr(logprob), st),
                        "ac_argmax_rows")
         self._ctx = dict(attn_emb=attn_emb, attn_len=attn_len_dev, words=word_rows, pads=pad_rows, rows=rows, n_seq=n_seq,
-                         B=B, T=T, L=L, p_drop=p_drop, seed=seed, nbytes=nbytes, Vp=Vp)
-        logit3 = logits.view(B, L, Vp)
+                         B=B, T=T, L=L, R=R, p_drop=p_drop, seed=seed, nbytes=nbytes, Vp=Vp)
+        logit3 = logits.view(R, L, Vp)
         return {"logit": logit3 if Vp == dec.vocab_size else logit3[:, :, :dec.vocab_size], "logit_padded": logit3,
                 "embed": embed, "seq": seq, "sampled_logprob": logprob}
 
@@ -370,7 +372,7 @@ class DecoderTrainEngine:
         with torch.cuda.device(dev):
             ws = self._ws.get(c["nbytes"], dev)
             dattn = torch.empty_like(c["attn_emb"]) if need_dattn else None
-            _lib.check(l.ac_trm_train_bwd(self._handle, _lib.ptr(dlogits), _lib.ptr(c["rows"]), c["B"] * c["L"],
+            _lib.check(l.ac_trm_train_bwd(self._handle, _lib.ptr(dlogits), _lib.ptr(c["rows"]), c["R"] * c["L"],
                                           _lib.ptr(c["words"]), _lib.ptr(c["pads"]), c["n_seq"], c["n_seq"], c["L"],
                                           _lib.ptr(c["attn_emb"]), _lib.ptr(c["attn_len"]), c["B"], c["T"], c["p_drop"],
                                           c["seed"], _lib.ptr(dattn), _lib.ptr(ws), c["nbytes"], _lib.current_stream()),

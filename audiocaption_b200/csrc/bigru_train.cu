@@ -156,6 +156,7 @@ __global__ void drop_mul_kernel(const float* __restrict__ src, float* __restrict
 struct ac_bigru_train {
     int input_dim = 0, layers = 0;
     bool need_dx0 = false;            // also pack layer 0's W_ih^T (gradient w.r.t. the encoder input)
+    ac::TcPackJob* jobs_dev = nullptr; int n_jobs = 0; long long job_items = 0;
     std::vector<ac::GruTrainLayer> layer;
     float* blob = nullptr;
 };
@@ -221,6 +222,14 @@ int ac_bigru_train_create(const float* const* p, float* const* g, const int64_t*
     float* cur = h->blob;
     for (int l = 0; l < num_layers; ++l)
         for (int d = 0; d < 2; ++d) { h->layer[l].ih[d].pk = cur; cur += linear_pack_floats(3 * H, h->layer[l].din, l > 0 || h->need_dx0); }
+    std::vector<TcPackJob> jobs;
+    long long first = 0;
+    for (int l = 0; l < num_layers; ++l)
+        for (int d = 0; d < 2; ++d) first = linear_plan(h->layer[l].ih[d], l > 0 || h->need_dx0, first, jobs);
+    h->n_jobs = (int)jobs.size(); h->job_items = first;
+    rc = check_cuda(cudaMalloc(&h->jobs_dev, jobs.size() * sizeof(TcPackJob)), "ac_bigru_train_create: cudaMalloc jobs");
+    if (rc == AC_OK) rc = check_cuda(cudaMemcpy(h->jobs_dev, jobs.data(), jobs.size() * sizeof(TcPackJob), cudaMemcpyHostToDevice), "jobs upload");
+    if (rc != AC_OK) { cudaFree(h->blob); cudaFree(h->jobs_dev); delete h; return rc; }
     *out = h;
     return AC_OK;
 }
@@ -228,6 +237,7 @@ int ac_bigru_train_create(const float* const* p, float* const* g, const int64_t*
 void ac_bigru_train_destroy(ac_bigru_train_t* h) {
     if (!h) return;
     cudaFree(h->blob);
+    cudaFree(h->jobs_dev);
     delete h;
 }
 
@@ -239,9 +249,7 @@ size_t ac_bigru_train_workspace_bytes(const ac_bigru_train_t* h, int batch, int 
 int ac_bigru_train_refresh(ac_bigru_train_t* h, void* stream) {
     using namespace ac;
     AC_REQUIRE(h, "ac_bigru_train_refresh: null handle");
-    for (int l = 0; l < h->layers; ++l)
-        for (int d = 0; d < 2; ++d) { int rc = linear_refresh(h->layer[l].ih[d], l > 0 || h->need_dx0, (cudaStream_t)stream); if (rc) return rc; }
-    return AC_OK;
+    return tc_pack_multi(h->jobs_dev, h->n_jobs, h->job_items, (cudaStream_t)stream);
 }
 
 // x_dev [batch, T, input_dim] (T = max(lens): the frozen CNN's frames), lens_dev [batch] int64 -> out_dev [batch, T, 512].

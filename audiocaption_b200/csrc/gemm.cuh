@@ -35,6 +35,14 @@ int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, flo
 int tc_pack_weight_strided(const float* W_dev, const float* scale_dev, int N, int K, int64_t sn, int64_t sk, float* dst_dev,
                            cudaStream_t st, TcWeight* out);
 
+// Batched packing: a static table of jobs (one per matrix image) lives in device memory; tc_pack_multi re-packs them all
+// in ONE launch.  tc_pack_plan fills a job + its TcWeight and returns the job's item count (float4 units); `first` is the
+// running sum of the counts of the jobs before it.
+struct TcPackJob { const float* W; float* dst; int N, K, BN, n_tiles, k_chunks; long long sn, sk, first; };
+long long tc_pack_plan(const float* W, int N, int K, long long sn, long long sk, float* dst, long long first, TcPackJob* job,
+                       TcWeight* out);
+int tc_pack_multi(const TcPackJob* jobs_dev, int n_jobs, long long total_items, cudaStream_t st);
+
 struct GemmArgs {
     const float* A; const float* W; float* C;
     int M, N, K;

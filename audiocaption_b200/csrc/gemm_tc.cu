@@ -526,6 +526,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks);
+
 // ------------------------------------------------------------------------------------ weight packing
 // One thread per packed float4: [n_tile][k_chunk][hi|lo][row BN][16-byte chunk 8 (swizzled)].
 __global__ void tc_pack_kernel(const float* __restrict__ W, const float* __restrict__ scale, float* __restrict__ dst,
@@ -553,6 +555,55 @@ __global__ void tc_pack_kernel(const float* __restrict__ W, const float* __restr
         o[e] = hl == 0 ? h : v[e] - h;
     }
     reinterpret_cast<float4*>(dst)[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// Many matrices in ONE launch (the training path re-packs ~70 weight images per step): job j covers packed float4 items
+// [first_j, first_{j+1}); a thread finds its job by binary search in the (device-resident, static) job table.
+__global__ void tc_pack_multi_kernel(const TcPackJob* __restrict__ jobs, int n_jobs, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const TcPackJob j = jobs[lo];
+    long long r = i - j.first;
+    const int pc = (int)(r % 8); r /= 8;
+    const int row = (int)(r % j.BN); r /= j.BN;
+    const int hl = (int)(r % 2); r /= 2;
+    const int kc = (int)(r % j.k_chunks);
+    const int n_t = (int)(r / j.k_chunks);
+    const int lc = pc ^ (row & 7);
+    const int n = n_t * j.BN + row, k = kc * TC_BK + lc * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < j.N) {
+        for (int e = 0; e < 4; ++e)
+            if (k + e < j.K) v[e] = j.W[(size_t)n * j.sn + (size_t)(k + e) * j.sk];
+    }
+    float o[4];
+    for (int e = 0; e < 4; ++e) {
+        const float h = ptx::tf32_rna(v[e]);
+        o[e] = hl == 0 ? h : v[e] - h;
+    }
+    reinterpret_cast<float4*>(j.dst)[i - j.first] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+long long tc_pack_plan(const float* W, int N, int K, long long sn, long long sk, float* dst, long long first, TcPackJob* job,
+                       TcWeight* out) {
+    int BN, n_tiles, k_chunks;
+    tc_tiling(N, K, BN, n_tiles, k_chunks);
+    job->W = W; job->dst = dst; job->N = N; job->K = K; job->BN = BN; job->n_tiles = n_tiles; job->k_chunks = k_chunks;
+    job->sn = sn; job->sk = sk; job->first = first;
+    out->packed = dst; out->scale = nullptr; out->N = N; out->K = K; out->BN = BN; out->n_tiles = n_tiles; out->k_chunks = k_chunks;
+    return (long long)n_tiles * k_chunks * 2 * BN * 8;
+}
+
+int tc_pack_multi(const TcPackJob* jobs_dev, int n_jobs, long long total_items, cudaStream_t st) {
+    if (n_jobs <= 0 || total_items <= 0) return AC_OK;
+    tc_pack_multi_kernel<<<(unsigned)cdiv64(total_items, 256), 256, 0, st>>>(jobs_dev, n_jobs, total_items);
+    AC_LAUNCHED("tc_pack_multi_kernel");
+    return AC_OK;
 }
 
 // PyTorch Conv2d weight [Cout, Cin, 3, 3] -> [Cout, 9 * Cin] with k = (ky*3+kx) * Cin + c (tap-major: a 32-wide

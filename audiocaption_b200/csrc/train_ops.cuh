@@ -3,6 +3,8 @@
 // Used by trm_train.cu (Transformer decoder) and bigru_train.cu (bi-GRU encoder); the loss and the optimizer live in
 // train_ops.cu as well.
 #pragma once
+#include <vector>
+
 #include "gemm.cuh"
 
 namespace ac {
@@ -39,6 +41,8 @@ struct Linear {
 };
 size_t linear_pack_floats(int N, int K, bool need_dx);     // storage `Linear::pk` (+ pkT) needs
 int linear_refresh(Linear& l, bool need_dx, cudaStream_t st);
+// Batched variant: plan every layer once (handle creation), upload the job table, then ONE tc_pack_multi launch per step.
+long long linear_plan(Linear& l, bool need_dx, long long first, std::vector<TcPackJob>& jobs);
 // Y [M, ldy] = act(X [M, K] W^T + b) (+ R);  act as in gemm.cuh
 int linear_fwd(const Linear& l, const float* X, int M, float* Y, int ldy, int act, const float* R, cudaStream_t st);
 // Gradients of y = x W^T + b given dY [M, N] (row stride ldy):

@@ -61,6 +61,7 @@ struct ac_trm_train {
     const float* ap_lnw = nullptr; const float* ap_lnb = nullptr; float* dap_lnw = nullptr; float* dap_lnb = nullptr;
     float* cls_stage = nullptr; float* dcls_stage = nullptr;     // [Vp, D] when V % 8 != 0
     float* blob = nullptr;
+    ac::TcPackJob* jobs_dev = nullptr; int n_jobs = 0; long long job_items = 0;   // one batched re-pack launch per step
 };
 
 namespace ac {
@@ -183,6 +184,24 @@ int ac_trm_train_create(const float* const* p, float* const* g, const int64_t* n
         h->dcls_stage = cur; cur += align_up((size_t)h->Vp * D, 32);
         h->cls.W = h->cls_stage; h->cls.dW = h->dcls_w ? h->dcls_stage : nullptr;
     }
+    // the static job table of ac_trm_train_refresh: every weight image (forward and transposed) of every Linear
+    std::vector<TcPackJob> jobs;
+    long long first = 0;
+    for (auto& y : h->layer) {
+        Linear* ls[7] = {&y.sa_in, &y.sa_out, &y.ca_q, &y.ca_kv, &y.ca_out, &y.l1, &y.l2};
+        for (Linear* l : ls) first = linear_plan(*l, true, first, jobs);
+    }
+    first = linear_plan(h->ap0, false, first, jobs);
+    {
+        TcPackJob j;
+        first += tc_pack_plan(h->ap0.W, E, D, 1, E, h->ap0.pkT, first, &j, &h->ap0.twT);
+        jobs.push_back(j);
+    }
+    first = linear_plan(h->cls, true, first, jobs);
+    h->n_jobs = (int)jobs.size(); h->job_items = first;
+    rc = check_cuda(cudaMalloc(&h->jobs_dev, jobs.size() * sizeof(TcPackJob)), "ac_trm_train_create: cudaMalloc jobs");
+    if (rc == AC_OK) rc = check_cuda(cudaMemcpy(h->jobs_dev, jobs.data(), jobs.size() * sizeof(TcPackJob), cudaMemcpyHostToDevice), "jobs upload");
+    if (rc != AC_OK) { cudaFree(h->blob); cudaFree(h->jobs_dev); delete h; return rc; }
     *out = h;
     return AC_OK;
 }
@@ -190,6 +209,7 @@ int ac_trm_train_create(const float* const* p, float* const* g, const int64_t* n
 void ac_trm_train_destroy(ac_trm_train_t* h) {
     if (!h) return;
     cudaFree(h->blob);
+    cudaFree(h->jobs_dev);
     delete h;
 }
 
@@ -203,19 +223,12 @@ int ac_trm_train_refresh(ac_trm_train_t* h, void* stream) {
     using namespace ac;
     AC_REQUIRE(h, "ac_trm_train_refresh: null handle");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = AC_OK;
-    for (auto& y : h->layer) {
-        Linear* ls[7] = {&y.sa_in, &y.sa_out, &y.ca_q, &y.ca_kv, &y.ca_out, &y.l1, &y.l2};
-        for (Linear* l : ls) { rc = linear_refresh(*l, true, st); if (rc) return rc; }
-    }
-    rc = linear_refresh(h->ap0, false, st); if (rc) return rc;
-    rc = tc_pack_weight_strided(h->ap0.W, nullptr, h->E, h->D, 1, h->E, h->ap0.pkT, st, &h->ap0.twT); if (rc) return rc;
     if (h->cls_stage != nullptr) {
         const int64_t n = (int64_t)h->Vp * h->D;
         pad_rows_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(h->cls_w, h->cls_stage, h->V, h->Vp, h->D);
         AC_LAUNCHED("pad_rows_kernel");
     }
-    return linear_refresh(h->cls, true, st);
+    return tc_pack_multi(h->jobs_dev, h->n_jobs, h->job_items, st);       // all ~32 weight images in one launch
 }
 
 // Memory side: attn_emb_dev [B, T, E] -> projected memory and every layer's cross-attention keys / values (kept in the

@@ -96,12 +96,14 @@ def kernel_families(report, n_steps, batch):
 
 def measured_traffic(family):
     """dram__bytes_read.sum + dram__bytes_write.sum of the family's launches in one step, from the committed ncu
-    capture (profiles/r1_dram_traffic.json, produced by scripts/gpu_profile.sh); None when absent."""
-    p = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    try:
-        d = json.load(open(p))
-        f = d["families"][family]
-        return {"bytes_per_step": f["dram_bytes"], "launches_per_step": f["launches"],
-                "bytes_per_launch": f["dram_bytes"] / max(f["launches"], 1), "source": d.get("source", p)}
-    except Exception:
-        return None
+    capture (profiles/r2_dram_traffic.json, produced by scripts/gpu_profile_r2.sh + scripts/summarize_profiles_r2.py); None when absent."""
+    for name in ("r2_dram_traffic.json", "r1_dram_traffic.json"):          # newest committed capture first
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            d = json.load(open(p))
+            f = d["families"][family]
+            return {"bytes_per_step": f["dram_bytes"], "launches_per_step": f["launches"],
+                    "bytes_per_launch": f["dram_bytes"] / max(f["launches"], 1), "source": f"profiles/{name}: " + d.get("source", "")}
+        except Exception:
+            continue
+    return None

@@ -171,12 +171,14 @@ def greedy_decode(decoder, attn_emb, attn_emb_len, max_length=20):
     return {"seq": seq, "logit": logit, "sampled_logprob": logprob, "embed": embed, "steps": steps}
 
 
-def beam_search(decoder, attn_emb, attn_emb_len, beam_size=3, max_length=20, temp=1.0):
+def beam_search(decoder, attn_emb, attn_emb_len, beam_size=3, max_length=20, temp=1.0, n_best_size=None):
     """Per-sample beam search with the reference's exact bookkeeping: double log-softmax,
     step-0 top-k from row 0, finished beams stay in the beam with a -1000 penalty, stop on
     ``len(done) == beam_size`` (equality), score = logprob / (t+1), stable best-first sort."""
     B, V = attn_emb.size(0), decoder.vocab_size
     seq_out = torch.full((B, max_length), END, dtype=torch.long)
+    nbest_out = torch.full((B, n_best_size or 1, max_length), END, dtype=torch.long)     # base.py:259-263 (`n_best`)
+    nbest_score = torch.full((B, n_best_size or 1), float("-inf"))
     for i in range(B):
         mem = attn_emb[i].unsqueeze(0).repeat(beam_size, 1, 1)
         mlen = torch.as_tensor(attn_emb_len)[i].repeat(beam_size)
@@ -204,9 +206,48 @@ def beam_search(decoder, attn_emb, attn_emb_len, beam_size=3, max_length=20, tem
             scores[is_end] -= 1000
             if len(done) == beam_size:
                 break
-        best = sorted(done, key=lambda x: -x["score"])[0]["seq"]
+        ranked = sorted(done, key=lambda x: -x["score"])
+        best = ranked[0]["seq"]
         seq_out[i, :len(best)] = best
-    return {"seq": seq_out}
+        for j, d in enumerate(ranked[:n_best_size or 1]):                # base.py:351-358
+            nbest_out[i, j, :len(d["seq"])] = d["seq"]
+            nbest_score[i, j] = d["score"]
+    out = {"seq": seq_out}
+    if n_best_size:
+        out["n_best_seq"], out["n_best_score"] = nbest_out, nbest_score
+    return out
+
+
+def sample_next_word(logit, method, temp, generator=None):
+    """base.py:214-252.  Returns (word [N], sampled_logprob [N]).  `generator` seeds the random draws (the reference uses
+    torch's global generator)."""
+    logprob = torch.log_softmax(logit, dim=1)
+    if method == "greedy":
+        lp, word = torch.max(logprob, 1)
+        return word, lp
+    if method == "gumbel":
+        u = torch.rand(logprob.shape, generator=generator)
+        y = logprob - torch.log(-torch.log(u + 1e-20) + 1e-20)
+        word = torch.log_softmax(y / temp, dim=-1).argmax(1)
+        return word, logprob.gather(1, word.unsqueeze(-1)).squeeze(1)
+    logprob = logprob / temp
+    if method.startswith("top"):
+        top_num = float(method[3:])
+        if 0 < top_num < 1:                                   # nucleus: keep the smallest prefix reaching top_num
+            probs = torch.softmax(logit, dim=1)
+            sp, si = torch.sort(probs, descending=True, dim=1)
+            keep = sp.cumsum(1) < top_num
+            keep = torch.cat([torch.ones_like(keep[:, :1]), keep[:, :-1]], 1)
+            sp = sp * keep.to(sp)
+            sp = sp / sp.sum(1, keepdim=True)
+            logprob = logprob.scatter(1, si, sp.log())
+        else:                                                 # top-k
+            k = int(top_num)
+            tk, ti = torch.topk(logprob, k, dim=1)
+            logprob = torch.full_like(logprob, float("-inf")).scatter(1, ti, tk)
+    p = torch.softmax(logprob, dim=1)
+    word = torch.multinomial(p, 1, generator=generator).squeeze(1)
+    return word, logprob.gather(1, word.unsqueeze(-1)).squeeze(1)
 
 
 # --------------------------------------------------------------------------- full model

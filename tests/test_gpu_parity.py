@@ -883,3 +883,48 @@ def test_cuda_graph_replay_matches_eager_calls(mirror, golden_wav):
         assert (mirror(wav, lens, sample_method="greedy") == want_g).all()
     finally:
         mirror.reset_graphs()
+
+
+# ------------------------------------------------------------------ samplers and n-best beams
+def test_sampling_methods_and_n_best(crnn_mirror):
+    """`sample_method` in {topK, topP, gumbel, temperature} (base.py:219-249) and `n_best` beam search (base.py:327-358)
+    through `TransformerModel.forward`: the deterministic corners equal greedy (top-1, a vanishing nucleus), the n-best
+    lists equal the oracle's (and their first entry the single-launch beam kernel's) on perturbation-stable rows, and the
+    stochastic samplers are seeded, stay inside their support and report the log-probability of the word they drew."""
+    from oracle import cnn14 as oc, crnn
+    m, g = crnn_mirror
+    wav, lens = cm.synth_wav(int(g["batch"]), int(g["n_samples"]), seed=int(g["wav_seed"]), ragged=True, varied=True,
+                             sample_rate=32000)
+    base = {"wav": wav.to(DEV), "wav_len": lens, "specaug": False, "mode": "inference", "temp": 1.0, "max_length": 12}
+    with torch.no_grad():
+        greedy = m(dict(base, sample_method="greedy"))
+        for method in ("top1", "top0.00001"):
+            out = m(dict(base, sample_method=method))
+            assert (out["seq"] == greedy["seq"]).all(), method
+            assert (out["sampled_logprob"] - greedy["sampled_logprob"]).abs().max() < 1e-4 or method != "top1"
+        torch.manual_seed(5)
+        a = m(dict(base, sample_method="top5", temp=0.8))
+        torch.manual_seed(5)
+        b = m(dict(base, sample_method="top5", temp=0.8))
+        assert (a["seq"] == b["seq"]).all() and a["seq"].shape == (int(g["batch"]), 12) and not a["seq"].is_cuda
+        # every drawn word is among the 5 most likely words of its step
+        top5 = a["logit"].topk(5, dim=-1).indices.cpu()
+        steps = (a["seq"] != cm.END).long().sum(1).clamp(max=11) + 1
+        for bi in range(a["seq"].shape[0]):
+            for t in range(int(steps[bi])):
+                if t < a["seq"].shape[1] and (t == 0 or a["seq"][bi, t - 1] != cm.END):
+                    assert a["seq"][bi, t] in top5[bi, t], (bi, t)
+        for method in ("gumbel", "top0.9", "sample"):
+            out = m(dict(base, sample_method=method, temp=0.7))
+            assert out["seq"].shape == (int(g["batch"]), 12) and torch.isfinite(out["sampled_logprob"]).all()
+        nb = m(dict(base, sample_method="beam", beam_size=3, n_best=True, n_best_size=2, max_length=20))
+        b3 = m(dict(base, sample_method="beam", beam_size=3, max_length=20))
+    assert nb["seq"].shape == (int(g["batch"]), 2, 20)
+    dec = crnn.build_decoder(int(g["dec_seed"]))
+    mem, mlen = torch.as_tensor(g["attn_emb"]), torch.as_tensor(g["attn_emb_len"])
+    with torch.no_grad():
+        fn = lambda a: cm.beam_search(dec, a, mlen, 3, 20, 1.0, n_best_size=2)["n_best_seq"].reshape(a.shape[0], -1)
+        ref, stable = _stable_rows(fn, mem)
+    assert stable.any()
+    assert (nb["seq"].reshape(len(stable), -1)[stable] == ref[stable]).all()
+    assert (nb["seq"][:, 0][stable] == b3["seq"][stable]).all()
