@@ -121,6 +121,7 @@ _SIGS = {
                                    C.c_void_p]),
     "ac_ls_ce_fwd_bwd": (C.c_int, [c_f32p, C.c_int, c_i64p, C.c_int, c_i64p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                    c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ac_specaug_apply": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ac_argmax_rows": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_i64p, c_f32p, C.c_void_p]),
     "ac_clip_adam_workspace_bytes": (C.c_size_t, []),
     "ac_clip_adam": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

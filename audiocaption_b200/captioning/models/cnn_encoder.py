@@ -276,6 +276,24 @@ class EfficientNetB2(nn.Module):
         return {"fc_emb": fc_emb, "attn_emb": attn_emb, "attn_emb_len": len_dev if feat_length.is_cuda else feat_length.cpu()}
 
 
+def draw_specaug_stripes(batch, n_frames, n_mels, time_drop_width=64, time_stripes_num=2, freq_drop_width=8,
+                         freq_stripes_num=2):
+    """Stripe positions of torchlibrosa's `SpecAugmentation` (`DropStripes`: per clip and stripe, width ~ U{0..drop_width-1},
+    begin ~ U{0..total - width - 1}; all time stripes of the batch first, then all mel stripes), drawn from torch's global
+    CPU generator in that order.  torchlibrosa is a third-party dependency absent from this image: its published algorithm
+    is restated, unpinned.  Returns int32 [batch, 2 * stripes, 2] (begin, width): frame ranges first, then mel ranges."""
+    assert time_stripes_num == freq_stripes_num, "one stripe count for both axes"
+    ns = time_stripes_num
+    out = torch.zeros(batch, 2 * ns, 2, dtype=torch.int32)
+    for axis, (total, width) in enumerate(((n_frames, time_drop_width), (n_mels, freq_drop_width))):
+        for b in range(batch):
+            for k in range(ns):
+                distance = int(torch.randint(low=0, high=width, size=(1,))[0])
+                bgn = int(torch.randint(low=0, high=total - distance, size=(1,))[0])
+                out[b, axis * ns + k, 0], out[b, axis * ns + k, 1] = bgn, distance
+    return out
+
+
 # ----------------------------------------------------------------------------- Cnn14
 class _ConvBlock(nn.Module):
     """Parameter holder with the state_dict layout of cnn_encoder.py:32-50 `ConvBlock`."""
@@ -398,13 +416,19 @@ class Cnn14Encoder(nn.Module):
         # the HF copy (hf_wrapper.py:1259-1261) receives the log-mel as `lms`, the training class the waveform
         wav = input_dict["lms"] if "lms" in input_dict else input_dict["wav"]
         wav_len = input_dict["wav_len"]
-        if self.training and input_dict.get("specaug", False):
-            raise NotImplementedError("SpecAugment (training) is out of scope of the B200 inference path")
         require_cuda(wav, "Cnn14Encoder.forward")
         l = _lib.lib()
         with torch.cuda.device(wav.device):
             lms = wav.float().contiguous() if "lms" in input_dict else self.log_mel(wav)
             B, F, T = lms.shape
+            if self.training and input_dict.get("specaug", False):          # cnn_encoder.py:424-425
+                stripes = input_dict.get("_specaug_stripes")
+                stripes = draw_specaug_stripes(B, T, F) if stripes is None else stripes
+                if "lms" in input_dict:
+                    lms = lms.clone()
+                st_dev = to_device_async(stripes.to(torch.int32).contiguous(), wav.device)
+                _lib.check(l.ac_specaug_apply(_lib.ptr(lms), B, F, T, _lib.ptr(st_dev), stripes.shape[1] // 2,
+                                              _lib.current_stream()), "ac_specaug_apply")
             Tp = l.ac_cnn14_out_frames(T)
             wave_length = torch.as_tensor(wav_len)
             feat_length = torch.div(wave_length, self.hop_length, rounding_mode="floor") + 1

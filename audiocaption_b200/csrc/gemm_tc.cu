@@ -631,7 +631,9 @@ static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks) {
     n_tiles = 1;
     BN = cdiv(N, 16) * 16;
     if (N <= TC_MAX_BN_RESIDENT && tc_resident(BN, 1, k_chunks)) return;
-    n_tiles = cdiv(N, TC_MAX_BN_STREAM);
+    static const int bn_stream = [] { const char* e = getenv("AC_TC_BN_STREAM"); const int v = e ? atoi(e) : 0;
+                                      return v >= 16 && v <= TC_MAX_BN_STREAM ? v / 16 * 16 : TC_MAX_BN_STREAM; }();   // tuning aid
+    n_tiles = cdiv(N, bn_stream);
     BN = cdiv(cdiv(N, n_tiles), 16) * 16;
 }
 

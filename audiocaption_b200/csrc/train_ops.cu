@@ -653,6 +653,19 @@ __global__ void adam_step_kernel(int* step, const float* loss, const float* part
     if (!((loss != nullptr && isnan(*loss)) || isnan(tot))) *step += 1;
 }
 
+__global__ void specaug_kernel(float* __restrict__ x, int F, int T, const int* __restrict__ stripes, int ns, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int t = (int)(i % T), f = (int)((i / T) % F), b = (int)(i / ((int64_t)T * F));
+    const int* s = stripes + (size_t)b * 4 * ns;
+    bool drop = false;
+    for (int k = 0; k < ns; ++k) {
+        drop = drop || (t >= s[2 * k] && t < s[2 * k] + s[2 * k + 1]);
+        drop = drop || (f >= s[2 * (ns + k)] && f < s[2 * (ns + k)] + s[2 * (ns + k) + 1]);
+    }
+    if (drop) x[i] = 0.0f;
+}
+
 }  // namespace ac
 
 extern "C" {
@@ -670,6 +683,21 @@ int ac_ls_ce_fwd_bwd(const float* logit_dev, int ld_logit, const int64_t* tgt_de
     AC_LAUNCHED("ls_ce_kernel");
     ls_ce_reduce_kernel<<<1, 256, 0, st>>>(row_loss, tgt_len_dev, B, L, loss_dev);
     AC_LAUNCHED("ls_ce_reduce_kernel");
+    return AC_OK;
+}
+
+// SpecAugment (cnn_encoder.py:352-353,424-425: torchlibrosa SpecAugmentation, training only): zero `n_stripes` time stripes
+// and `n_stripes` mel stripes per clip of the dB log-mel.  stripes_dev [batch][2 * n_stripes][2] int32 = (begin, width):
+// the first n_stripes entries are frame ranges, the rest mel ranges (drawn on the host by the module, in the library's
+// draw order).  lms_dev [batch, n_mels, n_frames], in place.
+int ac_specaug_apply(float* lms_dev, int batch, int n_mels, int n_frames, const int* stripes_dev, int n_stripes, void* stream) {
+    using namespace ac;
+    AC_REQUIRE(batch >= 0 && n_mels >= 1 && n_frames >= 1 && n_stripes >= 0 && n_stripes <= 8, "ac_specaug_apply: bad argument");
+    if (batch == 0 || n_stripes == 0) return AC_OK;
+    AC_REQUIRE(lms_dev && stripes_dev, "ac_specaug_apply: null argument");
+    const int64_t total = (int64_t)batch * n_mels * n_frames;
+    specaug_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(lms_dev, n_mels, n_frames, stripes_dev, n_stripes, total);
+    AC_LAUNCHED("specaug_kernel");
     return AC_OK;
 }
 

@@ -68,7 +68,7 @@ class TrainStep:
 
     def __init__(self, model, total_iters, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, max_grad_norm=1.0,
                  smoothing=0.1, final_lr=5e-7, warmup_iters=None, ss_mode="linear", ss_final_ratio=0.7, use_ss=True,
-                 process_group=None):
+                 process_group=None, specaug=False):
         from .captioning.models.crnn_trm_encoder import CrnnEncoder
         from .captioning.models.transformer_model import TransformerModel
         if not isinstance(model, TransformerModel) or not isinstance(model.encoder, CrnnEncoder):
@@ -87,6 +87,7 @@ class TrainStep:
         self.smoothing = float(smoothing)
         self.use_ss, self.ss_mode, self.ss_final_ratio = use_ss, ss_mode, float(ss_final_ratio)
         self.ss_ratio = 1.0
+        self.specaug = bool(specaug)                 # SpecAugment on the log-mel (the YAML's top-level `specaug:`)
         self.iteration = 0
         self.group = process_group
         self.world = 1
@@ -137,7 +138,7 @@ class TrainStep:
             cap_len = torch.as_tensor(batch["cap_len"]).to(torch.int64)
             tgt_len_dev = to_device_async(cap_len - 1, dev, torch.int64)
             # frozen CNN (dropout on, BatchNorm eval) -> frames; bi-GRU; decoder
-            cnn_out = m.encoder.cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": False})
+            cnn_out = m.encoder.cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": self.specaug})
             lens = cnn_out["attn_emb_len"]
             t_out = int(lens.max())
             x = cnn_out["attn_emb"][:, :t_out].contiguous()

@@ -363,6 +363,12 @@ int ac_trm_train_bwd(ac_trm_train_t* dec, const float* dlogits_dev, const int* r
                      const int64_t* attn_len_dev, int B, int T, float p_drop, uint64_t seed, float* dattn_emb_dev,
                      void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* SpecAugment on the dB log-mel (cnn_encoder.py:352-353,424-425: torchlibrosa `SpecAugmentation(time_drop_width=64,
+ * time_stripes_num=2, freq_drop_width=8, freq_stripes_num=2)`, training only): zeroes, per clip, n_stripes frame ranges and
+ * n_stripes mel ranges.  stripes_dev [batch][2 * n_stripes][2] int32 (begin, width): frame ranges first, then mel ranges
+ * (drawn by the caller).  lms_dev [batch, n_mels, n_frames] is modified in place. */
+int ac_specaug_apply(float* lms_dev, int batch, int n_mels, int n_frames, const int* stripes_dev, int n_stripes, void* stream);
+
 /* ------------------------------------------------------------------ loss and optimizer
  * captioning/losses/loss.py:51-74 `LabelSmoothingLoss.forward` (reduction "mean") fused with its gradient:
  * logit_dev [B, L, ld_logit >= V], tgt_dev [B, *] int64 with row stride ld_tgt (tgt = cap[:, 1:] is a strided view),

@@ -206,7 +206,7 @@ class Runner:
                                         weight_decay=opt_args.get("weight_decay", 0.0), max_grad_norm=self.max_grad_norm,
                                         smoothing=self.smoothing, final_lr=sched_args["final_lrs"], warmup_iters=warmup,
                                         ss_mode=ss_cfg.get("mode", "linear"), ss_final_ratio=ss_cfg.get("final_ratio", 1.0),
-                                        use_ss=ss_cfg.get("use", False))
+                                        use_ss=ss_cfg.get("use", False), specaug=self.config.get("specaug", False))
         else:
             self.optimizer = train_util.init_obj_from_dict(
                 self.config["optimizer"], params=[p for p in self.model.parameters() if p.requires_grad])

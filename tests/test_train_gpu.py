@@ -507,3 +507,37 @@ def test_tf32_convolution_mode():
         step = TrainStep(m2, total_iters=1000, lr=1e-3, warmup_iters=10)
         losses[prec] = step.step({"wav": wav, "wav_len": lens, "cap": cap, "cap_len": cap_len.numpy()}, coins=None)["loss"].item()
     assert abs(losses["fp32"] - losses["tf32"]) < 2e-3 * abs(losses["fp32"]), losses
+
+
+def test_specaugment_stripes():
+    """SpecAugment on the dB log-mel in train mode (cnn_encoder.py:352-353,424-425): the device kernel zeroes exactly the
+    host-drawn frame / mel stripes (vs torch indexing), the stripes follow torchlibrosa's draw rule (width < drop width,
+    inside the spectrogram, seeded by torch's generator), eval mode ignores `specaug`."""
+    from audiocaption_b200 import _lib
+    from audiocaption_b200.captioning.models.cnn_encoder import Cnn14Encoder, draw_specaug_stripes
+    torch.manual_seed(3)
+    st = draw_specaug_stripes(5, 301, 64)
+    torch.manual_seed(3)
+    assert (draw_specaug_stripes(5, 301, 64) == st).all() and st.shape == (5, 4, 2)
+    assert (st[:, :2, 1] < 64).all() and (st[:, 2:, 1] < 8).all() and (st[:, :2, 0] + st[:, :2, 1] <= 301).all()
+    assert (st[:, 2:, 0] + st[:, 2:, 1] <= 64).all()
+    x = torch.randn(5, 64, 301, generator=torch.Generator().manual_seed(1)) - 40.0
+    want = x.clone()
+    for b in range(5):
+        for k in range(2):
+            want[b, :, st[b, k, 0]:st[b, k, 0] + st[b, k, 1]] = 0
+            want[b, st[b, 2 + k, 0]:st[b, 2 + k, 0] + st[b, 2 + k, 1], :] = 0
+    got = x.to(DEV)
+    _lib.check(_lib.lib().ac_specaug_apply(_lib.ptr(got), 5, 64, 301, _lib.ptr(st.to(DEV)), 2, None), "ac_specaug_apply")
+    assert (got.cpu() == want).all() and (want == 0).any()
+    enc = Cnn14Encoder(sample_rate=32000, freeze=True)
+    enc.load_state_dict(oc.build_state_dict(3), strict=True)
+    enc = enc.to(DEV)
+    enc.conv_dropout = enc.fc_dropout = 0.0
+    wav, lens = cm.synth_wav(2, 64000, seed=5, varied=True, sample_rate=32000)
+    inp = {"wav": wav.to(DEV), "wav_len": lens}
+    with torch.no_grad():
+        plain = enc.train()(dict(inp, specaug=False))["attn_emb"]
+        aug = enc.train()(dict(inp, specaug=True))["attn_emb"]
+        ev = enc.eval()(dict(inp, specaug=True))["attn_emb"]
+    assert (ev == plain).all() and not (aug == plain).all()
