@@ -37,7 +37,64 @@ struct DwParams {
     int Ht, Ws, nsub, n_t;            // tile: Ht output rows x Ws output columns; nsub column sub-segments of n_t
     int tiles_h, tiles_w, chunks, total_tiles;
     int Hbox, Wbox, stages, tile_bytes;
+    // fused squeeze-and-excitation tail (gate == nullptr: off).  Every warp counts its finished (tile, warp) slots per clip;
+    // the CTA whose warp delivers a clip's last slot computes that clip's gate after its own tile loop.
+    const float* se_wr; const float* se_br; const float* se_we_t; const float* se_be;
+    float* gate; int* clip_count; int nsq, slots_per_clip, se_smem_off; float inv_hw;
 };
+
+constexpr int DW_SE_MAX_FIN = kDwSeMaxClips;   // clips one CTA can finish = batch limit of the fused tail (else: se_kernel)
+
+__device__ __forceinline__ void dw_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DW_COMPUTE_THREADS) : "memory"); }
+
+// Squeeze-and-excitation of ONE clip by the 256 compute threads of a CTA (same arithmetic and summation order as the
+// single-CTA path of effb2.cu `se_kernel`): channel means from the per-(tile, warp) partial sums, FC + swish, FC + sigmoid.
+__device__ void dw_se_clip(const DwParams& p, int b, float* s_mean, float* s_r, float4* s_scr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C, nsq = p.nsq, c4n = C / 4, strips = p.slots_per_clip / p.chunks;
+    const float4* p4 = reinterpret_cast<const float4*>(p.partial + (size_t)b * strips * C);
+    for (int cbase = 0; cbase < c4n; cbase += DW_COMPUTE_THREADS) {
+        const int width = min(c4n - cbase, DW_COMPUTE_THREADS);
+        const int G = max(1, min(DW_COMPUTE_THREADS / width, strips));
+        const int g = tid / width, c4 = cbase + tid % width;
+        if (g < G) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = g; q < strips; q += G) {
+                const float4 v = __ldcg(p4 + (size_t)q * c4n + c4);          // written by other CTAs of this launch: L2
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            s_scr[tid] = a;
+        }
+        dw_bar();
+        if (tid < width) {
+            float4 t = s_scr[tid];
+            for (int q = 1; q < G; ++q) {
+                const float4 u = s_scr[q * width + tid];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            reinterpret_cast<float4*>(s_mean)[c4] = make_float4(t.x * p.inv_hw, t.y * p.inv_hw, t.z * p.inv_hw, t.w * p.inv_hw);
+        }
+        dw_bar();
+    }
+    for (int j = warp; j < nsq; j += DW_COMPUTE_THREADS / 32) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(p.se_wr + (size_t)j * C + c), s_mean[c], a);
+        a = warp_sum(a);
+        if (lane == 0) s_r[j] = swishf(a + p.se_br[j]);
+    }
+    dw_bar();
+    for (int c = tid; c < C; c += DW_COMPUTE_THREADS) {
+        float s0 = 0.f, s1 = 0.f;
+        int j = 0;
+        for (; j + 1 < nsq; j += 2) {
+            s0 = fmaf(__ldg(p.se_we_t + (size_t)j * C + c), s_r[j], s0);
+            s1 = fmaf(__ldg(p.se_we_t + (size_t)(j + 1) * C + c), s_r[j + 1], s1);
+        }
+        if (j < nsq) s0 = fmaf(__ldg(p.se_we_t + (size_t)j * C + c), s_r[j], s0);
+        p.gate[(size_t)b * C + c] = sigmoidf_(s0 + s1 + p.se_be[c]);
+    }
+    dw_bar();
+}
 
 using ptx::tma_load_4d;
 
@@ -60,8 +117,11 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 32u + 8u * s; };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ int s_nfin;
+    int* s_fin = reinterpret_cast<int*>(smem_raw + (base - raw) + p.se_smem_off);        // [DW_SE_MAX_FIN] (only with the SE tail)
 
     if (tid == 0) {
+        s_nfin = 0;
         prefetch_tensormap(&mapIn);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full(s), 1);
@@ -208,6 +268,25 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
         if (c_ok && lane < TPG)
             *reinterpret_cast<float2*>(p.partial + (((size_t)b * (p.tiles_h * p.tiles_w) + th * p.tiles_w + tw) * (DW_COMPUTE_THREADS / 32) + warp) * p.C + c) =
                 make_float2(sum[0], sum[1]);
+        if (p.gate != nullptr) {
+            // this warp's slot of clip b is complete: publish it, and note the clip if it was the clip's last slot
+            __threadfence();
+            __syncwarp();
+            if (lane == 0 && atomicAdd(p.clip_count + b, 1) == p.slots_per_clip - 1) s_fin[atomicAdd(&s_nfin, 1)] = b;
+        }
+    }
+    if (p.gate != nullptr) {
+        dw_bar();                                   // all 8 compute warps are past their tile loops
+        const int n = s_nfin;
+        float* s_mean = reinterpret_cast<float*>(smem_raw + (base - raw));      // the TMA stages are free now: SE scratch
+        float* s_r = s_mean + p.C;
+        float4* s_scr = reinterpret_cast<float4*>(s_mean + ((p.C + p.nsq + 3) / 4) * 4);
+        for (int i = 0; i < n; ++i) {
+            const int b = s_fin[i];
+            __threadfence();                        // (acquire side of the slot counters)
+            dw_se_clip(p, b, s_mean, s_r, s_scr);
+            if (tid == 0) p.clip_count[b] = 0;      // ready for the next launch
+        }
     }
 }
 
@@ -225,7 +304,7 @@ static void dw_tile_shape(int Ho, int Wo, int C, int k, int s, int& CC, int& gro
     Ws = nsub * n_t;
     // at least two tiles (input box with halo) must fit in shared memory
     const size_t cap = k == 3 ? 110 * 1024 : DW_SMEM_LIMIT;      // 3x3 kernels run 2 CTAs per SM
-    while (n_t > 1 && (size_t)((Ht - 1) * s + k) * ((Ws - 1) * s + k) * CC * 4 * 2 > cap - 512) {
+    while (n_t > 1 && (size_t)((Ht - 1) * s + k) * ((Ws - 1) * s + k) * CC * 4 * 2 > cap - 768) {
         n_t /= 2;
         Ws = nsub * n_t;
     }
@@ -252,12 +331,22 @@ int dwconv_tma(const DwArgs& a, cudaStream_t st) {
     p.Hbox = (p.Ht - 1) * a.s + a.k; p.Wbox = (p.Ws - 1) * a.s + a.k;
     AC_REQUIRE(p.Wbox <= 256 && p.Hbox <= 256, "dwconv_tma: tile too large");
     p.tile_bytes = (int)align_up((size_t)p.Hbox * p.Wbox * p.CC * 4, 128);
-    const int fixed = 128 + 128;
+    bool fuse_se = a.gate != nullptr && a.B <= DW_SE_MAX_FIN;
+    p.gate = fuse_se ? a.gate : nullptr; p.clip_count = a.clip_count; p.se_wr = a.se_wr; p.se_br = a.se_br; p.se_we_t = a.se_we_t;
+    p.se_be = a.se_be; p.nsq = a.nsq; p.inv_hw = 1.0f / (float)(a.Ho * a.Wo);
+    p.slots_per_clip = p.chunks * p.tiles_h * p.tiles_w * (DW_COMPUTE_THREADS / 32);
+    AC_REQUIRE(!fuse_se || (a.clip_count && a.se_wr && a.se_br && a.se_we_t && a.se_be && a.nsq > 0), "dwconv_tma: SE tail needs its weights and counters");
+    // [stages x tile (after the tile loop: SE scratch mean[C] | r[nsq] | 256 float4)][barriers 128 B][finished-clip list 256 B]
+    const int se_scratch = (((a.C + a.nsq + 3) / 4) * 4 + DW_COMPUTE_THREADS * 4) * 4;
+    const int fixed = 128 + 128 + DW_SE_MAX_FIN * 4;
     const int ctas_per_sm = a.k == 3 ? 2 : 1;     // the 5x5 kernels need > 113 registers (measured slower when capped)
     const int smem_cap = a.k == 3 ? 110 * 1024 : DW_SMEM_LIMIT;
     p.stages = std::min(DW_MAX_STAGES, (smem_cap - fixed) / p.tile_bytes);
     AC_REQUIRE(p.stages >= 2, "dwconv_tma: tile of %d bytes does not fit twice in shared memory", p.tile_bytes);
     const size_t smem = (size_t)p.stages * p.tile_bytes + fixed;
+    p.se_smem_off = p.stages * p.tile_bytes + 128;          // after the barriers (64 B used)
+    if (fuse_se && p.stages * p.tile_bytes < se_scratch) { fuse_se = false; p.gate = nullptr; }    // (never for the B2 plan)
+    if (a.gate != nullptr && !fuse_se) { set_error("dwconv_tma: the fused SE tail does not fit (batch %d, stage bytes %d)", a.B, p.stages * p.tile_bytes); return AC_ERR_ARG; }
 
     CUtensorMap map;
     const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.B};

@@ -192,11 +192,26 @@ se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const flo
         }
         __syncthreads();
     }
-    // 2. squeeze: r[j] = swish(wr[j] . mean + br[j]) for my units, one warp per unit
+    // 2. squeeze: r[j] = swish(wr[j] . mean + br[j]) for my units, one warp per unit; the row is read as float4 with
+    //    four independent loads in flight per lane (the phase is a chain of L2 round trips, not bandwidth)
     for (int j = j0 + warp; j < j1; j += kSeThreads / 32) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + (size_t)j * C + c), s_mean[c], s);
-        s = warp_sum(s);
+        const float4* w4 = reinterpret_cast<const float4*>(wr + (size_t)j * C);
+        const float4* m4 = reinterpret_cast<const float4*>(s_mean);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int c = lane;
+        for (; c + 96 < c4n; c += 128) {
+            const float4 a0 = __ldg(w4 + c), a1 = __ldg(w4 + c + 32), a2 = __ldg(w4 + c + 64), a3 = __ldg(w4 + c + 96);
+            const float4 b0 = m4[c], b1 = m4[c + 32], b2 = m4[c + 64], b3 = m4[c + 96];
+            s0 = fmaf(a0.x, b0.x, fmaf(a0.y, b0.y, fmaf(a0.z, b0.z, fmaf(a0.w, b0.w, s0))));
+            s1 = fmaf(a1.x, b1.x, fmaf(a1.y, b1.y, fmaf(a1.z, b1.z, fmaf(a1.w, b1.w, s1))));
+            s2 = fmaf(a2.x, b2.x, fmaf(a2.y, b2.y, fmaf(a2.z, b2.z, fmaf(a2.w, b2.w, s2))));
+            s3 = fmaf(a3.x, b3.x, fmaf(a3.y, b3.y, fmaf(a3.z, b3.z, fmaf(a3.w, b3.w, s3))));
+        }
+        for (; c < c4n; c += 32) {
+            const float4 a0 = __ldg(w4 + c), b0 = m4[c];
+            s0 = fmaf(a0.x, b0.x, fmaf(a0.y, b0.y, fmaf(a0.z, b0.z, fmaf(a0.w, b0.w, s0))));
+        }
+        const float s = warp_sum((s0 + s1) + (s2 + s3));
         if (lane == 0) s_r[j] = swishf(s + br[j]);
     }
     if (P > 1) {
@@ -210,16 +225,45 @@ se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const flo
         }
     }
     __syncthreads();
-    // 3. excite: gate[c] = sigmoid(sum_j we_t[j][c] * r[j] + be[c]) for my channels
-    for (int c = 4 * q0 + tid; c < 4 * q1; c += kSeThreads) {
-        float s0 = 0.f, s1 = 0.f;
-        int j = 0;
-        for (; j + 1 < nsq; j += 2) {
-            s0 = fmaf(__ldg(we_t + (size_t)j * C + c), s_r[j], s0);
-            s1 = fmaf(__ldg(we_t + (size_t)(j + 1) * C + c), s_r[j + 1], s1);
+    // 3. excite: gate[c] = sigmoid(sum_j we_t[j][c] * r[j] + be[c]) for my channel quads.  thread = (unit group g, quad):
+    //    the units are dealt round-robin to G groups so that every thread has only nsq / G independent loads to wait for;
+    //    the groups' partial sums meet in shared memory (fixed order: deterministic)
+    for (int cbase = q0; cbase < q1; cbase += kSeThreads) {
+        const int width = min(q1 - cbase, kSeThreads);
+        const int G = max(1, min(kSeThreads / width, nsq));
+        const int g = tid / width, c4 = cbase + tid % width;
+        if (g < G) {
+            const float4* w4 = reinterpret_cast<const float4*>(we_t) + c4;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            int j = g;
+            for (; j + 3 * G < nsq; j += 4 * G) {
+                const float4 a0 = __ldg(w4 + (size_t)j * c4n), a1 = __ldg(w4 + (size_t)(j + G) * c4n);
+                const float4 a2 = __ldg(w4 + (size_t)(j + 2 * G) * c4n), a3 = __ldg(w4 + (size_t)(j + 3 * G) * c4n);
+                const float r0 = s_r[j], r1 = s_r[j + G], r2 = s_r[j + 2 * G], r3 = s_r[j + 3 * G];
+                s.x = fmaf(a3.x, r3, fmaf(a2.x, r2, fmaf(a1.x, r1, fmaf(a0.x, r0, s.x))));
+                s.y = fmaf(a3.y, r3, fmaf(a2.y, r2, fmaf(a1.y, r1, fmaf(a0.y, r0, s.y))));
+                s.z = fmaf(a3.z, r3, fmaf(a2.z, r2, fmaf(a1.z, r1, fmaf(a0.z, r0, s.z))));
+                s.w = fmaf(a3.w, r3, fmaf(a2.w, r2, fmaf(a1.w, r1, fmaf(a0.w, r0, s.w))));
+            }
+            for (; j < nsq; j += G) {
+                const float4 a0 = __ldg(w4 + (size_t)j * c4n);
+                const float r0 = s_r[j];
+                s.x = fmaf(a0.x, r0, s.x); s.y = fmaf(a0.y, r0, s.y); s.z = fmaf(a0.z, r0, s.z); s.w = fmaf(a0.w, r0, s.w);
+            }
+            s_scr[tid] = s;
         }
-        if (j < nsq) s0 = fmaf(__ldg(we_t + (size_t)j * C + c), s_r[j], s0);
-        gate[(size_t)b * C + c] = sigmoidf_(s0 + s1 + be[c]);
+        __syncthreads();
+        if (tid < width) {
+            float4 t = s_scr[tid];
+            for (int q = 1; q < G; ++q) {
+                const float4 u = s_scr[q * width + tid];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(be) + c4);
+            reinterpret_cast<float4*>(gate + (size_t)b * C)[c4] =
+                make_float4(sigmoidf_(t.x + bq.x), sigmoidf_(t.y + bq.y), sigmoidf_(t.z + bq.z), sigmoidf_(t.w + bq.w));
+        }
+        __syncthreads();
     }
     if (P > 1) cluster.sync();   // nobody exits while a peer may still read its shared memory
 }
@@ -364,7 +408,8 @@ int ac_effb2_block_info(int block, int* o) {
 size_t ac_effb2_workspace_bytes(int batch, int n_mels, int n_frames) {
     ac::WsLayout L = ac::ws_layout(batch, n_mels, n_frames);
     size_t fl = 2 * ac::align_up(L.x_elems, 64) + ac::align_up(L.e_elems, 64) + ac::align_up(L.d_elems, 64) +
-                ac::align_up(L.part_elems, 64) + ac::align_up(L.gate_elems, 64) + ac::align_up(L.head_elems, 64);
+                ac::align_up(L.part_elems, 64) + ac::align_up(L.gate_elems, 64) + ac::align_up(L.head_elems, 64) +
+                ac::align_up((size_t)batch, 64);          // + per-clip slot counters of the fused SE tail (int32)
     return fl * sizeof(float);
 }
 
@@ -496,7 +541,14 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
     float* D = p; p += align_up(L.d_elems, 64);
     float* PART = p; p += align_up(L.part_elems, 64);
     float* GATE = p; p += align_up(L.gate_elems, 64);
-    float* HEAD = p;
+    float* HEAD = p; p += align_up(L.head_elems, 64);
+    int* COUNT = reinterpret_cast<int*>(p);
+    // AC_EFFB2_SE=1: squeeze-and-excitation in the depthwise kernel's tail (the CTA that completes a clip computes its gate)
+    // instead of se_kernel.  Bit-identical but measured SLOWER (dw 0.91 -> 2.58 ms per step against 0.39 ms of se_kernel
+    // launches saved: every finisher streams the whole FC weights alone at the end of the kernel), so it stays off.
+    static const bool fuse_se_env = [] { const char* e = getenv("AC_EFFB2_SE"); return e && e[0] == '1'; }();
+    const bool fuse_se = fuse_se_env && B <= kDwSeMaxClips;
+    if (fuse_se) AC_CUDA(cudaMemsetAsync(COUNT, 0, (size_t)B * sizeof(int), st));
 
     Dims stem; std::vector<Dims> din, dout;
     walk(n_mels, n_frames, stem, din, dout);
@@ -519,9 +571,15 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         da.in = dw_in; da.out = D; da.partial = PART; da.w = w.dw.w; da.scale = w.dw.scale; da.bias = w.dw.bias;
         da.B = nb; da.Hi = din[i].H; da.Wi = din[i].W; da.Ho = dout[i].H; da.Wo = dout[i].W; da.C = ce;
         da.k = b.k; da.s = b.s; da.pad_lo = b.pad_lo;
+        if (fuse_se) {
+            da.gate = GATE; da.clip_count = COUNT; da.se_wr = w.se_wr; da.se_br = w.se_br; da.se_we_t = w.se_we; da.se_be = w.se_be;
+            da.nsq = b.nsq;
+        }
         int rc = dwconv_tma(da, st); if (rc) return rc;
-        const int strips = dwconv_tiles_per_clip(dout[i].H, dout[i].W, ce, b.k, b.s);
-        rc = launch_se(PART, strips, 1.0f / (float)pout, w, GATE, nb, ce, b.nsq, st); if (rc) return rc;
+        if (!fuse_se) {
+            const int strips = dwconv_tiles_per_clip(dout[i].H, dout[i].W, ce, b.k, b.s);
+            rc = launch_se(PART, strips, 1.0f / (float)pout, w, GATE, nb, ce, b.nsq, st); if (rc) return rc;
+        }
         GemmArgs g; g.A = D; g.W = w.project.w; g.C = out; g.M = nb * pout; g.N = b.cout; g.K = ce;
         g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
         g.act = ACT_NONE; g.R = b.skip ? in : nullptr;

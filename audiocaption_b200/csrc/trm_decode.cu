@@ -430,6 +430,336 @@ greedy_kernel(DecodeArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------ greedy, one CTA per head
+// Second greedy layout (the default when it fits): a cluster of NH = 4 CTAs decodes G clips, CTA h OWNS attention head h.
+//   * projections feeding attention (self q|k|v, cross q) and the first FFN layer are split over output columns so that
+//     CTA h computes exactly head h's 64 columns (a quarter of the hidden units): the results stay LOCAL, no exchange;
+//   * the projections that follow (attention out, second FFN layer) are split over K -- CTA h multiplies its own 64
+//     (256) inputs with the matching weight rows -- and the four partial [G][256] vectors meet in every CTA's shared
+//     memory (one distributed-shared-memory push + cluster.sync), where the residual add + LayerNorm is done redundantly;
+//   * the classifier is split over the vocabulary; each CTA reduces its slice to (max, arg-max, sum-exp) per row and
+//     only those three numbers are exchanged.
+// 7 cluster barriers per token step instead of 13, every CTA busy in every phase (attention included), the self- and
+// cross-attention K/V of the CTA's head live in shared memory, and with G = 2 the 12.4 MB of weights are streamed once
+// per TWO clips: half the L2 traffic of greedy_kernel<1> (which is what bounds it: 794 MB per step at 64 clips).
+constexpr int kHeadStride = 2 * HD + 4;       // K | V of one head per key, padded: conflict-free LDS.128 per key
+constexpr int kHeadPart = 8192;               // floats of split-K scratch
+
+// Slice GEMV: out[r][j], j in [0, 4 NQ) = sum_{k0 <= k < k1} xin[r][k - k0] * Wt[k][column quad colq(j / 4)].
+// thread = (K-slice, column quad): independent 128-bit loads, partial sums through `part`, fixed-order reduction.
+template <int G, class ColQ, class Epi>
+__device__ __forceinline__ void gemv_slice(const float* __restrict__ Wt, int ldw4, ColQ colq, int NQ, int k0, int k1,
+                                           const float* xin, int ldx, float* part, Epi epi) {
+    const int tid = threadIdx.x;
+    const int Nl = NQ * 4, K = k1 - k0;
+    const int KS = max(1, min(min(kThreads / NQ, kHeadPart / (G * Nl)), K));
+    const int kslice = (K + KS - 1) / KS;
+    const int s = tid / NQ, cl = tid - s * NQ;
+    if (s < KS) {
+        const int ka = k0 + s * kslice, kb = min(k1, ka + kslice);
+        float acc[G][4];
+#pragma unroll
+        for (int r = 0; r < G; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+        const float4* w = reinterpret_cast<const float4*>(Wt) + colq(cl);
+        int k = ka;
+        for (; k + 8 <= kb; k += 8) {                    // eight independent 128-bit loads in flight per thread
+            float4 wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(k + u) * ldw4);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int r = 0; r < G; ++r) {
+                    const float xv = xin[r * ldx + (k + u - k0)];
+                    acc[r][0] = fmaf(wv[u].x, xv, acc[r][0]); acc[r][1] = fmaf(wv[u].y, xv, acc[r][1]);
+                    acc[r][2] = fmaf(wv[u].z, xv, acc[r][2]); acc[r][3] = fmaf(wv[u].w, xv, acc[r][3]);
+                }
+            }
+        }
+        if (k < kb) {                                     // tail: the remaining (< 8) loads, again all in flight
+            float4 wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = k + u < kb ? __ldg(w + (size_t)(k + u) * ldw4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (k + u < kb) {
+#pragma unroll
+                    for (int r = 0; r < G; ++r) {
+                        const float xv = xin[r * ldx + (k + u - k0)];
+                        acc[r][0] = fmaf(wv[u].x, xv, acc[r][0]); acc[r][1] = fmaf(wv[u].y, xv, acc[r][1]);
+                        acc[r][2] = fmaf(wv[u].z, xv, acc[r][2]); acc[r][3] = fmaf(wv[u].w, xv, acc[r][3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < G; ++r)
+            *reinterpret_cast<float4*>(part + ((size_t)s * G + r) * Nl + 4 * cl) =
+                make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < G * Nl; i += kThreads) {
+        const int r = i / Nl, j = i - r * Nl;
+        float v = 0.f;
+        for (int q = 0; q < KS; ++q) v += part[((size_t)q * G + r) * Nl + j];
+        epi(r, j, v);
+    }
+}
+
+// x[r] = LayerNorm(x[r] + bias + sum_p red[p][r]) * g + b   (the four CTAs' K-split partial products), warp per row
+template <int G>
+__device__ __forceinline__ void reduce_add_layernorm(float* x, const float* red, const float* __restrict__ bias,
+                                                     const float* __restrict__ g, const float* __restrict__ b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < G) {
+        const int r = warp;
+        float v[D / 32];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) {
+            const int c = lane + 32 * i;
+            const float add = (red[(0 * G + r) * D + c] + red[(1 * G + r) * D + c]) +
+                              (red[(2 * G + r) * D + c] + red[(3 * G + r) * D + c]);
+            v[i] = x[r * D + c] + (add + __ldg(bias + c));
+            s += v[i];
+        }
+        const float mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) {
+            const int c = lane + 32 * i;
+            x[r * D + c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+        }
+    }
+}
+
+struct HeadSmem { size_t x, qkv, att, hid, part, red, logit, cls, kv, self, total; };
+static HeadSmem head_smem(int G, int nlayers, int dff, int vocab, int t_mem, int max_len) {
+    HeadSmem h; size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 3) / 4 * 4; return at; };
+    h.x = take((size_t)G * D); h.qkv = take((size_t)G * 3 * HD); h.att = take((size_t)G * HD);
+    h.hid = take((size_t)G * (dff / NH)); h.part = take(kHeadPart); h.red = take((size_t)2 * NH * G * D);
+    h.logit = take((size_t)G * (cdiv((vocab + 3) / 4, NH) * 4)); h.cls = take((size_t)2 * NH * G * 4);
+    h.kv = take((size_t)nlayers * G * t_mem * kHeadStride); h.self = take((size_t)nlayers * G * max_len * kHeadStride);
+    h.total = o;
+    return h;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads, 1)
+greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_x = smem + lay.x; float* s_qkv = smem + lay.qkv; float* s_att = smem + lay.att; float* s_hid = smem + lay.hid;
+    float* s_part = smem + lay.part; float* s_red = smem + lay.red; float* s_logit = smem + lay.logit;
+    float* s_cls = smem + lay.cls; float* s_kv = smem + lay.kv; float* s_self = smem + lay.self;
+    __shared__ unsigned char s_pad[kMaxLen][8];
+    __shared__ int s_word[G];
+    __shared__ int s_nmem[G];
+    constexpr int WPR = 32 / G >= 8 ? 8 : 32 / G;            // warps that scan one row's logits slice
+    __shared__ float s_cmax[G][WPR], s_cse[G][WPR];
+    __shared__ int s_cidx[G][WPR];
+    cg::cluster_group cluster = cg::this_cluster();
+    const DecW& W = a.w;
+    const int h = (int)cluster.block_rank();                 // my head
+    const int clip0 = (blockIdx.x / NH) * G, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool writer = h == 0;
+    const int V = W.vocab, VC = (V + 3) >> 2;
+    const int vc0 = (int)((int64_t)VC * h / NH), vc1 = (int)((int64_t)VC * (h + 1) / NH);   // my vocabulary quads
+    const int VQ = vc1 - vc0, ldl = ((VC + NH - 1) / NH) * 4;
+    const int dffl = W.dff / NH;
+    auto clip_of = [&](int r) { return min(clip0 + r, a.n_clips - 1); };   // rows past the batch replay the last clip
+    // cross-attention K | V of my head for the cluster's clips: [layer][row][frame][K 64 | V 64 | pad]
+    for (int l = 0; l < W.nlayers; ++l)
+        for (int r = 0; r < G; ++r) {
+            const float4* src = reinterpret_cast<const float4*>(a.kv_mem + (((size_t)l * a.n_clips + clip_of(r)) * a.t_mem) * 2 * D);
+            float* dst = s_kv + ((size_t)(l * G + r) * a.t_mem) * kHeadStride;
+            for (int i = tid; i < a.t_mem * 32; i += kThreads) {
+                const int frame = i >> 5, q = i & 31;              // q < 16: K quad, else V quad
+                const float4 v = __ldg(src + (size_t)frame * (2 * D / 4) + (q >> 4) * (D / 4) + h * (HD / 4) + (q & 15));
+                reinterpret_cast<float4*>(dst + (size_t)frame * kHeadStride)[q] = v;
+            }
+        }
+    if (tid < G) s_nmem[tid] = min((int)min((int64_t)a.t_mem, a.mem_len[clip_of(tid)]), a.t_mem);
+    int word[G]; bool finished[G]; bool valid[G];
+#pragma unroll
+    for (int r = 0; r < G; ++r) { word[r] = a.start_idx; valid[r] = clip0 + r < a.n_clips; finished[r] = !valid[r]; }
+    int xc = 0;                                          // exchange counter: s_red / s_cls are ping-pong buffers
+    cluster.sync();   // every CTA of the cluster is resident before the first push into its peers' shared memory
+    const bool full_outputs = a.logit_out != nullptr || a.embed_out != nullptr;
+    // push one row-slice value into the same slot of all four CTAs
+    auto push_red = [&](int r, int j, float v) {
+        float* slot = s_red + (((size_t)(xc & 1) * NH + h) * G + r) * D + j;
+#pragma unroll
+        for (int pr = 0; pr < NH; ++pr) *cluster.map_shared_rank(slot, pr) = v;
+    };
+    for (int t = 0; t < a.max_len; ++t) {
+        bool all_done = true;
+#pragma unroll
+        for (int r = 0; r < G; ++r) all_done = all_done && finished[r];
+        if (all_done && !full_outputs) {   // rows that emitted <end> keep <end> (base.py:161-168)
+            if (tid < G && writer && clip0 + tid < a.n_clips) a.seq[(size_t)(clip0 + tid) * a.max_len + t] = a.end_idx;
+            continue;
+        }
+        if (tid == 0) {
+#pragma unroll
+            for (int r = 0; r < G; ++r) { s_pad[t][r] = (word[r] == a.pad_idx); s_word[r] = word[r]; }
+        }
+        __syncthreads();
+        AC_DEC_STAMP(0);
+        for (int i = tid; i < G * D; i += kThreads) {
+            const int r = i / D, f = i - r * D;
+            s_x[i] = __ldg(W.emb + (size_t)s_word[r] * D + f) * 16.0f + __ldg(W.pe + (size_t)t * D + f);
+        }
+        __syncthreads();
+        for (int l = 0; l < W.nlayers; ++l) {
+            const LayerW& L = W.layer[l];
+            // ---- self attention, head h: q | k | v columns of my head (local), cache row t in shared memory
+            AC_DEC_STAMP(1 + 12 * l);
+            gemv_slice<G>(L.sa_in_wt, 3 * D / 4, [&](int cl) { return (cl >> 4) * (D / 4) + h * (HD / 4) + (cl & 15); }, 48, 0, D,
+                          s_x, D, s_part, [&](int r, int j, float v) {
+                              v += __ldg(L.sa_in_b + (j >> 6) * D + h * HD + (j & 63));
+                              if (j < HD) s_qkv[r * 3 * HD + j] = v;
+                              else s_self[((size_t)(l * G + r) * a.max_len + t) * kHeadStride + (j - HD)] = v;
+                          });
+            __syncthreads();
+            AC_DEC_STAMP(3 + 12 * l);
+            if (warp < G) {
+                const int r = warp;
+                const float* kc = s_self + ((size_t)(l * G + r) * a.max_len) * kHeadStride;
+                attend_head(s_qkv + r * 3 * HD, 0.125f, t + 1,
+                            [&](int j) { return kc + (size_t)j * kHeadStride; },
+                            [&](int j) { return kc + (size_t)j * kHeadStride + HD; },
+                            [&](int j) { return s_pad[j][r] != 0; }, s_att + r * HD);
+            }
+            __syncthreads();
+            AC_DEC_STAMP(4 + 12 * l);
+            gemv_slice<G>(L.sa_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s_att, HD, s_part, push_red);
+            cluster.sync();
+            AC_DEC_STAMP(5 + 12 * l);
+            reduce_add_layernorm<G>(s_x, s_red + (size_t)(xc & 1) * NH * G * D, L.sa_out_b, L.n1_g, L.n1_b);
+            ++xc;
+            __syncthreads();
+            // ---- cross attention, head h
+            AC_DEC_STAMP(6 + 12 * l);
+            gemv_slice<G>(L.ca_q_wt, D / 4, [&](int cl) { return h * (HD / 4) + cl; }, HD / 4, 0, D, s_x, D, s_part,
+                          [&](int r, int j, float v) { s_qkv[r * 3 * HD + j] = v + __ldg(L.ca_q_b + h * HD + j); });
+            __syncthreads();
+            AC_DEC_STAMP(7 + 12 * l);
+            if (warp < G) {
+                const int r = warp;
+                const float* km = s_kv + ((size_t)(l * G + r) * a.t_mem) * kHeadStride;
+                const int n_mem = s_nmem[r];
+                attend_head(s_qkv + r * 3 * HD, 0.125f, a.t_mem,
+                            [&](int j) { return km + (size_t)j * kHeadStride; },
+                            [&](int j) { return km + (size_t)j * kHeadStride + HD; },
+                            [&](int j) { return j >= n_mem; }, s_att + r * HD);
+            }
+            __syncthreads();
+            AC_DEC_STAMP(8 + 12 * l);
+            gemv_slice<G>(L.ca_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s_att, HD, s_part, push_red);
+            cluster.sync();
+            AC_DEC_STAMP(9 + 12 * l);
+            reduce_add_layernorm<G>(s_x, s_red + (size_t)(xc & 1) * NH * G * D, L.ca_out_b, L.n2_g, L.n2_b);
+            ++xc;
+            __syncthreads();
+            // ---- feed forward: my quarter of the hidden units, then their share of the output
+            AC_DEC_STAMP(10 + 12 * l);
+            gemv_slice<G>(L.ff1_wt, W.dff / 4, [&](int cl) { return h * (dffl / 4) + cl; }, dffl / 4, 0, D, s_x, D, s_part,
+                          [&](int r, int j, float v) { s_hid[r * dffl + j] = fmaxf(v + __ldg(L.ff1_b + h * dffl + j), 0.0f); });
+            __syncthreads();
+            AC_DEC_STAMP(11 + 12 * l);
+            gemv_slice<G>(L.ff2_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * dffl, (h + 1) * dffl, s_hid, dffl, s_part, push_red);
+            cluster.sync();
+            AC_DEC_STAMP(12 + 12 * l);
+            reduce_add_layernorm<G>(s_x, s_red + (size_t)(xc & 1) * NH * G * D, L.ff2_b, L.n3_g, L.n3_b);
+            ++xc;
+            __syncthreads();
+        }
+        AC_DEC_STAMP(40);
+        // ---- classifier (no bias) over my slice of the vocabulary
+        gemv_slice<G>(W.cls_wt, VC, [&](int cl) { return vc0 + cl; }, VQ, 0, D, s_x, D, s_part,
+                      [&](int r, int j, float v) {
+                          s_logit[r * ldl + j] = v;
+                          const int col = 4 * vc0 + j;
+                          if (a.logit_out != nullptr && col < V && valid[r])
+                              a.logit_out[((size_t)(clip0 + r) * a.max_len + t) * V + col] = v;
+                      });
+        __syncthreads();
+        AC_DEC_STAMP(41);
+        // my slice -> (max, first arg-max, sum exp(x - max)) per row: WPR warps scan a row (each its own max), one warp
+        // merges them and pushes the three numbers to all four CTAs
+        if (warp < G * WPR) {
+            const int r = warp / WPR, pt = warp - r * WPR;
+            const int n_my = min(4 * VQ, V - 4 * vc0), chunk = (n_my + WPR - 1) / WPR;
+            const int n0 = pt * chunk, n1 = min(n_my, n0 + chunk);
+            const float* lg = s_logit + r * ldl;
+            float best = -INFINITY; int bi = 0x7fffffff;
+            for (int n = n0 + lane; n < n1; n += 32) {
+                const float v = lg[n];
+                if (v > best) { best = v; bi = 4 * vc0 + n; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            float se = 0.f;
+            for (int n = n0 + lane; n < n1; n += 32) se += expf(lg[n] - best);
+            se = warp_sum(se);
+            if (lane == 0) { s_cmax[r][pt] = best; s_cidx[r][pt] = bi; s_cse[r][pt] = se; }
+        }
+        __syncthreads();
+        if (warp < G && lane < NH) {
+            const int r = warp;
+            float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+            for (int q = 0; q < WPR; ++q)          // chunks are in vocabulary order: the first maximum wins
+                if (s_cmax[r][q] > best) { best = s_cmax[r][q]; bi = s_cidx[r][q]; }
+            float se = 0.f;
+#pragma unroll
+            for (int q = 0; q < WPR; ++q) se += s_cse[r][q] > 0.f ? s_cse[r][q] * expf(s_cmax[r][q] - best) : 0.f;
+            float* slot = cluster.map_shared_rank(s_cls + (((size_t)(xc & 1) * NH + h) * G + r) * 4, lane);
+            slot[0] = best; slot[1] = __int_as_float(bi); slot[2] = se;
+        }
+        cluster.sync();
+        {
+            const float* c = s_cls + (size_t)(xc & 1) * NH * G * 4;
+            ++xc;
+#pragma unroll
+            for (int r = 0; r < G; ++r) {
+                float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+                for (int pr = 0; pr < NH; ++pr) {     // slices are in vocabulary order: the first maximum wins (torch.max on CPU)
+                    const float v = c[(pr * G + r) * 4];
+                    const int vi = __float_as_int(c[(pr * G + r) * 4 + 1]);
+                    if (v > best) { best = v; bi = vi; }
+                }
+                float se = 0.f;
+#pragma unroll
+                for (int pr = 0; pr < NH; ++pr) se += c[(pr * G + r) * 4 + 2] * expf(c[(pr * G + r) * 4] - best);
+                if (a.embed_out && writer && valid[r] && tid < D)
+                    a.embed_out[((size_t)(clip0 + r) * a.max_len + t) * D + tid] = s_x[r * D + tid];
+                word[r] = finished[r] ? a.end_idx : bi;
+                if (a.forced != nullptr && valid[r]) {
+                    const int64_t f = a.forced[(size_t)(clip0 + r) * a.max_len + t];
+                    if (f >= 0) word[r] = (int)f;
+                }
+                if (tid == 0 && writer && valid[r]) {
+                    a.seq[(size_t)(clip0 + r) * a.max_len + t] = word[r];
+                    if (a.logprob) a.logprob[(size_t)(clip0 + r) * a.max_len + t] = -logf(se);
+                }
+                finished[r] = !valid[r] || (!a.train_mode && (finished[r] || (word[r] == a.end_idx)));
+            }
+        }
+        AC_DEC_STAMP(42);
+    }
+    cluster.sync();   // nobody exits while a peer may still push into its shared memory
+}
+
 // ------------------------------------------------------------------------------------ beam search
 template <int R>
 __global__ void __launch_bounds__(kThreads)
@@ -835,6 +1165,35 @@ static int trm_greedy_impl(const ac_trm_t* dec, const float* attn_emb, const int
     a.seq = seq; a.logprob = logprob; a.logit_out = logit; a.embed_out = embed; a.beam = 1; a.temp = 1.0f;
     a.forced = forced; a.train_mode = train_mode;
     a.dbg = g_dec_trace;
+    // Default: one CTA per attention head, G clips per 4-CTA cluster (greedy_heads_kernel) when its shared-memory plan fits;
+    // AC_GREEDY="P,G" selects the column-split kernel below with that cluster shape (experiments, fallback).
+    if (getenv("AC_GREEDY") == nullptr && dec->w.dff % (4 * NH) == 0) {
+        int G = batch * NH <= kNumSMs ? 1 : 2;
+        if (const char* e = getenv("AC_GREEDY_HEADS")) G = atoi(e);      // 0 disables
+        if (G == 1 || G == 2 || G == 4) {
+            const HeadSmem lay = head_smem(G, dec->w.nlayers, dec->w.dff, dec->w.vocab, t_mem, max_len);
+            if (lay.total * sizeof(float) <= (size_t)kDecSmemLimit) {
+                const size_t sm = lay.total * sizeof(float);
+                AC_TIMED("trm_greedy", st);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(cdiv(batch, G) * NH); cfg.blockDim = dim3(kThreads);
+                cfg.dynamicSmemBytes = sm; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = NH; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+#define AC_HEADS_CASE(GG)                                                                                              \
+    case GG:                                                                                                           \
+        AC_CUDA(cudaFuncSetAttribute(greedy_heads_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  \
+        AC_CUDA(cudaLaunchKernelEx(&cfg, greedy_heads_kernel<GG>, a, lay));                                            \
+        break;
+                switch (G) { AC_HEADS_CASE(1) AC_HEADS_CASE(2) AC_HEADS_CASE(4) }
+#undef AC_HEADS_CASE
+                AC_LAUNCHED("greedy_heads_kernel");
+                return AC_OK;
+            }
+        }
+    }
     // (CTAs per cluster, clips per cluster); AC_GREEDY="P,G" overrides for experiments
     int P = trm_cluster_size(batch, kGreedyCluster), G = kGreedyClips;
     if (const char* e = getenv("AC_GREEDY")) sscanf(e, "%d,%d", &P, &G);
