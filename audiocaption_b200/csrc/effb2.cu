@@ -323,7 +323,25 @@ __global__ void masked_mean_kernel(const float* __restrict__ x, const int64_t* _
     out[(size_t)b * D + d] = s / (float)len;
 }
 
-struct ConvBN { float* w; float* scale; float* bias; TcWeight tw; };
+constexpr int kNarrowLevels = 2;                       // extra tensor-core images per 1x1 convolution: n-tiles <= 64, <= 32 columns
+constexpr int kNarrowCap[kNarrowLevels] = {64, 32};
+struct ConvBN {
+    float* w; float* scale; float* bias; TcWeight tw;
+    TcWeight narrow[kNarrowLevels];
+    // A launch with fewer than 64 tiles (small batches; at 64 clips no layer) takes the next narrower image: B = 32 encoder
+    // GEMM time 1.19 -> 1.13 ms, B = 1 0.84 -> 0.73 ms.  At 64 tiles (the K >= 720 projections of the last blocks at 64
+    // clips) narrower tiles measured SLOWER (1.60 -> 1.64 ms): the chunk period is the issue / commit chain, not the
+    // MMA width, so more CTAs only add A re-reads and transform work.  AC_TC_NARROW=<tiles> moves the threshold, 0 = never.
+    const TcWeight* pick(int M) const {
+        if (tw.packed == nullptr) return nullptr;
+        static const int below = [] { const char* e = getenv("AC_TC_NARROW"); return e ? atoi(e) : 64; }();
+        const TcWeight* best = &tw;
+        const int m_tiles = cdiv(M, 128);
+        for (int l = 0; l < kNarrowLevels && m_tiles * best->n_tiles < below; ++l)
+            if (narrow[l].packed != nullptr && narrow[l].n_tiles > best->n_tiles) best = &narrow[l];
+        return best;
+    }
+};
 struct BlockW {
     ConvBN expand, dw, project;
     float *se_wr, *se_br, *se_we, *se_be;
@@ -447,10 +465,15 @@ int ac_effb2_create(const float* const* t, const int64_t* numels, int n_tensors,
     // ---- size the packed blob
     size_t total = 0;
     auto take = [&](size_t n) { size_t o = total; total += align_up(n, 64); return o; };
-    struct Off { size_t w, s, b, pk; };
-    auto take_cb = [&](size_t wn, size_t c) { Off o; o.w = take(wn); o.s = take(c); o.b = take(c); o.pk = 0; return o; };
+    struct Off { size_t w, s, b, pk, npk[kNarrowLevels]; };
+    auto take_cb = [&](size_t wn, size_t c) { Off o{}; o.w = take(wn); o.s = take(c); o.b = take(c); o.pk = 0; return o; };
     // 1x1 convolutions also get a tensor-core image (BN scale folded in, hi/lo split, swizzled; see gemm.cuh)
-    auto take_pw = [&](int n, int k) { Off o = take_cb((size_t)n * k, n); o.pk = take(tc_packed_floats(n, k)); return o; };
+    auto take_pw = [&](int n, int k) {
+        Off o = take_cb((size_t)n * k, n);
+        o.pk = take(tc_packed_floats(n, k));
+        for (int l = 0; l < kNarrowLevels; ++l) o.npk[l] = n > kNarrowCap[l] ? take(tc_packed_floats_bn(n, k, kNarrowCap[l])) : 0;
+        return o;
+    };
     Off stem_o = take_cb(9 * P.stem_out, P.stem_out);
     struct BOff { Off e, d, p; size_t wr, br, we, be; };
     std::vector<BOff> bo;
@@ -505,6 +528,9 @@ int ac_effb2_create(const float* const* t, const int64_t* numels, int n_tensors,
     auto pack_pw = [&](const Off& o, int n, int k, ConvBN& cb) {
         cb = {B0 + o.w, B0 + o.s, B0 + o.b, TcWeight()};
         if (rc == AC_OK && k % 8 == 0) rc = tc_pack_weight(B0 + o.w, B0 + o.s, n, k, B0 + o.pk, st, &cb.tw);
+        for (int l = 0; l < kNarrowLevels; ++l)
+            if (rc == AC_OK && k % 8 == 0 && o.npk[l] != 0)
+                rc = tc_pack_weight_bn(B0 + o.w, B0 + o.s, n, k, kNarrowCap[l], B0 + o.npk[l], st, &cb.narrow[l]);
     };
     transposed(stem_o.w, P.stem_out, 9, "_conv_stem.weight");
     bn(stem_o, P.stem_out, "_bn0");
@@ -586,7 +612,7 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         if (b.expand != 1) {
             GemmArgs g; g.A = in; g.W = w.expand.w; g.C = E; g.M = nb * pin; g.N = ce; g.K = b.cin;
             g.cscale = w.expand.scale; g.cbias = w.expand.bias; g.act = ACT_SWISH;
-            g.tw = w.expand.tw.packed ? &w.expand.tw : nullptr;
+            g.tw = w.expand.pick(g.M);
             int rc = gemm_tn(g, st); if (rc) return rc;
             dw_in = E;
         }
@@ -606,7 +632,7 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         GemmArgs g; g.A = D; g.W = w.project.w; g.C = out; g.M = nb * pout; g.N = b.cout; g.K = ce;
         g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
         g.act = ACT_NONE; g.R = b.skip ? in : nullptr;
-        g.tw = w.project.tw.packed ? &w.project.tw : nullptr;
+        g.tw = w.project.pick(g.M);
         return gemm_tn(g, st);
     };
     auto run_stem = [&](const float* lms_c, float* out, int nb) -> int {
@@ -661,7 +687,7 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
     {
         GemmArgs g; g.A = cur; g.W = net->head.w; g.C = HEAD; g.M = B * last.H * last.W; g.N = P.head_out;
         g.K = P.head_in; g.cscale = net->head.scale; g.cbias = net->head.bias; g.act = ACT_SWISH;
-        g.tw = net->head.tw.packed ? &net->head.tw : nullptr;
+        g.tw = net->head.pick(g.M);
         int rc = gemm_tn(g, st); if (rc) return rc;
         int64_t total = (int64_t)B * last.W * P.head_out / 4;
         AC_TIMED("freq_mean", st);

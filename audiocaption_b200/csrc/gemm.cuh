@@ -25,6 +25,11 @@ struct TcWeight {
     int k_chunks = 0;  // ceil(K / 32)
 };
 size_t tc_packed_floats(int N, int K);
+// Narrow images (n-tiles of at most bn_cap columns, streamed): the same GEMM cut into more CTAs, for launches whose M is
+// too small to fill the SMs with the default tiling.
+size_t tc_packed_floats_bn(int N, int K, int bn_cap);
+int tc_pack_weight_bn(const float* W_dev, const float* scale_dev, int N, int K, int bn_cap, float* dst_dev, cudaStream_t st,
+                      TcWeight* out);
 // W_dev [N, K] row-major -> dst_dev (tc_packed_floats(N, K) floats); fills *out.
 // scale_dev [N] (nullable) is multiplied into the rows before the hi/lo split (folded BN scale).
 int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, float* dst_dev, cudaStream_t st,

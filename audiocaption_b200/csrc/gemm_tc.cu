@@ -128,6 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    if (threadIdx.x == 0) AC_TC_STAMP(7, 255);           // kernel entry
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&mapA);
@@ -155,6 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) AC_TC_STAMP(7, 254);           // barriers initialised, tensor memory allocated
     pdl_trigger();                                   // the next kernel may start its own prologue
     if (warp == 0 && lane == 0 && p.resident) {      // weights are constants: fetch them before the dependency wait
         const uint32_t wb = (uint32_t)p.k_chunks * w_chunk_bytes;
@@ -162,6 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         bulk_load(w_res, p.wpacked, wb, bar_w);
     }
     pdl_wait();                                      // A, the SE gate, the residual: produced by earlier kernels
+    if (threadIdx.x == 0) AC_TC_STAMP(7, 253);           // dependencies resolved
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -523,10 +526,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) AC_TC_STAMP(7, 252);           // all roles done
     if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks);
+static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks, int bn_cap = 0);
 
 // ------------------------------------------------------------------------------------ weight packing
 // One thread per packed float4: [n_tile][k_chunk][hi|lo][row BN][16-byte chunk 8 (swizzled)].
@@ -626,10 +630,15 @@ int conv3x3_permute_weight(const float* w_dev, float* out_dev, int Cout, int Cin
 static bool tc_resident(int BN, int n_tiles, int k_chunks) {
     return n_tiles == 1 && (int64_t)k_chunks * BN * 256 <= TC_RESIDENT_W_BYTES;
 }
-static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks) {
+static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks, int bn_cap) {
     k_chunks = cdiv(K, TC_BK);
     n_tiles = 1;
     BN = cdiv(N, 16) * 16;
+    if (bn_cap > 0) {      // a narrow image for small-M launches: more n-tiles (more CTAs), weights streamed
+        n_tiles = cdiv(N, std::max(16, bn_cap / 16 * 16));
+        BN = cdiv(cdiv(N, n_tiles), 16) * 16;
+        return;
+    }
     if (N <= TC_MAX_BN_RESIDENT && tc_resident(BN, 1, k_chunks)) return;
     static const int bn_stream = [] { const char* e = getenv("AC_TC_BN_STREAM"); const int v = e ? atoi(e) : 0;
                                       return v >= 16 && v <= TC_MAX_BN_STREAM ? v / 16 * 16 : TC_MAX_BN_STREAM; }();   // tuning aid
@@ -637,15 +646,29 @@ static void tc_tiling(int N, int K, int& BN, int& n_tiles, int& k_chunks) {
     BN = cdiv(cdiv(N, n_tiles), 16) * 16;
 }
 
-size_t tc_packed_floats(int N, int K) {
+size_t tc_packed_floats(int N, int K) { return tc_packed_floats_bn(N, K, 0); }
+size_t tc_packed_floats_bn(int N, int K, int bn_cap) {
     int BN, n_tiles, k_chunks;
-    tc_tiling(N, K, BN, n_tiles, k_chunks);
+    tc_tiling(N, K, BN, n_tiles, k_chunks, bn_cap);
     return (size_t)n_tiles * k_chunks * BN * 64;
 }
 
 int tc_pack_weight(const float* W_dev, const float* scale_dev, int N, int K, float* dst_dev, cudaStream_t st,
                    TcWeight* out) {
     return tc_pack_weight_strided(W_dev, scale_dev, N, K, K, 1, dst_dev, st, out);
+}
+
+int tc_pack_weight_bn(const float* W_dev, const float* scale_dev, int N, int K, int bn_cap, float* dst_dev, cudaStream_t st,
+                      TcWeight* out) {
+    AC_REQUIRE(W_dev && dst_dev && out && N > 0 && K > 0, "tc_pack_weight: bad argument");
+    AC_REQUIRE(((uintptr_t)dst_dev & 127) == 0, "tc_pack_weight: destination must be 128-byte aligned");
+    int BN, n_tiles, k_chunks;
+    tc_tiling(N, K, BN, n_tiles, k_chunks, bn_cap);
+    const int64_t total = (int64_t)n_tiles * k_chunks * 2 * BN * 8;
+    tc_pack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(W_dev, scale_dev, dst_dev, N, K, BN, n_tiles, k_chunks, K, 1);
+    AC_LAUNCHED("tc_pack_kernel");
+    out->packed = dst_dev; out->scale = scale_dev; out->N = N; out->K = K; out->BN = BN; out->n_tiles = n_tiles; out->k_chunks = k_chunks;
+    return AC_OK;
 }
 
 int tc_pack_weight_strided(const float* W_dev, const float* scale_dev, int N, int K, int64_t sn, int64_t sk, float* dst_dev,

@@ -125,6 +125,8 @@ if mode == "trace":
     print(f"trace M={M} N={N} K={K}: {n} chunks, cycles relative to first event")
     for i in range(min(n, 40)):
         print(i, " ".join(f"{names[k]}={int(buf[k][i]-t0) if buf[k][i] else -1:7d}" for k in range(5)))
+    print("kernel entry", int(buf[7][255] - t0), "setup done", int(buf[7][254] - t0), "pdl wait done", int(buf[7][253] - t0),
+          "all roles done", int(buf[7][252] - t0))
     ne = int((buf[5] > 0).sum())
     for i in range(min(ne, 12)):
         print("tile", i, f"acc_full={int(buf[5][i]-t0)} epi_done={int(buf[6][i]-t0)}")
