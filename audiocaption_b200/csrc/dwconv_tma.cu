@@ -24,9 +24,16 @@
 namespace ac {
 
 // CC = channels per tile (16, 32 or 64: 64 / 128 / 256 contiguous bytes per pixel); a pixel's chunk is served by
-// CC/2 threads (one channel pair each), so the 256 compute threads form 256 / (CC/2) (row, column sub-segment) groups.
-constexpr int DW_COMPUTE_THREADS = 256;
-constexpr int DW_THREADS = DW_COMPUTE_THREADS + 32;           // + producer warp
+// CC / CPT threads (CPT = channels per thread), so the compute threads form 256 / (CC/2) (row, column sub-segment) groups.
+// CPT = 2 everywhere (a channel pair per thread, LDS.64 / STG.64, 256 compute threads; 3x3 kernels run two CTAs per SM).
+// The 5x5 kernels hold 50 weight registers per thread and fit only one 9-warp CTA per SM; the CPT = 1 variant of the same
+// code (512 compute threads, 96 registers, 17 warps per SM) was measured SLOWER (all 5x5 layers of a 64-clip step:
+// 0.445 -> 0.493 ms): twice the LDS / STG instructions outweigh the extra latency hiding.  dw_cpt() keeps the switch.
+constexpr int DW_GROUP_THREADS = 256;                        // (compute threads) x CPT / 2: fixes the tile shape
+__host__ __device__ constexpr int dw_cpt(int k) { (void)k; return 2; }
+__host__ __device__ constexpr int dw_compute_threads(int k) { return DW_GROUP_THREADS * 2 / dw_cpt(k); }
+// partial-sum slots per tile: one per compute warp, or per group of warps that share a pixel chunk (CC / CPT > 32 threads)
+__host__ __device__ constexpr int dw_slots(int k, int cc) { return (dw_compute_threads(k) / 32) / (cc / dw_cpt(k) > 32 ? cc / dw_cpt(k) / 32 : 1); }
 constexpr int DW_MAX_STAGES = 4;
 constexpr int DW_SMEM_LIMIT = 200 * 1024;
 
@@ -37,64 +44,7 @@ struct DwParams {
     int Ht, Ws, nsub, n_t;            // tile: Ht output rows x Ws output columns; nsub column sub-segments of n_t
     int tiles_h, tiles_w, chunks, total_tiles;
     int Hbox, Wbox, stages, tile_bytes;
-    // fused squeeze-and-excitation tail (gate == nullptr: off).  Every warp counts its finished (tile, warp) slots per clip;
-    // the CTA whose warp delivers a clip's last slot computes that clip's gate after its own tile loop.
-    const float* se_wr; const float* se_br; const float* se_we_t; const float* se_be;
-    float* gate; int* clip_count; int nsq, slots_per_clip, se_smem_off; float inv_hw;
 };
-
-constexpr int DW_SE_MAX_FIN = kDwSeMaxClips;   // clips one CTA can finish = batch limit of the fused tail (else: se_kernel)
-
-__device__ __forceinline__ void dw_bar() { asm volatile("bar.sync 1, %0;" ::"n"(DW_COMPUTE_THREADS) : "memory"); }
-
-// Squeeze-and-excitation of ONE clip by the 256 compute threads of a CTA (same arithmetic and summation order as the
-// single-CTA path of effb2.cu `se_kernel`): channel means from the per-(tile, warp) partial sums, FC + swish, FC + sigmoid.
-__device__ void dw_se_clip(const DwParams& p, int b, float* s_mean, float* s_r, float4* s_scr) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = p.C, nsq = p.nsq, c4n = C / 4, strips = p.slots_per_clip / p.chunks;
-    const float4* p4 = reinterpret_cast<const float4*>(p.partial + (size_t)b * strips * C);
-    for (int cbase = 0; cbase < c4n; cbase += DW_COMPUTE_THREADS) {
-        const int width = min(c4n - cbase, DW_COMPUTE_THREADS);
-        const int G = max(1, min(DW_COMPUTE_THREADS / width, strips));
-        const int g = tid / width, c4 = cbase + tid % width;
-        if (g < G) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = g; q < strips; q += G) {
-                const float4 v = __ldcg(p4 + (size_t)q * c4n + c4);          // written by other CTAs of this launch: L2
-                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-            }
-            s_scr[tid] = a;
-        }
-        dw_bar();
-        if (tid < width) {
-            float4 t = s_scr[tid];
-            for (int q = 1; q < G; ++q) {
-                const float4 u = s_scr[q * width + tid];
-                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-            }
-            reinterpret_cast<float4*>(s_mean)[c4] = make_float4(t.x * p.inv_hw, t.y * p.inv_hw, t.z * p.inv_hw, t.w * p.inv_hw);
-        }
-        dw_bar();
-    }
-    for (int j = warp; j < nsq; j += DW_COMPUTE_THREADS / 32) {
-        float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(__ldg(p.se_wr + (size_t)j * C + c), s_mean[c], a);
-        a = warp_sum(a);
-        if (lane == 0) s_r[j] = swishf(a + p.se_br[j]);
-    }
-    dw_bar();
-    for (int c = tid; c < C; c += DW_COMPUTE_THREADS) {
-        float s0 = 0.f, s1 = 0.f;
-        int j = 0;
-        for (; j + 1 < nsq; j += 2) {
-            s0 = fmaf(__ldg(p.se_we_t + (size_t)j * C + c), s_r[j], s0);
-            s1 = fmaf(__ldg(p.se_we_t + (size_t)(j + 1) * C + c), s_r[j + 1], s1);
-        }
-        if (j < nsq) s0 = fmaf(__ldg(p.se_we_t + (size_t)j * C + c), s_r[j], s0);
-        p.gate[(size_t)b * C + c] = sigmoidf_(s0 + s1 + p.se_be[c]);
-    }
-    dw_bar();
-}
 
 using ptx::tma_load_4d;
 
@@ -107,9 +57,11 @@ __device__ __forceinline__ void dw_tile_coords(const DwParams& p, int tile, int&
 }
 
 template <int K, int S, int CC>
-__global__ void __launch_bounds__(DW_THREADS, K == 3 ? 2 : 1)     // 3x3: 2 CTAs per SM (16 compute warps)
+__global__ void __launch_bounds__(dw_compute_threads(K) + 32, K == 3 ? 2 : 1)     // 3x3: 2 CTAs per SM (16 compute warps)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     using namespace ptx;
+    constexpr int CPT = dw_cpt(K);                       // channels per thread
+    constexpr int NT = dw_compute_threads(K);            // compute threads (+ one producer warp)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 127u) & ~127u;
@@ -117,15 +69,12 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 32u + 8u * s; };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    __shared__ int s_nfin;
-    int* s_fin = reinterpret_cast<int*>(smem_raw + (base - raw) + p.se_smem_off);        // [DW_SE_MAX_FIN] (only with the SE tail)
 
     if (tid == 0) {
-        s_nfin = 0;
         prefetch_tensormap(&mapIn);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), DW_COMPUTE_THREADS / 32);
+            mbar_init(bar_empty(s), NT / 32);
         }
         fence_mbar_init();
     }
@@ -133,7 +82,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     pdl_trigger();
     pdl_wait();        // the input activation is the previous kernel's output
 
-    if (warp == DW_COMPUTE_THREADS / 32) {
+    if (warp == NT / 32) {
         // ------------------------------------------------------------ producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -151,31 +100,32 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
     }
 
     // ---------------------------------------------------------------- compute threads
-    constexpr int TPG = CC / 2;              // threads per pixel chunk
-    const int cp = tid % TPG;                // channel pair inside the chunk
+    constexpr int TPG = CC / CPT;            // threads per pixel chunk
+    const int cp = tid % TPG;                // channel group inside the chunk
     const int g = tid / TPG;                 // group: output row r (fast) x column sub-segment
     const int r = g % p.Ht, sub = g / p.Ht;
     const int wl0 = sub * p.n_t;             // first local output column of this thread
-    float wr[K * K][2];
-    float sc[2] = {0.f, 0.f}, bi[2] = {0.f, 0.f};
+    float wr[K * K][CPT];
+    float sc[CPT], bi[CPT];
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) { sc[e] = 0.f; bi[e] = 0.f; }
     int cur_chunk = -1;
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int chunk, b, th, tw;
         dw_tile_coords(p, tile, chunk, b, th, tw);
-        const int c = chunk * CC + 2 * cp;
+        const int c = chunk * CC + CPT * cp;
         const bool c_ok = c < p.C;
         if (chunk != cur_chunk) {
             cur_chunk = chunk;
 #pragma unroll
             for (int q = 0; q < K * K; ++q) {
-                const float2 v = c_ok ? __ldg(reinterpret_cast<const float2*>(p.w + (size_t)q * p.C + c)) : make_float2(0.f, 0.f);
-                wr[q][0] = v.x; wr[q][1] = v.y;
+#pragma unroll
+                for (int e = 0; e < CPT; ++e) wr[q][e] = c_ok ? __ldg(p.w + (size_t)q * p.C + c + e) : 0.f;
             }
             if (c_ok) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(p.scale + c));
-                const float2 d = __ldg(reinterpret_cast<const float2*>(p.bias + c));
-                sc[0] = a.x; sc[1] = a.y; bi[0] = d.x; bi[1] = d.y;
+#pragma unroll
+                for (int e = 0; e < CPT; ++e) { sc[e] = __ldg(p.scale + c + e); bi[e] = __ldg(p.bias + c + e); }
             }
         }
         const int ho = th * p.Ht + r;
@@ -183,7 +133,9 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
         const int n_out = max(0, min(p.n_t, p.Wo - wo_base));
         const bool row_ok = ho < p.Ho;
         float* orow = p.out + ((size_t)(b * p.Ho + ho) * p.Wo + wo_base) * p.C + c;
-        float sum[2] = {0.f, 0.f};
+        float sum[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) sum[e] = 0.f;
 
         mbar_wait(bar_full(stage), phase);
         // tile[row][col][CC ch]: this thread reads rows r*S + kh, columns wl0*S + j.  32-bit shared addresses, one per
@@ -191,13 +143,13 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
         uint32_t rowaddr[K];
         {
             const uint32_t a0 = base + (uint32_t)stage * (uint32_t)p.tile_bytes +
-                                (uint32_t)(((r * S) * p.Wbox + wl0 * S) * (CC * 4) + cp * 8);
+                                (uint32_t)(((r * S) * p.Wbox + wl0 * S) * (CC * 4) + cp * (4 * CPT));
             const uint32_t rstride = (uint32_t)(p.Wbox * CC * 4);
 #pragma unroll
             for (int kh = 0; kh < K; ++kh) rowaddr[kh] = a0 + kh * rstride;
         }
         if (row_ok && c_ok && n_out > 0) {
-            float acc[K][2];
+            float acc[K][CPT];
             const int n_cols = (n_out - 1) * S + K;
             constexpr int G = K * S;
             // one input column (relative index jb + JJ): load its K rows, add it into the outputs it touches, finish
@@ -206,29 +158,35 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
             auto column = [&](int jb, int jj, bool first, bool tail) {
                 const int j = jb + jj;
                 if (tail && j >= n_cols) return;
-                float x[K][2];
+                float x[K][CPT];
 #pragma unroll
-                for (int kh = 0; kh < K; ++kh)
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
-                                 : "=f"(x[kh][0]), "=f"(x[kh][1]) : "r"(rowaddr[kh] + (uint32_t)(jj * CC * 4)));
+                for (int kh = 0; kh < K; ++kh) {
+                    if constexpr (CPT == 2)
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                                     : "=f"(x[kh][0]), "=f"(x[kh][1]) : "r"(rowaddr[kh] + (uint32_t)(jj * CC * 4)));
+                    else
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[kh][0]) : "r"(rowaddr[kh] + (uint32_t)(jj * CC * 4)));
+                }
 #pragma unroll
                 for (int kw = 0; kw < K; ++kw) {
                     if ((jj - kw) % S != 0) continue;
                     const int slot = ((((jj - kw) / S) % K) + K) % K;
-                    float t0 = kw == 0 ? x[0][0] * wr[0][0] : fmaf(x[0][0], wr[kw][0], acc[slot][0]);
-                    float t1 = kw == 0 ? x[0][1] * wr[0][1] : fmaf(x[0][1], wr[kw][1], acc[slot][1]);
+                    float t[CPT];
 #pragma unroll
-                    for (int kh = 1; kh < K; ++kh) {
-                        t0 = fmaf(x[kh][0], wr[kh * K + kw][0], t0);
-                        t1 = fmaf(x[kh][1], wr[kh * K + kw][1], t1);
+                    for (int e = 0; e < CPT; ++e) {
+                        t[e] = kw == 0 ? x[0][e] * wr[0][e] : fmaf(x[0][e], wr[kw][e], acc[slot][e]);
+#pragma unroll
+                        for (int kh = 1; kh < K; ++kh) t[e] = fmaf(x[kh][e], wr[kh * K + kw][e], t[e]);
+                        acc[slot][e] = t[e];
                     }
-                    acc[slot][0] = t0; acc[slot][1] = t1;
                     if (kw == K - 1) {                     // last tap: output u = (j - kw) / S is complete
                         if (!first || j >= kw) {
-                            const float o0 = fast_swish(fmaf(t0, sc[0], bi[0]));
-                            const float o1 = fast_swish(fmaf(t1, sc[1], bi[1]));
-                            sum[0] += o0; sum[1] += o1;
-                            *reinterpret_cast<float2*>(orow + (size_t)((j - kw) / S) * p.C) = make_float2(o0, o1);
+                            float o[CPT];
+#pragma unroll
+                            for (int e = 0; e < CPT; ++e) { o[e] = fast_swish(fmaf(t[e], sc[e], bi[e])); sum[e] += o[e]; }
+                            float* dst = orow + (size_t)((j - kw) / S) * p.C;
+                            if constexpr (CPT == 2) *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+                            else *dst = o[0];
                         }
                     }
                 }
@@ -257,35 +215,20 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap mapIn, const DwParams p) {
         if (lane == 0) mbar_arrive(bar_empty(stage));      // this warp is done reading the stage
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
 
-        // channel sums of this thread's outputs.  Lanes of a warp that hold the same channel pair (32 / TPG groups)
-        // are combined by shuffles in a fixed order, then one slot per (tile, warp) is written -- no CTA-wide
-        // barrier; the SE kernel adds the slots in a fixed order (deterministic).
+        // channel sums of this thread's outputs.  Lanes of a warp that hold the same channels (32 / TPG groups) are
+        // combined by shuffles in a fixed order, then one slot per (tile, warp) is written -- no CTA-wide barrier; the
+        // SE kernel adds the slots in a fixed order (deterministic).  When a pixel chunk spans several warps (TPG > 32)
+        // those warps hold disjoint channels of the SAME slot.
 #pragma unroll
         for (int o = 16; o >= TPG; o >>= 1) {
-            sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o);
-            sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o);
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) sum[e] += __shfl_xor_sync(0xffffffffu, sum[e], o);
         }
-        if (c_ok && lane < TPG)
-            *reinterpret_cast<float2*>(p.partial + (((size_t)b * (p.tiles_h * p.tiles_w) + th * p.tiles_w + tw) * (DW_COMPUTE_THREADS / 32) + warp) * p.C + c) =
-                make_float2(sum[0], sum[1]);
-        if (p.gate != nullptr) {
-            // this warp's slot of clip b is complete: publish it, and note the clip if it was the clip's last slot
-            __threadfence();
-            __syncwarp();
-            if (lane == 0 && atomicAdd(p.clip_count + b, 1) == p.slots_per_clip - 1) s_fin[atomicAdd(&s_nfin, 1)] = b;
-        }
-    }
-    if (p.gate != nullptr) {
-        dw_bar();                                   // all 8 compute warps are past their tile loops
-        const int n = s_nfin;
-        float* s_mean = reinterpret_cast<float*>(smem_raw + (base - raw));      // the TMA stages are free now: SE scratch
-        float* s_r = s_mean + p.C;
-        float4* s_scr = reinterpret_cast<float4*>(s_mean + ((p.C + p.nsq + 3) / 4) * 4);
-        for (int i = 0; i < n; ++i) {
-            const int b = s_fin[i];
-            __threadfence();                        // (acquire side of the slot counters)
-            dw_se_clip(p, b, s_mean, s_r, s_scr);
-            if (tid == 0) p.clip_count[b] = 0;      // ready for the next launch
+        constexpr int WPS = TPG > 32 ? TPG / 32 : 1;       // warps per slot
+        if (c_ok && (TPG >= 32 || lane < TPG)) {
+            float* dst = p.partial + (((size_t)b * (p.tiles_h * p.tiles_w) + th * p.tiles_w + tw) * dw_slots(K, CC) + warp / WPS) * p.C + c;
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) dst[e] = sum[e];
         }
     }
 }
@@ -294,7 +237,7 @@ static int dw_chunk(int C, int k) { (void)k; return C >= 256 ? 64 : (C >= 32 ? 3
 
 static void dw_tile_shape(int Ho, int Wo, int C, int k, int s, int& CC, int& groups, int& Ht, int& Ws, int& nsub, int& n_t) {
     CC = dw_chunk(C, k);
-    groups = DW_COMPUTE_THREADS / (CC / 2);
+    groups = DW_GROUP_THREADS / (CC / 2);
     Ht = Ho >= 8 ? 8 : (Ho >= 4 ? 4 : (Ho >= 2 ? 2 : 1));
     nsub = groups / Ht;
     // output columns per thread: 16 when the row is long enough, never below 4
@@ -313,7 +256,7 @@ static void dw_tile_shape(int Ho, int Wo, int C, int k, int s, int& CC, int& gro
 int dwconv_tiles_per_clip(int Ho, int Wo, int C, int k, int s) {
     int CC, groups, Ht, Ws, nsub, n_t;
     dw_tile_shape(Ho, Wo, C, k, s, CC, groups, Ht, Ws, nsub, n_t);
-    return cdiv(Ho, Ht) * cdiv(Wo, Ws) * (DW_COMPUTE_THREADS / 32);
+    return cdiv(Ho, Ht) * cdiv(Wo, Ws) * dw_slots(k, CC);
 }
 
 int dwconv_tma(const DwArgs& a, cudaStream_t st) {
@@ -331,22 +274,12 @@ int dwconv_tma(const DwArgs& a, cudaStream_t st) {
     p.Hbox = (p.Ht - 1) * a.s + a.k; p.Wbox = (p.Ws - 1) * a.s + a.k;
     AC_REQUIRE(p.Wbox <= 256 && p.Hbox <= 256, "dwconv_tma: tile too large");
     p.tile_bytes = (int)align_up((size_t)p.Hbox * p.Wbox * p.CC * 4, 128);
-    bool fuse_se = a.gate != nullptr && a.B <= DW_SE_MAX_FIN;
-    p.gate = fuse_se ? a.gate : nullptr; p.clip_count = a.clip_count; p.se_wr = a.se_wr; p.se_br = a.se_br; p.se_we_t = a.se_we_t;
-    p.se_be = a.se_be; p.nsq = a.nsq; p.inv_hw = 1.0f / (float)(a.Ho * a.Wo);
-    p.slots_per_clip = p.chunks * p.tiles_h * p.tiles_w * (DW_COMPUTE_THREADS / 32);
-    AC_REQUIRE(!fuse_se || (a.clip_count && a.se_wr && a.se_br && a.se_we_t && a.se_be && a.nsq > 0), "dwconv_tma: SE tail needs its weights and counters");
-    // [stages x tile (after the tile loop: SE scratch mean[C] | r[nsq] | 256 float4)][barriers 128 B][finished-clip list 256 B]
-    const int se_scratch = (((a.C + a.nsq + 3) / 4) * 4 + DW_COMPUTE_THREADS * 4) * 4;
-    const int fixed = 128 + 128 + DW_SE_MAX_FIN * 4;
+    const int fixed = 128 + 128;                  // alignment slack + barriers
     const int ctas_per_sm = a.k == 3 ? 2 : 1;     // the 5x5 kernels need > 113 registers (measured slower when capped)
     const int smem_cap = a.k == 3 ? 110 * 1024 : DW_SMEM_LIMIT;
     p.stages = std::min(DW_MAX_STAGES, (smem_cap - fixed) / p.tile_bytes);
     AC_REQUIRE(p.stages >= 2, "dwconv_tma: tile of %d bytes does not fit twice in shared memory", p.tile_bytes);
     const size_t smem = (size_t)p.stages * p.tile_bytes + fixed;
-    p.se_smem_off = p.stages * p.tile_bytes + 128;          // after the barriers (64 B used)
-    if (fuse_se && p.stages * p.tile_bytes < se_scratch) { fuse_se = false; p.gate = nullptr; }    // (never for the B2 plan)
-    if (a.gate != nullptr && !fuse_se) { set_error("dwconv_tma: the fused SE tail does not fit (batch %d, stage bytes %d)", a.B, p.stages * p.tile_bytes); return AC_ERR_ARG; }
 
     CUtensorMap map;
     const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.Wi, (cuuint64_t)a.Hi, (cuuint64_t)a.B};
@@ -366,7 +299,7 @@ int dwconv_tma(const DwArgs& a, cudaStream_t st) {
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_LIMIT); \
         AC_CUDA(attr_rc);                                                                                        \
         cudaLaunchConfig_t cfg = {};                                                                             \
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(DW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(dw_compute_threads(K) + 32); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
         cudaLaunchAttribute at[1] = {pdl_attr()};                                                                \
         cfg.attrs = at; cfg.numAttrs = 1;                                                                        \
         AC_CUDA(cudaLaunchKernelEx(&cfg, dwconv_tma_kernel<K, S, CC>, map, p));                                  \

@@ -449,8 +449,7 @@ int ac_effb2_block_info(int block, int* o) {
 size_t ac_effb2_workspace_bytes(int batch, int n_mels, int n_frames) {
     ac::WsLayout L = ac::ws_layout(batch, n_mels, n_frames);
     size_t fl = 2 * ac::align_up(L.x_elems, 64) + ac::align_up(L.e_elems, 64) + ac::align_up(L.d_elems, 64) +
-                ac::align_up(L.part_elems, 64) + ac::align_up(L.gate_elems, 64) + ac::align_up(L.head_elems, 64) +
-                ac::align_up((size_t)batch, 64);          // + per-clip slot counters of the fused SE tail (int32)
+                ac::align_up(L.part_elems, 64) + ac::align_up(L.gate_elems, 64) + ac::align_up(L.head_elems, 64);
     return fl * sizeof(float);
 }
 
@@ -591,13 +590,6 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
     float* PART = p; p += align_up(L.part_elems, 64);
     float* GATE = p; p += align_up(L.gate_elems, 64);
     float* HEAD = p; p += align_up(L.head_elems, 64);
-    int* COUNT = reinterpret_cast<int*>(p);
-    // AC_EFFB2_SE=1: squeeze-and-excitation in the depthwise kernel's tail (the CTA that completes a clip computes its gate)
-    // instead of se_kernel.  Bit-identical but measured SLOWER (dw 0.91 -> 2.58 ms per step against 0.39 ms of se_kernel
-    // launches saved: every finisher streams the whole FC weights alone at the end of the kernel), so it stays off.
-    static const bool fuse_se_env = [] { const char* e = getenv("AC_EFFB2_SE"); return e && e[0] == '1'; }();
-    const bool fuse_se = fuse_se_env && B <= kDwSeMaxClips;
-    if (fuse_se) AC_CUDA(cudaMemsetAsync(COUNT, 0, (size_t)B * sizeof(int), st));
 
     Dims stem; std::vector<Dims> din, dout;
     walk(n_mels, n_frames, stem, din, dout);
@@ -620,15 +612,9 @@ int ac_effb2_fwd(const ac_effb2_t* net, const float* lms, const float* gmax, flo
         da.in = dw_in; da.out = D; da.partial = PART; da.w = w.dw.w; da.scale = w.dw.scale; da.bias = w.dw.bias;
         da.B = nb; da.Hi = din[i].H; da.Wi = din[i].W; da.Ho = dout[i].H; da.Wo = dout[i].W; da.C = ce;
         da.k = b.k; da.s = b.s; da.pad_lo = b.pad_lo;
-        if (fuse_se) {
-            da.gate = GATE; da.clip_count = COUNT; da.se_wr = w.se_wr; da.se_br = w.se_br; da.se_we_t = w.se_we; da.se_be = w.se_be;
-            da.nsq = b.nsq;
-        }
         int rc = dwconv_tma(da, st); if (rc) return rc;
-        if (!fuse_se) {
-            const int strips = dwconv_tiles_per_clip(dout[i].H, dout[i].W, ce, b.k, b.s);
-            rc = launch_se(PART, strips, 1.0f / (float)pout, w, GATE, nb, ce, b.nsq, st); if (rc) return rc;
-        }
+        const int strips = dwconv_tiles_per_clip(dout[i].H, dout[i].W, ce, b.k, b.s);
+        rc = launch_se(PART, strips, 1.0f / (float)pout, w, GATE, nb, ce, b.nsq, st); if (rc) return rc;
         GemmArgs g; g.A = D; g.W = w.project.w; g.C = out; g.M = nb * pout; g.N = b.cout; g.K = ce;
         g.ascale = GATE; g.rows_per_group = pout; g.cscale = w.project.scale; g.cbias = w.project.bias;
         g.act = ACT_NONE; g.R = b.skip ? in : nullptr;

@@ -92,14 +92,7 @@ struct DwArgs {
     const float* scale;   // [C] folded BN
     const float* bias;    // [C]
     int B, Hi, Wi, Ho, Wo, C, k, s, pad_lo;
-    // optional fused squeeze-and-excitation tail: gate [B][C] = sigmoid(W_e swish(W_r mean(out) + b_r) + b_e), computed by
-    // the CTA that completes a clip's last tile (no separate SE launch).  se_wr [nsq][C], se_we_t [nsq][C] (transposed),
-    // clip_count [B] int32 zero on entry (the kernel leaves it zero).  gate == nullptr: only `partial` is produced.
-    float* gate = nullptr; int* clip_count = nullptr;
-    const float* se_wr = nullptr; const float* se_br = nullptr; const float* se_we_t = nullptr; const float* se_be = nullptr;
-    int nsq = 0;
 };
-constexpr int kDwSeMaxClips = 64;       // batch limit of the fused tail (beyond it: the separate SE kernel)
 int dwconv_tiles_per_clip(int Ho, int Wo, int C, int k, int s);   // second dimension of `partial` (tiles x warps)
 int dwconv_tma(const DwArgs& a, cudaStream_t st);
 
