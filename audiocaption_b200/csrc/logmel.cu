@@ -5,10 +5,13 @@
 //
 // One CTA = 32 consecutive frames of one clip.  The waveform segment the 32 frames cover is
 // staged once in shared memory (reflect padding resolved while loading, coalesced reads); each
-// warp then transforms 4 frames: window multiply, N/2-point complex FFT of the even/odd packed
-// frame (radix-4 Stockham passes between two private shared-memory buffers), real-FFT unpacking to the power spectrum, banded
-// mel accumulation (only the non-zero band of each filter, detected from the module's own
-// `fb` buffer at create time), dB.  The 64x32 result tile is written back with frames
+// warp then transforms 4 frames.  The N/2-point complex FFT of the even/odd packed, windowed frame lives in REGISTERS:
+// lane l holds z[l + 32 j] (j < R = N/64), runs an R-point FFT over j on its own registers, applies the W^(l q) twiddles,
+// and the remaining 32-point FFT over the LANES is five radix-2 stages of warp shuffles; the real-FFT unpacking pairs
+// bin k with bin N/2 - k through two more shuffles.  Shared memory only sees the 257 (513) power values for the banded
+// mel accumulation (only the non-zero band of each filter, detected from the module's own `fb` buffer at create time)
+// and the dB tile.  (The first version ran radix-4 Stockham passes through shared memory: 5 round trips per frame with
+// up to 8-way bank conflicts, 0.19 ms per 64 clips; this one 0.1x ms.)  The 64x32 result tile is written back with frames
 // contiguous (128 B rows) in the [B, n_mels, T] layout the reference produces.
 //
 // Algorithmic HBM traffic: 4*n_samples (read) + 4*n_mels*T (write) bytes per clip.
@@ -24,6 +27,7 @@ struct ac_frontend {
     float2* twiddle_dev;   // [n_fft/2 + 1]  e^{-2 pi i k / n_fft}
     float* fbw_dev;        // band-compact filter weights
     int* band_dev;         // [n_mels][3] = {first bin, n bins, offset into fbw}
+    int fbw_len;           // floats in fbw_dev
 };
 
 namespace ac {
@@ -33,24 +37,61 @@ constexpr int kMelThreads = 256;
 constexpr int kMelWarps = kMelThreads / 32;
 constexpr int kMaxMels = 64;
 
+__host__ __device__ constexpr int bitrev_c(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// In-register radix-2 DIF FFT of size R (8 or 16): natural order in, position p holds output bitrev(p).
+template <int R>
+__device__ __forceinline__ void fft_regs(float (&re)[R], float (&im)[R]) {
+    // e^{-2 pi i t / 16}, t = 0..7
+    constexpr float C16[8] = {1.f, 0.9238795325112867f, 0.7071067811865476f, 0.3826834323650898f,
+                              0.f, -0.3826834323650898f, -0.7071067811865476f, -0.9238795325112867f};
+    constexpr float S16[8] = {0.f, -0.3826834323650898f, -0.7071067811865476f, -0.9238795325112867f,
+                              -1.f, -0.9238795325112867f, -0.7071067811865476f, -0.3826834323650898f};
+#pragma unroll
+    for (int half = R / 2; half >= 1; half >>= 1) {
+#pragma unroll
+        for (int b = 0; b < R; b += 2 * half) {
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const int t = i * (16 / (2 * half));
+                const float ar = re[b + i], ai = im[b + i], cr = re[b + i + half], ci = im[b + i + half];
+                re[b + i] = ar + cr; im[b + i] = ai + ci;
+                const float dr = ar - cr, di = ai - ci;
+                if (t == 0) { re[b + i + half] = dr; im[b + i + half] = di; }
+                else if (t == 4) { re[b + i + half] = di; im[b + i + half] = -dr; }          // * (-i)
+                else {
+                    re[b + i + half] = dr * C16[t] - di * S16[t];
+                    im[b + i + half] = dr * S16[t] + di * C16[t];
+                }
+            }
+        }
+    }
+}
+
 template <int NFFT>
-__global__ void __launch_bounds__(kMelThreads)
+__global__ void __launch_bounds__(kMelThreads, NFFT == 512 ? 4 : 2)
 logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int hop, int n_mels,
               const float* __restrict__ window, const float2* __restrict__ twiddle,
-              const float* __restrict__ fbw, const int* __restrict__ band,
+              const float* __restrict__ fbw, int fbw_len, const int* __restrict__ band,
               float* __restrict__ out, float* __restrict__ gmax) {
     constexpr int M = NFFT / 2;           // complex FFT size
-    constexpr int NF = NFFT / 2 + 1;      // one-sided bins
-    constexpr int PSTRIDE = NF + 7;       // power buffer stride per warp
+    constexpr int R = M / 32;             // points per lane
+    constexpr int LOGR = R == 8 ? 3 : 4;
+    static_assert(R == 8 || R == 16, "n_fft must be 512 or 1024");
+    constexpr int PSTRIDE = M + M / 32 + 8;       // power buffer per warp: bin k lives at k + (k >> 5) (conflict-free)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int seg_len = (kFramesPerCta - 1) * hop + NFFT;
     float* s_seg = reinterpret_cast<float*>(smem_raw);                       // [seg_len] (+pad to 4)
-    float2* s_tw = reinterpret_cast<float2*>(s_seg + ((seg_len + 3) & ~3));  // [M+1]
-    float2* s_fft = s_tw + (M + 2);                                          // [warps][2][M]
-    float* s_pow = reinterpret_cast<float*>(s_fft + 2 * kMelWarps * M);      // [warps][PSTRIDE]
+    float2* s_tw = reinterpret_cast<float2*>(s_seg + ((seg_len + 3) & ~3));  // [M+1]  e^{-2 pi i k / NFFT}
+    float* s_pow = reinterpret_cast<float*>(s_tw + (M + 2));                 // [warps][PSTRIDE]
     float* s_win = s_pow + kMelWarps * PSTRIDE;                              // [NFFT]
     float* s_tile = s_win + NFFT;                                            // [kMaxMels][33]
+    float* s_fbw = s_tile + kMaxMels * 33;                                   // [fbw_len] band-compact filter weights
     __shared__ float s_red[kMelWarps];
 
     const int b = blockIdx.y;
@@ -69,89 +110,107 @@ logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int ho
     }
     for (int i = tid; i <= M; i += kMelThreads) s_tw[i] = twiddle[i];
     for (int i = tid; i < NFFT; i += kMelThreads) s_win[i] = window[i];
+    for (int i = tid; i < fbw_len; i += kMelThreads) s_fbw[i] = fbw[i];
     __syncthreads();
 
-    float2* za = s_fft + warp * 2 * M;       // ping-pong buffers of the Stockham FFT
-    float2* zb = za + M;
+    // twid(m) = e^{-2 pi i m / NFFT}, 0 <= m <= NFFT (the table covers m <= M)
+    auto twid = [&](int m) {
+        const float2 t = s_tw[m > M ? m - M : m];
+        return m > M ? make_float2(-t.x, -t.y) : t;
+    };
+    // per-lane constants: lane-FFT twiddles W_{2d}^(lane mod d), the output index m = bitrev5(lane) of the lane FFT,
+    // and the lane that holds bin group (32 - m) mod 32 (partner of this lane's q = 0 bin in the real-FFT unpacking)
+    float2 tw_d[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int d = 16 >> s;
+        tw_d[s] = twid((lane & (d - 1)) * (NFFT / (2 * d)));
+    }
+    const int m_out = (int)(__brev((unsigned)lane) >> 27);
+    const int lane_q0 = (int)(__brev((unsigned)((32 - m_out) & 31)) >> 27);
+
     float* pw = s_pow + warp * PSTRIDE;
     float local_max = -INFINITY;
+    // this lane's two mel filters (lane, lane + 32): first bin, length, offset into the compact weights
+    const bool has0 = lane < n_mels, has1 = lane + 32 < n_mels;
+    const int lo0 = has0 ? band[3 * lane] : 0, nb0 = has0 ? band[3 * lane + 1] : 0, of0 = has0 ? band[3 * lane + 2] : 0;
+    const int lo1 = has1 ? band[3 * (lane + 32)] : 0, nb1 = has1 ? band[3 * (lane + 32) + 1] : 0, of1 = has1 ? band[3 * (lane + 32) + 2] : 0;
 
     for (int f = warp; f < kFramesPerCta; f += kMelWarps) {
         const int t = t0 + f;
         if (t >= n_frames) break;   // warp-uniform
         const float* x = s_seg + f * hop;
-        // windowed frame packed as z[n] = x[2n] + i x[2n+1] (natural order)
-        for (int n = lane; n < M; n += 32) {
-            float2 v = *reinterpret_cast<const float2*>(x + 2 * n);
-            float2 wv = *reinterpret_cast<const float2*>(s_win + 2 * n);
-            za[n] = make_float2(v.x * wv.x, v.y * wv.y);
+        // windowed frame packed as z[n] = x[2n] + i x[2n+1]; this lane: n = lane + 32 j
+        float re[R], im[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int n = lane + 32 * j;
+            const float2 v = *reinterpret_cast<const float2*>(x + 2 * n);
+            const float2 wv = *reinterpret_cast<const float2*>(s_win + 2 * n);
+            re[j] = v.x * wv.x; im[j] = v.y * wv.y;
         }
-        __syncwarp();
-        // Stockham autosort FFT (no bit reversal; ping-pong between the warp's two buffers): radix-4 passes in
-        // registers -- 4 passes for M = 256 instead of 8 radix-2 round trips through shared memory -- plus one
-        // radix-2 pass when M is not a power of 4.  twid(m) = e^{-2 pi i m / NFFT}; the table covers m <= M.
-        auto twid = [&](int m) {
-            float2 t = s_tw[m > M ? m - M : m];
-            return m > M ? make_float2(-t.x, -t.y) : t;
-        };
-        auto cmul = [](float2 p, float2 q) { return make_float2(p.x * q.x - p.y * q.y, p.x * q.y + p.y * q.x); };
-        float2* in = za; float2* out = zb;
-        int Ns = 1;
-        for (; Ns * 4 <= M; Ns *= 4) {
-            const int tstep = NFFT / (4 * Ns);
-            for (int j = lane; j < M / 4; j += 32) {
-                const int k = j & (Ns - 1);
-                float2 v0 = in[j], v1 = in[j + M / 4], v2 = in[j + M / 2], v3 = in[j + 3 * M / 4];
-                if (Ns > 1) {
-                    v1 = cmul(v1, twid(k * tstep));
-                    v2 = cmul(v2, twid(2 * k * tstep));
-                    v3 = cmul(v3, twid(3 * k * tstep));
-                }
-                // forward DFT-4: multiplication by -i is (a, b) -> (b, -a)
-                const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
-                const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
-                const int j0 = ((j - k) << 2) + k;
-                out[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
-                out[j0 + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);
-                out[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
-                out[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);
+        fft_regs<R>(re, im);                                  // position p: Y_lane[q], q = bitrev(p)
+#pragma unroll
+        for (int p = 1; p < R; ++p) {                         // * W_M^(lane q)
+            const int q = bitrev_c(p, LOGR);
+            const float2 tw = twid(2 * lane * q);
+            const float a = re[p], c = im[p];
+            re[p] = a * tw.x - c * tw.y; im[p] = a * tw.y + c * tw.x;
+        }
+        // 32-point DIF FFT over the lanes, every register position at once.  Lower lane of a pair: u + v; upper lane:
+        // (u - v) W.  Both as (other + sgn * mine) * W' with W' = 1 on the lower lanes: no branch, no wasted half.
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int d = 16 >> s;
+            const bool upper = (lane & d) != 0;
+            const float sgn = upper ? -1.0f : 1.0f;
+            const float wx = upper ? tw_d[s].x : 1.0f, wy = upper ? tw_d[s].y : 0.0f;
+#pragma unroll
+            for (int p = 0; p < R; ++p) {
+                const float a = fmaf(sgn, re[p], __shfl_xor_sync(0xffffffffu, re[p], d));
+                const float c = fmaf(sgn, im[p], __shfl_xor_sync(0xffffffffu, im[p], d));
+                re[p] = a * wx - c * wy; im[p] = a * wy + c * wx;
             }
-            __syncwarp();
-            float2* tmp = in; in = out; out = tmp;
         }
-        if (Ns < M) {   // M = 2 * 4^p: final radix-2 pass
-            const int tstep = NFFT / (2 * Ns);
-            for (int j = lane; j < M / 2; j += 32) {
-                const int k = j & (Ns - 1);
-                const float2 v0 = in[j], v1 = cmul(in[j + M / 2], twid(k * tstep));
-                const int j0 = ((j - k) << 1) + k;
-                out[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
-                out[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
-            }
-            __syncwarp();
-            float2* tmp = in; in = out; out = tmp;
+        // position p of this lane now holds Z[k], k = R * m_out + bitrev(p).  Real-FFT unpacking against Z[M - k]:
+        // q >= 1: lane ^ 31 holds group 31 - m_out, position bitrev(R - q);  q = 0: lane_q0, position 0.
+        const float z0r = re[0], z0i = im[0];
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+            const int q = bitrev_c(p, LOGR);
+            const int pp = q == 0 ? 0 : bitrev_c(R - q, LOGR);
+            const int src = q == 0 ? lane_q0 : (lane ^ 31);
+            const float br = __shfl_sync(0xffffffffu, re[pp], src);
+            const float bi = __shfl_sync(0xffffffffu, im[pp], src);
+            const int k = R * m_out + q;
+            const float ex = 0.5f * (re[p] + br), ey = 0.5f * (im[p] - bi);
+            const float ox = 0.5f * (im[p] + bi), oy = -0.5f * (re[p] - br);
+            const float2 tw = s_tw[k];
+            const float xr = ex + (ox * tw.x - oy * tw.y);
+            const float xi = ey + (ox * tw.y + oy * tw.x);
+            pw[k + (k >> 5)] = xr * xr + xi * xi;
         }
-        const float2* z = in;
-        // unpack the real FFT and take |X|^2
-        for (int k = lane; k <= M; k += 32) {
-            float2 A = z[k & (M - 1)];
-            float2 Bm = z[(M - k) & (M - 1)];
-            float2 E = make_float2(0.5f * (A.x + Bm.x), 0.5f * (A.y - Bm.y));
-            float2 O = make_float2(0.5f * (A.y + Bm.y), -0.5f * (A.x - Bm.x));
-            float2 tw = s_tw[k];
-            float xr = E.x + (O.x * tw.x - O.y * tw.y);
-            float xi = E.y + (O.x * tw.y + O.y * tw.x);
-            pw[k] = xr * xr + xi * xi;
-        }
+        if (m_out == 0) pw[M + (M >> 5)] = (z0r - z0i) * (z0r - z0i);     // Nyquist bin
         __syncwarp();
-        // banded mel filters + dB
-        for (int m = lane; m < n_mels; m += 32) {
-            int lo = band[3 * m], n = band[3 * m + 1], off = band[3 * m + 2];
-            float acc = 0.0f;
-            for (int j = 0; j < n; ++j) acc = fmaf(pw[lo + j], __ldg(fbw + off + j), acc);
-            float db = 10.0f * log10f(fmaxf(acc, 1e-10f));
-            s_tile[m * 33 + f] = db;
-            local_max = fmaxf(local_max, db);
+        // banded mel filters + dB: both filters of the lane advance in one loop (two independent chains)
+        {
+            float a0 = 0.0f, a1 = 0.0f;
+            const int nmax = max(nb0, nb1);
+            for (int j = 0; j < nmax; ++j) {
+                const int k0 = lo0 + j, k1 = lo1 + j;
+                if (j < nb0) a0 = fmaf(pw[k0 + (k0 >> 5)], s_fbw[of0 + j], a0);
+                if (j < nb1) a1 = fmaf(pw[k1 + (k1 >> 5)], s_fbw[of1 + j], a1);
+            }
+            if (has0) {
+                const float db = 10.0f * log10f(fmaxf(a0, 1e-10f));
+                s_tile[lane * 33 + f] = db;
+                local_max = fmaxf(local_max, db);
+            }
+            if (has1) {
+                const float db = 10.0f * log10f(fmaxf(a1, 1e-10f));
+                s_tile[(lane + 32) * 33 + f] = db;
+                local_max = fmaxf(local_max, db);
+            }
         }
         __syncwarp();
     }
@@ -175,12 +234,10 @@ logmel_kernel(const float* __restrict__ wav, int n_samples, int n_frames, int ho
 }
 
 template <int NFFT>
-static size_t logmel_smem_bytes(int hop) {
+static size_t logmel_smem_bytes(int hop, int fbw_len) {
     constexpr int M = NFFT / 2;
-    constexpr int NF = NFFT / 2 + 1;
     int seg_len = (kFramesPerCta - 1) * hop + NFFT;
-    size_t fl = ((seg_len + 3) & ~3) + 2 * (M + 2) + 4 * kMelWarps * M + kMelWarps * (NF + 7) + NFFT +
-                kMaxMels * 33;
+    size_t fl = ((seg_len + 3) & ~3) + 2 * (M + 2) + kMelWarps * (M + M / 32 + 8) + NFFT + kMaxMels * 33 + fbw_len;
     return fl * sizeof(float);
 }
 
@@ -234,10 +291,13 @@ int ac_frontend_create(const float* window_host, int n_fft, int hop, const float
     AC_CUDA(cudaMemcpy(fe->twiddle_dev, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
     AC_CUDA(cudaMemcpy(fe->fbw_dev, fbw.data(), fbw.size() * sizeof(float), cudaMemcpyHostToDevice));
     AC_CUDA(cudaMemcpy(fe->band_dev, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice));
+    fe->fbw_len = (int)fbw.size();
+    AC_CUDA(cudaFuncSetAttribute(ac::logmel_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    AC_CUDA(cudaFuncSetAttribute(ac::logmel_kernel<1024>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     AC_CUDA(cudaFuncSetAttribute(ac::logmel_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ac::logmel_smem_bytes<512>(512)));
+                                 (int)ac::logmel_smem_bytes<512>(512, fe->fbw_len)));
     AC_CUDA(cudaFuncSetAttribute(ac::logmel_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ac::logmel_smem_bytes<1024>(1024)));
+                                 (int)ac::logmel_smem_bytes<1024>(1024, fe->fbw_len)));
     *out = fe;
     return AC_OK;
 }
@@ -267,15 +327,15 @@ int ac_logmel_fwd(const ac_frontend_t* fe, const float* wav_dev, int batch, int 
     dim3 grid(ac::cdiv(T, ac::kFramesPerCta), batch);
     AC_TIMED("logmel", st);
     if (fe->n_fft == 512) {
-        size_t sm = ac::logmel_smem_bytes<512>(fe->hop);
+        size_t sm = ac::logmel_smem_bytes<512>(fe->hop, fe->fbw_len);
         ac::logmel_kernel<512><<<grid, ac::kMelThreads, sm, st>>>(
             wav_dev, n_samples, T, fe->hop, fe->n_mels, fe->window_dev, fe->twiddle_dev, fe->fbw_dev,
-            fe->band_dev, lms_dev, gmax_dev);
+            fe->fbw_len, fe->band_dev, lms_dev, gmax_dev);
     } else {
-        size_t sm = ac::logmel_smem_bytes<1024>(fe->hop);
+        size_t sm = ac::logmel_smem_bytes<1024>(fe->hop, fe->fbw_len);
         ac::logmel_kernel<1024><<<grid, ac::kMelThreads, sm, st>>>(
             wav_dev, n_samples, T, fe->hop, fe->n_mels, fe->window_dev, fe->twiddle_dev, fe->fbw_dev,
-            fe->band_dev, lms_dev, gmax_dev);
+            fe->fbw_len, fe->band_dev, lms_dev, gmax_dev);
     }
     AC_LAUNCHED("logmel_kernel");
     return AC_OK;
