@@ -461,13 +461,14 @@ __device__ __forceinline__ void gemv_slice(const float* __restrict__ Wt, int ldw
 #pragma unroll
         for (int r = 0; r < G; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
         const float4* w = reinterpret_cast<const float4*>(Wt) + colq(cl);
+        constexpr int U = G <= 2 ? 8 : 4;                // independent 128-bit loads in flight per thread (64 registers)
         int k = ka;
-        for (; k + 8 <= kb; k += 8) {                    // eight independent 128-bit loads in flight per thread
-            float4 wv[8];
+        for (; k + U <= kb; k += U) {
+            float4 wv[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(k + u) * ldw4);
+            for (int u = 0; u < U; ++u) wv[u] = __ldg(w + (size_t)(k + u) * ldw4);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < U; ++u) {
 #pragma unroll
                 for (int r = 0; r < G; ++r) {
                     const float xv = xin[r * ldx + (k + u - k0)];
@@ -476,12 +477,12 @@ __device__ __forceinline__ void gemv_slice(const float* __restrict__ Wt, int ldw
                 }
             }
         }
-        if (k < kb) {                                     // tail: the remaining (< 8) loads, again all in flight
-            float4 wv[8];
+        if (k < kb) {                                     // tail: the remaining (< U) loads, again all in flight
+            float4 wv[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) wv[u] = k + u < kb ? __ldg(w + (size_t)(k + u) * ldw4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < U; ++u) wv[u] = k + u < kb ? __ldg(w + (size_t)(k + u) * ldw4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < U; ++u) {
                 if (k + u < kb) {
 #pragma unroll
                     for (int r = 0; r < G; ++r) {
@@ -536,25 +537,174 @@ __device__ __forceinline__ void reduce_add_layernorm(float* x, const float* red,
     }
 }
 
-struct HeadSmem { size_t x, qkv, att, hid, part, red, logit, cls, kv, self, total; };
-static HeadSmem head_smem(int G, int nlayers, int dff, int vocab, int t_mem, int max_len) {
+struct HeadSmem { size_t x, qkv, att, hid, part, red, logit, cls, kv, self, total; int self_global, self_stride; };
+// self_global: the self-attention K/V of the CTA's head live in its private slice of the global cache workspace (stride
+// 2 HD, read back through L2) instead of shared memory -- for the row counts whose cache does not fit (beam 4 and 5)
+static HeadSmem head_smem(int G, int clips, int nlayers, int dff, int vocab, int t_mem, int max_len, bool self_global = false) {
     HeadSmem h; size_t o = 0;
     auto take = [&](size_t n) { const size_t at = o; o += (n + 3) / 4 * 4; return at; };
     h.x = take((size_t)G * D); h.qkv = take((size_t)G * 3 * HD); h.att = take((size_t)G * HD);
     h.hid = take((size_t)G * (dff / NH)); h.part = take(kHeadPart); h.red = take((size_t)2 * NH * G * D);
     h.logit = take((size_t)G * (cdiv((vocab + 3) / 4, NH) * 4)); h.cls = take((size_t)2 * NH * G * 4);
-    h.kv = take((size_t)nlayers * G * t_mem * kHeadStride); h.self = take((size_t)nlayers * G * max_len * kHeadStride);
+    h.kv = take((size_t)nlayers * clips * t_mem * kHeadStride);
+    h.self = self_global ? 0 : take((size_t)nlayers * G * max_len * kHeadStride);
+    h.self_global = self_global ? 1 : 0; h.self_stride = self_global ? 2 * HD : kHeadStride;
     h.total = o;
     return h;
+}
+
+struct HeadBufs { float *x, *qkv, *att, *hid, *part, *red, *logit, *kv, *self; int self_stride; };
+
+// cross-attention K | V of head h for the cluster's clips [clip0, clip0 + NC): [layer][clip slot][frame][K 64 | V 64 | pad]
+template <int NC>
+__device__ __forceinline__ void heads_stage_kv(const DecodeArgs& a, int clip0, int h, float* s_kv) {
+    for (int l = 0; l < a.w.nlayers; ++l)
+        for (int c = 0; c < NC; ++c) {
+            const int clip = min(clip0 + c, a.n_clips - 1);      // slots past the batch replay the last clip
+            const float4* src = reinterpret_cast<const float4*>(a.kv_mem + (((size_t)l * a.n_clips + clip) * a.t_mem) * 2 * D);
+            float* dst = s_kv + ((size_t)(l * NC + c) * a.t_mem) * kHeadStride;
+            for (int i = threadIdx.x; i < a.t_mem * 32; i += kThreads) {
+                const int frame = i >> 5, q = i & 31;              // q < 16: K quad, else V quad
+                const float4 v = __ldg(src + (size_t)frame * (2 * D / 4) + (q >> 4) * (D / 4) + h * (HD / 4) + (q & 15));
+                reinterpret_cast<float4*>(dst + (size_t)frame * kHeadStride)[q] = v;
+            }
+        }
+}
+
+// One token step of the G rows of a cluster, executed by the CTA of head h.  Row r: token words[r] at position t; rows are
+// grouped RPC per clip (greedy: 1, beam search: the beams of a clip); anc(r, j) = row slot whose cache entry at position
+// j belongs to row r's history (greedy: r).  On return every CTA holds the final hidden states in s.x and its own slice
+// of the logits in s.logit[r][ldl] (vocabulary quads [vc0, vc0 + VQ)); emit(r, j, v) sees every logit of the slice.
+template <int G, int RPC, class Anc, class Emit>
+__device__ __forceinline__ void heads_step(const DecodeArgs& a, const HeadBufs& s, int h, int t, const int* words,
+                                           const unsigned char (*padflag)[8], const int* nmem, Anc anc, int& xc,
+                                           int vc0, int VQ, int ldl, Emit emit) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const DecW& W = a.w;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int dffl = W.dff / NH, VC = (W.vocab + 3) >> 2;
+    constexpr int NC = G / RPC;
+    // push one row-slice value into the same slot of all four CTAs
+    auto push_red = [&](int r, int j, float v) {
+        float* slot = s.red + (((size_t)(xc & 1) * NH + h) * G + r) * D + j;
+#pragma unroll
+        for (int pr = 0; pr < NH; ++pr) *cluster.map_shared_rank(slot, pr) = v;
+    };
+    AC_DEC_STAMP(0);
+    for (int i = tid; i < G * D; i += kThreads) {
+        const int r = i / D, f = i - r * D;
+        s.x[i] = __ldg(W.emb + (size_t)words[r] * D + f) * 16.0f + __ldg(W.pe + (size_t)t * D + f);
+    }
+    __syncthreads();
+    for (int l = 0; l < W.nlayers; ++l) {
+        const LayerW& L = W.layer[l];
+        // ---- self attention, head h: q | k | v columns of my head (local), cache row t in shared memory
+        AC_DEC_STAMP(1 + 12 * l);
+        gemv_slice<G>(L.sa_in_wt, 3 * D / 4, [&](int cl) { return (cl >> 4) * (D / 4) + h * (HD / 4) + (cl & 15); }, 48, 0, D,
+                      s.x, D, s.part, [&](int r, int j, float v) {
+                          v += __ldg(L.sa_in_b + (j >> 6) * D + h * HD + (j & 63));
+                          if (j < HD) s.qkv[r * 3 * HD + j] = v;
+                          else s.self[((size_t)(l * G + r) * a.max_len + t) * s.self_stride + (j - HD)] = v;
+                      });
+        __syncthreads();
+        AC_DEC_STAMP(3 + 12 * l);
+        if (warp < G) {
+            const int r = warp;
+            const float* kc = s.self + ((size_t)l * G * a.max_len) * s.self_stride;
+            attend_head(s.qkv + r * 3 * HD, 0.125f, t + 1,
+                        [&](int j) { return kc + ((size_t)anc(r, j) * a.max_len + j) * s.self_stride; },
+                        [&](int j) { return kc + ((size_t)anc(r, j) * a.max_len + j) * s.self_stride + HD; },
+                        [&](int j) { return padflag[j][anc(r, j)] != 0; }, s.att + r * HD);
+        }
+        __syncthreads();
+        AC_DEC_STAMP(4 + 12 * l);
+        gemv_slice<G>(L.sa_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s.att, HD, s.part, push_red);
+        cluster.sync();
+        AC_DEC_STAMP(5 + 12 * l);
+        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, L.sa_out_b, L.n1_g, L.n1_b);
+        ++xc;
+        __syncthreads();
+        // ---- cross attention, head h
+        AC_DEC_STAMP(6 + 12 * l);
+        gemv_slice<G>(L.ca_q_wt, D / 4, [&](int cl) { return h * (HD / 4) + cl; }, HD / 4, 0, D, s.x, D, s.part,
+                      [&](int r, int j, float v) { s.qkv[r * 3 * HD + j] = v + __ldg(L.ca_q_b + h * HD + j); });
+        __syncthreads();
+        AC_DEC_STAMP(7 + 12 * l);
+        if (warp < G) {
+            const int r = warp;
+            const float* km = s.kv + ((size_t)(l * NC + r / RPC) * a.t_mem) * kHeadStride;
+            const int n_mem = nmem[r / RPC];
+            attend_head(s.qkv + r * 3 * HD, 0.125f, a.t_mem,
+                        [&](int j) { return km + (size_t)j * kHeadStride; },
+                        [&](int j) { return km + (size_t)j * kHeadStride + HD; },
+                        [&](int j) { return j >= n_mem; }, s.att + r * HD);
+        }
+        __syncthreads();
+        AC_DEC_STAMP(8 + 12 * l);
+        gemv_slice<G>(L.ca_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s.att, HD, s.part, push_red);
+        cluster.sync();
+        AC_DEC_STAMP(9 + 12 * l);
+        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, L.ca_out_b, L.n2_g, L.n2_b);
+        ++xc;
+        __syncthreads();
+        // ---- feed forward: my quarter of the hidden units, then their share of the output
+        AC_DEC_STAMP(10 + 12 * l);
+        gemv_slice<G>(L.ff1_wt, W.dff / 4, [&](int cl) { return h * (dffl / 4) + cl; }, dffl / 4, 0, D, s.x, D, s.part,
+                      [&](int r, int j, float v) { s.hid[r * dffl + j] = fmaxf(v + __ldg(L.ff1_b + h * dffl + j), 0.0f); });
+        __syncthreads();
+        AC_DEC_STAMP(11 + 12 * l);
+        gemv_slice<G>(L.ff2_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * dffl, (h + 1) * dffl, s.hid, dffl, s.part, push_red);
+        cluster.sync();
+        AC_DEC_STAMP(12 + 12 * l);
+        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, L.ff2_b, L.n3_g, L.n3_b);
+        ++xc;
+        __syncthreads();
+    }
+    AC_DEC_STAMP(40);
+    // ---- classifier (no bias) over my slice of the vocabulary
+    gemv_slice<G>(W.cls_wt, VC, [&](int cl) { return vc0 + cl; }, VQ, 0, D, s.x, D, s.part,
+                  [&](int r, int j, float v) { s.logit[r * ldl + j] = v; emit(r, j, v); });
+    __syncthreads();
+    AC_DEC_STAMP(41);
+}
+
+// (max, sum exp(x - max)) of every row's logits slice: WPR warps scan a row (each with its own maximum), results in
+// sm[r][part] / sse[r][part] (+ the first arg-max in sidx when it is wanted).  n_my = valid columns of the slice.
+template <int G, int WPR>
+__device__ __forceinline__ void heads_slice_max_sumexp(const float* s_logit, int ldl, int n_my, int col0, float (*sm)[WPR],
+                                                       float (*sse)[WPR], int (*sidx)[WPR]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < G * WPR) {
+        const int r = warp / WPR, pt = warp - r * WPR;
+        const int chunk = (n_my + WPR - 1) / WPR;
+        const int n0 = pt * chunk, n1 = min(n_my, n0 + chunk);
+        const float* lg = s_logit + r * ldl;
+        float best = -INFINITY; int bi = 0x7fffffff;
+        for (int n = n0 + lane; n < n1; n += 32) {
+            const float v = lg[n];
+            if (v > best) { best = v; bi = col0 + n; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        float se = 0.f;
+        for (int n = n0 + lane; n < n1; n += 32) se += expf(lg[n] - best);
+        se = warp_sum(se);
+        if (lane == 0) { sm[r][pt] = best; sidx[r][pt] = bi; sse[r][pt] = se; }
+    }
+    __syncthreads();
 }
 
 template <int G>
 __global__ void __launch_bounds__(kThreads, 1)
 greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
     extern __shared__ __align__(16) float smem[];
-    float* s_x = smem + lay.x; float* s_qkv = smem + lay.qkv; float* s_att = smem + lay.att; float* s_hid = smem + lay.hid;
-    float* s_part = smem + lay.part; float* s_red = smem + lay.red; float* s_logit = smem + lay.logit;
-    float* s_cls = smem + lay.cls; float* s_kv = smem + lay.kv; float* s_self = smem + lay.self;
+    const HeadBufs s{smem + lay.x, smem + lay.qkv, smem + lay.att, smem + lay.hid, smem + lay.part,
+                     smem + lay.red, smem + lay.logit, smem + lay.kv, smem + lay.self, lay.self_stride};
+    float* s_cls = smem + lay.cls;
     __shared__ unsigned char s_pad[kMaxLen][8];
     __shared__ int s_word[G];
     __shared__ int s_nmem[G];
@@ -569,32 +719,14 @@ greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
     const int V = W.vocab, VC = (V + 3) >> 2;
     const int vc0 = (int)((int64_t)VC * h / NH), vc1 = (int)((int64_t)VC * (h + 1) / NH);   // my vocabulary quads
     const int VQ = vc1 - vc0, ldl = ((VC + NH - 1) / NH) * 4;
-    const int dffl = W.dff / NH;
-    auto clip_of = [&](int r) { return min(clip0 + r, a.n_clips - 1); };   // rows past the batch replay the last clip
-    // cross-attention K | V of my head for the cluster's clips: [layer][row][frame][K 64 | V 64 | pad]
-    for (int l = 0; l < W.nlayers; ++l)
-        for (int r = 0; r < G; ++r) {
-            const float4* src = reinterpret_cast<const float4*>(a.kv_mem + (((size_t)l * a.n_clips + clip_of(r)) * a.t_mem) * 2 * D);
-            float* dst = s_kv + ((size_t)(l * G + r) * a.t_mem) * kHeadStride;
-            for (int i = tid; i < a.t_mem * 32; i += kThreads) {
-                const int frame = i >> 5, q = i & 31;              // q < 16: K quad, else V quad
-                const float4 v = __ldg(src + (size_t)frame * (2 * D / 4) + (q >> 4) * (D / 4) + h * (HD / 4) + (q & 15));
-                reinterpret_cast<float4*>(dst + (size_t)frame * kHeadStride)[q] = v;
-            }
-        }
-    if (tid < G) s_nmem[tid] = min((int)min((int64_t)a.t_mem, a.mem_len[clip_of(tid)]), a.t_mem);
+    heads_stage_kv<G>(a, clip0, h, s.kv);
+    if (tid < G) s_nmem[tid] = min((int)min((int64_t)a.t_mem, a.mem_len[min(clip0 + tid, a.n_clips - 1)]), a.t_mem);
     int word[G]; bool finished[G]; bool valid[G];
 #pragma unroll
     for (int r = 0; r < G; ++r) { word[r] = a.start_idx; valid[r] = clip0 + r < a.n_clips; finished[r] = !valid[r]; }
-    int xc = 0;                                          // exchange counter: s_red / s_cls are ping-pong buffers
+    int xc = 0;                                          // exchange counter: s.red / s_cls are ping-pong buffers
     cluster.sync();   // every CTA of the cluster is resident before the first push into its peers' shared memory
     const bool full_outputs = a.logit_out != nullptr || a.embed_out != nullptr;
-    // push one row-slice value into the same slot of all four CTAs
-    auto push_red = [&](int r, int j, float v) {
-        float* slot = s_red + (((size_t)(xc & 1) * NH + h) * G + r) * D + j;
-#pragma unroll
-        for (int pr = 0; pr < NH; ++pr) *cluster.map_shared_rank(slot, pr) = v;
-    };
     for (int t = 0; t < a.max_len; ++t) {
         bool all_done = true;
 #pragma unroll
@@ -608,111 +740,15 @@ greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
             for (int r = 0; r < G; ++r) { s_pad[t][r] = (word[r] == a.pad_idx); s_word[r] = word[r]; }
         }
         __syncthreads();
-        AC_DEC_STAMP(0);
-        for (int i = tid; i < G * D; i += kThreads) {
-            const int r = i / D, f = i - r * D;
-            s_x[i] = __ldg(W.emb + (size_t)s_word[r] * D + f) * 16.0f + __ldg(W.pe + (size_t)t * D + f);
-        }
-        __syncthreads();
-        for (int l = 0; l < W.nlayers; ++l) {
-            const LayerW& L = W.layer[l];
-            // ---- self attention, head h: q | k | v columns of my head (local), cache row t in shared memory
-            AC_DEC_STAMP(1 + 12 * l);
-            gemv_slice<G>(L.sa_in_wt, 3 * D / 4, [&](int cl) { return (cl >> 4) * (D / 4) + h * (HD / 4) + (cl & 15); }, 48, 0, D,
-                          s_x, D, s_part, [&](int r, int j, float v) {
-                              v += __ldg(L.sa_in_b + (j >> 6) * D + h * HD + (j & 63));
-                              if (j < HD) s_qkv[r * 3 * HD + j] = v;
-                              else s_self[((size_t)(l * G + r) * a.max_len + t) * kHeadStride + (j - HD)] = v;
-                          });
-            __syncthreads();
-            AC_DEC_STAMP(3 + 12 * l);
-            if (warp < G) {
-                const int r = warp;
-                const float* kc = s_self + ((size_t)(l * G + r) * a.max_len) * kHeadStride;
-                attend_head(s_qkv + r * 3 * HD, 0.125f, t + 1,
-                            [&](int j) { return kc + (size_t)j * kHeadStride; },
-                            [&](int j) { return kc + (size_t)j * kHeadStride + HD; },
-                            [&](int j) { return s_pad[j][r] != 0; }, s_att + r * HD);
-            }
-            __syncthreads();
-            AC_DEC_STAMP(4 + 12 * l);
-            gemv_slice<G>(L.sa_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s_att, HD, s_part, push_red);
-            cluster.sync();
-            AC_DEC_STAMP(5 + 12 * l);
-            reduce_add_layernorm<G>(s_x, s_red + (size_t)(xc & 1) * NH * G * D, L.sa_out_b, L.n1_g, L.n1_b);
-            ++xc;
-            __syncthreads();
-            // ---- cross attention, head h
-            AC_DEC_STAMP(6 + 12 * l);
-            gemv_slice<G>(L.ca_q_wt, D / 4, [&](int cl) { return h * (HD / 4) + cl; }, HD / 4, 0, D, s_x, D, s_part,
-                          [&](int r, int j, float v) { s_qkv[r * 3 * HD + j] = v + __ldg(L.ca_q_b + h * HD + j); });
-            __syncthreads();
-            AC_DEC_STAMP(7 + 12 * l);
-            if (warp < G) {
-                const int r = warp;
-                const float* km = s_kv + ((size_t)(l * G + r) * a.t_mem) * kHeadStride;
-                const int n_mem = s_nmem[r];
-                attend_head(s_qkv + r * 3 * HD, 0.125f, a.t_mem,
-                            [&](int j) { return km + (size_t)j * kHeadStride; },
-                            [&](int j) { return km + (size_t)j * kHeadStride + HD; },
-                            [&](int j) { return j >= n_mem; }, s_att + r * HD);
-            }
-            __syncthreads();
-            AC_DEC_STAMP(8 + 12 * l);
-            gemv_slice<G>(L.ca_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s_att, HD, s_part, push_red);
-            cluster.sync();
-            AC_DEC_STAMP(9 + 12 * l);
-            reduce_add_layernorm<G>(s_x, s_red + (size_t)(xc & 1) * NH * G * D, L.ca_out_b, L.n2_g, L.n2_b);
-            ++xc;
-            __syncthreads();
-            // ---- feed forward: my quarter of the hidden units, then their share of the output
-            AC_DEC_STAMP(10 + 12 * l);
-            gemv_slice<G>(L.ff1_wt, W.dff / 4, [&](int cl) { return h * (dffl / 4) + cl; }, dffl / 4, 0, D, s_x, D, s_part,
-                          [&](int r, int j, float v) { s_hid[r * dffl + j] = fmaxf(v + __ldg(L.ff1_b + h * dffl + j), 0.0f); });
-            __syncthreads();
-            AC_DEC_STAMP(11 + 12 * l);
-            gemv_slice<G>(L.ff2_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * dffl, (h + 1) * dffl, s_hid, dffl, s_part, push_red);
-            cluster.sync();
-            AC_DEC_STAMP(12 + 12 * l);
-            reduce_add_layernorm<G>(s_x, s_red + (size_t)(xc & 1) * NH * G * D, L.ff2_b, L.n3_g, L.n3_b);
-            ++xc;
-            __syncthreads();
-        }
-        AC_DEC_STAMP(40);
-        // ---- classifier (no bias) over my slice of the vocabulary
-        gemv_slice<G>(W.cls_wt, VC, [&](int cl) { return vc0 + cl; }, VQ, 0, D, s_x, D, s_part,
-                      [&](int r, int j, float v) {
-                          s_logit[r * ldl + j] = v;
-                          const int col = 4 * vc0 + j;
-                          if (a.logit_out != nullptr && col < V && valid[r])
-                              a.logit_out[((size_t)(clip0 + r) * a.max_len + t) * V + col] = v;
-                      });
-        __syncthreads();
-        AC_DEC_STAMP(41);
-        // my slice -> (max, first arg-max, sum exp(x - max)) per row: WPR warps scan a row (each its own max), one warp
-        // merges them and pushes the three numbers to all four CTAs
-        if (warp < G * WPR) {
-            const int r = warp / WPR, pt = warp - r * WPR;
-            const int n_my = min(4 * VQ, V - 4 * vc0), chunk = (n_my + WPR - 1) / WPR;
-            const int n0 = pt * chunk, n1 = min(n_my, n0 + chunk);
-            const float* lg = s_logit + r * ldl;
-            float best = -INFINITY; int bi = 0x7fffffff;
-            for (int n = n0 + lane; n < n1; n += 32) {
-                const float v = lg[n];
-                if (v > best) { best = v; bi = 4 * vc0 + n; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            float se = 0.f;
-            for (int n = n0 + lane; n < n1; n += 32) se += expf(lg[n] - best);
-            se = warp_sum(se);
-            if (lane == 0) { s_cmax[r][pt] = best; s_cidx[r][pt] = bi; s_cse[r][pt] = se; }
-        }
-        __syncthreads();
+        heads_step<G, 1>(a, s, h, t, s_word, s_pad, s_nmem, [](int r, int) { return r; }, xc, vc0, VQ, ldl,
+                         [&](int r, int j, float v) {
+                             const int col = 4 * vc0 + j;
+                             if (a.logit_out != nullptr && col < V && valid[r])
+                                 a.logit_out[((size_t)(clip0 + r) * a.max_len + t) * V + col] = v;
+                         });
+        // my slice -> (max, first arg-max, sum exp(x - max)) per row; one warp merges the WPR parts and pushes the three
+        // numbers to all four CTAs
+        heads_slice_max_sumexp<G, WPR>(s.logit, ldl, min(4 * VQ, V - 4 * vc0), 4 * vc0, s_cmax, s_cse, s_cidx);
         if (warp < G && lane < NH) {
             const int r = warp;
             float best = -INFINITY; int bi = 0x7fffffff;
@@ -742,7 +778,7 @@ greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
 #pragma unroll
                 for (int pr = 0; pr < NH; ++pr) se += c[(pr * G + r) * 4 + 2] * expf(c[(pr * G + r) * 4] - best);
                 if (a.embed_out && writer && valid[r] && tid < D)
-                    a.embed_out[((size_t)(clip0 + r) * a.max_len + t) * D + tid] = s_x[r * D + tid];
+                    a.embed_out[((size_t)(clip0 + r) * a.max_len + t) * D + tid] = s.x[r * D + tid];
                 word[r] = finished[r] ? a.end_idx : bi;
                 if (a.forced != nullptr && valid[r]) {
                     const int64_t f = a.forced[(size_t)(clip0 + r) * a.max_len + t];
@@ -757,6 +793,223 @@ greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
         }
         AC_DEC_STAMP(42);
     }
+    cluster.sync();   // nobody exits while a peer may still push into its shared memory
+}
+
+// ------------------------------------------------------------------------------------ beam search, one CTA per head
+// The same 4-CTA layout for beam search: a cluster decodes CL clips with R beams each (G = CL * R rows share every weight
+// load).  The scoring of base.py:282-304 is distributed over the vocabulary slices: two (max, sum-exp) exchanges give the
+// two log-softmax normalisers of every row, each CTA keeps its R best (score, flat index) candidates per clip and the four
+// candidate lists are merged identically in every CTA -- the global top-R is a subset of the four local top-R.
+template <int R, int CL>
+__global__ void __launch_bounds__(kThreads, 1)
+beam_heads_kernel(DecodeArgs a, HeadSmem lay) {
+    constexpr int G = R * CL;
+    static_assert(G <= 8, "pad flags hold 8 rows");
+    extern __shared__ __align__(16) float smem[];
+    // self-attention cache of my head: shared memory, or (lay.self_global) my private slice of the global cache workspace
+    float* self_cache = lay.self_global
+        ? a.kv_cache + (size_t)blockIdx.x * ((size_t)a.w.nlayers * G * a.max_len * 2 * HD)
+        : smem + lay.self;
+    const HeadBufs s{smem + lay.x, smem + lay.qkv, smem + lay.att, smem + lay.hid, smem + lay.part,
+                     smem + lay.red, smem + lay.logit, smem + lay.kv, self_cache, lay.self_stride};
+    float* s_cls = smem + lay.cls;                        // [2][NH][G][4] exchange slots
+    __shared__ unsigned char s_pad[kMaxLen][8];
+    __shared__ int s_anc[2][G][kMaxLen];                  // row slot (of the cluster) holding the ancestor at a position
+    __shared__ int s_seq[2][G][kMaxLen];
+    __shared__ int s_words[G];
+    __shared__ float s_score[G];
+    __shared__ float s_newscore[G];
+    __shared__ int s_newidx[G];                           // flat index (beam of the clip) * V + word
+    __shared__ float s_lval[G];
+    __shared__ int s_lidx[G];
+    __shared__ float s_lse1[G], s_lse2[G], s_max[G];
+    __shared__ int s_best_seq[CL][kMaxLen];
+    __shared__ int s_best_len[CL], s_ndone[CL], s_stop[CL];
+    __shared__ float s_best_score[CL];
+    __shared__ int s_nmem[CL];
+    __shared__ float s_rv[kWarps];
+    __shared__ int s_ri[kWarps];
+    constexpr int WPR = 32 / G >= 8 ? 8 : 32 / G;
+    __shared__ float s_cmax[G][WPR], s_cse[G][WPR];
+    __shared__ int s_cidx[G][WPR];
+    cg::cluster_group cluster = cg::this_cluster();
+    const DecW& W = a.w;
+    const int h = (int)cluster.block_rank();
+    const int clip0 = (blockIdx.x / NH) * CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int V = W.vocab, VC = (V + 3) >> 2;
+    const int vc0 = (int)((int64_t)VC * h / NH), vc1 = (int)((int64_t)VC * (h + 1) / NH);
+    const int VQ = vc1 - vc0, ldl = ((VC + NH - 1) / NH) * 4;
+    const int n_my = min(4 * VQ, V - 4 * vc0), col0 = 4 * vc0;
+    const float inv_t = 1.0f / a.temp;
+    heads_stage_kv<CL>(a, clip0, h, s.kv);
+    if (tid < CL) {
+        s_nmem[tid] = min((int)min((int64_t)a.t_mem, a.mem_len[min(clip0 + tid, a.n_clips - 1)]), a.t_mem);
+        s_ndone[tid] = 0; s_best_len[tid] = 0; s_best_score[tid] = -INFINITY;
+        s_stop[tid] = clip0 + tid < a.n_clips ? 0 : 1;      // slots past the batch never report
+    }
+    if (tid < G) { s_words[tid] = a.start_idx; s_score[tid] = 0.f; }
+    for (int i = tid; i < G * kMaxLen; i += kThreads) s_anc[0][i / kMaxLen][i % kMaxLen] = i / kMaxLen;
+    int xc = 0;
+    cluster.sync();   // peers resident before the first distributed-shared-memory push
+    int cur = 0;
+    // one (value, value) pair per row from every CTA: push, barrier, then every CTA reads the four contributions
+    auto exchange2 = [&](float v0, float v1, int r) {      // called by lanes < NH of warp r
+        float* slot = cluster.map_shared_rank(s_cls + (((size_t)(xc & 1) * NH + h) * G + r) * 4, lane);
+        slot[0] = v0; slot[1] = v1;
+    };
+    for (int t = 0; t < a.max_len; ++t) {
+        if (tid < G) { s_pad[t][tid] = (s_words[tid] == a.pad_idx); s_anc[cur][tid][t] = tid; }
+        __syncthreads();
+        heads_step<G, R>(a, s, h, t, s_words, s_pad, s_nmem, [&](int r, int j) { return s_anc[cur][r][j]; }, xc, vc0, VQ, ldl,
+                         [](int, int, float) {});
+        // ---- lp = log_softmax(log_softmax(logit) / temp) + running score   (base.py:282-290), over vocabulary slices
+        // first normaliser: lse1 = max + log sum exp(x - max)
+        heads_slice_max_sumexp<G, WPR>(s.logit, ldl, n_my, col0, s_cmax, s_cse, s_cidx);
+        if (warp < G && lane < NH) {
+            const int r = warp;
+            float best = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < WPR; ++q) best = fmaxf(best, s_cmax[r][q]);
+            float se = 0.f;
+#pragma unroll
+            for (int q = 0; q < WPR; ++q) se += s_cse[r][q] > 0.f ? s_cse[r][q] * expf(s_cmax[r][q] - best) : 0.f;
+            exchange2(best, se, r);
+        }
+        cluster.sync();
+        if (tid < G) {
+            const float* c = s_cls + (size_t)(xc & 1) * NH * G * 4;
+            float m = -INFINITY;
+#pragma unroll
+            for (int pr = 0; pr < NH; ++pr) m = fmaxf(m, c[(pr * G + tid) * 4]);
+            float se = 0.f;
+#pragma unroll
+            for (int pr = 0; pr < NH; ++pr) se += c[(pr * G + tid) * 4 + 1] * expf(c[(pr * G + tid) * 4] - m);
+            s_max[tid] = m; s_lse1[tid] = m + logf(se);
+        }
+        ++xc;
+        __syncthreads();
+        // second normaliser over y = (x - lse1) / temp, whose maximum is (max - lse1) / temp
+        if (warp < G * WPR) {
+            const int r = warp / WPR, pt = warp - r * WPR;
+            const int chunk = (n_my + WPR - 1) / WPR;
+            const int n0 = pt * chunk, n1 = min(n_my, n0 + chunk);
+            const float* lg = s.logit + r * ldl;
+            const float l1 = s_lse1[r], m2 = (s_max[r] - l1) * inv_t;
+            float se = 0.f;
+            for (int n = n0 + lane; n < n1; n += 32) se += expf((lg[n] - l1) * inv_t - m2);
+            se = warp_sum(se);
+            if (lane == 0) s_cse[r][pt] = se;
+        }
+        __syncthreads();
+        if (warp < G && lane < NH) {
+            const int r = warp;
+            float se = 0.f;
+#pragma unroll
+            for (int q = 0; q < WPR; ++q) se += s_cse[r][q];
+            exchange2(se, 0.f, r);
+        }
+        cluster.sync();
+        if (tid < G) {
+            const float* c = s_cls + (size_t)(xc & 1) * NH * G * 4;
+            float se = 0.f;
+#pragma unroll
+            for (int pr = 0; pr < NH; ++pr) se += c[(pr * G + tid) * 4];
+            s_lse2[tid] = (s_max[tid] - s_lse1[tid]) * inv_t + logf(se);
+        }
+        ++xc;
+        __syncthreads();
+        // my slice's R best candidates of every clip (step 0: the clip's first row only), R rounds of block arg-max;
+        // ties go to the lower flat index, as in the single-slice kernel
+        for (int c = 0; c < CL; ++c) {
+            const int rows = t == 0 ? 1 : R;
+            for (int k = 0; k < R; ++k) {
+                float best = -INFINITY; int bi = 0x7fffffff;
+                for (int i = tid; i < rows * n_my; i += kThreads) {
+                    const int rl = i / n_my, n = i - rl * n_my;
+                    const int r = c * R + rl;
+                    const int flat = rl * V + col0 + n;
+                    bool taken = false;
+                    for (int q = 0; q < k; ++q) taken |= (s_lidx[c * R + q] == flat);
+                    const float v = s_score[r] + ((s.logit[r * ldl + n] - s_lse1[r]) * inv_t - s_lse2[r]);
+                    if (!taken && (v > best || (v == best && flat < bi))) { best = v; bi = flat; }
+                }
+                block_argmax(best, bi, s_rv, s_ri);
+                if (tid == 0) { s_lval[c * R + k] = best; s_lidx[c * R + k] = bi; }
+                __syncthreads();
+            }
+        }
+        if (warp < G && lane < NH) exchange2(s_lval[warp], __int_as_float(s_lidx[warp]), warp);
+        cluster.sync();
+        // merge the 4 R candidates of a clip (identical in every CTA) and update the clip's beams
+        if (tid < CL && !s_stop[tid]) {
+            const int c = tid;
+            const float* cs = s_cls + (size_t)(xc & 1) * NH * G * 4;
+            bool used[NH * R];
+            for (int i = 0; i < NH * R; ++i) used[i] = false;
+            for (int k = 0; k < R; ++k) {
+                float best = -INFINITY; int bi = 0x7fffffff, bj = -1;
+                for (int i = 0; i < NH * R; ++i) {
+                    const int pr = i / R, q = i - pr * R;
+                    const float v = cs[(pr * G + c * R + q) * 4];
+                    const int vi = __float_as_int(cs[(pr * G + c * R + q) * 4 + 1]);
+                    if (!used[i] && vi != 0x7fffffff && (v > best || (v == best && vi < bi))) { best = v; bi = vi; bj = i; }
+                }
+                if (bj >= 0) used[bj] = true;
+                s_newscore[c * R + k] = best; s_newidx[c * R + k] = bi;
+            }
+        }
+        ++xc;
+        __syncthreads();
+        // reorder beams: histories follow their parent (base.py:291-304)
+        const int nxt = cur ^ 1;
+        for (int i = tid; i < G * kMaxLen; i += kThreads) {
+            const int r = i / kMaxLen, j = i % kMaxLen, c = r / R;
+            if (s_stop[c]) continue;
+            const int parent = c * R + s_newidx[r] / V;
+            if (j <= t) s_anc[nxt][r][j] = s_anc[cur][parent][j];
+            if (j < t) s_seq[nxt][r][j] = s_seq[cur][parent][j];
+            if (j == t) s_seq[nxt][r][j] = s_newidx[r] % V;
+        }
+        __syncthreads();
+        if (tid < CL && !s_stop[tid]) {
+            const int c = tid;
+            for (int rl = 0; rl < R; ++rl) {
+                const int r = c * R + rl;
+                const int wd = s_newidx[r] % V;
+                float sc = s_newscore[r];
+                const bool is_end = (wd == a.end_idx) || (t == a.max_len - 1);
+                if (is_end) {
+                    const float fs = sc / (float)(t + 1);
+                    s_ndone[c]++;
+                    if (fs > s_best_score[c]) {   // stable best-first: earlier beam wins ties
+                        s_best_score[c] = fs; s_best_len[c] = t + 1;
+                        for (int j = 0; j <= t; ++j) s_best_seq[c][j] = s_seq[nxt][r][j];
+                    }
+                    sc -= 1000.0f;
+                }
+                s_score[r] = sc; s_words[r] = wd;
+            }
+            if (s_ndone[c] == R) s_stop[c] = 1;   // equality, as the reference
+        }
+        __syncthreads();
+        // a stopped clip keeps its last histories in BOTH buffers (its rows are still stepped, their results unused)
+        for (int i = tid; i < G * kMaxLen; i += kThreads) {
+            const int r = i / kMaxLen, j = i % kMaxLen;
+            if (s_stop[r / R] && j <= t) { s_anc[nxt][r][j] = s_anc[cur][r][j]; }
+        }
+        cur = nxt;
+        bool all_stop = true;
+#pragma unroll
+        for (int c = 0; c < CL; ++c) all_stop = all_stop && s_stop[c] != 0;
+        __syncthreads();
+        if (all_stop) break;
+    }
+    if (h == 0)
+        for (int i = tid; i < CL * a.max_len; i += kThreads) {
+            const int c = i / a.max_len, j = i - c * a.max_len;
+            if (clip0 + c < a.n_clips) a.seq[(size_t)(clip0 + c) * a.max_len + j] = j < s_best_len[c] ? s_best_seq[c][j] : a.end_idx;
+        }
     cluster.sync();   // nobody exits while a peer may still push into its shared memory
 }
 
@@ -1171,7 +1424,7 @@ static int trm_greedy_impl(const ac_trm_t* dec, const float* attn_emb, const int
         int G = batch * NH <= kNumSMs ? 1 : 2;
         if (const char* e = getenv("AC_GREEDY_HEADS")) G = atoi(e);      // 0 disables
         if (G == 1 || G == 2 || G == 4) {
-            const HeadSmem lay = head_smem(G, dec->w.nlayers, dec->w.dff, dec->w.vocab, t_mem, max_len);
+            const HeadSmem lay = head_smem(G, G, dec->w.nlayers, dec->w.dff, dec->w.vocab, t_mem, max_len);
             if (lay.total * sizeof(float) <= (size_t)kDecSmemLimit) {
                 const size_t sm = lay.total * sizeof(float);
                 AC_TIMED("trm_greedy", st);
@@ -1233,6 +1486,40 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
     a.w = dec->w; a.kv_mem = kvmem; a.n_clips = batch; a.mem_len = attn_emb_len; a.kv_cache = cache; a.logits_ws = lws;
     a.t_mem = t_mem; a.max_len = max_len; a.start_idx = start_idx; a.end_idx = end_idx; a.pad_idx = pad_idx;
     a.seq = seq; a.beam = beam; a.temp = temp;
+    // Up to 37 clips (4 CTAs per clip fit the SMs): one CTA per attention head (beam_heads_kernel), beam-3 2.38 -> 1.47 ms.
+    // Beyond, the column-split kernel with 2 CTAs per clip stays faster than two waves of 4-CTA clusters (2.76 vs 2.94 ms at
+    // 64 clips) and than two clips x three beams per cluster (3.0-3.5 ms: six rows leave the split-K scratch room for a
+    // third of the threads only).  AC_BEAM_HEADS=0 / 1 forces the choice.
+    {
+        const char* e = getenv("AC_BEAM_HEADS");
+        const bool want = e ? atoi(e) != 0 : batch * NH <= kNumSMs;
+        if (want && dec->w.dff % (4 * NH) == 0) {
+            HeadSmem lay = head_smem(beam, 1, dec->w.nlayers, dec->w.dff, dec->w.vocab, t_mem, max_len);
+            if (lay.total * sizeof(float) > (size_t)kDecSmemLimit &&
+                (size_t)batch * NH * dec->w.nlayers * beam * max_len * 2 * HD <= s.cache)
+                lay = head_smem(beam, 1, dec->w.nlayers, dec->w.dff, dec->w.vocab, t_mem, max_len, true);
+            if (lay.total * sizeof(float) <= (size_t)kDecSmemLimit) {
+                const size_t hsm = lay.total * sizeof(float);
+                AC_TIMED("trm_beam", st);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(batch * NH); cfg.blockDim = dim3(kThreads);
+                cfg.dynamicSmemBytes = hsm; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = NH; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+#define AC_BH(RR)                                                                                                      \
+    case RR:                                                                                                           \
+        AC_CUDA(cudaFuncSetAttribute(beam_heads_kernel<RR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm)); \
+        AC_CUDA(cudaLaunchKernelEx(&cfg, beam_heads_kernel<RR, 1>, a, lay));                                           \
+        break;
+                switch (beam) { AC_BH(1) AC_BH(2) AC_BH(3) AC_BH(4) AC_BH(5) }
+#undef AC_BH
+                AC_LAUNCHED("beam_heads_kernel");
+                return AC_OK;
+            }
+        }
+    }
     size_t sm = dec_smem_floats(beam) * sizeof(float);
     const size_t kvb = kv_smem_floats(dec->w.nlayers, 1, t_mem) * sizeof(float);
     a.kv_in_smem = sm + kvb <= (size_t)kDecSmemLimit ? 1 : 0;
