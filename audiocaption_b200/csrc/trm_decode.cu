@@ -521,7 +521,7 @@ __device__ __forceinline__ void reduce_add_layernorm(float* x, const float* red,
             const int c = lane + 32 * i;
             const float add = (red[(0 * G + r) * D + c] + red[(1 * G + r) * D + c]) +
                               (red[(2 * G + r) * D + c] + red[(3 * G + r) * D + c]);
-            v[i] = x[r * D + c] + (add + __ldg(bias + c));
+            v[i] = x[r * D + c] + (add + bias[c]);
             s += v[i];
         }
         const float mean = warp_sum(s) * (1.0f / D);
@@ -532,12 +532,13 @@ __device__ __forceinline__ void reduce_add_layernorm(float* x, const float* red,
 #pragma unroll
         for (int i = 0; i < D / 32; ++i) {
             const int c = lane + 32 * i;
-            x[r * D + c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+            x[r * D + c] = (v[i] - mean) * rstd * g[c] + b[c];
         }
     }
 }
 
-struct HeadSmem { size_t x, qkv, att, hid, part, red, logit, cls, kv, self, total; int self_global, self_stride; };
+__host__ __device__ constexpr int head_par_stride(int dff) { return 3 * HD + HD + dff / NH + 9 * D; }
+struct HeadSmem { size_t x, qkv, att, hid, part, red, logit, cls, kv, self, par, total; int self_global, self_stride; };
 // self_global: the self-attention K/V of the CTA's head live in its private slice of the global cache workspace (stride
 // 2 HD, read back through L2) instead of shared memory -- for the row counts whose cache does not fit (beam 4 and 5)
 static HeadSmem head_smem(int G, int clips, int nlayers, int dff, int vocab, int t_mem, int max_len, bool self_global = false) {
@@ -547,13 +548,39 @@ static HeadSmem head_smem(int G, int clips, int nlayers, int dff, int vocab, int
     h.hid = take((size_t)G * (dff / NH)); h.part = take(kHeadPart); h.red = take((size_t)2 * NH * G * D);
     h.logit = take((size_t)G * (cdiv((vocab + 3) / 4, NH) * 4)); h.cls = take((size_t)2 * NH * G * 4);
     h.kv = take((size_t)nlayers * clips * t_mem * kHeadStride);
+    h.par = take((size_t)nlayers * head_par_stride(dff));
     h.self = self_global ? 0 : take((size_t)nlayers * G * max_len * kHeadStride);
     h.self_global = self_global ? 1 : 0; h.self_stride = self_global ? 2 * HD : kHeadStride;
     h.total = o;
     return h;
 }
 
-struct HeadBufs { float *x, *qkv, *att, *hid, *part, *red, *logit, *kv, *self; int self_stride; };
+struct HeadBufs { float *x, *qkv, *att, *hid, *part, *red, *logit, *kv, *self; int self_stride; float* par; };
+
+// Biases and LayerNorm parameters of every layer, staged once per CTA (the streamed weights evict them from L1, and an L2
+// round trip at the end of each GEMV / in front of each LayerNorm is ~10 % of a token step).  Per layer:
+// [sa_in_b of my head: q|k|v 192][ca_q_b of my head 64][ff1_b of my hidden units dff/4][9 x 256: sa_out_b n1_g n1_b
+//  ca_out_b n2_g n2_b ff2_b n3_g n3_b]
+__device__ __forceinline__ void heads_stage_par(const DecW& W, int h, float* par) {
+    const int dffl = W.dff / NH, stride = head_par_stride(W.dff);
+    for (int l = 0; l < W.nlayers; ++l) {
+        const LayerW& L = W.layer[l];
+        float* P = par + (size_t)l * stride;
+        for (int i = threadIdx.x; i < stride; i += kThreads) {
+            float v;
+            if (i < 3 * HD) v = L.sa_in_b[(i >> 6) * D + h * HD + (i & 63)];
+            else if (i < 4 * HD) v = L.ca_q_b[h * HD + (i - 3 * HD)];
+            else if (i < 4 * HD + dffl) v = L.ff1_b[h * dffl + (i - 4 * HD)];
+            else {
+                const int j = i - 4 * HD - dffl, which = j / D, c = j - which * D;
+                const float* src = which == 0 ? L.sa_out_b : which == 1 ? L.n1_g : which == 2 ? L.n1_b : which == 3 ? L.ca_out_b
+                                 : which == 4 ? L.n2_g : which == 5 ? L.n2_b : which == 6 ? L.ff2_b : which == 7 ? L.n3_g : L.n3_b;
+                v = src[c];
+            }
+            P[i] = v;
+        }
+    }
+}
 
 // cross-attention K | V of head h for the cluster's clips [clip0, clip0 + NC): [layer][clip slot][frame][K 64 | V 64 | pad]
 template <int NC>
@@ -598,11 +625,13 @@ __device__ __forceinline__ void heads_step(const DecodeArgs& a, const HeadBufs& 
     __syncthreads();
     for (int l = 0; l < W.nlayers; ++l) {
         const LayerW& L = W.layer[l];
+        const float* P = s.par + (size_t)l * head_par_stride(W.dff);          // staged biases / LayerNorm parameters
+        const float* P9 = P + 4 * HD + dffl;
         // ---- self attention, head h: q | k | v columns of my head (local), cache row t in shared memory
         AC_DEC_STAMP(1 + 12 * l);
         gemv_slice<G>(L.sa_in_wt, 3 * D / 4, [&](int cl) { return (cl >> 4) * (D / 4) + h * (HD / 4) + (cl & 15); }, 48, 0, D,
                       s.x, D, s.part, [&](int r, int j, float v) {
-                          v += __ldg(L.sa_in_b + (j >> 6) * D + h * HD + (j & 63));
+                          v += P[j];
                           if (j < HD) s.qkv[r * 3 * HD + j] = v;
                           else s.self[((size_t)(l * G + r) * a.max_len + t) * s.self_stride + (j - HD)] = v;
                       });
@@ -621,13 +650,13 @@ __device__ __forceinline__ void heads_step(const DecodeArgs& a, const HeadBufs& 
         gemv_slice<G>(L.sa_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s.att, HD, s.part, push_red);
         cluster.sync();
         AC_DEC_STAMP(5 + 12 * l);
-        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, L.sa_out_b, L.n1_g, L.n1_b);
+        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, P9, P9 + D, P9 + 2 * D);
         ++xc;
         __syncthreads();
         // ---- cross attention, head h
         AC_DEC_STAMP(6 + 12 * l);
         gemv_slice<G>(L.ca_q_wt, D / 4, [&](int cl) { return h * (HD / 4) + cl; }, HD / 4, 0, D, s.x, D, s.part,
-                      [&](int r, int j, float v) { s.qkv[r * 3 * HD + j] = v + __ldg(L.ca_q_b + h * HD + j); });
+                      [&](int r, int j, float v) { s.qkv[r * 3 * HD + j] = v + P[3 * HD + j]; });
         __syncthreads();
         AC_DEC_STAMP(7 + 12 * l);
         if (warp < G) {
@@ -644,19 +673,19 @@ __device__ __forceinline__ void heads_step(const DecodeArgs& a, const HeadBufs& 
         gemv_slice<G>(L.ca_out_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * HD, (h + 1) * HD, s.att, HD, s.part, push_red);
         cluster.sync();
         AC_DEC_STAMP(9 + 12 * l);
-        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, L.ca_out_b, L.n2_g, L.n2_b);
+        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, P9 + 3 * D, P9 + 4 * D, P9 + 5 * D);
         ++xc;
         __syncthreads();
         // ---- feed forward: my quarter of the hidden units, then their share of the output
         AC_DEC_STAMP(10 + 12 * l);
         gemv_slice<G>(L.ff1_wt, W.dff / 4, [&](int cl) { return h * (dffl / 4) + cl; }, dffl / 4, 0, D, s.x, D, s.part,
-                      [&](int r, int j, float v) { s.hid[r * dffl + j] = fmaxf(v + __ldg(L.ff1_b + h * dffl + j), 0.0f); });
+                      [&](int r, int j, float v) { s.hid[r * dffl + j] = fmaxf(v + P[4 * HD + j], 0.0f); });
         __syncthreads();
         AC_DEC_STAMP(11 + 12 * l);
         gemv_slice<G>(L.ff2_wt, D / 4, [&](int cl) { return cl; }, D / 4, h * dffl, (h + 1) * dffl, s.hid, dffl, s.part, push_red);
         cluster.sync();
         AC_DEC_STAMP(12 + 12 * l);
-        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, L.ff2_b, L.n3_g, L.n3_b);
+        reduce_add_layernorm<G>(s.x, s.red + (size_t)(xc & 1) * NH * G * D, P9 + 6 * D, P9 + 7 * D, P9 + 8 * D);
         ++xc;
         __syncthreads();
     }
@@ -703,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
     extern __shared__ __align__(16) float smem[];
     const HeadBufs s{smem + lay.x, smem + lay.qkv, smem + lay.att, smem + lay.hid, smem + lay.part,
-                     smem + lay.red, smem + lay.logit, smem + lay.kv, smem + lay.self, lay.self_stride};
+                     smem + lay.red, smem + lay.logit, smem + lay.kv, smem + lay.self, lay.self_stride, smem + lay.par};
     float* s_cls = smem + lay.cls;
     __shared__ unsigned char s_pad[kMaxLen][8];
     __shared__ int s_word[G];
@@ -720,6 +749,7 @@ greedy_heads_kernel(DecodeArgs a, HeadSmem lay) {
     const int vc0 = (int)((int64_t)VC * h / NH), vc1 = (int)((int64_t)VC * (h + 1) / NH);   // my vocabulary quads
     const int VQ = vc1 - vc0, ldl = ((VC + NH - 1) / NH) * 4;
     heads_stage_kv<G>(a, clip0, h, s.kv);
+    heads_stage_par(a.w, h, s.par);
     if (tid < G) s_nmem[tid] = min((int)min((int64_t)a.t_mem, a.mem_len[min(clip0 + tid, a.n_clips - 1)]), a.t_mem);
     int word[G]; bool finished[G]; bool valid[G];
 #pragma unroll
@@ -812,7 +842,7 @@ beam_heads_kernel(DecodeArgs a, HeadSmem lay) {
         ? a.kv_cache + (size_t)blockIdx.x * ((size_t)a.w.nlayers * G * a.max_len * 2 * HD)
         : smem + lay.self;
     const HeadBufs s{smem + lay.x, smem + lay.qkv, smem + lay.att, smem + lay.hid, smem + lay.part,
-                     smem + lay.red, smem + lay.logit, smem + lay.kv, self_cache, lay.self_stride};
+                     smem + lay.red, smem + lay.logit, smem + lay.kv, self_cache, lay.self_stride, smem + lay.par};
     float* s_cls = smem + lay.cls;                        // [2][NH][G][4] exchange slots
     __shared__ unsigned char s_pad[kMaxLen][8];
     __shared__ int s_anc[2][G][kMaxLen];                  // row slot (of the cluster) holding the ancestor at a position
@@ -843,6 +873,7 @@ beam_heads_kernel(DecodeArgs a, HeadSmem lay) {
     const int n_my = min(4 * VQ, V - 4 * vc0), col0 = 4 * vc0;
     const float inv_t = 1.0f / a.temp;
     heads_stage_kv<CL>(a, clip0, h, s.kv);
+    heads_stage_par(a.w, h, s.par);
     if (tid < CL) {
         s_nmem[tid] = min((int)min((int64_t)a.t_mem, a.mem_len[min(clip0 + tid, a.n_clips - 1)]), a.t_mem);
         s_ndone[tid] = 0; s_best_len[tid] = 0; s_best_score[tid] = -INFINITY;
