@@ -453,7 +453,7 @@ __device__ __forceinline__ void gemv_slice(const float* __restrict__ Wt, int ldw
     const int tid = threadIdx.x;
     const int Nl = NQ * 4, K = k1 - k0;
     const int KS = max(1, min(min(kThreads / NQ, kHeadPart / (G * Nl)), K));
-    const int kslice = (K + KS - 1) / KS;
+    const int kslice = ((K + KS - 1) / KS + 3) & ~3;     // multiple of 4: a slice's activations are read as float4 (ldx % 4 == 0)
     const int s = tid / NQ, cl = tid - s * NQ;
     if (s < KS) {
         const int ka = k0 + s * kslice, kb = min(k1, ka + kslice);
@@ -467,13 +467,30 @@ __device__ __forceinline__ void gemv_slice(const float* __restrict__ Wt, int ldw
             float4 wv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) wv[u] = __ldg(w + (size_t)(k + u) * ldw4);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
+            if constexpr (G <= 2) {                       // activations as float4: a quarter of the LDS instructions
 #pragma unroll
                 for (int r = 0; r < G; ++r) {
-                    const float xv = xin[r * ldx + (k + u - k0)];
-                    acc[r][0] = fmaf(wv[u].x, xv, acc[r][0]); acc[r][1] = fmaf(wv[u].y, xv, acc[r][1]);
-                    acc[r][2] = fmaf(wv[u].z, xv, acc[r][2]); acc[r][3] = fmaf(wv[u].w, xv, acc[r][3]);
+#pragma unroll
+                    for (int u4 = 0; u4 < U / 4; ++u4) {
+                        const float4 xq = *reinterpret_cast<const float4*>(xin + r * ldx + (k + 4 * u4 - k0));
+                        const float xs[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 ww = wv[4 * u4 + e];
+                            acc[r][0] = fmaf(ww.x, xs[e], acc[r][0]); acc[r][1] = fmaf(ww.y, xs[e], acc[r][1]);
+                            acc[r][2] = fmaf(ww.z, xs[e], acc[r][2]); acc[r][3] = fmaf(ww.w, xs[e], acc[r][3]);
+                        }
+                    }
+                }
+            } else {                                      // (more rows: the extra live registers spill)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int r = 0; r < G; ++r) {
+                        const float xv = xin[r * ldx + (k + u - k0)];
+                        acc[r][0] = fmaf(wv[u].x, xv, acc[r][0]); acc[r][1] = fmaf(wv[u].y, xv, acc[r][1]);
+                        acc[r][2] = fmaf(wv[u].z, xv, acc[r][2]); acc[r][3] = fmaf(wv[u].w, xv, acc[r][3]);
+                    }
                 }
             }
         }

@@ -78,7 +78,7 @@ want = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_membar.ratio",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio")
 summary = []
-for name in ("bigru_bwd", "bigru_fwd", "attn_bwd", "conv_tf32", "ls_ce", "adam"):
+for name in ("greedy_heads", "beam_heads", "stem", "logmel", "se", "bigru_bwd", "bigru_fwd", "attn_bwd", "conv_tf32", "ls_ce", "adam"):
     rep = os.path.join(ROOT, "gpurun_out", f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
