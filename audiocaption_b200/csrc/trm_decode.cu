@@ -12,14 +12,16 @@
 //                   K/V, cross-attention against K_l/V_l, FFN, classifier.
 // Clips are independent, so one thread-block CLUSTER owns a small group of rows for the whole decode (all
 // `max_len` steps): no grid-wide synchronisation, no host round trip per token, a single launch.  A step is
-// bound by streaming the 12.4 MB of weights out of L2, so (a) the P CTAs of a cluster each stream 1/P of the
-// output columns of every projection / FFN / classifier GEMV and push their slice of the result into every
-// CTA's shared memory (distributed shared memory), and (b) greedy decoding groups 4 clips per cluster of 8 CTAs
-// (R = 4 rows share every weight load; beam search: R = beam rows of one clip, 2 CTAs), which divides the L2
-// traffic by 4 and keeps 128 of the 148 SMs pulling weights.  The cheap per-row work (attention over the
-// caches, LayerNorm, log-softmax / arg-max / top-k) is done redundantly by every CTA of the cluster, so nothing
-// but the GEMV slices has to be exchanged.  Weights are stored transposed ([K][N]) at pack time so
-// that thread n streams column n with coalesced loads while the R activations are broadcast from shared memory.
+// bound by streaming the 12.4 MB of weights out of L2.  Two layouts:
+//   * head-split (default; greedy_heads_kernel / beam_heads_kernel further down): a cluster of 4 CTAs, CTA h owns attention
+//     head h; projections are split over columns where the result can stay local and over K where it must be shared, so a
+//     token step needs 7 cluster barriers and every CTA works in every phase; greedy decodes 2 clips per cluster;
+//   * column-split (greedy_kernel / beam_kernel, the round-1 layout, kept as fallback): the P CTAs of a cluster each stream
+//     1/P of the output columns of every projection / FFN / classifier GEMV and push their slice of the result into every
+//     CTA's shared memory; the cheap per-row work (attention over the caches, LayerNorm, log-softmax / arg-max / top-k) is
+//     done redundantly by every CTA, so nothing but the GEMV slices is exchanged.  Weights are stored transposed ([K][N])
+//     at pack time so that thread n streams column n with coalesced loads while the activations are broadcast from
+//     shared memory.
 //
 // Masks: causal by construction (only positions <= t are cached); `tgt_key_padding_mask`
 // = (prefix token == <pad>) and `memory_key_padding_mask` = (frame >= attn_emb_len) are applied

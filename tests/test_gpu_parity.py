@@ -273,6 +273,30 @@ def test_decoder_matches_oracle_random_memory(mirror, oracle_effb2, seed):
     assert (outb["seq"].cpu()[stable] == refb["seq"][stable]).all(), (outb["seq"].cpu(), refb["seq"], stable)
 
 
+def test_decode_layouts_agree(mirror, monkeypatch):
+    """The head-split kernels (default) and the column-split kernels of round 1 (fallback for shapes whose shared-memory
+    plan does not fit, forced here through the tuning switches) decode the same clips to the same tokens and logits."""
+    gen = torch.Generator().manual_seed(77)
+    dec = _decoder(mirror)
+    for batch in (3, 41):
+        attn = torch.randn(batch, 32, 1408, generator=gen).to(DEV)
+        lens = torch.randint(1, 33, (batch,), generator=gen)
+        a = dec.greedy(attn, lens, 20, cm.START, cm.END, cm.PAD)
+        monkeypatch.setenv("AC_GREEDY", "2,1")
+        b = dec.greedy(attn, lens, 20, cm.START, cm.END, cm.PAD)
+        monkeypatch.delenv("AC_GREEDY")
+        assert (a["seq"] == b["seq"]).all()
+        assert (a["logit"][:, 0] - b["logit"][:, 0]).abs().max() < 2e-5          # same fp32 sums in a different order
+    attn = torch.randn(5, 32, 1408, generator=gen).to(DEV)
+    lens = torch.tensor([32, 9, 1, 20, 31])
+    for beam in (2, 3, 5):
+        a = dec.beam_search(attn, lens, 20, beam, 1.0, cm.START, cm.END, cm.PAD)["seq"]
+        monkeypatch.setenv("AC_BEAM_HEADS", "0")
+        b = dec.beam_search(attn, lens, 20, beam, 1.0, cm.START, cm.END, cm.PAD)["seq"]
+        monkeypatch.delenv("AC_BEAM_HEADS")
+        assert (a == b).all(), (beam, a, b)
+
+
 # ------------------------------------------------------------------ whole model through the public API
 def test_model_end_to_end(mirror, oracle_effb2, golden_effb2, golden_wav):
     g = golden_effb2
