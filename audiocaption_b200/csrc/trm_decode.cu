@@ -1470,7 +1470,7 @@ static int trm_greedy_impl(const ac_trm_t* dec, const float* attn_emb, const int
     a.dbg = g_dec_trace;
     // Default: one CTA per attention head, G clips per 4-CTA cluster (greedy_heads_kernel) when its shared-memory plan fits;
     // AC_GREEDY="P,G" selects the column-split kernel below with that cluster shape (experiments, fallback).
-    if (getenv("AC_GREEDY") == nullptr && dec->w.dff % (4 * NH) == 0) {
+    if (getenv("AC_GREEDY") == nullptr && dec->w.dff % (4 * NH) == 0 && dec->w.vocab >= 64) {
         int G = batch * NH <= kNumSMs ? 1 : 2;
         if (const char* e = getenv("AC_GREEDY_HEADS")) G = atoi(e);      // 0 disables
         if (G == 1 || G == 2 || G == 4) {
@@ -1543,7 +1543,7 @@ int ac_trm_beam(const ac_trm_t* dec, const float* attn_emb, const int64_t* attn_
     {
         const char* e = getenv("AC_BEAM_HEADS");
         const bool want = e ? atoi(e) != 0 : batch * NH <= kNumSMs;
-        if (want && dec->w.dff % (4 * NH) == 0) {
+        if (want && dec->w.dff % (4 * NH) == 0 && dec->w.vocab >= 64) {
             HeadSmem lay = head_smem(beam, 1, dec->w.nlayers, dec->w.dff, dec->w.vocab, t_mem, max_len);
             if (lay.total * sizeof(float) > (size_t)kDecSmemLimit &&
                 (size_t)batch * NH * dec->w.nlayers * beam * max_len * 2 * HD <= s.cache)
