@@ -183,12 +183,24 @@ se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const flo
         const int G = max(1, min(kSeThreads / width, strips));
         const int g = tid / width, c4 = cbase + tid % width;
         if (g < G) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = g; q < strips; q += G) {
-                const float4 v = __ldg(p4 + (size_t)q * c4n + c4);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            // four loads in flight per thread (the early blocks have 512 slots per clip: eight dependent L2 round trips
+            // otherwise); the partial sums are combined in a fixed order
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            int q = g;
+            for (; q + 3 * G < strips; q += 4 * G) {
+                const float4 v0 = __ldg(p4 + (size_t)q * c4n + c4), v1 = __ldg(p4 + (size_t)(q + G) * c4n + c4);
+                const float4 v2 = __ldg(p4 + (size_t)(q + 2 * G) * c4n + c4), v3 = __ldg(p4 + (size_t)(q + 3 * G) * c4n + c4);
+                s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+                s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+                s2.x += v2.x; s2.y += v2.y; s2.z += v2.z; s2.w += v2.w;
+                s3.x += v3.x; s3.y += v3.y; s3.z += v3.z; s3.w += v3.w;
             }
-            s_scr[tid] = s;
+            for (; q < strips; q += G) {
+                const float4 v = __ldg(p4 + (size_t)q * c4n + c4);
+                s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+            }
+            s_scr[tid] = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y),
+                                     (s0.z + s1.z) + (s2.z + s3.z), (s0.w + s1.w) + (s2.w + s3.w));
         }
         __syncthreads();
         if (tid < width) {
