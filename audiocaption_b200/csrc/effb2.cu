@@ -301,6 +301,104 @@ se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const flo
     if (P > 1) cluster.sync();   // nobody exits while a peer may still read its shared memory
 }
 
+// The same for the layers whose FC weights are small (blocks 0-12: <= 46 KB): P plain CTAs per clip, no cluster.  Every
+// CTA computes ALL channel means and ALL squeezed units itself (redundant L2 reads of a few KB) and only its own slice of
+// the gates, so nothing is exchanged: no cluster barriers (each a MEMBAR.ALL.GPU + CCTL.IVALL), no DSMEM gathers.
+__global__ void __launch_bounds__(kSeThreads)
+se_solo_kernel(const float* __restrict__ partial, int strips, float inv_hw, const float* __restrict__ wr,
+               const float* __restrict__ br, const float* __restrict__ we_t, const float* __restrict__ be,
+               float* __restrict__ gate, int C, int nsq, int P) {
+    extern __shared__ __align__(16) float s_se[];   // mean[C] | r[nsq] | scratch[kSeThreads * 4]
+    float* s_mean = s_se;
+    float* s_r = s_se + C;
+    float4* s_scr = reinterpret_cast<float4*>(s_se + ((C + nsq + 3) / 4) * 4);
+    const int b = blockIdx.x / P, rank = blockIdx.x - b * P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c4n = C / 4;
+    const int q0 = (int)((int64_t)c4n * rank / P), q1 = (int)((int64_t)c4n * (rank + 1) / P);   // my gate quads
+    const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)b * strips * C);
+    pdl_trigger();
+    pdl_wait();        // `partial` is the depthwise kernel's output
+    for (int cbase = 0; cbase < c4n; cbase += kSeThreads) {
+        const int width = min(c4n - cbase, kSeThreads);
+        const int G = max(1, min(kSeThreads / width, strips));
+        const int g = tid / width, c4 = cbase + tid % width;
+        if (g < G) {
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            int q = g;
+            for (; q + 3 * G < strips; q += 4 * G) {
+                const float4 v0 = __ldg(p4 + (size_t)q * c4n + c4), v1 = __ldg(p4 + (size_t)(q + G) * c4n + c4);
+                const float4 v2 = __ldg(p4 + (size_t)(q + 2 * G) * c4n + c4), v3 = __ldg(p4 + (size_t)(q + 3 * G) * c4n + c4);
+                s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+                s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+                s2.x += v2.x; s2.y += v2.y; s2.z += v2.z; s2.w += v2.w;
+                s3.x += v3.x; s3.y += v3.y; s3.z += v3.z; s3.w += v3.w;
+            }
+            for (; q < strips; q += G) {
+                const float4 v = __ldg(p4 + (size_t)q * c4n + c4);
+                s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+            }
+            s_scr[tid] = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y),
+                                     (s0.z + s1.z) + (s2.z + s3.z), (s0.w + s1.w) + (s2.w + s3.w));
+        }
+        __syncthreads();
+        if (tid < width) {
+            float4 t = s_scr[tid];
+            for (int q = 1; q < G; ++q) {
+                const float4 u = s_scr[q * width + tid];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            reinterpret_cast<float4*>(s_mean)[c4] = make_float4(t.x * inv_hw, t.y * inv_hw, t.z * inv_hw, t.w * inv_hw);
+        }
+        __syncthreads();
+    }
+    for (int j = warp; j < nsq; j += kSeThreads / 32) {
+        const float4* w4 = reinterpret_cast<const float4*>(wr + (size_t)j * C);
+        const float4* m4 = reinterpret_cast<const float4*>(s_mean);
+        float s0 = 0.f, s1 = 0.f;
+        int c = lane;
+        for (; c + 32 < c4n; c += 64) {
+            const float4 a0 = __ldg(w4 + c), a1 = __ldg(w4 + c + 32);
+            const float4 b0 = m4[c], b1 = m4[c + 32];
+            s0 = fmaf(a0.x, b0.x, fmaf(a0.y, b0.y, fmaf(a0.z, b0.z, fmaf(a0.w, b0.w, s0))));
+            s1 = fmaf(a1.x, b1.x, fmaf(a1.y, b1.y, fmaf(a1.z, b1.z, fmaf(a1.w, b1.w, s1))));
+        }
+        for (; c < c4n; c += 32) {
+            const float4 a0 = __ldg(w4 + c), b0 = m4[c];
+            s0 = fmaf(a0.x, b0.x, fmaf(a0.y, b0.y, fmaf(a0.z, b0.z, fmaf(a0.w, b0.w, s0))));
+        }
+        const float s = warp_sum(s0 + s1);
+        if (lane == 0) s_r[j] = swishf(s + br[j]);
+    }
+    __syncthreads();
+    for (int cbase = q0; cbase < q1; cbase += kSeThreads) {
+        const int width = min(q1 - cbase, kSeThreads);
+        const int G = max(1, min(kSeThreads / width, nsq));
+        const int g = tid / width, c4 = cbase + tid % width;
+        if (g < G) {
+            const float4* w4 = reinterpret_cast<const float4*>(we_t) + c4;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = g; j < nsq; j += G) {
+                const float4 a0 = __ldg(w4 + (size_t)j * c4n);
+                const float r0 = s_r[j];
+                s.x = fmaf(a0.x, r0, s.x); s.y = fmaf(a0.y, r0, s.y); s.z = fmaf(a0.z, r0, s.z); s.w = fmaf(a0.w, r0, s.w);
+            }
+            s_scr[tid] = s;
+        }
+        __syncthreads();
+        if (tid < width) {
+            float4 t = s_scr[tid];
+            for (int q = 1; q < G; ++q) {
+                const float4 u = s_scr[q * width + tid];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(be) + c4);
+            reinterpret_cast<float4*>(gate + (size_t)b * C)[c4] =
+                make_float4(sigmoidf_(t.x + bq.x), sigmoidf_(t.y + bq.y), sigmoidf_(t.z + bq.z), sigmoidf_(t.w + bq.w));
+        }
+        __syncthreads();
+    }
+}
+
 // ----------------------------------------------------------------------------- head tail
 // y [B, H, W, C] -> out [B, W, C] = mean over H  ('b c f t -> b t c', 'mean')
 __global__ void freq_mean_kernel(const float* __restrict__ y, float* __restrict__ out, int H, int W, int C,
@@ -369,6 +467,16 @@ static int launch_se(const float* partial, int strips, float inv_hw, const Block
     cfg.gridDim = dim3(B * P); cfg.blockDim = dim3(kSeThreads);
     cfg.dynamicSmemBytes = (((C + nsq + 3) / 4) * 4 + kSeThreads * 4) * sizeof(float);
     cfg.stream = st;
+    static const int solo_bytes = [] { const char* e = getenv("AC_SE_SOLO"); return e ? atoi(e) : 64 * 1024; }();   // 0 = never
+    if ((size_t)nsq * C * sizeof(float) <= (size_t)solo_bytes) {
+        cudaLaunchAttribute at[1] = {pdl_attr()};
+        cfg.attrs = at; cfg.numAttrs = 1;
+        AC_TIMED("se", st);
+        AC_CUDA(cudaLaunchKernelEx(&cfg, se_solo_kernel, partial, strips, inv_hw, (const float*)w.se_wr, (const float*)w.se_br,
+                                   (const float*)w.se_we, (const float*)w.se_be, gate, C, nsq, P));
+        AC_LAUNCHED("se_solo_kernel");
+        return AC_OK;
+    }
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
