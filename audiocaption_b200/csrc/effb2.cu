@@ -301,7 +301,7 @@ se_kernel(const float* __restrict__ partial, int strips, float inv_hw, const flo
     if (P > 1) cluster.sync();   // nobody exits while a peer may still read its shared memory
 }
 
-// The same for the layers whose FC weights are small (blocks 0-12: <= 46 KB): P plain CTAs per clip, no cluster.  Every
+// The same for the layers whose FC weights are small (blocks 0-16: <= 86 KB per matrix): P plain CTAs per clip, no cluster.  Every
 // CTA computes ALL channel means and ALL squeezed units itself (redundant L2 reads of a few KB) and only its own slice of
 // the gates, so nothing is exchanged: no cluster barriers (each a MEMBAR.ALL.GPU + CCTL.IVALL), no DSMEM gathers.
 __global__ void __launch_bounds__(kSeThreads)
@@ -467,7 +467,7 @@ static int launch_se(const float* partial, int strips, float inv_hw, const Block
     cfg.gridDim = dim3(B * P); cfg.blockDim = dim3(kSeThreads);
     cfg.dynamicSmemBytes = (((C + nsq + 3) / 4) * 4 + kSeThreads * 4) * sizeof(float);
     cfg.stream = st;
-    static const int solo_bytes = [] { const char* e = getenv("AC_SE_SOLO"); return e ? atoi(e) : 64 * 1024; }();   // 0 = never
+    static const int solo_bytes = [] { const char* e = getenv("AC_SE_SOLO"); return e ? atoi(e) : 100000; }();   // bytes of one FC matrix; 0 = never
     if ((size_t)nsq * C * sizeof(float) <= (size_t)solo_bytes) {
         cudaLaunchAttribute at[1] = {pdl_attr()};
         cfg.attrs = at; cfg.numAttrs = 1;
