@@ -53,7 +53,7 @@ print("\n".join(lines[:14]))
 p = os.path.join(ROOT, "gpurun_out", f"{tag}_traffic.csv")
 if os.path.exists(p):
     step = launches(p)
-    fam_of = lambda n: ("gemm" if "gemm_tc" in n or "gemm_tn" in n else "dwconv" if "dwconv" in n else "se" if short(n).startswith("se_kernel") else "other" if "transpose" in n
+    fam_of = lambda n: ("gemm" if "gemm_tc" in n or "gemm_tn" in n else "dwconv" if "dwconv" in n else "se" if short(n).startswith(("se_kernel", "se_solo_kernel")) else "other" if "transpose" in n
                         else "logmel" if "logmel" in n else "stem" if "stem" in n else "trm_greedy" if "greedy" in n else "other")
     fams = {}
     for l in step:
