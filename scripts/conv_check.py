@@ -20,8 +20,9 @@ def run(B, H, W, Cin, Cout, act=2, seed=0, check=True, reps=0):
     bi = torch.randn(Cout, generator=g).to(dev)
     out = torch.full((B, H, W, Cout), float("nan"), device=dev)
     st = _lib.current_stream()
-    call = lambda: _lib.check(lib.ac_conv3x3(_lib.ptr(x), _lib.ptr(w), _lib.ptr(sc), _lib.ptr(bi), _lib.ptr(out), B, H, W,
-                                             Cin, Cout, act, st), "ac_conv3x3")
+    passes = int(os.environ.get("CONV_PASSES", "3"))       # 1 = plain TF32 mode
+    call = lambda: _lib.check(lib.ac_conv3x3_p(_lib.ptr(x), _lib.ptr(w), _lib.ptr(sc), _lib.ptr(bi), _lib.ptr(out), B, H, W,
+                                               Cin, Cout, act, passes, st), "ac_conv3x3")
     call()
     torch.cuda.synchronize()
     err = None
