@@ -88,6 +88,8 @@ _SIGS = {
     "ac_sed_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "ac_conv3x3_p": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_void_p]),
+    "ac_conv3x3_bf16": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p]),
     # ---- training step
     "ac_cnn14_fwd_train": (C.c_int, [C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_uint64,
                                      c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),

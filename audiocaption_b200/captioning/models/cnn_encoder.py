@@ -317,7 +317,9 @@ class Cnn14Encoder(nn.Module):
     conv_dropout = 0.2
     fc_dropout = 0.5
     # "fp32": 3xTF32 tensor-core convolutions (fp32-level accuracy, every fp32 parity claim); "tf32": plain TF32 operands
-    # with fp32 accumulation -- for the configurations BASELINE.json states in bf16 (training, temporal captioner)
+    # with fp32 accumulation; "bf16": bf16 activations and weights between bn0 and the pooled output, fp32 accumulation
+    # (csrc/conv_bf16.cu, 3.7x the TF32 convolutions) -- the last two for the configurations BASELINE.json states in bf16
+    # (training with the frozen CNN, temporal captioner)
     conv_precision = "fp32"
 
     def __init__(self, sample_rate: int = 32000, freeze: bool = False):
@@ -391,10 +393,10 @@ class Cnn14Encoder(nn.Module):
             _lib.check(_lib.lib().ac_cnn14_create(ptrs, numels, n, _lib.current_stream(), ctypes.byref(h)),
                        "ac_cnn14_create")
             self._handle, self._sig = h, sig
-        if self.conv_precision not in ("fp32", "tf32"):
-            raise ValueError(f"conv_precision {self.conv_precision!r}: expected 'fp32' or 'tf32'")
-        _lib.check(_lib.lib().ac_cnn14_set_precision(self._handle, 1 if self.conv_precision == "tf32" else 3),
-                   "ac_cnn14_set_precision")
+        modes = {"fp32": 3, "tf32": 1, "bf16": 16}
+        if self.conv_precision not in modes:
+            raise ValueError(f"conv_precision {self.conv_precision!r}: expected 'fp32', 'tf32' or 'bf16'")
+        _lib.check(_lib.lib().ac_cnn14_set_precision(self._handle, modes[self.conv_precision]), "ac_cnn14_set_precision")
         return self._handle
 
     def release(self):

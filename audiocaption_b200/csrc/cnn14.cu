@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "gemm.cuh"
 #include "train_ops.cuh"
 
@@ -44,10 +46,12 @@ __global__ void cnn14_w1_kernel(const float* __restrict__ w, float* __restrict__
 // A CTA owns kC1Time time steps of one clip: the (kC1Time + 2) x (M + 2) input patch (bn0 applied, zero padding
 // outside the image) sits in shared memory; 16 threads serve one pixel (4 output channels each, 36 weights in
 // registers), so a pixel's 64 channels leave as one 256-byte run.
+// (OT = float, or __nv_bfloat16 in the bf16 precision mode: the same arithmetic, the store rounds)
+template <typename OT>
 __global__ void __launch_bounds__(kC1Threads)
 cnn14_conv1_kernel(const float* __restrict__ lms, const float* __restrict__ s0, const float* __restrict__ t0,
                    const float* __restrict__ w /*[9][64]*/, const float* __restrict__ scale,
-                   const float* __restrict__ bias, float* __restrict__ out, int M, int T) {
+                   const float* __restrict__ bias, OT* __restrict__ out, int M, int T) {
     extern __shared__ float patch[];                     // [(kC1Time + 2)][M + 2]
     const int b = blockIdx.y, tb = blockIdx.x * kC1Time;
     const int PW = M + 2;
@@ -89,8 +93,69 @@ cnn14_conv1_kernel(const float* __restrict__ lms, const float* __restrict__ s0, 
         float4 o;
         o.x = fmaxf(fmaf(acc[0], sc[0], bi[0]), 0.f); o.y = fmaxf(fmaf(acc[1], sc[1], bi[1]), 0.f);
         o.z = fmaxf(fmaf(acc[2], sc[2], bi[2]), 0.f); o.w = fmaxf(fmaf(acc[3], sc[3], bi[3]), 0.f);
-        reinterpret_cast<float4*>(out + (((size_t)b * T + tb + dt) * M + m) * 64)[cg] = o;
+        OT* dst = out + (((size_t)b * T + tb + dt) * M + m) * 64 + 4 * cg;
+        if constexpr (sizeof(OT) == 4) {
+            *reinterpret_cast<float4*>(dst) = o;
+        } else {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
     }
+}
+
+// ---- bf16 precision mode: the pooling / dropout / tail kernels on bf16 NHWC activations (8 channels = 16 bytes per thread)
+__device__ __forceinline__ void bf16x8_to_float(const uint4 v, float (&f)[8]) {
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+        f[2 * e] = p.x; f[2 * e + 1] = p.y;
+    }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
+    uint32_t u[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        u[e] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    return make_uint4(u[0], u[1], u[2], u[3]);
+}
+// avg_pool2d 2x2 (+ the ConvBlock dropout in training): same element indices for the dropout stream as the fp32 kernel
+__global__ void __launch_bounds__(256)
+cnn14_avgpool_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int C8, int Ho, int Wo,
+                          int64_t total, Dropout dp, uint32_t site) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C8);
+    int64_t r = i / C8;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int64_t b = r / Ho;
+    const uint4* p = in + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C8 + c;
+    float a[8], bb[8], cc[8], d[8], o[8];
+    bf16x8_to_float(__ldg(p), a); bf16x8_to_float(__ldg(p + C8), bb);
+    bf16x8_to_float(__ldg(p + (size_t)W * C8), cc); bf16x8_to_float(__ldg(p + (size_t)W * C8 + C8), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        o[e] = 0.25f * (a[e] + bb[e] + cc[e] + d[e]);
+        if (dp.p > 0.0f) o[e] *= drop_scale(dp.seed, site, (uint64_t)i * 8 + e, dp.p);
+    }
+    out[i] = float_to_bf16x8(o);
+}
+__global__ void __launch_bounds__(256)
+cnn14_dropout_bf16_kernel(uint4* __restrict__ x, int64_t total, Dropout dp, uint32_t site) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float f[8];
+    bf16x8_to_float(x[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= drop_scale(dp.seed, site, (uint64_t)i * 8 + e, dp.p);
+    x[i] = float_to_bf16x8(f);
 }
 
 // avg_pool2d(kernel 2x2, stride 2, floor): in [B, H, W, C] -> out [B, H/2, W/2, C]; one float4 per thread.
@@ -210,8 +275,9 @@ __global__ void sed_hysteresis_kernel(const float* __restrict__ prob, unsigned c
 
 // y [B, H, W, C] -> attn_emb [B, H, C] = mean over W (torch.mean(x, dim=3), 'b c t f -> b t c') and
 // pooled [B, C] = max_{t < len} attn_emb + (sum_{t < len} attn_emb) / len   (max_with_lens + mean_with_lens)
+template <typename IT>
 __global__ void __launch_bounds__(128)
-cnn14_tail_kernel(const float* __restrict__ y, const int64_t* __restrict__ lens, float* __restrict__ attn,
+cnn14_tail_kernel(const IT* __restrict__ y, const int64_t* __restrict__ lens, float* __restrict__ attn,
                   float* __restrict__ pooled, int H, int W, int C) {
     pdl_trigger();
     pdl_wait();
@@ -222,7 +288,10 @@ cnn14_tail_kernel(const float* __restrict__ y, const int64_t* __restrict__ lens,
     float mx = -INFINITY, sum = 0.0f;
     for (int t = 0; t < H; ++t) {
         float s = 0.0f;
-        for (int w = 0; w < W; ++w) s += __ldg(y + (((size_t)b * H + t) * W + w) * C + c);
+        for (int w = 0; w < W; ++w) {
+            if constexpr (sizeof(IT) == 4) s += __ldg(y + (((size_t)b * H + t) * W + w) * C + c);
+            else s += __bfloat162float(y[(((size_t)b * H + t) * W + w) * C + c]);
+        }
         s *= inv_w;
         attn[((size_t)b * H + t) * C + c] = s;
         if (t < len) { mx = fmaxf(mx, s); sum += s; }
@@ -230,17 +299,18 @@ cnn14_tail_kernel(const float* __restrict__ y, const int64_t* __restrict__ lens,
     pooled[(size_t)b * C + c] = mx + sum / (float)len;
 }
 
-struct Cnn14Conv { float* scale; float* bias; TcWeight tw; int cin, cout; };
+struct Cnn14Conv { float* scale; float* bias; TcWeight tw; ConvBf16Weight bw; int cin, cout; };
 
 }  // namespace ac
 
 struct ac_cnn14 {
     float* blob = nullptr;
+    void* blob_bf16 = nullptr;    // bf16 images of the convolution weights (precision mode 16)
     float *bn0_s, *bn0_b, *w1, *s1, *b1;
     ac::Cnn14Conv conv[2 * ac::kCnn14Blocks - 1];   // block1.conv2, block2.conv1, ... block6.conv2
     float *fc_w, *fc_b;
     ac::TcWeight fc_tw;
-    int conv_passes = 3;          // 3 = 3xTF32 (fp32-level), 1 = plain TF32 (ac_cnn14_set_precision)
+    int conv_passes = 3;          // 3 = 3xTF32 (fp32-level), 1 = plain TF32, 16 = bf16 activations + weights (ac_cnn14_set_precision)
 };
 
 namespace ac {
@@ -320,9 +390,12 @@ int ac_cnn14_create(const float* const* t, const int64_t* numels, int n_tensors,
     const size_t o_fcw = take((size_t)D * D), o_fcb = take(D), o_fcpk = take(tc_packed_floats(D, D));
     ac_cnn14_t* net = new ac_cnn14_t();
     float* perm = nullptr;
+    size_t bf_total = 0, bf_off[2 * kCnn14Blocks - 1];
+    for (int q = 0; q < 2 * kCnn14Blocks - 1; ++q) { bf_off[q] = bf_total; bf_total += align_up(conv_bf16_packed_elems(cout_[q], cin_[q]), 64); }
     int rc = check_cuda(cudaMalloc(&net->blob, total * sizeof(float)), "ac_cnn14_create: cudaMalloc(weights)");
+    if (rc == AC_OK) rc = check_cuda(cudaMalloc(&net->blob_bf16, bf_total * 2), "ac_cnn14_create: cudaMalloc(bf16 weights)");
     if (rc == AC_OK) rc = check_cuda(cudaMalloc(&perm, perm_max * sizeof(float)), "ac_cnn14_create: cudaMalloc(scratch)");
-    if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
+    if (rc != AC_OK) { cudaFree(net->blob); cudaFree(net->blob_bf16); delete net; return rc; }
     float* B0 = net->blob;
     auto fold = [&](int ti, int c, float* s, float* b) {
         cnn14_bn_fold_kernel<<<cdiv(c, 256), 256, 0, st>>>(t[ti], t[ti + 1], t[ti + 2], t[ti + 3], kCnn14BnEps, s, b, c);
@@ -346,6 +419,7 @@ int ac_cnn14_create(const float* const* t, const int64_t* numels, int n_tensors,
             fold(bn_ti, c.cout, c.scale, c.bias);
             rc = conv3x3_permute_weight(t[base + j], perm, c.cout, c.cin, st);
             if (rc == AC_OK) rc = tc_pack_weight(perm, c.scale, c.cout, 9 * c.cin, B0 + co_[l].pk, st, &c.tw);
+            if (rc == AC_OK) rc = conv_bf16_pack(perm, c.scale, c.cout, c.cin, (uint16_t*)net->blob_bf16 + bf_off[l], st, &c.bw);
             ++l;
         }
     }
@@ -357,7 +431,7 @@ int ac_cnn14_create(const float* const* t, const int64_t* numels, int n_tensors,
     if (rc == AC_OK) rc = check_cuda(cudaGetLastError(), "ac_cnn14_create pack kernels");
     if (rc == AC_OK) rc = check_cuda(cudaStreamSynchronize(st), "ac_cnn14_create sync");
     cudaFree(perm);
-    if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
+    if (rc != AC_OK) { cudaFree(net->blob); cudaFree(net->blob_bf16); delete net; return rc; }
     *out = net;
     return AC_OK;
 }
@@ -365,6 +439,7 @@ int ac_cnn14_create(const float* const* t, const int64_t* numels, int n_tensors,
 void ac_cnn14_destroy(ac_cnn14_t* net) {
     if (!net) return;
     cudaFree(net->blob);
+    cudaFree(net->blob_bf16);
     delete net;
 }
 
@@ -373,7 +448,8 @@ void ac_cnn14_destroy(ac_cnn14_t* net) {
 // the configurations BASELINE.json states in bf16 (training, temporal captioner).
 int ac_cnn14_set_precision(ac_cnn14_t* net, int tf32_passes) {
     using namespace ac;
-    AC_REQUIRE(net && (tf32_passes == 1 || tf32_passes == 3), "ac_cnn14_set_precision: passes must be 1 or 3");
+    AC_REQUIRE(net && (tf32_passes == 1 || tf32_passes == 3 || tf32_passes == 16),
+               "ac_cnn14_set_precision: mode must be 3 (3xTF32), 1 (TF32) or 16 (bf16)");
     net->conv_passes = tf32_passes;
     return AC_OK;
 }
@@ -407,11 +483,69 @@ int ac_cnn14_fwd_train(const ac_cnn14_t* net, const float* lms, int B, int n_mel
     Cnn14Dims d[kCnn14Blocks];
     cnn14_walk(n_mels, n_frames, d);
     int rc;
+    if (net->conv_passes == 16) {
+        // ---- bf16 precision mode: every activation between bn0 and the pooled output lives in bf16 NHWC (the two fp32
+        // activation buffers of the workspace hold them), the convolutions run on conv3x3_bf16 (bf16 x bf16 -> fp32 in TMEM)
+        __nv_bfloat16* bcur = reinterpret_cast<__nv_bfloat16*>(cur);
+        __nv_bfloat16* bnxt = reinterpret_cast<__nv_bfloat16*>(nxt);
+        {
+            AC_TIMED("cnn14_conv1", st);
+            dim3 grid(cdiv(n_frames, kC1Time), B);
+            const size_t smem = (size_t)(kC1Time + 2) * (n_mels + 2) * sizeof(float);
+            rc = launch_pdl(cnn14_conv1_kernel<__nv_bfloat16>, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s,
+                            (const float*)net->bn0_b, (const float*)net->w1, (const float*)net->s1, (const float*)net->b1, bcur,
+                            n_mels, n_frames);
+            if (rc) return rc;
+            AC_LAUNCHED("cnn14_conv1_kernel");
+        }
+        int l = 0;
+        for (int i = 0; i < kCnn14Blocks; ++i) {
+            for (int j = 0; j < 2; ++j) {
+                if (i == 0 && j == 0) continue;
+                const Cnn14Conv& c = net->conv[l++];
+                ConvBf16Args a; a.in = bcur; a.out = bnxt; a.B = B; a.H = d[i].H; a.W = d[i].W; a.Cin = c.cin; a.Cout = c.cout;
+                a.bias = c.bias; a.w = &c.bw; a.act = ACT_RELU;
+                rc = conv3x3_bf16(a, st); if (rc) return rc;
+                std::swap(bcur, bnxt);
+            }
+            if (i + 1 < kCnn14Blocks) {
+                const int C8 = kCnn14Ch[i + 1] / 8, Ho = d[i].H / 2, Wo = d[i].W / 2;
+                const int64_t total = (int64_t)B * Ho * Wo * C8;
+                AC_TIMED("cnn14_avgpool", st);
+                rc = launch_pdl(cnn14_avgpool_bf16_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st,
+                                (const uint4*)bcur, (uint4*)bnxt, d[i].H, d[i].W, C8, Ho, Wo, total, dpc, kSiteCnn + (uint32_t)i);
+                if (rc) return rc;
+                AC_LAUNCHED("cnn14_avgpool_kernel");
+                std::swap(bcur, bnxt);
+            }
+        }
+        const Cnn14Dims last = d[kCnn14Blocks - 1];
+        const int D = ac_cnn14_out_dim();
+        if (dpc.p > 0.0f) {
+            const int64_t total = (int64_t)B * last.H * last.W * D / 8;
+            rc = launch_pdl(cnn14_dropout_bf16_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st, (uint4*)bcur, total, dpc,
+                            kSiteCnn + (uint32_t)kCnn14Blocks - 1);
+            if (rc) return rc;
+            AC_LAUNCHED("cnn14_dropout_kernel");
+        }
+        {
+            AC_TIMED("cnn14_tail", st);
+            rc = launch_pdl(cnn14_tail_kernel<__nv_bfloat16>, dim3(cdiv(D, 128), B), dim3(128), 0, st, (const __nv_bfloat16*)bcur, lens,
+                            attn_emb, pooled, last.H, last.W, D);
+            if (rc) return rc;
+            AC_LAUNCHED("cnn14_tail_kernel");
+        }
+        rc = dropout_apply(pooled, 0, (int64_t)B * D, dpf, kSiteCnn + kCnn14Blocks, st); if (rc) return rc;
+        GemmArgs g; g.A = pooled; g.W = net->fc_w; g.C = fc_emb; g.M = B; g.N = D; g.K = D; g.cbias = net->fc_b; g.act = ACT_RELU;
+        g.tw = &net->fc_tw;
+        rc = gemm_tn(g, st); if (rc) return rc;
+        return dropout_apply(fc_emb, 0, (int64_t)B * D, dpf, kSiteCnn + kCnn14Blocks + 1, st);
+    }
     {
         AC_TIMED("cnn14_conv1", st);
         dim3 grid(cdiv(n_frames, kC1Time), B);
         const size_t smem = (size_t)(kC1Time + 2) * (n_mels + 2) * sizeof(float);
-        rc = launch_pdl(cnn14_conv1_kernel, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s,
+        rc = launch_pdl(cnn14_conv1_kernel<float>, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s,
                         (const float*)net->bn0_b, (const float*)net->w1, (const float*)net->s1, (const float*)net->b1, cur,
                         n_mels, n_frames);
         if (rc) return rc;
@@ -443,7 +577,7 @@ int ac_cnn14_fwd_train(const ac_cnn14_t* net, const float* lms, int B, int n_mel
     rc = dropout_apply(cur, 0, (int64_t)B * last.H * last.W * D, dpc, kSiteCnn + kCnn14Blocks - 1, st); if (rc) return rc;
     {
         AC_TIMED("cnn14_tail", st);
-        rc = launch_pdl(cnn14_tail_kernel, dim3(cdiv(D, 128), B), dim3(128), 0, st, (const float*)cur, lens, attn_emb, pooled,
+        rc = launch_pdl(cnn14_tail_kernel<float>, dim3(cdiv(D, 128), B), dim3(128), 0, st, (const float*)cur, lens, attn_emb, pooled,
                         last.H, last.W, D);
         if (rc) return rc;
         AC_LAUNCHED("cnn14_tail_kernel");
@@ -642,7 +776,7 @@ int ac_sed_fwd(const ac_sed_t* net, const float* lms, int B, int n_mels, int n_f
         AC_TIMED("sed_conv1", st);
         dim3 grid(cdiv(n_frames, kC1Time), B);
         const size_t smem = (size_t)(kC1Time + 2) * (n_mels + 2) * sizeof(float);
-        rc = launch_pdl(cnn14_conv1_kernel, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s, (const float*)net->bn0_b,
+        rc = launch_pdl(cnn14_conv1_kernel<float>, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s, (const float*)net->bn0_b,
                         (const float*)net->w1, (const float*)net->s1, (const float*)net->b1, cur, n_mels, n_frames);
         if (rc) return rc;
         AC_LAUNCHED("cnn14_conv1_kernel");

@@ -84,6 +84,19 @@ int conv3x3_tc(const Conv3Args& a, cudaStream_t st);
 int conv3x3_permute_weight(const float* w_dev, float* out_dev, int Cout, int Cin, cudaStream_t st);
 void conv3x3_tile_shape(int H, int W, int& Hbox, int& Bbox);
 
+// The same convolution with bf16 activations and weights (conv_bf16.cu): in / out NHWC bf16, bias fp32; the weight is the
+// tap-major [Cout, 9*Cin] matrix (conv3x3_permute_weight) packed to bf16 with the BN scale folded in.
+struct ConvBf16Weight { const void* packed = nullptr; int Cout = 0, Cin = 0, BN = 0, n_tiles = 0, k_chunks = 0; };
+struct ConvBf16Args {
+    const void* in; void* out; const float* bias; const ConvBf16Weight* w = nullptr;
+    int B, H, W, Cin, Cout;
+    int act = ACT_NONE;
+};
+size_t conv_bf16_packed_elems(int Cout, int Cin);
+int conv_bf16_pack(const float* w_perm_dev, const float* scale_dev, int Cout, int Cin, void* dst_dev, cudaStream_t st,
+                   ConvBf16Weight* out);
+int conv3x3_bf16(const ConvBf16Args& a, cudaStream_t st);
+
 // Depthwise k x k convolution + folded BN + swish + per-tile channel sums (SE squeeze), NHWC fp32, fed by 4-D
 // TMA tiles (dwconv_tma.cu).  in [B,Hi,Wi,C] -> out [B,Ho,Wo,C]; partial [B][dwconv_tiles_per_clip][C].
 struct DwArgs {

@@ -167,6 +167,12 @@ int ac_sed_set_precision(ac_sed_t* net, int tf32_passes);
 /* ac_conv3x3 with the precision switch (diagnostic). */
 int ac_conv3x3_p(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev, float* out_dev,
                  int B, int H, int W, int Cin, int Cout, int act, int tf32_passes, void* stream);
+/* The bf16 form of the same convolution (diagnostic; the "bf16" precision mode of ac_cnn14_set_precision, value 16, runs it
+ * on every layer): in_dev / out_dev are NHWC bf16 [B,H,W,Cin] / [B,H,W,Cout], w_dev the fp32 Conv2d weight, bias fp32,
+ * Cin % 64 == 0.  Replaces the same ConvBlock arithmetic (captioning/models/cnn_encoder.py:32-75) at bf16 operand precision
+ * with fp32 accumulation. */
+int ac_conv3x3_bf16(const void* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev, void* out_dev,
+                    int B, int H, int W, int Cin, int Cout, int act, void* stream);
 
 /* Train-mode forward of the frozen encoder (BatchNorm folded = eval, `freeze_cnn_bn`), with the functional dropouts of
  * captioning/models/cnn_encoder.py:432-456 active: p_conv after each ConvBlock (reference 0.2), p_fc around fc1 (0.5).

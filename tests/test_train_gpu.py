@@ -488,6 +488,18 @@ def test_tf32_convolution_mode():
                                   None), "ac_conv3x3_p")
         errs[passes] = ((out.cpu().double() - ref).abs().max() / ref.abs().max()).item()
     assert errs[3] < 2e-5 and 2e-5 < errs[1] < 2e-3, errs
+    # the bf16 convolution against float64 on the SAME bf16-rounded operands: only the fp32 accumulation and the bf16 store
+    sc, bi = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    xb = x.to(DEV).to(torch.bfloat16)
+    outb = torch.empty(B, H, W, Cout, device=DEV, dtype=torch.bfloat16)
+    wd, scd, bid = w.to(DEV), sc.to(DEV), bi.to(DEV)          # (named: the device copies must outlive the call)
+    _lib.check(l.ac_conv3x3_bf16(xb.data_ptr(), _lib.ptr(wd), _lib.ptr(scd), _lib.ptr(bid), outb.data_ptr(), B, H, W,
+                                 Cin, Cout, 2, None), "ac_conv3x3_bf16")
+    wq = (w * sc.view(-1, 1, 1, 1)).to(torch.bfloat16).double()
+    refb = (torch.nn.functional.conv2d(xb.cpu().double().permute(0, 3, 1, 2), wq, padding=1) + bi.double().view(1, -1, 1, 1))
+    refb = refb.clamp_min(0).permute(0, 2, 3, 1)
+    errb = ((outb.cpu().double() - refb).abs().max() / refb.abs().max()).item()
+    assert errb < 6e-3, errb                           # 2^-9 relative from the bf16 store
     vocab = 4368
     m = _no_dropout(_train_model(vocab))
     wav, lens = cm.synth_wav(3, 64000, seed=21, ragged=True, varied=True, sample_rate=32000)
@@ -499,14 +511,21 @@ def test_tf32_convolution_mode():
         b = m.encoder.cnn(dict(inp))["attn_emb"]
     rel = ((a - b).abs().max() / a.abs().max()).item()
     assert 1e-6 < rel < 1e-2, rel
+    with torch.no_grad():
+        m.encoder.cnn.conv_precision = "bf16"          # bf16 activations + weights: 8-bit mantissas through 12 layers
+        c = m.encoder.cnn(dict(inp))
+        m.encoder.cnn.conv_precision = "fp32"
+    relb = ((a - c["attn_emb"]).abs().max() / a.abs().max()).item()
+    assert 1e-4 < relb < 5e-2, relb
     cap, cap_len = ts.synth_captions(3, 7, vocab, seed=4)
     losses = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32", "bf16"):
         m2 = _no_dropout(_train_model(vocab))
         m2.encoder.cnn.conv_precision = prec
         step = TrainStep(m2, total_iters=1000, lr=1e-3, warmup_iters=10)
         losses[prec] = step.step({"wav": wav, "wav_len": lens, "cap": cap, "cap_len": cap_len.numpy()}, coins=None)["loss"].item()
     assert abs(losses["fp32"] - losses["tf32"]) < 2e-3 * abs(losses["fp32"]), losses
+    assert abs(losses["fp32"] - losses["bf16"]) < 2e-2 * abs(losses["fp32"]), losses
 
 
 def test_specaugment_stripes():
