@@ -412,7 +412,7 @@ class Cnn8rnnSedModel(nn.Module):
     reference's state_dict names; network and double threshold in csrc/cnn14.cu (`ac_sed_*`), only the 0/1 segment labels
     come back to the host for the pairwise segment rule (hf_wrapper.py:180-216)."""
 
-    conv_precision = "fp32"          # or "tf32": see Cnn14Encoder.conv_precision
+    conv_precision = "fp32"          # or "tf32" / "bf16": see Cnn14Encoder.conv_precision
 
     def __init__(self, classes_num):
         super().__init__()
@@ -457,8 +457,10 @@ class Cnn8rnnSedModel(nn.Module):
             _lib.check(_lib.lib().ac_sed_create(ptrs, numels, n, self.classes_num, _lib.current_stream(), ctypes.byref(h)),
                        "ac_sed_create")
             self._handle, self._sig = h, sig
-        _lib.check(_lib.lib().ac_sed_set_precision(self._handle, 1 if self.conv_precision == "tf32" else 3),
-                   "ac_sed_set_precision")
+        modes = {"fp32": 3, "tf32": 1, "bf16": 16}
+        if self.conv_precision not in modes:
+            raise ValueError(f"conv_precision {self.conv_precision!r}: expected 'fp32', 'tf32' or 'bf16'")
+        _lib.check(_lib.lib().ac_sed_set_precision(self._handle, modes[self.conv_precision]), "ac_sed_set_precision")
         return self._handle
 
     def release(self):

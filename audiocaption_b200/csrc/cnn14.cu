@@ -182,6 +182,57 @@ cnn14_avgpool_kernel(const float4* __restrict__ in, float4* __restrict__ out, in
     out[i] = o;
 }
 
+// bf16 forms of the SED pooling (avg + max over ph x pw) and of the mean over mel (-> fp32 for fc1)
+__global__ void __launch_bounds__(256)
+cnn_avgmax_pool_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int C8, int Ho, int Wo, int ph,
+                            int pw, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C8);
+    int64_t r = i / C8;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int64_t b = r / Ho;
+    float sum[8], mx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sum[e] = 0.f; mx[e] = -INFINITY; }
+    for (int dy = 0; dy < ph; ++dy)
+        for (int dx = 0; dx < pw; ++dx) {
+            float v[8];
+            bf16x8_to_float(__ldg(in + (((size_t)b * H + ho * ph + dy) * W + wo * pw + dx) * C8 + c), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sum[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
+        }
+    const float inv = 1.0f / (float)(ph * pw);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = sum[e] * inv + mx[e];
+    out[i] = float_to_bf16x8(o);
+}
+__global__ void __launch_bounds__(256)
+cnn_wmean_bf16_kernel(const uint4* __restrict__ y, float4* __restrict__ out, int W, int C8, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C8);
+    const int64_t bh = i / C8;
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    for (int w = 0; w < W; ++w) {
+        float v[8];
+        bf16x8_to_float(__ldg(y + ((size_t)bh * W + w) * C8 + c), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += v[e];
+    }
+    const float inv = 1.0f / (float)W;
+    out[2 * i] = make_float4(s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv);
+    out[2 * i + 1] = make_float4(s[4] * inv, s[5] * inv, s[6] * inv, s[7] * inv);
+}
+
 // ConvBlock pooling of the SED tagger (hf_wrapper.py:1204-1212, pool_type 'avg+max'): avg_pool2d + max_pool2d over
 // (ph x pw) windows, stride = window, floor.  in [B, H, W, C] -> out [B, H/ph, W/pw, C]; one float4 per thread.
 __global__ void __launch_bounds__(256)
@@ -601,6 +652,7 @@ int ac_cnn14_fwd_train(const ac_cnn14_t* net, const float* lms, int B, int n_mel
 // only the 0/1 label matrix goes back to the host for the tiny pairwise segment rule.
 struct ac_sed {
     float* blob = nullptr;
+    void* blob_bf16 = nullptr;    // bf16 images of the convolution weights (precision mode 16)
     float *bn0_s, *bn0_b, *w1, *s1, *b1;
     ac::Cnn14Conv conv[7];
     float *fc1_w, *fc1_b, *fco_w, *fco_b;
@@ -632,7 +684,8 @@ extern "C" {
 
 int ac_sed_set_precision(ac_sed_t* net, int tf32_passes) {
     using namespace ac;
-    AC_REQUIRE(net && (tf32_passes == 1 || tf32_passes == 3), "ac_sed_set_precision: passes must be 1 or 3");
+    AC_REQUIRE(net && (tf32_passes == 1 || tf32_passes == 3 || tf32_passes == 16),
+               "ac_sed_set_precision: mode must be 3 (3xTF32), 1 (TF32) or 16 (bf16)");
     net->conv_passes = tf32_passes;
     return AC_OK;
 }
@@ -682,7 +735,10 @@ int ac_sed_create(const float* const* t, const int64_t* numels, int n_tensors, i
     ac_sed_t* net = new ac_sed_t();
     net->classes = classes; net->classes_pad = CP;
     float* perm = nullptr;
+    size_t bf_total = 0, bf_off[7];
+    for (int q = 0; q < 7; ++q) { bf_off[q] = bf_total; bf_total += align_up(conv_bf16_packed_elems(cout_[q], cin_[q]), 64); }
     int rc = check_cuda(cudaMalloc(&net->blob, total * sizeof(float)), "ac_sed_create: cudaMalloc(weights)");
+    if (rc == AC_OK) rc = check_cuda(cudaMalloc(&net->blob_bf16, bf_total * 2), "ac_sed_create: cudaMalloc(bf16 weights)");
     if (rc == AC_OK) rc = check_cuda(cudaMalloc(&perm, perm_max * sizeof(float)), "ac_sed_create: cudaMalloc(scratch)");
     if (rc == AC_OK) rc = check_cuda(cudaMemsetAsync(net->blob, 0, total * sizeof(float), st), "memset");
     if (rc != AC_OK) { cudaFree(net->blob); delete net; return rc; }
@@ -709,6 +765,7 @@ int ac_sed_create(const float* const* t, const int64_t* numels, int n_tensors, i
             fold(bn_ti, c.cout, c.scale, c.bias);
             rc = conv3x3_permute_weight(t[base + j], perm, c.cout, c.cin, st);
             if (rc == AC_OK) rc = tc_pack_weight(perm, c.scale, c.cout, 9 * c.cin, B0 + co_[l].pk, st, &c.tw);
+            if (rc == AC_OK) rc = conv_bf16_pack(perm, c.scale, c.cout, c.cin, (uint16_t*)net->blob_bf16 + bf_off[l], st, &c.bw);
             ++l;
         }
     }
@@ -734,6 +791,7 @@ void ac_sed_destroy(ac_sed_t* net) {
     if (!net) return;
     ac_bigru_destroy(net->gru);
     cudaFree(net->blob);
+    cudaFree(net->blob_bf16);
     delete net;
 }
 
@@ -772,6 +830,45 @@ int ac_sed_fwd(const ac_sed_t* net, const float* lms, int B, int n_mels, int n_f
     sed_walk(n_mels, n_frames, d);
     AC_REQUIRE(d[kSedBlocks].H == S, "ac_sed_fwd: internal frame count mismatch");
     int rc;
+    if (net->conv_passes == 16) {
+        // bf16 precision mode: activations in bf16 NHWC up to the mean over mel (see ac_cnn14_fwd_train)
+        __nv_bfloat16* bcur = reinterpret_cast<__nv_bfloat16*>(cur);
+        __nv_bfloat16* bnxt = reinterpret_cast<__nv_bfloat16*>(nxt);
+        {
+            AC_TIMED("sed_conv1", st);
+            dim3 grid(cdiv(n_frames, kC1Time), B);
+            const size_t smem = (size_t)(kC1Time + 2) * (n_mels + 2) * sizeof(float);
+            rc = launch_pdl(cnn14_conv1_kernel<__nv_bfloat16>, grid, dim3(kC1Threads), smem, st, lms, (const float*)net->bn0_s,
+                            (const float*)net->bn0_b, (const float*)net->w1, (const float*)net->s1, (const float*)net->b1, bcur,
+                            n_mels, n_frames);
+            if (rc) return rc;
+            AC_LAUNCHED("cnn14_conv1_kernel");
+        }
+        int l = 0;
+        for (int i = 0; i < kSedBlocks; ++i) {
+            for (int j = 0; j < 2; ++j) {
+                if (i == 0 && j == 0) continue;
+                const Cnn14Conv& c = net->conv[l++];
+                ConvBf16Args a; a.in = bcur; a.out = bnxt; a.B = B; a.H = d[i].H; a.W = d[i].W; a.Cin = c.cin; a.Cout = c.cout;
+                a.bias = c.bias; a.w = &c.bw; a.act = ACT_RELU;
+                rc = conv3x3_bf16(a, st); if (rc) return rc;
+                std::swap(bcur, bnxt);
+            }
+            const int C8 = kSedCh[i + 1] / 8, Ho = d[i + 1].H, Wo = d[i + 1].W;
+            const int64_t total = (int64_t)B * Ho * Wo * C8;
+            AC_TIMED("sed_pool", st);
+            rc = launch_pdl(cnn_avgmax_pool_bf16_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st, (const uint4*)bcur,
+                            (uint4*)bnxt, d[i].H, d[i].W, C8, Ho, Wo, kSedPoolH[i], 2, total);
+            if (rc) return rc;
+            AC_LAUNCHED("cnn_avgmax_pool_kernel");
+            std::swap(bcur, bnxt);
+        }
+        const int64_t total = (int64_t)rows * (D / 8);
+        rc = launch_pdl(cnn_wmean_bf16_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, st, (const uint4*)bcur, (float4*)X,
+                        d[kSedBlocks].W, D / 8, total);
+        if (rc) return rc;
+        AC_LAUNCHED("cnn_wmean_kernel");
+    } else {
     {
         AC_TIMED("sed_conv1", st);
         dim3 grid(cdiv(n_frames, kC1Time), B);
@@ -806,6 +903,7 @@ int ac_sed_fwd(const ac_sed_t* net, const float* lms, int B, int n_mels, int n_f
                         d[kSedBlocks].W, D / 4, total);
         if (rc) return rc;
         AC_LAUNCHED("cnn_wmean_kernel");
+    }
     }
     GemmArgs g; g.A = X; g.W = net->fc1_w; g.C = F1; g.M = (int)rows; g.N = D; g.K = D; g.cbias = net->fc1_b; g.act = ACT_RELU; g.tw = &net->fc1_tw;
     rc = gemm_tn(g, st); if (rc) return rc;

@@ -364,7 +364,7 @@ def run_config5_leg(dev, rank, world, timed, steps=10):
     out = {}
     for prec in ("fp32", "tf32", "bf16"):
         m.cap_model.encoder.cnn.conv_precision = prec
-        m.sed_model.conv_precision = "tf32" if prec == "bf16" else prec      # (the SED tagger has no bf16 mode)
+        m.sed_model.conv_precision = prec
         ms, launches = timed(lambda i: m(devb[i % 8], lens, sample_method="beam", beam_size=4, max_length=MAX_LEN), steps, 3)
         ms_e2e, _ = timed(lambda i: m(host[i % 8], lens, sample_method="beam", beam_size=4, max_length=MAX_LEN), steps, 3)
         out[prec] = {"value": world * B / (ms / 1000.0), "unit": "clips/s", "ms_per_step": ms,
@@ -376,8 +376,8 @@ def run_config5_leg(dev, rank, world, timed, steps=10):
     return {"workload": "Cnn14Rnn-TempGRU temporal model, beam 4, SED tagger on, 16 clips x 10 s @ 32 kHz per GPU "
                         f"(configs[4]: 128 clips over 8 GPUs), {world} GPU(s), sharded over clips, no collective",
             "n_gpus": world, "bf16": out["bf16"], "tf32": out["tf32"], "fp32": out["fp32"],
-            "note": "bf16 = Cnn14 captioner encoder in bf16 (SED tagger convolutions in TF32); tf32 = plain-TF32 convolutions; "
-                    "fp32 = 3xTF32 everywhere"}
+            "note": "bf16 = Cnn14 encoder and SED tagger convolutions on bf16 activations / weights; tf32 = plain-TF32 "
+                    "convolutions; fp32 = 3xTF32 everywhere"}
 
 
 def run_native(args):
