@@ -39,8 +39,8 @@ for l in step:
     f["time_us"] += l.get("gpu__time_duration.sum", 0.0)
     f["dram_bytes"] += l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0)
 tot = sum(f["time_us"] for f in fam.values())
-lines = [f"# one training step (32 clips x 10 s, tf32 convolutions, 2 sampled steps), ncu --metrics gpu__time_duration.sum,dram__bytes_*"
-         f" --clock-control none python scripts/train_one_step.py 1 tf32: {len(step)} launches, {tot / 1e3:.3f} ms (cold-cache, serialised)",
+lines = [f"# one training step (32 clips x 10 s, bf16 frozen CNN, 2 sampled steps), ncu --metrics gpu__time_duration.sum,dram__bytes_*"
+         f" --clock-control none python scripts/train_one_step.py 1 bf16: {len(step)} launches, {tot / 1e3:.3f} ms (cold-cache, serialised)",
          f"{'kernel':58s} {'n':>4s} {'time us':>10s} {'share':>7s} {'DRAM MB':>9s}"]
 for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["time_us"]):
     f["share_of_step"] = f["time_us"] / tot
@@ -71,14 +71,14 @@ if os.path.exists(p):
 
 # ---- full captures
 want = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__shared_mem_per_block_dynamic", "launch__cluster_size", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_membar.ratio",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio")
 summary = []
-for name in ("greedy_heads", "beam_heads", "stem", "logmel", "se", "bigru_bwd", "bigru_fwd", "attn_bwd", "conv_tf32", "ls_ce", "adam"):
+for name in ("greedy_heads", "beam_heads", "stem", "logmel", "se", "conv_bf16", "bigru_bwd", "bigru_fwd", "attn_bwd", "conv_tf32", "ls_ce", "adam"):
     rep = os.path.join(ROOT, "gpurun_out", f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue

@@ -1,5 +1,5 @@
 """One warm training step + N profiled steps of the training workload (for ncu launch lists / captures).
-usage: python scripts/train_one_step.py [n_steps] [precision fp32|tf32] [ss_ratio]"""
+usage: python scripts/train_one_step.py [n_steps] [precision fp32|tf32|bf16] [ss_ratio]"""
 import os, random, sys, warnings
 warnings.filterwarnings("ignore")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
