@@ -159,6 +159,7 @@ struct ac_bigru_train {
     ac::TcPackJob* jobs_dev = nullptr; int n_jobs = 0; long long job_items = 0;
     std::vector<ac::GruTrainLayer> layer;
     float* blob = nullptr;
+    ac::SideStreams side;             // weight-gradient GEMMs off the backward pass's critical path
 };
 
 namespace ac {
@@ -166,7 +167,7 @@ struct GruWs {
     size_t total = 0;
     size_t G;                                     // [M, 6H] input projections of the current layer (forward only)
     std::vector<size_t> Y, Yd, save, hprev;       // per layer: output, dropped output (= next layer's input), saved gates
-    size_t dGi, dGh, dY, dX, lin;
+    size_t dGi, dGh, dY, dX, side, side_floats;   // side: private scratch of every linear_bwd call of one backward pass
 };
 static GruWs gru_ws_layout(const ac_bigru_train* h, int B, int T) {
     GruWs w;
@@ -179,10 +180,11 @@ static GruWs gru_ws_layout(const ac_bigru_train* h, int B, int T) {
         w.save.push_back(take(M * 8 * H)); w.hprev.push_back(take(M * 2 * H));
     }
     w.dGi = take(M * 6 * H); w.dGh = take(M * 6 * H); w.dY = take(M * 2 * H); w.dX = take(M * 2 * H);
-    size_t lin = 0;
-    lin = std::max(lin, linear_bwd_scratch_floats((int)M, 3 * H, h->input_dim));
-    lin = std::max(lin, linear_bwd_scratch_floats((int)M, 3 * H, 2 * H));
-    w.lin = take(lin);
+    size_t side = 0;
+    for (int l = 0; l < h->layers; ++l)
+        side += 2 * (linear_bwd_scratch_floats((int)M, 3 * H, l == 0 ? h->input_dim : 2 * H) + linear_bwd_scratch_floats((int)M, 3 * H, H));
+    w.side_floats = side;
+    w.side = take(side);
     return w;
 }
 }  // namespace ac
@@ -230,12 +232,15 @@ int ac_bigru_train_create(const float* const* p, float* const* g, const int64_t*
     rc = check_cuda(cudaMalloc(&h->jobs_dev, jobs.size() * sizeof(TcPackJob)), "ac_bigru_train_create: cudaMalloc jobs");
     if (rc == AC_OK) rc = check_cuda(cudaMemcpy(h->jobs_dev, jobs.data(), jobs.size() * sizeof(TcPackJob), cudaMemcpyHostToDevice), "jobs upload");
     if (rc != AC_OK) { cudaFree(h->blob); cudaFree(h->jobs_dev); delete h; return rc; }
+    rc = h->side.init();
+    if (rc != AC_OK) { h->side.destroy(); cudaFree(h->blob); cudaFree(h->jobs_dev); delete h; return rc; }
     *out = h;
     return AC_OK;
 }
 
 void ac_bigru_train_destroy(ac_bigru_train_t* h) {
     if (!h) return;
+    h->side.destroy();
     cudaFree(h->blob);
     cudaFree(h->jobs_dev);
     delete h;
@@ -305,6 +310,15 @@ int ac_bigru_train_bwd(ac_bigru_train_t* h, const float* x_dev, const int64_t* l
     static cudaError_t attr_rc = cudaFuncSetAttribute(bigru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGruBwdSmem);
     AC_CUDA(attr_rc);
     const float* dY = dout_dev;
+    // weight-gradient GEMMs run on side streams (train_ops.cuh): every call has its own scratch; dGi / dGh are transposed on
+    // the main stream before the next layer's recurrence overwrites them
+    SideStreams* side = &h->side;
+    size_t side_used = 0;
+    auto slot = [&](const Linear& y) {
+        float* p = ws + w.side + side_used;
+        side_used += linear_bwd_scratch_floats(M, y.N, y.K);
+        return side_used <= w.side_floats ? p : nullptr;
+    };
     for (int l = h->layers - 1; l >= 0; --l) {
         const GruTrainLayer& L = h->layer[l];
         GruBwdArgs a;
@@ -327,13 +341,16 @@ int ac_bigru_train_bwd(ac_bigru_train_t* h, const float* x_dev, const int64_t* l
             const float* dGi = ws + w.dGi + d * 3 * H;
             int rc = AC_OK;
             // (no dense copy of this direction's gate gradients: every consumer reads them through the 6H row stride)
-            rc = linear_bwd(L.ih[d], X, din, dGi, 6 * H, M, nullptr, nullptr, ws + w.lin, st); if (rc) return rc;
+            float* lin = slot(L.ih[d]);
+            AC_REQUIRE(lin != nullptr, "ac_bigru_train_bwd: side scratch exhausted");
+            rc = linear_bwd(L.ih[d], X, din, dGi, 6 * H, M, nullptr, nullptr, lin, st, side); if (rc) return rc;
             // hidden side: db_hh, dW_hh = dGh^T Hprev
             const float* dGh = ws + w.dGh + d * 3 * H;
-            if (L.dbhh[d]) { rc = colsum(dGh, M, 3 * H, 6 * H, L.dbhh[d], st); if (rc) return rc; }
-            if (L.dwhh[d]) {
-                Linear hh; hh.N = 3 * H; hh.K = H; hh.dW = L.dwhh[d];
-                rc = linear_bwd(hh, ws + w.hprev[l] + d * H, 2 * H, dGh, 6 * H, M, nullptr, nullptr, ws + w.lin, st); if (rc) return rc;
+            if (L.dbhh[d] || L.dwhh[d]) {
+                Linear hh; hh.N = 3 * H; hh.K = H; hh.dW = L.dwhh[d]; hh.db = L.dbhh[d];
+                lin = slot(hh);
+                AC_REQUIRE(lin != nullptr, "ac_bigru_train_bwd: side scratch exhausted");
+                rc = linear_bwd(hh, ws + w.hprev[l] + d * H, 2 * H, dGh, 6 * H, M, nullptr, nullptr, lin, st, side); if (rc) return rc;
             }
         }
         if (dXl != nullptr) {
@@ -358,7 +375,7 @@ int ac_bigru_train_bwd(ac_bigru_train_t* h, const float* x_dev, const int64_t* l
             }
         }
     }
-    return AC_OK;
+    return side->join(st);
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 // All fp32.  The GEMMs run on the tcgen05 kernel of gemm_tc.cu (3xTF32); everything else here is HBM/latency-bound
 // row-wise work over [rows, 256]-sized tensors (a training batch is 32 captions x <= 21 tokens = 672 rows).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "train_ops.cuh"
@@ -39,6 +40,79 @@ int colsum(const float* X, int M, int N, int ld, float* out, cudaStream_t st) {
     if (N <= 0) return AC_OK;
     colsum_kernel<<<cdiv(N, 32), 1024, 0, st>>>(X, M, N, ld, out);
     AC_LAUNCHED("colsum_kernel");
+    return AC_OK;
+}
+
+__global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ XT, int N, int Mp, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float4* row = reinterpret_cast<const float4*>(XT + (size_t)n * Mp);
+    float a0 = 0.0f, a1 = 0.0f;
+    int i = lane;
+    for (; i + 32 < Mp / 4; i += 64) {
+        const float4 u = row[i], v = row[i + 32];
+        a0 += (u.x + u.y) + (u.z + u.w); a1 += (v.x + v.y) + (v.z + v.w);
+    }
+    if (i < Mp / 4) { const float4 u = row[i]; a0 += (u.x + u.y) + (u.z + u.w); }
+    float t = a0 + a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) out[n] = t;
+}
+int rowsum(const float* XT, int N, int Mp, float* out, cudaStream_t st) {
+    if (N <= 0) return AC_OK;
+    AC_REQUIRE(Mp % 4 == 0, "rowsum: row length %d is not a multiple of 4", Mp);
+    rowsum_kernel<<<cdiv(N, 8), 256, 0, st>>>(XT, N, Mp, out);
+    AC_LAUNCHED("rowsum_kernel");
+    return AC_OK;
+}
+
+// ------------------------------------------------------------------------------------ side streams (weight gradients)
+int SideStreams::init() {
+    const char* e = getenv("AC_TRAIN_SIDE");
+    if (e != nullptr && atoi(e) == 0) return AC_OK;
+    for (int i = 0; i < kN; ++i) {
+        AC_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+        AC_CUDA(cudaEventCreateWithFlags(&fork_ev[i], cudaEventDisableTiming));
+        AC_CUDA(cudaEventCreateWithFlags(&done_ev[i], cudaEventDisableTiming));
+    }
+    AC_CUDA(cudaEventCreateWithFlags(&mark_ev, cudaEventDisableTiming));
+    ready = true;
+    return AC_OK;
+}
+void SideStreams::destroy() {
+    for (int i = 0; i < kN; ++i) {
+        if (s[i]) { cudaStreamSynchronize(s[i]); cudaStreamDestroy(s[i]); s[i] = nullptr; }
+        if (fork_ev[i]) { cudaEventDestroy(fork_ev[i]); fork_ev[i] = nullptr; }
+        if (done_ev[i]) { cudaEventDestroy(done_ev[i]); done_ev[i] = nullptr; }
+    }
+    if (mark_ev) { cudaEventDestroy(mark_ev); mark_ev = nullptr; }
+    ready = false;
+}
+int SideStreams::fork(cudaStream_t main_st, cudaStream_t* side) {
+    const int i = next; next = (next + 1) % kN;
+    AC_CUDA(cudaEventRecord(fork_ev[i], main_st));
+    AC_CUDA(cudaStreamWaitEvent(s[i], fork_ev[i], 0));
+    pending[i] = true; last = i;
+    *side = s[i];
+    return AC_OK;
+}
+int SideStreams::mark() {
+    AC_REQUIRE(last >= 0, "SideStreams::mark before any fork");
+    AC_CUDA(cudaEventRecord(mark_ev, s[last]));
+    return AC_OK;
+}
+int SideStreams::wait_mark(cudaStream_t main_st) {
+    AC_CUDA(cudaStreamWaitEvent(main_st, mark_ev, 0));
+    return AC_OK;
+}
+int SideStreams::join(cudaStream_t main_st) {
+    for (int i = 0; i < kN; ++i) {
+        if (!pending[i]) continue;
+        AC_CUDA(cudaEventRecord(done_ev[i], s[i]));
+        AC_CUDA(cudaStreamWaitEvent(main_st, done_ev[i], 0));
+        pending[i] = false;
+    }
     return AC_OK;
 }
 
@@ -100,20 +174,24 @@ size_t linear_bwd_scratch_floats(int M, int N, int K) {
     return align_up((size_t)N * Mp, 32) + align_up(tc_packed_floats(K, Mp), 32);
 }
 int linear_bwd(const Linear& l, const float* X, int ldx, const float* dY, int ldy, int M, float* dX, const float* R,
-               float* scratch, cudaStream_t st) {
+               float* scratch, cudaStream_t st, SideStreams* side) {
     int rc = AC_OK;
     const int Mp = pad8(M);
-    if (l.db != nullptr) { rc = colsum(dY, M, l.N, ldy, l.db, st); if (rc) return rc; }
     if (l.dW != nullptr) {
         float* dYT = scratch;                                        // [N, Mp]
         float* xpk = scratch + align_up((size_t)l.N * Mp, 32);       // packed X^T: "weight" [K, Mp]
         rc = transpose_pad(dY, M, l.N, ldy, dYT, Mp, st); if (rc) return rc;
+        cudaStream_t ws = st;                                        // the stream of the weight-gradient work
+        if (side != nullptr && side->enabled()) { rc = side->fork(st, &ws); if (rc) return rc; }
+        if (l.db != nullptr) { rc = rowsum(dYT, l.N, Mp, l.db, ws); if (rc) return rc; }
         TcWeight txw;
-        rc = tc_pack_weight_strided(X, nullptr, l.K, M, 1, ldx, xpk, st, &txw); if (rc) return rc;   // (k, m) -> X[m * ldx + k]
+        rc = tc_pack_weight_strided(X, nullptr, l.K, M, 1, ldx, xpk, ws, &txw); if (rc) return rc;   // (k, m) -> X[m * ldx + k]
         txw.K = Mp;                                                  // columns M..Mp-1 of the pack are zero
         GemmArgs g;
         g.A = dYT; g.W = nullptr; g.C = l.dW; g.M = l.N; g.N = l.K; g.K = Mp; g.tw = &txw;
-        rc = gemm_tc(g, st); if (rc) return rc;
+        rc = gemm_tc(g, ws); if (rc) return rc;
+    } else if (l.db != nullptr) {
+        rc = colsum(dY, M, l.N, ldy, l.db, st); if (rc) return rc;
     }
     if (dX != nullptr) {
         AC_REQUIRE(l.pkT != nullptr, "linear_bwd: the transposed weight was not packed (need_dx)");

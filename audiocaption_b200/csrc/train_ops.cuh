@@ -49,12 +49,35 @@ int linear_fwd(const Linear& l, const float* X, int M, float* Y, int ldy, int ac
 //   db = colsum(dY), dW = dY^T X (written, not accumulated), dX = dY W + R (R nullable; dX nullable).
 // scratch: linear_bwd_scratch_floats(M, N, K) floats, 128-byte aligned.
 size_t linear_bwd_scratch_floats(int M, int N, int K);
+// Weight gradients are LEAVES of the backward pass (only the optimizer reads them) and their GEMMs are tiny (4-24 CTAs, a
+// K loop over the token rows), so they leave the critical path: with `side` non-null the main stream only transposes dY
+// into the call's PRIVATE scratch, and db (row sums of dY^T), the pack of X and the dW GEMM run on one of the side
+// streams, concurrently with the dX GEMM and whatever follows on the main stream.  X must stay unmodified until
+// SideStreams::join (saved forward activations are).  Without `side` everything runs on `st` in order.
+struct SideStreams {
+    static constexpr int kN = 2;
+    cudaStream_t s[kN] = {};
+    cudaEvent_t fork_ev[kN] = {}, done_ev[kN] = {}, mark_ev = nullptr;
+    bool pending[kN] = {};
+    int next = 0, last = -1;
+    bool ready = false;
+    int init();                                          // creates the streams / events (AC_TRAIN_SIDE=0: stays disabled)
+    void destroy();
+    bool enabled() const { return ready; }
+    int fork(cudaStream_t main_st, cudaStream_t* side);  // *side waits for everything enqueued on main_st so far
+    cudaStream_t last_stream() const { return last >= 0 ? s[last] : nullptr; }
+    int mark();                                          // remember "everything enqueued on the last forked stream"
+    int wait_mark(cudaStream_t main_st);                 // ... and make main_st wait for it
+    int join(cudaStream_t main_st);                      // main_st waits for every side stream with work in flight
+};
 int linear_bwd(const Linear& l, const float* X, int ldx, const float* dY, int ldy, int M, float* dX, const float* R,
-               float* scratch, cudaStream_t st);
+               float* scratch, cudaStream_t st, SideStreams* side = nullptr);
 
 // ------------------------------------------------------------------------------------ small kernels
 // out[n] = sum_m X[m * ld + n]  (deterministic order)
 int colsum(const float* X, int M, int N, int ld, float* out, cudaStream_t st);
+// out[n] = sum_m XT[n * Mp + m]  (Mp % 4 == 0; one warp per row, fixed order)
+int rowsum(const float* XT, int N, int Mp, float* out, cudaStream_t st);
 // XT [N, Mp] = X[M, N]^T (row stride ld), zero-padded to Mp >= M columns
 int transpose_pad(const float* X, int M, int N, int ld, float* XT, int Mp, cudaStream_t st);
 // Row-wise kernels take BASE pointers and a row range [row0, row0 + n_rows): dropout masks are functions of the absolute

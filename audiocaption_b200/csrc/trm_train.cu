@@ -62,6 +62,7 @@ struct ac_trm_train {
     float* cls_stage = nullptr; float* dcls_stage = nullptr;     // [Vp, D] when V % 8 != 0
     float* blob = nullptr;
     ac::TcPackJob* jobs_dev = nullptr; int n_jobs = 0; long long job_items = 0;   // one batched re-pack launch per step
+    ac::SideStreams side;                                          // weight-gradient GEMMs off the backward pass's critical path
 };
 
 namespace ac {
@@ -77,7 +78,8 @@ struct TrmWs {
     std::vector<L> layer;
     size_t Xsel;
     // backward scratch
-    size_t dA, dB, dC, dQKV, dH, dKV, dPm, dU, lin, ln;
+    size_t dA, dB, dC, dQKV, dH, dKV, dPm, dU, ln;
+    size_t side, side_floats;    // private scratch of every linear_bwd call of one backward pass (they overlap in time)
 };
 static TrmWs trm_ws_layout(const ac_trm_train* h, int n_seq, int L, int B, int T) {
     TrmWs w;
@@ -100,14 +102,15 @@ static TrmWs trm_ws_layout(const ac_trm_train* h, int n_seq, int L, int B, int T
     w.dA = take(M * D); w.dB = take(M * D); w.dC = take(M * D); w.dQKV = take(M * 3 * D); w.dH = take(M * h->FF);
     w.dKV = take(Mm * 2 * D); w.dPm = take(Mm * D); w.dU = take(Mm * D);
     const size_t Mmax = std::max(M, Mm);
-    size_t lin = 0;
-    lin = std::max(lin, linear_bwd_scratch_floats((int)Mmax, h->Vp, D));
-    lin = std::max(lin, linear_bwd_scratch_floats((int)Mmax, 3 * D, D));
-    lin = std::max(lin, linear_bwd_scratch_floats((int)Mmax, h->FF, D));
-    lin = std::max(lin, linear_bwd_scratch_floats((int)Mmax, D, h->FF));
-    lin = std::max(lin, linear_bwd_scratch_floats((int)Mmax, D, h->E));
-    w.lin = take(lin);
     w.ln = take(ln_bwd_scratch_floats((int)Mmax, D));
+    // one slot per linear_bwd call, in the order ac_trm_train_bwd takes them
+    size_t side = linear_bwd_scratch_floats((int)M, h->Vp, D) + linear_bwd_scratch_floats((int)Mm, D, h->E);
+    for (int l = 0; l < h->NL; ++l)
+        side += linear_bwd_scratch_floats((int)M, D, h->FF) + linear_bwd_scratch_floats((int)M, h->FF, D) +
+                3 * linear_bwd_scratch_floats((int)M, D, D) + linear_bwd_scratch_floats((int)Mm, 2 * D, D) +
+                linear_bwd_scratch_floats((int)M, 3 * D, D);
+    w.side_floats = side;
+    w.side = take(side);
     return w;
 }
 
@@ -202,12 +205,15 @@ int ac_trm_train_create(const float* const* p, float* const* g, const int64_t* n
     rc = check_cuda(cudaMalloc(&h->jobs_dev, jobs.size() * sizeof(TcPackJob)), "ac_trm_train_create: cudaMalloc jobs");
     if (rc == AC_OK) rc = check_cuda(cudaMemcpy(h->jobs_dev, jobs.data(), jobs.size() * sizeof(TcPackJob), cudaMemcpyHostToDevice), "jobs upload");
     if (rc != AC_OK) { cudaFree(h->blob); cudaFree(h->jobs_dev); delete h; return rc; }
+    rc = h->side.init();
+    if (rc != AC_OK) { ac_trm_train_destroy(h); return rc; }
     *out = h;
     return AC_OK;
 }
 
 void ac_trm_train_destroy(ac_trm_train_t* h) {
     if (!h) return;
+    h->side.destroy();
     cudaFree(h->blob);
     cudaFree(h->jobs_dev);
     delete h;
@@ -358,21 +364,37 @@ int ac_trm_train_bwd(ac_trm_train_t* h, const float* dlogits_dev, const int* row
     float* ws = (float*)workspace_dev;
     const int D = h->D, FF = h->FF, M = n_seq * L, Mm = B * T;
     const Dropout dp{p_drop, seed};
-    float* lin = ws + w.lin; float* lns = ws + w.ln;
+    float* lns = ws + w.ln;
     AC_TIMED("span_trm_train_bwd", st);      // wrapper span: contains the per-kernel timers below
     int rc = AC_OK;
+    SideStreams* side = &h->side;
+    size_t side_used = 0;                    // every linear_bwd call gets its own scratch: its dW work runs on a side stream
+    auto slot = [&](int m, const Linear& y) {
+        float* p = ws + w.side + side_used;
+        side_used += linear_bwd_scratch_floats(m, y.N, y.K);
+        return side_used <= w.side_floats ? p : nullptr;
+    };
+    float* lin = nullptr;
+#define AC_SLOT(m, y) lin = slot(m, y); AC_REQUIRE(lin != nullptr, "ac_trm_train_bwd: side scratch exhausted")
     // ---- classifier: dXsel = dlogits W, dW = dlogits^T Xsel
     float* dXf = ws + w.dA;              // gradient of the current layer's output [M, D]
     if (rows_dev != nullptr) {
-        rc = linear_bwd(h->cls, ws + w.Xsel, D, dlogits_dev, h->Vp, n_rows, ws + w.dB, nullptr, lin, st); if (rc) return rc;
+        AC_SLOT(n_rows, h->cls);
+        rc = linear_bwd(h->cls, ws + w.Xsel, D, dlogits_dev, h->Vp, n_rows, ws + w.dB, nullptr, lin, st, side); if (rc) return rc;
         AC_CUDA(cudaMemsetAsync(dXf, 0, (size_t)M * D * sizeof(float), st));
         rc = scatter_rows(ws + w.dB, rows_dev, n_rows, D, dXf, st); if (rc) return rc;
     } else {
         AC_REQUIRE(n_rows == M, "ac_trm_train_bwd: without a row selection the logits must cover all %d rows", M);
-        rc = linear_bwd(h->cls, ws + w.Xsel, D, dlogits_dev, h->Vp, n_rows, dXf, nullptr, lin, st); if (rc) return rc;
+        AC_SLOT(n_rows, h->cls);
+        rc = linear_bwd(h->cls, ws + w.Xsel, D, dlogits_dev, h->Vp, n_rows, dXf, nullptr, lin, st, side); if (rc) return rc;
     }
+    // the classifier's weight gradient was computed on a side stream (when enabled): the un-padding copy follows it there,
+    // and the embedding gradient (which accumulates on top of it when the weights are tied) waits for the mark below
+    const bool cls_on_side = side->enabled() && h->cls.dW != nullptr;
     if (h->dcls_stage != nullptr && h->dcls_w != nullptr)
-        AC_CUDA(cudaMemcpyAsync(h->dcls_w, h->dcls_stage, (size_t)h->V * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        AC_CUDA(cudaMemcpyAsync(h->dcls_w, h->dcls_stage, (size_t)h->V * D * sizeof(float), cudaMemcpyDeviceToDevice,
+                                cls_on_side ? side->last_stream() : st));
+    if (cls_on_side) { rc = side->mark(); if (rc) return rc; }
     // ---- decoder layers, last to first.  dKV accumulates the memory-side gradient of each layer into dPm.
     bool first_mem = true;
     for (int l = h->NL - 1; l >= 0; --l) {
@@ -383,39 +405,47 @@ int ac_trm_train_bwd(ac_trm_train_t* h, const float* dlogits_dev, const int* row
         float* dS = ws + w.dB; float* dO = ws + w.dC;
         // X3 = LN3(X2 + drop(F)),  F = l2(Hff)
         rc = add_ln_bwd(dXf, ws + a.S3, ws + a.mean3, ws + a.rstd3, y.nw[2], M, D, dp, site + LS_FF_OUT, dS, dO, y.dnw[2], y.dnb[2], lns, st); if (rc) return rc;
-        rc = linear_bwd(y.l2, ws + a.Hff, FF, dO, D, M, ws + w.dH, nullptr, lin, st); if (rc) return rc;
+        AC_SLOT(M, y.l2);
+        rc = linear_bwd(y.l2, ws + a.Hff, FF, dO, D, M, ws + w.dH, nullptr, lin, st, side); if (rc) return rc;
         rc = relu_drop_bwd(ws + w.dH, ws + a.Hff, (int64_t)M * FF, dp, site + LS_FF_H, ws + w.dH, st); if (rc) return rc;
-        rc = linear_bwd(y.l1, ws + a.X2, D, ws + w.dH, FF, M, dXf, dS, lin, st); if (rc) return rc;           // dX2 = dH W1 + dS3
+        AC_SLOT(M, y.l1);
+        rc = linear_bwd(y.l1, ws + a.X2, D, ws + w.dH, FF, M, dXf, dS, lin, st, side); if (rc) return rc;           // dX2 = dH W1 + dS3
         // X2 = LN2(X1 + drop(Oc)),  Oc = ca_out(Aca)
         rc = add_ln_bwd(dXf, ws + a.S2, ws + a.mean2, ws + a.rstd2, y.nw[1], M, D, dp, site + LS_CA_OUT, dS, dO, y.dnw[1], y.dnb[1], lns, st); if (rc) return rc;
-        rc = linear_bwd(y.ca_out, ws + a.Aca, D, dO, D, M, dXf, nullptr, lin, st); if (rc) return rc;         // dXf = dAca
+        AC_SLOT(M, y.ca_out);
+        rc = linear_bwd(y.ca_out, ws + a.Aca, D, dO, D, M, dXf, nullptr, lin, st, side); if (rc) return rc;         // dXf = dAca
         AttnBwdArgs cb{};
         cb.f.Q = ws + a.Qc; cb.f.K = ws + w.KV[l]; cb.f.V = ws + w.KV[l] + D; cb.f.ldq = D; cb.f.ldkv = 2 * D;
         cb.f.key_pad = nullptr; cb.f.kv_len = attn_len_dev; cb.f.seq0 = 0; cb.f.n_seq = n_seq; cb.f.n_kv_seq = B; cb.f.L = L; cb.f.Lk = T;
         cb.f.H = h->H; cb.f.causal = false; cb.f.dp = dp; cb.f.site = site + LS_CA_P; cb.f.P = ws + a.Pca;
         cb.dO = dXf; cb.lddo = D; cb.dQ = dO; cb.lddq = D; cb.dK = ws + w.dKV; cb.dV = ws + w.dKV + D; cb.lddkv = 2 * D;
         rc = attn_bwd(cb, st); if (rc) return rc;                                                              // dO = dQc
-        rc = linear_bwd(y.ca_q, ws + a.X1, D, dO, D, M, dXf, dS, lin, st); if (rc) return rc;                  // dX1 = dQc Wq + dS2
+        AC_SLOT(M, y.ca_q);
+        rc = linear_bwd(y.ca_q, ws + a.X1, D, dO, D, M, dXf, dS, lin, st, side); if (rc) return rc;                  // dX1 = dQc Wq + dS2
         // memory side of this layer: dPm (+)= dKV W_kv
-        if (first_mem) { rc = linear_bwd(y.ca_kv, ws + w.Pm, D, ws + w.dKV, 2 * D, Mm, ws + w.dPm, nullptr, lin, st); first_mem = false; }
+        AC_SLOT(Mm, y.ca_kv);
+        if (first_mem) { rc = linear_bwd(y.ca_kv, ws + w.Pm, D, ws + w.dKV, 2 * D, Mm, ws + w.dPm, nullptr, lin, st, side); first_mem = false; }
         else {
-            rc = linear_bwd(y.ca_kv, ws + w.Pm, D, ws + w.dKV, 2 * D, Mm, ws + w.dU, ws + w.dPm, lin, st);
+            rc = linear_bwd(y.ca_kv, ws + w.Pm, D, ws + w.dKV, 2 * D, Mm, ws + w.dU, ws + w.dPm, lin, st, side);
             if (rc == AC_OK) rc = check_cuda(cudaMemcpyAsync(ws + w.dPm, ws + w.dU, (size_t)Mm * D * sizeof(float), cudaMemcpyDeviceToDevice, st), "dPm copy");
         }
         if (rc) return rc;
         // X1 = LN1(X + drop(Osa)),  Osa = sa_out(Asa)
         rc = add_ln_bwd(dXf, ws + a.S1, ws + a.mean1, ws + a.rstd1, y.nw[0], M, D, dp, site + LS_SA_OUT, dS, dO, y.dnw[0], y.dnb[0], lns, st); if (rc) return rc;
-        rc = linear_bwd(y.sa_out, ws + a.Asa, D, dO, D, M, dXf, nullptr, lin, st); if (rc) return rc;         // dXf = dAsa
+        AC_SLOT(M, y.sa_out);
+        rc = linear_bwd(y.sa_out, ws + a.Asa, D, dO, D, M, dXf, nullptr, lin, st, side); if (rc) return rc;         // dXf = dAsa
         AttnBwdArgs sb{};
         sb.f.Q = ws + a.QKV; sb.f.K = ws + a.QKV + D; sb.f.V = ws + a.QKV + 2 * D; sb.f.ldq = 3 * D; sb.f.ldkv = 3 * D;
         sb.f.key_pad = key_pad_dev; sb.f.kv_len = nullptr; sb.f.seq0 = 0; sb.f.n_seq = n_seq; sb.f.n_kv_seq = n_seq; sb.f.L = L; sb.f.Lk = L;
         sb.f.H = h->H; sb.f.causal = true; sb.f.dp = dp; sb.f.site = site + LS_SA_P; sb.f.P = ws + a.Psa;
         sb.dO = dXf; sb.lddo = D; sb.dQ = ws + w.dQKV; sb.lddq = 3 * D; sb.dK = ws + w.dQKV + D; sb.dV = ws + w.dQKV + 2 * D; sb.lddkv = 3 * D;
         rc = attn_bwd(sb, st); if (rc) return rc;
-        rc = linear_bwd(y.sa_in, Xin, D, ws + w.dQKV, 3 * D, M, dXf, dS, lin, st); if (rc) return rc;         // dXin = dQKV Win + dS1
+        AC_SLOT(M, y.sa_in);
+        rc = linear_bwd(y.sa_in, Xin, D, ws + w.dQKV, 3 * D, M, dXf, dS, lin, st, side); if (rc) return rc;         // dXin = dQKV Win + dS1
     }
     // ---- embedding
     if (h->demb != nullptr) {
+        if (cls_on_side && h->tied) { rc = side->wait_mark(st); if (rc) return rc; }
         if (!(h->tied && h->dcls_w != nullptr)) AC_CUDA(cudaMemsetAsync(h->demb, 0, (size_t)h->V * D * sizeof(float), st));
         rc = embed_bwd(dXf, word_dev, M, L, D, h->V, sqrtf((float)D), dp, h->demb, st); if (rc) return rc;
     }
@@ -426,9 +456,11 @@ int ac_trm_train_bwd(ac_trm_train_t* h, const float* dlogits_dev, const int* row
     {
         Linear ap = h->ap0;
         if (dattn_emb_dev == nullptr) ap.pkT = nullptr;
-        rc = linear_bwd(ap, attn_emb_dev, h->E, ws + w.dU, D, Mm, dattn_emb_dev, nullptr, lin, st); if (rc) return rc;
+        AC_SLOT(Mm, ap);
+        rc = linear_bwd(ap, attn_emb_dev, h->E, ws + w.dU, D, Mm, dattn_emb_dev, nullptr, lin, st, side); if (rc) return rc;
     }
-    return AC_OK;
+#undef AC_SLOT
+    return side->join(st);          // the caller's stream sees every gradient (and may reuse the workspace) after this call
 }
 
 }  // extern "C"
