@@ -172,7 +172,13 @@ class GruTrainEngine:
             self._handle, self._key, self._grads = h, key, gts
         return self._handle
 
-    def forward(self, x, len_dev, p_drop=0.0, seed=None, grads="param", need_dx=False):
+    def refresh(self, grads="param", need_dx=False):
+        """Re-pack the live weights into the tensor core's layout on the CURRENT stream (once per optimizer step; `forward`
+        does it itself unless told that the caller already has, e.g. on a side stream next to the frozen CNN)."""
+        with torch.cuda.device(self.enc.network.weight_hh_l0.device):
+            _lib.check(_lib.lib().ac_bigru_train_refresh(self.handle(grads, need_dx), _lib.current_stream()), "ac_bigru_train_refresh")
+
+    def forward(self, x, len_dev, p_drop=0.0, seed=None, grads="param", need_dx=False, refresh=True):
         """x [B, T, D] fp32 cuda (T = max length), len_dev [B] int64 cuda -> out [B, T, 512].  need_dx: the backward call
         will be asked for the gradient w.r.t. x (never the case when the CNN below is frozen)."""
         l = _lib.lib()
@@ -185,7 +191,8 @@ class GruTrainEngine:
             nbytes = l.ac_bigru_train_workspace_bytes(h, B, T)
             ws = self._ws.get(nbytes, dev)
             out = torch.empty(B, T, self.enc.embed_dim, dtype=torch.float32, device=dev)
-            _lib.check(l.ac_bigru_train_refresh(h, st), "ac_bigru_train_refresh")
+            if refresh:
+                _lib.check(l.ac_bigru_train_refresh(h, st), "ac_bigru_train_refresh")
             _lib.check(l.ac_bigru_train_fwd(h, _lib.ptr(x), _lib.ptr(len_dev), B, T, p_drop, seed, _lib.ptr(out), _lib.ptr(ws),
                                             nbytes, st), "ac_bigru_train_fwd")
         self._ctx = dict(x=x, lens=len_dev, B=B, T=T, p_drop=p_drop, seed=seed, nbytes=nbytes)

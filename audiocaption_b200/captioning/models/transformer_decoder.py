@@ -287,8 +287,14 @@ class DecoderTrainEngine:
     def new_seed():
         return int(torch.randint(0, 2 ** 62, (1,)).item())
 
+    def refresh(self, grads="param"):
+        """Re-pack the live weights on the CURRENT stream (once per optimizer step; `forward` does it itself unless told
+        that the caller already has)."""
+        with torch.cuda.device(self.dec.classifier.weight.device):
+            _lib.check(_lib.lib().ac_trm_train_refresh(self.handle(grads), _lib.current_stream()), "ac_trm_train_refresh")
+
     def forward(self, attn_emb, attn_len_dev, words, key_pad=None, coins=None, p_drop=0.0, seed=None, grads="param",
-                start_idx=1, pad_idx=0, end_idx=2):
+                start_idx=1, pad_idx=0, end_idx=2, refresh=True):
         """attn_emb [B, T, E] fp32 cuda; attn_len_dev [B] int64 cuda; words [B, L] int64 cuda (ground-truth prefix tokens
         `cap[:, :-1]`, or the given prefix for a plain decoder call); key_pad [B, L] bool (default: words == pad_idx);
         coins: None (teacher forcing) or a list of L bools, True = this step's prefix is the ground truth.
@@ -309,7 +315,8 @@ class DecoderTrainEngine:
             Vp = l.ac_trm_train_vocab_padded(h)
             nbytes = l.ac_trm_train_workspace_bytes(h, n_seq, L, B, T)
             ws = self._ws.get(nbytes, dev)
-            _lib.check(l.ac_trm_train_refresh(h, st), "ac_trm_train_refresh")
+            if refresh:
+                _lib.check(l.ac_trm_train_refresh(h, st), "ac_trm_train_refresh")
             _lib.check(l.ac_trm_train_memory_fwd(h, _lib.ptr(attn_emb), B, T, n_seq, L, p_drop, seed, _lib.ptr(ws), nbytes, st),
                        "ac_trm_train_memory_fwd")
             word_rows = torch.full((n_seq, L), pad_idx, dtype=torch.int64, device=dev)

@@ -272,9 +272,14 @@ int ac_bigru_train_fwd(ac_bigru_train_t* h, const float* x_dev, const int64_t* l
     const float* in = x_dev;
     for (int l = 0; l < h->layers; ++l) {
         const GruTrainLayer& L = h->layer[l];
+        // the two directions' input projections are independent: the second one runs on a side stream (forked BEFORE the
+        // first is enqueued, so that it only waits for the layer's input)
+        cudaStream_t ps = st;
+        if (h->side.enabled()) { int rc = h->side.fork(st, &ps); if (rc) return rc; }
         for (int d = 0; d < 2; ++d) {
-            int rc = linear_fwd(L.ih[d], in, M, ws + w.G + d * 3 * H, 6 * H, ACT_NONE, nullptr, st); if (rc) return rc;
+            int rc = linear_fwd(L.ih[d], in, M, ws + w.G + d * 3 * H, 6 * H, ACT_NONE, nullptr, d == 0 ? st : ps); if (rc) return rc;
         }
+        { int rc = h->side.join(st); if (rc) return rc; }
         const bool last = l + 1 == h->layers;
         GruStepArgs a;
         a.G = ws + w.G; a.lens = lens_dev; a.out = last ? out_dev : ws + w.Y[l]; a.B = B; a.T_in = T; a.T_out = T;

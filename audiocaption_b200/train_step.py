@@ -62,6 +62,32 @@ def allreduce_gradients(flat_grad, group=None):
     return 1.0 / world
 
 
+def allreduce_bucket_async(bucket, group=None):
+    """Start the sum all-reduce of one contiguous slice of the flat gradient (it runs on the collective's own stream, behind
+    everything enqueued on the current stream so far); returns the work handle, or None when not distributed."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return None
+    if torch.distributed.get_world_size(group) == 1 or bucket.numel() == 0:
+        return None
+    return torch.distributed.all_reduce(bucket, group=group, async_op=True)
+
+
+def bucket_boundary(model, params):
+    """Offset (in floats of the flat buffers) where the decoder's parameters start, when the flat order is
+    [encoder..., decoder...] (it is: `model.parameters()` yields the encoder first) -- else None.  The decoder's gradients
+    are complete before the GRU's backward pass starts, so their all-reduce overlaps it."""
+    dec_ids = {id(p) for p in model.decoder.parameters()}
+    off, boundary = 0, None
+    for p in params:
+        if id(p) in dec_ids:
+            if boundary is None:
+                boundary = off
+        elif boundary is not None:
+            return None                      # an encoder parameter after a decoder one: no clean split
+        off += (p.numel() + 31) // 32 * 32
+    return boundary
+
+
 class TrainStep:
     """`step(batch)` = one optimizer step of the reference's training loop on the Cnn14Rnn-Transformer captioner
     (eg_configs/*/waveform/cnn14rnn_trm.yaml): TransformerModel(CrnnEncoder(Cnn14Encoder, RnnEncoder), TransformerDecoder)."""
@@ -108,6 +134,7 @@ class TrainStep:
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.n_trainable = sum(p.numel() for p in self.params)
+        self.dec_offset = bucket_boundary(self.model, self.params)      # flat_grad[dec_offset:] = the decoder's gradients
 
     # ---- schedules (host) ---------------------------------------------------------------------------------------------
     def _update_ss_ratio(self):
@@ -121,10 +148,37 @@ class TrainStep:
         else:
             raise Exception(f"mode {self.ss_mode} not supported")
 
+    # ---- input staging ------------------------------------------------------------------------------------------------
+    def prefetch(self, batch):
+        """Start the host -> device upload of a batch's waveforms and captions on a copy stream (asynchronous when the host
+        tensors are pinned) and return the staged batch for `step`: the upload of batch i+1 then overlaps the kernels of
+        step i (what a DataLoader prefetcher does for the reference's loop).  Two staging slots; a slot is overwritten only
+        after the step that read it has finished with it."""
+        dev = self.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [{"free": None, "wav": None, "cap": None}, {"free": None, "wav": None, "cap": None}]
+            self._stage_i = 0
+        k = self._stage_i
+        self._stage_i ^= 1
+        s = self._stage[k]
+        with torch.cuda.device(dev), torch.cuda.stream(self._copy_stream), torch.no_grad():
+            if s["free"] is not None:
+                self._copy_stream.wait_event(s["free"])
+            for name, dt in (("wav", torch.float32), ("cap", torch.int64)):
+                src = batch[name]
+                if s[name] is None or s[name].shape != src.shape:
+                    s[name] = torch.empty(src.shape, dtype=dt, device=dev)
+                s[name].copy_(src, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        return dict(batch, wav=s["wav"], cap=s["cap"], _ready=ready, _slot=k)
+
     # ---- one step -------------------------------------------------------------------------------------------------------
     def step(self, batch, coins=None):
-        """batch: {"wav" [B, N] fp32 (host, ideally pinned, or cuda), "wav_len" [B], "cap" [B, Lc] int64, "cap_len" [B]}.
-        Returns {"loss": device scalar tensor [1], "tokens": int, "lr": float, "ss_ratio": float}."""
+        """batch: {"wav" [B, N] fp32 (host, ideally pinned, or cuda), "wav_len" [B], "cap" [B, Lc] int64, "cap_len" [B]},
+        or what `prefetch(batch)` returned.  Returns {"loss": device scalar tensor [1], "tokens": int, "lr": float,
+        "ss_ratio": float}."""
         m = self.model
         dev = self.device
         l = _lib.lib()
@@ -132,6 +186,18 @@ class TrainStep:
         # the scheduler was stepped once by its constructor; iteration k (0-based) steps it for the (k+2)-th time (run.py:105)
         self.lr = exponential_decay_lr(self.iteration + 2, self.base_lr, self.final_lr, self.total_iters, self.warmup_iters)
         with torch.cuda.device(dev), torch.no_grad():
+            main = torch.cuda.current_stream()
+            if "_ready" in batch:
+                main.wait_event(batch["_ready"])
+            # the weight re-pack of both trainable engines only depends on the previous optimizer step: it runs on a side
+            # stream next to the frozen CNN's forward pass
+            rnn, dec = m.encoder.rnn, m.decoder
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            self._side_stream.wait_stream(main)
+            with torch.cuda.stream(self._side_stream):
+                rnn.train_engine.refresh(grads="param")
+                dec.train_engine.refresh(grads="param")
             wav = batch["wav"]
             wav = wav.to(dev, torch.float32, non_blocking=True)
             cap = batch["cap"].to(dev, torch.int64, non_blocking=True)
@@ -143,25 +209,38 @@ class TrainStep:
             t_out = int(lens.max())
             x = cnn_out["attn_emb"][:, :t_out].contiguous()
             len_dev = to_device_async(lens, dev, torch.int64)
-            rnn = m.encoder.rnn
-            mem = rnn.train_engine.forward(x, len_dev, p_drop=float(rnn.dropout) if rnn.num_layers > 1 else 0.0, grads="param")
+            main.wait_stream(self._side_stream)
+            mem = rnn.train_engine.forward(x, len_dev, p_drop=float(rnn.dropout) if rnn.num_layers > 1 else 0.0, grads="param",
+                                           refresh=False)
             L = cap.size(1) - 1
             if coins is None:
                 coins = [random.random() < self.ss_ratio for _ in range(L)] if self.ss_ratio != 1 else None
-            dec = m.decoder
             out = dec.train_engine.forward(mem, len_dev, cap[:, :-1].contiguous(), coins=coins,
                                            p_drop=float(dec.in_dropout.p), grads="param", start_idx=m.start_idx,
-                                           end_idx=m.end_idx, pad_idx=m.pad_idx)
+                                           end_idx=m.end_idx, pad_idx=m.pad_idx, refresh=False)
             from .captioning.losses.loss import ls_ce_fwd_bwd
             loss, dlogit = ls_ce_fwd_bwd(out["logit_padded"][:, :, :dec.vocab_size], cap[:, 1:], tgt_len_dev, self.smoothing)
             dmem = dec.train_engine.backward(dlogit, need_dattn=True)
+            # data parallel: the decoder's gradients are final here -- their all-reduce overlaps the GRU's backward pass
+            work = None
+            if self.world > 1 and self.dec_offset is not None:
+                work = allreduce_bucket_async(self.flat_grad[self.dec_offset:], self.group)
             rnn.train_engine.backward(dmem, need_dx=False)
-            grad_scale = allreduce_gradients(self.flat_grad, self.group) if self.world > 1 else 1.0
+            if work is not None:
+                allreduce_gradients(self.flat_grad[:self.dec_offset], self.group)
+                work.wait()
+                grad_scale = 1.0 / self.world
+            else:
+                grad_scale = allreduce_gradients(self.flat_grad, self.group) if self.world > 1 else 1.0
             _lib.check(l.ac_clip_adam(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
                                       _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), self.lr, self.betas[0], self.betas[1],
                                       self.eps, self.weight_decay, self.max_grad_norm, grad_scale, _lib.ptr(loss),
                                       _lib.ptr(self._step_dev), _lib.ptr(self.grad_norm), _lib.ptr(self._adam_ws),
                                       self._adam_ws.numel(), _lib.current_stream()), "ac_clip_adam")
+            if "_slot" in batch:                     # the staging slot may be overwritten once this step's kernels are done
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._stage[batch["_slot"]]["free"] = ev
         self.iteration += 1
         self.last_output = out
         return {"loss": loss, "tokens": int((cap_len - 1).sum()), "lr": self.lr, "ss_ratio": self.ss_ratio}

@@ -115,3 +115,49 @@ def test_flat_gradient_allreduce_two_ranks():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------ training: two-bucket exchange (decoder bucket overlaps the GRU backward)
+def _bucket_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from audiocaption_b200.train_step import allreduce_bucket_async, allreduce_gradients, bucket_boundary, flatten_trainable
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 7))
+            self.decoder = torch.nn.Sequential(torch.nn.Linear(7, 3), torch.nn.LayerNorm(3))
+    torch.manual_seed(0)
+    model = M()
+    params, flat_p, flat_g = flatten_trainable(model)
+    off = bucket_boundary(model, params)
+    # encoder tensors: 35, 7, 49, 7 floats, each rounded up to 32 -> 64 + 32 + 64 + 32
+    ok = off == 192 and params[4] is model.decoder[0].weight and flat_g.numel() > off
+    flat_g.fill_(float(rank + 1))
+    work = allreduce_bucket_async(flat_g[off:])            # TrainStep.step: right after the decoder's backward pass
+    scale = allreduce_gradients(flat_g[:off])              # ... and after the GRU's
+    work.wait()
+    ok = ok and abs(scale - 0.5) < 1e-12 and bool((flat_g == 3.0).all())
+    # a model whose flat order interleaves the two halves has no clean boundary: the step falls back to one all-reduce
+    shuffled = [params[4], params[0], params[5]]
+    ok = ok and bucket_boundary(model, shuffled) is None and allreduce_bucket_async(flat_g[:0]) is None
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_bucket_gradient_exchange_two_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
