@@ -218,6 +218,14 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
     # accumulation; csrc/conv_bf16.cu); the TF32 and the fp32-exact (3xTF32) modes are timed beside it
     model.encoder.cnn.conv_precision = "bf16"
     ms_step, launches = timed(step_resident, steps, warmup)
+    # host time to enqueue ONE step on an idle GPU (a loop of many steps is throttled by the launch queue, not the host)
+    host_ms = 0.0
+    for i in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_resident(i)
+        host_ms += (time.perf_counter() - t0) * 1e3 / 5
+    torch.cuda.synchronize()
     ms_e2e, _ = timed(step_e2e, steps, 3)
     keep.pop("staged", None)
     ms_e2e_sync, _ = timed(step_e2e_sync, steps, 3)
@@ -268,7 +276,7 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
                     "api": "TrainStep.prefetch(batch i+1) + TrainStep.step(staged batch i): pinned host waveforms + captions in "
                            "(upload of the next batch overlaps the step), loss.item() out every step",
                     "unpipelined_ms_per_step": ms_e2e_sync},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "tensor", "kernel": "conv3x3_bf16 (frozen Cnn14 forward, 11 launches)", "achieved": achieved,
                          "peak": bf16_sust, "unit": "TFLOP/s", "frac": achieved / bf16_sust if bf16_sust else None,
                          "traffic": None, "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,
@@ -433,8 +441,10 @@ def run_native(args):
         l0 = lib.ac_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(warmup + i)
+        timed.host_ms_per_step = (time.perf_counter() - t0) * 1e3 / steps     # host time to ENQUEUE a step (no sync inside fn)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
