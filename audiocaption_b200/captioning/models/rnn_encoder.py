@@ -127,6 +127,8 @@ class GruTrainEngine:
         self.enc = enc
         self._handle = None
         self._key = None
+        self.layout_pinned = None
+        self._handle_mode = None
         self._ws = Workspace()
         self._scratch = None
         self._grads = None
@@ -144,6 +146,9 @@ class GruTrainEngine:
             pass
 
     def handle(self, grads="param", need_dx=False):
+        # `layout_pinned` (set by TrainStep, which owns the flat parameter / gradient buffers): skip the pointer signature
+        if self._handle is not None and self.layout_pinned == (grads, bool(need_dx)) and self._handle_mode == (grads, bool(need_dx)):
+            return self._handle
         enc = self.enc
         params = enc._tensors()
         for p in params:
@@ -170,6 +175,7 @@ class GruTrainEngine:
                                                         int(need_dx), _lib.current_stream(), ctypes.byref(h)),
                        "ac_bigru_train_create")
             self._handle, self._key, self._grads = h, key, gts
+        self._handle_mode = (grads, bool(need_dx))     # the mode the CURRENT handle serves
         return self._handle
 
     def refresh(self, grads="param", need_dx=False):

@@ -135,6 +135,14 @@ class TrainStep:
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.n_trainable = sum(p.numel() for p in self.params)
         self.dec_offset = bucket_boundary(self.model, self.params)      # flat_grad[dec_offset:] = the decoder's gradients
+        # the flat buffers fix every parameter's and gradient's storage, and nothing writes the frozen CNN: the engines skip
+        # their per-call pointer / version signatures (~1 ms of host time per step); re-run _flatten() after moving the model
+        m = self.model
+        for eng, pin in ((m.encoder.rnn.train_engine, ("param", False)), (m.decoder.train_engine, "param")):
+            eng.release()
+            eng.layout_pinned = pin
+        m.encoder.cnn.release()
+        m.encoder.cnn.weights_pinned = True
 
     # ---- schedules (host) ---------------------------------------------------------------------------------------------
     def _update_ss_ratio(self):
