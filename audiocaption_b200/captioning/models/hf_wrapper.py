@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 import ctypes
+import os
 
 from ... import _lib
 from . import BaseDecoder
@@ -505,7 +506,12 @@ class Cnn8rnnSedModel(nn.Module):
         return {"segmentwise_output": seg, "framewise_output": frame}
 
     def forward(self, lms):
-        _, labels, T, runs, n_runs = self._run(lms, False)
+        return self._finish(self._run(lms, False))
+
+    def _finish(self, state):
+        """Read the run list back (synchronises the CURRENT stream, which must be the one `_run` was enqueued on) and apply
+        the pairwise segment rule on the host."""
+        _, labels, T, runs, n_runs = state
         n = int(n_runs.item())
         if n > runs.shape[0]:         # more runs than the compact list holds: decode from the label matrix instead
             return decode_segment_labels(labels.cpu().numpy(), T, self.interpolate_ratio, self.time_resolution)
@@ -609,7 +615,25 @@ class Cnn14RnnTempAttnGruModel(nn.Module):
                 max_length: int = 20, temp: float = 1.0):
         dev = self.device
         lms, _ = self.melspec_extractor(audio.to(dev, non_blocking=True))
-        sed_tag = torch.as_tensor(self.sed_model(lms))
+        # The tagger and the captioner's encoder both start from the log-mel and are independent until the decoder needs the
+        # tag: the tagger (network, double threshold, the read-back of its run list and the host-side segment rule) runs on a
+        # side stream while the main stream runs the Cnn14 + bi-GRU encoder.  AC_SED_OVERLAP=0: one after the other.
+        overlap = os.environ.get("AC_SED_OVERLAP", "1") != "0"
+        enc_out = None
+        if overlap:
+            with torch.cuda.device(dev):
+                if getattr(self, "_sed_stream", None) is None:
+                    self._sed_stream = torch.cuda.Stream(device=dev)
+                main = torch.cuda.current_stream()
+                self._sed_stream.wait_stream(main)                       # the log-mel is ready
+                with torch.cuda.stream(self._sed_stream):
+                    sed_state = self.sed_model._run(lms, False)         # asynchronous
+                enc_out = self.cap_model.encoder({"lms": lms, "wav_len": audio_length, "specaug": False})
+                with torch.cuda.stream(self._sed_stream):
+                    sed_tag = torch.as_tensor(self.sed_model._finish(sed_state))   # waits for the side stream only
+                main.wait_stream(self._sed_stream)
+        else:
+            sed_tag = torch.as_tensor(self.sed_model(lms))
         if temporal_tag is not None:          # hf_wrapper.py:1954-1958: the caller's tag can only lower the SED tag
             temporal_tag = torch.min(torch.stack([torch.as_tensor(temporal_tag).cpu(), sed_tag], dim=0), dim=0).values
         else:
@@ -619,4 +643,6 @@ class Cnn14RnnTempAttnGruModel(nn.Module):
                       "need_logit": False}
         if sample_method == "beam":
             input_dict["beam_size"] = beam_size
+        if enc_out is not None:
+            return self.cap_model.forward_decoder(input_dict, enc_out)["seq"].cpu()
         return self.cap_model(input_dict)["seq"].cpu()
