@@ -10,8 +10,10 @@ same per-iteration order as run.py:77-148.  Differences, all on the host side:
     loss_fn(output) -> backward -> clip_grad_norm_ -> optimizer.step());
   * `data:` entries are built with the same reflection factory; the datasets shipped here read wav / npy files or
     generate seeded synthetic clips (captioning/datasets), HDF5 needs h5py which this image lacks;
-  * validation monitors the teacher-forced label-smoothing loss on the validation split ("score" = -loss) instead of
-    CIDEr (pycocoevalcap + Java are not available); predictions still go through beam search (inference_args).
+  * validation monitors CIDEr of the beam-search predictions against the validation captions, as run.py:150-155 does,
+    with captioning.metrics.cider (a restatement of pycocoevalcap's scorer, which this image lacks) and a plain
+    lower-case / punctuation-stripping tokenizer in place of the Java PTB tokenizer; `trainer.monitor: loss` monitors the
+    teacher-forced label-smoothing loss of the validation split instead ("score" = -loss).
 `fire`, tensorboard and wandb are replaced by argparse and a plain log file."""
 import argparse
 import os
@@ -131,6 +133,36 @@ class Runner:
 
     @torch.no_grad()
     def _eval_epoch(self):
+        if getattr(self, "monitor", "cider") == "cider":
+            return self._eval_epoch_cider()
+        return self._eval_epoch_loss()
+
+    @torch.no_grad()
+    def _eval_epoch_cider(self):
+        """run.py:150-155: predictions of the validation split (inference_args: beam search) scored with CIDEr against
+        every caption the split holds for the same audio_id."""
+        from captioning.metrics.cider import Cider, simple_tokenize
+        self.model.eval()
+        key2refs, key2pred = {}, {}
+        for batch in self.val_dataloader:
+            refs = batch["caption"] if "caption" in batch else self.tokenizer.decode(np.asarray(batch["cap"]))
+            todo = []
+            for i, (aid, ref) in enumerate(zip(batch["audio_id"], refs)):
+                key2refs.setdefault(aid, []).append(simple_tokenize(ref))
+                if aid not in key2pred:
+                    key2pred[aid] = None
+                    todo.append(i)
+            if todo:                                                     # decode every audio clip once
+                wav = torch.as_tensor(batch["wav"])[todo]
+                wav_len = np.asarray(batch["wav_len"])[todo]
+                output = self._forward({"wav": wav, "wav_len": wav_len}, training=False)
+                for i, caption in zip(todo, self.tokenizer.decode(output["seq"].cpu().numpy())):
+                    key2pred[batch["audio_id"][i]] = [simple_tokenize(caption)]
+        score, _ = Cider().compute_score(key2refs, key2pred)
+        return {"score": score}
+
+    @torch.no_grad()
+    def _eval_epoch_loss(self):
         from captioning.losses.loss import ls_ce_fwd_bwd
         self.model.eval()
         total, count = 0.0, 0
@@ -196,6 +228,7 @@ class Runner:
         self.max_grad_norm = trainer.get("max_grad_norm", 1.0)
         self.smoothing = self.config["loss"]["args"].get("smoothing", 0.0)
         self.fused = trainer.get("fused", True)
+        self.monitor = trainer.get("monitor", "cider")                           # "cider" (run.py:150-155) or "loss"
         sched_args = dict(self.config["lr_scheduler"]["args"])
         warmup = sched_args.get("warmup_iters", self.iterations // 5)            # run.py:249-251
         opt_args = self.config["optimizer"]["args"]

@@ -6,6 +6,7 @@ import importlib.util
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch
 import yaml
@@ -124,3 +125,37 @@ def test_reference_factory_builds_b200_mirrors_from_the_reference_yaml(alias):
     theirs = {k: tuple(v.shape) for k, v in ref_model.state_dict().items()}
     assert ours == theirs
     model.load_state_dict(ref_model.state_dict(), strict=True)
+
+
+# ------------------------------------------------------------------ CIDEr (captioning/metrics/cider.py; run.py:150-155 monitors it)
+def test_cider_properties():
+    """pycocoevalcap is absent (parity unpinned): pin what the published definition implies."""
+    from audiocaption_b200.captioning.metrics.cider import Cider, simple_tokenize
+    assert simple_tokenize("A dog's bark -- loud, isn't it? (Yes) ...") == "a dog's bark loud isn't it yes"
+    gts = {"a": ["a dog barks loudly at night", "a dog is barking"], "b": ["rain falls on a tin roof", "heavy rain is falling"],
+           "c": ["a man speaks to a crowd", "someone is talking"], "d": ["birds sing in the morning"]}
+    exact = {k: [v[0]] for k, v in gts.items()}
+    score, per = Cider().compute_score(gts, exact)
+    assert Cider().method() == "CIDEr" and per.shape == (4,) and abs(score - per.mean()) < 1e-12
+    # a candidate equal to its only reference: cosine 1 for every n-gram order, no length penalty -> 10
+    assert abs(per[3] - 10.0) < 1e-9
+    # equal to one of two references: half of that reference's weight plus whatever the other shares (here nothing)
+    assert 4.9 < per[0] <= 10.0 and 4.9 < per[1] <= 10.0
+    # unrelated candidates score 0; permuting the keys permutes the scores
+    wrong = {"a": exact["b"], "b": exact["c"], "c": exact["d"], "d": exact["a"]}
+    s_wrong, per_wrong = Cider().compute_score(gts, wrong)
+    assert s_wrong < 0.5 * score and (per_wrong <= per + 1e-12).all()
+    rev = dict(reversed(list(gts.items())))
+    _, per_rev = Cider().compute_score(rev, {k: exact[k] for k in rev})
+    assert np.allclose(per_rev[::-1], per)
+    # the Gaussian length penalty: repeating the caption keeps every cosine but changes the (bigram) length
+    longer = {"d": [exact["d"][0] + " " + exact["d"][0]]}
+    one = {"d": gts["d"], "a": gts["a"]}
+    _, p_same = Cider().compute_score(one, {"d": exact["d"], "a": exact["a"]})
+    _, p_long = Cider().compute_score(one, {"d": longer["d"], "a": exact["a"]})
+    assert p_long[0] < p_same[0]
+    # words that occur in every reference set carry no weight (idf 0): a candidate made of them scores 0
+    common = {"x": ["the the the"], "y": ["the the the"]}
+    assert Cider().compute_score(common, {"x": ["the the the"], "y": ["the the the"]})[0] == 0.0
+    with pytest.raises(ValueError):
+        Cider().compute_score(gts, {"a": ["x"]})

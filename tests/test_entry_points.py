@@ -96,7 +96,8 @@ def _write_config(path, exp_dir, fused=True):
     cfg = {"experiment_path": str(exp_dir), "seed": 1, "model": model, "specaug": False, "data": {"train": data, "val": val},
            "optimizer": {"type": "torch.optim.Adam", "args": {"lr": 5e-4, "weight_decay": 1e-6}},
            "lr_scheduler": {"type": "captioning.utils.lr_scheduler.ExponentialDecayScheduler", "args": {"final_lrs": 5e-7}},
-           "trainer": {"max_grad_norm": 1.0, "epochs": 3, "save_interval": 1, "fused": fused},
+           "trainer": {"max_grad_norm": 1.0, "epochs": 3, "save_interval": 1, "fused": fused,
+                       "monitor": "cider" if fused else "loss"},      # CIDEr of the beam-search predictions (run.py:150-155) / -val loss
            "inference_args": {"sample_method": "beam", "beam_size": 3},
            "scheduled_sampling": {"use": True, "mode": "linear", "final_ratio": 0.7},
            "loss": {"type": "captioning.losses.loss.LabelSmoothingLoss", "args": {"smoothing": 0.1}},
