@@ -20,6 +20,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
@@ -29,7 +30,16 @@ namespace ac {
 constexpr int CB_BM = 128;
 constexpr int CB_KC = 64;                          // bf16 channels per k-chunk = one 128-byte swizzle row
 constexpr int CB_A_BYTES = CB_BM * 128;            // 16 KB
-constexpr int CB_MAX_BN = 128;
+// Widest n-tile.  A k-chunk of 64 channels brings 16 KB of activations + BN x 128 B of weights into the SM for
+// 128 x BN x 64 MACs: at BN = 128 that is 32 KB per ~262 tensor cycles = 125 B/clk, twice what one SM pulls from L2
+// (~60 B/clk; ncu: tensor pipe 54 % busy) -- at BN = 256 the same activations serve twice the columns: 48 KB per ~524
+// cycles = 92 B/clk.  AC_CONV_BF16_BN=128 restores the narrow tiles (read when the weights are packed).
+constexpr int CB_MAX_BN_LIMIT = 256;
+static int cb_max_bn() {
+    static const int v = [] { const char* e = getenv("AC_CONV_BF16_BN"); const int x = e ? atoi(e) : 256;
+                              return x == 128 || x == 256 ? x : 256; }();
+    return v;
+}
 constexpr int CB_THREADS = 192;
 constexpr int CB_MAX_STAGES = 6;
 constexpr int CB_SMEM_LIMIT = 227 * 1024;
@@ -199,7 +209,7 @@ __global__ void conv_bf16_pack_kernel(const float* __restrict__ w, const float* 
 }
 
 static void conv_bf16_tiling(int Cout, int Cin, int& BN, int& n_tiles, int& k_chunks) {
-    BN = std::min(CB_MAX_BN, Cout);
+    BN = std::min(cb_max_bn(), Cout);
     n_tiles = cdiv(Cout, BN);
     k_chunks = 9 * Cin / CB_KC;
 }
@@ -213,8 +223,8 @@ size_t conv_bf16_packed_elems(int Cout, int Cin) {
 int conv_bf16_pack(const float* w_perm_dev, const float* scale_dev, int Cout, int Cin, void* dst_dev, cudaStream_t st,
                    ConvBf16Weight* out) {
     AC_REQUIRE(w_perm_dev && dst_dev && out, "conv_bf16_pack: null argument");
-    AC_REQUIRE(Cin % CB_KC == 0 && Cout % 32 == 0 && (Cout <= CB_MAX_BN || Cout % CB_MAX_BN == 0),
-               "conv_bf16_pack: Cin (%d) %% 64, Cout (%d) %% 32 (and %% 128 beyond 128) must be 0", Cin, Cout);
+    AC_REQUIRE(Cin % CB_KC == 0 && Cout % 32 == 0 && (Cout <= cb_max_bn() || Cout % cb_max_bn() == 0),
+               "conv_bf16_pack: Cin (%d) %% 64, Cout (%d) %% 32 (and %% %d beyond %d) must be 0", Cin, Cout, cb_max_bn(), cb_max_bn());
     AC_REQUIRE(((uintptr_t)dst_dev & 127) == 0, "conv_bf16_pack: destination must be 128-byte aligned");
     int BN, n_tiles, k_chunks;
     conv_bf16_tiling(Cout, Cin, BN, n_tiles, k_chunks);
@@ -257,7 +267,8 @@ int conv3x3_bf16(const ConvBf16Args& a, cudaStream_t st) {
     const int sb = CB_A_BYTES + w.BN * 128;
     const int fixed = 1024 + 256;
     p.stages = std::min(CB_MAX_STAGES, (CB_SMEM_LIMIT - fixed) / sb);
-    p.tmem_cols = 2 * w.BN <= 32 ? 32 : (2 * w.BN <= 64 ? 64 : (2 * w.BN <= 128 ? 128 : 256));
+    p.tmem_cols = 2 * w.BN <= 32 ? 32 : (2 * w.BN <= 64 ? 64 : (2 * w.BN <= 128 ? 128 : (2 * w.BN <= 256 ? 256 : 512)));
+    AC_REQUIRE(w.BN <= CB_MAX_BN_LIMIT && p.stages >= 2, "conv3x3_bf16: n-tile %d does not fit (stages %d)", w.BN, p.stages);
     const size_t smem = (size_t)p.stages * sb + fixed;
     const int grid = std::min(p.m_tiles * p.n_tiles, kNumSMs);
     AC_TIMED("conv3x3_bf16", st);
