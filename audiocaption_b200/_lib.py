@@ -85,6 +85,11 @@ _SIGS = {
     "ac_resample_out_len": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "ac_resample": (C.c_int, [c_f32p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "ac_cnn14_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "ac_cnn14_set_sm_limit": (C.c_int, [C.c_void_p, C.c_int]),
+    "ac_sm_partition_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "ac_sm_partition_stream": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "ac_sm_partition_sms": (C.c_int, [C.c_void_p, C.c_int]),
+    "ac_sm_partition_destroy": (None, [C.c_void_p]),
     "ac_sed_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "ac_conv3x3_p": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_void_p]),

@@ -13,7 +13,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libaudiocaption_b200.so")
 SOURCES = ["capi.cu", "logmel.cu", "gemm.cu", "gemm_tc.cu", "dwconv_tma.cu", "effb2.cu", "cnn14.cu", "bigru.cu",
-           "trm_decode.cu", "bah_decode.cu", "train_ops.cu", "trm_train.cu", "bigru_train.cu", "resample.cu", "conv_bf16.cu"]
+           "trm_decode.cu", "bah_decode.cu", "train_ops.cu", "trm_train.cu", "bigru_train.cu", "resample.cu", "conv_bf16.cu", "sm_partition.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -382,7 +382,8 @@ class Cnn14Encoder(nn.Module):
 
     def _net(self):
         # `weights_pinned` (set by TrainStep for the frozen CNN): nothing writes the weights, skip the per-call signature
-        if self._handle is not None and getattr(self, "weights_pinned", False) and self._pinned_precision == self.conv_precision:
+        if self._handle is not None and getattr(self, "weights_pinned", False) and \
+                self._pinned_precision == (self.conv_precision, getattr(self, "sm_limit", 0)):
             return self._handle
         tensors = self._body_tensors()
         sig = params_signature(tensors)
@@ -400,7 +401,8 @@ class Cnn14Encoder(nn.Module):
         if self.conv_precision not in modes:
             raise ValueError(f"conv_precision {self.conv_precision!r}: expected 'fp32', 'tf32' or 'bf16'")
         _lib.check(_lib.lib().ac_cnn14_set_precision(self._handle, modes[self.conv_precision]), "ac_cnn14_set_precision")
-        self._pinned_precision = self.conv_precision
+        _lib.check(_lib.lib().ac_cnn14_set_sm_limit(self._handle, int(getattr(self, "sm_limit", 0))), "ac_cnn14_set_sm_limit")
+        self._pinned_precision = (self.conv_precision, getattr(self, "sm_limit", 0))
         return self._handle
 
     def release(self):

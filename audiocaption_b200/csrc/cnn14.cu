@@ -362,6 +362,7 @@ struct ac_cnn14 {
     float *fc_w, *fc_b;
     ac::TcWeight fc_tw;
     int conv_passes = 3;          // 3 = 3xTF32 (fp32-level), 1 = plain TF32, 16 = bf16 activations + weights (ac_cnn14_set_precision)
+    int sm_limit = 0;             // persistent CTAs of the bf16 convolutions (0 = one per SM): ac_cnn14_set_sm_limit
 };
 
 namespace ac {
@@ -505,6 +506,17 @@ int ac_cnn14_set_precision(ac_cnn14_t* net, int tf32_passes) {
     return AC_OK;
 }
 
+// Caps the persistent grid of the bf16 convolutions at n CTAs (0 = one per SM).  The training step runs the frozen
+// encoder of batch i+1 on a second stream next to the (latency-bound, few-CTA) trainable part of batch i
+// (audiocaption_b200/train_step.py `TrainStep.prefetch`): leaving some SMs to that chain keeps it moving while the
+// convolutions hold the rest.
+int ac_cnn14_set_sm_limit(ac_cnn14_t* net, int n) {
+    using namespace ac;
+    AC_REQUIRE(net && n >= 0, "ac_cnn14_set_sm_limit: bad argument");
+    net->sm_limit = n;
+    return AC_OK;
+}
+
 int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms, int B, int n_mels, int n_frames, const int64_t* lens,
                  float* attn_emb, float* fc_emb, void* workspace, size_t ws_bytes, void* stream) {
     return ac_cnn14_fwd_train(net, lms, B, n_mels, n_frames, lens, 0.0f, 0.0f, 0, attn_emb, fc_emb, workspace, ws_bytes, stream);
@@ -555,7 +567,7 @@ int ac_cnn14_fwd_train(const ac_cnn14_t* net, const float* lms, int B, int n_mel
                 if (i == 0 && j == 0) continue;
                 const Cnn14Conv& c = net->conv[l++];
                 ConvBf16Args a; a.in = bcur; a.out = bnxt; a.B = B; a.H = d[i].H; a.W = d[i].W; a.Cin = c.cin; a.Cout = c.cout;
-                a.bias = c.bias; a.w = &c.bw; a.act = ACT_RELU;
+                a.bias = c.bias; a.w = &c.bw; a.act = ACT_RELU; a.max_ctas = net->sm_limit;
                 rc = conv3x3_bf16(a, st); if (rc) return rc;
                 std::swap(bcur, bnxt);
             }

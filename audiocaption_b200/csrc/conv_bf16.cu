@@ -270,7 +270,7 @@ int conv3x3_bf16(const ConvBf16Args& a, cudaStream_t st) {
     p.tmem_cols = 2 * w.BN <= 32 ? 32 : (2 * w.BN <= 64 ? 64 : (2 * w.BN <= 128 ? 128 : (2 * w.BN <= 256 ? 256 : 512)));
     AC_REQUIRE(w.BN <= CB_MAX_BN_LIMIT && p.stages >= 2, "conv3x3_bf16: n-tile %d does not fit (stages %d)", w.BN, p.stages);
     const size_t smem = (size_t)p.stages * sb + fixed;
-    const int grid = std::min(p.m_tiles * p.n_tiles, kNumSMs);
+    const int grid = std::min(p.m_tiles * p.n_tiles, a.max_ctas > 0 ? std::min(a.max_ctas, kNumSMs) : kNumSMs);
     AC_TIMED("conv3x3_bf16", st);
     static cudaError_t attr_rc = cudaFuncSetAttribute(conv3x3_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM_LIMIT);
     AC_CUDA(attr_rc);

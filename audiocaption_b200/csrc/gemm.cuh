@@ -91,6 +91,7 @@ struct ConvBf16Args {
     const void* in; void* out; const float* bias; const ConvBf16Weight* w = nullptr;
     int B, H, W, Cin, Cout;
     int act = ACT_NONE;
+    int max_ctas = 0;            // persistent CTAs of the launch (0 = one per SM): ac_cnn14_set_sm_limit
 };
 size_t conv_bf16_packed_elems(int Cout, int Cin);
 int conv_bf16_pack(const float* w_perm_dev, const float* scale_dev, int Cout, int Cin, void* dst_dev, cudaStream_t st,

@@ -17,6 +17,10 @@ Adam step (:127), skipped when the loss is NaN (:123).  Here:
 The frozen Cnn14 runs forward only (BatchNorm in eval mode, dropout active: `freeze_cnn`, `freeze_cnn_bn`)."""
 import random
 
+import contextlib
+import ctypes
+import os
+
 import torch
 
 from . import _lib
@@ -114,6 +118,9 @@ class TrainStep:
         self.use_ss, self.ss_mode, self.ss_final_ratio = use_ss, ss_mode, float(ss_final_ratio)
         self.ss_ratio = 1.0
         self.specaug = bool(specaug)                 # SpecAugment on the log-mel (the YAML's top-level `specaug:`)
+        # persistent CTAs the look-ahead encoder's convolutions may hold (prefetch(encode=True)); the rest of the 148 SMs
+        # stay free for the trainable chain of the step in flight
+        self.cnn_sms = int(os.environ.get("AC_TRAIN_CNN_SMS", "84"))
         self.iteration = 0
         self.group = process_group
         self.world = 1
@@ -156,31 +163,82 @@ class TrainStep:
         else:
             raise Exception(f"mode {self.ss_mode} not supported")
 
-    # ---- input staging ------------------------------------------------------------------------------------------------
-    def prefetch(self, batch):
-        """Start the host -> device upload of a batch's waveforms and captions on a copy stream (asynchronous when the host
-        tensors are pinned) and return the staged batch for `step`: the upload of batch i+1 then overlaps the kernels of
-        step i (what a DataLoader prefetcher does for the reference's loop).  Two staging slots; a slot is overwritten only
-        after the step that read it has finished with it."""
+    # ---- input staging / look-ahead ---------------------------------------------------------------------------------------
+    def prefetch(self, batch, encode=True):
+        """Look-ahead for the NEXT step; returns the staged batch to hand to `step`.
+
+        1. Upload: the host -> device copy of the waveforms and captions runs on a copy stream (asynchronous when the host
+           tensors are pinned), as a DataLoader prefetcher does for the reference's loop.  Two staging slots; a slot is
+           overwritten only after the step that read it has finished with it.  Device-resident batches skip this.
+        2. `encode`: the FROZEN CNN's forward pass of that batch (log-mel, Cnn14 with its train-mode dropouts) runs on a
+           second stream.  It does not depend on the optimizer step in flight, and the trainable part of a step (bi-GRU,
+           decoder, backward passes: ~250 latency-bound launches of a few CTAs each) leaves most of the chip idle, so the
+           tensor-core-bound encoder of batch i+1 fills it while step i runs.  The convolutions' persistent grid is capped
+           at `cnn_sms` CTAs (AC_TRAIN_CNN_SMS) so that the trainable chain always finds free SMs, and `step` runs that
+           chain on a high-priority stream."""
         dev = self.device
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(device=dev)
-            self._stage = [{"free": None, "wav": None, "cap": None}, {"free": None, "wav": None, "cap": None}]
-            self._stage_i = 0
-        k = self._stage_i
-        self._stage_i ^= 1
-        s = self._stage[k]
-        with torch.cuda.device(dev), torch.cuda.stream(self._copy_stream), torch.no_grad():
-            if s["free"] is not None:
-                self._copy_stream.wait_event(s["free"])
-            for name, dt in (("wav", torch.float32), ("cap", torch.int64)):
-                src = batch[name]
-                if s[name] is None or s[name].shape != src.shape:
-                    s[name] = torch.empty(src.shape, dtype=dt, device=dev)
-                s[name].copy_(src, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(self._copy_stream)
-        return dict(batch, wav=s["wav"], cap=s["cap"], _ready=ready, _slot=k)
+        m = self.model
+        with torch.cuda.device(dev), torch.no_grad():
+            user = torch.cuda.current_stream()
+            staged = dict(batch)
+            ready = None
+            if not batch["wav"].is_cuda:
+                if getattr(self, "_copy_stream", None) is None:
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                    self._stage = [{"free": None, "wav": None, "cap": None}, {"free": None, "wav": None, "cap": None}]
+                    self._stage_i = 0
+                k = self._stage_i
+                self._stage_i ^= 1
+                s = self._stage[k]
+                with torch.cuda.stream(self._copy_stream):
+                    if s["free"] is not None:
+                        self._copy_stream.wait_event(s["free"])
+                    for name, dt in (("wav", torch.float32), ("cap", torch.int64)):
+                        src = batch[name]
+                        if s[name] is None or s[name].shape != src.shape:
+                            s[name] = torch.empty(src.shape, dtype=dt, device=dev)
+                        s[name].copy_(src, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self._copy_stream)
+                staged.update(wav=s["wav"], cap=s["cap"], _ready=ready, _slot=k)
+            if encode:
+                if getattr(self, "_cnn_stream", None) is None:
+                    self._make_look_ahead_streams()
+                cnn = m.encoder.cnn
+                cnn.sm_limit = self.cnn_sms
+                if ready is not None:
+                    self._cnn_stream.wait_event(ready)
+                else:
+                    self._cnn_stream.wait_stream(user)               # a device-resident batch: whatever produced it
+                with torch.cuda.stream(self._cnn_stream):
+                    wav = staged["wav"].to(dev, torch.float32)
+                    staged["_cnn_out"] = cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": self.specaug})
+                    done = torch.cuda.Event()
+                    done.record(self._cnn_stream)
+                staged["_cnn_ready"] = done
+        return staged
+
+    def _make_look_ahead_streams(self):
+        """Two streams on DISJOINT SM sets (csrc/sm_partition.cu: CUDA green contexts): `cnn_sms` SMs for the look-ahead
+        encoder, the rest for the trainable chain.  On ordinary streams the convolutions' pending CTAs take every SM that
+        frees up and the small kernels starve (measured: no gain).  AC_TRAIN_PARTITION=0, or a driver without green
+        contexts: ordinary streams (trainable chain at high priority)."""
+        dev = self.device
+        self.partition, self.partition_error = None, None
+        if os.environ.get("AC_TRAIN_PARTITION", "1") != "0":
+            l = _lib.lib()
+            h = ctypes.c_void_p()
+            if l.ac_sm_partition_create(int(self.cnn_sms), ctypes.byref(h)) == 0:
+                self.partition = h
+                self._cnn_stream = torch.cuda.ExternalStream(l.ac_sm_partition_stream(h, 0), device=dev)
+                self._hi_stream = torch.cuda.ExternalStream(l.ac_sm_partition_stream(h, 1), device=dev)
+                self.cnn_sms = int(l.ac_sm_partition_sms(h, 0))
+                self.train_sms = int(l.ac_sm_partition_sms(h, 1))
+                return
+            self.partition_error = l.ac_last_error().decode()
+        self._cnn_stream = torch.cuda.Stream(device=dev)
+        self._hi_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.train_sms = None
 
     # ---- one step -------------------------------------------------------------------------------------------------------
     def step(self, batch, coins=None):
@@ -193,8 +251,15 @@ class TrainStep:
         self._update_ss_ratio()
         # the scheduler was stepped once by its constructor; iteration k (0-based) steps it for the (k+2)-th time (run.py:105)
         self.lr = exponential_decay_lr(self.iteration + 2, self.base_lr, self.final_lr, self.total_iters, self.warmup_iters)
-        with torch.cuda.device(dev), torch.no_grad():
-            main = torch.cuda.current_stream()
+        look_ahead = "_cnn_out" in batch
+        with contextlib.ExitStack() as stack, torch.cuda.device(dev), torch.no_grad():
+            user = torch.cuda.current_stream()
+            # with the encoder of the next batch running beside this step (prefetch(encode=True)), the trainable chain runs
+            # on a high-priority stream: its few CTAs win the SMs the look-ahead's kernels free up
+            main = self._hi_stream if look_ahead else user
+            if main is not user:
+                main.wait_stream(user)
+            stack.enter_context(torch.cuda.stream(main))
             if "_ready" in batch:
                 main.wait_event(batch["_ready"])
             # the weight re-pack of both trainable engines only depends on the previous optimizer step: it runs on a side
@@ -212,7 +277,16 @@ class TrainStep:
             cap_len = torch.as_tensor(batch["cap_len"]).to(torch.int64)
             tgt_len_dev = to_device_async(cap_len - 1, dev, torch.int64)
             # frozen CNN (dropout on, BatchNorm eval) -> frames; bi-GRU; decoder
-            cnn_out = m.encoder.cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": self.specaug})
+            if look_ahead:
+                main.wait_event(batch["_cnn_ready"])
+                cnn_out = batch["_cnn_out"]
+                for t in (cnn_out["attn_emb"], cnn_out["fc_emb"]):          # allocated on the look-ahead stream, read here
+                    t.record_stream(main)
+            else:
+                if getattr(self, "_cnn_stream", None) is not None:         # never two encoder passes at once (one workspace)
+                    main.wait_stream(self._cnn_stream)
+                m.encoder.cnn.sm_limit = 0
+                cnn_out = m.encoder.cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": self.specaug})
             lens = cnn_out["attn_emb_len"]
             t_out = int(lens.max())
             x = cnn_out["attn_emb"][:, :t_out].contiguous()
@@ -249,6 +323,9 @@ class TrainStep:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 self._stage[batch["_slot"]]["free"] = ev
+            if main is not user:
+                loss.record_stream(user)
+                user.wait_stream(main)
         self.iteration += 1
         self.last_output = out
         return {"loss": loss, "tokens": int((cap_len - 1).sum()), "lr": self.lr, "ss_ratio": self.ss_ratio}

@@ -200,6 +200,13 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
     def step_resident(i):
         keep["loss"] = step.step(devb[i % n_rot])["loss"]
 
+    def step_pipelined(i):
+        # device-resident inputs, look-ahead on: the frozen encoder of batch i+1 runs on a second stream beside the trainable
+        # part of step i (TrainStep.prefetch); every timed step still contains one full encoder pass and one optimizer step
+        cur = keep.pop("staged_dev", None) or step.prefetch(devb[i % n_rot])
+        keep["staged_dev"] = step.prefetch(devb[(i + 1) % n_rot])
+        keep["loss"] = step.step(cur)["loss"]
+
     def step_e2e(i):
         # every step: one pinned H2D upload (of the NEXT batch, on the copy stream, overlapping this step's kernels -- the
         # prefetch a DataLoader does for the reference's loop) and one D2H read of this step's loss
@@ -217,7 +224,10 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
     # BASELINE configs[2..3] are stated in bf16: the headline runs the frozen CNN in bf16 (activations and weights, fp32
     # accumulation; csrc/conv_bf16.cu); the TF32 and the fp32-exact (3xTF32) modes are timed beside it
     model.encoder.cnn.conv_precision = "bf16"
-    ms_step, launches = timed(step_resident, steps, warmup)
+    ms_inline, launches = timed(step_resident, steps, warmup)
+    ms_step, _ = timed(step_pipelined, steps, warmup)
+    keep.pop("staged_dev", None)
+    torch.cuda.synchronize()
     # host time to enqueue ONE step on an idle GPU (a loop of many steps is throttled by the launch queue, not the host)
     host_ms = 0.0
     for i in range(5):
@@ -270,6 +280,15 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
                        "collective": "one all_reduce(sum) of the flat fp32 gradient per step" if world > 1 else "none (1 GPU)",
                        "l2": f"rotating {n_rot} batches (4 x 41 MB of waveforms > 126 MB L2)"},
             "ms_per_step_ss_ratio_0.85": ms_ss085,
+            "pipeline": {"what": "value / ms_per_step: TrainStep.prefetch(next batch) + TrainStep.step(staged batch) -- the frozen "
+                                 "Cnn14 encoder of batch i+1 runs on a second stream (convolutions capped at cnn_sms persistent CTAs) "
+                                 "beside the bi-GRU / decoder forward + backward + optimizer of batch i; unpipelined = "
+                                 "TrainStep.step(batch) alone, encoder and trainable part back to back on one stream",
+                         "cnn_sms": step.cnn_sms, "trainable_sms": getattr(step, "train_sms", None),
+                         "sm_partition": "green contexts" if getattr(step, "partition", None) is not None else
+                                         f"none ({getattr(step, 'partition_error', None)})",
+                         "unpipelined_ms_per_step": ms_inline,
+                         "unpipelined_value": world * (sum(tokens_per_step) / len(tokens_per_step)) / (ms_inline / 1000.0)},
             "e2e": {"value": world * tok / (ms_e2e / 1000.0), "unit": "tokens/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": TRAIN_BATCH * TRAIN_SAMPLES * 4 + int(host[0]["cap"].numel()) * 8,
                     "d2h_bytes_per_step": 4,
@@ -279,7 +298,7 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "tensor", "kernel": "conv3x3_bf16 (frozen Cnn14 forward, 11 launches)", "achieved": achieved,
                          "peak": bf16_sust, "unit": "TFLOP/s", "frac": achieved / bf16_sust if bf16_sust else None,
-                         "traffic": None, "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,
+                         "traffic": None, "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_inline,
                          "note": "achieved = algorithmic flops (40.07 GFLOP/clip) of the bf16 convolutions over their CUDA-event "
                                  "time; peak = measured dense bf16",
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "kernel_shares": shares,

@@ -163,6 +163,9 @@ int ac_cnn14_fwd(const ac_cnn14_t* net, const float* lms_dev, int batch, int n_m
  * the mode of every fp32 parity claim), 1 uses plain TF32 operands (10-bit mantissa, fp32 accumulation) -- the tensor-core
  * mode for the configurations BASELINE.json states in bf16 (training, temporal captioner). */
 int ac_cnn14_set_precision(ac_cnn14_t* net, int tf32_passes);
+/* Caps the persistent grid of the bf16-mode convolutions at n CTAs (0 = one per SM), so that a frozen encoder running on a
+ * second stream (the training step's look-ahead, audiocaption_b200/train_step.py) leaves SMs to the trainable chain. */
+int ac_cnn14_set_sm_limit(ac_cnn14_t* net, int n);
 int ac_sed_set_precision(ac_sed_t* net, int tf32_passes);
 /* ac_conv3x3 with the precision switch (diagnostic). */
 int ac_conv3x3_p(const float* in_dev, const float* w_dev, const float* scale_dev, const float* bias_dev, float* out_dev,
@@ -395,6 +398,16 @@ int ac_clip_adam(float* param_dev, const float* grad_dev, float* exp_avg_dev, fl
                  float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                  const float* loss_dev, int* step_dev, float* norm_out_dev, void* workspace_dev, size_t workspace_bytes,
                  void* stream);
+
+/* ---- SM partition for the training step's look-ahead (csrc/sm_partition.cu) ------------------------------------------
+ * The reference's loop (python_scripts/train_eval/run.py:77-148) runs the frozen CNN and the trainable part of a step back
+ * to back; here the frozen encoder of batch i+1 runs beside the trainable part of batch i on a DISJOINT set of SMs (CUDA
+ * green contexts).  Set 0 gets about `sms_first` SMs (8-SM granularity), set 1 the rest; one stream per set. */
+typedef struct ac_sm_partition ac_sm_partition_t;
+int ac_sm_partition_create(int sms_first, ac_sm_partition_t** out);
+void* ac_sm_partition_stream(const ac_sm_partition_t* p, int which);   /* cudaStream_t of set 0 / 1 */
+int ac_sm_partition_sms(const ac_sm_partition_t* p, int which);        /* SMs in set 0 / 1 */
+void ac_sm_partition_destroy(ac_sm_partition_t* p);
 
 #ifdef __cplusplus
 }

@@ -469,6 +469,49 @@ def test_training_reduces_the_loss_on_a_fixed_batch():
     assert step._step_dev.item() == 10
 
 
+@pytest.mark.parametrize("host_input", [True, False])
+def test_look_ahead_steps_equal_inline_steps(host_input):
+    """TrainStep.prefetch(next batch) runs the upload and the frozen encoder of batch i+1 on other streams while step i runs
+    (capped convolution grid, trainable chain on a high-priority stream).  With dropout off the schedule cannot change any
+    number beyond summation order: four look-ahead steps over three different batches give the losses, gradient norms and
+    parameters of four inline steps -- a stale / overwritten staging buffer or a missed stream dependency would not."""
+    from audiocaption_b200.train_step import TrainStep
+    vocab = 520
+    batches = []
+    for i, (B, n, L) in enumerate([(4, 64000, 10), (3, 96000, 7), (4, 48000, 12)]):
+        wav, lens = cm.synth_wav(B, n, seed=40 + i, ragged=True, varied=True, sample_rate=32000)
+        cap, cap_len = ts.synth_captions(B, L, vocab, seed=9 + i)
+        wav = wav.pin_memory() if host_input else wav.to(DEV)
+        batches.append({"wav": wav, "wav_len": lens, "cap": cap if host_input else cap.to(DEV), "cap_len": cap_len.numpy()})
+    order = [0, 1, 2, 0]
+    coins = [[True] * 32, [True, False] * 16, [False] * 32, [True] * 32]
+    runs = {}
+    for mode in ("inline", "look_ahead"):
+        m = _no_dropout(_train_model(vocab))
+        step = TrainStep(m, total_iters=1000, lr=1e-3, warmup_iters=10)
+        step.cnn_sms = 100
+        losses, norms = [], []
+        staged = step.prefetch(batches[order[0]]) if mode == "look_ahead" else None
+        for k, bi in enumerate(order):
+            L = batches[bi]["cap"].shape[1] - 1
+            if mode == "look_ahead":
+                nxt = step.prefetch(batches[order[k + 1]]) if k + 1 < len(order) else None
+                res = step.step(staged, coins=coins[k][:L])
+                staged = nxt
+            else:
+                res = step.step(batches[bi], coins=coins[k][:L])
+            losses.append(res["loss"].item())
+            norms.append(step.grad_norm.item())
+        torch.cuda.synchronize()
+        runs[mode] = (losses, norms, step.flat_param.detach().cpu().clone())
+    # (not bit-identical: the embedding gradient is accumulated with fp32 atomics, whose order depends on what else runs)
+    assert np.allclose(runs["inline"][0], runs["look_ahead"][0], rtol=2e-6, atol=0), (runs["inline"][0], runs["look_ahead"][0])
+    assert np.allclose(runs["inline"][1], runs["look_ahead"][1], rtol=2e-5, atol=0)
+    d = (runs["inline"][2] - runs["look_ahead"][2]).abs().max().item()
+    assert d <= 1e-5 * runs["inline"][2].abs().max().item(), d
+    assert all(np.isfinite(runs["inline"][0]))
+
+
 def test_tf32_convolution_mode():
     """The "tf32" precision mode of the Cnn14 convolutions (plain TF32 operands, fp32 accumulation; BASELINE configs[2..4]
     are stated in bf16): one convolution vs float64 (<= 2e-3 of the output scale, against 2e-5 in the default 3xTF32
