@@ -115,6 +115,45 @@ def test_tensor_core_gemm_matches_float64(case):
     assert _gemm(path=0, **case) < 5e-6
 
 
+def test_two_issuer_mma_ordering_stress():
+    """gemm_tc's K loop is fed by TWO issuing warps that alternate k-chunks; the accumulator-full commit of one is taken to
+    cover the other's earlier MMAs (the pipe retires in issue order -- DESIGN.md).  PTX only scopes a commit to the
+    executing thread's own operations, so the assumption is pinned empirically: 40 random shapes with long K loops (every
+    chunk parity, ragged M / N / K, gated and plain), each run 8 times on the SAME inputs concurrently with a second stream
+    that keeps the SMs busy -- every repeat must be bit-identical to the first (an early accumulator read would see a
+    partial sum that depends on timing) and within the 3xTF32 bound of the float64 product."""
+    from audiocaption_b200 import _lib
+    l = _lib.lib()
+    rng = np.random.default_rng(123)
+    noise_stream = torch.cuda.Stream()
+    noise = torch.randn(4096, 4096, device=DEV)
+    for it in range(40):
+        M = int(rng.integers(1, 9000))
+        N = int(rng.choice([16, 24, 48, 88, 104, 120, 144, 208, 256, 352]))
+        K = int(rng.integers(33, 300)) * 8                       # 264 .. 2392: 9 .. 75 k-chunks, odd and even counts
+        gate = int(rng.choice([0, 0, 64, 252]))
+        g = torch.Generator().manual_seed(1000 + it)
+        A = torch.randn(M, K, generator=g).to(DEV)
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        G = torch.rand((M + gate - 1) // gate, K, generator=g).to(DEV) if gate else None
+        outs = []
+        with torch.cuda.stream(noise_stream):
+            for _ in range(12):
+                noise = torch.tanh(noise @ noise * 1e-2)            # library kernels competing for the SMs / L2
+        for rep in range(8):
+            C = torch.full((M, N), float("nan"), device=DEV)
+            _lib.check(l.ac_gemm(_lib.ptr(A), _lib.ptr(W), _lib.ptr(C), M, N, K, _lib.ptr(G), gate, None, None, None, 0, 1,
+                                 _lib.current_stream()), "ac_gemm")
+            outs.append(C)
+        torch.cuda.synchronize()
+        Ad = A.double() * (G.double().repeat_interleave(gate, dim=0)[:M] if gate else 1.0)
+        ref = Ad @ W.double().t()
+        assert not torch.isnan(outs[0]).any()
+        assert ((outs[0].double() - ref).abs().max() / ref.abs().max()).item() < 2e-5, (M, N, K, gate)
+        for rep in range(1, 8):
+            assert torch.equal(outs[rep], outs[0]), (it, rep, M, N, K, gate)
+
+
 # ------------------------------------------------------------------ depthwise kernel (TMA tiles) vs torch conv2d
 DW_CASES = [  # (B, Hi, Wi, C, k, s, pad_lo, pad_hi)
     (2, 32, 501, 32, 3, 1, 1, 1),      # block 0
