@@ -205,18 +205,27 @@ class TrainStep:
                 if getattr(self, "_cnn_stream", None) is None:
                     self._make_look_ahead_streams()
                 cnn = m.encoder.cnn
-                cnn.sm_limit = self.cnn_sms
                 if ready is not None:
                     self._cnn_stream.wait_event(ready)
                 else:
                     self._cnn_stream.wait_stream(user)               # a device-resident batch: whatever produced it
-                with torch.cuda.stream(self._cnn_stream):
-                    wav = staged["wav"].to(dev, torch.float32)
-                    staged["_cnn_out"] = cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": self.specaug})
-                    done = torch.cuda.Event()
-                    done.record(self._cnn_stream)
+                cnn.sm_limit = self.cnn_sms                          # (only this pass: other callers get the whole chip)
+                try:
+                    with torch.cuda.stream(self._cnn_stream):
+                        wav = staged["wav"].to(dev, torch.float32)
+                        staged["_cnn_out"] = cnn({"wav": wav, "wav_len": batch["wav_len"], "specaug": self.specaug})
+                        done = torch.cuda.Event()
+                        done.record(self._cnn_stream)
+                finally:
+                    cnn.sm_limit = 0
                 staged["_cnn_ready"] = done
         return staged
+
+    def wait_look_ahead(self):
+        """Make the current stream wait for an encoder pass `prefetch` may have in flight (the CNN has ONE workspace: call
+        this before running the encoder yourself, e.g. for validation between epochs)."""
+        if getattr(self, "_cnn_stream", None) is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._cnn_stream)
 
     def _make_look_ahead_streams(self):
         """Two streams on DISJOINT SM sets (csrc/sm_partition.cu: CUDA green contexts): `cnn_sms` SMs for the look-ahead

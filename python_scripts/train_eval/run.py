@@ -102,12 +102,22 @@ class Runner:
         total_loss, nsamples = 0.0, 0
         self.model.train()
         losses = []
-        for _ in range(self.epoch_length):
+        def next_batch():
             try:
-                batch = next(self.train_iter)
+                return next(self.train_iter)
             except StopIteration:
                 self.train_iter = iter(self.train_dataloader)
-                batch = next(self.train_iter)
+                return next(self.train_iter)
+
+        for _ in range(self.epoch_length):
+            if self.fused and self.look_ahead:
+                # one batch of look-ahead: while this iteration's trainable part runs, the NEXT batch is uploaded and goes
+                # through the frozen CNN on its own SM set (TrainStep.prefetch)
+                if getattr(self, "_staged", None) is None:
+                    self._staged = self.train_step.prefetch(next_batch())
+                batch, self._staged = self._staged, self.train_step.prefetch(next_batch())
+            else:
+                batch = next_batch()
             nsample = int(np.sum(batch["cap_len"] - 1))
             if self.fused:
                 res = self.train_step.step(batch)                 # schedules, forward, loss, backward, clip, Adam
@@ -133,6 +143,8 @@ class Runner:
 
     @torch.no_grad()
     def _eval_epoch(self):
+        if getattr(self, "train_step", None) is not None:
+            self.train_step.wait_look_ahead()                     # the CNN has one workspace: no encoder pass in flight
         if getattr(self, "monitor", "cider") == "cider":
             return self._eval_epoch_cider()
         return self._eval_epoch_loss()
@@ -229,6 +241,7 @@ class Runner:
         self.smoothing = self.config["loss"]["args"].get("smoothing", 0.0)
         self.fused = trainer.get("fused", True)
         self.monitor = trainer.get("monitor", "cider")                           # "cider" (run.py:150-155) or "loss"
+        self.look_ahead = trainer.get("look_ahead", True)                        # TrainStep.prefetch one batch ahead
         sched_args = dict(self.config["lr_scheduler"]["args"])
         warmup = sched_args.get("warmup_iters", self.iterations // 5)            # run.py:249-251
         opt_args = self.config["optimizer"]["args"]

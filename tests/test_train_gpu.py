@@ -507,8 +507,11 @@ def test_look_ahead_steps_equal_inline_steps(host_input):
     # (not bit-identical: the embedding gradient is accumulated with fp32 atomics, whose order depends on what else runs)
     assert np.allclose(runs["inline"][0], runs["look_ahead"][0], rtol=2e-6, atol=0), (runs["inline"][0], runs["look_ahead"][0])
     assert np.allclose(runs["inline"][1], runs["look_ahead"][1], rtol=2e-5, atol=0)
-    d = (runs["inline"][2] - runs["look_ahead"][2]).abs().max().item()
-    assert d <= 1e-5 * runs["inline"][2].abs().max().item(), d
+    # parameters: Adam divides by sqrt(v) + eps, so an element whose gradient is itself at the atomics' noise level (sums that
+    # cancel to ~1e-9) may move by a fraction of the learning rate either way; everything else agrees to fp32 rounding
+    diff = (runs["inline"][2] - runs["look_ahead"][2]).abs()
+    assert diff.max().item() < 2e-3, diff.max().item()
+    assert (diff > 1e-6).float().mean().item() < 1e-3, (diff > 1e-6).float().mean().item()
     assert all(np.isfinite(runs["inline"][0]))
 
 
