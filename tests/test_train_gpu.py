@@ -505,8 +505,11 @@ def test_look_ahead_steps_equal_inline_steps(host_input):
         torch.cuda.synchronize()
         runs[mode] = (losses, norms, step.flat_param.detach().cpu().clone())
     # (not bit-identical: the embedding gradient is accumulated with fp32 atomics, whose order depends on what else runs)
-    assert np.allclose(runs["inline"][0], runs["look_ahead"][0], rtol=2e-6, atol=0), (runs["inline"][0], runs["look_ahead"][0])
-    assert np.allclose(runs["inline"][1], runs["look_ahead"][1], rtol=2e-5, atol=0)
+    # step 0 sees identical parameters: equal to rounding; later steps inherit the noise-level parameter differences below
+    # (a stale staging buffer or a missed dependency changes the loss in the first digits, or makes it NaN)
+    assert abs(runs["inline"][0][0] - runs["look_ahead"][0][0]) <= 2e-6 * abs(runs["inline"][0][0])
+    assert np.allclose(runs["inline"][0], runs["look_ahead"][0], rtol=2e-4, atol=0), (runs["inline"][0], runs["look_ahead"][0])
+    assert np.allclose(runs["inline"][1], runs["look_ahead"][1], rtol=2e-3, atol=0), (runs["inline"][1], runs["look_ahead"][1])
     # parameters: Adam divides by sqrt(v) + eps, so an element whose gradient is itself at the atomics' noise level (sums that
     # cancel to ~1e-9) may move by a fraction of the learning rate either way; everything else agrees to fp32 rounding
     diff = (runs["inline"][2] - runs["look_ahead"][2]).abs()
