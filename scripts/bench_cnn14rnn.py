@@ -120,6 +120,13 @@ for i in range(6):
     flops += 2.0 * H * W * 9 * (chans[i] * chans[i + 1] + chans[i + 1] * chans[i + 1]) if i else 2.0 * H * W * 9 * chans[1] * chans[1]
     if i < 5:
         H, W = H // 2, W // 2
+if getattr(args, "sed", False):
+    # the SED tagger's convolutions run on the same kernel and are inside conv_ms: CNN8 blocks 64-128-256-512, time pooled
+    # x4 only (hf_wrapper.py:1791-1859) = 33.1 GFLOP per clip
+    sH, sW, sch = 1001, 64, (1, 64, 128, 256, 512)
+    for i in range(4):
+        flops += 2.0 * sH * sW * 9 * (sch[i] * sch[i + 1] + sch[i + 1] * sch[i + 1])
+        sH, sW = (sH // 2, sW // 2) if i < 2 else (sH, sW // 2)
 conv_ms = sum(v for k, v in per.items() if k.startswith("conv3x3"))
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 bf16 = float(peaks.get("bf16_tflops", peaks.get("bf16_dense_tflops", 1593.5)))

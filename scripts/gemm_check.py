@@ -23,7 +23,10 @@ def run(M, N, K, gate=0, affine=True, act=1, resid=False, path=1, seed=0, check=
     Bv = torch.randn(N, generator=g).to(dev) if affine else None
     R = torch.randn(M, N, generator=g).to(dev) if resid else None
     st = _lib.current_stream()
-    if time_it:
+    if time_it:          # one untimed launch first: module load / attribute setup of a first launch is not kernel time
+        _lib.check(lib.ac_gemm(_lib.ptr(A), _lib.ptr(W), _lib.ptr(C), M, N, K, _lib.ptr(G), gate, _lib.ptr(S), _lib.ptr(Bv),
+                               _lib.ptr(R), act, path, st), "ac_gemm")
+        torch.cuda.synchronize()
         lib.ac_timing_enable(1)
     rc = lib.ac_gemm(_lib.ptr(A), _lib.ptr(W), _lib.ptr(C), M, N, K, _lib.ptr(G), gate, _lib.ptr(S), _lib.ptr(Bv),
                      _lib.ptr(R), act, path, st)
