@@ -173,9 +173,10 @@ class TrainStep:
         2. `encode`: the FROZEN CNN's forward pass of that batch (log-mel, Cnn14 with its train-mode dropouts) runs on a
            second stream.  It does not depend on the optimizer step in flight, and the trainable part of a step (bi-GRU,
            decoder, backward passes: ~250 latency-bound launches of a few CTAs each) leaves most of the chip idle, so the
-           tensor-core-bound encoder of batch i+1 fills it while step i runs.  The convolutions' persistent grid is capped
-           at `cnn_sms` CTAs (AC_TRAIN_CNN_SMS) so that the trainable chain always finds free SMs, and `step` runs that
-           chain on a high-priority stream."""
+           tensor-core-bound encoder of batch i+1 fills it while step i runs.  The two run on DISJOINT SM sets (CUDA green
+           contexts, `_make_look_ahead_streams`): `cnn_sms` SMs (AC_TRAIN_CNN_SMS, default 84) for the encoder, whose
+           convolutions size their persistent grid to that set, the other 64 for the trainable chain.  Results equal the
+           inline schedule's (only the order in which dropout seeds are drawn changes)."""
         dev = self.device
         m = self.model
         with torch.cuda.device(dev), torch.no_grad():
@@ -185,14 +186,16 @@ class TrainStep:
             if not batch["wav"].is_cuda:
                 if getattr(self, "_copy_stream", None) is None:
                     self._copy_stream = torch.cuda.Stream(device=dev)
-                    self._stage = [{"free": None, "wav": None, "cap": None}, {"free": None, "wav": None, "cap": None}]
+                    self._stage = [{"free": None, "enc": None, "wav": None, "cap": None},
+                                   {"free": None, "enc": None, "wav": None, "cap": None}]
                     self._stage_i = 0
                 k = self._stage_i
                 self._stage_i ^= 1
                 s = self._stage[k]
                 with torch.cuda.stream(self._copy_stream):
-                    if s["free"] is not None:
-                        self._copy_stream.wait_event(s["free"])
+                    for ev in (s["free"], s["enc"]):        # the step / the look-ahead encoder pass that last read this slot
+                        if ev is not None:
+                            self._copy_stream.wait_event(ev)
                     for name, dt in (("wav", torch.float32), ("cap", torch.int64)):
                         src = batch[name]
                         if s[name] is None or s[name].shape != src.shape:
@@ -219,6 +222,8 @@ class TrainStep:
                 finally:
                     cnn.sm_limit = 0
                 staged["_cnn_ready"] = done
+                if "_slot" in staged:
+                    self._stage[staged["_slot"]]["enc"] = done      # (prefetching more than one batch ahead stays safe)
         return staged
 
     def wait_look_ahead(self):

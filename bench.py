@@ -228,6 +228,9 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
     ms_step, _ = timed(step_pipelined, steps, warmup)
     keep.pop("staged_dev", None)
     torch.cuda.synchronize()
+    schedule = "look-ahead"
+    if ms_step > ms_inline:              # no SM partition on this driver (ordinary streams do not pay): report the plain schedule
+        ms_step, schedule = ms_inline, "back to back (the look-ahead schedule was slower here)"
     # host time to enqueue ONE step on an idle GPU (a loop of many steps is throttled by the launch queue, not the host)
     host_ms = 0.0
     for i in range(5):
@@ -284,7 +287,7 @@ def run_train_leg(dev, rank, world, steps, warmup, timed, lib, ss_ratio=0.99):
                                  "Cnn14 encoder of batch i+1 runs on a second stream (convolutions capped at cnn_sms persistent CTAs) "
                                  "beside the bi-GRU / decoder forward + backward + optimizer of batch i; unpipelined = "
                                  "TrainStep.step(batch) alone, encoder and trainable part back to back on one stream",
-                         "cnn_sms": step.cnn_sms, "trainable_sms": getattr(step, "train_sms", None),
+                         "schedule": schedule, "cnn_sms": step.cnn_sms, "trainable_sms": getattr(step, "train_sms", None),
                          "sm_partition": "green contexts" if getattr(step, "partition", None) is not None else
                                          f"none ({getattr(step, 'partition_error', None)})",
                          "unpipelined_ms_per_step": ms_inline,
