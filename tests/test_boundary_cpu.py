@@ -137,6 +137,12 @@ def test_cider_properties():
     exact = {k: [v[0]] for k, v in gts.items()}
     score, per = Cider().compute_score(gts, exact)
     assert Cider().method() == "CIDEr" and per.shape == (4,) and abs(score - per.mean()) < 1e-12
+    # known answer by hand: a 3-word candidate equal to one of its two references has cosine 1 for n = 1..3 and no 4-grams,
+    # so mean over n = 3/4, over the two references 3/8, x 10 = 3.75 (the other reference shares nothing with it)
+    kgts = {"p": ["a man speaks", "someone is talking"], "q": ["rain falls hard"], "r": ["birds sing loudly"]}
+    kres = {"p": ["a man speaks"], "q": ["rain falls hard"], "r": ["birds sing loudly"]}
+    _, kper = Cider().compute_score(kgts, kres)
+    assert abs(kper[0] - 3.75) < 1e-9 and abs(kper[1] - 7.5) < 1e-9, kper
     # a candidate equal to its only reference: cosine 1 for every n-gram order, no length penalty -> 10
     assert abs(per[3] - 10.0) < 1e-9
     # equal to one of two references: half of that reference's weight plus whatever the other shares (here nothing)
